@@ -1,0 +1,246 @@
+// cloud_core.cuh -- one ray of the Cloud compute pass (cloudRayMarch.comp:690-826), restructured for the GPU:
+//   * per-frame quantities (camera basis, light direction, cone kernel, wind drift, sky constants) are hoisted
+//     out of the ray (MarchConst / SkyConst);
+//   * the erosion term of the six light-cone samples re-uses the curl + high-frequency fetch of the march sample
+//     (cloudRayMarch.comp:665 passes the march sample's coordinates), so an in-cloud step costs 1 + 1 + 1 + 6
+//     filtered fetches instead of 1 + 2 + 6*(1+2);
+//   * radiance is grey, so one scalar is carried instead of a vec3.
+// None of this changes a rounding: the decision-carrying values (t sequence, jitter index, densities, accumulated
+// density) are bit-identical to oracle/meteoros_oracle.c.
+#pragma once
+
+#include "mt_params.h"
+
+struct RayCounters {
+    unsigned rays, marched, steps, incloud, cone, early;
+};
+
+// cloud_setup: the per-frame MarchConst (cloudRayMarch.comp:199-207, 585-624, 489-497).
+MT_DEVICE void cloud_frame_setup(const CamU& cam, const TimeU& tm, const MtTuning& tun, MarchConst& m)
+{
+    RayBasis b = ray_basis(cam);
+    m.basisRight = b.right;
+    m.basisUp = b.up;
+    m.basisLook = b.look;
+    m.eyePos = mk3(-cam.eye[0], -cam.eye[1], -cam.eye[2]);
+    m.earthCenter = mk3(m.eyePos.x, -MT_EARTH_RADIUS, m.eyePos.z);
+    f3 sun = mk3(tun.sun_location[0], tun.sun_location[1], tun.sun_location[2]);
+    f3 l = norm3(sun - m.eyePos);
+    m.lightDir = l;
+    float a0 = fabsf(l.x), a1 = fabsf(l.y), a2 = fabsf(l.z);
+    f3 mc;
+    if (a0 > a1 && a0 > a2) mc = mk3(a0, 0.0f, 0.0f);
+    else if (a1 > a0 && a1 > a2) mc = mk3(0.0f, a1, 0.0f);
+    else mc = mk3(0.0f, 0.0f, a2);
+    f3 zc = cross3(l, mc);
+    f3 xc = cross3(zc, l);
+    const float K[6][3] = { { 0.1f, 0.25f, -0.15f }, { 0.2f, 0.5f, 0.2f },  { -0.2f, 0.1f, -0.1f },
+                            { -0.05f, 0.75f, 0.05f }, { -0.1f, 1.0f, 0.0f }, { 0.0f, 3.0f, 0.0f } };
+    for (int i = 0; i < 6; ++i) m.coneStep[i] = (xc * K[i][0] + l * K[i][1]) + zc * K[i][2];
+    f3 wind = mk3(tun.wind_direction[0], tun.wind_direction[1], tun.wind_direction[2]);
+    m.windSkew = ((wind + mk3(0.0f, 0.1f, 0.0f)) * tun.cloud_speed) * tm.time[1];
+}
+
+MT_DEVICE float hg_phase(float cosa, float g)
+{
+    float num = 1.0f - g * g;
+    float den = MT_POWF((1.0f + g * g) - (2.0f * g) * cosa, 1.5f);
+    return (num / den) * 0.07957747154594767f;
+}
+
+// getAtmosphereColorPhysical (cloudRayMarch.comp:427-467) with the ray-independent part in SkyConst.
+MT_DEVICE f3 sky_color(const SkyConst& S, f3 dir)
+{
+    const float PI_F = 3.14159265f;
+    float zenith = acosf(fmaxf(0.0f, dir.y));
+    float inverse = 1.0f / (cosf(zenith) + 0.15f * MT_POWF(93.885f - ((zenith * 180.0f) / PI_F), -1.253f));
+    float sR = 8.4E3f * inverse;
+    float sM = 1.25E3f * inverse;
+    float fex[3], col[3];
+    f3 sunDir = mk3(S.sunDir[0], S.sunDir[1], S.sunDir[2]);
+    float cosTheta = dot3(sunDir, dir);
+    float rc = cosTheta * 0.5f + 0.5f;
+    float rPhase = 0.05968310365946075f * (1.0f + rc * rc);
+    float mPhase = hg_phase(cosTheta, 0.8f);
+    const float SUN_ANGULAR_COS = 0.999956676946448443553574619906976478926848692873900859324f;
+    float sunDisk = smoothstep1(SUN_ANGULAR_COS, SUN_ANGULAR_COS + 0.00002f, cosTheta);
+    const float add[3] = { 0.0f, 0.0003f, 0.00075f };
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        fex[c] = MT_EXPF((-S.betaR[c]) * sR + S.betaM[c] * sM);
+        float betas = (S.betaR[c] * rPhase + S.betaM[c] * mPhase) / (S.betaR[c] + S.betaM[c]);
+        float lin = MT_POWF((S.sunE * betas) * (1.0f - fex[c]), 1.5f);
+        lin *= mix1(1.0f, MT_POWF((S.sunE * betas) * fex[c], 0.5f), S.yDotMix);
+        float l0 = 0.1f * fex[c];
+        l0 += ((S.sunE * 15000.0f) * fex[c]) * sunDisk;
+        col[c] = (lin + l0) * 0.04f + add[c];
+    }
+    return mk3(col[0], col[1], col[2]);
+}
+
+// sampleLowFrequency (cloudRayMarch.comp:499-540): base cloud density with coverage applied.
+MT_DEVICE float low_freq_density(const Tex3D& low, float coverage, f3 p)
+{
+    Rgba n = tex3d_rgba(low, p.x, p.y, p.z);
+    float fbm = sat1((n.g * 0.625f + n.b * 0.25f) + n.a * 0.125f);
+    float omin = fbm - 0.9f;
+    float base = sat1((n.r - omin) / (1.0f - omin));  // remapClamped(r, fbm-.9, 1, 0, 1)
+    float v = clamp1(base, coverage, 1.0f);           // remapClampedBeforeAndAfter(base, cov, 1, 0, 1)
+    float b = sat1((v - coverage) / (1.0f - coverage));
+    return b * coverage;
+}
+
+// The part of erodeCloudWithHighFrequency (cloudRayMarch.comp:542-563) that depends only on the march sample:
+// returns high_freq_modifier * 0.005, the lower edge of the final remap.
+MT_DEVICE float erosion_edge(const Tex2D& curl, const Tex3D& high, f3 p, float h)
+{
+    float cr, cg;
+    tex2d_rg(curl, p.x, p.y, cr, cg);
+    float px = p.x + (cr * (1.0f - h)) * 0.5f;
+    float py = p.y + (cg * (1.0f - h)) * 0.5f;
+    Rgba n = tex3d_rgb(high, px, py, p.z);
+    float fbm = (n.r * 0.625f + n.g * 0.25f) + n.b * 0.125f;
+    float m = sat1(mix1(fbm, 1.0f - fbm, sat1(h * 2.0f)));
+    return m * 0.005f;
+}
+MT_DEVICE float erode(float base, float edge) { return (base - edge) / (1.0f - edge); }  // remap(base, edge, 1, 0, 1)
+
+// GetLightEnergy (cloudRayMarch.comp:331-388), live branch only.
+MT_DEVICE float light_energy(float h, float dl, float ds, float phase, float cosa)
+{
+    float p = MT_EXPF(-dl);
+    float att = fmaxf(remap1(cosa, 0.7f, 1.0f, p, p * 0.25f), p);
+    float depth = 0.05f + MT_POWF(ds, clamp1(remap1(h * 0.125f, 0.3f, 0.85f, 0.5f, 2.0f), 0.5f, 2.0f));
+    float vert = MT_POWF(clamp1(remap1(h * 1.5f, 0.07f, 0.34f, 0.1f, 1.0f), 0.1f, 1.0f), 0.8f);
+    return (((att * p) * (depth * vert)) * phase) * 5.0f;
+}
+
+MT_DEVICE void encode_mask(float v, F4& o)
+{
+    float e0 = v, e1 = 255.0f * v, e2 = 65025.0f * v, e3 = 16581375.0f * v;
+    e0 = e0 - floorf(e0); e1 = e1 - floorf(e1); e2 = e2 - floorf(e2); e3 = e3 - floorf(e3);
+    const float k = 1.0f / 255.0f;
+    o.x = e0 - e1 * k; o.y = e1 - e2 * k; o.z = e2 - e3 * k; o.w = e3 - e3 * 0.0f;
+}
+
+#define MT_MAX_MARCH_ITERS 128  /* maxSteps <= 60; guards degenerate shells (also in the oracle) */
+
+// One invocation of main().  Returns false when the reference would not have written this pixel.
+template <bool COUNT, bool DEBUG>
+MT_DEVICE void cloud_ray(const CloudParams& P, const MarchConst& M, int px, int py, int pixelID, F4& hdr, F4& mask,
+                         RayCounters& cnt, MtRayDebug* dbg)
+{
+    // ---- castRay (:194-226) ----
+    float u = (float)px / (float)P.W;
+    float v = 1.0f - (float)py / (float)P.H;
+    int hj = pixelID >> 1;  // getJitterOffset: halton[hj] / halton[4 + hj] for hj < 4, else [8 + hj-4] / [12 + hj-4]
+    int hx = hj < 4 ? hj : hj + 4;
+    float jx = P.tm.halton[hx] / (float)P.W;
+    float jy = P.tm.halton[hx + 4] / (float)P.H;
+    RayBasis B;
+    B.right = M.basisRight; B.up = M.basisUp; B.look = M.basisLook;
+    const f3 origin = M.eyePos;
+    const f3 dir = cast_ray_dir(P.cam, B, origin, u, v, jx, jy);
+    if (COUNT) cnt.rays++;
+    if (DEBUG) {
+        dbg->dir[0] = dir.x; dbg->dir[1] = dir.y; dbg->dir[2] = dir.z;
+        dbg->t_in = dbg->t_out = dbg->step_size = dbg->accum = 0.0f;
+        dbg->branch = 0; dbg->steps = 0; dbg->jitter_hash = 0u;
+    }
+
+    const float dotUp = (0.0f * dir.x + 1.0f * dir.y) + 0.0f * dir.z;
+    mask.x = mask.y = mask.z = mask.w = 0.0f;
+    hdr.w = 1.0f;
+    if (dotUp < 0.0f) {  // ocean (:718-729)
+        float a = -dir.y * 5.5f;
+        hdr.x = mix1(0.0f * 0.4f, 0.0f * 0.5f, a);
+        hdr.y = mix1(0.16f * 0.4f, 0.73f * 0.5f, a);
+        hdr.z = mix1(0.51f * 0.4f, 0.95f * 0.5f, a);
+        return;
+    }
+    f3 bg = sky_color(P.sky, dir) * fmaxf(0.620f, dotUp);
+    if (dotUp < 0.06f) {  // sky band below the cloud fade-out (:730-740)
+        hdr.x = bg.x; hdr.y = bg.y; hdr.z = bg.z;
+        if (DEBUG) dbg->branch = 1;
+        return;
+    }
+
+    // ---- shells (:750-753) ----
+    const f3 ec = M.earthCenter;
+    ShellHit hin = ray_shell(origin, dir, ec, MT_R_INNER);
+    ShellHit hout = ray_shell(origin, dir, ec, MT_R_OUTER);
+
+    // ---- rayMarch (:565-688) ----
+    const float maxSteps = floorf(mix1(35.0f, 60.0f, 1.0f - dotUp));
+    const float stepSize = (hout.t - hin.t) / maxSteps;
+    const float cosAngle = dot3(norm3(dir), M.lightDir);
+    const float phase = fmaxf(hg_phase(cosAngle, 0.6f), 0.7f * hg_phase(cosAngle, 0.99f - 0.1f));
+    const float lenToInner = len3(hin.point - origin);
+    const f3 relOrigin = mk3(ec.x, MT_R_INNER - MT_EARTH_RADIUS, ec.z);
+    const f3 wind = mk3(P.tun.wind_direction[0], P.tun.wind_direction[1], P.tun.wind_direction[2]);
+    const float coverage = P.tun.coverage;
+
+    float accum = 0.0f, transmittance = 1.0f, color = 0.0f;
+    unsigned jhash = 2166136261u;
+    int iters = 0;
+    if (COUNT) cnt.marched++;
+    if (DEBUG) { dbg->branch = 2; dbg->t_in = hin.t; dbg->t_out = hout.t; dbg->step_size = stepSize; }
+
+    for (float t = hin.t; t < hout.t && iters < MT_MAX_MARCH_ITERS; t += stepSize, ++iters) {
+        int jidx = (pixelID + mt_f2i(t)) & 15;  // int(mod(float(pixelID + int(t)), 16.0)), argument >= 0
+        int hs = jidx >> 1;
+        int hi = hs < 4 ? hs : hs + 4;
+        float sx = P.tm.halton[hi] / 75.0f, sy = P.tm.halton[hi + 4] / 75.0f;
+        f3 jdir = dir + mk3(sx, (sx + sy) * 1.180f, sy);
+        f3 pos = origin + jdir * t;
+        f3 sp = ((pos - relOrigin) / MT_THICKNESS) / 8.0f;
+        // getRelativeHeightInAtmosphere (:171-186)
+        float lenFromCam = len3(pos - origin);
+        float cosTheta = dot3(dir, norm3(pos - ec));
+        float h = fabsf(cosTheta * (lenFromCam - lenToInner)) / MT_THICKNESS;
+        // skewSamplePointWithWind (:489-497)
+        f3 skew = (sp + ((wind * h) * P.tun.cloud_top_offset) * 0.009f) + M.windSkew;
+        float baseDensity = low_freq_density(P.low, coverage, skew) * P.tun.base_density_factor;
+        if (COUNT) cnt.steps++;
+        if (DEBUG) jhash = (jhash ^ (unsigned)jidx) * 16777619u;
+
+        if (baseDensity > 0.0f) {
+            if (COUNT) cnt.incloud++;
+            float edge = erosion_edge(P.curl, P.high, skew, h);
+            accum += erode(baseDensity * 1.4f, edge) * 0.5f;
+            float dl = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                f3 lp = pos + (M.coneStep[i] * stepSize) * (float)i;
+                f3 sl = (lp - relOrigin) / MT_THICKNESS;
+                float cur = low_freq_density(P.low, coverage, sl);
+                if (cur > 0.0f) {
+                    if (COUNT) cnt.cone++;
+                    dl += erode(1.5f * cur, edge);
+                }
+            }
+            float E = light_energy(h, dl, baseDensity, phase, cosAngle);
+            transmittance = mix1(transmittance, E, 1.0f - accum);
+            color += transmittance;
+        }
+        if (accum >= 1.0f) {
+            accum = 1.0f;
+            if (COUNT) cnt.early++;
+            ++iters;
+            break;
+        }
+    }
+    if (DEBUG) { dbg->steps = iters; dbg->jitter_hash = jhash; dbg->accum = accum; }
+
+    // ---- composite (:759-779) ----
+    float fade = smoothstep1(0.0f, 1.0f, fminf(1.0f, remap1(dir.y, 0.06f, 0.2f, 0.0f, 1.0f)));
+    float a = accum * fade;
+    hdr.x = mix1(bg.x, color, a);
+    hdr.y = mix1(bg.y, color, a);
+    hdr.z = mix1(bg.z, color, a);
+    encode_mask(25.0f * fminf(0.05f, 1.0f - accum), mask);
+    if (dir.y < 0.05f) {  // unreachable here (dir.y >= 0.06) but part of the shader (:775-779)
+        float k = fmaxf(5.0f, dir.y);
+        mask.x *= k; mask.y *= k; mask.z *= k; mask.w *= k;
+    }
+}

@@ -1,0 +1,654 @@
+// mt_context.cu -- host side of the C ABI (include/meteoros_b200.h): the part of Meteoros' Renderer that a CUDA
+// replacement substitutes -- resource creation (Renderer.cpp:1428-1447), uniform / texture binding
+// (Renderer.cpp:914-1165), the per-frame dispatch order and ping-pong (Renderer.cpp:122-192, 653-722, 823-846).
+// One context = one device + one stream; calls execute in order on that stream.  No CPU fallback exists: every
+// dispatch either launches the sm_100a kernels or returns an error.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "mt_host_consts.h"
+#include "mt_launch.h"
+
+#define MT_FLAG_PASS_TIMING_INTERNAL MT_FLAG_PASS_TIMING
+#define MT_USER_EVENTS 16
+
+struct MtContext {
+    int device = 0;
+    int W = 0, H = 0;
+    uint32_t storage = MT_STORAGE_F32;
+    uint32_t flags = 0;
+    cudaStream_t stream = nullptr;
+    F4* hdr[2] = { nullptr, nullptr };
+    int cur = 0;  // index of the image that currently plays "currentFrameResultImage"
+    F4* mask = nullptr;
+    uint32_t* ldr = nullptr;
+    uint32_t* tex[4] = { nullptr, nullptr, nullptr, nullptr };
+    int texw[4] = { 0, 0, 0, 0 }, texh[4] = { 0, 0, 0, 0 }, texd[4] = { 0, 0, 0, 0 };
+    MarchConst* mc = nullptr;
+    unsigned long long* counters = nullptr;
+    MtRayDebug* debug = nullptr;  // lazily allocated W*H records
+    int* taps = nullptr;          // lazily allocated W*H*10
+    MtCameraUBO cam, camOld;
+    MtTimeUBO tm;
+    MtSunAndSkyUBO sky;
+    MtTuning tun;
+    int32_t key = 0;
+    bool haveCam = false, haveCamOld = false, haveTime = false;
+    F4* outHdr = nullptr;  // mtSetCloudOutput overrides
+    F4* outMask = nullptr;
+    cudaEvent_t ev[MT_PASS_COUNT][2] = {};
+    bool evValid[MT_PASS_COUNT] = { false, false, false, false };
+    cudaEvent_t userEv[MT_USER_EVENTS] = {};
+    bool userEvValid[MT_USER_EVENTS] = {};
+    uint64_t launches = 0;
+    std::string err;
+};
+
+static MtStatus fail(MtContext* c, MtStatus s, const std::string& msg)
+{
+    if (c) c->err = msg;
+    return s;
+}
+static MtStatus cuda_fail(MtContext* c, cudaError_t e, const char* what)
+{
+    if (e == cudaErrorMemoryAllocation) return fail(c, MT_ERR_OOM, std::string(what) + ": " + cudaGetErrorString(e));
+    return fail(c, MT_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define MT_CUDA(c, call)                                    \
+    do {                                                    \
+        cudaError_t e__ = (call);                           \
+        if (e__ != cudaSuccess) return cuda_fail((c), e__, #call); \
+    } while (0)
+#define MT_REQUIRE(c, cond, msg)                            \
+    do {                                                    \
+        if (!(cond)) return fail((c), MT_ERR_INVALID, (msg)); \
+    } while (0)
+
+static size_t image_bytes(const MtContext* c, MtImage w)
+{
+    size_t px = (size_t)c->W * (size_t)c->H;
+    return w == MT_IMAGE_LDR ? px * 4 : px * 16;
+}
+static void* image_ptr(MtContext* c, MtImage w)
+{
+    switch (w) {
+        case MT_IMAGE_CLOUD_CUR: return c->hdr[c->cur];
+        case MT_IMAGE_CLOUD_PREV: return c->hdr[c->cur ^ 1];
+        case MT_IMAGE_GODRAY_MASK: return c->mask;
+        case MT_IMAGE_LDR: return c->ldr;
+    }
+    return nullptr;
+}
+static bool is_pow2(uint32_t v) { return v && !(v & (v - 1)); }
+
+static void free_images(MtContext* c)
+{
+    cudaFree(c->hdr[0]); cudaFree(c->hdr[1]); cudaFree(c->mask); cudaFree(c->ldr);
+    cudaFree(c->debug); cudaFree(c->taps);
+    c->hdr[0] = c->hdr[1] = c->mask = nullptr;
+    c->ldr = nullptr; c->debug = nullptr; c->taps = nullptr;
+}
+static MtStatus alloc_images(MtContext* c)
+{
+    size_t px = (size_t)c->W * (size_t)c->H;
+    MT_CUDA(c, cudaMalloc((void**)&c->hdr[0], px * 16));
+    MT_CUDA(c, cudaMalloc((void**)&c->hdr[1], px * 16));
+    MT_CUDA(c, cudaMalloc((void**)&c->mask, px * 16));
+    MT_CUDA(c, cudaMalloc((void**)&c->ldr, px * 4));
+    MT_CUDA(c, cudaMemsetAsync(c->hdr[0], 0, px * 16, c->stream));
+    MT_CUDA(c, cudaMemsetAsync(c->hdr[1], 0, px * 16, c->stream));
+    MT_CUDA(c, cudaMemsetAsync(c->mask, 0, px * 16, c->stream));
+    MT_CUDA(c, cudaMemsetAsync(c->ldr, 0, px * 4, c->stream));
+    c->cur = 0;
+    return MT_OK;
+}
+
+extern "C" {
+
+uint32_t mtAbiVersion(void) { return MT_ABI_VERSION; }
+
+const char* mtStatusString(MtStatus s)
+{
+    switch (s) {
+        case MT_OK: return "MT_OK";
+        case MT_ERR_INVALID: return "MT_ERR_INVALID";
+        case MT_ERR_CUDA: return "MT_ERR_CUDA";
+        case MT_ERR_OOM: return "MT_ERR_OOM";
+        case MT_ERR_UNSUPPORTED_ARCH: return "MT_ERR_UNSUPPORTED_ARCH";
+        case MT_ERR_NOT_READY: return "MT_ERR_NOT_READY";
+    }
+    return "MT_ERR_UNKNOWN";
+}
+
+void mtDefaultTuning(MtTuning* t)
+{
+    if (!t) return;
+    t->coverage = 0.6f;
+    t->sun_location[0] = 0.0f;
+    t->sun_location[1] = MT_R_OUTER * 0.9f;
+    t->sun_location[2] = -MT_R_OUTER * 0.9f;
+    t->sky_sun_location[0] = 0.0f;
+    t->sky_sun_location[1] = MT_EARTH_RADIUS * 2.0f;
+    t->sky_sun_location[2] = -MT_EARTH_RADIUS * 10.0f;
+    t->wind_direction[0] = 1.0f; t->wind_direction[1] = 0.0f; t->wind_direction[2] = 0.0f;
+    t->cloud_speed = 0.080f;
+    t->cloud_top_offset = 1.0f;
+    t->base_density_factor = 0.380f;
+}
+
+MtStatus mtCreate(const MtConfig* cfg, MtContext** out)
+{
+    if (!cfg || !out) return MT_ERR_INVALID;
+    *out = nullptr;
+    if (cfg->struct_size != sizeof(MtConfig) || cfg->width == 0 || cfg->height == 0 || cfg->width > 32768 ||
+        cfg->height > 32768 || cfg->storage > MT_STORAGE_F16_EMULATE)
+        return MT_ERR_INVALID;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || cfg->device < 0 || cfg->device >= ndev) return MT_ERR_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return MT_ERR_CUDA;
+    if (prop.major != 10) return MT_ERR_UNSUPPORTED_ARCH;  // the kernels exist as sm_100a SASS only
+    MtContext* c = new (std::nothrow) MtContext();
+    if (!c) return MT_ERR_OOM;
+    c->device = cfg->device;
+    c->W = (int)cfg->width;
+    c->H = (int)cfg->height;
+    c->storage = cfg->storage;
+    c->flags = cfg->flags;
+    memset(&c->cam, 0, sizeof(c->cam)); memset(&c->camOld, 0, sizeof(c->camOld));
+    memset(&c->tm, 0, sizeof(c->tm)); memset(&c->sky, 0, sizeof(c->sky));
+    mtDefaultTuning(&c->tun);
+    MtStatus st = MT_OK;
+    do {
+        if (cudaSetDevice(c->device) != cudaSuccess) { st = MT_ERR_CUDA; break; }
+        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { st = MT_ERR_CUDA; break; }
+        for (int p = 0; p < MT_PASS_COUNT; ++p) {
+            if (cudaEventCreate(&c->ev[p][0]) != cudaSuccess || cudaEventCreate(&c->ev[p][1]) != cudaSuccess) st = MT_ERR_CUDA;
+        }
+        if (st != MT_OK) break;
+        if ((st = alloc_images(c)) != MT_OK) break;
+        if (cudaMalloc((void**)&c->mc, sizeof(MarchConst)) != cudaSuccess) { st = MT_ERR_OOM; break; }
+        if (cudaMalloc((void**)&c->counters, 8 * sizeof(unsigned long long)) != cudaSuccess) { st = MT_ERR_OOM; break; }
+        if (cudaMemsetAsync(c->counters, 0, 8 * sizeof(unsigned long long), c->stream) != cudaSuccess) { st = MT_ERR_CUDA; break; }
+    } while (0);
+    if (st != MT_OK) {
+        mtDestroy(c);
+        return st;
+    }
+    *out = c;
+    return MT_OK;
+}
+
+void mtDestroy(MtContext* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    free_images(c);
+    for (int i = 0; i < 4; ++i) cudaFree(c->tex[i]);
+    cudaFree(c->mc);
+    cudaFree(c->counters);
+    for (int p = 0; p < MT_PASS_COUNT; ++p) {
+        if (c->ev[p][0]) cudaEventDestroy(c->ev[p][0]);
+        if (c->ev[p][1]) cudaEventDestroy(c->ev[p][1]);
+    }
+    for (int i = 0; i < MT_USER_EVENTS; ++i)
+        if (c->userEv[i]) cudaEventDestroy(c->userEv[i]);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char* mtGetLastError(const MtContext* c) { return c ? c->err.c_str() : "null context"; }
+
+MtStatus mtResize(MtContext* c, uint32_t w, uint32_t h)
+{
+    if (!c) return MT_ERR_INVALID;
+    MT_REQUIRE(c, w > 0 && h > 0 && w <= 32768 && h <= 32768, "mtResize: bad size");
+    MT_CUDA(c, cudaSetDevice(c->device));
+    MT_CUDA(c, cudaStreamSynchronize(c->stream));
+    free_images(c);
+    c->W = (int)w;
+    c->H = (int)h;
+    c->outHdr = c->outMask = nullptr;
+    return alloc_images(c);
+}
+
+MtStatus mtSetCamera(MtContext* c, const MtCameraUBO* u)
+{
+    if (!c) return MT_ERR_INVALID;
+    MT_REQUIRE(c, u != nullptr, "mtSetCamera: null ubo");
+    c->cam = *u;
+    c->haveCam = true;
+    return MT_OK;
+}
+MtStatus mtSetCameraOld(MtContext* c, const MtCameraUBO* u)
+{
+    if (!c) return MT_ERR_INVALID;
+    MT_REQUIRE(c, u != nullptr, "mtSetCameraOld: null ubo");
+    c->camOld = *u;
+    c->haveCamOld = true;
+    return MT_OK;
+}
+MtStatus mtSetTime(MtContext* c, const MtTimeUBO* u)
+{
+    if (!c) return MT_ERR_INVALID;
+    MT_REQUIRE(c, u != nullptr, "mtSetTime: null ubo");
+    MT_REQUIRE(c, u->frameCountMod16 >= 0 && u->frameCountMod16 < 16, "mtSetTime: frameCountMod16 outside 0..15");
+    c->tm = *u;
+    c->haveTime = true;
+    return MT_OK;
+}
+MtStatus mtSetSunAndSky(MtContext* c, const MtSunAndSkyUBO* u)
+{
+    if (!c) return MT_ERR_INVALID;
+    MT_REQUIRE(c, u != nullptr, "mtSetSunAndSky: null ubo");
+    c->sky = *u;
+    return MT_OK;
+}
+MtStatus mtSetKeyPressQuery(MtContext* c, int32_t k)
+{
+    if (!c) return MT_ERR_INVALID;
+    c->key = k;  // bound at set 5 of the cloud pipeline, never read by the shader (Renderer.cpp:706)
+    return MT_OK;
+}
+MtStatus mtSetTuning(MtContext* c, const MtTuning* t)
+{
+    if (!c) return MT_ERR_INVALID;
+    MT_REQUIRE(c, t != nullptr, "mtSetTuning: null tuning");
+    MT_REQUIRE(c, t->coverage >= 0.0f && t->coverage < 1.0f, "mtSetTuning: coverage must be in [0, 1)");
+    c->tun = *t;
+    return MT_OK;
+}
+
+static MtStatus upload(MtContext* c, int slot, uint32_t w, uint32_t h, uint32_t d, const uint8_t* rgba8)
+{
+    MT_REQUIRE(c, rgba8 != nullptr, "texture upload: null data");
+    MT_REQUIRE(c, is_pow2(w) && is_pow2(h) && is_pow2(d) && w <= 2048 && h <= 2048 && d <= 2048,
+               "texture upload: extents must be powers of two <= 2048 (reference: 128^3, 32^3, 128^2, 512^2)");
+    MT_CUDA(c, cudaSetDevice(c->device));
+    size_t bytes = (size_t)w * h * d * 4;
+    if (c->tex[slot]) {
+        MT_CUDA(c, cudaStreamSynchronize(c->stream));
+        cudaFree(c->tex[slot]);
+        c->tex[slot] = nullptr;
+    }
+    MT_CUDA(c, cudaMalloc((void**)&c->tex[slot], bytes));
+    MT_CUDA(c, cudaMemcpyAsync(c->tex[slot], rgba8, bytes, cudaMemcpyHostToDevice, c->stream));
+    MT_CUDA(c, cudaStreamSynchronize(c->stream));  // the caller may free its buffer on return
+    c->texw[slot] = (int)w; c->texh[slot] = (int)h; c->texd[slot] = (int)d;
+    return MT_OK;
+}
+MtStatus mtUploadTexture3D(MtContext* c, MtTextureSlot slot, uint32_t w, uint32_t h, uint32_t d, const uint8_t* rgba8)
+{
+    if (!c) return MT_ERR_INVALID;
+    MT_REQUIRE(c, slot == MT_TEX_LOW_FREQ || slot == MT_TEX_HIGH_FREQ, "mtUploadTexture3D: slot is not a 3D texture");
+    return upload(c, (int)slot, w, h, d, rgba8);
+}
+MtStatus mtUploadTexture2D(MtContext* c, MtTextureSlot slot, uint32_t w, uint32_t h, const uint8_t* rgba8)
+{
+    if (!c) return MT_ERR_INVALID;
+    MT_REQUIRE(c, slot == MT_TEX_CURL || slot == MT_TEX_WEATHER, "mtUploadTexture2D: slot is not a 2D texture");
+    return upload(c, (int)slot, w, h, 1, rgba8);
+}
+
+// ---- dispatch helpers ---------------------------------------------------------------------------------------------
+static void copy_cam(CamU& d, const MtCameraUBO& s)
+{
+    static_assert(sizeof(CamU) == sizeof(MtCameraUBO), "CamU layout");
+    memcpy(&d, &s, sizeof(CamU));
+}
+static void copy_time(TimeU& d, const MtTimeUBO& s)
+{
+    static_assert(sizeof(TimeU) == sizeof(MtTimeUBO), "TimeU layout");
+    memcpy(&d, &s, sizeof(TimeU));
+}
+static void pass_begin(MtContext* c, MtPass p)
+{
+    if (c->flags & MT_FLAG_PASS_TIMING_INTERNAL) cudaEventRecord(c->ev[p][0], c->stream);
+}
+static void pass_end(MtContext* c, MtPass p)
+{
+    if (c->flags & MT_FLAG_PASS_TIMING_INTERNAL) {
+        cudaEventRecord(c->ev[p][1], c->stream);
+        c->evValid[p] = true;
+    }
+}
+static int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+static MtStatus cloud_dispatch(MtContext* c, int full, const RowTiles* tiles, bool debug)
+{
+    if (!c->haveCam || !c->haveTime) return fail(c, MT_ERR_NOT_READY, "cloud dispatch: camera / time uniforms not set");
+    if (!c->tex[MT_TEX_LOW_FREQ] || !c->tex[MT_TEX_HIGH_FREQ] || !c->tex[MT_TEX_CURL])
+        return fail(c, MT_ERR_NOT_READY, "cloud dispatch: low-frequency, high-frequency and curl textures must be uploaded");
+    MT_CUDA(c, cudaSetDevice(c->device));
+    CloudParams P;
+    memset(&P, 0, sizeof(P));
+    copy_cam(P.cam, c->cam);
+    copy_time(P.tm, c->tm);
+    P.tun = c->tun;
+    mt_host_sky_const(c->cam, c->tun, P.sky);
+    P.low.texels = c->tex[MT_TEX_LOW_FREQ];
+    P.low.w = c->texw[MT_TEX_LOW_FREQ]; P.low.h = c->texh[MT_TEX_LOW_FREQ]; P.low.d = c->texd[MT_TEX_LOW_FREQ];
+    P.high.texels = c->tex[MT_TEX_HIGH_FREQ];
+    P.high.w = c->texw[MT_TEX_HIGH_FREQ]; P.high.h = c->texh[MT_TEX_HIGH_FREQ]; P.high.d = c->texd[MT_TEX_HIGH_FREQ];
+    P.curl.texels = c->tex[MT_TEX_CURL];
+    P.curl.w = c->texw[MT_TEX_CURL]; P.curl.h = c->texh[MT_TEX_CURL];
+    P.mc = c->mc;
+    P.hdr = c->outHdr ? c->outHdr : c->hdr[c->cur];
+    P.mask = c->outMask ? c->outMask : c->mask;
+    P.W = c->W; P.H = c->H;
+    P.tx = (((c->W / 4) + 31) / 32) * 32;  // Renderer.cpp:713-714
+    P.ty = (((c->H / 4) + 31) / 32) * 32;
+    P.full = full;
+    P.f16_emulate = c->storage == MT_STORAGE_F16_EMULATE;
+    if (tiles) P.rows = *tiles;
+    else {
+        P.rows.tile_rows = round_up(full ? c->H : P.ty, 8);
+        P.rows.tile_begin = 0; P.rows.tile_stride = 1; P.rows.tile_count = 1;
+    }
+    P.counters = (debug || (c->flags & MT_FLAG_COUNTERS)) ? c->counters : nullptr;
+    P.debug = nullptr;
+    if (debug) {
+        if (!c->debug) MT_CUDA(c, cudaMalloc((void**)&c->debug, (size_t)c->W * c->H * sizeof(MtRayDebug)));
+        MT_CUDA(c, cudaMemsetAsync(c->debug, 0, (size_t)c->W * c->H * sizeof(MtRayDebug), c->stream));
+        P.debug = c->debug;
+    }
+    MT_CUDA(c, mt_launch_cloud_setup(P, c->mc, c->stream));
+    pass_begin(c, MT_PASS_CLOUD);
+    MT_CUDA(c, mt_launch_cloud(P, c->stream));
+    pass_end(c, MT_PASS_CLOUD);
+    c->launches += 2;
+    return MT_OK;
+}
+
+MtStatus mtDispatchCloud(MtContext* c)
+{
+    if (!c) return MT_ERR_INVALID;
+    return cloud_dispatch(c, 0, nullptr, false);
+}
+MtStatus mtDispatchCloudFull(MtContext* c)
+{
+    if (!c) return MT_ERR_INVALID;
+    return cloud_dispatch(c, 1, nullptr, false);
+}
+MtStatus mtDispatchCloudTiles(MtContext* c, uint32_t tile_rows, uint32_t tile_begin, uint32_t tile_end, uint32_t tile_stride)
+{
+    if (!c) return MT_ERR_INVALID;
+    MT_REQUIRE(c, tile_rows >= 8 && tile_rows % 8 == 0, "mtDispatchCloudTiles: tile_rows must be a positive multiple of 8");
+    MT_REQUIRE(c, tile_stride >= 1, "mtDispatchCloudTiles: tile_stride must be >= 1");
+    uint32_t ntiles = ((uint32_t)c->H + tile_rows - 1) / tile_rows;
+    if (tile_end > ntiles) tile_end = ntiles;
+    RowTiles t;
+    t.tile_rows = (int)tile_rows;
+    t.tile_begin = (int)tile_begin;
+    t.tile_stride = (int)tile_stride;
+    t.tile_count = tile_begin < tile_end ? (int)((tile_end - tile_begin + tile_stride - 1) / tile_stride) : 0;
+    if (t.tile_count == 0) return MT_OK;
+    return cloud_dispatch(c, 1, &t, false);
+}
+MtStatus mtDispatchCloudDebug(MtContext* c, int full, MtRayDebug* out, size_t out_bytes)
+{
+    if (!c) return MT_ERR_INVALID;
+    size_t need = (size_t)c->W * c->H * sizeof(MtRayDebug);
+    MT_REQUIRE(c, out != nullptr && out_bytes >= need, "mtDispatchCloudDebug: output buffer too small");
+    MtStatus st = cloud_dispatch(c, full ? 1 : 0, nullptr, true);
+    if (st != MT_OK) return st;
+    MT_CUDA(c, cudaMemcpyAsync(out, c->debug, need, cudaMemcpyDeviceToHost, c->stream));
+    MT_CUDA(c, cudaStreamSynchronize(c->stream));
+    return MT_OK;
+}
+
+static MtStatus reproject_dispatch(MtContext* c, bool debug)
+{
+    if (!c->haveCam || !c->haveCamOld || !c->haveTime)
+        return fail(c, MT_ERR_NOT_READY, "reprojection dispatch: camera, cameraOld and time uniforms must be set");
+    MT_CUDA(c, cudaSetDevice(c->device));
+    ReprojParams P;
+    memset(&P, 0, sizeof(P));
+    copy_cam(P.cam, c->cam);
+    copy_cam(P.camOld, c->camOld);
+    copy_time(P.tm, c->tm);
+    P.prev = c->hdr[c->cur ^ 1];
+    P.cur = c->hdr[c->cur];
+    P.W = c->W; P.H = c->H;
+    P.f16_emulate = c->storage == MT_STORAGE_F16_EMULATE;
+    P.taps = nullptr;
+    if (debug) {
+        if (!c->taps) MT_CUDA(c, cudaMalloc((void**)&c->taps, (size_t)c->W * c->H * 10 * sizeof(int)));
+        P.taps = c->taps;
+    }
+    pass_begin(c, MT_PASS_REPROJECT);
+    MT_CUDA(c, mt_launch_reproject(P, c->stream));
+    pass_end(c, MT_PASS_REPROJECT);
+    c->launches += 1;
+    return MT_OK;
+}
+MtStatus mtDispatchReprojection(MtContext* c)
+{
+    if (!c) return MT_ERR_INVALID;
+    return reproject_dispatch(c, false);
+}
+MtStatus mtDispatchReprojectionDebug(MtContext* c, int32_t* taps, size_t taps_bytes)
+{
+    if (!c) return MT_ERR_INVALID;
+    size_t need = (size_t)c->W * c->H * 10 * sizeof(int32_t);
+    MT_REQUIRE(c, taps != nullptr && taps_bytes >= need, "mtDispatchReprojectionDebug: output buffer too small");
+    MtStatus st = reproject_dispatch(c, true);
+    if (st != MT_OK) return st;
+    MT_CUDA(c, cudaMemcpyAsync(taps, c->taps, need, cudaMemcpyDeviceToHost, c->stream));
+    MT_CUDA(c, cudaStreamSynchronize(c->stream));
+    return MT_OK;
+}
+
+MtStatus mtDispatchGodRays(MtContext* c)
+{
+    if (!c) return MT_ERR_INVALID;
+    if (!c->haveCam) return fail(c, MT_ERR_NOT_READY, "god-ray dispatch: camera uniform not set");
+    MT_CUDA(c, cudaSetDevice(c->device));
+    GodRayParams P;
+    memset(&P, 0, sizeof(P));
+    copy_cam(P.cam, c->cam);
+    P.lightColor[0] = c->sky.lightColor[0]; P.lightColor[1] = c->sky.lightColor[1]; P.lightColor[2] = c->sky.lightColor[2];
+    P.mask = c->mask;
+    P.hdr = c->hdr[c->cur];
+    P.W = c->W; P.H = c->H;
+    P.f16_emulate = c->storage == MT_STORAGE_F16_EMULATE;
+    pass_begin(c, MT_PASS_GODRAYS);
+    MT_CUDA(c, mt_launch_godrays(P, c->stream));
+    pass_end(c, MT_PASS_GODRAYS);
+    c->launches += 1;
+    return MT_OK;
+}
+
+MtStatus mtDispatchToneMap(MtContext* c)
+{
+    if (!c) return MT_ERR_INVALID;
+    if (!c->haveTime) return fail(c, MT_ERR_NOT_READY, "tone-map dispatch: time uniform not set");
+    MT_CUDA(c, cudaSetDevice(c->device));
+    ToneMapParams P;
+    P.hdr = c->hdr[c->cur];
+    P.ldr = c->ldr;
+    P.W = c->W; P.H = c->H;
+    float ty = c->tm.time[1];  // uint(time.y): truncate, saturate, NaN -> 0
+    P.seed = (ty != ty || ty <= 0.0f) ? 0u : (ty >= 4294967296.0f ? 0xffffffffu : (unsigned)ty);
+    pass_begin(c, MT_PASS_TONEMAP);
+    MT_CUDA(c, mt_launch_tonemap(P, c->stream));
+    pass_end(c, MT_PASS_TONEMAP);
+    c->launches += 1;
+    return MT_OK;
+}
+
+MtStatus mtSwapPingPong(MtContext* c)
+{
+    if (!c) return MT_ERR_INVALID;
+    c->cur ^= 1;
+    return MT_OK;
+}
+
+MtStatus mtFrame(MtContext* c, int with_godrays)
+{
+    if (!c) return MT_ERR_INVALID;
+    MtStatus st;
+    if ((st = reproject_dispatch(c, false)) != MT_OK) return st;
+    if ((st = cloud_dispatch(c, 0, nullptr, false)) != MT_OK) return st;
+    if (with_godrays && (st = mtDispatchGodRays(c)) != MT_OK) return st;
+    if ((st = mtDispatchToneMap(c)) != MT_OK) return st;
+    return mtSwapPingPong(c);
+}
+
+MtStatus mtSynchronize(MtContext* c)
+{
+    if (!c) return MT_ERR_INVALID;
+    MT_CUDA(c, cudaSetDevice(c->device));
+    MT_CUDA(c, cudaStreamSynchronize(c->stream));
+    return MT_OK;
+}
+
+// ---- images -------------------------------------------------------------------------------------------------------
+MtStatus mtImageBytes(const MtContext* c, MtImage which, size_t* bytes)
+{
+    if (!c || !bytes || (int)which < 0 || (int)which > MT_IMAGE_LDR) return MT_ERR_INVALID;
+    *bytes = image_bytes(c, which);
+    return MT_OK;
+}
+MtStatus mtReadImageRows(MtContext* c, MtImage which, uint32_t row_begin, uint32_t row_end, void* host, size_t bytes)
+{
+    if (!c) return MT_ERR_INVALID;
+    MT_REQUIRE(c, (int)which >= 0 && (int)which <= MT_IMAGE_LDR && host != nullptr, "mtReadImageRows: bad arguments");
+    MT_REQUIRE(c, row_begin <= row_end && row_end <= (uint32_t)c->H, "mtReadImageRows: bad row range");
+    size_t pitch = (size_t)c->W * (which == MT_IMAGE_LDR ? 4 : 16);
+    size_t need = pitch * (row_end - row_begin);
+    MT_REQUIRE(c, bytes >= need, "mtReadImageRows: host buffer too small");
+    MT_CUDA(c, cudaSetDevice(c->device));
+    const char* src = (const char*)image_ptr(c, which) + pitch * row_begin;
+    if (need) MT_CUDA(c, cudaMemcpyAsync(host, src, need, cudaMemcpyDeviceToHost, c->stream));
+    MT_CUDA(c, cudaStreamSynchronize(c->stream));
+    return MT_OK;
+}
+MtStatus mtReadImage(MtContext* c, MtImage which, void* host, size_t bytes)
+{
+    if (!c) return MT_ERR_INVALID;
+    return mtReadImageRows(c, which, 0, (uint32_t)c->H, host, bytes);
+}
+MtStatus mtWriteImage(MtContext* c, MtImage which, const void* host, size_t bytes)
+{
+    if (!c) return MT_ERR_INVALID;
+    MT_REQUIRE(c, (int)which >= 0 && (int)which <= MT_IMAGE_LDR && host != nullptr, "mtWriteImage: bad arguments");
+    MT_REQUIRE(c, bytes == image_bytes(c, which), "mtWriteImage: size must equal the image size");
+    MT_CUDA(c, cudaSetDevice(c->device));
+    MT_CUDA(c, cudaMemcpyAsync(image_ptr(c, which), host, bytes, cudaMemcpyHostToDevice, c->stream));
+    return MT_OK;
+}
+MtStatus mtClearImages(MtContext* c)
+{
+    if (!c) return MT_ERR_INVALID;
+    MT_CUDA(c, cudaSetDevice(c->device));
+    size_t px = (size_t)c->W * c->H;
+    MT_CUDA(c, cudaMemsetAsync(c->hdr[0], 0, px * 16, c->stream));
+    MT_CUDA(c, cudaMemsetAsync(c->hdr[1], 0, px * 16, c->stream));
+    MT_CUDA(c, cudaMemsetAsync(c->mask, 0, px * 16, c->stream));
+    MT_CUDA(c, cudaMemsetAsync(c->ldr, 0, px * 4, c->stream));
+    return MT_OK;
+}
+MtStatus mtImageDevicePtr(MtContext* c, MtImage which, void** p)
+{
+    if (!c || !p || (int)which < 0 || (int)which > MT_IMAGE_LDR) return MT_ERR_INVALID;
+    *p = image_ptr(c, which);
+    return MT_OK;
+}
+MtStatus mtSetCloudOutput(MtContext* c, void* hdr, void* mask)
+{
+    if (!c) return MT_ERR_INVALID;
+    c->outHdr = (F4*)hdr;
+    c->outMask = (F4*)mask;
+    return MT_OK;
+}
+MtStatus mtExportImageHandle(MtContext* c, MtImage which, uint8_t handle[64])
+{
+    if (!c) return MT_ERR_INVALID;
+    MT_REQUIRE(c, handle != nullptr && (int)which >= 0 && (int)which <= MT_IMAGE_LDR, "mtExportImageHandle: bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+    MT_CUDA(c, cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    MT_CUDA(c, cudaIpcGetMemHandle(&h, image_ptr(c, which)));
+    memcpy(handle, &h, 64);
+    return MT_OK;
+}
+MtStatus mtOpenPeerImage(MtContext* c, const uint8_t handle[64], void** p)
+{
+    if (!c) return MT_ERR_INVALID;
+    MT_REQUIRE(c, handle != nullptr && p != nullptr, "mtOpenPeerImage: bad arguments");
+    MT_CUDA(c, cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    MT_CUDA(c, cudaIpcOpenMemHandle(p, h, cudaIpcMemLazyEnablePeerAccess));
+    return MT_OK;
+}
+MtStatus mtClosePeerImage(MtContext* c, void* p)
+{
+    if (!c) return MT_ERR_INVALID;
+    MT_CUDA(c, cudaSetDevice(c->device));
+    MT_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->outHdr == p) c->outHdr = nullptr;
+    if (c->outMask == p) c->outMask = nullptr;
+    MT_CUDA(c, cudaIpcCloseMemHandle(p));
+    return MT_OK;
+}
+
+// ---- measurement --------------------------------------------------------------------------------------------------
+MtStatus mtGetCounters(MtContext* c, MtCounters* out, int reset)
+{
+    if (!c) return MT_ERR_INVALID;
+    MT_REQUIRE(c, out != nullptr, "mtGetCounters: null output");
+    MT_CUDA(c, cudaSetDevice(c->device));
+    unsigned long long v[8];
+    MT_CUDA(c, cudaMemcpyAsync(v, c->counters, sizeof(v), cudaMemcpyDeviceToHost, c->stream));
+    MT_CUDA(c, cudaStreamSynchronize(c->stream));
+    out->rays = v[0]; out->rays_marched = v[1]; out->steps = v[2];
+    out->steps_incloud = v[3]; out->cone_hits = v[4]; out->early_exits = v[5];
+    if (reset) MT_CUDA(c, cudaMemsetAsync(c->counters, 0, sizeof(v), c->stream));
+    return MT_OK;
+}
+MtStatus mtLastPassMs(MtContext* c, MtPass pass, float* ms)
+{
+    if (!c) return MT_ERR_INVALID;
+    MT_REQUIRE(c, ms != nullptr && (int)pass >= 0 && (int)pass < MT_PASS_COUNT, "mtLastPassMs: bad arguments");
+    MT_REQUIRE(c, (c->flags & MT_FLAG_PASS_TIMING_INTERNAL) && c->evValid[pass], "mtLastPassMs: pass timing not enabled or pass never ran");
+    MT_CUDA(c, cudaSetDevice(c->device));
+    MT_CUDA(c, cudaEventSynchronize(c->ev[pass][1]));
+    MT_CUDA(c, cudaEventElapsedTime(ms, c->ev[pass][0], c->ev[pass][1]));
+    return MT_OK;
+}
+MtStatus mtStreamHandle(MtContext* c, void** s)
+{
+    if (!c || !s) return MT_ERR_INVALID;
+    *s = (void*)c->stream;
+    return MT_OK;
+}
+MtStatus mtEventRecord(MtContext* c, uint32_t slot)
+{
+    if (!c) return MT_ERR_INVALID;
+    MT_REQUIRE(c, slot < MT_USER_EVENTS, "mtEventRecord: slot out of range");
+    MT_CUDA(c, cudaSetDevice(c->device));
+    if (!c->userEv[slot]) MT_CUDA(c, cudaEventCreate(&c->userEv[slot]));
+    MT_CUDA(c, cudaEventRecord(c->userEv[slot], c->stream));
+    c->userEvValid[slot] = true;
+    return MT_OK;
+}
+MtStatus mtEventElapsedMs(MtContext* c, uint32_t from, uint32_t to, float* ms)
+{
+    if (!c) return MT_ERR_INVALID;
+    MT_REQUIRE(c, ms != nullptr && from < MT_USER_EVENTS && to < MT_USER_EVENTS, "mtEventElapsedMs: bad arguments");
+    MT_REQUIRE(c, c->userEvValid[from] && c->userEvValid[to], "mtEventElapsedMs: event slot never recorded");
+    MT_CUDA(c, cudaSetDevice(c->device));
+    MT_CUDA(c, cudaEventSynchronize(c->userEv[to]));
+    MT_CUDA(c, cudaEventElapsedTime(ms, c->userEv[from], c->userEv[to]));
+    return MT_OK;
+}
+uint64_t mtLaunchCount(const MtContext* c) { return c ? c->launches : 0; }
+
+}  // extern "C"

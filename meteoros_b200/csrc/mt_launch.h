@@ -1,0 +1,12 @@
+// mt_launch.h -- launchers of the pass kernels (implemented in the .cu files, called by mt_context.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "mt_params.h"
+
+cudaError_t mt_launch_cloud_setup(const CloudParams& P, MarchConst* out, cudaStream_t stream);
+cudaError_t mt_launch_cloud(const CloudParams& P, cudaStream_t stream);
+cudaError_t mt_launch_reproject(const ReprojParams& P, cudaStream_t stream);
+cudaError_t mt_launch_godrays(const GodRayParams& P, cudaStream_t stream);
+cudaError_t mt_launch_tonemap(const ToneMapParams& P, cudaStream_t stream);

@@ -1,0 +1,85 @@
+// mt_params.h -- kernel parameter blocks (passed by value; they live in the constant bank of each launch).
+#pragma once
+
+#include "../../include/meteoros_b200.h"
+#include "mt_math.cuh"
+#include "mt_tex.cuh"
+
+struct F4 {  // 16-byte pixel; float4 on the device
+    float x, y, z, w;
+};
+
+// Per-frame constants of the Preetham sky (cloudRayMarch.comp:401-467): everything that does not depend on the
+// ray.  Continuous radiance terms only, so they are evaluated once on the host (mt_host_sky_const).
+struct SkyConst {
+    float sunDir[3];   // normalize(BACKGROUND_SKY_SUN_LOCATION - origin)
+    float sunE;        // SUN_INTENSITY * calcSunIntensity()
+    float betaR[3];    // calcSkyBetaR()
+    float betaM[3];    // calcSkyBetaV()
+    float invBeta[3];  // unused by the canonical path (kept for alignment)
+    float yDotMix;     // clamp((1 - sunDir.y)^5, 0, 1)
+};
+
+// Per-frame constants of the march that feed discrete decisions; computed on the device by cloud_setup_kernel
+// with the canonical operation order (cloudRayMarch.comp:585-624).
+struct MarchConst {
+    f3 basisRight, basisUp, basisLook;  // castRay basis
+    f3 eyePos;                          // -camera.eye
+    f3 earthCenter;                     // (eye.x, -R, eye.z)
+    f3 lightDir;                        // normalize(SUN_LOCATION - origin)
+    f3 coneStep[6];                     // noise_kernel[i] (unscaled)
+    f3 windSkew;                        // (WIND_DIRECTION * h * CLOUD_TOP_OFFSET * 0.009) is per-step; this holds
+                                        // ((WIND_DIRECTION + (0,.1,0)) * CLOUD_SPEED) * time.y
+};
+
+struct RowTiles {  // which pixel rows this launch covers (multi-GPU row-tile shards); default = whole image
+    int tile_rows;    // rows per tile (multiple of the block height)
+    int tile_begin;   // first tile owned
+    int tile_stride;  // distance between owned tiles
+    int tile_count;   // number of owned tiles
+};
+
+struct CloudParams {
+    CamU cam;
+    TimeU tm;
+    MtTuning tun;
+    SkyConst sky;
+    Tex3D low, high;
+    Tex2D curl;
+    const MarchConst* mc;  // device memory, written by cloud_setup_kernel
+    F4* hdr;
+    F4* mask;
+    int W, H;
+    int tx, ty;  // threads of the reference dispatch (Renderer.cpp:713-716)
+    int full;    // 0: one id (tm.frameCountMod16) -- 1: all sixteen
+    int f16_emulate;
+    RowTiles rows;
+    unsigned long long* counters;  // 6 x u64 or null
+    MtRayDebug* debug;             // W*H records or null
+};
+
+struct ReprojParams {
+    CamU cam, camOld;
+    TimeU tm;
+    const F4* prev;
+    F4* cur;
+    int W, H;
+    int f16_emulate;
+    int* taps;  // debug: 10 per pixel, or null
+};
+
+struct GodRayParams {
+    CamU cam;
+    float lightColor[3];
+    const F4* mask;
+    F4* hdr;
+    int W, H;
+    int f16_emulate;
+};
+
+struct ToneMapParams {
+    const F4* hdr;
+    uint32_t* ldr;  // packed RGBA8
+    int W, H;
+    unsigned seed;  // uint(time.y)
+};

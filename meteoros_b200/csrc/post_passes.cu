@@ -1,0 +1,94 @@
+// post_passes.cu -- Reprojection, god-ray and tone-map passes as sm_100a kernels.  All three are bound by memory
+// traffic, not arithmetic: every global access is a 16-byte (float4) or 4-byte (packed RGBA8) vector per thread and
+// contiguous across a warp.  Compiled with -fmad=false (mt_math.cuh): the tap indices of the reprojection and the
+// tone-map dither are integer-exact with respect to the oracle.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include "mt_launch.h"
+#include "post_core.cuh"
+
+__device__ __forceinline__ float f16_round(float x) { return __half2float(__float2half_rn(x)); }
+__device__ __forceinline__ float4 f16_round4(float4 v)
+{
+    return make_float4(f16_round(v.x), f16_round(v.y), f16_round(v.z), f16_round(v.w));
+}
+
+// ---- Reprojection: 32x8 pixels per CTA, a warp is one 32-pixel row segment (512 contiguous bytes per access) -----
+__global__ void __launch_bounds__(256) reproject_kernel(const __grid_constant__ ReprojParams P)
+{
+    __shared__ RayBasis basis;
+    if (threadIdx.x == 0) basis = ray_basis(P.cam);
+    __syncthreads();
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= P.W || y >= P.H) return;
+    int taps[10];
+    reproject_taps(P, basis, x, y, taps);
+    const float4* prev = reinterpret_cast<const float4*>(P.prev);
+    float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        float4 t = __ldg(prev + taps[i]);
+        acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+    }
+    acc.x /= 10.0f; acc.y /= 10.0f; acc.z /= 10.0f; acc.w /= 10.0f;
+    if (P.f16_emulate) acc = f16_round4(acc);
+    const size_t idx = (size_t)y * P.W + x;
+    reinterpret_cast<float4*>(P.cur)[idx] = acc;
+    if (P.taps) {
+#pragma unroll
+        for (int i = 0; i < 10; ++i) P.taps[idx * 10 + i] = taps[i];
+    }
+}
+
+// ---- God rays: a warp is an 8x4 pixel tile so the footprint of tap i stays within a few cache lines ---------------
+__global__ void __launch_bounds__(128) godrays_kernel(const __grid_constant__ GodRayParams P)
+{
+    __shared__ GodRayFrame frame;
+    if (threadIdx.x == 0) frame = godray_frame(P.cam);
+    __syncthreads();
+    if (frame.blend < 0.0f) return;  // sun behind the camera: the fragment shader returns before any store
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int x = blockIdx.x * 16 + ((warp & 1) << 3) + (lane & 7);
+    const int y = blockIdx.y * 8 + ((warp >> 1) << 2) + (lane >> 3);
+    if (x >= P.W || y >= P.H) return;
+    F4 g = godray_pixel(P, frame, x, y);
+    float4* px = reinterpret_cast<float4*>(P.hdr) + ((size_t)y * P.W + x);
+    float4 c = *px;
+    c.x += g.x; c.y += g.y; c.z += g.z; c.w += g.w;
+    if (P.f16_emulate) c = f16_round4(c);
+    *px = c;
+}
+
+// ---- Tone map: one pixel per thread, 16 B in / 4 B out ------------------------------------------------------------
+__global__ void __launch_bounds__(256) tonemap_kernel(const __grid_constant__ ToneMapParams P)
+{
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= P.W || y >= P.H) return;
+    const size_t idx = (size_t)y * P.W + x;
+    float4 v = __ldg(reinterpret_cast<const float4*>(P.hdr) + idx);
+    F4 in;
+    in.x = v.x; in.y = v.y; in.z = v.z; in.w = v.w;
+    P.ldr[idx] = tonemap_pixel(P, in, x, y);
+}
+
+cudaError_t mt_launch_reproject(const ReprojParams& P, cudaStream_t stream)
+{
+    dim3 grid((unsigned)((P.W + 31) / 32), (unsigned)((P.H + 7) / 8), 1);
+    reproject_kernel<<<grid, 256, 0, stream>>>(P);
+    return cudaGetLastError();
+}
+cudaError_t mt_launch_godrays(const GodRayParams& P, cudaStream_t stream)
+{
+    dim3 grid((unsigned)((P.W + 15) / 16), (unsigned)((P.H + 7) / 8), 1);
+    godrays_kernel<<<grid, 128, 0, stream>>>(P);
+    return cudaGetLastError();
+}
+cudaError_t mt_launch_tonemap(const ToneMapParams& P, cudaStream_t stream)
+{
+    dim3 grid((unsigned)((P.W + 31) / 32), (unsigned)((P.H + 7) / 8), 1);
+    tonemap_kernel<<<grid, 256, 0, stream>>>(P);
+    return cudaGetLastError();
+}

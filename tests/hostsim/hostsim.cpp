@@ -1,0 +1,130 @@
+// hostsim.cpp -- TEST TOOL, never part of the product.  Compiles the per-pixel device functions of the CUDA
+// kernels (meteoros_b200/csrc/*_core.cuh) with g++ (MT_HOSTSIM) so that the restructured arithmetic of the
+// kernels -- hoisted frame constants, shared erosion fetch, scalar radiance, specialised filters -- can be checked
+// bit-for-bit against the independent oracle on a machine without a GPU.  With -ffp-contract=off the host
+// evaluates the same IEEE operations the device does under -fmad=false; only exp/pow/acos/cos differ on the GPU.
+// libmeteoros_b200.so does not contain, link or load any of this.
+#define MT_HOSTSIM 1
+#include <algorithm>
+#include <cstring>
+using std::max;
+using std::min;
+
+#include "../../meteoros_b200/csrc/cloud_core.cuh"
+#include "../../meteoros_b200/csrc/mt_host_consts.h"
+#include "../../meteoros_b200/csrc/post_core.cuh"
+
+extern "C" {
+
+int hs_cloud(const MtCameraUBO* cam, const MtTimeUBO* tm, const MtTuning* tun, const uint8_t* low, int lw, int lh, int ld,
+             const uint8_t* high, int hw, int hh, int hd, const uint8_t* curl, int cw, int ch, int W, int H, int full,
+             float* hdr, float* mask, unsigned long long* counters, MtRayDebug* debug)
+{
+    CloudParams P;
+    memset(&P, 0, sizeof(P));
+    memcpy(&P.cam, cam, sizeof(CamU));
+    memcpy(&P.tm, tm, sizeof(TimeU));
+    P.tun = *tun;
+    mt_host_sky_const(*cam, *tun, P.sky);
+    P.low.texels = (const uint32_t*)low; P.low.w = lw; P.low.h = lh; P.low.d = ld;
+    P.high.texels = (const uint32_t*)high; P.high.w = hw; P.high.h = hh; P.high.d = hd;
+    P.curl.texels = (const uint32_t*)curl; P.curl.w = cw; P.curl.h = ch;
+    P.W = W; P.H = H;
+    P.tx = (((W / 4) + 31) / 32) * 32;
+    P.ty = (((H / 4) + 31) / 32) * 32;
+    P.full = full;
+    MarchConst M;
+    cloud_frame_setup(P.cam, P.tm, P.tun, M);
+    RayCounters cnt = { 0, 0, 0, 0, 0, 0 };
+    unsigned long long tot[6] = { 0, 0, 0, 0, 0, 0 };
+    const int gw = full ? W : P.tx, gh = full ? H : P.ty;
+    for (int gy = 0; gy < gh; ++gy)
+        for (int gx = 0; gx < gw; ++gx) {
+            int px, py, id;
+            bool valid;
+            if (full) {
+                px = gx; py = gy;
+                id = ((px & 3) << 2) | (py & 3);
+                valid = px < W && py < H && (px >> 2) < P.tx && (py >> 2) < P.ty;
+            } else {
+                id = P.tm.frameCountMod16;
+                px = gx * 4 + (id >> 2);
+                py = gy * 4 + (id & 3);
+                valid = px < W && py < H;
+            }
+            if (!valid) continue;
+            F4 h, m;
+            size_t idx = (size_t)py * W + px;
+            MtRayDebug scratch;
+            memset(&cnt, 0, sizeof(cnt));
+            cloud_ray<true, true>(P, M, px, py, id, h, m, cnt, debug ? debug + idx : &scratch);
+            tot[0] += cnt.rays; tot[1] += cnt.marched; tot[2] += cnt.steps; tot[3] += cnt.incloud; tot[4] += cnt.cone; tot[5] += cnt.early;
+            memcpy(hdr + 4 * idx, &h, 16);
+            memcpy(mask + 4 * idx, &m, 16);
+        }
+    if (counters) for (int k = 0; k < 6; ++k) counters[k] += tot[k];
+    return 0;
+}
+
+int hs_reproject(const MtCameraUBO* cam, const MtCameraUBO* camOld, const MtTimeUBO* tm, int W, int H, const float* prev,
+                 float* cur, int* taps_out)
+{
+    ReprojParams P;
+    memset(&P, 0, sizeof(P));
+    memcpy(&P.cam, cam, sizeof(CamU));
+    memcpy(&P.camOld, camOld, sizeof(CamU));
+    memcpy(&P.tm, tm, sizeof(TimeU));
+    P.W = W; P.H = H;
+    RayBasis B = ray_basis(P.cam);
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+            int taps[10];
+            reproject_taps(P, B, x, y, taps);
+            float acc[4] = { 0, 0, 0, 0 };
+            for (int i = 0; i < 10; ++i) {
+                const float* p = prev + 4 * (size_t)taps[i];
+                acc[0] += p[0]; acc[1] += p[1]; acc[2] += p[2]; acc[3] += p[3];
+                if (taps_out) taps_out[((size_t)y * W + x) * 10 + i] = taps[i];
+            }
+            float* o = cur + 4 * ((size_t)y * W + x);
+            for (int c = 0; c < 4; ++c) o[c] = acc[c] / 10.0f;
+        }
+    return 0;
+}
+
+int hs_godrays(const MtCameraUBO* cam, const float* lightColor, int W, int H, const float* mask, float* hdr)
+{
+    GodRayParams P;
+    memset(&P, 0, sizeof(P));
+    memcpy(&P.cam, cam, sizeof(CamU));
+    P.lightColor[0] = lightColor[0]; P.lightColor[1] = lightColor[1]; P.lightColor[2] = lightColor[2];
+    P.mask = (const F4*)mask;
+    P.W = W; P.H = H;
+    GodRayFrame G = godray_frame(P.cam);
+    if (G.blend < 0.0f) return 0;
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+            F4 g = godray_pixel(P, G, x, y);
+            float* o = hdr + 4 * ((size_t)y * W + x);
+            o[0] += g.x; o[1] += g.y; o[2] += g.z; o[3] += g.w;
+        }
+    return 0;
+}
+
+int hs_tonemap(const MtTimeUBO* tm, int W, int H, const float* hdr, uint32_t* ldr)
+{
+    ToneMapParams P;
+    P.hdr = (const F4*)hdr;
+    P.ldr = ldr;
+    P.W = W; P.H = H;
+    P.seed = mt_f2u(tm->time[1]);
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+            F4 in;
+            memcpy(&in, hdr + 4 * ((size_t)y * W + x), 16);
+            ldr[(size_t)y * W + x] = tonemap_pixel(P, in, x, y);
+        }
+    return 0;
+}
+
+}  // extern "C"
