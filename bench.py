@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the cloud hot path (BASELINE.json: raymarched Mrays/s at 3840x2160).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cloud4k|frame8k|seq1080p]
+
+A step = one full-quality Cloud pass (mtDispatchCloudFull: all sixteen pixel ids, max steps, full light cone, no
+reprojection) over one synthetic 3840x2160 frame of the default cloudscape = 8 294 400 rays (BASELINE config 3).
+  value  device-timed Mrays/s: CUDA events on the context's stream around each dispatch, inputs resident in HBM,
+         L2 evicted between steps (mtFlushL2 writes 256 MiB), summed over exactly K steps, max over ranks.
+  e2e    the same metric through the public C-ABI call sequence with host buffers: uniforms from host memory in, the
+         RGBA32F HDR frame read back into pinned host memory, every step, wall-clock between synchronisations.
+  N > 1  weak scaling, no data-path collective: every rank renders its own 4K view of a sun-elevation / coverage
+         sweep (BASELINE config 5 style); value = N * rays / max-over-ranks time.  `--workload frame8k` instead shards
+         ONE 7680x4320 frame by cyclic 32-row tiles with stores straight into GPU 0's image over NVLink (config 4).
+  --impl reference   the CPU restatement of the reference shaders (oracle/, OpenMP over all host cores) on a bounded,
+         evenly spread sample of the same frame: the reference's own path needs Vulkan + a window.
+Rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+W4K, H4K = 3840, 2160
+METRIC = "raymarched Mrays/s at 3840x2160 (device-timed)"
+UNIT = "Mrays/s"
+
+# Algorithmic FP32 operations per unit of work (DESIGN.md "Work model"; fma = 2, div/sqrt/exp/pow = 1), counted
+# from the canonical arithmetic of oracle/meteoros_oracle.c.
+FLOP_PER_RAY = 40.0            # castRay + horizon test (every ray)
+FLOP_PER_MARCHED_RAY = 300.0   # Preetham sky, two shell intersections, phase function, composite, mask encode
+FLOP_PER_STEP = 182.0          # jittered position, height, wind skew + 1 filtered RGBA low-frequency sample (112)
+FLOP_PER_INCLOUD_STEP = 936.0  # curl + high-frequency erosion (127), 6 cone samples (6 x 127), light energy (47)
+FLOP_PER_CONE_HIT = 4.0        # erosion remap of a cone sample with density > 0
+HBM_BYTES_PER_RAY = 32.0       # RGBA32F colour + RGBA32F god-ray mask, written once
+
+
+def algorithmic_flop(c: dict) -> float:
+    return (FLOP_PER_RAY * c["rays"] + FLOP_PER_MARCHED_RAY * c["rays_marched"] + FLOP_PER_STEP * c["steps"]
+            + FLOP_PER_INCLOUD_STEP * c["steps_incloud"] + FLOP_PER_CONE_HIT * c["cone_hits"])
+
+
+def filtered_fetches(c: dict) -> int:
+    return c["steps"] + 8 * c["steps_incloud"]  # S + 8C
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device, self.rows, self.proc, self.thread = device, [], None, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 7:
+                self.rows.append(parts)
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        if self.thread:
+            self.thread.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        pw = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(self.rows), "reasons": reasons}
+
+
+def scene_for_view(view: int, w: int, h: int):
+    """View 0 = the default cloudscape; views > 0 sweep sun elevation (5..85 deg) x coverage (0.3..0.9), config 5."""
+    from meteoros_b200 import scene
+
+    cam, sc, sky = scene.Camera(w, h), scene.Scene(), scene.Sky()
+    sc.update_time(1.0 / 60.0)
+    tun = scene.default_tuning()
+    if view > 0:
+        tun["sun_location"] = scene.sun_on_elevation_circle(5.0 + 80.0 * ((view % 16) / 15.0))
+        tun["coverage"] = 0.3 + 0.6 * (((view // 16) % 16) / 15.0)
+    return cam.ubo(), sc.ubo(), sky.ubo(), tun
+
+
+def cpu_reference_sample(noise, w, h, target_s=12.0, probe_stride=64):
+    """Times the CPU oracle on every `stride`-th 4-row group of the frame (evenly spread, so ocean / sky / cloud rows
+    are sampled in proportion).  Returns (Mrays/s, cores, description, seconds)."""
+    import oracle
+
+    cam, tm, _, tun = scene_for_view(0, w, h)
+    hdr = np.zeros((h, w, 4), np.float32)
+    mask = np.zeros((h, w, 4), np.float32)
+    cores = os.cpu_count() or 1
+    groups = (h + 3) // 4
+
+    def run(stride):
+        t0 = time.perf_counter()
+        r = oracle.cloud(cam, tm, tun, noise, w, h, full=True, hdr=hdr, mask=mask, counters=True, group_stride=stride)
+        return time.perf_counter() - t0, r["counters"]["rays"]
+
+    run(max(probe_stride * 4, 1))  # warm the library / page in the volumes
+    dt, rays = run(probe_stride)
+    est_full = dt * probe_stride
+    stride = int(min(max(round(est_full / target_s), 1), groups // 8))
+    dt, rays = run(stride)
+    desc = f"every {stride}th 4-row group of the {w}x{h} full-quality frame ({rays} rays), OpenMP x{cores}"
+    return rays / dt / 1e6, cores, desc, dt
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the CPU restatement on the host cores; rank 0 only."""
+    if rank != 0:
+        return
+    from meteoros_b200 import textures
+
+    noise = textures.load_noise()
+    w, h = (W4K, H4K)
+    vals, secs, desc, cores = [], [], "", 1
+    budget = 150.0 / max(args.steps + args.warmup, 1)
+    for i in range(args.warmup + args.steps):
+        v, cores, desc, dt = cpu_reference_sample(noise, w, h, target_s=min(12.0, budget))
+        if i >= args.warmup:
+            vals.append(v)
+            secs.append(dt)
+    value = statistics.mean(vals)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(1e3 * statistics.mean(secs), 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "3840x2160 full-quality Cloud pass, default cloudscape (BASELINE config 3)", "sample": desc},
+        "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference shaders need Vulkan + a window and ship no SPIR-V (SURVEY.md 8c): timed arm is the CPU oracle port",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cloud4k", choices=["cloud4k", "frame8k", "seq1080p"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+
+    from meteoros_b200 import api, sharding, textures
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    noise = textures.load_noise()
+
+    if args.workload == "frame8k":
+        w, h, workload = 7680, 4320, "7680x4320 full-quality frame, cyclic 32-row tiles over the ranks, NVLink peer stores to GPU 0 (BASELINE config 4)"
+    elif args.workload == "seq1080p":
+        w, h, workload = 1920, 1080, "1920x1080 16-frame pan: Reprojection + 1/16 Cloud + god rays + tone map (BASELINE config 2)"
+    else:
+        w, h, workload = W4K, H4K, "3840x2160 full-quality Cloud pass, all 16 pixel ids, no reprojection (BASELINE config 3)"
+
+    view = rank if (args.workload == "cloud4k" and world > 1) else 0
+    cam, tm, sky, tun = scene_for_view(view, w, h)
+
+    # ---- work accounting (untimed): exact counters of this rank's frame from the counting variant of the kernel
+    with api.CloudRenderer(w, h, device=local_rank, flags=api.FLAG_COUNTERS) as rc:
+        rc.upload_noise(noise)
+        rc.set_camera(cam); rc.set_time(tm); rc.set_tuning(tun)
+        rc.dispatch_cloud_full()
+        counters = rc.counters()
+        fp32_peak_gflops = rc.measure_fp32_peak_gflops()
+
+    r = api.CloudRenderer(w, h, device=local_rank)
+    r.upload_noise(noise)
+    r.set_camera(cam); r.set_camera_old(cam); r.set_time(tm); r.set_sun_and_sky(sky); r.set_tuning(tun)
+
+    shard = None
+    if args.workload == "frame8k":
+        class _Dist:  # single-process stand-in so N=1 runs the same code path
+            def get_rank(self): return 0
+            def get_world_size(self): return 1
+        shard = sharding.ShardedFrame(r, dist if world > 1 else _Dist(), tile_rows=32, with_mask=True)
+
+    seq_state = {"frame": 0}
+
+    def step():
+        if args.workload == "cloud4k":
+            r.dispatch_cloud_full()
+        elif args.workload == "frame8k":
+            shard.dispatch()
+        else:
+            t = tm.copy()
+            t["frameCountMod16"] = (seq_state["frame"] + 1) % 16
+            seq_state["frame"] += 1
+            r.set_time(t)
+            r.frame(with_godrays=True)
+
+    def barrier():
+        r.synchronize()
+        if world > 1:
+            torch.cuda.synchronize()
+            dist.barrier()
+
+    rays_per_step_rank = counters["rays"] if args.workload != "seq1080p" else counters["rays"] // 16
+    if args.workload == "frame8k" and world > 1:
+        rays_total_per_step = w * h
+    else:
+        rays_total_per_step = rays_per_step_rank * world
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+
+    # ---- device-timed region: exactly K steps, events on the launching stream, L2 evicted between steps
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = r.launch_count()
+    step_ms = []
+    barrier()
+    for _ in range(args.steps):
+        r.flush_l2(0)
+        r.event_record(0)
+        step()
+        r.event_record(1)
+        if args.workload == "frame8k" and world > 1:
+            shard.finish()  # frame boundary: all ranks' tiles have landed on GPU 0
+        step_ms.append(r.event_elapsed_ms(0, 1))
+    barrier()
+    launches = r.launch_count() - launches0
+    clocks = sampler.stop()
+    dev_ms_total = float(sum(step_ms))
+
+    # ---- end-to-end region: host uniforms in, HDR frame out to pinned host memory, every step
+    out_which = api.IMAGE_CLOUD_CUR if args.workload != "seq1080p" else api.IMAGE_LDR
+    nbytes = w * h * (16 if out_which != api.IMAGE_LDR else 4)
+    pinned = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    h2d = int(cam.nbytes + tm.nbytes + tun.nbytes + sky.nbytes)
+    e2e_read = (rank == 0) or args.workload != "frame8k"
+    for _ in range(2):
+        step()
+        if e2e_read:
+            r.read_image_into(out_which, pinned.data_ptr(), nbytes)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r.set_camera(cam); r.set_time(tm); r.set_tuning(tun); r.set_sun_and_sky(sky)
+        step()
+        if args.workload == "frame8k" and world > 1:
+            shard.finish()
+        if e2e_read:
+            if args.workload == "seq1080p":
+                r.read_image_into(api.IMAGE_LDR, pinned.data_ptr(), nbytes)
+            else:
+                r.read_image_into(out_which, pinned.data_ptr(), nbytes)  # synchronises
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    # ---- max over ranks
+    if world > 1:
+        t = torch.tensor([dev_ms_total, e2e_s], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms_total, e2e_s = float(t[0]), float(t[1])
+        cs = torch.tensor([counters[k] for k in ("rays", "rays_marched", "steps", "steps_incloud", "cone_hits", "early_exits")],
+                          dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(cs, op=dist.ReduceOp.SUM)
+
+    ms_per_step = dev_ms_total / args.steps
+    value = rays_total_per_step / (ms_per_step * 1e-3) / 1e6
+    e2e_value = rays_total_per_step * args.steps / e2e_s / 1e6
+
+    line = None
+    if rank == 0:
+        peaks = {}
+        pk = ROOT / "MEASURED_PEAKS.json"
+        if pk.exists():
+            peaks = json.loads(pk.read_text())
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        hbm_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+        # roofline of the dominant kernel (cloud_raymarch), per launch, rank 0's frame
+        flop = algorithmic_flop(counters)
+        kern_ms = statistics.mean(step_ms) if args.workload != "seq1080p" else None
+        roofline = None
+        if kern_ms:
+            ach_tflops = flop / (kern_ms * 1e-3) / 1e12
+            hbm_ach = HBM_BYTES_PER_RAY * counters["rays"] / (kern_ms * 1e-3) / 1e9
+            roofline = {
+                "bound": "fp32-issue", "kernel": "cloud_raymarch_kernel", "achieved": round(ach_tflops, 3),
+                "peak": round(fp32_peak_gflops / 1e3, 3), "unit": "TFLOP/s", "frac": round(ach_tflops / (fp32_peak_gflops / 1e3), 4),
+                "peak_source": "measured FP32 FMA micro-benchmark (mtMeasureFp32Peak) on this GPU; no tensor work in this path",
+                "algorithmic_gflop_per_launch": round(flop / 1e9, 3), "filtered_fetches_per_launch": filtered_fetches(counters),
+                "gfetch_per_s": round(filtered_fetches(counters) / (kern_ms * 1e-3) / 1e9, 3), "traffic": None,
+                "hbm": {"bound": "hbm", "achieved": round(hbm_ach, 2), "peak": hbm_peak, "unit": "GB/s", "frac": round(hbm_ach / hbm_peak, 5),
+                        "algorithmic_bytes_per_launch": int(HBM_BYTES_PER_RAY * counters["rays"]), "peak_source": hbm_src},
+            }
+        line = {
+            "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
+            "scaling": "strong" if (args.workload == "frame8k") else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload, "rays_per_step": int(rays_total_per_step), "l2": "flushed between timed steps (256 MiB memset)",
+                       "noise": "reference noise volumes (tests/golden/noise_volumes.npz)", "parallelism": f"views x{world}" if args.workload == "cloud4k" else f"row-tiles x{world}"},
+            "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(nbytes if e2e_read else 0),
+                    "ms_per_step": round(1e3 * e2e_s / args.steps, 4)},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+            "work": {k: int(v) for k, v in counters.items()},
+        }
+
+    if shard is not None and world > 1:
+        shard.close()
+    r.close()
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "cloud4k":
+        v, cores, desc, _ = cpu_reference_sample(noise, W4K, H4K, target_s=12.0)
+        line["cpu_baseline"] = {"value": round(v, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -222,6 +222,12 @@ MT_API MtStatus mtStreamHandle(MtContext* ctx, void** cuda_stream);        /* cu
  * slot 0..15, then read the device time between two recorded slots.  mtEventElapsedMs synchronises on `to`. */
 MT_API MtStatus mtEventRecord(MtContext* ctx, uint32_t slot);
 MT_API MtStatus mtEventElapsedMs(MtContext* ctx, uint32_t from, uint32_t to, float* ms);
+/* Evict the L2 between timed iterations: overwrites an internal scratch buffer of `bytes` (rounded up to 256 MiB,
+ * larger than the 126 MB L2) on the context's stream.  Not counted by mtLaunchCount.                            */
+MT_API MtStatus mtFlushL2(MtContext* ctx, size_t bytes);
+/* Micro-benchmark for the raymarch roofline: sustained FP32 FMA rate of the device in GFLOP/s (2 flop per FMA,
+ * all SMs, register-resident independent chains).  The denominator for an issue-bound, non-tensor kernel.      */
+MT_API MtStatus mtMeasureFp32Peak(MtContext* ctx, float* gflops);
 /* Number of kernel launches issued by this context since creation (bench.py's gpu_launches). */
 MT_API uint64_t mtLaunchCount(const MtContext* ctx);
 

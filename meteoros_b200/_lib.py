@@ -83,6 +83,8 @@ PROTOTYPES = {
     "mtStreamHandle": (C.c_int, [C.c_void_p, c_void_pp]),
     "mtEventRecord": (C.c_int, [C.c_void_p, C.c_uint32]),
     "mtEventElapsedMs": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_float)]),
+    "mtFlushL2": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "mtMeasureFp32Peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "mtLaunchCount": (C.c_uint64, [C.c_void_p]),
 }
 

@@ -257,5 +257,13 @@ class CloudRenderer:
         self._check(self._lib.mtStreamHandle(self._h, C.byref(p)), "mtStreamHandle")
         return int(p.value or 0)
 
+    def flush_l2(self, nbytes: int = 0):
+        self._check(self._lib.mtFlushL2(self._h, nbytes), "mtFlushL2")
+
+    def measure_fp32_peak_gflops(self) -> float:
+        g = C.c_float()
+        self._check(self._lib.mtMeasureFp32Peak(self._h, C.byref(g)), "mtMeasureFp32Peak")
+        return float(g.value)
+
     def launch_count(self) -> int:
         return int(self._lib.mtLaunchCount(self._h))

@@ -45,6 +45,8 @@ struct MtContext {
     cudaEvent_t userEv[MT_USER_EVENTS] = {};
     bool userEvValid[MT_USER_EVENTS] = {};
     uint64_t launches = 0;
+    void* flushBuf = nullptr;
+    size_t flushBytes = 0;
     std::string err;
 };
 
@@ -192,6 +194,7 @@ void mtDestroy(MtContext* c)
     for (int i = 0; i < 4; ++i) cudaFree(c->tex[i]);
     cudaFree(c->mc);
     cudaFree(c->counters);
+    cudaFree(c->flushBuf);
     for (int p = 0; p < MT_PASS_COUNT; ++p) {
         if (c->ev[p][0]) cudaEventDestroy(c->ev[p][0]);
         if (c->ev[p][1]) cudaEventDestroy(c->ev[p][1]);
@@ -647,6 +650,55 @@ MtStatus mtEventElapsedMs(MtContext* c, uint32_t from, uint32_t to, float* ms)
     MT_CUDA(c, cudaSetDevice(c->device));
     MT_CUDA(c, cudaEventSynchronize(c->userEv[to]));
     MT_CUDA(c, cudaEventElapsedTime(ms, c->userEv[from], c->userEv[to]));
+    return MT_OK;
+}
+MtStatus mtFlushL2(MtContext* c, size_t bytes)
+{
+    if (!c) return MT_ERR_INVALID;
+    MT_CUDA(c, cudaSetDevice(c->device));
+    const size_t unit = (size_t)256 << 20;
+    size_t want = ((bytes ? bytes : unit) + unit - 1) / unit * unit;
+    if (want > c->flushBytes) {
+        MT_CUDA(c, cudaStreamSynchronize(c->stream));
+        cudaFree(c->flushBuf);
+        c->flushBuf = nullptr;
+        c->flushBytes = 0;
+        MT_CUDA(c, cudaMalloc(&c->flushBuf, want));
+        c->flushBytes = want;
+    }
+    MT_CUDA(c, cudaMemsetAsync(c->flushBuf, 0, want, c->stream));
+    return MT_OK;
+}
+MtStatus mtMeasureFp32Peak(MtContext* c, float* gflops)
+{
+    if (!c) return MT_ERR_INVALID;
+    MT_REQUIRE(c, gflops != nullptr, "mtMeasureFp32Peak: null output");
+    MT_CUDA(c, cudaSetDevice(c->device));
+    cudaDeviceProp prop;
+    MT_CUDA(c, cudaGetDeviceProperties(&prop, c->device));
+    const int blocks = prop.multiProcessorCount * 8, iters = 4096;
+    float* sink = (float*)c->counters + 14;  // scratch word behind the six counters
+    cudaEvent_t e0, e1;
+    MT_CUDA(c, cudaEventCreate(&e0));
+    MT_CUDA(c, cudaEventCreate(&e1));
+    float best = 0.0f;
+    for (int rep = 0; rep < 6; ++rep) {  // first reps double as warm-up
+        cudaEventRecord(e0, c->stream);
+        cudaError_t le = mt_launch_fma_probe(sink, blocks, iters, c->stream);
+        cudaEventRecord(e1, c->stream);
+        if (le != cudaSuccess || cudaEventSynchronize(e1) != cudaSuccess) {
+            cudaEventDestroy(e0); cudaEventDestroy(e1);
+            return cuda_fail(c, le != cudaSuccess ? le : cudaGetLastError(), "fma probe");
+        }
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        double flop = 2.0 * 16.0 * (double)iters * 256.0 * (double)blocks;
+        float g = (float)(flop / (ms * 1e-3) * 1e-9);
+        if (rep >= 2 && g > best) best = g;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *gflops = best;
     return MT_OK;
 }
 uint64_t mtLaunchCount(const MtContext* c) { return c ? c->launches : 0; }

@@ -10,3 +10,4 @@ cudaError_t mt_launch_cloud(const CloudParams& P, cudaStream_t stream);
 cudaError_t mt_launch_reproject(const ReprojParams& P, cudaStream_t stream);
 cudaError_t mt_launch_godrays(const GodRayParams& P, cudaStream_t stream);
 cudaError_t mt_launch_tonemap(const ToneMapParams& P, cudaStream_t stream);
+cudaError_t mt_launch_fma_probe(float* sink, int blocks, int iters, cudaStream_t stream);

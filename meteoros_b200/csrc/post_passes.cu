@@ -92,3 +92,25 @@ cudaError_t mt_launch_tonemap(const ToneMapParams& P, cudaStream_t stream)
     tonemap_kernel<<<grid, 256, 0, stream>>>(P);
     return cudaGetLastError();
 }
+
+// ---- FP32 issue-rate probe (mtMeasureFp32Peak): 16 independent FMA chains per thread, registers only --------------
+__global__ void __launch_bounds__(256) fma_probe_kernel(float* sink, int iters)
+{
+    float a[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a[k] = (float)(threadIdx.x + k) * 1e-3f;
+    const float m = 1.0000001f, c = 1e-7f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) a[k] = fmaf(a[k], m, c);
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s += a[k];
+    if (s == 123.456f) sink[0] = s;  // never true; keeps the chains alive
+}
+cudaError_t mt_launch_fma_probe(float* sink, int blocks, int iters, cudaStream_t stream)
+{
+    fma_probe_kernel<<<blocks, 256, 0, stream>>>(sink, iters);
+    return cudaGetLastError();
+}

@@ -79,7 +79,8 @@ def _textures(noise):
     return t, keep
 
 
-def cloud(cam, tm, tuning, noise, W, H, full=False, rows=None, hdr=None, mask=None, counters=False, debug=False):
+def cloud(cam, tm, tuning, noise, W, H, full=False, rows=None, hdr=None, mask=None, counters=False, debug=False,
+          group_stride=1):
     """cloudRayMarch.comp over the reference grid.  Returns dict(hdr, mask[, counters][, debug]).
     hdr / mask may be passed in (float32 HxWx4, modified in place: unwritten pixels keep their value)."""
     cam = np.ascontiguousarray(cam); tm = np.ascontiguousarray(tm); tuning = np.ascontiguousarray(tuning)
@@ -91,7 +92,7 @@ def cloud(cam, tm, tuning, noise, W, H, full=False, rows=None, hdr=None, mask=No
     dbg = np.zeros((H, W), RAY_DEBUG_DTYPE) if debug else None
     r0, r1 = rows if rows is not None else (0, H)
     rc = lib().mto_cloud(_p(cam), _p(tm), _p(tuning), C.byref(tex), C.c_int(W), C.c_int(H), C.c_int(int(bool(full))),
-                         C.c_int(r0), C.c_int(r1), _p(hdr), _p(mask), C.byref(cnt) if counters else None, _p(dbg))
+                         C.c_int(r0), C.c_int(r1), C.c_int(group_stride), _p(hdr), _p(mask), C.byref(cnt) if counters else None, _p(dbg))
     if rc != 0:
         raise ValueError("mto_cloud: invalid arguments")
     del keep

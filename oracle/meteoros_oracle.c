@@ -586,8 +586,10 @@ static void cloud_grid(int W, int H, int* tx, int* ty)
 }
 
 int mto_cloud(const MtCameraUBO* cam, const MtTimeUBO* tm, const MtTuning* tun, const MtoTextures* tex, int W, int H,
-              int full, int row_begin, int row_end, float* hdr, float* mask, MtCounters* counters, MtRayDebug* debug)
+              int full, int row_begin, int row_end, int group_stride, float* hdr, float* mask, MtCounters* counters,
+              MtRayDebug* debug)
 {
+    if (group_stride < 1) group_stride = 1;
     if (!cam || !tm || !tun || !tex || !hdr || !mask || W <= 0 || H <= 0) return 1;
     if (!tex->low || !tex->high || !tex->curl) return 1;
     CloudEnv e = { cam, tm, tun, tex, W, H };
@@ -604,7 +606,7 @@ int mto_cloud(const MtCameraUBO* cam, const MtTimeUBO* tm, const MtTuning* tun, 
         MtCounters local;
         memset(&local, 0, sizeof(local));
 #pragma omp for schedule(dynamic, 1)
-        for (int gy = 0; gy < ty; ++gy) {
+        for (int gy = 0; gy < ty; gy += group_stride) {
             for (int k = 0; k < nid; ++k) {
                 int pixelID = full ? k : id0;
                 int pX = pixelID / 4, pY = pixelID % 4; /* :697-698 */

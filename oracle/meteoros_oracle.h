@@ -22,10 +22,12 @@ typedef struct MtoTextures {
 
 /* cloudRayMarch.comp main() over the reference grid (Renderer.cpp:713-716).  full == 0: one dispatch with
  * pixelID = tm->frameCountMod16; full != 0: the union of the 16 dispatches.  Only pixel rows in
- * [row_begin, row_end) are produced (row_end <= 0 means H) -- used for bounded CPU-baseline samples.
+ * [row_begin, row_end) are produced (row_end <= 0 means H), and of the 4-row groups only every group_stride-th
+ * (1 = all) -- both used for bounded CPU-baseline samples spread evenly over the frame.
  * counters / debug may be NULL; debug holds W*H records.                                               */
 int mto_cloud(const MtCameraUBO* cam, const MtTimeUBO* tm, const MtTuning* tun, const MtoTextures* tex, int W, int H,
-              int full, int row_begin, int row_end, float* hdr, float* mask, MtCounters* counters, MtRayDebug* debug);
+              int full, int row_begin, int row_end, int group_stride, float* hdr, float* mask, MtCounters* counters,
+              MtRayDebug* debug);
 /* reprojection.comp main(); taps (optional) receives 10 clamped linear indices per pixel. */
 int mto_reproject(const MtCameraUBO* cam, const MtCameraUBO* camOld, const MtTimeUBO* tm, int W, int H, const float* prev,
                   float* cur, int32_t* taps);

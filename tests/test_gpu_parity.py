@@ -1,0 +1,358 @@
+"""Parity of the sm_100a kernels against the CPU oracle, through the C ABI (needs a B200: run with -m gpu).
+
+Bars (BASELINE.json north_star): pixel selection and reprojection tap indices bit-exact; HDR radiance max relative
+error <= 1e-3 and PSNR >= 50 dB; god-ray mask within 1/255.  The kernels are designed for more than that -- every
+decision-carrying value (ray, shell distances, step count, jitter sequence, accumulated density, mask) bit-identical,
+radiance differing only through the SFU exp/pow -- and the tests assert the stronger property too.
+"""
+import numpy as np
+import pytest
+
+from conftest import default_scene, psnr, rel_err
+
+pytestmark = pytest.mark.gpu
+
+HDR_MAX_REL = 1e-3   # north_star tolerance
+HDR_MIN_PSNR = 50.0  # dB
+MASK_TOL = 1.0 / 255.0
+
+
+@pytest.fixture(scope="module")
+def api():
+    from meteoros_b200 import api as _api
+
+    return _api
+
+
+def make_renderer(api, noise, w, h, **kw):
+    r = api.CloudRenderer(w, h, **kw)
+    r.upload_noise(noise)
+    return r
+
+
+def check_hdr(got, want, where=None):
+    if where is not None:
+        got, want = got[where], want[where]
+    e = rel_err(got[..., :3], want[..., :3])
+    assert e.max() <= HDR_MAX_REL, f"max rel err {e.max():.3e}"
+    assert psnr(got[..., :3], want[..., :3]) >= HDR_MIN_PSNR
+    return float(e.max())
+
+
+@pytest.mark.parametrize("w,h,fid,yaw,pitch,t", [
+    (240, 136, 1, 0.0, 0.0, 0.016),
+    (240, 136, 6, 25.0, 5.0, 12.5),
+    (130, 70, 15, -10.0, -3.0, 100.0),   # trailing columns 128,129 are never marched (Renderer.cpp:713)
+    (1284, 720, 9, 0.0, 0.0, 0.5),       # the reference's own default window (main.cpp:22-23)
+])
+def test_cloud_sixteenth_dispatch(api, oracle_mod, noise, w, h, fid, yaw, pitch, t):
+    cam, tm, _, tun = default_scene(w, h, frame_id=fid, total_time=t, yaw=yaw, pitch=pitch)
+    sentinel = np.full((h, w, 4), -7.0, np.float32)
+    ref = oracle_mod.cloud(cam, tm, tun, noise, w, h, full=False, hdr=sentinel.copy(), mask=sentinel.copy())
+    with make_renderer(api, noise, w, h) as r:
+        r.set_camera(cam); r.set_time(tm); r.set_tuning(tun)
+        r.write_image(api.IMAGE_CLOUD_CUR, sentinel)
+        r.write_image(api.IMAGE_GODRAY_MASK, sentinel)
+        r.dispatch_cloud()
+        hdr = r.read_image(api.IMAGE_CLOUD_CUR)
+        mask = r.read_image(api.IMAGE_GODRAY_MASK)
+    written = hdr[..., 3] != -7.0
+    assert np.array_equal(written, ref["hdr"][..., 3] != -7.0)      # pixel selection: bit-exact
+    assert np.array_equal(hdr[~written], sentinel[~written])        # nothing else touched
+    check_hdr(hdr, ref["hdr"], written)
+    assert np.abs(mask - ref["mask"]).max() <= MASK_TOL
+    assert np.array_equal(mask, ref["mask"])                        # designed to be exact
+
+
+@pytest.mark.parametrize("w,h,yaw,pitch,t", [(480, 270, 0.0, 0.0, 0.016), (322, 182, 40.0, 10.0, 7.0)])
+def test_cloud_full_dispatch_and_debug_records(api, oracle_mod, noise, w, h, yaw, pitch, t):
+    cam, tm, _, tun = default_scene(w, h, frame_id=3, total_time=t, yaw=yaw, pitch=pitch)
+    ref = oracle_mod.cloud(cam, tm, tun, noise, w, h, full=True, counters=True, debug=True)
+    with make_renderer(api, noise, w, h, flags=api.FLAG_COUNTERS) as r:
+        r.set_camera(cam); r.set_time(tm); r.set_tuning(tun)
+        r.dispatch_cloud_full()
+        hdr = r.read_image(api.IMAGE_CLOUD_CUR)
+        mask = r.read_image(api.IMAGE_GODRAY_MASK)
+        cnt = r.counters()
+        dbg = r.dispatch_cloud_debug(True)
+        hdr2 = r.read_image(api.IMAGE_CLOUD_CUR)
+    assert cnt == ref["counters"]
+    for f in oracle_mod.RAY_DEBUG_DTYPE.names:  # ray, shells, step count, jitter sequence, accumulated density
+        assert np.array_equal(dbg[f], ref["debug"][f]), f
+    assert np.array_equal(mask, ref["mask"])
+    e = check_hdr(hdr, ref["hdr"])
+    assert e < 1e-4  # SFU exp/pow only
+    assert np.array_equal(hdr, hdr2)  # debug / counter variants compute the same pixels
+
+
+def test_cloud_tuning_sweep(api, oracle_mod, noise):
+    from meteoros_b200 import scene
+
+    w, h = 160, 90
+    cam, tm, _, tun = default_scene(w, h, frame_id=11, total_time=33.0)
+    with make_renderer(api, noise, w, h) as r:
+        r.set_camera(cam); r.set_time(tm)
+        for cov, elev in ((0.3, 5.0), (0.9, 85.0), (0.5, 45.0)):
+            tun["coverage"] = cov
+            tun["sun_location"] = scene.sun_on_elevation_circle(elev)
+            r.set_tuning(tun)
+            r.dispatch_cloud_full()
+            hdr = r.read_image(api.IMAGE_CLOUD_CUR)
+            mask = r.read_image(api.IMAGE_GODRAY_MASK)
+            ref = oracle_mod.cloud(cam, tm, tun, noise, w, h, full=True)
+            check_hdr(hdr, ref["hdr"])
+            assert np.array_equal(mask, ref["mask"])
+
+
+def test_cloud_row_tiles_are_bit_identical_to_one_launch(api, noise):
+    """Multi-GPU sharding must not change arithmetic: N tile launches == one launch (run here on one device)."""
+    w, h = 320, 200  # 200 rows: the last 32-row tile is partial
+    cam, tm, _, tun = default_scene(w, h, yaw=15.0)
+    with make_renderer(api, noise, w, h) as r:
+        r.set_camera(cam); r.set_time(tm)
+        r.dispatch_cloud_full()
+        full_hdr = r.read_image(api.IMAGE_CLOUD_CUR)
+        full_mask = r.read_image(api.IMAGE_GODRAY_MASK)
+        for world in (2, 3, 8):
+            r.clear_images()
+            n = (h + 31) // 32
+            for rank in range(world):
+                r.dispatch_cloud_tiles(32, rank, n, world)
+            assert np.array_equal(r.read_image(api.IMAGE_CLOUD_CUR), full_hdr)
+            assert np.array_equal(r.read_image(api.IMAGE_GODRAY_MASK), full_mask)
+        # a single rank's shard leaves the other tiles untouched
+        r.clear_images()
+        r.dispatch_cloud_tiles(32, 1, n, 2)
+        part = r.read_image(api.IMAGE_CLOUD_CUR)
+        for t in range(n):
+            rows = slice(t * 32, min(h, (t + 1) * 32))
+            if t % 2 == 1:
+                assert np.array_equal(part[rows], full_hdr[rows])
+            else:
+                assert not part[rows].any()
+
+
+def test_cloud_output_redirect_and_ipc_roundtrip(api, noise):
+    """mtSetCloudOutput: the kernel stores into caller-provided device memory (the peer-mapped image on GPU 0 in a
+    multi-GPU run; here a second context's image on the same device)."""
+    w, h = 128, 72
+    cam, tm, _, tun = default_scene(w, h)
+    with make_renderer(api, noise, w, h) as a, make_renderer(api, noise, w, h) as b:
+        for r in (a, b):
+            r.set_camera(cam); r.set_time(tm)
+        a.dispatch_cloud_full()
+        want = a.read_image(api.IMAGE_CLOUD_CUR)
+        b.set_cloud_output(a.image_device_ptr(api.IMAGE_CLOUD_PREV), None)
+        b.dispatch_cloud_full()
+        b.synchronize()
+        assert np.array_equal(a.read_image(api.IMAGE_CLOUD_PREV), want)
+        assert not b.read_image(api.IMAGE_CLOUD_CUR).any()
+        assert len(a.export_image_handle(api.IMAGE_CLOUD_CUR)) == 64
+
+
+def test_reprojection_indices_and_image(api, oracle_mod):
+    from meteoros_b200 import scene
+
+    w, h = 400, 226
+    rng = np.random.default_rng(5)
+    prev = rng.random((h, w, 4), dtype=np.float32)
+    cam = scene.Camera(w, h)
+    old = cam.ubo()
+    cam.rotate_about_up(0.25)
+    cam.rotate_about_right(0.25)
+    new = cam.ubo()
+    sc = scene.Scene()
+    with api.CloudRenderer(w, h) as r:
+        for fid in (1, 10):
+            sc.time["frameCountMod16"] = fid
+            r.set_camera(new); r.set_camera_old(old); r.set_time(sc.ubo())
+            r.write_image(api.IMAGE_CLOUD_PREV, prev)
+            taps = r.dispatch_reprojection_debug()
+            cur = r.read_image(api.IMAGE_CLOUD_CUR)
+            ref, ref_taps = oracle_mod.reproject(new, old, sc.ubo(), prev, taps=True)
+            assert np.array_equal(taps, ref_taps)   # reprojection indices: bit-exact
+            assert np.array_equal(cur, ref)         # ten exact adds and one divide
+            r.dispatch_reprojection()
+            assert np.array_equal(r.read_image(api.IMAGE_CLOUD_CUR), ref)
+
+
+def test_godrays_and_tonemap(api, oracle_mod, noise):
+    w, h = 256, 144
+    cam, tm, sky, tun = default_scene(w, h, total_time=9.75)
+    ref = oracle_mod.cloud(cam, tm, tun, noise, w, h, full=True)
+    with make_renderer(api, noise, w, h) as r:
+        r.set_camera(cam); r.set_time(tm); r.set_sun_and_sky(sky)
+        # feed the oracle's images so each pass is judged on identical inputs
+        r.write_image(api.IMAGE_CLOUD_CUR, ref["hdr"])
+        r.write_image(api.IMAGE_GODRAY_MASK, ref["mask"])
+        r.dispatch_god_rays()
+        got = r.read_image(api.IMAGE_CLOUD_CUR)
+        want = oracle_mod.godrays(cam, sky, ref["mask"], ref["hdr"])
+        assert (want != ref["hdr"]).any()
+        assert np.array_equal(got, want)  # no transcendental in this pass
+        r.dispatch_tone_map()
+        ldr = r.read_image(api.IMAGE_LDR)
+        want_ldr = oracle_mod.tonemap(tm, want)
+        d = np.abs(ldr.astype(np.int32) - want_ldr.astype(np.int32))
+        assert d.max() <= 1 and (d > 0).mean() < 0.01  # SFU pow can move a value across a rounding boundary
+        assert (ldr[..., 3] == 255).all()
+    # sun behind the camera: the god-ray pass writes nothing
+    from meteoros_b200 import scene
+
+    c2 = scene.Camera(w, h)
+    c2.rotate_about_right(-80.0)
+    with api.CloudRenderer(w, h) as r:
+        r.set_camera(c2.ubo()); r.set_sun_and_sky(sky)
+        r.write_image(api.IMAGE_CLOUD_CUR, ref["hdr"])
+        r.write_image(api.IMAGE_GODRAY_MASK, ref["mask"])
+        r.dispatch_god_rays()
+        out = r.read_image(api.IMAGE_CLOUD_CUR)
+        assert np.array_equal(out, oracle_mod.godrays(c2.ubo(), sky, ref["mask"], ref["hdr"]))
+
+
+def test_sixteen_frame_pan_sequence(api, oracle_mod, noise):
+    """BASELINE config 2 at reduced size: 16 frames, 0.25 deg/frame pan, REPROJ + CLOUD + GODRAYS + TONEMAP + swap."""
+    from meteoros_b200 import scene
+
+    w, h = 192, 108
+    cam, sc, sky = scene.Camera(w, h), scene.Scene(), scene.Sky()
+    tun = scene.default_tuning()
+    img = [np.zeros((h, w, 4), np.float32), np.zeros((h, w, 4), np.float32)]
+    mask = np.zeros((h, w, 4), np.float32)
+    cur = 0
+    cam_old = cam.ubo()
+    worst = 0.0
+    with make_renderer(api, noise, w, h) as r:
+        r.set_sun_and_sky(sky.ubo())
+        for frame in range(16):
+            cam.rotate_about_up(0.25)
+            sc.update_time(1 / 60)
+            c, t = cam.ubo(), sc.ubo()
+            # oracle frame
+            img[cur] = oracle_mod.reproject(c, cam_old, t, img[cur ^ 1])
+            oracle_mod.cloud(c, t, tun, noise, w, h, full=False, hdr=img[cur], mask=mask)
+            img[cur] = oracle_mod.godrays(c, sky.ubo(), mask, img[cur])
+            ldr_ref = oracle_mod.tonemap(t, img[cur])
+            # CUDA frame through mtFrame
+            r.set_camera(c); r.set_camera_old(cam_old); r.set_time(t)
+            r.frame(with_godrays=True)
+            got = r.read_image(api.IMAGE_CLOUD_PREV)  # roles swapped at the end of the frame
+            worst = max(worst, check_hdr(got, img[cur]))
+            assert np.abs(r.read_image(api.IMAGE_GODRAY_MASK) - mask).max() <= MASK_TOL
+            d = np.abs(r.read_image(api.IMAGE_LDR).astype(np.int32) - ldr_ref.astype(np.int32))
+            assert d.max() <= 1
+            cur ^= 1
+            cam_old = c
+    assert worst < 1e-3
+    g = np.load(__import__("pathlib").Path(__file__).parent / "golden" / "sequence_96x54.npz")
+    assert g["ldr"].shape == (4, 54, 96, 4)  # the committed sequence golden is checked on CPU (test_golden_sequence)
+
+
+def test_f16_storage_emulation(api, oracle_mod, noise):
+    w, h = 128, 72
+    cam, tm, _, tun = default_scene(w, h)
+    ref = oracle_mod.cloud(cam, tm, tun, noise, w, h, full=True)
+    with make_renderer(api, noise, w, h, storage=api.STORAGE_F16_EMULATE) as r:
+        r.set_camera(cam); r.set_time(tm)
+        r.dispatch_cloud_full()
+        hdr = r.read_image(api.IMAGE_CLOUD_CUR)
+    want = ref["hdr"].astype(np.float16).astype(np.float32)  # R16G16B16A16_SFLOAT store (Renderer.cpp:1431)
+    finite = np.isfinite(want)
+    assert np.array_equal(hdr.astype(np.float16).astype(np.float32), hdr)  # every stored value is a binary16 value
+    assert rel_err(hdr[finite], want[finite]).max() <= 2e-3               # at most one binary16 ulp apart
+
+
+def test_error_paths(api, noise):
+    with api.CloudRenderer(64, 36) as r:
+        with pytest.raises(api.MeteorosError) as e:
+            r.dispatch_cloud()            # no uniforms yet
+        assert e.value.status == 5
+        cam, tm, _, tun = default_scene(64, 36)
+        r.set_camera(cam); r.set_time(tm)
+        with pytest.raises(api.MeteorosError) as e:
+            r.dispatch_cloud()            # no textures yet
+        assert e.value.status == 5 and "textures" in str(e.value)
+        with pytest.raises(api.MeteorosError):
+            r.upload_texture_3d(api.TEX_LOW_FREQ, np.zeros((3, 3, 3, 4), np.uint8))  # not a power of two
+        with pytest.raises(api.MeteorosError):
+            r.upload_texture_3d(api.TEX_CURL, np.zeros((4, 4, 4, 4), np.uint8))      # wrong slot kind
+        bad = tm.copy()
+        bad["frameCountMod16"] = 16
+        with pytest.raises(api.MeteorosError):
+            r.set_time(bad)
+        with pytest.raises(api.MeteorosError):
+            r.dispatch_cloud_tiles(12, 0, 4, 1)
+        r.upload_noise(noise)
+        r.dispatch_cloud()
+        r.synchronize()
+        assert r.launch_count() >= 1
+
+
+def test_resize(api, oracle_mod, noise):
+    cam, tm, _, tun = default_scene(96, 54)
+    with make_renderer(api, noise, 64, 36) as r:
+        r._check(r._lib.mtResize(r._h, 96, 54), "mtResize")
+        r.width, r.height = 96, 54
+        r.set_camera(cam); r.set_time(tm)
+        r.dispatch_cloud_full()
+        hdr = r.read_image(api.IMAGE_CLOUD_CUR)
+    check_hdr(hdr, oracle_mod.cloud(cam, tm, tun, noise, 96, 54, full=True)["hdr"])
+
+
+def test_full_size_properties_4k(api, noise):
+    """BASELINE config 3 size (3840x2160), checked through size-independent properties: determinism, the union of
+    the sixteen 1/16 dispatches equals the full dispatch bit for bit, row shards equal the full frame, counters obey
+    their identities, and a band of rows matches the oracle."""
+    w, h = 3840, 2160
+    cam, tm, _, tun = default_scene(w, h)
+    with make_renderer(api, noise, w, h, flags=api.FLAG_COUNTERS) as r:
+        r.set_camera(cam); r.set_time(tm)
+        r.dispatch_cloud_full()
+        a = r.read_image(api.IMAGE_CLOUD_CUR)
+        am = r.read_image(api.IMAGE_GODRAY_MASK)
+        c = r.counters()
+        assert c["rays"] == w * h
+        assert c["steps"] >= 35 * (c["rays_marched"] - c["early_exits"]) and c["steps"] <= 60 * c["rays_marched"]
+        assert c["steps_incloud"] <= c["steps"] and c["cone_hits"] <= 6 * c["steps_incloud"]
+        assert 0.40 < c["rays_marched"] / c["rays"] < 0.46
+        assert np.isfinite(a).all() and (a[..., 3] == 1.0).all()
+        r.clear_images()
+        r.dispatch_cloud_full()
+        assert np.array_equal(r.read_image(api.IMAGE_CLOUD_CUR), a)  # deterministic
+        r.clear_images()
+        t = tm.copy()
+        for fid in range(16):
+            t["frameCountMod16"] = fid
+            r.set_time(t)
+            r.dispatch_cloud()
+        assert np.array_equal(r.read_image(api.IMAGE_CLOUD_CUR), a)
+        assert np.array_equal(r.read_image(api.IMAGE_GODRAY_MASK), am)
+        r.set_time(tm)
+        r.clear_images()
+        n = (h + 31) // 32
+        for rank in range(8):
+            r.dispatch_cloud_tiles(32, rank, n, 8)
+        assert np.array_equal(r.read_image(api.IMAGE_CLOUD_CUR), a)
+    import oracle
+
+    rows = (700, 716)  # a band in the marched half
+    ref = oracle.cloud(cam, tm, tun, noise, w, h, full=True, rows=rows)
+    check_hdr(a[rows[0]:rows[1]], ref["hdr"][rows[0]:rows[1]])
+    assert np.array_equal(am[rows[0]:rows[1]], ref["mask"][rows[0]:rows[1]])
+
+
+def test_committed_golden_frame(api, noise):
+    """The CUDA path against the committed golden (tests/golden/cloud_64x36.npz, oracle-generated)."""
+    import pathlib
+
+    g = np.load(pathlib.Path(__file__).parent / "golden" / "cloud_64x36.npz")
+    w, h = 64, 36
+    cam, tm, _, tun = default_scene(w, h, frame_id=int(g["frame_id"]), total_time=float(g["total_time"]), yaw=float(g["yaw"]))
+    with make_renderer(api, noise, w, h) as r:
+        r.set_camera(cam); r.set_time(tm)
+        dbg = r.dispatch_cloud_debug(True)
+        hdr = r.read_image(api.IMAGE_CLOUD_CUR)
+        mask = r.read_image(api.IMAGE_GODRAY_MASK)
+    assert np.array_equal(dbg["steps"], g["steps"]) and np.array_equal(dbg["jitter_hash"], g["jitter_hash"])
+    assert np.array_equal(dbg["accum"], g["accum"]) and np.array_equal(mask, g["mask"])
+    check_hdr(hdr, g["hdr"])

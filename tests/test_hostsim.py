@@ -1,0 +1,86 @@
+"""The kernels' per-pixel cores (meteoros_b200/csrc/*_core.cuh), compiled for the host, against the oracle.
+
+The CUDA kernels restructure the shader (hoisted frame constants, one shared erosion fetch for the six cone
+samples, scalar radiance, channel-specialised filters).  This checks on CPU that none of that changes a single
+bit of any decision-carrying value; the -m gpu tests then check the same through the real kernels."""
+import numpy as np
+import pytest
+
+from conftest import default_scene
+from tests_hostsim_loader import hostsim  # noqa: F401  (see tests_hostsim_loader.py)
+
+
+@pytest.mark.parametrize("w,h,full,fid,yaw,pitch,t", [
+    (96, 54, True, 1, 0.0, 0.0, 0.016),
+    (130, 70, True, 7, 12.0, 3.0, 41.5),      # grid quirk: columns 128,129 never marched
+    (200, 112, False, 14, -30.0, 8.0, 3.25),
+    (64, 36, False, 0, 0.0, -4.0, 0.0),
+])
+def test_cloud_core_bit_identical(oracle_mod, noise, hostsim, w, h, full, fid, yaw, pitch, t):
+    cam, tm, _, tun = default_scene(w, h, frame_id=fid, total_time=t, yaw=yaw, pitch=pitch)
+    ref = oracle_mod.cloud(cam, tm, tun, noise, w, h, full=full, counters=True, debug=True)
+    hdr, mask, cnt, dbg = hostsim.cloud(cam, tm, tun, noise, w, h, full, oracle_mod.RAY_DEBUG_DTYPE)
+    assert cnt == ref["counters"]
+    for f in oracle_mod.RAY_DEBUG_DTYPE.names:
+        assert np.array_equal(dbg[f], ref["debug"][f]), f
+    assert np.array_equal(mask, ref["mask"])
+    assert np.array_equal(hdr, ref["hdr"])
+
+
+def test_cloud_core_tuning_sweep(oracle_mod, noise, hostsim):
+    from meteoros_b200 import scene
+
+    w, h = 80, 45
+    cam, tm, _, tun = default_scene(w, h, frame_id=5, total_time=10.0)
+    for cov, elev in ((0.3, 5.0), (0.9, 85.0), (0.45, 30.0)):
+        tun["coverage"] = cov
+        tun["sun_location"] = scene.sun_on_elevation_circle(elev)
+        ref = oracle_mod.cloud(cam, tm, tun, noise, w, h, full=True, debug=True)
+        hdr, mask, _, dbg = hostsim.cloud(cam, tm, tun, noise, w, h, True, oracle_mod.RAY_DEBUG_DTYPE)
+        assert np.array_equal(dbg["accum"], ref["debug"]["accum"])
+        assert np.array_equal(hdr, ref["hdr"]) and np.array_equal(mask, ref["mask"])
+
+
+def test_post_cores_bit_identical(oracle_mod, hostsim):
+    from meteoros_b200 import scene
+
+    w, h = 160, 90
+    rng = np.random.default_rng(3)
+    prev = rng.random((h, w, 4), dtype=np.float32)
+    cam = scene.Camera(w, h)
+    old = cam.ubo()
+    cam.rotate_about_up(0.25)
+    cam.rotate_about_right(-0.5)
+    new = cam.ubo()
+    sc = scene.Scene()
+    for fid in (1, 8, 15):
+        sc.time["frameCountMod16"] = fid
+        cur, taps = oracle_mod.reproject(new, old, sc.ubo(), prev, taps=True)
+        cur2, taps2 = hostsim.reproject(new, old, sc.ubo(), prev)
+        assert np.array_equal(taps, taps2) and np.array_equal(cur, cur2)
+    mask = rng.random((h, w, 4), dtype=np.float32)
+    hdr = rng.random((h, w, 4), dtype=np.float32)
+    sky = scene.Sky().ubo()
+    for cu in (old, new):
+        assert np.array_equal(oracle_mod.godrays(cu, sky, mask, hdr), hostsim.godrays(cu, sky["lightColor"][:3], mask, hdr))
+    sc.time["time"][1] = 77.7
+    hdr[0, 0] = 0.0
+    hdr[0, 1] = (1e4, 1e-8, -1.0, 1.0)
+    assert np.array_equal(oracle_mod.tonemap(sc.ubo(), hdr * 4), hostsim.tonemap(sc.ubo(), hdr * 4))
+
+
+def test_static_camera_reprojects_onto_itself(oracle_mod):
+    """reprojection.comp does not flip v (:200-201) yet lands on (nearly) the same pixel when the camera is static:
+    the ten taps stay within two texels of the pixel."""
+    from meteoros_b200 import scene
+
+    w, h = 128, 72
+    cam = scene.Camera(w, h).ubo()
+    sc = scene.Scene()
+    sc.update_time(1 / 60)
+    _, taps = oracle_mod.reproject(cam, cam, sc.ubo(), np.zeros((h, w, 4), np.float32), taps=True)
+    ys, xs = np.divmod(taps, w)
+    dy = np.abs(ys - np.arange(h)[:, None, None])
+    dx = np.abs(xs - np.arange(w)[None, :, None])
+    assert dx.max() <= 2 and dy.max() <= 2
+    assert (taps >= 0).all() and (taps < w * h).all()
