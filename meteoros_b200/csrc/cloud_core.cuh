@@ -41,6 +41,23 @@ MT_DEVICE void cloud_frame_setup(const CamU& cam, const TimeU& tm, const MtTunin
     m.windSkew = ((wind + mk3(0.0f, 0.1f, 0.0f)) * tun.cloud_speed) * tm.time[1];
 }
 
+// The two Halton look-ups of the shader (getJitterOffset, cloudRayMarch.comp:114-132) have only eight distinct
+// results per frame each; tabulate them so that the march loop does no division and no divergent constant fetch.
+MT_DEVICE void cloud_frame_jitter(const TimeU& tm, int W, int H, MarchConst& m)
+{
+    for (int hj = 0; hj < 8; ++hj) {
+        int hx = hj < 4 ? hj : hj + 4;  // haltonSeq1/2 for index < 4, haltonSeq3/4 otherwise
+        float x = tm.halton[hx], y = tm.halton[hx + 4];
+        m.rayJitter[hj][0] = x / (float)W;
+        m.rayJitter[hj][1] = y / (float)H;
+        float sx = x / 75.0f, sy = y / 75.0f;
+        m.stepJitter[hj][0] = sx;
+        m.stepJitter[hj][1] = (sx + sy) * 1.180f;
+        m.stepJitter[hj][2] = sy;
+        m.stepJitter[hj][3] = 0.0f;
+    }
+}
+
 MT_DEVICE float hg_phase(float cosa, float g)
 {
     float num = 1.0f - g * g;
@@ -52,8 +69,11 @@ MT_DEVICE float hg_phase(float cosa, float g)
 MT_DEVICE f3 sky_color(const SkyConst& S, f3 dir)
 {
     const float PI_F = 3.14159265f;
-    float zenith = acosf(fmaxf(0.0f, dir.y));
-    float inverse = 1.0f / (cosf(zenith) + 0.15f * MT_POWF(93.885f - ((zenith * 180.0f) / PI_F), -1.253f));
+    // cos(acos(x)) == x up to 1 ulp: the shader's cos(zenith) is evaluated as x itself (radiance-only term; this
+    // also keeps cosf's Payne-Hanek slow path, and its local-memory scratch, out of the kernel)
+    const float cosZenith = fmaxf(0.0f, dir.y);
+    float zenith = acosf(cosZenith);
+    float inverse = 1.0f / (cosZenith + 0.15f * MT_POWF(93.885f - ((zenith * 180.0f) / PI_F), -1.253f));
     float sR = 8.4E3f * inverse;
     float sM = 1.25E3f * inverse;
     float fex[3], col[3];
@@ -81,12 +101,19 @@ MT_DEVICE f3 sky_color(const SkyConst& S, f3 dir)
 // sampleLowFrequency (cloudRayMarch.comp:499-540): base cloud density with coverage applied.
 MT_DEVICE float low_freq_density(const Tex3D& low, float coverage, f3 p)
 {
-    Rgba n = tex3d_rgba(low, p.x, p.y, p.z);
+    LinAxis X = lin_axis_repeat(p.x, low.w), Y = lin_axis_repeat(p.y, low.h), Z = lin_axis_repeat(p.z, low.d);
+    // provably empty filter cell: the result is exactly +0.  A warp whose lanes all sit in empty cells skips the
+    // whole fetch + filter (SIMT: the branch is free when nobody takes it).
+    if (low.occ && !occ_cell_may_be_cloud(low, X.i0, Y.i0, Z.i0)) return 0.0f;
+    Rgba n = tex3d_rgba_axes(low, X, Y, Z);
     float fbm = sat1((n.g * 0.625f + n.b * 0.25f) + n.a * 0.125f);
     float omin = fbm - 0.9f;
     float base = sat1((n.r - omin) / (1.0f - omin));  // remapClamped(r, fbm-.9, 1, 0, 1)
-    float v = clamp1(base, coverage, 1.0f);           // remapClampedBeforeAndAfter(base, cov, 1, 0, 1)
-    float b = sat1((v - coverage) / (1.0f - coverage));
+    // remapClampedBeforeAndAfter(base, cov, 1, 0, 1) * cov.  base <= cov clamps to cov and yields exactly +0; returning
+    // it here also keeps 0/(1-cov) away from the IEEE division's zero-dividend slow path (85 % of its calls in the
+    // first profile).
+    if (!(base > coverage)) return 0.0f;
+    float b = sat1((base - coverage) / (1.0f - coverage));
     return b * coverage;
 }
 
@@ -133,10 +160,7 @@ MT_DEVICE void cloud_ray(const CloudParams& P, const MarchConst& M, int px, int 
     // ---- castRay (:194-226) ----
     float u = (float)px / (float)P.W;
     float v = 1.0f - (float)py / (float)P.H;
-    int hj = pixelID >> 1;  // getJitterOffset: halton[hj] / halton[4 + hj] for hj < 4, else [8 + hj-4] / [12 + hj-4]
-    int hx = hj < 4 ? hj : hj + 4;
-    float jx = P.tm.halton[hx] / (float)P.W;
-    float jy = P.tm.halton[hx + 4] / (float)P.H;
+    const float jx = M.rayJitter[pixelID >> 1][0], jy = M.rayJitter[pixelID >> 1][1];
     RayBasis B;
     B.right = M.basisRight; B.up = M.basisUp; B.look = M.basisLook;
     const f3 origin = M.eyePos;
@@ -188,16 +212,15 @@ MT_DEVICE void cloud_ray(const CloudParams& P, const MarchConst& M, int px, int 
 
     for (float t = hin.t; t < hout.t && iters < MT_MAX_MARCH_ITERS; t += stepSize, ++iters) {
         int jidx = (pixelID + mt_f2i(t)) & 15;  // int(mod(float(pixelID + int(t)), 16.0)), argument >= 0
-        int hs = jidx >> 1;
-        int hi = hs < 4 ? hs : hs + 4;
-        float sx = P.tm.halton[hi] / 75.0f, sy = P.tm.halton[hi + 4] / 75.0f;
-        f3 jdir = dir + mk3(sx, (sx + sy) * 1.180f, sy);
+        const float* sj = M.stepJitter[jidx >> 1];
+        f3 jdir = dir + mk3(sj[0], sj[1], sj[2]);
         f3 pos = origin + jdir * t;
-        f3 sp = ((pos - relOrigin) / MT_THICKNESS) / 8.0f;
+        f3 rp = pos - relOrigin;
+        f3 sp = mk3(div_thickness(rp.x) * 0.125f, div_thickness(rp.y) * 0.125f, div_thickness(rp.z) * 0.125f);  // /12500, /8
         // getRelativeHeightInAtmosphere (:171-186)
         float lenFromCam = len3(pos - origin);
         float cosTheta = dot3(dir, norm3(pos - ec));
-        float h = fabsf(cosTheta * (lenFromCam - lenToInner)) / MT_THICKNESS;
+        float h = div_thickness(fabsf(cosTheta * (lenFromCam - lenToInner)));
         // skewSamplePointWithWind (:489-497)
         f3 skew = (sp + ((wind * h) * P.tun.cloud_top_offset) * 0.009f) + M.windSkew;
         float baseDensity = low_freq_density(P.low, coverage, skew) * P.tun.base_density_factor;
@@ -209,10 +232,11 @@ MT_DEVICE void cloud_ray(const CloudParams& P, const MarchConst& M, int px, int 
             float edge = erosion_edge(P.curl, P.high, skew, h);
             accum += erode(baseDensity * 1.4f, edge) * 0.5f;
             float dl = 0.0f;
-#pragma unroll
-            for (int i = 0; i < 6; ++i) {
+#pragma unroll 1
+            for (int i = 0; i < 6; ++i) {  // one copy of the filter in the instruction stream (I-cache)
                 f3 lp = pos + (M.coneStep[i] * stepSize) * (float)i;
-                f3 sl = (lp - relOrigin) / MT_THICKNESS;
+                f3 lr = lp - relOrigin;
+                f3 sl = mk3(div_thickness(lr.x), div_thickness(lr.y), div_thickness(lr.z));
                 float cur = low_freq_density(P.low, coverage, sl);
                 if (cur > 0.0f) {
                     if (COUNT) cnt.cone++;

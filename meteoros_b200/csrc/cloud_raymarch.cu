@@ -12,11 +12,42 @@
 #include "cloud_core.cuh"
 #include "mt_launch.h"
 
-__global__ void cloud_setup_kernel(CamU cam, TimeU tm, MtTuning tun, MarchConst* out)
+__global__ void cloud_setup_kernel(CamU cam, TimeU tm, MtTuning tun, int W, int H, MarchConst* out)
 {
     MarchConst m;
     cloud_frame_setup(cam, tm, tun, m);
+    cloud_frame_jitter(tm, W, H, m);
     *out = m;
+}
+
+// One thread per 32 cells (one output word): bit x of the word = any of the cell's eight corner texels may carry cloud.
+__global__ void __launch_bounds__(256) occupancy_build_kernel(Tex3D T, uint32_t* occ, float coverage)
+{
+    const unsigned wpr = (unsigned)T.w >> 5;
+    const unsigned nwords = wpr * (unsigned)T.h * (unsigned)T.d;
+    const unsigned wi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (wi >= nwords) return;
+    const unsigned xw = wi % wpr, y = (wi / wpr) % (unsigned)T.h, z = wi / (wpr * (unsigned)T.h);
+    const unsigned y1 = (y + 1u) & (unsigned)(T.h - 1), z1 = (z + 1u) & (unsigned)(T.d - 1);
+    const unsigned rows[4] = { (z * T.h + y) * T.w, (z * T.h + y1) * T.w, (z1 * T.h + y) * T.w, (z1 * T.h + y1) * T.w };
+    uint32_t bits = 0;
+    for (unsigned k = 0; k < 32; ++k) {
+        const unsigned x = xw * 32u + k, x1 = (x + 1u) & (unsigned)(T.w - 1);
+        bool any = false;
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            any = any || occ_texel_may_be_cloud(__ldg(T.texels + rows[r] + x), coverage) ||
+                  occ_texel_may_be_cloud(__ldg(T.texels + rows[r] + x1), coverage);
+        bits |= (any ? 1u : 0u) << k;
+    }
+    occ[wi] = bits;
+}
+
+cudaError_t mt_launch_occupancy(const Tex3D& low, uint32_t* occ, float coverage, cudaStream_t stream)
+{
+    const unsigned nwords = (unsigned)(low.w >> 5) * (unsigned)low.h * (unsigned)low.d;
+    occupancy_build_kernel<<<(nwords + 255) / 256, 256, 0, stream>>>(low, occ, coverage);
+    return cudaGetLastError();
 }
 
 __device__ __forceinline__ float f16_round(float x) { return __half2float(__float2half_rn(x)); }
@@ -46,9 +77,14 @@ __global__ void __launch_bounds__(128) cloud_raymarch_kernel(const __grid_consta
         valid = gx < P.tx && gy < P.ty && px < P.W && py < P.H; // imageStore outside the image is dropped
     }
 
+    // stage the per-frame constants: read as warp-uniform (broadcast) or 8-way indexed LDS from here on
+    __shared__ MarchConst M;
+    if (threadIdx.x < MT_MARCHCONST_WORDS)
+        reinterpret_cast<float*>(&M)[threadIdx.x] = __ldg(reinterpret_cast<const float*>(P.mc) + threadIdx.x);
+    __syncthreads();
+
     RayCounters cnt = { 0u, 0u, 0u, 0u, 0u, 0u };
     if (valid) {
-        const MarchConst M = *P.mc;
         F4 hdr, mask;
         const size_t idx = (size_t)py * (size_t)P.W + (size_t)px;
         cloud_ray<COUNT, DEBUG>(P, M, px, py, pixelID, hdr, mask, cnt, DEBUG ? (P.debug + idx) : nullptr);
@@ -73,7 +109,7 @@ __global__ void __launch_bounds__(128) cloud_raymarch_kernel(const __grid_consta
 
 cudaError_t mt_launch_cloud_setup(const CloudParams& P, MarchConst* out, cudaStream_t stream)
 {
-    cloud_setup_kernel<<<1, 1, 0, stream>>>(P.cam, P.tm, P.tun, out);
+    cloud_setup_kernel<<<1, 1, 0, stream>>>(P.cam, P.tm, P.tun, P.W, P.H, out);
     return cudaGetLastError();
 }
 

@@ -29,6 +29,8 @@ struct MtContext {
     uint32_t* tex[4] = { nullptr, nullptr, nullptr, nullptr };
     int texw[4] = { 0, 0, 0, 0 }, texh[4] = { 0, 0, 0, 0 }, texd[4] = { 0, 0, 0, 0 };
     MarchConst* mc = nullptr;
+    uint32_t* occ = nullptr;      // empty-cell bitmap of the low-frequency volume (mt_tex.cuh)
+    float occCoverage = -1.0f;    // coverage the bitmap was built for; < 0 = stale
     unsigned long long* counters = nullptr;
     MtRayDebug* debug = nullptr;  // lazily allocated W*H records
     int* taps = nullptr;          // lazily allocated W*H*10
@@ -193,6 +195,7 @@ void mtDestroy(MtContext* c)
     free_images(c);
     for (int i = 0; i < 4; ++i) cudaFree(c->tex[i]);
     cudaFree(c->mc);
+    cudaFree(c->occ);
     cudaFree(c->counters);
     cudaFree(c->flushBuf);
     for (int p = 0; p < MT_PASS_COUNT; ++p) {
@@ -283,6 +286,12 @@ static MtStatus upload(MtContext* c, int slot, uint32_t w, uint32_t h, uint32_t 
     MT_CUDA(c, cudaMemcpyAsync(c->tex[slot], rgba8, bytes, cudaMemcpyHostToDevice, c->stream));
     MT_CUDA(c, cudaStreamSynchronize(c->stream));  // the caller may free its buffer on return
     c->texw[slot] = (int)w; c->texh[slot] = (int)h; c->texd[slot] = (int)d;
+    if (slot == MT_TEX_LOW_FREQ) {
+        cudaFree(c->occ);
+        c->occ = nullptr;
+        c->occCoverage = -1.0f;
+        if (w >= 32) MT_CUDA(c, cudaMalloc((void**)&c->occ, (size_t)(w / 32) * h * d * sizeof(uint32_t)));
+    }
     return MT_OK;
 }
 MtStatus mtUploadTexture3D(MtContext* c, MtTextureSlot slot, uint32_t w, uint32_t h, uint32_t d, const uint8_t* rgba8)
@@ -340,6 +349,16 @@ static MtStatus cloud_dispatch(MtContext* c, int full, const RowTiles* tiles, bo
     P.high.w = c->texw[MT_TEX_HIGH_FREQ]; P.high.h = c->texh[MT_TEX_HIGH_FREQ]; P.high.d = c->texd[MT_TEX_HIGH_FREQ];
     P.curl.texels = c->tex[MT_TEX_CURL];
     P.curl.w = c->texw[MT_TEX_CURL]; P.curl.h = c->texh[MT_TEX_CURL];
+    P.low.occ = nullptr;
+    P.high.occ = nullptr;
+    if (c->occ) {  // (re)build the empty-cell bitmap when the volume or the coverage changed
+        if (c->occCoverage != c->tun.coverage) {
+            MT_CUDA(c, mt_launch_occupancy(P.low, c->occ, c->tun.coverage, c->stream));
+            c->occCoverage = c->tun.coverage;
+            c->launches += 1;
+        }
+        P.low.occ = c->occ;
+    }
     P.mc = c->mc;
     P.hdr = c->outHdr ? c->outHdr : c->hdr[c->cur];
     P.mask = c->outMask ? c->outMask : c->mask;

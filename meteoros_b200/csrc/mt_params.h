@@ -21,16 +21,19 @@ struct SkyConst {
 };
 
 // Per-frame constants of the march that feed discrete decisions; computed on the device by cloud_setup_kernel
-// with the canonical operation order (cloudRayMarch.comp:585-624).
+// with the canonical operation order (cloudRayMarch.comp:114-132, 199-207, 585-624, 489-497), then staged in
+// shared memory by every CTA of the march kernel (broadcast LDS instead of registers).
 struct MarchConst {
     f3 basisRight, basisUp, basisLook;  // castRay basis
     f3 eyePos;                          // -camera.eye
     f3 earthCenter;                     // (eye.x, -R, eye.z)
     f3 lightDir;                        // normalize(SUN_LOCATION - origin)
+    f3 windSkew;                        // ((WIND_DIRECTION + (0,.1,0)) * CLOUD_SPEED) * time.y
     f3 coneStep[6];                     // noise_kernel[i] (unscaled)
-    f3 windSkew;                        // (WIND_DIRECTION * h * CLOUD_TOP_OFFSET * 0.009) is per-step; this holds
-                                        // ((WIND_DIRECTION + (0,.1,0)) * CLOUD_SPEED) * time.y
+    float rayJitter[8][2];              // getJitterOffset(id, dim): (halton_x / W, halton_y / H) for id/2 = 0..7
+    float stepJitter[8][4];             // per-step direction offset (jx, (jx+jy)*1.18, jy, 0), j = halton / 75
 };
+#define MT_MARCHCONST_WORDS (sizeof(MarchConst) / 4)
 
 struct RowTiles {  // which pixel rows this launch covers (multi-GPU row-tile shards); default = whole image
     int tile_rows;    // rows per tile (multiple of the block height)

@@ -11,11 +11,15 @@
 // Texture extents must be powers of two (the reference's are 128^3, 32^3, 128^2, 512^2).
 #pragma once
 
+#include <string.h>
+
 #include "mt_math.cuh"
 
 struct Tex3D {
     const uint32_t* texels;  // packed RGBA8, little endian: r = bits 0..7
     int w, h, d;             // powers of two
+    const uint32_t* occ;     // optional: 1 bit per filter cell (x fastest, 32 cells per word), 0 = the cell's eight
+                             // corner texels all have zero cloud density at the current coverage (see occ_* below)
 };
 struct Tex2D {
     const uint32_t* texels;
@@ -23,7 +27,7 @@ struct Tex2D {
 };
 
 struct LinAxis {
-    int i0, i1;
+    unsigned i0, i1;
     float w0, w1;
 };
 
@@ -31,42 +35,62 @@ MT_DEVICE LinAxis lin_axis_repeat(float s, int n)
 {
     LinAxis a;
     float u = s * (float)n - 0.5f;
-    float fl = floorf(u);
+    int fi = mt_floor2i(u);   // F2I.FLOOR (XU) ...
+    float fl = (float)fi;     // ... and I2FP back (ALU): == floorf(u) for |u| < 2^24, one XU op instead of two
     a.w1 = u - fl;
     a.w0 = 1.0f - a.w1;
-    a.i0 = mt_f2i(fl) & (n - 1);
-    a.i1 = (a.i0 + 1) & (n - 1);
+    a.i0 = (unsigned)fi & (unsigned)(n - 1);
+    a.i1 = (a.i0 + 1u) & (unsigned)(n - 1);
     return a;
 }
 
-#define MT_B0(t) ((float)((t) & 0xffu))
-#define MT_B1(t) ((float)(((t) >> 8) & 0xffu))
-#define MT_B2(t) ((float)(((t) >> 16) & 0xffu))
-#define MT_B3(t) ((float)((t) >> 24))
+// Byte k of a packed texel as the float  c * 2^-133  -- WITHOUT an int->float conversion (I2F runs on the quarter-rate
+// XU pipe and was 66 % of the kernel's critical pipe in the first profile, profiles/r1_cloud_v1.md).  Placing the
+// byte at bits 16..23 of a zero word gives the bit pattern c << 16: for c < 128 a denormal, for c >= 128 exponent
+// field 1 -- and binary32 is linear across that boundary, so the value is exactly c * 2^-133 for all 256 bytes.
+// One PRMT on the ALU pipe.  The filter weights carry the compensating 2^120 (MT_WSCALE, folded into the two z
+// weights) and the final 1/255 carries 2^13; powers of two commute with every rounding as long as nothing leaves
+// the normal range (weights >= 2^-75, sums <= 255), so every result is bit-identical to the oracle's
+// (w * float(c)) chain.  Needs denormal inputs honoured (nvcc default -ftz=false; never --use_fast_math).
+#if defined(MT_HOSTSIM)
+static inline float mt_bits_to_float(uint32_t b) { float f; memcpy(&f, &b, 4); return f; }
+#define MT_B0(t) mt_bits_to_float(((t) & 0xffu) << 16)
+#define MT_B1(t) mt_bits_to_float((((t) >> 8) & 0xffu) << 16)
+#define MT_B2(t) mt_bits_to_float((t) & 0x00ff0000u)
+#define MT_B3(t) mt_bits_to_float(((t) >> 24) << 16)
+#else
+#define MT_B0(t) __uint_as_float(__byte_perm((t), 0u, 0x4044))
+#define MT_B1(t) __uint_as_float(__byte_perm((t), 0u, 0x4144))
+#define MT_B2(t) __uint_as_float((t) & 0x00ff0000u)
+#define MT_B3(t) __uint_as_float(__byte_perm((t), 0u, 0x4344))
+#endif
+#define MT_WSCALE 0x1p120f                          /* on the z weights (or y weights in 2D) */
+#define MT_INV255 ((1.0f / 255.0f) * 8192.0f)       /* 2^13 / 255: undoes 2^-133 * 2^120      */
 
 struct Rgba {
     float r, g, b, a;
 };
 
-MT_DEVICE Rgba tex3d_rgba(const Tex3D& T, float s, float t, float r)
+MT_DEVICE Rgba tex3d_rgba_axes(const Tex3D& T, const LinAxis& X, const LinAxis& Y, const LinAxis& Z)
 {
-    LinAxis X = lin_axis_repeat(s, T.w), Y = lin_axis_repeat(t, T.h), Z = lin_axis_repeat(r, T.d);
-    const uint32_t* p00 = T.texels + (size_t)((Z.i0 * T.h + Y.i0) * T.w);
-    const uint32_t* p01 = T.texels + (size_t)((Z.i0 * T.h + Y.i1) * T.w);
-    const uint32_t* p10 = T.texels + (size_t)((Z.i1 * T.h + Y.i0) * T.w);
-    const uint32_t* p11 = T.texels + (size_t)((Z.i1 * T.h + Y.i1) * T.w);
-    uint32_t t000 = MT_LDG(p00 + X.i0), t001 = MT_LDG(p00 + X.i1);
-    uint32_t t010 = MT_LDG(p01 + X.i0), t011 = MT_LDG(p01 + X.i1);
-    uint32_t t100 = MT_LDG(p10 + X.i0), t101 = MT_LDG(p10 + X.i1);
-    uint32_t t110 = MT_LDG(p11 + X.i0), t111 = MT_LDG(p11 + X.i1);
+    // 32-bit unsigned texel offsets from one uniform base: LDG [R.U32 + UR] addressing, no 64-bit pointer math
+    const unsigned W = (unsigned)T.w, H = (unsigned)T.h;
+    const unsigned r00 = (Z.i0 * H + Y.i0) * W, r01 = (Z.i0 * H + Y.i1) * W;
+    const unsigned r10 = (Z.i1 * H + Y.i0) * W, r11 = (Z.i1 * H + Y.i1) * W;
+    const uint32_t* __restrict__ tx = T.texels;
+    uint32_t t000 = MT_LDG(tx + (r00 + X.i0)), t001 = MT_LDG(tx + (r00 + X.i1));
+    uint32_t t010 = MT_LDG(tx + (r01 + X.i0)), t011 = MT_LDG(tx + (r01 + X.i1));
+    uint32_t t100 = MT_LDG(tx + (r10 + X.i0)), t101 = MT_LDG(tx + (r10 + X.i1));
+    uint32_t t110 = MT_LDG(tx + (r11 + X.i0)), t111 = MT_LDG(tx + (r11 + X.i1));
     float w00 = X.w0 * Y.w0, w01 = X.w1 * Y.w0, w10 = X.w0 * Y.w1, w11 = X.w1 * Y.w1;
-    float w000 = w00 * Z.w0, w001 = w01 * Z.w0, w010 = w10 * Z.w0, w011 = w11 * Z.w0;
-    float w100 = w00 * Z.w1, w101 = w01 * Z.w1, w110 = w10 * Z.w1, w111 = w11 * Z.w1;
+    const float z0 = Z.w0 * MT_WSCALE, z1 = Z.w1 * MT_WSCALE;
+    float w000 = w00 * z0, w001 = w01 * z0, w010 = w10 * z0, w011 = w11 * z0;
+    float w100 = w00 * z1, w101 = w01 * z1, w110 = w10 * z1, w111 = w11 * z1;
     Rgba o;
 #define MT_ACC(B)                                                                                                   \
     fmaf(w111, B(t111), fmaf(w110, B(t110), fmaf(w101, B(t101), fmaf(w100, B(t100),                                  \
          fmaf(w011, B(t011), fmaf(w010, B(t010), fmaf(w001, B(t001), w000 * B(t000))))))))
-    const float inv255 = 1.0f / 255.0f;
+    const float inv255 = MT_INV255;
     o.r = MT_ACC(MT_B0) * inv255;
     o.g = MT_ACC(MT_B1) * inv255;
     o.b = MT_ACC(MT_B2) * inv255;
@@ -75,26 +99,56 @@ MT_DEVICE Rgba tex3d_rgba(const Tex3D& T, float s, float t, float r)
     return o;
 }
 
+MT_DEVICE Rgba tex3d_rgba(const Tex3D& T, float s, float t, float r)
+{
+    LinAxis X = lin_axis_repeat(s, T.w), Y = lin_axis_repeat(t, T.h), Z = lin_axis_repeat(r, T.d);
+    return tex3d_rgba_axes(T, X, Y, Z);
+}
+
+// ---- empty-cell map of the low-frequency volume ----------------------------------------------------------------------
+// A sample has cloud density > 0 iff remapClamped(r, fbm-.9, 1, 0, 1) > coverage (cloudRayMarch.comp:513-537), which
+// in exact arithmetic is the LINEAR condition  L := r - (1-cov)*fbm > 1.9*cov - 0.9  on the filtered channels.  The
+// filtered L is a convex combination of the eight corner texels' L_i, so if every corner has L_i <= threshold the
+// sample's density is exactly 0 and the fetch + filter can be skipped without changing the result.  The test keeps
+// a margin of 1e-4 (fp32 filter / remap error is < 2e-6), so a skipped sample is provably one the full evaluation
+// would have returned +0 for.  One bit per cell, rebuilt whenever the texture or the coverage changes.
+#define MT_OCC_MARGIN 1e-4f
+MT_DEVICE bool occ_texel_may_be_cloud(uint32_t texel, float coverage)
+{
+    float r = (float)(texel & 0xffu), g = (float)((texel >> 8) & 0xffu), b = (float)((texel >> 16) & 0xffu), a = (float)(texel >> 24);
+    float fbm = (g * 0.625f + b * 0.25f + a * 0.125f) * (1.0f / 255.0f);
+    float L = r * (1.0f / 255.0f) - (1.0f - coverage) * fbm;
+    return L > (1.9f * coverage - 0.9f) - MT_OCC_MARGIN;
+}
+MT_DEVICE bool occ_cell_may_be_cloud(const Tex3D& T, unsigned x0, unsigned y0, unsigned z0)
+{
+    const unsigned wpr = (unsigned)T.w >> 5;  // words per row
+    uint32_t word = MT_LDG(T.occ + ((z0 * (unsigned)T.h + y0) * wpr + (x0 >> 5)));
+    return (word >> (x0 & 31u)) & 1u;
+}
+
 // Same filter, only the first three channels (the high-frequency volume's alpha is never read).
 MT_DEVICE Rgba tex3d_rgb(const Tex3D& T, float s, float t, float r)
 {
     LinAxis X = lin_axis_repeat(s, T.w), Y = lin_axis_repeat(t, T.h), Z = lin_axis_repeat(r, T.d);
-    const uint32_t* p00 = T.texels + (size_t)((Z.i0 * T.h + Y.i0) * T.w);
-    const uint32_t* p01 = T.texels + (size_t)((Z.i0 * T.h + Y.i1) * T.w);
-    const uint32_t* p10 = T.texels + (size_t)((Z.i1 * T.h + Y.i0) * T.w);
-    const uint32_t* p11 = T.texels + (size_t)((Z.i1 * T.h + Y.i1) * T.w);
-    uint32_t t000 = MT_LDG(p00 + X.i0), t001 = MT_LDG(p00 + X.i1);
-    uint32_t t010 = MT_LDG(p01 + X.i0), t011 = MT_LDG(p01 + X.i1);
-    uint32_t t100 = MT_LDG(p10 + X.i0), t101 = MT_LDG(p10 + X.i1);
-    uint32_t t110 = MT_LDG(p11 + X.i0), t111 = MT_LDG(p11 + X.i1);
+    // 32-bit unsigned texel offsets from one uniform base: LDG [R.U32 + UR] addressing, no 64-bit pointer math
+    const unsigned W = (unsigned)T.w, H = (unsigned)T.h;
+    const unsigned r00 = (Z.i0 * H + Y.i0) * W, r01 = (Z.i0 * H + Y.i1) * W;
+    const unsigned r10 = (Z.i1 * H + Y.i0) * W, r11 = (Z.i1 * H + Y.i1) * W;
+    const uint32_t* __restrict__ tx = T.texels;
+    uint32_t t000 = MT_LDG(tx + (r00 + X.i0)), t001 = MT_LDG(tx + (r00 + X.i1));
+    uint32_t t010 = MT_LDG(tx + (r01 + X.i0)), t011 = MT_LDG(tx + (r01 + X.i1));
+    uint32_t t100 = MT_LDG(tx + (r10 + X.i0)), t101 = MT_LDG(tx + (r10 + X.i1));
+    uint32_t t110 = MT_LDG(tx + (r11 + X.i0)), t111 = MT_LDG(tx + (r11 + X.i1));
     float w00 = X.w0 * Y.w0, w01 = X.w1 * Y.w0, w10 = X.w0 * Y.w1, w11 = X.w1 * Y.w1;
-    float w000 = w00 * Z.w0, w001 = w01 * Z.w0, w010 = w10 * Z.w0, w011 = w11 * Z.w0;
-    float w100 = w00 * Z.w1, w101 = w01 * Z.w1, w110 = w10 * Z.w1, w111 = w11 * Z.w1;
+    const float z0 = Z.w0 * MT_WSCALE, z1 = Z.w1 * MT_WSCALE;
+    float w000 = w00 * z0, w001 = w01 * z0, w010 = w10 * z0, w011 = w11 * z0;
+    float w100 = w00 * z1, w101 = w01 * z1, w110 = w10 * z1, w111 = w11 * z1;
     Rgba o;
 #define MT_ACC(B)                                                                                                   \
     fmaf(w111, B(t111), fmaf(w110, B(t110), fmaf(w101, B(t101), fmaf(w100, B(t100),                                  \
          fmaf(w011, B(t011), fmaf(w010, B(t010), fmaf(w001, B(t001), w000 * B(t000))))))))
-    const float inv255 = 1.0f / 255.0f;
+    const float inv255 = MT_INV255;
     o.r = MT_ACC(MT_B0) * inv255;
     o.g = MT_ACC(MT_B1) * inv255;
     o.b = MT_ACC(MT_B2) * inv255;
@@ -107,12 +161,14 @@ MT_DEVICE Rgba tex3d_rgb(const Tex3D& T, float s, float t, float r)
 MT_DEVICE void tex2d_rg(const Tex2D& T, float s, float t, float& r, float& g)
 {
     LinAxis X = lin_axis_repeat(s, T.w), Y = lin_axis_repeat(t, T.h);
-    const uint32_t* p0 = T.texels + (size_t)(Y.i0 * T.w);
-    const uint32_t* p1 = T.texels + (size_t)(Y.i1 * T.w);
-    uint32_t t00 = MT_LDG(p0 + X.i0), t01 = MT_LDG(p0 + X.i1);
-    uint32_t t10 = MT_LDG(p1 + X.i0), t11 = MT_LDG(p1 + X.i1);
-    float w00 = X.w0 * Y.w0, w01 = X.w1 * Y.w0, w10 = X.w0 * Y.w1, w11 = X.w1 * Y.w1;
-    const float inv255 = 1.0f / 255.0f;
+    const unsigned W = (unsigned)T.w;
+    const uint32_t* __restrict__ tx = T.texels;
+    uint32_t t00 = MT_LDG(tx + (Y.i0 * W + X.i0)), t01 = MT_LDG(tx + (Y.i0 * W + X.i1));
+    uint32_t t10 = MT_LDG(tx + (Y.i1 * W + X.i0)), t11 = MT_LDG(tx + (Y.i1 * W + X.i1));
+    // 2D: the oracle's weight is wx*wy, so the 2^120 rides on the y weight
+    const float y0 = Y.w0 * MT_WSCALE, y1 = Y.w1 * MT_WSCALE;
+    float w00 = X.w0 * y0, w01 = X.w1 * y0, w10 = X.w0 * y1, w11 = X.w1 * y1;
+    const float inv255 = MT_INV255;
     r = fmaf(w11, MT_B0(t11), fmaf(w10, MT_B0(t10), fmaf(w01, MT_B0(t01), w00 * MT_B0(t00)))) * inv255;
     g = fmaf(w11, MT_B1(t11), fmaf(w10, MT_B1(t10), fmaf(w01, MT_B1(t01), w00 * MT_B1(t00)))) * inv255;
 }

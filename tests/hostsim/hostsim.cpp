@@ -7,6 +7,7 @@
 #define MT_HOSTSIM 1
 #include <algorithm>
 #include <cstring>
+#include <vector>
 using std::max;
 using std::min;
 
@@ -29,12 +30,32 @@ int hs_cloud(const MtCameraUBO* cam, const MtTimeUBO* tm, const MtTuning* tun, c
     P.low.texels = (const uint32_t*)low; P.low.w = lw; P.low.h = lh; P.low.d = ld;
     P.high.texels = (const uint32_t*)high; P.high.w = hw; P.high.h = hh; P.high.d = hd;
     P.curl.texels = (const uint32_t*)curl; P.curl.w = cw; P.curl.h = ch;
+    // empty-cell bitmap, built exactly like occupancy_build_kernel does
+    std::vector<uint32_t> occ;
+    if (lw >= 32) {
+        const unsigned wpr = (unsigned)lw >> 5;
+        occ.assign((size_t)wpr * lh * ld, 0u);
+        for (unsigned z = 0; z < (unsigned)ld; ++z)
+            for (unsigned y = 0; y < (unsigned)lh; ++y)
+                for (unsigned x = 0; x < (unsigned)lw; ++x) {
+                    bool any = false;
+                    for (unsigned dz = 0; dz < 2; ++dz)
+                        for (unsigned dy = 0; dy < 2; ++dy)
+                            for (unsigned dx = 0; dx < 2; ++dx) {
+                                unsigned xx = (x + dx) & (lw - 1), yy = (y + dy) & (lh - 1), zz = (z + dz) & (ld - 1);
+                                any = any || occ_texel_may_be_cloud(P.low.texels[(zz * lh + yy) * lw + xx], tun->coverage);
+                            }
+                    if (any) occ[(z * lh + y) * wpr + (x >> 5)] |= 1u << (x & 31u);
+                }
+        P.low.occ = occ.data();
+    }
     P.W = W; P.H = H;
     P.tx = (((W / 4) + 31) / 32) * 32;
     P.ty = (((H / 4) + 31) / 32) * 32;
     P.full = full;
     MarchConst M;
     cloud_frame_setup(P.cam, P.tm, P.tun, M);
+    cloud_frame_jitter(P.tm, W, H, M);
     RayCounters cnt = { 0, 0, 0, 0, 0, 0 };
     unsigned long long tot[6] = { 0, 0, 0, 0, 0, 0 };
     const int gw = full ? W : P.tx, gh = full ? H : P.ty;
