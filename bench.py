@@ -9,8 +9,8 @@ reprojection) over one synthetic 3840x2160 frame of the default cloudscape = 8 2
          L2 evicted between steps (mtFlushL2 writes 256 MiB), summed over exactly K steps, max over ranks.
   e2e    the same metric through the public C-ABI call sequence with host buffers: uniforms from host memory in, the
          RGBA32F HDR frame read back into pinned host memory, every step, wall-clock between synchronisations.
-  N > 1  weak scaling, no data-path collective: every rank renders its own 4K view of a sun-elevation / coverage
-         sweep (BASELINE config 5 style); value = N * rays / max-over-ranks time.  `--workload frame8k` instead shards
+  N > 1  weak scaling, no data-path collective: every rank renders its own copy of the 4K frame (independent views,
+         BASELINE config 5 style; --sweep varies sun elevation / coverage per rank); value = N * rays / max-over-ranks time.  `--workload frame8k` instead shards
          ONE 7680x4320 frame by cyclic 32-row tiles with stores straight into GPU 0's image over NVLink (config 4).
   --impl reference   the CPU restatement of the reference shaders (oracle/, OpenMP over all host cores) on a bounded,
          evenly spread sample of the same frame: the reference's own path needs Vulkan + a window.
@@ -175,6 +175,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cloud4k", choices=["cloud4k", "frame8k", "seq1080p"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sweep", action="store_true", help="N>1: rank r renders view r of the sun/coverage sweep")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -205,7 +206,9 @@ def main():
     else:
         w, h, workload = W4K, H4K, "3840x2160 full-quality Cloud pass, all 16 pixel ids, no reprojection (BASELINE config 3)"
 
-    view = rank if (args.workload == "cloud4k" and world > 1) else 0
+    # weak scaling wants identical work per GPU: every rank renders the default view (--sweep gives each rank its own
+    # sun-elevation / coverage view as in BASELINE config 5, whose cost varies with coverage)
+    view = rank if (args.workload == "cloud4k" and world > 1 and args.sweep) else 0
     cam, tm, sky, tun = scene_for_view(view, w, h)
 
     # ---- work accounting (untimed): exact counters of this rank's frame from the counting variant of the kernel

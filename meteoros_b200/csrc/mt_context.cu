@@ -25,6 +25,7 @@ struct MtContext {
     F4* hdr[2] = { nullptr, nullptr };
     int cur = 0;  // index of the image that currently plays "currentFrameResultImage"
     F4* mask = nullptr;
+    float* maskDecoded = nullptr;  // (W+2) x (H+2): scratch of the god-ray pass
     uint32_t* ldr = nullptr;
     uint32_t* tex[4] = { nullptr, nullptr, nullptr, nullptr };
     int texw[4] = { 0, 0, 0, 0 }, texh[4] = { 0, 0, 0, 0 }, texd[4] = { 0, 0, 0, 0 };
@@ -92,7 +93,8 @@ static bool is_pow2(uint32_t v) { return v && !(v & (v - 1)); }
 static void free_images(MtContext* c)
 {
     cudaFree(c->hdr[0]); cudaFree(c->hdr[1]); cudaFree(c->mask); cudaFree(c->ldr);
-    cudaFree(c->debug); cudaFree(c->taps);
+    cudaFree(c->debug); cudaFree(c->taps); cudaFree(c->maskDecoded);
+    c->maskDecoded = nullptr;
     c->hdr[0] = c->hdr[1] = c->mask = nullptr;
     c->ldr = nullptr; c->debug = nullptr; c->taps = nullptr;
 }
@@ -103,6 +105,7 @@ static MtStatus alloc_images(MtContext* c)
     MT_CUDA(c, cudaMalloc((void**)&c->hdr[1], px * 16));
     MT_CUDA(c, cudaMalloc((void**)&c->mask, px * 16));
     MT_CUDA(c, cudaMalloc((void**)&c->ldr, px * 4));
+    MT_CUDA(c, cudaMalloc((void**)&c->maskDecoded, (size_t)(c->W + 2) * (size_t)(c->H + 2) * sizeof(float)));
     MT_CUDA(c, cudaMemsetAsync(c->hdr[0], 0, px * 16, c->stream));
     MT_CUDA(c, cudaMemsetAsync(c->hdr[1], 0, px * 16, c->stream));
     MT_CUDA(c, cudaMemsetAsync(c->mask, 0, px * 16, c->stream));
@@ -476,13 +479,14 @@ MtStatus mtDispatchGodRays(MtContext* c)
     copy_cam(P.cam, c->cam);
     P.lightColor[0] = c->sky.lightColor[0]; P.lightColor[1] = c->sky.lightColor[1]; P.lightColor[2] = c->sky.lightColor[2];
     P.mask = c->mask;
+    P.decoded = c->maskDecoded;
     P.hdr = c->hdr[c->cur];
     P.W = c->W; P.H = c->H;
     P.f16_emulate = c->storage == MT_STORAGE_F16_EMULATE;
     pass_begin(c, MT_PASS_GODRAYS);
     MT_CUDA(c, mt_launch_godrays(P, c->stream));
     pass_end(c, MT_PASS_GODRAYS);
-    c->launches += 1;
+    c->launches += 2;  // mask_decode_kernel + godrays_kernel
     return MT_OK;
 }
 

@@ -74,7 +74,8 @@ struct ReprojParams {
 struct GodRayParams {
     CamU cam;
     float lightColor[3];
-    const F4* mask;
+    const F4* mask;     // encoded god-ray mask (RGBA32F)
+    float* decoded;     // (W+2) x (H+2) floats: the mask decoded per texel, ringed by the sampler's border value
     F4* hdr;
     int W, H;
     int f16_emulate;

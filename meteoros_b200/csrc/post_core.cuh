@@ -68,37 +68,32 @@ MT_DEVICE GodRayFrame godray_frame(const CamU& cam)
     return g;
 }
 
-MT_DEVICE F4 mask_fetch(const F4* mask, int W, int H, int x, int y)
+// dot(texel, 1/bitEnc): postProcess_GodRays.frag:36-43.
+MT_DEVICE float mask_texel_decode(F4 t)
 {
-    F4 t;
-    if (x < 0 || y < 0 || x >= W || y >= H) {  // CLAMP_TO_BORDER, opaque black (Texture2D.cpp:75, Image.cpp:322)
-        t.x = t.y = t.z = 0.0f; t.w = 1.0f;
-        return t;
-    }
-#if defined(MT_HOSTSIM)
-    return mask[(size_t)y * W + x];
-#else
-    float4 v = __ldg(reinterpret_cast<const float4*>(mask) + ((size_t)y * W + x));
-    t.x = v.x; t.y = v.y; t.z = v.z; t.w = v.w;
-    return t;
-#endif
+    return ((t.x * (1.0f / 1.0f) + t.y * (1.0f / 255.0f)) + t.z * (1.0f / 65025.0f)) + t.w * (1.0f / 16581375.0f);
 }
+// CLAMP_TO_BORDER, VK_BORDER_COLOR_INT_OPAQUE_BLACK = (0,0,0,1) (Texture2D.cpp:75, Image.cpp:322): decodes to 1/16581375.
+#define MT_MASK_BORDER_DECODED (((0.0f * (1.0f / 1.0f) + 0.0f * (1.0f / 255.0f)) + 0.0f * (1.0f / 65025.0f)) + 1.0f * (1.0f / 16581375.0f))
 
-// extract32fFromRGBA8f (postProcess_GodRays.frag:39-43): bilinear fetch of the ENCODED channels, then decode.
-MT_DEVICE float mask_decode(const F4* mask, int W, int H, float s, float t)
+// extract32fFromRGBA8f (postProcess_GodRays.frag:39-43).  The shader filters the four ENCODED channels bilinearly and
+// then takes the dot product with 1/bitEnc; both steps are linear, so the kernel decodes each texel once
+// (mask_decode_kernel, 16 B read -> 4 B written per pixel) and filters the decoded scalar: 16 instead of 64 bytes
+// and 4 instead of 16 multiply-adds per tap, 100 taps per pixel.  The two orders agree to rounding (~1e-7 relative on
+// a term that is itself <= 2.5 % of the pixel); no decision depends on it.  `dec` is the (W+2) x (H+2) decoded image
+// whose one-texel ring holds the border value, so the taps need no bounds tests.
+MT_DEVICE float mask_decode(const float* dec, int W, int H, float s, float t)
 {
     float u = s * (float)W - 0.5f, v = t * (float)H - 0.5f;
-    float fu = floorf(u), fv = floorf(v);
-    float ax = u - fu, ay = v - fv;
-    int x0 = mt_f2i(fu), y0 = mt_f2i(fv);
+    int x0 = mt_floor2i(u), y0 = mt_floor2i(v);
+    float ax = u - (float)x0, ay = v - (float)y0;
+    // uv stays inside [0,1] (the march runs from the pixel towards the clamped sun position), so x0 in [-1, W-1]
+    x0 = min(max(x0, -1), W - 1);
+    y0 = min(max(y0, -1), H - 1);
+    const float* p = dec + (size_t)(y0 + 1) * (size_t)(W + 2) + (size_t)(x0 + 1);
+    float a = MT_LDG(p), b = MT_LDG(p + 1), c = MT_LDG(p + (W + 2)), d = MT_LDG(p + (W + 3));
     float w00 = (1.0f - ax) * (1.0f - ay), w01 = ax * (1.0f - ay), w10 = (1.0f - ax) * ay, w11 = ax * ay;
-    F4 a = mask_fetch(mask, W, H, x0, y0), b = mask_fetch(mask, W, H, x0 + 1, y0);
-    F4 c = mask_fetch(mask, W, H, x0, y0 + 1), d = mask_fetch(mask, W, H, x0 + 1, y0 + 1);
-    float r0 = fmaf(w11, d.x, fmaf(w10, c.x, fmaf(w01, b.x, w00 * a.x)));
-    float r1 = fmaf(w11, d.y, fmaf(w10, c.y, fmaf(w01, b.y, w00 * a.y)));
-    float r2 = fmaf(w11, d.z, fmaf(w10, c.z, fmaf(w01, b.z, w00 * a.z)));
-    float r3 = fmaf(w11, d.w, fmaf(w10, c.w, fmaf(w01, b.w, w00 * a.w)));
-    return ((r0 * (1.0f / 1.0f) + r1 * (1.0f / 255.0f)) + r2 * (1.0f / 65025.0f)) + r3 * (1.0f / 16581375.0f);
+    return fmaf(w11, d, fmaf(w10, c, fmaf(w01, b, w00 * a)));
 }
 
 // The radial accumulation of one fragment; returns the colour to ADD to the HDR pixel (already * blend).
@@ -110,7 +105,7 @@ MT_DEVICE F4 godray_pixel(const GodRayParams& P, const GodRayFrame& G, int x, in
     const float dv = ((v - G.suny) / 100.0f) * 1.0f;
     float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f;
     for (int i = 0; i < 100; ++i) {
-        float a = mask_decode(P.mask, P.W, P.H, u, v);
+        float a = mask_decode(P.decoded, P.W, P.H, u, v);
         acc0 += (P.lightColor[0] * a) * (1.0f * 0.001f);
         acc1 += (P.lightColor[1] * a) * (1.0f * 0.001f);
         acc2 += (P.lightColor[2] * a) * (1.0f * 0.001f);

@@ -42,6 +42,22 @@ __global__ void __launch_bounds__(256) reproject_kernel(const __grid_constant__ 
     }
 }
 
+// ---- God-ray mask decode: (W+2) x (H+2) scalar image, ring = border value.  16 B in, 4 B out per pixel. ----------------
+__global__ void __launch_bounds__(256) mask_decode_kernel(const __grid_constant__ GodRayParams P)
+{
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31) - 1;  // -1 .. W
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5) - 1;   // -1 .. H
+    if (x > P.W || y > P.H) return;
+    float d = MT_MASK_BORDER_DECODED;
+    if (x >= 0 && y >= 0 && x < P.W && y < P.H) {
+        float4 v = __ldg(reinterpret_cast<const float4*>(P.mask) + ((size_t)y * P.W + x));
+        F4 t;
+        t.x = v.x; t.y = v.y; t.z = v.z; t.w = v.w;
+        d = mask_texel_decode(t);
+    }
+    P.decoded[(size_t)(y + 1) * (size_t)(P.W + 2) + (size_t)(x + 1)] = d;
+}
+
 // ---- God rays: a warp is an 8x4 pixel tile so the footprint of tap i stays within a few cache lines ---------------
 __global__ void __launch_bounds__(128) godrays_kernel(const __grid_constant__ GodRayParams P)
 {
@@ -82,6 +98,10 @@ cudaError_t mt_launch_reproject(const ReprojParams& P, cudaStream_t stream)
 }
 cudaError_t mt_launch_godrays(const GodRayParams& P, cudaStream_t stream)
 {
+    dim3 dgrid((unsigned)((P.W + 2 + 31) / 32), (unsigned)((P.H + 2 + 7) / 8), 1);
+    mask_decode_kernel<<<dgrid, 256, 0, stream>>>(P);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
     dim3 grid((unsigned)((P.W + 15) / 16), (unsigned)((P.H + 7) / 8), 1);
     godrays_kernel<<<grid, 128, 0, stream>>>(P);
     return cudaGetLastError();

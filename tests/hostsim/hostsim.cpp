@@ -121,6 +121,10 @@ int hs_godrays(const MtCameraUBO* cam, const float* lightColor, int W, int H, co
     P.lightColor[0] = lightColor[0]; P.lightColor[1] = lightColor[1]; P.lightColor[2] = lightColor[2];
     P.mask = (const F4*)mask;
     P.W = W; P.H = H;
+    std::vector<float> dec((size_t)(W + 2) * (H + 2), MT_MASK_BORDER_DECODED);
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) dec[(size_t)(y + 1) * (W + 2) + (x + 1)] = mask_texel_decode(P.mask[(size_t)y * W + x]);
+    P.decoded = dec.data();
     GodRayFrame G = godray_frame(P.cam);
     if (G.blend < 0.0f) return 0;
     for (int y = 0; y < H; ++y)
