@@ -98,6 +98,7 @@ typedef struct MtConfig {
 
 #define MT_FLAG_COUNTERS 1u    /* cloud pass also accumulates MtCounters (slower; for work accounting) */
 #define MT_FLAG_PASS_TIMING 2u /* bracket every pass with CUDA events so mtLastPassMs works               */
+#define MT_FLAG_SEQUENTIAL_MARCH 4u /* 1-of-16 dispatch: one kernel, one thread per ray (default: step-parallel) */
 
 /* Texture slots = set 1 of the cloud pipeline (Renderer.cpp:1110-1114, cloudRayMarch.comp:9-12). */
 typedef enum MtTextureSlot {

@@ -10,7 +10,10 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
-LIB_PATH = Path(__file__).resolve().parent / "libmeteoros_b200.so"
+import os
+
+# METEOROS_B200_LIB: developer override used by tools/ab_bench.sh to A/B kernel variants; normal use loads the in-tree build
+LIB_PATH = Path(os.environ.get("METEOROS_B200_LIB") or (Path(__file__).resolve().parent / "libmeteoros_b200.so"))
 
 c_void_pp = C.POINTER(C.c_void_p)
 

@@ -99,9 +99,10 @@ MT_DEVICE f3 sky_color(const SkyConst& S, f3 dir)
 }
 
 // sampleLowFrequency (cloudRayMarch.comp:499-540): base cloud density with coverage applied.
-MT_DEVICE float low_freq_density(const Tex3D& low, float coverage, f3 p)
+MT_DEVICE float low_freq_density(const Tex3D& low, float coverage, P2 pxy, float pz)
 {
-    LinAxis X = lin_axis_repeat(p.x, low.w), Y = lin_axis_repeat(p.y, low.h), Z = lin_axis_repeat(p.z, low.d);
+    LinAxis X, Y, Z = lin_axis_repeat(pz, low.d);
+    lin_axes_xy(pxy, low.w, low.h, X, Y);
     // provably empty filter cell: the result is exactly +0.  A warp whose lanes all sit in empty cells skips the
     // whole fetch + filter (SIMT: the branch is free when nobody takes it).
     if (low.occ && !occ_cell_may_be_cloud(low, X.i0, Y.i0, Z.i0)) return 0.0f;
@@ -151,13 +152,31 @@ MT_DEVICE void encode_mask(float v, F4& o)
 }
 
 #define MT_MAX_MARCH_ITERS 128  /* maxSteps <= 60; guards degenerate shells (also in the oracle) */
+#define MT_STEP_SLICES 64       /* step-parallel path: slices launched per ray (maxSteps <= 58 + fp slack) */
 
-// One invocation of main().  Returns false when the reference would not have written this pixel.
-template <bool COUNT, bool DEBUG>
-MT_DEVICE void cloud_ray(const CloudParams& P, const MarchConst& M, int px, int py, int pixelID, F4& hdr, F4& mask,
-                         RayCounters& cnt, MtRayDebug* dbg)
+// Everything about one ray that does not change along the march (castRay, the horizon branches, the two shell
+// intersections, the phase function).  64 bytes: also the record the step-parallel path keeps per ray.
+struct RaySetup {
+    f3 dir;
+    float t_in, t_out, stepSize;
+    float lenToInner, cosAngle, phase;
+    f3 bg;           // Preetham sky * max(.62, dir.y)
+    int branch;      // 0 ocean, 1 sky band, 2 march
+    int pad[3];
+};
+
+static_assert(sizeof(RaySetup) == 64, "RaySetup is the 64-byte per-ray record of the step-parallel path");
+
+// One march step's contribution, independent of the steps before it.
+struct StepSample {
+    float inc;     // highFreqDensity * 0.5  (added to accumDensity)
+    float energy;  // GetLightEnergy(...)    (mixed into the transmittance); < 0 marks "baseDensity <= 0"
+};
+
+// castRay + branches (cloudRayMarch.comp:690-753).  For branch 0/1 `hdr` is final; mask is zero.
+MT_DEVICE RaySetup cloud_ray_setup(const CloudParams& P, const MarchConst& M, int px, int py, int pixelID, F4& hdr)
 {
-    // ---- castRay (:194-226) ----
+    RaySetup R;
     float u = (float)px / (float)P.W;
     float v = 1.0f - (float)py / (float)P.H;
     const float jx = M.rayJitter[pixelID >> 1][0], jy = M.rayJitter[pixelID >> 1][1];
@@ -165,106 +184,151 @@ MT_DEVICE void cloud_ray(const CloudParams& P, const MarchConst& M, int px, int 
     B.right = M.basisRight; B.up = M.basisUp; B.look = M.basisLook;
     const f3 origin = M.eyePos;
     const f3 dir = cast_ray_dir(P.cam, B, origin, u, v, jx, jy);
-    if (COUNT) cnt.rays++;
-    if (DEBUG) {
-        dbg->dir[0] = dir.x; dbg->dir[1] = dir.y; dbg->dir[2] = dir.z;
-        dbg->t_in = dbg->t_out = dbg->step_size = dbg->accum = 0.0f;
-        dbg->branch = 0; dbg->steps = 0; dbg->jitter_hash = 0u;
-    }
-
+    R.dir = dir;
+    R.t_in = R.t_out = R.stepSize = R.lenToInner = R.cosAngle = R.phase = 0.0f;
+    R.bg = mk3(0.0f, 0.0f, 0.0f);
+    R.pad[0] = R.pad[1] = R.pad[2] = 0;
     const float dotUp = (0.0f * dir.x + 1.0f * dir.y) + 0.0f * dir.z;
-    mask.x = mask.y = mask.z = mask.w = 0.0f;
     hdr.w = 1.0f;
     if (dotUp < 0.0f) {  // ocean (:718-729)
         float a = -dir.y * 5.5f;
         hdr.x = mix1(0.0f * 0.4f, 0.0f * 0.5f, a);
         hdr.y = mix1(0.16f * 0.4f, 0.73f * 0.5f, a);
         hdr.z = mix1(0.51f * 0.4f, 0.95f * 0.5f, a);
-        return;
+        R.branch = 0;
+        return R;
     }
-    f3 bg = sky_color(P.sky, dir) * fmaxf(0.620f, dotUp);
+    R.bg = sky_color(P.sky, dir) * fmaxf(0.620f, dotUp);
     if (dotUp < 0.06f) {  // sky band below the cloud fade-out (:730-740)
-        hdr.x = bg.x; hdr.y = bg.y; hdr.z = bg.z;
-        if (DEBUG) dbg->branch = 1;
-        return;
+        hdr.x = R.bg.x; hdr.y = R.bg.y; hdr.z = R.bg.z;
+        R.branch = 1;
+        return R;
     }
-
-    // ---- shells (:750-753) ----
+    R.branch = 2;
+    // shells (:750-753) and the per-ray constants of rayMarch (:567-590)
     const f3 ec = M.earthCenter;
     ShellHit hin = ray_shell(origin, dir, ec, MT_R_INNER);
     ShellHit hout = ray_shell(origin, dir, ec, MT_R_OUTER);
-
-    // ---- rayMarch (:565-688) ----
     const float maxSteps = floorf(mix1(35.0f, 60.0f, 1.0f - dotUp));
-    const float stepSize = (hout.t - hin.t) / maxSteps;
-    const float cosAngle = dot3(norm3(dir), M.lightDir);
-    const float phase = fmaxf(hg_phase(cosAngle, 0.6f), 0.7f * hg_phase(cosAngle, 0.99f - 0.1f));
-    const float lenToInner = len3(hin.point - origin);
+    R.t_in = hin.t;
+    R.t_out = hout.t;
+    R.stepSize = (hout.t - hin.t) / maxSteps;
+    R.cosAngle = dot3(norm3(dir), M.lightDir);
+    R.phase = fmaxf(hg_phase(R.cosAngle, 0.6f), 0.7f * hg_phase(R.cosAngle, 0.99f - 0.1f));
+    R.lenToInner = len3(hin.point - origin);
+    return R;
+}
+
+// One iteration of the march loop (cloudRayMarch.comp:629-678) at parameter t, without the running sums.
+template <bool COUNT>
+MT_DEVICE StepSample cloud_step_sample(const CloudParams& P, const MarchConst& M, const RaySetup& R, int jidx, float t,
+                                       RayCounters& cnt)
+{
+    StepSample S;
+    S.inc = 0.0f;
+    S.energy = -1.0f;
+    const f3 origin = M.eyePos, ec = M.earthCenter, dir = R.dir;
     const f3 relOrigin = mk3(ec.x, MT_R_INNER - MT_EARTH_RADIUS, ec.z);
     const f3 wind = mk3(P.tun.wind_direction[0], P.tun.wind_direction[1], P.tun.wind_direction[2]);
     const float coverage = P.tun.coverage;
+    const float* sj = M.stepJitter[jidx >> 1];
+    f3 jdir = dir + mk3(sj[0], sj[1], sj[2]);
+    f3 pos = origin + jdir * t;
+    f3 rp = pos - relOrigin;
+    f3 sp = mk3(div_thickness(rp.x) * 0.125f, div_thickness(rp.y) * 0.125f, div_thickness(rp.z) * 0.125f);  // /12500, /8
+    // getRelativeHeightInAtmosphere (:171-186)
+    float lenFromCam = len3(pos - origin);
+    float cosTheta = dot3(dir, norm3(pos - ec));
+    float h = div_thickness(fabsf(cosTheta * (lenFromCam - R.lenToInner)));
+    // skewSamplePointWithWind (:489-497)
+    f3 skew = (sp + ((wind * h) * P.tun.cloud_top_offset) * 0.009f) + M.windSkew;
+    float baseDensity = low_freq_density(P.low, coverage, pk2(skew.x, skew.y), skew.z) * P.tun.base_density_factor;
+    if (COUNT) cnt.steps++;
+    if (baseDensity > 0.0f) {
+        if (COUNT) cnt.incloud++;
+        float edge = erosion_edge(P.curl, P.high, skew, h);
+        S.inc = erode(baseDensity * 1.4f, edge) * 0.5f;
+        float dl = 0.0f;
+        const P2 posxy = pk2(pos.x, pos.y), relxy = pk2(relOrigin.x, relOrigin.y);
+#pragma unroll 1
+        for (int i = 0; i < 6; ++i) {  // one copy of the filter in the instruction stream (I-cache)
+            // lightPos = pos + (stepSize * noise_kernel[i]) * i ; sample = (lightPos - relOrigin) / 12500  -- x,y as a pair
+            const float fi = (float)i;
+            const f3 cs = M.coneStep[i];
+            P2 lxy = sub2(add2(posxy, mul2(mul2(pk2(cs.x, cs.y), bc2(R.stepSize)), bc2(fi))), relxy);
+            float lz = (pos.z + (cs.z * R.stepSize) * fi) - relOrigin.z;
+            float cur = low_freq_density(P.low, coverage, div_thickness2(lxy), div_thickness(lz));
+            if (cur > 0.0f) {
+                if (COUNT) cnt.cone++;
+                dl += erode(1.5f * cur, edge);
+            }
+        }
+        S.energy = light_energy(h, dl, baseDensity, R.phase, R.cosAngle);
+    }
+    return S;
+}
+
+// Running sums of the march (cloudRayMarch.comp:648, 674-684).  Returns true when the loop must stop.
+MT_DEVICE bool cloud_step_combine(const StepSample& S, float& accum, float& transmittance, float& color)
+{
+    if (S.energy >= 0.0f) {
+        accum += S.inc;
+        transmittance = mix1(transmittance, S.energy, 1.0f - accum);
+        color += transmittance;
+    }
+    if (accum >= 1.0f) {
+        accum = 1.0f;
+        return true;
+    }
+    return false;
+}
+
+// Composite + god-ray mask (cloudRayMarch.comp:759-779).
+MT_DEVICE void cloud_composite(const RaySetup& R, float accum, float color, F4& hdr, F4& mask)
+{
+    float fade = smoothstep1(0.0f, 1.0f, fminf(1.0f, remap1(R.dir.y, 0.06f, 0.2f, 0.0f, 1.0f)));
+    float a = accum * fade;
+    hdr.x = mix1(R.bg.x, color, a);
+    hdr.y = mix1(R.bg.y, color, a);
+    hdr.z = mix1(R.bg.z, color, a);
+    hdr.w = 1.0f;
+    encode_mask(25.0f * fminf(0.05f, 1.0f - accum), mask);
+    if (R.dir.y < 0.05f) {  // unreachable here (dir.y >= 0.06) but part of the shader (:775-779)
+        float k = fmaxf(5.0f, R.dir.y);
+        mask.x *= k; mask.y *= k; mask.z *= k; mask.w *= k;
+    }
+}
+
+// One invocation of main(): setup, the sequential march, composite.
+template <bool COUNT, bool DEBUG>
+MT_DEVICE void cloud_ray(const CloudParams& P, const MarchConst& M, int px, int py, int pixelID, F4& hdr, F4& mask,
+                         RayCounters& cnt, MtRayDebug* dbg)
+{
+    mask.x = mask.y = mask.z = mask.w = 0.0f;
+    const RaySetup R = cloud_ray_setup(P, M, px, py, pixelID, hdr);
+    if (COUNT) cnt.rays++;
+    if (DEBUG) {
+        dbg->dir[0] = R.dir.x; dbg->dir[1] = R.dir.y; dbg->dir[2] = R.dir.z;
+        dbg->t_in = dbg->t_out = dbg->step_size = dbg->accum = 0.0f;
+        dbg->branch = R.branch; dbg->steps = 0; dbg->jitter_hash = 0u;
+    }
+    if (R.branch != 2) return;
 
     float accum = 0.0f, transmittance = 1.0f, color = 0.0f;
     unsigned jhash = 2166136261u;
     int iters = 0;
     if (COUNT) cnt.marched++;
-    if (DEBUG) { dbg->branch = 2; dbg->t_in = hin.t; dbg->t_out = hout.t; dbg->step_size = stepSize; }
-
-    for (float t = hin.t; t < hout.t && iters < MT_MAX_MARCH_ITERS; t += stepSize, ++iters) {
-        int jidx = (pixelID + mt_f2i(t)) & 15;  // int(mod(float(pixelID + int(t)), 16.0)), argument >= 0
-        const float* sj = M.stepJitter[jidx >> 1];
-        f3 jdir = dir + mk3(sj[0], sj[1], sj[2]);
-        f3 pos = origin + jdir * t;
-        f3 rp = pos - relOrigin;
-        f3 sp = mk3(div_thickness(rp.x) * 0.125f, div_thickness(rp.y) * 0.125f, div_thickness(rp.z) * 0.125f);  // /12500, /8
-        // getRelativeHeightInAtmosphere (:171-186)
-        float lenFromCam = len3(pos - origin);
-        float cosTheta = dot3(dir, norm3(pos - ec));
-        float h = div_thickness(fabsf(cosTheta * (lenFromCam - lenToInner)));
-        // skewSamplePointWithWind (:489-497)
-        f3 skew = (sp + ((wind * h) * P.tun.cloud_top_offset) * 0.009f) + M.windSkew;
-        float baseDensity = low_freq_density(P.low, coverage, skew) * P.tun.base_density_factor;
-        if (COUNT) cnt.steps++;
+    if (DEBUG) { dbg->t_in = R.t_in; dbg->t_out = R.t_out; dbg->step_size = R.stepSize; }
+    for (float t = R.t_in; t < R.t_out && iters < MT_MAX_MARCH_ITERS; t += R.stepSize, ++iters) {
+        const int jidx = (pixelID + mt_f2i(t)) & 15;  // int(mod(float(pixelID + int(t)), 16.0)), argument >= 0
         if (DEBUG) jhash = (jhash ^ (unsigned)jidx) * 16777619u;
-
-        if (baseDensity > 0.0f) {
-            if (COUNT) cnt.incloud++;
-            float edge = erosion_edge(P.curl, P.high, skew, h);
-            accum += erode(baseDensity * 1.4f, edge) * 0.5f;
-            float dl = 0.0f;
-#pragma unroll 1
-            for (int i = 0; i < 6; ++i) {  // one copy of the filter in the instruction stream (I-cache)
-                f3 lp = pos + (M.coneStep[i] * stepSize) * (float)i;
-                f3 lr = lp - relOrigin;
-                f3 sl = mk3(div_thickness(lr.x), div_thickness(lr.y), div_thickness(lr.z));
-                float cur = low_freq_density(P.low, coverage, sl);
-                if (cur > 0.0f) {
-                    if (COUNT) cnt.cone++;
-                    dl += erode(1.5f * cur, edge);
-                }
-            }
-            float E = light_energy(h, dl, baseDensity, phase, cosAngle);
-            transmittance = mix1(transmittance, E, 1.0f - accum);
-            color += transmittance;
-        }
-        if (accum >= 1.0f) {
-            accum = 1.0f;
+        const StepSample S = cloud_step_sample<COUNT>(P, M, R, jidx, t, cnt);
+        if (cloud_step_combine(S, accum, transmittance, color)) {
             if (COUNT) cnt.early++;
             ++iters;
             break;
         }
     }
     if (DEBUG) { dbg->steps = iters; dbg->jitter_hash = jhash; dbg->accum = accum; }
-
-    // ---- composite (:759-779) ----
-    float fade = smoothstep1(0.0f, 1.0f, fminf(1.0f, remap1(dir.y, 0.06f, 0.2f, 0.0f, 1.0f)));
-    float a = accum * fade;
-    hdr.x = mix1(bg.x, color, a);
-    hdr.y = mix1(bg.y, color, a);
-    hdr.z = mix1(bg.z, color, a);
-    encode_mask(25.0f * fminf(0.05f, 1.0f - accum), mask);
-    if (dir.y < 0.05f) {  // unreachable here (dir.y >= 0.06) but part of the shader (:775-779)
-        float k = fmaxf(5.0f, dir.y);
-        mask.x *= k; mask.y *= k; mask.z *= k; mask.w *= k;
-    }
+    cloud_composite(R, accum, color, hdr, mask);
 }

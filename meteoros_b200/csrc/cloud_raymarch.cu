@@ -53,24 +53,34 @@ cudaError_t mt_launch_occupancy(const Tex3D& low, uint32_t* occ, float coverage,
 __device__ __forceinline__ float f16_round(float x) { return __half2float(__float2half_rn(x)); }
 
 template <bool FULL, bool COUNT, bool DEBUG>
-__global__ void __launch_bounds__(128) cloud_raymarch_kernel(const __grid_constant__ CloudParams P)
+#ifndef MT_CLOUD_MINBLOCKS
+#define MT_CLOUD_MINBLOCKS 8  /* 64 registers/thread: 8 CTAs = 32 warps per SM (profiles/r1_cloud_ab.md) */
+#endif
+__global__ void __launch_bounds__(128, MT_CLOUD_MINBLOCKS) cloud_raymarch_kernel(const __grid_constant__ CloudParams P)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int lx = ((warp & 1) << 3) + (lane & 7);
-    const int ly = ((warp >> 1) << 2) + (lane >> 3);
-    const int bpt = P.rows.tile_rows >> 3;                      // CTAs per tile, vertically
-    const int ltile = blockIdx.y / bpt;
-    const int tile = P.rows.tile_begin + ltile * P.rows.tile_stride;
-    const int gx = blockIdx.x * 16 + lx;
-    const int gy = tile * P.rows.tile_rows + (blockIdx.y - ltile * bpt) * 8 + ly;
-
     int px, py, pixelID;
     bool valid;
     if (FULL) {
-        px = gx; py = gy;
+        // CTA = 16x8 pixels, warp = 8x4: the two float4 stores of a warp are four 128-byte rows each
+        const int lx = ((warp & 1) << 3) + (lane & 7);
+        const int ly = ((warp >> 1) << 2) + (lane >> 3);
+        const int bpt = P.rows.tile_rows >> 3;                  // CTAs per row tile, vertically
+        const int ltile = blockIdx.y / bpt;
+        const int tile = P.rows.tile_begin + ltile * P.rows.tile_stride;
+        px = blockIdx.x * 16 + lx;
+        py = tile * P.rows.tile_rows + (blockIdx.y - ltile * bpt) * 8 + ly;
         pixelID = ((px & 3) << 2) | (py & 3);                   // id = pX*4 + pY with (pX,pY) = (px%4, py%4)
         valid = px < P.W && py < P.H && (px >> 2) < P.tx && (py >> 2) < P.ty;
     } else {
+        // 1-of-16 dispatch: only (W/4)x(H/4) rays, fewer warps than the GPU has slots, so every CTA is resident from
+        // the start and nothing re-balances.  Warp q of CTA k therefore takes ray tile q*(NT/4)+k: one warp from each
+        // horizontal quarter of the frame (sky .. ocean), which gives every CTA -- hence every SM -- the same mix of
+        // marching and horizon-culled rays.
+        const int tilesX = P.tx >> 3;                           // 8x4-ray tiles per row (tx is a multiple of 32)
+        const int tileIdx = warp * (int)gridDim.x + (int)blockIdx.x;
+        const int tyi = tileIdx / tilesX, txi = tileIdx - tyi * tilesX;
+        const int gx = txi * 8 + (lane & 7), gy = tyi * 4 + (lane >> 3);
         pixelID = P.tm.frameCountMod16;
         px = gx * 4 + (pixelID >> 2);                           // pX = id/4
         py = gy * 4 + (pixelID & 3);                            // pY = id%4
@@ -107,6 +117,115 @@ __global__ void __launch_bounds__(128) cloud_raymarch_kernel(const __grid_consta
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Step-parallel form of the 1-of-16 dispatch.  The reference's real-time frame marches only (W/4)x(H/4) rays: 4 050
+// warps at 1080p for 148 SMs x 64 warp slots, each warp a ~50 000-instruction dependent chain -- the monolithic
+// kernel is latency bound there (0.41 ms, IPC 0.23 per scheduler).  But a march step depends on the steps before it
+// only through three running sums; the sample itself (position, densities, light cone, light energy) needs just t_k,
+// and t_k = t_in + stepSize + ... + stepSize is k additions.  So: (1) one thread per ray does castRay / horizon
+// branches / shells and files a 64-byte record; (2) one thread per (ray, step) recomputes t_k with the same k
+// additions and evaluates the sample -- 64x more parallelism, the same arithmetic; (3) one thread per ray folds the
+// samples in step order (the only sequential part, ~8 instructions per step) and composites.  Every value is produced
+// by the same device functions in the same order as in the monolithic kernel, so the output is bit-identical.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sixteenth_pixel(const CloudParams& P, int& px, int& py, int& pixelID, bool& valid)
+{
+    const int tilesX = P.tx >> 3;  // 8x4-ray tiles; the record / sample index of a ray is its global thread id
+    const int tileIdx = (int)blockIdx.x * 4 + (int)(threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const int tyi = tileIdx / tilesX, txi = tileIdx - tyi * tilesX;
+    const int gx = txi * 8 + (lane & 7), gy = tyi * 4 + (lane >> 3);
+    pixelID = P.tm.frameCountMod16;
+    px = gx * 4 + (pixelID >> 2);
+    py = gy * 4 + (pixelID & 3);
+    valid = gx < P.tx && gy < P.ty && px < P.W && py < P.H;
+}
+
+__device__ __forceinline__ void stage_march_const(MarchConst& M, const MarchConst* src)
+{
+    if (threadIdx.x < MT_MARCHCONST_WORDS)
+        reinterpret_cast<float*>(&M)[threadIdx.x] = __ldg(reinterpret_cast<const float*>(src) + threadIdx.x);
+    __syncthreads();
+}
+
+__device__ __forceinline__ void store_pixel(const CloudParams& P, size_t idx, F4 hdr, F4 mask)
+{
+    if (P.f16_emulate) {
+        hdr.x = f16_round(hdr.x); hdr.y = f16_round(hdr.y); hdr.z = f16_round(hdr.z); hdr.w = f16_round(hdr.w);
+        mask.x = f16_round(mask.x); mask.y = f16_round(mask.y); mask.z = f16_round(mask.z); mask.w = f16_round(mask.w);
+    }
+    reinterpret_cast<float4*>(P.hdr)[idx] = make_float4(hdr.x, hdr.y, hdr.z, hdr.w);
+    reinterpret_cast<float4*>(P.mask)[idx] = make_float4(mask.x, mask.y, mask.z, mask.w);
+}
+
+__global__ void __launch_bounds__(128) cloud_rays_kernel(const __grid_constant__ CloudParams P)
+{
+    __shared__ MarchConst M;
+    stage_march_const(M, P.mc);
+    int px, py, pixelID;
+    bool valid;
+    sixteenth_pixel(P, px, py, pixelID, valid);
+    RaySetup* rec = reinterpret_cast<RaySetup*>(P.rays) + ((size_t)blockIdx.x * 128 + threadIdx.x);
+    if (!valid) {
+        rec->branch = -1;
+        return;
+    }
+    F4 hdr, mask;
+    mask.x = mask.y = mask.z = mask.w = 0.0f;
+    const RaySetup R = cloud_ray_setup(P, M, px, py, pixelID, hdr);
+    *rec = R;
+    if (R.branch != 2) store_pixel(P, (size_t)py * P.W + px, hdr, mask);  // ocean / sky band: final
+}
+
+__global__ void __launch_bounds__(128, MT_CLOUD_MINBLOCKS) cloud_steps_kernel(const __grid_constant__ CloudParams P)
+{
+    __shared__ MarchConst M;
+    stage_march_const(M, P.mc);
+    const size_t ray = (size_t)blockIdx.x * 128 + threadIdx.x;
+    const RaySetup R = reinterpret_cast<const RaySetup*>(P.rays)[ray];
+    if (R.branch != 2) return;
+    const int k = blockIdx.y;
+    float t = R.t_in;
+    for (int i = 0; i < k; ++i) t += R.stepSize;  // the same k roundings the sequential loop performs
+    if (!(t < R.t_out)) return;
+    const int jidx = (P.tm.frameCountMod16 + mt_f2i(t)) & 15;
+    RayCounters none = { 0u, 0u, 0u, 0u, 0u, 0u };
+    const StepSample S = cloud_step_sample<false>(P, M, R, jidx, t, none);
+    P.samples[(size_t)k * ((size_t)gridDim.x * 128) + ray] = make_float2(S.inc, S.energy);
+}
+
+__global__ void __launch_bounds__(128) cloud_fold_kernel(const __grid_constant__ CloudParams P)
+{
+    const size_t ray = (size_t)blockIdx.x * 128 + threadIdx.x;
+    const RaySetup R = reinterpret_cast<const RaySetup*>(P.rays)[ray];
+    if (R.branch != 2) return;
+    int px, py, pixelID;
+    bool valid;
+    sixteenth_pixel(P, px, py, pixelID, valid);
+    const size_t stride = (size_t)gridDim.x * 128;
+    float accum = 0.0f, transmittance = 1.0f, color = 0.0f;
+    int k = 0;
+    for (float t = R.t_in; t < R.t_out && k < MT_STEP_SLICES; t += R.stepSize, ++k) {
+        const float2 v = __ldg(P.samples + (size_t)k * stride + ray);
+        StepSample S;
+        S.inc = v.x; S.energy = v.y;
+        if (cloud_step_combine(S, accum, transmittance, color)) break;
+    }
+    F4 hdr, mask;
+    cloud_composite(R, accum, color, hdr, mask);
+    store_pixel(P, (size_t)py * P.W + px, hdr, mask);
+}
+
+cudaError_t mt_launch_cloud_sixteenth_split(const CloudParams& P, cudaStream_t stream, int* launches)
+{
+    const unsigned ctas = (unsigned)((P.tx / 8) * (P.ty / 4) / 4);  // tx, ty are multiples of 32
+    cloud_rays_kernel<<<ctas, 128, 0, stream>>>(P);
+    cloud_steps_kernel<<<dim3(ctas, MT_STEP_SLICES, 1), 128, 0, stream>>>(P);
+    cloud_fold_kernel<<<ctas, 128, 0, stream>>>(P);
+    *launches = 3;
+    return cudaGetLastError();
+}
+
 cudaError_t mt_launch_cloud_setup(const CloudParams& P, MarchConst* out, cudaStream_t stream)
 {
     cloud_setup_kernel<<<1, 1, 0, stream>>>(P.cam, P.tm, P.tun, P.W, P.H, out);
@@ -116,8 +235,8 @@ cudaError_t mt_launch_cloud_setup(const CloudParams& P, MarchConst* out, cudaStr
 cudaError_t mt_launch_cloud(const CloudParams& P, cudaStream_t stream)
 {
     const int bpt = P.rows.tile_rows / 8;
-    int cols = P.full ? P.W : P.tx;
-    dim3 grid((unsigned)((cols + 15) / 16), (unsigned)(bpt * P.rows.tile_count), 1);
+    dim3 grid((unsigned)((P.W + 15) / 16), (unsigned)(bpt * P.rows.tile_count), 1);
+    if (!P.full) grid = dim3((unsigned)((P.tx / 8) * (P.ty / 4) / 4), 1, 1);  // tx, ty are multiples of 32
     dim3 block(128, 1, 1);
     if (grid.x == 0 || grid.y == 0) return cudaSuccess;
     const bool count = P.counters != nullptr, debug = P.debug != nullptr;

@@ -33,6 +33,8 @@ struct MtContext {
     uint32_t* occ = nullptr;      // empty-cell bitmap of the low-frequency volume (mt_tex.cuh)
     float occCoverage = -1.0f;    // coverage the bitmap was built for; < 0 = stale
     unsigned long long* counters = nullptr;
+    void* rays = nullptr;         // step-parallel 1/16 path: RaySetup per ray (lazily allocated)
+    float2* samples = nullptr;    //   and (inc, energy) per (step, ray)
     MtRayDebug* debug = nullptr;  // lazily allocated W*H records
     int* taps = nullptr;          // lazily allocated W*H*10
     MtCameraUBO cam, camOld;
@@ -93,8 +95,8 @@ static bool is_pow2(uint32_t v) { return v && !(v & (v - 1)); }
 static void free_images(MtContext* c)
 {
     cudaFree(c->hdr[0]); cudaFree(c->hdr[1]); cudaFree(c->mask); cudaFree(c->ldr);
-    cudaFree(c->debug); cudaFree(c->taps); cudaFree(c->maskDecoded);
-    c->maskDecoded = nullptr;
+    cudaFree(c->debug); cudaFree(c->taps); cudaFree(c->maskDecoded); cudaFree(c->rays); cudaFree(c->samples);
+    c->maskDecoded = nullptr; c->rays = nullptr; c->samples = nullptr;
     c->hdr[0] = c->hdr[1] = c->mask = nullptr;
     c->ldr = nullptr; c->debug = nullptr; c->taps = nullptr;
 }
@@ -382,11 +384,22 @@ static MtStatus cloud_dispatch(MtContext* c, int full, const RowTiles* tiles, bo
         MT_CUDA(c, cudaMemsetAsync(c->debug, 0, (size_t)c->W * c->H * sizeof(MtRayDebug), c->stream));
         P.debug = c->debug;
     }
+    // the 1-of-16 dispatch runs step-parallel (cloud_raymarch.cu) unless counters / debug records are wanted
+    const bool split = !full && !debug && !P.counters && !(c->flags & MT_FLAG_SEQUENTIAL_MARCH);
+    if (split && !c->samples) {
+        const size_t nrays = (size_t)P.tx * (size_t)P.ty;
+        MT_CUDA(c, cudaMalloc(&c->rays, nrays * 64));
+        MT_CUDA(c, cudaMalloc((void**)&c->samples, nrays * 64 * sizeof(float2)));
+    }
+    P.rays = c->rays;
+    P.samples = c->samples;
     MT_CUDA(c, mt_launch_cloud_setup(P, c->mc, c->stream));
     pass_begin(c, MT_PASS_CLOUD);
-    MT_CUDA(c, mt_launch_cloud(P, c->stream));
+    int n = 1;
+    if (split) MT_CUDA(c, mt_launch_cloud_sixteenth_split(P, c->stream, &n));
+    else MT_CUDA(c, mt_launch_cloud(P, c->stream));
     pass_end(c, MT_PASS_CLOUD);
-    c->launches += 2;
+    c->launches += 1 + (uint64_t)n;
     return MT_OK;
 }
 

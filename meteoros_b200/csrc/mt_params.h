@@ -2,6 +2,11 @@
 #pragma once
 
 #include "../../include/meteoros_b200.h"
+#if defined(MT_HOSTSIM)
+struct float2 { float x, y; };
+#else
+#include <vector_types.h>
+#endif
 #include "mt_math.cuh"
 #include "mt_tex.cuh"
 
@@ -59,6 +64,9 @@ struct CloudParams {
     RowTiles rows;
     unsigned long long* counters;  // 6 x u64 or null
     MtRayDebug* debug;             // W*H records or null
+    // step-parallel path of the 1-of-16 dispatch (cloud_raymarch.cu): per-ray records and per-(step, ray) samples
+    void* rays;                    // RaySetup[tx*ty], tile-major
+    float2* samples;               // [MT_STEP_SLICES][tx*ty] (inc, energy)
 };
 
 struct ReprojParams {

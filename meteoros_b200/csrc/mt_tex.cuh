@@ -44,6 +44,20 @@ MT_DEVICE LinAxis lin_axis_repeat(float s, int n)
     return a;
 }
 
+// x and y axes of one sample computed as a pair (FMUL2 / FADD2), identical per-component arithmetic
+MT_DEVICE void lin_axes_xy(P2 st, int nx, int ny, LinAxis& X, LinAxis& Y)
+{
+    P2 u = sub2(mul2(st, pk2((float)nx, (float)ny)), bc2(0.5f));
+    int fx = mt_floor2i(lo2(u)), fy = mt_floor2i(hi2(u));
+    P2 w1 = sub2(u, pk2((float)fx, (float)fy));
+    P2 w0 = sub2(bc2(1.0f), w1);
+    X.w1 = lo2(w1); X.w0 = lo2(w0);
+    Y.w1 = hi2(w1); Y.w0 = hi2(w0);
+    X.i0 = (unsigned)fx & (unsigned)(nx - 1); X.i1 = (X.i0 + 1u) & (unsigned)(nx - 1);
+    Y.i0 = (unsigned)fy & (unsigned)(ny - 1); Y.i1 = (Y.i0 + 1u) & (unsigned)(ny - 1);
+}
+
+
 // Byte k of a packed texel as the float  c * 2^-133  -- WITHOUT an int->float conversion (I2F runs on the quarter-rate
 // XU pipe and was 66 % of the kernel's critical pipe in the first profile, profiles/r1_cloud_v1.md).  Placing the
 // byte at bits 16..23 of a zero word gives the bit pattern c << 16: for c < 128 a denormal, for c >= 128 exponent
@@ -71,9 +85,31 @@ struct Rgba {
     float r, g, b, a;
 };
 
+// The eight filter weights (wx_i*wy_j)*wz_k as four pairs (i = 0,1 in the two halves): 6 packed multiplies.
+struct Weights8 {
+    P2 w00, w01, w10, w11;  // index = (k, j): pair over i
+};
+MT_DEVICE Weights8 filter_weights(const LinAxis& X, const LinAxis& Y, const LinAxis& Z)
+{
+    const P2 wx = pk2(X.w0, X.w1);
+    const P2 xy0 = mul2(wx, bc2(Y.w0)), xy1 = mul2(wx, bc2(Y.w1));
+    const float z0 = Z.w0 * MT_WSCALE, z1 = Z.w1 * MT_WSCALE;
+    Weights8 w;
+    w.w00 = mul2(xy0, bc2(z0)); w.w01 = mul2(xy1, bc2(z0));
+    w.w10 = mul2(xy0, bc2(z1)); w.w11 = mul2(xy1, bc2(z1));
+    return w;
+}
+#define MT_RG(t) pk2(MT_B0(t), MT_B1(t))
+#define MT_BA(t) pk2(MT_B2(t), MT_B3(t))
+// acc = w000*t000 (+fma) w001*t001 ... w111*t111 on a channel pair; texel order z-major, x fastest (as the oracle)
+#define MT_ACC2(CH)                                                                                                    \
+    fma2(bc2(hi2(w.w11)), CH(t111), fma2(bc2(lo2(w.w11)), CH(t110), fma2(bc2(hi2(w.w10)), CH(t101),                      \
+    fma2(bc2(lo2(w.w10)), CH(t100), fma2(bc2(hi2(w.w01)), CH(t011), fma2(bc2(lo2(w.w01)), CH(t010),                      \
+    fma2(bc2(hi2(w.w00)), CH(t001), mul2(bc2(lo2(w.w00)), CH(t000)))))))))
+
 MT_DEVICE Rgba tex3d_rgba_axes(const Tex3D& T, const LinAxis& X, const LinAxis& Y, const LinAxis& Z)
 {
-    // 32-bit unsigned texel offsets from one uniform base: LDG [R.U32 + UR] addressing, no 64-bit pointer math
+    // 32-bit unsigned texel offsets from one uniform base: no 64-bit pointer arithmetic per texel
     const unsigned W = (unsigned)T.w, H = (unsigned)T.h;
     const unsigned r00 = (Z.i0 * H + Y.i0) * W, r01 = (Z.i0 * H + Y.i1) * W;
     const unsigned r10 = (Z.i1 * H + Y.i0) * W, r11 = (Z.i1 * H + Y.i1) * W;
@@ -82,20 +118,11 @@ MT_DEVICE Rgba tex3d_rgba_axes(const Tex3D& T, const LinAxis& X, const LinAxis& 
     uint32_t t010 = MT_LDG(tx + (r01 + X.i0)), t011 = MT_LDG(tx + (r01 + X.i1));
     uint32_t t100 = MT_LDG(tx + (r10 + X.i0)), t101 = MT_LDG(tx + (r10 + X.i1));
     uint32_t t110 = MT_LDG(tx + (r11 + X.i0)), t111 = MT_LDG(tx + (r11 + X.i1));
-    float w00 = X.w0 * Y.w0, w01 = X.w1 * Y.w0, w10 = X.w0 * Y.w1, w11 = X.w1 * Y.w1;
-    const float z0 = Z.w0 * MT_WSCALE, z1 = Z.w1 * MT_WSCALE;
-    float w000 = w00 * z0, w001 = w01 * z0, w010 = w10 * z0, w011 = w11 * z0;
-    float w100 = w00 * z1, w101 = w01 * z1, w110 = w10 * z1, w111 = w11 * z1;
+    const Weights8 w = filter_weights(X, Y, Z);
+    const P2 rg = mul2(MT_ACC2(MT_RG), bc2(MT_INV255));
+    const P2 ba = mul2(MT_ACC2(MT_BA), bc2(MT_INV255));
     Rgba o;
-#define MT_ACC(B)                                                                                                   \
-    fmaf(w111, B(t111), fmaf(w110, B(t110), fmaf(w101, B(t101), fmaf(w100, B(t100),                                  \
-         fmaf(w011, B(t011), fmaf(w010, B(t010), fmaf(w001, B(t001), w000 * B(t000))))))))
-    const float inv255 = MT_INV255;
-    o.r = MT_ACC(MT_B0) * inv255;
-    o.g = MT_ACC(MT_B1) * inv255;
-    o.b = MT_ACC(MT_B2) * inv255;
-    o.a = MT_ACC(MT_B3) * inv255;
-#undef MT_ACC
+    o.r = lo2(rg); o.g = hi2(rg); o.b = lo2(ba); o.a = hi2(ba);
     return o;
 }
 
@@ -131,7 +158,6 @@ MT_DEVICE bool occ_cell_may_be_cloud(const Tex3D& T, unsigned x0, unsigned y0, u
 MT_DEVICE Rgba tex3d_rgb(const Tex3D& T, float s, float t, float r)
 {
     LinAxis X = lin_axis_repeat(s, T.w), Y = lin_axis_repeat(t, T.h), Z = lin_axis_repeat(r, T.d);
-    // 32-bit unsigned texel offsets from one uniform base: LDG [R.U32 + UR] addressing, no 64-bit pointer math
     const unsigned W = (unsigned)T.w, H = (unsigned)T.h;
     const unsigned r00 = (Z.i0 * H + Y.i0) * W, r01 = (Z.i0 * H + Y.i1) * W;
     const unsigned r10 = (Z.i1 * H + Y.i0) * W, r11 = (Z.i1 * H + Y.i1) * W;
@@ -140,20 +166,13 @@ MT_DEVICE Rgba tex3d_rgb(const Tex3D& T, float s, float t, float r)
     uint32_t t010 = MT_LDG(tx + (r01 + X.i0)), t011 = MT_LDG(tx + (r01 + X.i1));
     uint32_t t100 = MT_LDG(tx + (r10 + X.i0)), t101 = MT_LDG(tx + (r10 + X.i1));
     uint32_t t110 = MT_LDG(tx + (r11 + X.i0)), t111 = MT_LDG(tx + (r11 + X.i1));
-    float w00 = X.w0 * Y.w0, w01 = X.w1 * Y.w0, w10 = X.w0 * Y.w1, w11 = X.w1 * Y.w1;
-    const float z0 = Z.w0 * MT_WSCALE, z1 = Z.w1 * MT_WSCALE;
-    float w000 = w00 * z0, w001 = w01 * z0, w010 = w10 * z0, w011 = w11 * z0;
-    float w100 = w00 * z1, w101 = w01 * z1, w110 = w10 * z1, w111 = w11 * z1;
+    const Weights8 w = filter_weights(X, Y, Z);
+    const P2 rg = mul2(MT_ACC2(MT_RG), bc2(MT_INV255));
+    const float b = fmaf(hi2(w.w11), MT_B2(t111), fmaf(lo2(w.w11), MT_B2(t110), fmaf(hi2(w.w10), MT_B2(t101),
+                    fmaf(lo2(w.w10), MT_B2(t100), fmaf(hi2(w.w01), MT_B2(t011), fmaf(lo2(w.w01), MT_B2(t010),
+                    fmaf(hi2(w.w00), MT_B2(t001), lo2(w.w00) * MT_B2(t000)))))))) * MT_INV255;
     Rgba o;
-#define MT_ACC(B)                                                                                                   \
-    fmaf(w111, B(t111), fmaf(w110, B(t110), fmaf(w101, B(t101), fmaf(w100, B(t100),                                  \
-         fmaf(w011, B(t011), fmaf(w010, B(t010), fmaf(w001, B(t001), w000 * B(t000))))))))
-    const float inv255 = MT_INV255;
-    o.r = MT_ACC(MT_B0) * inv255;
-    o.g = MT_ACC(MT_B1) * inv255;
-    o.b = MT_ACC(MT_B2) * inv255;
-    o.a = 0.0f;
-#undef MT_ACC
+    o.r = lo2(rg); o.g = hi2(rg); o.b = b; o.a = 0.0f;
     return o;
 }
 
@@ -166,9 +185,10 @@ MT_DEVICE void tex2d_rg(const Tex2D& T, float s, float t, float& r, float& g)
     uint32_t t00 = MT_LDG(tx + (Y.i0 * W + X.i0)), t01 = MT_LDG(tx + (Y.i0 * W + X.i1));
     uint32_t t10 = MT_LDG(tx + (Y.i1 * W + X.i0)), t11 = MT_LDG(tx + (Y.i1 * W + X.i1));
     // 2D: the oracle's weight is wx*wy, so the 2^120 rides on the y weight
-    const float y0 = Y.w0 * MT_WSCALE, y1 = Y.w1 * MT_WSCALE;
-    float w00 = X.w0 * y0, w01 = X.w1 * y0, w10 = X.w0 * y1, w11 = X.w1 * y1;
-    const float inv255 = MT_INV255;
-    r = fmaf(w11, MT_B0(t11), fmaf(w10, MT_B0(t10), fmaf(w01, MT_B0(t01), w00 * MT_B0(t00)))) * inv255;
-    g = fmaf(w11, MT_B1(t11), fmaf(w10, MT_B1(t10), fmaf(w01, MT_B1(t01), w00 * MT_B1(t00)))) * inv255;
+    const P2 wx = pk2(X.w0, X.w1);
+    const P2 w0 = mul2(wx, bc2(Y.w0 * MT_WSCALE)), w1 = mul2(wx, bc2(Y.w1 * MT_WSCALE));  // (w00, w01), (w10, w11)
+    const P2 rg = mul2(fma2(bc2(hi2(w1)), MT_RG(t11), fma2(bc2(lo2(w1)), MT_RG(t10), fma2(bc2(hi2(w0)), MT_RG(t01),
+                       mul2(bc2(lo2(w0)), MT_RG(t00))))), bc2(MT_INV255));
+    r = lo2(rg);
+    g = hi2(rg);
 }

@@ -85,6 +85,27 @@ def test_cloud_full_dispatch_and_debug_records(api, oracle_mod, noise, w, h, yaw
     assert np.array_equal(hdr, hdr2)  # debug / counter variants compute the same pixels
 
 
+@pytest.mark.parametrize("w,h", [(1920, 1080), (130, 70), (500, 281)])
+def test_sixteenth_step_parallel_equals_sequential(api, noise, w, h):
+    """The 1-of-16 dispatch runs as rays -> (ray, step) samples -> fold by default; MT_FLAG_SEQUENTIAL_MARCH keeps the
+    one-thread-per-ray kernel.  Same device functions, same order: the images must be bit-identical."""
+    sentinel = np.full((h, w, 4), -7.0, np.float32)
+    out = {}
+    for flags in (0, api.FLAG_SEQUENTIAL_MARCH):
+        with make_renderer(api, noise, w, h, flags=flags) as r:
+            imgs = []
+            for fid in (0, 7, 13):
+                cam, tm, _, tun = default_scene(w, h, frame_id=fid, total_time=3.0 + fid, yaw=2.0 * fid)
+                r.set_camera(cam); r.set_time(tm)
+                r.write_image(api.IMAGE_CLOUD_CUR, sentinel)
+                r.write_image(api.IMAGE_GODRAY_MASK, sentinel)
+                r.dispatch_cloud()
+                imgs.append((r.read_image(api.IMAGE_CLOUD_CUR), r.read_image(api.IMAGE_GODRAY_MASK)))
+            out[flags] = imgs
+    for (h0, m0), (h1, m1) in zip(out[0], out[api.FLAG_SEQUENTIAL_MARCH]):
+        assert np.array_equal(h0, h1) and np.array_equal(m0, m1)
+
+
 def test_cloud_tuning_sweep(api, oracle_mod, noise):
     from meteoros_b200 import scene
 
