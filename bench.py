@@ -52,6 +52,15 @@ def algorithmic_flop(c: dict) -> float:
             + FLOP_PER_INCLOUD_STEP * c["steps_incloud"] + FLOP_PER_CONE_HIT * c["cone_hits"])
 
 
+def ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed ncu capture."""
+    f = ROOT / "profiles" / "cloud_raymarch_traffic.json"
+    try:
+        return int(json.loads(f.read_text())["dram_bytes_per_launch"])
+    except (OSError, ValueError, KeyError):
+        return None
+
+
 def filtered_fetches(c: dict) -> int:
     return c["steps"] + 8 * c["steps_incloud"]  # SURVEY 8d: S + 8C
 
@@ -219,9 +228,13 @@ def main():
         counters = rc.counters()
         fp32_peak_gflops = rc.measure_fp32_peak_gflops()
 
-    r = api.CloudRenderer(w, h, device=local_rank)
+    r = api.CloudRenderer(w, h, device=local_rank, flags=api.FLAG_PASS_TIMING if args.workload == "seq1080p" else 0)
     r.upload_noise(noise)
     r.set_camera(cam); r.set_camera_old(cam); r.set_time(tm); r.set_sun_and_sky(sky); r.set_tuning(tun)
+    from meteoros_b200 import scene as _scene
+    pan_cam, pan_scene = _scene.Camera(w, h), _scene.Scene()   # seq1080p: the reference's frame loop (main.cpp:172-194)
+    pan_old = [pan_cam.ubo()]
+    pass_ms = {"reproject": [], "cloud_1of16": [], "godrays": [], "tonemap": []}
 
     shard = None
     if args.workload == "frame8k":
@@ -237,12 +250,14 @@ def main():
             r.dispatch_cloud_full()
         elif args.workload == "frame8k":
             shard.dispatch()
-        else:
-            t = tm.copy()
-            t["frameCountMod16"] = (seq_state["frame"] + 1) % 16
-            seq_state["frame"] += 1
-            r.set_time(t)
+        else:  # one reference frame: 0.25 deg pan, dt = 1/60, ids 1..15,0, REPROJ + CLOUD + GODRAYS + TONEMAP + swap
+            pan_cam.rotate_about_up(0.25)
+            pan_scene.update_time(1.0 / 60.0)
+            c = pan_cam.ubo()
+            r.set_camera(c); r.set_camera_old(pan_old[0]); r.set_time(pan_scene.ubo())
             r.frame(with_godrays=True)
+            pan_old[0] = c
+            seq_state["frame"] += 1
 
     def barrier():
         r.synchronize()
@@ -274,6 +289,9 @@ def main():
         if args.workload == "frame8k" and world > 1:
             shard.finish()  # frame boundary: all ranks' tiles have landed on GPU 0
         step_ms.append(r.event_elapsed_ms(0, 1))
+        if args.workload == "seq1080p":
+            for k, name in enumerate(pass_ms):
+                pass_ms[name].append(r.last_pass_ms(k))
     barrier()
     launches = r.launch_count() - launches0
     clocks = sampler.stop()
@@ -337,7 +355,7 @@ def main():
                 "peak": round(fp32_peak_gflops / 1e3, 3), "unit": "TFLOP/s", "frac": round(ach_tflops / (fp32_peak_gflops / 1e3), 4),
                 "peak_source": "measured FP32 FMA micro-benchmark (mtMeasureFp32Peak) on this GPU; no tensor work in this path",
                 "algorithmic_gflop_per_launch": round(flop / 1e9, 3), "filtered_fetches_per_launch": filtered_fetches(counters),
-                "gfetch_per_s": round(filtered_fetches(counters) / (kern_ms * 1e-3) / 1e9, 3), "traffic": None,
+                "gfetch_per_s": round(filtered_fetches(counters) / (kern_ms * 1e-3) / 1e9, 3), "traffic": ncu_traffic_bytes(),
                 "hbm": {"bound": "hbm", "achieved": round(hbm_ach, 2), "peak": hbm_peak, "unit": "GB/s", "frac": round(hbm_ach / hbm_peak, 5),
                         "algorithmic_bytes_per_launch": int(HBM_BYTES_PER_RAY * counters["rays"]), "peak_source": hbm_src},
             }
@@ -352,6 +370,20 @@ def main():
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
             "work": {k: int(v) for k, v in counters.items()},
         }
+        if args.workload == "seq1080p":  # per-pass device time and HBM roofline of the bandwidth passes (SURVEY 8d bytes/pixel)
+            px = w * h
+            algo = {"reproject": 32 * px, "godrays": 48 * px, "tonemap": 20 * px}
+            passes = {}
+            for name, v in pass_ms.items():
+                ms = statistics.median(v)
+                e = {"ms": round(ms, 4)}
+                if name in algo:
+                    gbs = algo[name] / (ms * 1e-3) / 1e9
+                    e.update({"bound": "hbm", "algorithmic_bytes": algo[name], "achieved": round(gbs, 1), "peak": hbm_peak, "unit": "GB/s",
+                              "frac": round(gbs / hbm_peak, 4)})
+                passes[name] = e
+            line["passes"] = passes
+            line["config"]["frame"] = "16-frame pan repeated; value = rays marched per frame (W*H/16) / frame time"
 
     if shard is not None and world > 1:
         shard.close()

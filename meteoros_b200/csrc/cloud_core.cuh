@@ -249,13 +249,15 @@ MT_DEVICE StepSample cloud_step_sample(const CloudParams& P, const MarchConst& M
         float edge = erosion_edge(P.curl, P.high, skew, h);
         S.inc = erode(baseDensity * 1.4f, edge) * 0.5f;
         float dl = 0.0f;
-        const P2 posxy = pk2(pos.x, pos.y), relxy = pk2(relOrigin.x, relOrigin.y);
+        const P2 relxy = pk2(relOrigin.x, relOrigin.y);
 #pragma unroll 1
         for (int i = 0; i < 6; ++i) {  // one copy of the filter in the instruction stream (I-cache)
             // lightPos = pos + (stepSize * noise_kernel[i]) * i ; sample = (lightPos - relOrigin) / 12500  -- x,y as a pair
             const float fi = (float)i;
             const f3 cs = M.coneStep[i];
-            P2 lxy = sub2(add2(posxy, mul2(mul2(pk2(cs.x, cs.y), bc2(R.stepSize)), bc2(fi))), relxy);
+            const P2 off = mul2(mul2(pk2(cs.x, cs.y), bc2(R.stepSize)), bc2(fi));
+            // scalar adds: a mul2 feeding an add2 would be contracted into an FFMA2 (mt_math.cuh)
+            P2 lxy = sub2(pk2(pos.x + lo2(off), pos.y + hi2(off)), relxy);
             float lz = (pos.z + (cs.z * R.stepSize) * fi) - relOrigin.z;
             float cur = low_freq_density(P.low, coverage, div_thickness2(lxy), div_thickness(lz));
             if (cur > 0.0f) {

@@ -47,9 +47,10 @@ MT_DEVICE LinAxis lin_axis_repeat(float s, int n)
 // x and y axes of one sample computed as a pair (FMUL2 / FADD2), identical per-component arithmetic
 MT_DEVICE void lin_axes_xy(P2 st, int nx, int ny, LinAxis& X, LinAxis& Y)
 {
-    P2 u = sub2(mul2(st, pk2((float)nx, (float)ny)), bc2(0.5f));
-    int fx = mt_floor2i(lo2(u)), fy = mt_floor2i(hi2(u));
-    P2 w1 = sub2(u, pk2((float)fx, (float)fy));
+    const P2 m = mul2(st, pk2((float)nx, (float)ny));
+    const float ux = lo2(m) - 0.5f, uy = hi2(m) - 0.5f;  // scalar: mul2 -> sub2 would be contracted (mt_math.cuh)
+    int fx = mt_floor2i(ux), fy = mt_floor2i(uy);
+    P2 w1 = sub2(pk2(ux, uy), pk2((float)fx, (float)fy));
     P2 w0 = sub2(bc2(1.0f), w1);
     X.w1 = lo2(w1); X.w0 = lo2(w0);
     Y.w1 = hi2(w1); Y.w0 = hi2(w0);

@@ -5,37 +5,65 @@
 #include "mt_params.h"
 
 // ---- Reprojection ------------------------------------------------------------------------------------------------
-// Returns the ten clamped tap positions (linear index y*W + x) of pixel (x, y); the caller gathers and averages.
-MT_DEVICE void reproject_taps(const ReprojParams& P, const RayBasis& B, int x, int y, int taps[10])
+// Per-frame values of reprojection.comp:203-211: camera basis, ray origin, the unit-sphere origin of the inner-shell
+// intersection (raySphereIntersection's rO, identical for every pixel) and its C term, this shader's Halton offset.
+struct ReprojFrame {
+    RayBasis basis;
+    f3 eye, ec, o;
+    float C;
+    float jx, jy;
+};
+
+MT_DEVICE ReprojFrame reproject_frame(const ReprojParams& P)
 {
-    const float fw = (float)P.W, fh = (float)P.H;
-    float u = (float)x / fw;
-    float v = (float)y / fh;  // no y flip here (reprojection.comp:200-201)
+    ReprojFrame F;
+    F.basis = ray_basis(P.cam);
+    F.eye = mk3(-P.cam.eye[0], -P.cam.eye[1], -P.cam.eye[2]);
+    F.ec = mk3(F.eye.x, -MT_EARTH_RADIUS, F.eye.z);
+    F.o = (F.eye - F.ec) / MT_R_INNER;
+    F.C = dot3(F.o, F.o) - 1.0f;
     // getJitterOffset of THIS shader: index >= 4 re-reads haltonSeq1/2 (reprojection.comp:83-88)
-    int hj = (P.tm.frameCountMod16 >> 1) & 3;
-    float jx = P.tm.halton[hj] / fw;
-    float jy = P.tm.halton[4 + hj] / fh;
-    f3 eye = mk3(-P.cam.eye[0], -P.cam.eye[1], -P.cam.eye[2]);
-    f3 dir = cast_ray_dir(P.cam, B, eye, u, v, jx, jy);
-    f3 ec = mk3(eye.x, -MT_EARTH_RADIUS, eye.z);
-    ShellHit hit = ray_shell(eye, dir, ec, MT_R_INNER);
+    const int hj = (P.tm.frameCountMod16 >> 1) & 3;
+    F.jx = P.tm.halton[hj] / (float)P.W;
+    F.jy = P.tm.halton[4 + hj] / (float)P.H;
+    return F;
+}
+
+// Returns the ten clamped tap positions (linear index y*W + x) of the pixel whose uv is (u, v) = (x/W, y/H).
+MT_DEVICE void reproject_taps(const ReprojParams& P, const ReprojFrame& F, float u, float v, int taps[10])
+{
+    const float fw = (float)P.W, fh = (float)P.H;  // no y flip here (reprojection.comp:200-201)
+    const f3 dir = cast_ray_dir(P.cam, F.basis, F.eye, u, v, F.jx, F.jy);
+    // raySphereIntersection (reprojection.comp:147-191) with the pixel-independent terms hoisted; only .point is used
+    f3 p = mk3(0.0f, 0.0f, 0.0f);
+    {
+        const float A = dot3(dir, dir);
+        const float B = 2.0f * dot3(dir, F.o);
+        const float disc = B * B - (4.0f * A) * F.C;
+        if (!(disc < 0.0f)) {
+            const float sq = sqrtf(disc);
+            float t = (-B - sq) / (2.0f * A);
+            if (t < 0.0f) t = (-B + sq) / (2.0f * A);
+            if (t >= 0.0f) p = ((F.o + dir * t) * MT_R_INNER) + F.ec;
+        }
+    }
     const float* m = P.camOld.view;
-    f3 p = hit.point;
     f3 q = mk3(((m[0] * p.x + m[4] * p.y) + m[8] * p.z) + m[12] * 1.0f,
                ((m[1] * p.x + m[5] * p.y) + m[9] * p.z) + m[13] * 1.0f,
                ((m[2] * p.x + m[6] * p.y) + m[10] * p.z) + m[14] * 1.0f);
     q = norm3(q);
     q = q / (-q.z);
-    float old_u = (q.x / P.cam.tanFovBy2[0]) * 0.5f + 0.5f;
-    float old_v = (q.y / P.cam.tanFovBy2[1]) * 0.5f + 0.5f;
-    float mx = old_u - u, my = old_v - v;
+    const float old_u = (q.x / P.cam.tanFovBy2[0]) * 0.5f + 0.5f;
+    const float old_v = (q.y / P.cam.tanFovBy2[1]) * 0.5f + 0.5f;
+    const P2 mv = pk2(old_u - u, old_v - v), dim = pk2(fw, fh);
 #pragma unroll
     for (int i = 0; i < 10; ++i) {
         const float f = (float)i / 10.0f;
-        float ix = rintf((old_u - mx * f) * fw);
-        float iy = rintf((old_v - my * f) * fh);
-        int cx = min(max(mt_f2i(ix), 0), P.W - 1);
-        int cy = min(max(mt_f2i(iy), 0), P.H - 1);
+        // (old_uv - motion * (i/10)) * dim; the subtraction is scalar (a mul2 feeding a sub2 would be contracted)
+        const P2 b = mul2(mv, bc2(f));
+        const P2 c = mul2(pk2(old_u - lo2(b), old_v - hi2(b)), dim);
+        const int cx = min(max(mt_round2i(lo2(c)), 0), P.W - 1);
+        const int cy = min(max(mt_round2i(hi2(c)), 0), P.H - 1);
         taps[i] = cy * P.W + cx;
     }
 }
@@ -82,35 +110,41 @@ MT_DEVICE float mask_texel_decode(F4 t)
 // and 4 instead of 16 multiply-adds per tap, 100 taps per pixel.  The two orders agree to rounding (~1e-7 relative on
 // a term that is itself <= 2.5 % of the pixel); no decision depends on it.  `dec` is the (W+2) x (H+2) decoded image
 // whose one-texel ring holds the border value, so the taps need no bounds tests.
-MT_DEVICE float mask_decode(const float* dec, int W, int H, float s, float t)
+MT_DEVICE float mask_decode(const float* dec, int W, int H, P2 st)
 {
-    float u = s * (float)W - 0.5f, v = t * (float)H - 0.5f;
-    int x0 = mt_floor2i(u), y0 = mt_floor2i(v);
-    float ax = u - (float)x0, ay = v - (float)y0;
+    const P2 m = mul2(st, pk2((float)W, (float)H));
+    const float ux = lo2(m) - 0.5f, uy = hi2(m) - 0.5f;  // scalar: mul2 -> sub2 would be contracted (mt_math.cuh)
+    int x0 = mt_floor2i(ux), y0 = mt_floor2i(uy);
+    const P2 a1 = sub2(pk2(ux, uy), pk2((float)x0, (float)y0));  // (ax, ay)
+    const P2 a0 = sub2(bc2(1.0f), a1);                  // (1-ax, 1-ay)
     // uv stays inside [0,1] (the march runs from the pixel towards the clamped sun position), so x0 in [-1, W-1]
     x0 = min(max(x0, -1), W - 1);
     y0 = min(max(y0, -1), H - 1);
-    const float* p = dec + (size_t)(y0 + 1) * (size_t)(W + 2) + (size_t)(x0 + 1);
-    float a = MT_LDG(p), b = MT_LDG(p + 1), c = MT_LDG(p + (W + 2)), d = MT_LDG(p + (W + 3));
-    float w00 = (1.0f - ax) * (1.0f - ay), w01 = ax * (1.0f - ay), w10 = (1.0f - ax) * ay, w11 = ax * ay;
+    const unsigned pitch = (unsigned)(W + 2);
+    const float* __restrict__ p = dec + ((unsigned)(y0 + 1) * pitch + (unsigned)(x0 + 1));
+    float a = MT_LDG(p), b = MT_LDG(p + 1), c = MT_LDG(p + pitch), d = MT_LDG(p + pitch + 1);
+    const float ax = lo2(a1), ay = hi2(a1), bx = lo2(a0), by = hi2(a0);
+    float w00 = bx * by, w01 = ax * by, w10 = bx * ay, w11 = ax * ay;
     return fmaf(w11, d, fmaf(w10, c, fmaf(w01, b, w00 * a)));
 }
 
 // The radial accumulation of one fragment; returns the colour to ADD to the HDR pixel (already * blend).
 MT_DEVICE F4 godray_pixel(const GodRayParams& P, const GodRayFrame& G, int x, int y)
 {
-    float u = ((float)x + 0.5f) / (float)P.W;
-    float v = ((float)y + 0.5f) / (float)P.H;
+    const float u = ((float)x + 0.5f) / (float)P.W;
+    const float v = ((float)y + 0.5f) / (float)P.H;
     const float du = ((u - G.sunx) / 100.0f) * 1.0f;
     const float dv = ((v - G.suny) / 100.0f) * 1.0f;
+    P2 uv = pk2(u, v);
+    const P2 duv = pk2(du, dv), lc01 = pk2(P.lightColor[0], P.lightColor[1]);
     float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f;
     for (int i = 0; i < 100; ++i) {
-        float a = mask_decode(P.decoded, P.W, P.H, u, v);
-        acc0 += (P.lightColor[0] * a) * (1.0f * 0.001f);
-        acc1 += (P.lightColor[1] * a) * (1.0f * 0.001f);
+        const float a = mask_decode(P.decoded, P.W, P.H, uv);
+        const P2 s01 = mul2(mul2(lc01, bc2(a)), bc2(1.0f * 0.001f));
+        acc0 += lo2(s01);  // scalar adds: a mul2 feeding an add2 would be contracted
+        acc1 += hi2(s01);
         acc2 += (P.lightColor[2] * a) * (1.0f * 0.001f);
-        u -= du;
-        v -= dv;
+        uv = sub2(uv, duv);
     }
     F4 o;
     o.x = (acc0 * 1.0f) * G.blend;

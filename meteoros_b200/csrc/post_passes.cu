@@ -15,24 +15,34 @@ __device__ __forceinline__ float4 f16_round4(float4 v)
 }
 
 // ---- Reprojection: 32x8 pixels per CTA, a warp is one 32-pixel row segment (512 contiguous bytes per access) -----
+// Instruction-issue bound, not HBM bound: every pixel casts a ray, intersects the inner shell, normalises twice, takes
+// seven IEEE divisions and ten dependent-address taps (~350 instructions for 32 bytes of compulsory traffic).  What
+// does not depend on the pixel is computed once per CTA (frame constants, x/W for the CTA's 32 columns, y/H for its 8
+// rows); coordinates and the float4 accumulation run on fp32x2 pairs; the final /10 is the exact 3-instruction division.
 __global__ void __launch_bounds__(256) reproject_kernel(const __grid_constant__ ReprojParams P)
 {
-    __shared__ RayBasis basis;
-    if (threadIdx.x == 0) basis = ray_basis(P.cam);
+    __shared__ ReprojFrame frame;
+    __shared__ float su[32], sv[8];
+    if (threadIdx.x == 0) frame = reproject_frame(P);
+    if (threadIdx.x >= 32 && threadIdx.x < 64) su[threadIdx.x - 32] = (float)(blockIdx.x * 32 + (threadIdx.x - 32)) / (float)P.W;
+    if (threadIdx.x >= 64 && threadIdx.x < 72) sv[threadIdx.x - 64] = (float)(blockIdx.y * 8 + (threadIdx.x - 64)) / (float)P.H;
     __syncthreads();
     const int x = blockIdx.x * 32 + (threadIdx.x & 31);
     const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
     if (x >= P.W || y >= P.H) return;
     int taps[10];
-    reproject_taps(P, basis, x, y, taps);
+    reproject_taps(P, frame, su[threadIdx.x & 31], sv[threadIdx.x >> 5], taps);
     const float4* prev = reinterpret_cast<const float4*>(P.prev);
-    float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    P2 axy = pk2(0.0f, 0.0f), azw = pk2(0.0f, 0.0f);
 #pragma unroll
     for (int i = 0; i < 10; ++i) {
-        float4 t = __ldg(prev + taps[i]);
-        acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+        const float4 t = __ldg(prev + taps[i]);
+        axy = add2(axy, pk2(t.x, t.y));
+        azw = add2(azw, pk2(t.z, t.w));
     }
-    acc.x /= 10.0f; acc.y /= 10.0f; acc.z /= 10.0f; acc.w /= 10.0f;
+    axy = MT_DIV_CONST2(axy, 10.0f);
+    azw = MT_DIV_CONST2(azw, 10.0f);
+    float4 acc = make_float4(lo2(axy), hi2(axy), lo2(azw), hi2(azw));
     if (P.f16_emulate) acc = f16_round4(acc);
     const size_t idx = (size_t)y * P.W + x;
     reinterpret_cast<float4*>(P.cur)[idx] = acc;

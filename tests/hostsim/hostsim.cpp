@@ -96,19 +96,22 @@ int hs_reproject(const MtCameraUBO* cam, const MtCameraUBO* camOld, const MtTime
     memcpy(&P.camOld, camOld, sizeof(CamU));
     memcpy(&P.tm, tm, sizeof(TimeU));
     P.W = W; P.H = H;
-    RayBasis B = ray_basis(P.cam);
+    ReprojFrame F = reproject_frame(P);
     for (int y = 0; y < H; ++y)
         for (int x = 0; x < W; ++x) {
             int taps[10];
-            reproject_taps(P, B, x, y, taps);
-            float acc[4] = { 0, 0, 0, 0 };
+            reproject_taps(P, F, (float)x / (float)W, (float)y / (float)H, taps);
+            P2 axy = pk2(0.0f, 0.0f), azw = pk2(0.0f, 0.0f);
             for (int i = 0; i < 10; ++i) {
                 const float* p = prev + 4 * (size_t)taps[i];
-                acc[0] += p[0]; acc[1] += p[1]; acc[2] += p[2]; acc[3] += p[3];
+                axy = add2(axy, pk2(p[0], p[1]));
+                azw = add2(azw, pk2(p[2], p[3]));
                 if (taps_out) taps_out[((size_t)y * W + x) * 10 + i] = taps[i];
             }
+            axy = MT_DIV_CONST2(axy, 10.0f);
+            azw = MT_DIV_CONST2(azw, 10.0f);
             float* o = cur + 4 * ((size_t)y * W + x);
-            for (int c = 0; c < 4; ++c) o[c] = acc[c] / 10.0f;
+            o[0] = lo2(axy); o[1] = hi2(axy); o[2] = lo2(azw); o[3] = hi2(azw);
         }
     return 0;
 }
