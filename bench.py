@@ -298,8 +298,8 @@ def main():
     dev_ms_total = float(sum(step_ms))
 
     # ---- end-to-end region: host uniforms in, HDR frame out to pinned host memory, every step
-    out_which = api.IMAGE_CLOUD_CUR if args.workload != "seq1080p" else api.IMAGE_LDR
-    nbytes = w * h * (16 if out_which != api.IMAGE_LDR else 4)
+    out_which = api.IMAGE_CLOUD_CUR if args.workload != "seq1080p" else api.IMAGE_LDR_PREV  # the frame just finished (roles swapped)
+    nbytes = w * h * (4 if args.workload == "seq1080p" else 16)
     pinned = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
     h2d = int(cam.nbytes + tm.nbytes + tun.nbytes + sky.nbytes)
     e2e_read = (rank == 0) or args.workload != "frame8k"
@@ -315,10 +315,7 @@ def main():
         if args.workload == "frame8k" and world > 1:
             shard.finish()
         if e2e_read:
-            if args.workload == "seq1080p":
-                r.read_image_into(api.IMAGE_LDR, pinned.data_ptr(), nbytes)
-            else:
-                r.read_image_into(out_which, pinned.data_ptr(), nbytes)  # synchronises
+            r.read_image_into(out_which, pinned.data_ptr(), nbytes)  # synchronises
     barrier()
     e2e_s = time.perf_counter() - t0
 

@@ -113,7 +113,8 @@ typedef enum MtImage {
     MT_IMAGE_CLOUD_CUR = 0,   /* currentFrameResultImage   RGBA32F, W*H*16 bytes */
     MT_IMAGE_CLOUD_PREV = 1,  /* previousFrameResultImage  RGBA32F               */
     MT_IMAGE_GODRAY_MASK = 2, /* godRaysCreationDataImage  RGBA32F               */
-    MT_IMAGE_LDR = 3          /* tone-mapped frame         RGBA8 UNORM, W*H*4    */
+    MT_IMAGE_LDR = 3,         /* currentFrameTexture: tone-mapped (then TXAA'd) frame, RGBA8 UNORM, W*H*4 (Renderer.cpp:1442) */
+    MT_IMAGE_LDR_PREV = 4     /* previousFrameTexture: the LDR frame presented last frame (Renderer.cpp:1445)              */
 } MtImage;
 
 typedef enum MtPass {
@@ -121,7 +122,8 @@ typedef enum MtPass {
     MT_PASS_CLOUD = 1,
     MT_PASS_GODRAYS = 2,
     MT_PASS_TONEMAP = 3,
-    MT_PASS_COUNT = 4
+    MT_PASS_TXAA = 4,
+    MT_PASS_COUNT = 5
 } MtPass;
 
 /* Work counters of the cloud pass (MT_FLAG_COUNTERS); same struct is filled by the CPU oracle. */
@@ -190,11 +192,20 @@ MT_API MtStatus mtDispatchCloudDebug(MtContext* ctx, int full, MtRayDebug* out, 
 MT_API MtStatus mtDispatchGodRays(MtContext* ctx);
 /* vkCmdDraw(3) of postProcess_ToneMap pipeline (Renderer.cpp:834-838): CUR -> LDR. */
 MT_API MtStatus mtDispatchToneMap(MtContext* ctx);
+/* vkCmdDraw(3) of postProcess_TXAA pipeline (Renderer.cpp:840-846): neighbourhood-clamped temporal blend of MT_IMAGE_LDR
+ * with MT_IMAGE_LDR_PREV, result replaces MT_IMAGE_LDR (the image the reference presents).                      */
+MT_API MtStatus mtDispatchTXAA(MtContext* ctx);
 /* Debug variant of mtDispatchReprojection: also returns the 10 clamped tap indices (y*W+x) per pixel. Synchronous. */
 MT_API MtStatus mtDispatchReprojectionDebug(MtContext* ctx, int32_t* taps, size_t taps_bytes);
 /* One reference frame (Renderer::Frame, Renderer.cpp:122-192): REPROJ, CLOUD, [GODRAYS if with_godrays], TONEMAP,
  * then swap the ping-pong roles.  The caller copies camera -> cameraOld afterwards (main.cpp:185-186).         */
 MT_API MtStatus mtFrame(MtContext* ctx, int with_godrays);
+/* Same with a pass mask: REPROJ and CLOUD always run; MT_FRAME_GODRAYS / MT_FRAME_TONEMAP / MT_FRAME_TXAA select the post
+ * passes.  The reference's live frame is MT_FRAME_TONEMAP | MT_FRAME_TXAA (god rays commented out, Renderer.cpp:826-846). */
+#define MT_FRAME_GODRAYS 1u
+#define MT_FRAME_TONEMAP 2u
+#define MT_FRAME_TXAA 4u
+MT_API MtStatus mtFrameEx(MtContext* ctx, uint32_t passes);
 MT_API MtStatus mtSwapPingPong(MtContext* ctx);   /* swapPingPongBuffers = !swapPingPongBuffers, Renderer.cpp:191 */
 MT_API MtStatus mtSynchronize(MtContext* ctx);    /* vkQueueWaitIdle */
 

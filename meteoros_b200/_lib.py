@@ -67,6 +67,8 @@ PROTOTYPES = {
     "mtDispatchCloudDebug": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
     "mtDispatchGodRays": (C.c_int, [C.c_void_p]),
     "mtDispatchToneMap": (C.c_int, [C.c_void_p]),
+    "mtDispatchTXAA": (C.c_int, [C.c_void_p]),
+    "mtFrameEx": (C.c_int, [C.c_void_p, C.c_uint32]),
     "mtDispatchReprojectionDebug": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "mtFrame": (C.c_int, [C.c_void_p, C.c_int]),
     "mtSwapPingPong": (C.c_int, [C.c_void_p]),

@@ -18,8 +18,9 @@ MT_OK = 0
 STORAGE_F32, STORAGE_F16_EMULATE = 0, 1
 FLAG_COUNTERS, FLAG_PASS_TIMING, FLAG_SEQUENTIAL_MARCH = 1, 2, 4
 TEX_LOW_FREQ, TEX_HIGH_FREQ, TEX_CURL, TEX_WEATHER = 0, 1, 2, 3
-IMAGE_CLOUD_CUR, IMAGE_CLOUD_PREV, IMAGE_GODRAY_MASK, IMAGE_LDR = 0, 1, 2, 3
-PASS_REPROJECT, PASS_CLOUD, PASS_GODRAYS, PASS_TONEMAP = 0, 1, 2, 3
+IMAGE_CLOUD_CUR, IMAGE_CLOUD_PREV, IMAGE_GODRAY_MASK, IMAGE_LDR, IMAGE_LDR_PREV = 0, 1, 2, 3, 4
+PASS_REPROJECT, PASS_CLOUD, PASS_GODRAYS, PASS_TONEMAP, PASS_TXAA = 0, 1, 2, 3, 4
+FRAME_GODRAYS, FRAME_TONEMAP, FRAME_TXAA = 1, 2, 4
 
 RAY_DEBUG_DTYPE = np.dtype(
     [
@@ -165,9 +166,13 @@ class CloudRenderer:
         self._check(self._lib.mtDispatchReprojectionDebug(self._h, taps.ctypes.data, taps.nbytes), "mtDispatchReprojectionDebug")
         return taps
 
-    def frame(self, with_godrays: bool = False):
-        """Renderer::Frame: REPROJ, CLOUD, [GODRAYS], TONEMAP, swap."""
-        self._check(self._lib.mtFrame(self._h, int(bool(with_godrays))), "mtFrame")
+    def dispatch_txaa(self):
+        self._check(self._lib.mtDispatchTXAA(self._h), "mtDispatchTXAA")
+
+    def frame(self, with_godrays: bool = False, with_txaa: bool = False):
+        """Renderer::Frame: REPROJ, CLOUD, [GODRAYS], TONEMAP, [TXAA], swap."""
+        passes = FRAME_TONEMAP | (FRAME_GODRAYS if with_godrays else 0) | (FRAME_TXAA if with_txaa else 0)
+        self._check(self._lib.mtFrameEx(self._h, passes), "mtFrameEx")
 
     def swap_ping_pong(self):
         self._check(self._lib.mtSwapPingPong(self._h), "mtSwapPingPong")
@@ -177,7 +182,7 @@ class CloudRenderer:
 
     # ---- images ---------------------------------------------------------------------------------------------
     def _image_shape(self, which: int):
-        return (self.height, self.width, 4), (np.uint8 if which == IMAGE_LDR else np.float32)
+        return (self.height, self.width, 4), (np.uint8 if which in (IMAGE_LDR, IMAGE_LDR_PREV) else np.float32)
 
     def read_image(self, which: int, out: np.ndarray | None = None) -> np.ndarray:
         shape, dt = self._image_shape(which)

@@ -26,7 +26,8 @@ struct MtContext {
     int cur = 0;  // index of the image that currently plays "currentFrameResultImage"
     F4* mask = nullptr;
     float* maskDecoded = nullptr;  // (W+2) x (H+2): scratch of the god-ray pass
-    uint32_t* ldr = nullptr;
+    uint32_t* ldr[2] = { nullptr, nullptr };  // ping-pong with the HDR images (same `cur`)
+    uint32_t* ldrScratch = nullptr;           // TXAA output, swapped with ldr[cur] after the pass
     uint32_t* tex[4] = { nullptr, nullptr, nullptr, nullptr };
     int texw[4] = { 0, 0, 0, 0 }, texh[4] = { 0, 0, 0, 0 }, texd[4] = { 0, 0, 0, 0 };
     MarchConst* mc = nullptr;
@@ -46,7 +47,7 @@ struct MtContext {
     F4* outHdr = nullptr;  // mtSetCloudOutput overrides
     F4* outMask = nullptr;
     cudaEvent_t ev[MT_PASS_COUNT][2] = {};
-    bool evValid[MT_PASS_COUNT] = { false, false, false, false };
+    bool evValid[MT_PASS_COUNT] = {};
     cudaEvent_t userEv[MT_USER_EVENTS] = {};
     bool userEvValid[MT_USER_EVENTS] = {};
     uint64_t launches = 0;
@@ -78,7 +79,7 @@ static MtStatus cuda_fail(MtContext* c, cudaError_t e, const char* what)
 static size_t image_bytes(const MtContext* c, MtImage w)
 {
     size_t px = (size_t)c->W * (size_t)c->H;
-    return w == MT_IMAGE_LDR ? px * 4 : px * 16;
+    return (w == MT_IMAGE_LDR || w == MT_IMAGE_LDR_PREV) ? px * 4 : px * 16;
 }
 static void* image_ptr(MtContext* c, MtImage w)
 {
@@ -86,7 +87,8 @@ static void* image_ptr(MtContext* c, MtImage w)
         case MT_IMAGE_CLOUD_CUR: return c->hdr[c->cur];
         case MT_IMAGE_CLOUD_PREV: return c->hdr[c->cur ^ 1];
         case MT_IMAGE_GODRAY_MASK: return c->mask;
-        case MT_IMAGE_LDR: return c->ldr;
+        case MT_IMAGE_LDR: return c->ldr[c->cur];
+        case MT_IMAGE_LDR_PREV: return c->ldr[c->cur ^ 1];
     }
     return nullptr;
 }
@@ -94,11 +96,13 @@ static bool is_pow2(uint32_t v) { return v && !(v & (v - 1)); }
 
 static void free_images(MtContext* c)
 {
-    cudaFree(c->hdr[0]); cudaFree(c->hdr[1]); cudaFree(c->mask); cudaFree(c->ldr);
+    cudaFree(c->hdr[0]); cudaFree(c->hdr[1]); cudaFree(c->mask);
+    cudaFree(c->ldr[0]); cudaFree(c->ldr[1]); cudaFree(c->ldrScratch);
+    c->ldr[0] = c->ldr[1] = c->ldrScratch = nullptr;
     cudaFree(c->debug); cudaFree(c->taps); cudaFree(c->maskDecoded); cudaFree(c->rays); cudaFree(c->samples);
     c->maskDecoded = nullptr; c->rays = nullptr; c->samples = nullptr;
     c->hdr[0] = c->hdr[1] = c->mask = nullptr;
-    c->ldr = nullptr; c->debug = nullptr; c->taps = nullptr;
+    c->debug = nullptr; c->taps = nullptr;
 }
 static MtStatus alloc_images(MtContext* c)
 {
@@ -106,12 +110,15 @@ static MtStatus alloc_images(MtContext* c)
     MT_CUDA(c, cudaMalloc((void**)&c->hdr[0], px * 16));
     MT_CUDA(c, cudaMalloc((void**)&c->hdr[1], px * 16));
     MT_CUDA(c, cudaMalloc((void**)&c->mask, px * 16));
-    MT_CUDA(c, cudaMalloc((void**)&c->ldr, px * 4));
+    MT_CUDA(c, cudaMalloc((void**)&c->ldr[0], px * 4));
+    MT_CUDA(c, cudaMalloc((void**)&c->ldr[1], px * 4));
+    MT_CUDA(c, cudaMalloc((void**)&c->ldrScratch, px * 4));
     MT_CUDA(c, cudaMalloc((void**)&c->maskDecoded, (size_t)(c->W + 2) * (size_t)(c->H + 2) * sizeof(float)));
     MT_CUDA(c, cudaMemsetAsync(c->hdr[0], 0, px * 16, c->stream));
     MT_CUDA(c, cudaMemsetAsync(c->hdr[1], 0, px * 16, c->stream));
     MT_CUDA(c, cudaMemsetAsync(c->mask, 0, px * 16, c->stream));
-    MT_CUDA(c, cudaMemsetAsync(c->ldr, 0, px * 4, c->stream));
+    MT_CUDA(c, cudaMemsetAsync(c->ldr[0], 0, px * 4, c->stream));
+    MT_CUDA(c, cudaMemsetAsync(c->ldr[1], 0, px * 4, c->stream));
     c->cur = 0;
     return MT_OK;
 }
@@ -510,7 +517,7 @@ MtStatus mtDispatchToneMap(MtContext* c)
     MT_CUDA(c, cudaSetDevice(c->device));
     ToneMapParams P;
     P.hdr = c->hdr[c->cur];
-    P.ldr = c->ldr;
+    P.ldr = c->ldr[c->cur];
     P.W = c->W; P.H = c->H;
     float ty = c->tm.time[1];  // uint(time.y): truncate, saturate, NaN -> 0
     P.seed = (ty != ty || ty <= 0.0f) ? 0u : (ty >= 4294967296.0f ? 0xffffffffu : (unsigned)ty);
@@ -521,6 +528,32 @@ MtStatus mtDispatchToneMap(MtContext* c)
     return MT_OK;
 }
 
+MtStatus mtDispatchTXAA(MtContext* c)
+{
+    if (!c) return MT_ERR_INVALID;
+    if (!c->haveCam || !c->haveCamOld || !c->haveTime)
+        return fail(c, MT_ERR_NOT_READY, "TXAA dispatch: camera, cameraOld and time uniforms must be set");
+    MT_CUDA(c, cudaSetDevice(c->device));
+    TxaaParams P;
+    memset(&P, 0, sizeof(P));
+    copy_cam(P.cam, c->cam);
+    copy_cam(P.camOld, c->camOld);
+    copy_time(P.tm, c->tm);
+    P.cur = c->ldr[c->cur];
+    P.prev = c->ldr[c->cur ^ 1];
+    P.out = c->ldrScratch;
+    P.W = c->W; P.H = c->H;
+    pass_begin(c, MT_PASS_TXAA);
+    MT_CUDA(c, mt_launch_txaa(P, c->stream));
+    pass_end(c, MT_PASS_TXAA);
+    c->launches += 1;
+    // the shader writes its result back into currentFrameResultImage: the output becomes this frame's LDR image
+    uint32_t* t = c->ldr[c->cur];
+    c->ldr[c->cur] = c->ldrScratch;
+    c->ldrScratch = t;
+    return MT_OK;
+}
+
 MtStatus mtSwapPingPong(MtContext* c)
 {
     if (!c) return MT_ERR_INVALID;
@@ -528,15 +561,21 @@ MtStatus mtSwapPingPong(MtContext* c)
     return MT_OK;
 }
 
-MtStatus mtFrame(MtContext* c, int with_godrays)
+MtStatus mtFrameEx(MtContext* c, uint32_t passes)
 {
     if (!c) return MT_ERR_INVALID;
+    MT_REQUIRE(c, !(passes & MT_FRAME_TXAA) || (passes & MT_FRAME_TONEMAP), "mtFrameEx: TXAA needs the tone-map pass");
     MtStatus st;
     if ((st = reproject_dispatch(c, false)) != MT_OK) return st;
     if ((st = cloud_dispatch(c, 0, nullptr, false)) != MT_OK) return st;
-    if (with_godrays && (st = mtDispatchGodRays(c)) != MT_OK) return st;
-    if ((st = mtDispatchToneMap(c)) != MT_OK) return st;
+    if ((passes & MT_FRAME_GODRAYS) && (st = mtDispatchGodRays(c)) != MT_OK) return st;
+    if ((passes & MT_FRAME_TONEMAP) && (st = mtDispatchToneMap(c)) != MT_OK) return st;
+    if ((passes & MT_FRAME_TXAA) && (st = mtDispatchTXAA(c)) != MT_OK) return st;
     return mtSwapPingPong(c);
+}
+MtStatus mtFrame(MtContext* c, int with_godrays)
+{
+    return mtFrameEx(c, MT_FRAME_TONEMAP | (with_godrays ? MT_FRAME_GODRAYS : 0u));
 }
 
 MtStatus mtSynchronize(MtContext* c)
@@ -550,16 +589,16 @@ MtStatus mtSynchronize(MtContext* c)
 // ---- images -------------------------------------------------------------------------------------------------------
 MtStatus mtImageBytes(const MtContext* c, MtImage which, size_t* bytes)
 {
-    if (!c || !bytes || (int)which < 0 || (int)which > MT_IMAGE_LDR) return MT_ERR_INVALID;
+    if (!c || !bytes || (int)which < 0 || (int)which > MT_IMAGE_LDR_PREV) return MT_ERR_INVALID;
     *bytes = image_bytes(c, which);
     return MT_OK;
 }
 MtStatus mtReadImageRows(MtContext* c, MtImage which, uint32_t row_begin, uint32_t row_end, void* host, size_t bytes)
 {
     if (!c) return MT_ERR_INVALID;
-    MT_REQUIRE(c, (int)which >= 0 && (int)which <= MT_IMAGE_LDR && host != nullptr, "mtReadImageRows: bad arguments");
+    MT_REQUIRE(c, (int)which >= 0 && (int)which <= MT_IMAGE_LDR_PREV && host != nullptr, "mtReadImageRows: bad arguments");
     MT_REQUIRE(c, row_begin <= row_end && row_end <= (uint32_t)c->H, "mtReadImageRows: bad row range");
-    size_t pitch = (size_t)c->W * (which == MT_IMAGE_LDR ? 4 : 16);
+    size_t pitch = (size_t)c->W * ((which == MT_IMAGE_LDR || which == MT_IMAGE_LDR_PREV) ? 4 : 16);
     size_t need = pitch * (row_end - row_begin);
     MT_REQUIRE(c, bytes >= need, "mtReadImageRows: host buffer too small");
     MT_CUDA(c, cudaSetDevice(c->device));
@@ -576,7 +615,7 @@ MtStatus mtReadImage(MtContext* c, MtImage which, void* host, size_t bytes)
 MtStatus mtWriteImage(MtContext* c, MtImage which, const void* host, size_t bytes)
 {
     if (!c) return MT_ERR_INVALID;
-    MT_REQUIRE(c, (int)which >= 0 && (int)which <= MT_IMAGE_LDR && host != nullptr, "mtWriteImage: bad arguments");
+    MT_REQUIRE(c, (int)which >= 0 && (int)which <= MT_IMAGE_LDR_PREV && host != nullptr, "mtWriteImage: bad arguments");
     MT_REQUIRE(c, bytes == image_bytes(c, which), "mtWriteImage: size must equal the image size");
     MT_CUDA(c, cudaSetDevice(c->device));
     MT_CUDA(c, cudaMemcpyAsync(image_ptr(c, which), host, bytes, cudaMemcpyHostToDevice, c->stream));
@@ -590,12 +629,13 @@ MtStatus mtClearImages(MtContext* c)
     MT_CUDA(c, cudaMemsetAsync(c->hdr[0], 0, px * 16, c->stream));
     MT_CUDA(c, cudaMemsetAsync(c->hdr[1], 0, px * 16, c->stream));
     MT_CUDA(c, cudaMemsetAsync(c->mask, 0, px * 16, c->stream));
-    MT_CUDA(c, cudaMemsetAsync(c->ldr, 0, px * 4, c->stream));
+    MT_CUDA(c, cudaMemsetAsync(c->ldr[0], 0, px * 4, c->stream));
+    MT_CUDA(c, cudaMemsetAsync(c->ldr[1], 0, px * 4, c->stream));
     return MT_OK;
 }
 MtStatus mtImageDevicePtr(MtContext* c, MtImage which, void** p)
 {
-    if (!c || !p || (int)which < 0 || (int)which > MT_IMAGE_LDR) return MT_ERR_INVALID;
+    if (!c || !p || (int)which < 0 || (int)which > MT_IMAGE_LDR_PREV) return MT_ERR_INVALID;
     *p = image_ptr(c, which);
     return MT_OK;
 }
@@ -609,7 +649,7 @@ MtStatus mtSetCloudOutput(MtContext* c, void* hdr, void* mask)
 MtStatus mtExportImageHandle(MtContext* c, MtImage which, uint8_t handle[64])
 {
     if (!c) return MT_ERR_INVALID;
-    MT_REQUIRE(c, handle != nullptr && (int)which >= 0 && (int)which <= MT_IMAGE_LDR, "mtExportImageHandle: bad arguments");
+    MT_REQUIRE(c, handle != nullptr && (int)which >= 0 && (int)which <= MT_IMAGE_LDR_PREV, "mtExportImageHandle: bad arguments");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
     MT_CUDA(c, cudaSetDevice(c->device));
     cudaIpcMemHandle_t h;

@@ -89,6 +89,15 @@ struct GodRayParams {
     int f16_emulate;
 };
 
+struct TxaaParams {
+    CamU cam, camOld;
+    TimeU tm;
+    const uint32_t* cur;   // tone-mapped LDR of this frame (RGBA8)
+    const uint32_t* prev;  // presented LDR of the previous frame
+    uint32_t* out;         // result (becomes this frame's LDR image)
+    int W, H;
+};
+
 struct ToneMapParams {
     const F4* hdr;
     uint32_t* ldr;  // packed RGBA8

@@ -189,3 +189,146 @@ MT_DEVICE unsigned tonemap_pixel(const ToneMapParams& P, F4 in, int x, int y)
     float b = MT_POWF(uncharted2(2.5f * in.z) * whitemap, invGamma) + noise;
     return unorm8(r) | (unorm8(g) << 8) | (unorm8(b) << 16) | (255u << 24);
 }
+
+// ---- TXAA (postProcess_TXAA.frag:171-270) ---------------------------------------------------------------
+struct TxaaFrame {  // per-frame: like ReprojFrame, but with the Cloud pass's Halton variant (postProcess_TXAA.frag:63-82)
+    RayBasis basis;
+    f3 eye, ec, o;
+    float C;
+    float jx, jy;
+};
+MT_DEVICE TxaaFrame txaa_frame(const TxaaParams& P)
+{
+    TxaaFrame F;
+    F.basis = ray_basis(P.cam);
+    F.eye = mk3(-P.cam.eye[0], -P.cam.eye[1], -P.cam.eye[2]);
+    F.ec = mk3(F.eye.x, -MT_EARTH_RADIUS, F.eye.z);
+    F.o = (F.eye - F.ec) / MT_R_INNER;
+    F.C = dot3(F.o, F.o) - 1.0f;
+    const int hj = P.tm.frameCountMod16 >> 1;
+    const int hx = hj < 4 ? hj : hj + 4;
+    F.jx = P.tm.halton[hx] / (float)P.W;
+    F.jy = P.tm.halton[hx + 4] / (float)P.H;
+    return F;
+}
+
+struct C4 {
+    float c[4];
+};
+MT_DEVICE C4 ldr_unpack(uint32_t t)
+{
+    C4 r;
+    r.c[0] = (float)(t & 0xffu) * (1.0f / 255.0f);
+    r.c[1] = (float)((t >> 8) & 0xffu) * (1.0f / 255.0f);
+    r.c[2] = (float)((t >> 16) & 0xffu) * (1.0f / 255.0f);
+    r.c[3] = (float)(t >> 24) * (1.0f / 255.0f);
+    return r;
+}
+MT_DEVICE C4 ldr_load(const uint32_t* img, int W, int H, int x, int y)  // imageLoad: zero outside the image
+{
+    if (x < 0 || y < 0 || x >= W || y >= H) {
+        C4 z;
+        z.c[0] = z.c[1] = z.c[2] = z.c[3] = 0.0f;
+        return z;
+    }
+    return ldr_unpack(MT_LDG(img + ((unsigned)y * (unsigned)W + (unsigned)x)));
+}
+MT_DEVICE C4 ldr_border_texel(const uint32_t* img, int W, int H, int x, int y)  // sampler: CLAMP_TO_BORDER, (0,0,0,1)
+{
+    if (x < 0 || y < 0 || x >= W || y >= H) {
+        C4 z;
+        z.c[0] = z.c[1] = z.c[2] = 0.0f; z.c[3] = 1.0f;
+        return z;
+    }
+    return ldr_unpack(MT_LDG(img + ((unsigned)y * (unsigned)W + (unsigned)x)));
+}
+
+// One fragment of the TXAA pass; returns the packed RGBA8 result.
+MT_DEVICE uint32_t txaa_pixel(const TxaaParams& P, const TxaaFrame& F, int x, int y)
+{
+    const float u = ((float)x + 0.5f) / (float)P.W;
+    const float v = ((float)y + 0.5f) / (float)P.H;
+    const f3 dir = cast_ray_dir(P.cam, F.basis, F.eye, u, v, F.jx, F.jy);
+    f3 p = mk3(0.0f, 0.0f, 0.0f);
+    {
+        const float A = dot3(dir, dir);
+        const float B = 2.0f * dot3(dir, F.o);
+        const float disc = B * B - (4.0f * A) * F.C;
+        if (!(disc < 0.0f)) {
+            const float sq = sqrtf(disc);
+            float t = (-B - sq) / (2.0f * A);
+            if (t < 0.0f) t = (-B + sq) / (2.0f * A);
+            if (t >= 0.0f) p = ((F.o + dir * t) * MT_R_INNER) + F.ec;
+        }
+    }
+    const float* m = P.camOld.view;
+    f3 q = mk3(((m[0] * p.x + m[4] * p.y) + m[8] * p.z) + m[12] * 1.0f,
+               ((m[1] * p.x + m[5] * p.y) + m[9] * p.z) + m[13] * 1.0f,
+               ((m[2] * p.x + m[6] * p.y) + m[10] * p.z) + m[14] * 1.0f);
+    q = norm3(q);
+    q = q / (-q.z);
+    const float old_u = (q.x / P.cam.tanFovBy2[0]) * 0.5f + 0.5f;
+    const float old_v = (q.y / P.cam.tanFovBy2[1]) * 0.5f + 0.5f;
+
+    // 3x3 neighbourhood of the tone-mapped frame (order: tl tc tr ml mc mr bl bc br)
+    C4 n[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) n[k] = ldr_load(P.cur, P.W, P.H, x + (k % 3) - 1, y + (k / 3) - 1);
+    float cmin[4], cmax[4], cavg[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        float mn = n[8].c[c], mx = n[8].c[c];
+#pragma unroll
+        for (int j = 7; j >= 0; --j) { mn = fminf(n[j].c[c], mn); mx = fmaxf(n[j].c[c], mx); }
+        float sum = n[0].c[c];
+#pragma unroll
+        for (int j = 1; j < 9; ++j) sum += n[j].c[c];
+        const float avg = sum / 9.0f;
+        const float mn5 = fminf(n[1].c[c], fminf(n[3].c[c], fminf(n[4].c[c], fminf(n[5].c[c], n[7].c[c]))));
+        const float mx5 = fmaxf(n[1].c[c], fmaxf(n[3].c[c], fmaxf(n[4].c[c], fmaxf(n[5].c[c], n[7].c[c]))));
+        const float avg5 = ((((n[1].c[c] + n[3].c[c]) + n[4].c[c]) + n[5].c[c]) + n[7].c[c]) / 5.0f;
+        cmin[c] = 0.5f * (mn + mn5);
+        cmax[c] = 0.5f * (mx + mx5);
+        cavg[c] = 0.5f * (avg + avg5);
+    }
+    // texture(prevFrameImage, old_uv): bilinear, border (0,0,0,1)
+    float prevc[4];
+    {
+        const float tu = old_u * (float)P.W - 0.5f, tv = old_v * (float)P.H - 0.5f;
+        const float fu = floorf(tu), fv = floorf(tv);
+        const float ax = tu - fu, ay = tv - fv;
+        const int x0 = mt_f2i(fu), y0 = mt_f2i(fv);
+        const C4 a = ldr_border_texel(P.prev, P.W, P.H, x0, y0), b = ldr_border_texel(P.prev, P.W, P.H, x0 + 1, y0);
+        const C4 c2 = ldr_border_texel(P.prev, P.W, P.H, x0, y0 + 1), d = ldr_border_texel(P.prev, P.W, P.H, x0 + 1, y0 + 1);
+        const float w00 = (1.0f - ax) * (1.0f - ay), w01 = ax * (1.0f - ay), w10 = (1.0f - ax) * ay, w11 = ax * ay;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) prevc[c] = fmaf(w11, d.c[c], fmaf(w10, c2.c[c], fmaf(w01, b.c[c], w00 * a.c[c])));
+    }
+    // clip_aabb towards the neighbourhood box (:150-169)
+    const float pw = clamp1(cavg[3], cmin[3], cmax[3]);
+    float pclip[4], vclip[4], aunit[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        pclip[c] = 0.5f * (cmax[c] + cmin[c]);
+        const float e = 0.5f * (cmax[c] - cmin[c]) + 0.0000000001f;
+        vclip[c] = prevc[c] - pclip[c];
+        aunit[c] = fabsf(vclip[c] / e);
+    }
+    const float ma = fmaxf(aunit[0], fmaxf(aunit[1], aunit[2]));
+    pclip[3] = pw;
+    vclip[3] = prevc[3] - pw;
+    if (ma > 1.0f) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) prevc[c] = pclip[c] + vclip[c] / ma;
+    }
+    const float* curr = n[4].c;
+    const float lum0 = (curr[0] * 0.2125f + curr[1] * 0.7154f) + curr[2] * 0.0721f;
+    const float lum1 = (prevc[0] * 0.2125f + prevc[1] * 0.7154f) + prevc[2] * 0.0721f;
+    const float diff = fabsf(lum0 - lum1) / fmaxf(lum0, fmaxf(lum1, 0.2f));
+    const float wgt = 1.0f - diff;
+    const float kfb = mix1(0.0f, 0.5f, wgt * wgt);
+    uint32_t o = 0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) o |= unorm8(mix1(prevc[c], curr[c], kfb)) << (8 * c);
+    return o;
+}

@@ -100,6 +100,24 @@ __global__ void __launch_bounds__(256) tonemap_kernel(const __grid_constant__ To
     P.ldr[idx] = tonemap_pixel(P, in, x, y);
 }
 
+// ---- TXAA: one pixel per thread; 9 neighbour + 4 history texels are L1 hits, compulsory traffic 4 + 4 + 4 B/pixel ----
+__global__ void __launch_bounds__(256) txaa_kernel(const __grid_constant__ TxaaParams P)
+{
+    __shared__ TxaaFrame frame;
+    if (threadIdx.x == 0) frame = txaa_frame(P);
+    __syncthreads();
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= P.W || y >= P.H) return;
+    P.out[(size_t)y * P.W + x] = txaa_pixel(P, frame, x, y);
+}
+cudaError_t mt_launch_txaa(const TxaaParams& P, cudaStream_t stream)
+{
+    dim3 grid((unsigned)((P.W + 31) / 32), (unsigned)((P.H + 7) / 8), 1);
+    txaa_kernel<<<grid, 256, 0, stream>>>(P);
+    return cudaGetLastError();
+}
+
 cudaError_t mt_launch_reproject(const ReprojParams& P, cudaStream_t stream)
 {
     dim3 grid((unsigned)((P.W + 31) / 32), (unsigned)((P.H + 7) / 8), 1);

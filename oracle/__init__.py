@@ -140,6 +140,20 @@ def tonemap(tm, hdr, want_f32=False):
     return (ldr, f) if want_f32 else ldr
 
 
+def txaa(cam, cam_old, tm, cur, prev, want_f32=False):
+    H, W, _ = cur.shape
+    cur = np.ascontiguousarray(cur, dtype=np.uint8)
+    prev = np.ascontiguousarray(prev, dtype=np.uint8)
+    out = np.zeros((H, W, 4), np.uint8)
+    f = np.zeros((H, W, 4), np.float32) if want_f32 else None
+    cam = np.ascontiguousarray(cam); cam_old = np.ascontiguousarray(cam_old); tm = np.ascontiguousarray(tm)
+    lib().mto_txaa.restype = C.c_int
+    rc = lib().mto_txaa(_p(cam), _p(cam_old), _p(tm), C.c_int(W), C.c_int(H), _p(cur), _p(prev), _p(out), _p(f))
+    if rc != 0:
+        raise ValueError("mto_txaa: invalid arguments")
+    return (out, f) if want_f32 else out
+
+
 def sample3d(vol, s, t, r):
     vol = np.ascontiguousarray(vol, dtype=np.uint8)
     d, h, w, _ = vol.shape

@@ -810,6 +810,120 @@ int mto_tonemap(const MtTimeUBO* tm, int W, int H, const float* hdr, uint8_t* ld
 }
 
 /* ------------------------------------------------------------------------------------------------ */
+/* TXAA  postProcess_TXAA.frag:171-270.  LDR images are RGBA8 UNORM.           */
+/* The shader reads the 3x3 neighbourhood from, and writes its result to, the SAME storage image from   */
+/* concurrently running fragments (a race); canonical: the neighbourhood is read from the tone-mapped    */
+/* image as it was before the pass, the result goes to `out`.  imageLoad outside the image returns 0.   */
+/* ------------------------------------------------------------------------------------------------ */
+static inline void ldr_load(const uint8_t* img, int W, int H, int x, int y, float out[4])
+{
+    if (x < 0 || y < 0 || x >= W || y >= H) { out[0] = out[1] = out[2] = out[3] = 0.0f; return; }
+    const uint8_t* p = img + 4 * ((size_t)y * W + x);
+    for (int c = 0; c < 4; ++c) out[c] = (float)p[c] * (1.0f / 255.0f);
+}
+/* texture(prevFrameImage, uv): LINEAR, CLAMP_TO_BORDER with opaque black (Texture2D.cpp:75) */
+static void ldr_sample_border(const uint8_t* img, int W, int H, float s, float t, float out[4])
+{
+    float u = s * (float)W - 0.5f, v = t * (float)H - 0.5f;
+    float fu = floorf(u), fv = floorf(v);
+    float ax = u - fu, ay = v - fv;
+    int x0 = f2i(fu), y0 = f2i(fv);
+    float wx[2] = { 1.0f - ax, ax }, wy[2] = { 1.0f - ay, ay };
+    float acc[4] = { 0, 0, 0, 0 };
+    int first = 1;
+    for (int j = 0; j < 2; ++j)
+        for (int i = 0; i < 2; ++i) {
+            float tx[4];
+            int x = x0 + i, y = y0 + j;
+            if (x < 0 || y < 0 || x >= W || y >= H) { tx[0] = tx[1] = tx[2] = 0.0f; tx[3] = 1.0f; }
+            else ldr_load(img, W, H, x, y, tx);
+            float wgt = wx[i] * wy[j];
+            for (int c = 0; c < 4; ++c) {
+                if (first) acc[c] = wgt * tx[c];
+                else acc[c] = fmaf(wgt, tx[c], acc[c]);
+            }
+            first = 0;
+        }
+    for (int c = 0; c < 4; ++c) out[c] = acc[c];
+}
+
+int mto_txaa(const MtCameraUBO* cam, const MtCameraUBO* camOld, const MtTimeUBO* tm, int W, int H, const uint8_t* cur,
+             const uint8_t* prev, uint8_t* out, float* out_f32)
+{
+    if (!cam || !camOld || !tm || !cur || !prev || (!out && !out_f32) || W <= 0 || H <= 0) return 1;
+    const int pixelID = tm->frameCountMod16;
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < H; ++y) {
+        for (int x = 0; x < W; ++x) {
+            float u = ((float)x + 0.5f) / (float)W;
+            float v = ((float)y + 0.5f) / (float)H;
+            v3 eyePos = V3(-cam->eye[0], -cam->eye[1], -cam->eye[2]);
+            Ray ray = cast_ray(cam, tm, u, v, eyePos, pixelID, W, H, 0);
+            v3 earthCenter = eyePos;
+            earthCenter.y = -EARTH_RADIUS;
+            Intersection in = ray_sphere(ray.origin, ray.direction, earthCenter, ATMOSPHERE_RADIUS_INNER);
+            v4 pc = { in.point.x, in.point.y, in.point.z, 1.0f };
+            v4 q4 = mat4_mul_v4(camOld->view, pc);
+            v3 q = normalize3(V3(q4.x, q4.y, q4.z));
+            q = divs3(q, -q.z);
+            float old_u = (q.x / cam->tanFovBy2[0]) * 0.5f + 0.5f;
+            float old_v = (q.y / cam->tanFovBy2[1]) * 0.5f + 0.5f;
+
+            /* neighbourHoodClamping, :171-199; order: tl tc tr ml mc mr bl bc br */
+            float n[9][4];
+            int k = 0;
+            for (int dy = -1; dy <= 1; ++dy)
+                for (int dx = -1; dx <= 1; ++dx) ldr_load(cur, W, H, x + dx, y + dy, n[k++]);
+            float cmin[4], cmax[4], cavg[4];
+            for (int c = 0; c < 4; ++c) {
+                float mn = n[8][c], mx = n[8][c];
+                for (int j = 7; j >= 0; --j) { mn = fminf(n[j][c], mn); mx = fmaxf(n[j][c], mx); }
+                float sum = n[0][c];
+                for (int j = 1; j < 9; ++j) sum += n[j][c];
+                float avg = sum / 9.0f;
+                float mn5 = fminf(n[1][c], fminf(n[3][c], fminf(n[4][c], fminf(n[5][c], n[7][c]))));
+                float mx5 = fmaxf(n[1][c], fmaxf(n[3][c], fmaxf(n[4][c], fmaxf(n[5][c], n[7][c]))));
+                float avg5 = ((((n[1][c] + n[3][c]) + n[4][c]) + n[5][c]) + n[7][c]) / 5.0f;
+                cmin[c] = 0.5f * (mn + mn5);
+                cmax[c] = 0.5f * (mx + mx5);
+                cavg[c] = 0.5f * (avg + avg5);
+            }
+            const float* curr = n[4];
+            float prevc[4];
+            ldr_sample_border(prev, W, H, old_u, old_v, prevc);
+
+            /* clip_aabb(cmin.xyz, cmax.xyz, clamp(cavg, cmin, cmax), prevColor), :150-169 */
+            float pw = clampf(cavg[3], cmin[3], cmax[3]);
+            float pclip[4], vclip[4], aunit[3];
+            for (int c = 0; c < 3; ++c) {
+                pclip[c] = 0.5f * (cmax[c] + cmin[c]);
+                float e = 0.5f * (cmax[c] - cmin[c]) + 0.0000000001f; /* EPSILON */
+                vclip[c] = prevc[c] - pclip[c];
+                aunit[c] = fabsf(vclip[c] / e);
+            }
+            float ma = fmaxf(aunit[0], fmaxf(aunit[1], aunit[2]));
+            pclip[3] = pw;
+            vclip[3] = prevc[3] - pw;
+            if (ma > 1.0f)
+                for (int c = 0; c < 4; ++c) prevc[c] = pclip[c] + vclip[c] / ma;
+
+            float lum0 = (curr[0] * 0.2125f + curr[1] * 0.7154f) + curr[2] * 0.0721f;
+            float lum1 = (prevc[0] * 0.2125f + prevc[1] * 0.7154f) + prevc[2] * 0.0721f;
+            float diff = fabsf(lum0 - lum1) / fmaxf(lum0, fmaxf(lum1, 0.2f));
+            float wgt = 1.0f - diff;
+            float kfb = mixf(0.0f, 0.5f, wgt * wgt);
+            size_t idx = (size_t)y * W + x;
+            for (int c = 0; c < 4; ++c) {
+                float o = mixf(prevc[c], curr[c], kfb);
+                if (out) out[4 * idx + c] = to_unorm8(o);
+                if (out_f32) out_f32[4 * idx + c] = o;
+            }
+        }
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
 /* small exported helpers used by unit tests                                                         */
 /* ------------------------------------------------------------------------------------------------ */
 void mto_encode_float_rgba(float v, float out[4])

@@ -36,6 +36,11 @@ int mto_godrays(const MtCameraUBO* cam, const MtSunAndSkyUBO* sky, int W, int H,
 /* postProcess_ToneMap.frag main(); ldr = RGBA8 UNORM (may be NULL), ldr_f32 = unquantised RGBA32F (may be NULL). */
 int mto_tonemap(const MtTimeUBO* tm, int W, int H, const float* hdr, uint8_t* ldr, float* ldr_f32);
 
+/* postProcess_TXAA.frag main() (the pass after tone map in the reference frame): cur = tone-mapped LDR of this frame,
+ * prev = presented LDR of the previous frame; out (RGBA8) and/or out_f32 (unquantised) receive the result. */
+int mto_txaa(const MtCameraUBO* cam, const MtCameraUBO* camOld, const MtTimeUBO* tm, int W, int H, const uint8_t* cur,
+             const uint8_t* prev, uint8_t* out, float* out_f32);
+
 /* unit-test hooks */
 void mto_sample3d(const uint8_t* vol, int W, int H, int D, float s, float t, float r, float out[4]);
 void mto_sample2d(const uint8_t* img, int W, int H, float s, float t, float out[4]);

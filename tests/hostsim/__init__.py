@@ -74,3 +74,12 @@ def tonemap(tm, hdr):
     tm = np.ascontiguousarray(tm)
     lib().hs_tonemap(_p(tm), W, H, _p(hdr), _p(ldr))
     return ldr.view(np.uint8).reshape(H, W, 4)
+
+
+def txaa(cam, cam_old, tm, cur, prev):
+    H, W, _ = cur.shape
+    out = np.zeros((H, W), np.uint32)
+    cam, cam_old, tm = (np.ascontiguousarray(x) for x in (cam, cam_old, tm))
+    cur = np.ascontiguousarray(cur); prev = np.ascontiguousarray(prev)
+    lib().hs_txaa(_p(cam), _p(cam_old), _p(tm), W, H, _p(cur), _p(prev), _p(out))
+    return out.view(np.uint8).reshape(H, W, 4)

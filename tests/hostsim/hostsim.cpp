@@ -155,4 +155,20 @@ int hs_tonemap(const MtTimeUBO* tm, int W, int H, const float* hdr, uint32_t* ld
     return 0;
 }
 
+int hs_txaa(const MtCameraUBO* cam, const MtCameraUBO* camOld, const MtTimeUBO* tm, int W, int H, const uint32_t* cur,
+            const uint32_t* prev, uint32_t* out)
+{
+    TxaaParams P;
+    memset(&P, 0, sizeof(P));
+    memcpy(&P.cam, cam, sizeof(CamU));
+    memcpy(&P.camOld, camOld, sizeof(CamU));
+    memcpy(&P.tm, tm, sizeof(TimeU));
+    P.cur = cur; P.prev = prev; P.out = out;
+    P.W = W; P.H = H;
+    TxaaFrame F = txaa_frame(P);
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) out[(size_t)y * W + x] = txaa_pixel(P, F, x, y);
+    return 0;
+}
+
 }  // extern "C"

@@ -74,6 +74,41 @@ def test_post_cores_bit_identical(oracle_mod, hostsim):
     assert np.array_equal(oracle_mod.tonemap(sc.ubo(), hdr * 4), hostsim.tonemap(sc.ubo(), hdr * 4))
 
 
+def test_txaa_core_bit_identical(oracle_mod, hostsim):
+    from meteoros_b200 import scene
+
+    w, h = 150, 84
+    rng = np.random.default_rng(9)
+    cur = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+    prev = np.roll(cur, 2, axis=1)
+    prev[::7] = rng.integers(0, 256, prev[::7].shape, dtype=np.uint8)
+    cam = scene.Camera(w, h)
+    old = cam.ubo()
+    cam.rotate_about_up(0.25)
+    sc = scene.Scene()
+    for fid in (0, 5, 15):
+        sc.time["frameCountMod16"] = fid
+        assert np.array_equal(oracle_mod.txaa(cam.ubo(), old, sc.ubo(), cur, prev), hostsim.txaa(cam.ubo(), old, sc.ubo(), cur, prev))
+
+
+def test_txaa_properties(oracle_mod):
+    """Static camera, identical smooth history: the blend returns the current frame; a history far outside the
+    neighbourhood box is clipped to it (postProcess_TXAA.frag:150-169)."""
+    from meteoros_b200 import scene
+
+    w, h = 64, 36
+    cam = scene.Camera(w, h).ubo()
+    sc = scene.Scene()
+    sc.update_time(1 / 60)
+    smooth = np.tile(np.linspace(40, 210, w).astype(np.uint8)[None, :, None], (h, 1, 4))
+    out = oracle_mod.txaa(cam, cam, sc.ubo(), smooth, smooth)
+    assert np.abs(out.astype(int) - smooth.astype(int))[2:-2, 2:-2].max() <= 1
+    flat = np.full((h, w, 4), 100, np.uint8)
+    wild = np.full((h, w, 4), 250, np.uint8)
+    out = oracle_mod.txaa(cam, cam, sc.ubo(), flat, wild)
+    assert np.abs(out.astype(int)[3:-3, 3:-3, :3] - 100).max() <= 1  # history clipped onto the (degenerate) box
+
+
 def test_static_camera_reprojects_onto_itself(oracle_mod):
     """reprojection.comp does not flip v (:200-201) yet lands on (nearly) the same pixel when the camera is static:
     the ten taps stay within two texels of the pixel."""

@@ -20,7 +20,7 @@ def main():
     w, h = a.width, a.height
     flags = api.FLAG_PASS_TIMING | (api.FLAG_SEQUENTIAL_MARCH if a.sequential else 0)
     cam, sc, sky = scene.Camera(w, h), scene.Scene(), scene.Sky()
-    names = ["reproject", "cloud(1/16)", "godrays", "tonemap"]
+    names = ["reproject", "cloud(1/16)", "godrays", "tonemap", "txaa"]
     t = {n: [] for n in names}
     with api.CloudRenderer(w, h, flags=flags) as r:
         r.upload_noise(textures.load_noise())
@@ -30,7 +30,7 @@ def main():
             cam.rotate_about_up(0.25)
             sc.update_time(1 / 60)
             r.set_camera(cam.ubo()); r.set_camera_old(old); r.set_time(sc.ubo())
-            r.frame(True)
+            r.frame(True, True)
             old = cam.ubo()
             if f >= 16:
                 for k, n in enumerate(names):
