@@ -297,25 +297,34 @@ def main():
     clocks = sampler.stop()
     dev_ms_total = float(sum(step_ms))
 
-    # ---- end-to-end region: host uniforms in, HDR frame out to pinned host memory, every step
-    out_which = api.IMAGE_CLOUD_CUR if args.workload != "seq1080p" else api.IMAGE_LDR_PREV  # the frame just finished (roles swapped)
-    nbytes = w * h * (4 if args.workload == "seq1080p" else 16)
-    pinned = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    # ---- end-to-end region: host uniforms in, finished frame out to pinned host memory, every step.  The read-back of
+    # frame k runs on the context's copy stream while frame k+1 renders into the other ping-pong image (mtReadImageAsync).
+    seq = args.workload == "seq1080p"
+    out_which = api.IMAGE_LDR_PREV if seq else api.IMAGE_CLOUD_PREV  # after the swap: the frame just finished
+    nbytes = w * h * (4 if seq else 16)
+    pinned = [torch.empty(nbytes, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
     h2d = int(cam.nbytes + tm.nbytes + tun.nbytes + sky.nbytes)
     e2e_read = (rank == 0) or args.workload != "frame8k"
-    for _ in range(2):
-        step()
-        if e2e_read:
-            r.read_image_into(out_which, pinned.data_ptr(), nbytes)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        r.set_camera(cam); r.set_time(tm); r.set_tuning(tun); r.set_sun_and_sky(sky)
+
+    def e2e_step(i):
+        if not seq:
+            r.set_camera(cam); r.set_time(tm); r.set_tuning(tun); r.set_sun_and_sky(sky)
         step()
         if args.workload == "frame8k" and world > 1:
             shard.finish()
+        if not seq:
+            r.swap_ping_pong()  # mtFrame swaps by itself
         if e2e_read:
-            r.read_image_into(out_which, pinned.data_ptr(), nbytes)  # synchronises
+            r.read_image_async(out_which, pinned[i & 1].data_ptr(), nbytes)
+
+    for i in range(2):
+        e2e_step(i)
+    r.wait_reads()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        e2e_step(i)
+    r.wait_reads()
     barrier()
     e2e_s = time.perf_counter() - t0
 

@@ -213,6 +213,12 @@ MT_API MtStatus mtSynchronize(MtContext* ctx);    /* vkQueueWaitIdle */
 MT_API MtStatus mtImageBytes(const MtContext* ctx, MtImage which, size_t* bytes);
 MT_API MtStatus mtReadImage(MtContext* ctx, MtImage which, void* host, size_t bytes);        /* D2H + sync   */
 MT_API MtStatus mtReadImageRows(MtContext* ctx, MtImage which, uint32_t row_begin, uint32_t row_end, void* host, size_t bytes);
+/* Asynchronous read-back on the context's copy stream: starts when the work issued so far has produced the image, runs
+ * concurrently with later dispatches, and any later pass that would overwrite that image waits for it.  `host` should be
+ * pinned; it is valid after mtWaitReads (or mtSynchronize).  With the ping-pong swap this hides the read-back of frame k
+ * behind the rendering of frame k+1.                                                                                  */
+MT_API MtStatus mtReadImageAsync(MtContext* ctx, MtImage which, void* host, size_t bytes);
+MT_API MtStatus mtWaitReads(MtContext* ctx);
 MT_API MtStatus mtWriteImage(MtContext* ctx, MtImage which, const void* host, size_t bytes); /* H2D, ordered */
 MT_API MtStatus mtClearImages(MtContext* ctx);    /* zero all four images (reference: images are never cleared; zeros assumed) */
 MT_API MtStatus mtImageDevicePtr(MtContext* ctx, MtImage which, void** dev_ptr);             /* zero-copy interop */

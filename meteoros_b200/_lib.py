@@ -76,6 +76,8 @@ PROTOTYPES = {
     "mtImageBytes": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_size_t)]),
     "mtReadImage": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
     "mtReadImageRows": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t]),
+    "mtReadImageAsync": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
+    "mtWaitReads": (C.c_int, [C.c_void_p]),
     "mtWriteImage": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
     "mtClearImages": (C.c_int, [C.c_void_p]),
     "mtImageDevicePtr": (C.c_int, [C.c_void_p, C.c_int, c_void_pp]),

@@ -213,6 +213,13 @@ class CloudRenderer:
     def read_image_into(self, which: int, host_ptr: int, nbytes: int):
         self._check(self._lib.mtReadImage(self._h, which, C.c_void_p(host_ptr), nbytes), "mtReadImage")
 
+    def read_image_async(self, which: int, host_ptr: int, nbytes: int):
+        """D2H on the copy stream, overlapping later dispatches; valid after wait_reads()."""
+        self._check(self._lib.mtReadImageAsync(self._h, which, C.c_void_p(host_ptr), nbytes), "mtReadImageAsync")
+
+    def wait_reads(self):
+        self._check(self._lib.mtWaitReads(self._h), "mtWaitReads")
+
     def clear_images(self):
         self._check(self._lib.mtClearImages(self._h), "mtClearImages")
 

@@ -22,6 +22,9 @@ struct MtContext {
     uint32_t storage = MT_STORAGE_F32;
     uint32_t flags = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copyStream = nullptr;   // mtReadImageAsync
+    cudaEvent_t producedEv = nullptr;    // main stream -> copy stream
+    struct PendingRead { const void* dev; cudaEvent_t done; bool active; } pending[4] = {};
     F4* hdr[2] = { nullptr, nullptr };
     int cur = 0;  // index of the image that currently plays "currentFrameResultImage"
     F4* mask = nullptr;
@@ -91,6 +94,15 @@ static void* image_ptr(MtContext* c, MtImage w)
         case MT_IMAGE_LDR_PREV: return c->ldr[c->cur ^ 1];
     }
     return nullptr;
+}
+// A pass is about to write device memory `dev`: make the main stream wait for an in-flight asynchronous read of it.
+static void wait_pending_read(MtContext* c, const void* dev)
+{
+    for (auto& p : c->pending)
+        if (p.active && p.dev == dev) {
+            cudaStreamWaitEvent(c->stream, p.done, 0);
+            p.active = false;
+        }
 }
 static bool is_pow2(uint32_t v) { return v && !(v & (v - 1)); }
 
@@ -182,6 +194,11 @@ MtStatus mtCreate(const MtConfig* cfg, MtContext** out)
     do {
         if (cudaSetDevice(c->device) != cudaSuccess) { st = MT_ERR_CUDA; break; }
         if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { st = MT_ERR_CUDA; break; }
+        if (cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking) != cudaSuccess) { st = MT_ERR_CUDA; break; }
+        if (cudaEventCreateWithFlags(&c->producedEv, cudaEventDisableTiming) != cudaSuccess) { st = MT_ERR_CUDA; break; }
+        for (auto& p : c->pending)
+            if (cudaEventCreateWithFlags(&p.done, cudaEventDisableTiming) != cudaSuccess) st = MT_ERR_CUDA;
+        if (st != MT_OK) break;
         for (int p = 0; p < MT_PASS_COUNT; ++p) {
             if (cudaEventCreate(&c->ev[p][0]) != cudaSuccess || cudaEventCreate(&c->ev[p][1]) != cudaSuccess) st = MT_ERR_CUDA;
         }
@@ -204,6 +221,10 @@ void mtDestroy(MtContext* c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->copyStream) { cudaStreamSynchronize(c->copyStream); cudaStreamDestroy(c->copyStream); }
+    if (c->producedEv) cudaEventDestroy(c->producedEv);
+    for (auto& p : c->pending)
+        if (p.done) cudaEventDestroy(p.done);
     free_images(c);
     for (int i = 0; i < 4; ++i) cudaFree(c->tex[i]);
     cudaFree(c->mc);
@@ -400,6 +421,8 @@ static MtStatus cloud_dispatch(MtContext* c, int full, const RowTiles* tiles, bo
     }
     P.rays = c->rays;
     P.samples = c->samples;
+    wait_pending_read(c, P.hdr);
+    wait_pending_read(c, P.mask);
     MT_CUDA(c, mt_launch_cloud_setup(P, c->mc, c->stream));
     pass_begin(c, MT_PASS_CLOUD);
     int n = 1;
@@ -466,6 +489,7 @@ static MtStatus reproject_dispatch(MtContext* c, bool debug)
         if (!c->taps) MT_CUDA(c, cudaMalloc((void**)&c->taps, (size_t)c->W * c->H * 10 * sizeof(int)));
         P.taps = c->taps;
     }
+    wait_pending_read(c, P.cur);
     pass_begin(c, MT_PASS_REPROJECT);
     MT_CUDA(c, mt_launch_reproject(P, c->stream));
     pass_end(c, MT_PASS_REPROJECT);
@@ -503,6 +527,7 @@ MtStatus mtDispatchGodRays(MtContext* c)
     P.hdr = c->hdr[c->cur];
     P.W = c->W; P.H = c->H;
     P.f16_emulate = c->storage == MT_STORAGE_F16_EMULATE;
+    wait_pending_read(c, P.hdr);
     pass_begin(c, MT_PASS_GODRAYS);
     MT_CUDA(c, mt_launch_godrays(P, c->stream));
     pass_end(c, MT_PASS_GODRAYS);
@@ -521,6 +546,7 @@ MtStatus mtDispatchToneMap(MtContext* c)
     P.W = c->W; P.H = c->H;
     float ty = c->tm.time[1];  // uint(time.y): truncate, saturate, NaN -> 0
     P.seed = (ty != ty || ty <= 0.0f) ? 0u : (ty >= 4294967296.0f ? 0xffffffffu : (unsigned)ty);
+    wait_pending_read(c, P.ldr);
     pass_begin(c, MT_PASS_TONEMAP);
     MT_CUDA(c, mt_launch_tonemap(P, c->stream));
     pass_end(c, MT_PASS_TONEMAP);
@@ -543,6 +569,7 @@ MtStatus mtDispatchTXAA(MtContext* c)
     P.prev = c->ldr[c->cur ^ 1];
     P.out = c->ldrScratch;
     P.W = c->W; P.H = c->H;
+    wait_pending_read(c, P.out);
     pass_begin(c, MT_PASS_TXAA);
     MT_CUDA(c, mt_launch_txaa(P, c->stream));
     pass_end(c, MT_PASS_TXAA);
@@ -583,6 +610,8 @@ MtStatus mtSynchronize(MtContext* c)
     if (!c) return MT_ERR_INVALID;
     MT_CUDA(c, cudaSetDevice(c->device));
     MT_CUDA(c, cudaStreamSynchronize(c->stream));
+    MT_CUDA(c, cudaStreamSynchronize(c->copyStream));
+    for (auto& p : c->pending) p.active = false;
     return MT_OK;
 }
 
@@ -612,12 +641,46 @@ MtStatus mtReadImage(MtContext* c, MtImage which, void* host, size_t bytes)
     if (!c) return MT_ERR_INVALID;
     return mtReadImageRows(c, which, 0, (uint32_t)c->H, host, bytes);
 }
+MtStatus mtReadImageAsync(MtContext* c, MtImage which, void* host, size_t bytes)
+{
+    if (!c) return MT_ERR_INVALID;
+    MT_REQUIRE(c, (int)which >= 0 && (int)which <= MT_IMAGE_LDR_PREV && host != nullptr, "mtReadImageAsync: bad arguments");
+    MT_REQUIRE(c, bytes >= image_bytes(c, which), "mtReadImageAsync: host buffer too small");
+    MT_CUDA(c, cudaSetDevice(c->device));
+    const void* dev = image_ptr(c, which);
+    MtContext::PendingRead* slot = nullptr;
+    for (auto& p : c->pending)
+        if (p.active && p.dev == dev) slot = &p;     // a second read of the same image re-uses its slot
+    for (auto& p : c->pending)
+        if (!slot && !p.active) slot = &p;
+    if (!slot) {                                     // all slots busy: retire the oldest by waiting for the copy stream
+        MT_CUDA(c, cudaStreamSynchronize(c->copyStream));
+        for (auto& p : c->pending) p.active = false;
+        slot = &c->pending[0];
+    }
+    MT_CUDA(c, cudaEventRecord(c->producedEv, c->stream));
+    MT_CUDA(c, cudaStreamWaitEvent(c->copyStream, c->producedEv, 0));
+    MT_CUDA(c, cudaMemcpyAsync(host, dev, image_bytes(c, which), cudaMemcpyDeviceToHost, c->copyStream));
+    MT_CUDA(c, cudaEventRecord(slot->done, c->copyStream));
+    slot->dev = dev;
+    slot->active = true;
+    return MT_OK;
+}
+MtStatus mtWaitReads(MtContext* c)
+{
+    if (!c) return MT_ERR_INVALID;
+    MT_CUDA(c, cudaSetDevice(c->device));
+    MT_CUDA(c, cudaStreamSynchronize(c->copyStream));
+    for (auto& p : c->pending) p.active = false;
+    return MT_OK;
+}
 MtStatus mtWriteImage(MtContext* c, MtImage which, const void* host, size_t bytes)
 {
     if (!c) return MT_ERR_INVALID;
     MT_REQUIRE(c, (int)which >= 0 && (int)which <= MT_IMAGE_LDR_PREV && host != nullptr, "mtWriteImage: bad arguments");
     MT_REQUIRE(c, bytes == image_bytes(c, which), "mtWriteImage: size must equal the image size");
     MT_CUDA(c, cudaSetDevice(c->device));
+    wait_pending_read(c, image_ptr(c, which));
     MT_CUDA(c, cudaMemcpyAsync(image_ptr(c, which), host, bytes, cudaMemcpyHostToDevice, c->stream));
     return MT_OK;
 }
@@ -625,6 +688,8 @@ MtStatus mtClearImages(MtContext* c)
 {
     if (!c) return MT_ERR_INVALID;
     MT_CUDA(c, cudaSetDevice(c->device));
+    for (auto& p : c->pending)
+        if (p.active) wait_pending_read(c, p.dev);
     size_t px = (size_t)c->W * c->H;
     MT_CUDA(c, cudaMemsetAsync(c->hdr[0], 0, px * 16, c->stream));
     MT_CUDA(c, cudaMemsetAsync(c->hdr[1], 0, px * 16, c->stream));

@@ -335,6 +335,32 @@ def test_f16_storage_emulation(api, oracle_mod, noise):
     assert rel_err(hdr[finite], want[finite]).max() <= 2e-3               # at most one binary16 ulp apart
 
 
+def test_async_readback_overlaps_next_frame(api, noise):
+    """mtReadImageAsync: frame k is copied out on the copy stream while frame k+1 renders into the other ping-pong
+    image; a third frame that re-uses the first image must wait for its copy."""
+    import torch
+
+    w, h = 512, 288
+    views = [default_scene(w, h, yaw=10.0 * k) for k in range(3)]
+    with make_renderer(api, noise, w, h) as r:
+        want = []
+        for cam, tm, _, _ in views:
+            r.set_camera(cam); r.set_time(tm)
+            r.dispatch_cloud_full()
+            want.append(r.read_image(api.IMAGE_CLOUD_CUR))
+        assert not np.array_equal(want[0], want[1])
+        bufs = [torch.empty(w * h * 16, dtype=torch.uint8, pin_memory=True) for _ in range(3)]
+        for k, (cam, tm, _, _) in enumerate(views):
+            r.set_camera(cam); r.set_time(tm)
+            r.dispatch_cloud_full()
+            r.swap_ping_pong()
+            r.read_image_async(api.IMAGE_CLOUD_PREV, bufs[k].data_ptr(), w * h * 16)
+        r.wait_reads()
+        for k in range(3):
+            got = bufs[k].numpy().view(np.float32).reshape(h, w, 4)
+            assert np.array_equal(got, want[k])
+
+
 def test_error_paths(api, noise):
     with api.CloudRenderer(64, 36) as r:
         with pytest.raises(api.MeteorosError) as e:
