@@ -184,6 +184,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cloud4k", choices=["cloud4k", "frame8k", "seq1080p"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ctx-flags", type=int, default=0, help="extra MT_FLAG_* bits for A/B runs (e.g. 8 = no quad layout)")
     ap.add_argument("--sweep", action="store_true", help="N>1: rank r renders view r of the sun/coverage sweep")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -228,7 +229,7 @@ def main():
         counters = rc.counters()
         fp32_peak_gflops = rc.measure_fp32_peak_gflops()
 
-    r = api.CloudRenderer(w, h, device=local_rank, flags=api.FLAG_PASS_TIMING if args.workload == "seq1080p" else 0)
+    r = api.CloudRenderer(w, h, device=local_rank, flags=(api.FLAG_PASS_TIMING if args.workload == "seq1080p" else 0) | args.ctx_flags)
     r.upload_noise(noise)
     r.set_camera(cam); r.set_camera_old(cam); r.set_time(tm); r.set_sun_and_sky(sky); r.set_tuning(tun)
     from meteoros_b200 import scene as _scene

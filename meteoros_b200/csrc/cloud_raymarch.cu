@@ -43,6 +43,33 @@ __global__ void __launch_bounds__(256) occupancy_build_kernel(Tex3D T, uint32_t*
     occ[wi] = bits;
 }
 
+// quads[(z*h + y)*w + x] = the 2x2 texels of filter cell (x, y) in slice z, REPEAT applied (d = 1 for 2D textures)
+__global__ void __launch_bounds__(256) build_quads_kernel(const uint32_t* __restrict__ t, int w, int h, int d, uint4* __restrict__ q)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned n = (unsigned)w * (unsigned)h * (unsigned)d;
+    if (i >= n) return;
+    const unsigned x = i % (unsigned)w, y = (i / (unsigned)w) % (unsigned)h, z = i / ((unsigned)w * (unsigned)h);
+    const unsigned x1 = (x + 1u) & (unsigned)(w - 1), y1 = (y + 1u) & (unsigned)(h - 1);
+    const unsigned r0 = (z * h + y) * w, r1 = (z * h + y1) * w;
+#if MT_TEX_BRICKS
+    if (d > 1) {
+        const unsigned z1 = (z + 1u) & (unsigned)(d - 1);
+        const unsigned s0 = (z1 * h + y) * w, s1 = (z1 * h + y1) * w;
+        q[2 * i] = make_uint4(t[r0 + x], t[r0 + x1], t[r1 + x], t[r1 + x1]);
+        q[2 * i + 1] = make_uint4(t[s0 + x], t[s0 + x1], t[s1 + x], t[s1 + x1]);
+        return;
+    }
+#endif
+    q[i] = make_uint4(t[r0 + x], t[r0 + x1], t[r1 + x], t[r1 + x1]);
+}
+cudaError_t mt_launch_build_quads(const uint32_t* texels, int w, int h, int d, void* quads, cudaStream_t stream)
+{
+    const unsigned n = (unsigned)w * (unsigned)h * (unsigned)d;
+    build_quads_kernel<<<(n + 255) / 256, 256, 0, stream>>>(texels, w, h, d, (uint4*)quads);
+    return cudaGetLastError();
+}
+
 cudaError_t mt_launch_occupancy(const Tex3D& low, uint32_t* occ, float coverage, cudaStream_t stream)
 {
     const unsigned nwords = (unsigned)(low.w >> 5) * (unsigned)low.h * (unsigned)low.d;

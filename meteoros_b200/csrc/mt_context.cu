@@ -32,6 +32,7 @@ struct MtContext {
     uint32_t* ldr[2] = { nullptr, nullptr };  // ping-pong with the HDR images (same `cur`)
     uint32_t* ldrScratch = nullptr;           // TXAA output, swapped with ldr[cur] after the pass
     uint32_t* tex[4] = { nullptr, nullptr, nullptr, nullptr };
+    void* quads[4] = { nullptr, nullptr, nullptr, nullptr };  // per-cell 2x2 texel quads (mt_tex.cuh), built at upload
     int texw[4] = { 0, 0, 0, 0 }, texh[4] = { 0, 0, 0, 0 }, texd[4] = { 0, 0, 0, 0 };
     MarchConst* mc = nullptr;
     uint32_t* occ = nullptr;      // empty-cell bitmap of the low-frequency volume (mt_tex.cuh)
@@ -226,7 +227,7 @@ void mtDestroy(MtContext* c)
     for (auto& p : c->pending)
         if (p.done) cudaEventDestroy(p.done);
     free_images(c);
-    for (int i = 0; i < 4; ++i) cudaFree(c->tex[i]);
+    for (int i = 0; i < 4; ++i) { cudaFree(c->tex[i]); cudaFree(c->quads[i]); }
     cudaFree(c->mc);
     cudaFree(c->occ);
     cudaFree(c->counters);
@@ -317,6 +318,13 @@ static MtStatus upload(MtContext* c, int slot, uint32_t w, uint32_t h, uint32_t 
     }
     MT_CUDA(c, cudaMalloc((void**)&c->tex[slot], bytes));
     MT_CUDA(c, cudaMemcpyAsync(c->tex[slot], rgba8, bytes, cudaMemcpyHostToDevice, c->stream));
+    cudaFree(c->quads[slot]);
+    c->quads[slot] = nullptr;
+    if (slot != MT_TEX_WEATHER) {  // the weather map is never sampled
+        MT_CUDA(c, cudaMalloc(&c->quads[slot], bytes * 4 * ((MT_TEX_BRICKS && d > 1) ? 2 : 1)));
+        MT_CUDA(c, mt_launch_build_quads(c->tex[slot], (int)w, (int)h, (int)d, c->quads[slot], c->stream));
+        c->launches += 1;
+    }
     MT_CUDA(c, cudaStreamSynchronize(c->stream));  // the caller may free its buffer on return
     c->texw[slot] = (int)w; c->texh[slot] = (int)h; c->texd[slot] = (int)d;
     if (slot == MT_TEX_LOW_FREQ) {
@@ -376,6 +384,9 @@ static MtStatus cloud_dispatch(MtContext* c, int full, const RowTiles* tiles, bo
     copy_time(P.tm, c->tm);
     P.tun = c->tun;
     mt_host_sky_const(c->cam, c->tun, P.sky);
+    P.low.quads = (const Quad*)c->quads[MT_TEX_LOW_FREQ];
+    P.high.quads = (const Quad*)c->quads[MT_TEX_HIGH_FREQ];
+    P.curl.quads = (const Quad*)c->quads[MT_TEX_CURL];
     P.low.texels = c->tex[MT_TEX_LOW_FREQ];
     P.low.w = c->texw[MT_TEX_LOW_FREQ]; P.low.h = c->texh[MT_TEX_LOW_FREQ]; P.low.d = c->texd[MT_TEX_LOW_FREQ];
     P.high.texels = c->tex[MT_TEX_HIGH_FREQ];

@@ -16,9 +16,10 @@ def main():
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--frames", type=int, default=48)
     ap.add_argument("--sequential", action="store_true")
+    ap.add_argument("--ctx-flags", type=int, default=0)
     a = ap.parse_args()
     w, h = a.width, a.height
-    flags = api.FLAG_PASS_TIMING | (api.FLAG_SEQUENTIAL_MARCH if a.sequential else 0)
+    flags = api.FLAG_PASS_TIMING | (api.FLAG_SEQUENTIAL_MARCH if a.sequential else 0) | a.ctx_flags
     cam, sc, sky = scene.Camera(w, h), scene.Scene(), scene.Sky()
     names = ["reproject", "cloud(1/16)", "godrays", "tonemap", "txaa"]
     t = {n: [] for n in names}
