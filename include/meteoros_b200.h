@@ -231,6 +231,31 @@ MT_API MtStatus mtExportImageHandle(MtContext* ctx, MtImage which, uint8_t handl
 MT_API MtStatus mtOpenPeerImage(MtContext* ctx, const uint8_t handle[64], void** dev_ptr);
 MT_API MtStatus mtClosePeerImage(MtContext* ctx, void* dev_ptr);
 
+/* ---- uniform producers: the host-side state the reference keeps in Camera / Scene / Sky ------------------ */
+/* Pure host functions (no context, no GPU): a C/C++ application links them instead of re-deriving glm's arithmetic.        */
+typedef struct MtxCamera {       /* camera.h:20-68 */
+    float eye[3], ref[3];        /* position, look-at point                                   */
+    float forward[3], right[3], up[3];
+    float fovy_deg, aspect, near_clip, far_clip;
+    int32_t width, height;
+} MtxCamera;
+/* Camera::Camera + RecomputeAttributes (camera.cpp:3-17, 68-77).  Reference default: eye (0,0,2), ref (0,0,1), 45, .1, 1000. */
+MT_API void mtxCameraInit(MtxCamera* cam, int32_t width, int32_t height, const float eye[3], const float ref[3], float fovy_deg,
+                          float near_clip, float far_clip);
+MT_API void mtxCameraRotateAboutUp(MtxCamera* cam, float deg);       /* camera.cpp:79-87  */
+MT_API void mtxCameraRotateAboutRight(MtxCamera* cam, float deg);    /* camera.cpp:88-96  */
+MT_API void mtxCameraTranslateAlongLook(MtxCamera* cam, float amt);  /* camera.cpp:98-104 */
+MT_API void mtxCameraTranslateAlongRight(MtxCamera* cam, float amt); /* camera.cpp:105-111 */
+MT_API void mtxCameraTranslateAlongUp(MtxCamera* cam, float amt);    /* camera.cpp:112-118 */
+MT_API void mtxCameraUBO(const MtxCamera* cam, MtCameraUBO* out);    /* Camera::UpdateBuffer, camera.cpp:31-42 (glm lookAtRH / perspectiveRH_ZO) */
+MT_API void mtxTimeInit(MtTimeUBO* t);                               /* Scene::InitializeTime, Scene.cpp:86-119: Halton base 3, frame 0 */
+MT_API void mtxTimeUpdate(MtTimeUBO* t, float delta_seconds);        /* Scene::UpdateTime, Scene.cpp:65-85 with a caller-supplied delta   */
+MT_API void mtxSunAndSky(MtSunAndSkyUBO* s);                         /* Sky::UpdateSunAndSky, Sky.cpp:64-74 */
+/* One iteration of the reference main loop (main.cpp:172-194) for a context: uploads camera / cameraOld / time / sky,
+ * runs mtFrameEx(passes), then copies camera into camera_old.                                                      */
+MT_API MtStatus mtxRunFrame(MtContext* ctx, const MtxCamera* cam, MtCameraUBO* camera_old, MtTimeUBO* time, float delta_seconds,
+                            uint32_t passes);
+
 /* ---- measurement ----------------------------------------------------------------------------- */
 MT_API MtStatus mtGetCounters(MtContext* ctx, MtCounters* out, int reset); /* sync; needs MT_FLAG_COUNTERS */
 /* Device time (CUDA events on the context's stream) of the most recent dispatch of `pass`, in ms. Syncs. */

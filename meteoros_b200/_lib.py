@@ -43,6 +43,14 @@ class MtCounters(C.Structure):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}
 
 
+class MtxCamera(C.Structure):
+    _fields_ = [
+        ("eye", C.c_float * 3), ("ref", C.c_float * 3), ("forward", C.c_float * 3), ("right", C.c_float * 3), ("up", C.c_float * 3),
+        ("fovy_deg", C.c_float), ("aspect", C.c_float), ("near_clip", C.c_float), ("far_clip", C.c_float),
+        ("width", C.c_int32), ("height", C.c_int32),
+    ]
+
+
 # name -> (restype, argtypes); the single source of truth for the Python side of the ABI
 PROTOTYPES = {
     "mtAbiVersion": (C.c_uint32, []),
@@ -85,6 +93,17 @@ PROTOTYPES = {
     "mtExportImageHandle": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "mtOpenPeerImage": (C.c_int, [C.c_void_p, C.c_void_p, c_void_pp]),
     "mtClosePeerImage": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mtxCameraInit": (None, [C.POINTER(MtxCamera), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float]),
+    "mtxCameraRotateAboutUp": (None, [C.POINTER(MtxCamera), C.c_float]),
+    "mtxCameraRotateAboutRight": (None, [C.POINTER(MtxCamera), C.c_float]),
+    "mtxCameraTranslateAlongLook": (None, [C.POINTER(MtxCamera), C.c_float]),
+    "mtxCameraTranslateAlongRight": (None, [C.POINTER(MtxCamera), C.c_float]),
+    "mtxCameraTranslateAlongUp": (None, [C.POINTER(MtxCamera), C.c_float]),
+    "mtxCameraUBO": (None, [C.POINTER(MtxCamera), C.c_void_p]),
+    "mtxTimeInit": (None, [C.c_void_p]),
+    "mtxTimeUpdate": (None, [C.c_void_p, C.c_float]),
+    "mtxSunAndSky": (None, [C.c_void_p]),
+    "mtxRunFrame": (C.c_int, [C.c_void_p, C.POINTER(MtxCamera), C.c_void_p, C.c_void_p, C.c_float, C.c_uint32]),
     "mtGetCounters": (C.c_int, [C.c_void_p, C.POINTER(MtCounters), C.c_int]),
     "mtLastPassMs": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
     "mtStreamHandle": (C.c_int, [C.c_void_p, c_void_pp]),

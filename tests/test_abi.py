@@ -15,7 +15,7 @@ HEADER = ROOT / "include" / "meteoros_b200.h"
 
 def declared_symbols():
     text = HEADER.read_text()
-    return set(re.findall(r"MT_API\s+[\w\s\*]+?\b(mt[A-Z]\w+)\s*\(", text))
+    return set(re.findall(r"MT_API\s+[\w\s\*]+?\b(mtx?[A-Z]\w+)\s*\(", text))
 
 
 def test_library_exports_every_declared_symbol():

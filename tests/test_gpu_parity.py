@@ -321,6 +321,38 @@ def test_txaa_pass_and_reference_live_frame(api, oracle_mod, noise):
             cam_old = c
 
 
+def test_cxx_frame_driver_matches_python_driven_frames(api, noise):
+    """mtxRunFrame (the reference main loop in C++) against the same frames driven from Python."""
+    import ctypes as C
+
+    from meteoros_b200 import _lib, scene
+
+    lib = _lib.load()
+    w, h = 160, 90
+    passes = api.FRAME_TONEMAP | api.FRAME_TXAA
+    with make_renderer(api, noise, w, h) as a, make_renderer(api, noise, w, h) as b:
+        cam = _lib.MtxCamera()
+        lib.mtxCameraInit(C.byref(cam), w, h, None, None, 45.0, 0.1, 1000.0)
+        cam_old = np.zeros((), scene.CAMERA_DTYPE)
+        lib.mtxCameraUBO(C.byref(cam), cam_old.ctypes.data)
+        tm = np.zeros((), scene.TIME_DTYPE)
+        lib.mtxTimeInit(tm.ctypes.data)
+        py_old = cam_old.copy()
+        py_tm = scene.Scene()
+        for _ in range(5):
+            lib.mtxCameraRotateAboutUp(C.byref(cam), 0.25)
+            a._check(lib.mtxRunFrame(a._h, C.byref(cam), cam_old.ctypes.data, tm.ctypes.data, C.c_float(1 / 60), passes), "mtxRunFrame")
+            cur = np.zeros((), scene.CAMERA_DTYPE)
+            lib.mtxCameraUBO(C.byref(cam), cur.ctypes.data)
+            py_tm.update_time(1 / 60)
+            b.set_camera(cur); b.set_camera_old(py_old); b.set_time(py_tm.ubo()); b.set_sun_and_sky(scene.Sky().ubo())
+            b.frame(with_godrays=False, with_txaa=True)
+            py_old = cur
+            assert cam_old.tobytes() == cur.tobytes() and tm.tobytes() == py_tm.ubo().tobytes()
+            assert np.array_equal(a.read_image(api.IMAGE_LDR_PREV), b.read_image(api.IMAGE_LDR_PREV))
+            assert np.array_equal(a.read_image(api.IMAGE_CLOUD_PREV), b.read_image(api.IMAGE_CLOUD_PREV))
+
+
 def test_f16_storage_emulation(api, oracle_mod, noise):
     w, h = 128, 72
     cam, tm, _, tun = default_scene(w, h)
