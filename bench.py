@@ -185,6 +185,8 @@ def main():
     ap.add_argument("--workload", default="cloud4k", choices=["cloud4k", "frame8k", "seq1080p"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ctx-flags", type=int, default=0, help="extra MT_FLAG_* bits for A/B runs (e.g. 8 = no quad layout)")
+    ap.add_argument("--tile-rows", type=int, default=8, help="frame8k: pixel rows per cyclic tile (multiple of 8)")
+    ap.add_argument("--gather-mask", action="store_true", help="frame8k: also send the god-ray mask tiles to GPU 0 (needed only if god rays run)")
     ap.add_argument("--sweep", action="store_true", help="N>1: rank r renders view r of the sun/coverage sweep")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -210,7 +212,7 @@ def main():
     noise = textures.load_noise()
 
     if args.workload == "frame8k":
-        w, h, workload = 7680, 4320, "7680x4320 full-quality frame, cyclic 32-row tiles over the ranks, NVLink peer stores to GPU 0 (BASELINE config 4)"
+        w, h, workload = 7680, 4320, f"7680x4320 full-quality frame, cyclic {args.tile_rows}-row tiles over the ranks, HDR tiles stored straight into GPU 0 over NVLink (BASELINE config 4)"
     elif args.workload == "seq1080p":
         w, h, workload = 1920, 1080, "1920x1080 16-frame pan: Reprojection + 1/16 Cloud + god rays + tone map (BASELINE config 2)"
     else:
@@ -242,7 +244,7 @@ def main():
         class _Dist:  # single-process stand-in so N=1 runs the same code path
             def get_rank(self): return 0
             def get_world_size(self): return 1
-        shard = sharding.ShardedFrame(r, dist if world > 1 else _Dist(), tile_rows=32, with_mask=True)
+        shard = sharding.ShardedFrame(r, dist if world > 1 else _Dist(), tile_rows=args.tile_rows, with_mask=args.gather_mask)
 
     seq_state = {"frame": 0}
 
