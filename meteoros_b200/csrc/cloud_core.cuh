@@ -109,12 +109,12 @@ MT_DEVICE float low_freq_density(const Tex3D& low, float coverage, P2 pxy, float
     Rgba n = tex3d_rgba_axes(low, X, Y, Z);
     float fbm = sat1((n.g * 0.625f + n.b * 0.25f) + n.a * 0.125f);
     float omin = fbm - 0.9f;
-    float base = sat1((n.r - omin) / (1.0f - omin));  // remapClamped(r, fbm-.9, 1, 0, 1)
+    float base = sat1(div_nice(n.r - omin, 1.0f - omin));  // remapClamped(r, fbm-.9, 1, 0, 1); denominator in [0.9, 1.9]
     // remapClampedBeforeAndAfter(base, cov, 1, 0, 1) * cov.  base <= cov clamps to cov and yields exactly +0; returning
     // it here also keeps 0/(1-cov) away from the IEEE division's zero-dividend slow path (85 % of its calls in the
     // first profile).
     if (!(base > coverage)) return 0.0f;
-    float b = sat1((base - coverage) / (1.0f - coverage));
+    float b = sat1(div_nice(base - coverage, 1.0f - coverage));  // coverage in [0, 0.91] (mtSetTuning)
     return b * coverage;
 }
 
@@ -131,7 +131,7 @@ MT_DEVICE float erosion_edge(const Tex2D& curl, const Tex3D& high, f3 p, float h
     float m = sat1(mix1(fbm, 1.0f - fbm, sat1(h * 2.0f)));
     return m * 0.005f;
 }
-MT_DEVICE float erode(float base, float edge) { return (base - edge) / (1.0f - edge); }  // remap(base, edge, 1, 0, 1)
+MT_DEVICE float erode(float base, float edge) { return div_nice(base - edge, 1.0f - edge); }  // remap(base, edge, 1, 0, 1); edge in [0, 0.005]
 
 // GetLightEnergy (cloudRayMarch.comp:331-388), live branch only.
 MT_DEVICE float light_energy(float h, float dl, float ds, float phase, float cosa)

@@ -299,7 +299,7 @@ MtStatus mtSetTuning(MtContext* c, const MtTuning* t)
 {
     if (!c) return MT_ERR_INVALID;
     MT_REQUIRE(c, t != nullptr, "mtSetTuning: null tuning");
-    MT_REQUIRE(c, t->coverage >= 0.0f && t->coverage < 1.0f, "mtSetTuning: coverage must be in [0, 1)");
+    MT_REQUIRE(c, t->coverage >= 0.0f && t->coverage <= 0.91f, "mtSetTuning: coverage must be in [0, 0.91]");
     c->tun = *t;
     return MT_OK;
 }

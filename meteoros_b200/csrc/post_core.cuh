@@ -244,10 +244,9 @@ MT_DEVICE C4 ldr_border_texel(const uint32_t* img, int W, int H, int x, int y)  
 }
 
 // One fragment of the TXAA pass; returns the packed RGBA8 result.
-MT_DEVICE uint32_t txaa_pixel(const TxaaParams& P, const TxaaFrame& F, int x, int y)
+MT_DEVICE uint32_t txaa_pixel(const TxaaParams& P, const TxaaFrame& F, int x, int y, float u, float v)
 {
-    const float u = ((float)x + 0.5f) / (float)P.W;
-    const float v = ((float)y + 0.5f) / (float)P.H;
+    // (u, v) = in_uv = ((x + .5) / W, (y + .5) / H), computed once per CTA column / row by the caller
     const f3 dir = cast_ray_dir(P.cam, F.basis, F.eye, u, v, F.jx, F.jy);
     f3 p = mk3(0.0f, 0.0f, 0.0f);
     {
@@ -283,10 +282,10 @@ MT_DEVICE uint32_t txaa_pixel(const TxaaParams& P, const TxaaFrame& F, int x, in
         float sum = n[0].c[c];
 #pragma unroll
         for (int j = 1; j < 9; ++j) sum += n[j].c[c];
-        const float avg = sum / 9.0f;
+        const float avg = MT_DIV_CONST(sum, 9.0f);   // exact 3-instruction division (tests/test_exact_tricks.py)
         const float mn5 = fminf(n[1].c[c], fminf(n[3].c[c], fminf(n[4].c[c], fminf(n[5].c[c], n[7].c[c]))));
         const float mx5 = fmaxf(n[1].c[c], fmaxf(n[3].c[c], fmaxf(n[4].c[c], fmaxf(n[5].c[c], n[7].c[c]))));
-        const float avg5 = ((((n[1].c[c] + n[3].c[c]) + n[4].c[c]) + n[5].c[c]) + n[7].c[c]) / 5.0f;
+        const float avg5 = MT_DIV_CONST(((((n[1].c[c] + n[3].c[c]) + n[4].c[c]) + n[5].c[c]) + n[7].c[c]), 5.0f);
         cmin[c] = 0.5f * (mn + mn5);
         cmax[c] = 0.5f * (mx + mx5);
         cavg[c] = 0.5f * (avg + avg5);
@@ -312,19 +311,19 @@ MT_DEVICE uint32_t txaa_pixel(const TxaaParams& P, const TxaaFrame& F, int x, in
         pclip[c] = 0.5f * (cmax[c] + cmin[c]);
         const float e = 0.5f * (cmax[c] - cmin[c]) + 0.0000000001f;
         vclip[c] = prevc[c] - pclip[c];
-        aunit[c] = fabsf(vclip[c] / e);
+        aunit[c] = fabsf(div_nice(vclip[c], e));  // e >= 1e-10, |vclip| <= 1
     }
     const float ma = fmaxf(aunit[0], fmaxf(aunit[1], aunit[2]));
     pclip[3] = pw;
     vclip[3] = prevc[3] - pw;
     if (ma > 1.0f) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) prevc[c] = pclip[c] + vclip[c] / ma;
+        for (int c = 0; c < 4; ++c) prevc[c] = pclip[c] + div_nice(vclip[c], ma);  // ma > 1
     }
     const float* curr = n[4].c;
     const float lum0 = (curr[0] * 0.2125f + curr[1] * 0.7154f) + curr[2] * 0.0721f;
     const float lum1 = (prevc[0] * 0.2125f + prevc[1] * 0.7154f) + prevc[2] * 0.0721f;
-    const float diff = fabsf(lum0 - lum1) / fmaxf(lum0, fmaxf(lum1, 0.2f));
+    const float diff = div_nice(fabsf(lum0 - lum1), fmaxf(lum0, fmaxf(lum1, 0.2f)));
     const float wgt = 1.0f - diff;
     const float kfb = mix1(0.0f, 0.5f, wgt * wgt);
     uint32_t o = 0;

@@ -104,12 +104,15 @@ __global__ void __launch_bounds__(256) tonemap_kernel(const __grid_constant__ To
 __global__ void __launch_bounds__(256) txaa_kernel(const __grid_constant__ TxaaParams P)
 {
     __shared__ TxaaFrame frame;
+    __shared__ float su[32], sv[8];
     if (threadIdx.x == 0) frame = txaa_frame(P);
+    if (threadIdx.x >= 32 && threadIdx.x < 64) su[threadIdx.x - 32] = ((float)(blockIdx.x * 32 + (threadIdx.x - 32)) + 0.5f) / (float)P.W;
+    if (threadIdx.x >= 64 && threadIdx.x < 72) sv[threadIdx.x - 64] = ((float)(blockIdx.y * 8 + (threadIdx.x - 64)) + 0.5f) / (float)P.H;
     __syncthreads();
     const int x = blockIdx.x * 32 + (threadIdx.x & 31);
     const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
     if (x >= P.W || y >= P.H) return;
-    P.out[(size_t)y * P.W + x] = txaa_pixel(P, frame, x, y);
+    P.out[(size_t)y * P.W + x] = txaa_pixel(P, frame, x, y, su[threadIdx.x & 31], sv[threadIdx.x >> 5]);
 }
 cudaError_t mt_launch_txaa(const TxaaParams& P, cudaStream_t stream)
 {

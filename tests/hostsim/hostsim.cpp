@@ -167,7 +167,7 @@ int hs_txaa(const MtCameraUBO* cam, const MtCameraUBO* camOld, const MtTimeUBO* 
     P.W = W; P.H = H;
     TxaaFrame F = txaa_frame(P);
     for (int y = 0; y < H; ++y)
-        for (int x = 0; x < W; ++x) out[(size_t)y * W + x] = txaa_pixel(P, F, x, y);
+        for (int x = 0; x < W; ++x) out[(size_t)y * W + x] = txaa_pixel(P, F, x, y, ((float)x + 0.5f) / (float)W, ((float)y + 0.5f) / (float)H);
     return 0;
 }
 

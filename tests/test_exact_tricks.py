@@ -3,10 +3,14 @@ mt_tex.cuh), checked exhaustively / at scale on the host with the same IEEE oper
 import numpy as np
 
 
-def test_division_by_thickness_is_exact_for_every_significand():
-    """div_thickness(x) = fma(fma(-q, d, x), r, q), q = x*r, r = RN(1/12500) equals x / 12500 for all 2^23
+import pytest
+
+
+@pytest.mark.parametrize("divisor", [12500.0, 10.0, 9.0, 5.0])
+def test_division_by_constant_is_exact_for_every_significand(divisor):
+    """div_thickness / MT_DIV_CONST: fma(fma(-q, d, x), r, q), q = x*r, r = RN(1/d) equals x / d for all 2^23
     significands (the result is scale-invariant across binades in the normal range), both signs."""
-    d = np.float32(12500.0)
+    d = np.float32(divisor)
     r = np.float32(1.0) / d
     bits = (np.uint32(140) << np.uint32(23)) | np.arange(1 << 23, dtype=np.uint32)  # one full binade (~8192..16384)
     for sign in (1.0, -1.0):
