@@ -256,6 +256,19 @@ MT_API void mtxSunAndSky(MtSunAndSkyUBO* s);                         /* Sky::Upd
 MT_API MtStatus mtxRunFrame(MtContext* ctx, const MtxCamera* cam, MtCameraUBO* camera_old, MtTimeUBO* time, float delta_seconds,
                             uint32_t passes);
 
+/* ---- asset pipeline: the reference's texture files -> RGBA8 arrays, without stb / PIL --------------------- */
+/* TGA true-colour (raw / RLE, 24 / 32 bpp) and non-interlaced PNG (8 / 16 bit; 16-bit samples keep the high byte as stb_image
+ * does).  Output is tightly packed RGBA8, rows top-down (what stbi_load(..., STBI_rgb_alpha) returns,
+ * ImageLoadingUtility.cpp:91).  rgba8_out may be NULL to query the size.  MT_ERR_INVALID on any decode / IO failure.        */
+MT_API MtStatus mtxDecodeImage(const uint8_t* file_bytes, size_t n, int is_png, uint8_t* rgba8_out, size_t out_bytes, uint32_t* w, uint32_t* h);
+MT_API MtStatus mtxLoadImageFile(const char* path, uint8_t* rgba8_out, size_t out_bytes, uint32_t* w, uint32_t* h);
+/* ImageLoadingUtility::create3DTextureFromMany2DTextures (ImageLoadingUtility.cpp:75-139): slice z = folder + base + "(z+1)" + ext. */
+MT_API MtStatus mtxLoadVolumeFromSlices(const char* folder, const char* base_name, const char* extension, uint32_t w, uint32_t h, uint32_t d,
+                                        uint8_t* rgba8_out, size_t out_bytes);
+/* Packed cache of a decoded volume: "MTVOL001", u32 w, h, d, reserved, then raw RGBA8. */
+MT_API MtStatus mtxSaveVolume(const char* path, uint32_t w, uint32_t h, uint32_t d, const uint8_t* rgba8);
+MT_API MtStatus mtxLoadVolume(const char* path, uint8_t* rgba8_out, size_t out_bytes, uint32_t* w, uint32_t* h, uint32_t* d);
+
 /* ---- measurement ----------------------------------------------------------------------------- */
 MT_API MtStatus mtGetCounters(MtContext* ctx, MtCounters* out, int reset); /* sync; needs MT_FLAG_COUNTERS */
 /* Device time (CUDA events on the context's stream) of the most recent dispatch of `pass`, in ms. Syncs. */

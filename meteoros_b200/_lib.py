@@ -104,6 +104,11 @@ PROTOTYPES = {
     "mtxTimeUpdate": (None, [C.c_void_p, C.c_float]),
     "mtxSunAndSky": (None, [C.c_void_p]),
     "mtxRunFrame": (C.c_int, [C.c_void_p, C.POINTER(MtxCamera), C.c_void_p, C.c_void_p, C.c_float, C.c_uint32]),
+    "mtxDecodeImage": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "mtxLoadImageFile": (C.c_int, [C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "mtxLoadVolumeFromSlices": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t]),
+    "mtxSaveVolume": (C.c_int, [C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]),
+    "mtxLoadVolume": (C.c_int, [C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "mtGetCounters": (C.c_int, [C.c_void_p, C.POINTER(MtCounters), C.c_int]),
     "mtLastPassMs": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
     "mtStreamHandle": (C.c_int, [C.c_void_p, c_void_pp]),

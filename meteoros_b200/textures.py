@@ -54,3 +54,29 @@ def synthetic_noise(seed: int = 0) -> dict[str, np.ndarray]:
         "curl": rng.integers(0, 256, (128, 128, 4), dtype=np.uint8),
         "weather": rng.integers(0, 256, (512, 512, 4), dtype=np.uint8),
     }
+
+
+def load_noise_from_reference_tree(textures_dir) -> dict[str, np.ndarray]:
+    """Decode the reference's own texture files with the library's C++ decoders (mtx*, no PIL): what a C++ host does in
+    place of Sky::CreateCloudResources.  `textures_dir` = .../src/CloudScapes/textures/CloudTextures."""
+    import ctypes as C
+
+    from . import _lib
+
+    lib = _lib.load()
+    d = str(Path(textures_dir)) + "/"
+    low = np.zeros((128, 128, 128, 4), np.uint8)
+    high = np.zeros((32, 32, 32, 4), np.uint8)
+    for arr, sub, base, n in ((low, "LowFrequency/", "LowFrequency", 128), (high, "HighFrequency/", "HighFrequency", 32)):
+        st = lib.mtxLoadVolumeFromSlices((d + sub).encode(), base.encode(), b".tga", n, n, n, arr.ctypes.data, arr.nbytes)
+        if st != 0:
+            raise OSError(f"mtxLoadVolumeFromSlices failed for {d + sub}")
+    out = {"low": low, "high": high}
+    for key, name, n in (("curl", "curlNoise.png", 128), ("weather", "weatherMap.png", 512)):
+        arr = np.zeros((n, n, 4), np.uint8)
+        w, h = C.c_uint32(), C.c_uint32()
+        st = lib.mtxLoadImageFile((d + name).encode(), arr.ctypes.data, arr.nbytes, C.byref(w), C.byref(h))
+        if st != 0 or (w.value, h.value) != (n, n):
+            raise OSError(f"mtxLoadImageFile failed for {d + name}")
+        out[key] = arr
+    return out
