@@ -230,13 +230,24 @@ __global__ void __launch_bounds__(128) cloud_fold_kernel(const __grid_constant__
     bool valid;
     sixteenth_pixel(P, px, py, pixelID, valid);
     const size_t stride = (size_t)gridDim.x * 128;
+    int n = 0;  // number of march iterations: the t sequence of the sequential loop
+    for (float t = R.t_in; t < R.t_out && n < MT_STEP_SLICES; t += R.stepSize) ++n;
     float accum = 0.0f, transmittance = 1.0f, color = 0.0f;
-    int k = 0;
-    for (float t = R.t_in; t < R.t_out && k < MT_STEP_SLICES; t += R.stepSize, ++k) {
-        const float2 v = __ldg(P.samples + (size_t)k * stride + ray);
-        StepSample S;
-        S.inc = v.x; S.energy = v.y;
-        if (cloud_step_combine(S, accum, transmittance, color)) break;
+    bool stop = false;
+    // the fold is the only sequential part; its loads do not depend on the running sums, so fetch eight steps at a time
+    for (int k0 = 0; k0 < n && !stop; k0 += 8) {
+        float2 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            v[j] = (k0 + j < n) ? __ldg(P.samples + (size_t)(k0 + j) * stride + ray) : make_float2(0.0f, -1.0f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (!stop && k0 + j < n) {
+                StepSample S;
+                S.inc = v[j].x; S.energy = v[j].y;
+                stop = cloud_step_combine(S, accum, transmittance, color);
+            }
+        }
     }
     F4 hdr, mask;
     cloud_composite(R, accum, color, hdr, mask);

@@ -106,6 +106,46 @@ def test_sixteenth_step_parallel_equals_sequential(api, noise, w, h):
         assert np.array_equal(h0, h1) and np.array_equal(m0, m1)
 
 
+def test_randomised_scenes(api, oracle_mod, noise):
+    """Twelve random scenes (camera position / orientation / field of view, time, coverage, sun, frame id), both
+    dispatch modes: decisions bit-exact, radiance within tolerance -- the parity does not hinge on the default view."""
+    from meteoros_b200 import scene
+
+    rng = np.random.default_rng(2024)
+    w, h = 112, 63
+    with make_renderer(api, noise, w, h) as r:
+        for k in range(12):
+            eye = (float(rng.uniform(-500, 500)), float(rng.uniform(-3000, 50)), float(rng.uniform(-500, 500)))
+            cam = scene.Camera(w, h, eye=eye, ref=(eye[0], eye[1], eye[2] - 1.0), fovy=float(rng.uniform(25, 80)))
+            cam.rotate_about_up(float(rng.uniform(-180, 180)))
+            cam.rotate_about_right(float(rng.uniform(-10, 60)))
+            sc = scene.Scene()
+            sc.time["time"] = (0.016, float(rng.uniform(0, 500)))
+            sc.time["frameCountMod16"] = int(rng.integers(0, 16))
+            tun = scene.default_tuning()
+            tun["coverage"] = float(rng.uniform(0.3, 0.85))
+            tun["sun_location"] = scene.sun_on_elevation_circle(float(rng.uniform(5, 85)))
+            tun["cloud_speed"] = float(rng.uniform(0.0, 0.2))
+            c, t = cam.ubo(), sc.ubo()
+            r.set_camera(c); r.set_time(t); r.set_tuning(tun)
+            ref = oracle_mod.cloud(c, t, tun, noise, w, h, full=True, debug=True)
+            dbg = r.dispatch_cloud_debug(True)
+            for f in oracle_mod.RAY_DEBUG_DTYPE.names:
+                assert np.array_equal(dbg[f], ref["debug"][f]), (k, f)
+            assert np.array_equal(r.read_image(api.IMAGE_GODRAY_MASK), ref["mask"]), k
+            check_hdr(r.read_image(api.IMAGE_CLOUD_CUR), ref["hdr"])
+            sentinel = np.full((h, w, 4), -3.0, np.float32)
+            ref16 = oracle_mod.cloud(c, t, tun, noise, w, h, full=False, hdr=sentinel.copy(), mask=sentinel.copy())
+            r.write_image(api.IMAGE_CLOUD_CUR, sentinel)
+            r.write_image(api.IMAGE_GODRAY_MASK, sentinel)
+            r.dispatch_cloud()  # step-parallel path
+            got = r.read_image(api.IMAGE_CLOUD_CUR)
+            wr = got[..., 3] != -3.0
+            assert np.array_equal(wr, ref16["hdr"][..., 3] != -3.0)
+            assert np.array_equal(r.read_image(api.IMAGE_GODRAY_MASK), ref16["mask"]), k
+            check_hdr(got, ref16["hdr"], wr)
+
+
 def test_cloud_tuning_sweep(api, oracle_mod, noise):
     from meteoros_b200 import scene
 
