@@ -109,14 +109,14 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(self.rows), "reasons": reasons}
 
 
-def scene_for_view(view: int, w: int, h: int):
+def scene_for_view(view: int, w: int, h: int, sweep: bool = False):
     """View 0 = the default cloudscape; views > 0 sweep sun elevation (5..85 deg) x coverage (0.3..0.9), config 5."""
     from meteoros_b200 import scene
 
     cam, sc, sky = scene.Camera(w, h), scene.Scene(), scene.Sky()
     sc.update_time(1.0 / 60.0)
     tun = scene.default_tuning()
-    if view > 0:
+    if view > 0 or sweep:
         tun["sun_location"] = scene.sun_on_elevation_circle(5.0 + 80.0 * ((view % 16) / 15.0))
         tun["coverage"] = 0.3 + 0.6 * (((view // 16) % 16) / 15.0)
     return cam.ubo(), sc.ubo(), sky.ubo(), tun
@@ -182,7 +182,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cloud4k", choices=["cloud4k", "frame8k", "seq1080p"])
+    ap.add_argument("--workload", default="cloud4k", choices=["cloud4k", "frame8k", "seq1080p", "views256"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ctx-flags", type=int, default=0, help="extra MT_FLAG_* bits for A/B runs (e.g. 8 = no quad layout)")
     ap.add_argument("--tile-rows", type=int, default=8, help="frame8k: pixel rows per cyclic tile (multiple of 8)")
@@ -215,6 +215,8 @@ def main():
         w, h, workload = 7680, 4320, f"7680x4320 full-quality frame, cyclic {args.tile_rows}-row tiles over the ranks, HDR tiles stored straight into GPU 0 over NVLink (BASELINE config 4)"
     elif args.workload == "seq1080p":
         w, h, workload = 1920, 1080, "1920x1080 16-frame pan: Reprojection + 1/16 Cloud + god rays + tone map (BASELINE config 2)"
+    elif args.workload == "views256":
+        w, h, workload = 1920, 1080, "256 full-quality 1920x1080 views: 16 sun elevations x 16 coverages, round-robin over the ranks (BASELINE config 5)"
     else:
         w, h, workload = W4K, H4K, "3840x2160 full-quality Cloud pass, all 16 pixel ids, no reprojection (BASELINE config 3)"
 
@@ -247,12 +249,17 @@ def main():
         shard = sharding.ShardedFrame(r, dist if world > 1 else _Dist(), tile_rows=args.tile_rows, with_mask=args.gather_mask)
 
     seq_state = {"frame": 0}
+    my_views = [scene_for_view(v, w, h, sweep=True)[3] for v in sharding.views_of_rank(256, world, rank)] if args.workload == "views256" else []
 
     def step():
         if args.workload == "cloud4k":
             r.dispatch_cloud_full()
         elif args.workload == "frame8k":
             shard.dispatch()
+        elif args.workload == "views256":
+            for vt in my_views:  # every view: new sun position + coverage (the empty-cell bitmap is rebuilt per coverage)
+                r.set_tuning(vt)
+                r.dispatch_cloud_full()
         else:  # one reference frame: 0.25 deg pan, dt = 1/60, ids 1..15,0, REPROJ + CLOUD + GODRAYS + TONEMAP + swap
             pan_cam.rotate_about_up(0.25)
             pan_scene.update_time(1.0 / 60.0)
@@ -271,6 +278,8 @@ def main():
     rays_per_step_rank = counters["rays"] if args.workload != "seq1080p" else counters["rays"] // 16
     if args.workload == "frame8k" and world > 1:
         rays_total_per_step = w * h
+    elif args.workload == "views256":
+        rays_total_per_step = 256 * w * h
     else:
         rays_total_per_step = rays_per_step_rank * world
 
@@ -354,7 +363,7 @@ def main():
         hbm_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
         # roofline of the dominant kernel (cloud_raymarch), per launch, rank 0's frame
         flop = algorithmic_flop(counters)
-        kern_ms = statistics.mean(step_ms) if args.workload != "seq1080p" else None
+        kern_ms = statistics.mean(step_ms) if args.workload in ("cloud4k", "frame8k") and not (args.workload == "frame8k" and world > 1) else None
         roofline = None
         if kern_ms:
             ach_tflops = flop / (kern_ms * 1e-3) / 1e12
@@ -373,7 +382,7 @@ def main():
             "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
             "scaling": "strong" if (args.workload == "frame8k") else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload, "rays_per_step": int(rays_total_per_step), "l2": "flushed between timed steps (256 MiB memset)",
-                       "noise": "reference noise volumes (tests/golden/noise_volumes.npz)", "parallelism": f"views x{world}" if args.workload == "cloud4k" else f"row-tiles x{world}"},
+                       "noise": "reference noise volumes (tests/golden/noise_volumes.npz)", "parallelism": f"row-tiles x{world}" if args.workload == "frame8k" else f"views x{world}"},
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(nbytes if e2e_read else 0),
                     "ms_per_step": round(1e3 * e2e_s / args.steps, 4)},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,

@@ -136,20 +136,19 @@ MT_DEVICE F4 godray_pixel(const GodRayParams& P, const GodRayFrame& G, int x, in
     const float du = ((u - G.sunx) / 100.0f) * 1.0f;
     const float dv = ((v - G.suny) / 100.0f) * 1.0f;
     P2 uv = pk2(u, v);
-    const P2 duv = pk2(du, dv), lc01 = pk2(P.lightColor[0], P.lightColor[1]);
-    float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f;
+    const P2 duv = pk2(du, dv);
+    // sum_i (lightColor * a_i) * 0.001 is accumulated as lightColor * 0.001 * sum_i a_i: the same real number, one add
+    // per tap instead of seven instructions; the reordering moves the result by ~1e-7 of a term that is at most 2.5 %
+    // of the pixel (radiance only, no decision depends on it).
+    float sum = 0.0f;
     for (int i = 0; i < 100; ++i) {
-        const float a = mask_decode(P.decoded, P.W, P.H, uv);
-        const P2 s01 = mul2(mul2(lc01, bc2(a)), bc2(1.0f * 0.001f));
-        acc0 += lo2(s01);  // scalar adds: a mul2 feeding an add2 would be contracted
-        acc1 += hi2(s01);
-        acc2 += (P.lightColor[2] * a) * (1.0f * 0.001f);
+        sum += mask_decode(P.decoded, P.W, P.H, uv);
         uv = sub2(uv, duv);
     }
     F4 o;
-    o.x = (acc0 * 1.0f) * G.blend;
-    o.y = (acc1 * 1.0f) * G.blend;
-    o.z = (acc2 * 1.0f) * G.blend;
+    o.x = ((P.lightColor[0] * sum) * (1.0f * 0.001f)) * G.blend;
+    o.y = ((P.lightColor[1] * sum) * (1.0f * 0.001f)) * G.blend;
+    o.z = ((P.lightColor[2] * sum) * (1.0f * 0.001f)) * G.blend;
     o.w = 1.0f * G.blend;
     return o;
 }
