@@ -237,8 +237,8 @@ MT_DEVICE StepSample cloud_step_sample(const CloudParams& P, const MarchConst& M
     f3 rp = pos - relOrigin;
     f3 sp = mk3(div_thickness(rp.x) * 0.125f, div_thickness(rp.y) * 0.125f, div_thickness(rp.z) * 0.125f);  // /12500, /8
     // getRelativeHeightInAtmosphere (:171-186)
-    float lenFromCam = len3(pos - origin);
-    float cosTheta = dot3(dir, norm3(pos - ec));
+    float lenFromCam = len3_nice(pos - origin);          // 2e4 .. 3e5 m
+    float cosTheta = dot3(dir, norm3_nice(pos - ec));    // ~6.4e6 m
     float h = div_thickness(fabsf(cosTheta * (lenFromCam - R.lenToInner)));
     // skewSamplePointWithWind (:489-497)
     f3 skew = (sp + ((wind * h) * P.tun.cloud_top_offset) * 0.009f) + M.windSkew;
