@@ -192,26 +192,41 @@ __global__ void __launch_bounds__(128) cloud_rays_kernel(const __grid_constant__
     int px, py, pixelID;
     bool valid;
     sixteenth_pixel(P, px, py, pixelID, valid);
+    __shared__ int ctaSteps;
+    if (threadIdx.x == 0) ctaSteps = 0;
+    __syncthreads();
     RaySetup* rec = reinterpret_cast<RaySetup*>(P.rays) + ((size_t)blockIdx.x * 128 + threadIdx.x);
+    int n = 0;
     if (!valid) {
         rec->branch = -1;
-        return;
+    } else {
+        F4 hdr, mask;
+        mask.x = mask.y = mask.z = mask.w = 0.0f;
+        const RaySetup R = cloud_ray_setup(P, M, px, py, pixelID, hdr);
+        *rec = R;
+        if (R.branch != 2) store_pixel(P, (size_t)py * P.W + px, hdr, mask);  // ocean / sky band: final
+        else
+            for (float t = R.t_in; t < R.t_out && n < MT_STEP_SLICES; t += R.stepSize) ++n;  // this ray's step count
     }
-    F4 hdr, mask;
-    mask.x = mask.y = mask.z = mask.w = 0.0f;
-    const RaySetup R = cloud_ray_setup(P, M, px, py, pixelID, hdr);
-    *rec = R;
-    if (R.branch != 2) store_pixel(P, (size_t)py * P.W + px, hdr, mask);  // ocean / sky band: final
+    // the largest step count of the CTA's 128 rays: slices beyond it (and every slice of a horizon-culled CTA) have
+    // nothing to do, and cloud_steps_kernel learns that from one load
+    n = max(n, __shfl_xor_sync(0xffffffffu, n, 16)); n = max(n, __shfl_xor_sync(0xffffffffu, n, 8));
+    n = max(n, __shfl_xor_sync(0xffffffffu, n, 4));  n = max(n, __shfl_xor_sync(0xffffffffu, n, 2));
+    n = max(n, __shfl_xor_sync(0xffffffffu, n, 1));
+    if ((threadIdx.x & 31) == 0) atomicMax(&ctaSteps, n);
+    __syncthreads();
+    if (threadIdx.x == 0) P.ctaSteps[blockIdx.x] = ctaSteps;
 }
 
 __global__ void __launch_bounds__(128, MT_CLOUD_MINBLOCKS) cloud_steps_kernel(const __grid_constant__ CloudParams P)
 {
+    const int k = blockIdx.y;
+    if (k >= __ldg(P.ctaSteps + blockIdx.x)) return;  // whole CTA idle for this slice (uniform: taken by all 128 threads)
     __shared__ MarchConst M;
     stage_march_const(M, P.mc);
     const size_t ray = (size_t)blockIdx.x * 128 + threadIdx.x;
     const RaySetup R = reinterpret_cast<const RaySetup*>(P.rays)[ray];
     if (R.branch != 2) return;
-    const int k = blockIdx.y;
     float t = R.t_in;
     for (int i = 0; i < k; ++i) t += R.stepSize;  // the same k roundings the sequential loop performs
     if (!(t < R.t_out)) return;

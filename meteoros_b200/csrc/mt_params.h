@@ -67,6 +67,7 @@ struct CloudParams {
     // step-parallel path of the 1-of-16 dispatch (cloud_raymarch.cu): per-ray records and per-(step, ray) samples
     void* rays;                    // RaySetup[tx*ty], tile-major
     float2* samples;               // [MT_STEP_SLICES][tx*ty] (inc, energy)
+    int* ctaSteps;                 // per 128-ray CTA: the largest step count among its rays (0 = all horizon-culled)
 };
 
 struct ReprojParams {
