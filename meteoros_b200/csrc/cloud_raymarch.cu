@@ -1,6 +1,6 @@
 // cloud_raymarch.cu -- the Cloud compute pass (cloudRayMarch.comp) as one sm_100a kernel.
 //
-// Launch shape: one thread per ray; a warp owns an 8x4 tile of rays, a 128-thread CTA a 16x8 tile, so that the
+// Launch shape: one thread per ray; a warp owns a 16x2 tile of rays (mt_params.h), a 128-thread CTA a 16x8 tile, so that the
 // 32 rays of a warp stay inside the same few noise texels per step (pixel footprint << texel) and the HDR / mask
 // stores of a warp are four 128-byte rows.  Below-horizon CTAs retire after ~100 instructions; the hardware CTA
 // scheduler back-fills, so no persistent loop is needed (64 800 CTAs at 3840x2160).
@@ -89,14 +89,25 @@ __global__ void __launch_bounds__(128, MT_CLOUD_MINBLOCKS) cloud_raymarch_kernel
     int px, py, pixelID;
     bool valid;
     if (FULL) {
-        // CTA = 16x8 pixels, warp = 8x4: the two float4 stores of a warp are four 128-byte rows each
+        // warp = MT_WARP_SHAPE ray tile (default 16x2: two 256-byte rows per float4 store), CTA = MT_CTA_W x MT_CTA_H rays
+#if MT_WARP_SHAPE == 3   // 32x1 rays per warp, CTA = 1x4 warps (32x4 rays)
+        const int lx = lane;
+        const int ly = warp;
+#elif MT_WARP_SHAPE == 1 // 16x2 rays per warp, CTA = 1x4 warps
+        const int lx = lane & 15;
+        const int ly = (warp << 1) + (lane >> 4);
+#elif MT_WARP_SHAPE == 2  // 4x8 rays per warp, CTA = 4x1 warps
+        const int lx = (warp << 2) + (lane & 3);
+        const int ly = lane >> 2;
+#else                     // 8x4 rays per warp, CTA = 2x2 warps
         const int lx = ((warp & 1) << 3) + (lane & 7);
         const int ly = ((warp >> 1) << 2) + (lane >> 3);
-        const int bpt = P.rows.tile_rows >> 3;                  // CTAs per row tile, vertically
+#endif
+        const int bpt = P.rows.tile_rows / MT_CTA_H;            // CTAs per row tile, vertically
         const int ltile = blockIdx.y / bpt;
         const int tile = P.rows.tile_begin + ltile * P.rows.tile_stride;
-        px = blockIdx.x * 16 + lx;
-        py = tile * P.rows.tile_rows + (blockIdx.y - ltile * bpt) * 8 + ly;
+        px = blockIdx.x * MT_CTA_W + lx;
+        py = tile * P.rows.tile_rows + (blockIdx.y - ltile * bpt) * MT_CTA_H + ly;
         pixelID = ((px & 3) << 2) | (py & 3);                   // id = pX*4 + pY with (pX,pY) = (px%4, py%4)
         valid = px < P.W && py < P.H && (px >> 2) < P.tx && (py >> 2) < P.ty;
     } else {
@@ -287,8 +298,8 @@ cudaError_t mt_launch_cloud_setup(const CloudParams& P, MarchConst* out, cudaStr
 
 cudaError_t mt_launch_cloud(const CloudParams& P, cudaStream_t stream)
 {
-    const int bpt = P.rows.tile_rows / 8;
-    dim3 grid((unsigned)((P.W + 15) / 16), (unsigned)(bpt * P.rows.tile_count), 1);
+    const int bpt = P.rows.tile_rows / MT_CTA_H;
+    dim3 grid((unsigned)((P.W + MT_CTA_W - 1) / MT_CTA_W), (unsigned)(bpt * P.rows.tile_count), 1);
     if (!P.full) grid = dim3((unsigned)((P.tx / 8) * (P.ty / 4) / 4), 1, 1);  // tx, ty are multiples of 32
     dim3 block(128, 1, 1);
     if (grid.x == 0 || grid.y == 0) return cudaSuccess;

@@ -10,6 +10,19 @@ struct float2 { float x, y; };
 #include "mt_math.cuh"
 #include "mt_tex.cuh"
 
+// Ray tile of one warp / one 128-thread CTA in the full-quality Cloud launch (cloud_raymarch.cu).  0: 8x4 per warp, CTA
+// 16x8; 1: 16x2, CTA 16x8; 2: 4x8, CTA 16x8; 3: 32x1, CTA 32x4 (rays of a row share dir.y, hence step count and size).
+#ifndef MT_WARP_SHAPE
+#define MT_WARP_SHAPE 1  /* measured at 4K: 16x2 5.07 ms, 8x4 5.12 ms, 32x1 5.15 ms, 4x8 5.29 ms */
+#endif
+#if MT_WARP_SHAPE == 3
+#define MT_CTA_W 32
+#define MT_CTA_H 4
+#else
+#define MT_CTA_W 16
+#define MT_CTA_H 8
+#endif
+
 struct F4 {  // 16-byte pixel; float4 on the device
     float x, y, z, w;
 };
