@@ -69,3 +69,23 @@ def test_create_fails_loudly_without_gpu():
 
     with pytest.raises(MeteorosError):
         CloudRenderer(64, 36)
+
+
+def test_header_is_plain_c_and_the_example_links(tmp_path):
+    """include/meteoros_b200.h must be consumable from C (the reference-side binding is C/C++): compile and link
+    examples/frame_loop.c with gcc -std=c11 and run it without a GPU -- it must fail loudly at mtCreate, not fall back."""
+    import shutil
+
+    cc = "/usr/bin/gcc" if Path("/usr/bin/gcc").exists() else shutil.which("gcc")
+    exe = tmp_path / "frame_loop"
+    r = subprocess.run([cc, "-std=c11", "-Wall", "-Werror", f"-I{ROOT / 'include'}", str(ROOT / "examples" / "frame_loop.c"),
+                        f"-L{_lib.LIB_PATH.parent}", "-lmeteoros_b200", f"-Wl,-rpath,{_lib.LIB_PATH.parent}", "-o", str(exe)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    ref = Path("/root/reference/src/CloudScapes/textures/CloudTextures")
+    import torch
+
+    if ref.exists() and not torch.cuda.is_available():
+        run = subprocess.run([str(exe), str(ref), "2", "64", "36"], capture_output=True, text=True)
+        assert "assets decoded" in run.stdout            # the C++ decoders ran on the reference's files
+        assert run.returncode == 3 and "no CPU path" in run.stderr
