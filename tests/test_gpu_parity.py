@@ -146,6 +146,35 @@ def test_randomised_scenes(api, oracle_mod, noise):
             check_hdr(got, ref16["hdr"], wr)
 
 
+@pytest.mark.parametrize("eye_y", [-7400.0, -9000.0, -25000.0])
+def test_degenerate_cameras(api, oracle_mod, noise, eye_y):
+    """Cameras the reference never meets (ray origin = -eye just under the cloud base, inside the cloud layer, above the
+    outer shell): shell hits become invalid (t = 0, point = 0) and the march starts at the eye.  The kernels must still
+    agree with the oracle, NaNs included."""
+    from meteoros_b200 import scene
+
+    w, h = 96, 54
+    cam = scene.Camera(w, h, eye=(0.0, eye_y, 2.0), ref=(0.0, eye_y, 1.0))
+    cam.rotate_about_right(15.0)
+    sc = scene.Scene()
+    sc.update_time(0.5)
+    tun = scene.default_tuning()
+    c, t = cam.ubo(), sc.ubo()
+    ref = oracle_mod.cloud(c, t, tun, noise, w, h, full=True, debug=True)
+    with make_renderer(api, noise, w, h) as r:
+        r.set_camera(c); r.set_time(t)
+        dbg = r.dispatch_cloud_debug(True)
+        hdr = r.read_image(api.IMAGE_CLOUD_CUR)
+        mask = r.read_image(api.IMAGE_GODRAY_MASK)
+    for f in ("branch", "steps", "jitter_hash", "t_in", "t_out", "step_size"):
+        assert np.array_equal(dbg[f], ref["debug"][f], equal_nan=(dbg[f].dtype.kind == "f")), f
+    assert np.array_equal(np.isnan(hdr), np.isnan(ref["hdr"]))
+    ok = ~np.isnan(ref["hdr"])
+    assert np.allclose(hdr[ok], ref["hdr"][ok], rtol=1e-3, atol=1e-6)
+    assert np.array_equal(np.isnan(mask), np.isnan(ref["mask"]))
+    assert np.array_equal(mask[~np.isnan(mask)], ref["mask"][~np.isnan(mask)])
+
+
 def test_cloud_tuning_sweep(api, oracle_mod, noise):
     from meteoros_b200 import scene
 
