@@ -1,0 +1,33 @@
+#!/usr/bin/env python
+"""Small frame through every pass, for compute-sanitizer (memcheck / racecheck / initcheck):
+   compute-sanitizer --tool memcheck python tools/sanitize_small.py"""
+import sys
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+import numpy as np  # noqa: E402
+
+from meteoros_b200 import api, scene, textures  # noqa: E402
+
+w, h = 130, 70  # odd size: over-provisioned grid, partial tiles, dropped stores
+cam, sc, sky = scene.Camera(w, h), scene.Scene(), scene.Sky()
+with api.CloudRenderer(w, h, flags=api.FLAG_COUNTERS) as r:
+    r.upload_noise(textures.load_noise())
+    r.set_sun_and_sky(sky.ubo())
+    old = cam.ubo()
+    for f in range(3):
+        cam.rotate_about_up(0.25)
+        sc.update_time(1 / 60)
+        r.set_camera(cam.ubo()); r.set_camera_old(old); r.set_time(sc.ubo())
+        r.frame(True, True)
+        old = cam.ubo()
+    r.dispatch_cloud_full()
+    r.dispatch_cloud_tiles(8, 1, 9, 2)
+    r.dispatch_cloud_debug(False)
+    r.dispatch_reprojection_debug()
+    print("counters", r.counters())
+with api.CloudRenderer(w, h) as r:  # step-parallel 1/16 path
+    r.upload_noise(textures.load_noise())
+    r.set_camera(cam.ubo()); r.set_camera_old(old); r.set_time(sc.ubo())
+    r.dispatch_cloud()
+    print("mean", float(np.nanmean(r.read_image(api.IMAGE_CLOUD_CUR))))
