@@ -80,6 +80,9 @@ cudaError_t mt_launch_occupancy(const Tex3D& low, uint32_t* occ, float coverage,
 __device__ __forceinline__ float f16_round(float x) { return __half2float(__float2half_rn(x)); }
 
 template <bool FULL, bool COUNT, bool DEBUG>
+#ifndef MT_BOTTOM_UP
+#define MT_BOTTOM_UP 0  /* A/B at 4K and 8K: no measurable difference (5.09 ms both) */
+#endif
 #ifndef MT_CLOUD_MINBLOCKS
 #define MT_CLOUD_MINBLOCKS 8  /* 64 registers/thread: 8 CTAs = 32 warps per SM (profiles/r1_cloud_ab.md) */
 #endif
@@ -104,10 +107,18 @@ __global__ void __launch_bounds__(128, MT_CLOUD_MINBLOCKS) cloud_raymarch_kernel
         const int ly = ((warp >> 1) << 2) + (lane >> 3);
 #endif
         const int bpt = P.rows.tile_rows / MT_CTA_H;            // CTAs per row tile, vertically
-        const int ltile = blockIdx.y / bpt;
+#if MT_BOTTOM_UP
+        // CTAs are dispatched in blockIdx order: start at the bottom of the frame, so that the trivial ocean rows and
+        // then the heaviest rows (just above the horizon: most steps) go first and the kernel's tail is made of the
+        // lightest marching rows (zenith) instead of the heaviest
+        const int by = (int)gridDim.y - 1 - (int)blockIdx.y;
+#else
+        const int by = (int)blockIdx.y;
+#endif
+        const int ltile = by / bpt;
         const int tile = P.rows.tile_begin + ltile * P.rows.tile_stride;
         px = blockIdx.x * MT_CTA_W + lx;
-        py = tile * P.rows.tile_rows + (blockIdx.y - ltile * bpt) * MT_CTA_H + ly;
+        py = tile * P.rows.tile_rows + (by - ltile * bpt) * MT_CTA_H + ly;
         pixelID = ((px & 3) << 2) | (py & 3);                   // id = pX*4 + pY with (pX,pY) = (px%4, py%4)
         valid = px < P.W && py < P.H && (px >> 2) < P.tx && (py >> 2) < P.ty;
     } else {
