@@ -186,6 +186,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ctx-flags", type=int, default=0, help="extra MT_FLAG_* bits for A/B runs (e.g. 8 = no quad layout)")
     ap.add_argument("--tile-rows", type=int, default=8, help="frame8k: pixel rows per cyclic tile (multiple of 8)")
+    ap.add_argument("--gather", default="peer_store", choices=["peer_store", "copy"], help="frame8k: kernel peer stores or copy-engine tile pushes")
     ap.add_argument("--gather-mask", action="store_true", help="frame8k: also send the god-ray mask tiles to GPU 0 (needed only if god rays run)")
     ap.add_argument("--sweep", action="store_true", help="N>1: rank r renders view r of the sun/coverage sweep")
     args = ap.parse_args()
@@ -212,7 +213,7 @@ def main():
     noise = textures.load_noise()
 
     if args.workload == "frame8k":
-        w, h, workload = 7680, 4320, f"7680x4320 full-quality frame, cyclic {args.tile_rows}-row tiles over the ranks, HDR tiles stored straight into GPU 0 over NVLink (BASELINE config 4)"
+        w, h, workload = 7680, 4320, f"7680x4320 full-quality frame, cyclic {args.tile_rows}-row tiles over the ranks, HDR tiles {'stored straight into GPU 0 by the march kernel' if args.gather == 'peer_store' else 'pushed to GPU 0 by the copy engine behind the next tile group'} over NVLink (BASELINE config 4)"
     elif args.workload == "seq1080p":
         w, h, workload = 1920, 1080, "1920x1080 16-frame pan: Reprojection + 1/16 Cloud + god rays + tone map (BASELINE config 2)"
     elif args.workload == "views256":
@@ -246,7 +247,7 @@ def main():
         class _Dist:  # single-process stand-in so N=1 runs the same code path
             def get_rank(self): return 0
             def get_world_size(self): return 1
-        shard = sharding.ShardedFrame(r, dist if world > 1 else _Dist(), tile_rows=args.tile_rows, with_mask=args.gather_mask)
+        shard = sharding.ShardedFrame(r, dist if world > 1 else _Dist(), tile_rows=args.tile_rows, with_mask=args.gather_mask, mode=args.gather)
 
     seq_state = {"frame": 0}
     my_views = [scene_for_view(v, w, h, sweep=True)[3] for v in sharding.views_of_rank(256, world, rank)] if args.workload == "views256" else []
@@ -297,6 +298,8 @@ def main():
         r.flush_l2(0)
         r.event_record(0)
         step()
+        if args.workload == "frame8k" and args.gather == "copy":
+            r.join_copies()  # the timed interval ends when this rank's tile pushes have landed, not when its kernels end
         r.event_record(1)
         if args.workload == "frame8k" and world > 1:
             shard.finish()  # frame boundary: all ranks' tiles have landed on GPU 0

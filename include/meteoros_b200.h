@@ -219,6 +219,8 @@ MT_API MtStatus mtReadImageRows(MtContext* ctx, MtImage which, uint32_t row_begi
  * behind the rendering of frame k+1.                                                                                  */
 MT_API MtStatus mtReadImageAsync(MtContext* ctx, MtImage which, void* host, size_t bytes);
 MT_API MtStatus mtWaitReads(MtContext* ctx);
+/* Device-side join: work issued to the context after this call waits for every copy issued so far (no host sync). */
+MT_API MtStatus mtJoinCopies(MtContext* ctx);
 MT_API MtStatus mtWriteImage(MtContext* ctx, MtImage which, const void* host, size_t bytes); /* H2D, ordered */
 MT_API MtStatus mtClearImages(MtContext* ctx);    /* zero all four images (reference: images are never cleared; zeros assumed) */
 MT_API MtStatus mtImageDevicePtr(MtContext* ctx, MtImage which, void** dev_ptr);             /* zero-copy interop */
@@ -230,6 +232,11 @@ MT_API MtStatus mtSetCloudOutput(MtContext* ctx, void* hdr_dev_ptr, void* mask_d
 MT_API MtStatus mtExportImageHandle(MtContext* ctx, MtImage which, uint8_t handle[64]);
 MT_API MtStatus mtOpenPeerImage(MtContext* ctx, const uint8_t handle[64], void** dev_ptr);
 MT_API MtStatus mtClosePeerImage(MtContext* ctx, void* dev_ptr);
+/* Copy-engine variant of the gather: copies this context's rows of the row tiles [tile_begin, tile_end) step tile_stride
+ * of image `which` into the same rows of a peer image (mtOpenPeerImage pointer, same dimensions) on the context's copy
+ * stream, after the work issued so far; later dispatches overlap with the copies.  mtWaitReads / mtSynchronize wait.   */
+MT_API MtStatus mtCopyTilesToPeer(MtContext* ctx, MtImage which, uint32_t tile_rows, uint32_t tile_begin, uint32_t tile_end,
+                                  uint32_t tile_stride, void* peer_dev_ptr);
 
 /* ---- uniform producers: the host-side state the reference keeps in Camera / Scene / Sky ------------------ */
 /* Pure host functions (no context, no GPU): a C/C++ application links them instead of re-deriving glm's arithmetic.        */

@@ -86,6 +86,7 @@ PROTOTYPES = {
     "mtReadImageRows": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t]),
     "mtReadImageAsync": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
     "mtWaitReads": (C.c_int, [C.c_void_p]),
+    "mtJoinCopies": (C.c_int, [C.c_void_p]),
     "mtWriteImage": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
     "mtClearImages": (C.c_int, [C.c_void_p]),
     "mtImageDevicePtr": (C.c_int, [C.c_void_p, C.c_int, c_void_pp]),
@@ -109,6 +110,7 @@ PROTOTYPES = {
     "mtxLoadVolumeFromSlices": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t]),
     "mtxSaveVolume": (C.c_int, [C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]),
     "mtxLoadVolume": (C.c_int, [C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "mtCopyTilesToPeer": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]),
     "mtGetCounters": (C.c_int, [C.c_void_p, C.POINTER(MtCounters), C.c_int]),
     "mtLastPassMs": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
     "mtStreamHandle": (C.c_int, [C.c_void_p, c_void_pp]),

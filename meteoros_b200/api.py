@@ -220,6 +220,9 @@ class CloudRenderer:
     def wait_reads(self):
         self._check(self._lib.mtWaitReads(self._h), "mtWaitReads")
 
+    def join_copies(self):
+        self._check(self._lib.mtJoinCopies(self._h), "mtJoinCopies")
+
     def clear_images(self):
         self._check(self._lib.mtClearImages(self._h), "mtClearImages")
 
@@ -244,6 +247,10 @@ class CloudRenderer:
 
     def close_peer_image(self, ptr: int):
         self._check(self._lib.mtClosePeerImage(self._h, C.c_void_p(ptr)), "mtClosePeerImage")
+
+    def copy_tiles_to_peer(self, which: int, tile_rows: int, tile_begin: int, tile_end: int, tile_stride: int, peer_ptr: int):
+        self._check(self._lib.mtCopyTilesToPeer(self._h, which, tile_rows, tile_begin, tile_end, tile_stride, C.c_void_p(peer_ptr)),
+                    "mtCopyTilesToPeer")
 
     # ---- measurement ----------------------------------------------------------------------------------------
     def counters(self, reset: bool = True) -> dict:

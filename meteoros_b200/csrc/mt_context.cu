@@ -688,6 +688,14 @@ MtStatus mtWaitReads(MtContext* c)
     for (auto& p : c->pending) p.active = false;
     return MT_OK;
 }
+MtStatus mtJoinCopies(MtContext* c)
+{
+    if (!c) return MT_ERR_INVALID;
+    MT_CUDA(c, cudaSetDevice(c->device));
+    MT_CUDA(c, cudaEventRecord(c->producedEv, c->copyStream));
+    MT_CUDA(c, cudaStreamWaitEvent(c->stream, c->producedEv, 0));
+    return MT_OK;
+}
 MtStatus mtWriteImage(MtContext* c, MtImage which, const void* host, size_t bytes)
 {
     if (!c) return MT_ERR_INVALID;
@@ -754,6 +762,26 @@ MtStatus mtClosePeerImage(MtContext* c, void* p)
     if (c->outHdr == p) c->outHdr = nullptr;
     if (c->outMask == p) c->outMask = nullptr;
     MT_CUDA(c, cudaIpcCloseMemHandle(p));
+    return MT_OK;
+}
+
+MtStatus mtCopyTilesToPeer(MtContext* c, MtImage which, uint32_t tile_rows, uint32_t tile_begin, uint32_t tile_end,
+                           uint32_t tile_stride, void* peer)
+{
+    if (!c) return MT_ERR_INVALID;
+    MT_REQUIRE(c, peer != nullptr && (int)which >= 0 && (int)which <= MT_IMAGE_LDR_PREV, "mtCopyTilesToPeer: bad arguments");
+    MT_REQUIRE(c, tile_rows >= 1 && tile_stride >= 1, "mtCopyTilesToPeer: bad tiling");
+    MT_CUDA(c, cudaSetDevice(c->device));
+    const size_t pitch = (size_t)c->W * ((which == MT_IMAGE_LDR || which == MT_IMAGE_LDR_PREV) ? 4 : 16);
+    const char* src = (const char*)image_ptr(c, which);
+    const uint32_t ntiles = ((uint32_t)c->H + tile_rows - 1) / tile_rows;
+    if (tile_end > ntiles) tile_end = ntiles;
+    MT_CUDA(c, cudaEventRecord(c->producedEv, c->stream));
+    MT_CUDA(c, cudaStreamWaitEvent(c->copyStream, c->producedEv, 0));
+    for (uint32_t t = tile_begin; t < tile_end; t += tile_stride) {
+        const size_t r0 = (size_t)t * tile_rows, r1 = (r0 + tile_rows < (size_t)c->H) ? r0 + tile_rows : (size_t)c->H;
+        MT_CUDA(c, cudaMemcpyAsync((char*)peer + pitch * r0, src + pitch * r0, pitch * (r1 - r0), cudaMemcpyDeviceToDevice, c->copyStream));
+    }
     return MT_OK;
 }
 

@@ -52,7 +52,13 @@ class ShardedFrame:
     so the host logic can be exercised on CPU with the gloo backend and a stub renderer.
     """
 
-    def __init__(self, renderer, dist, tile_rows: int = 32, with_mask: bool = True):
+    def __init__(self, renderer, dist, tile_rows: int = 32, with_mask: bool = True, mode: str = "peer_store", groups: int = 4):
+        """mode "peer_store": the march kernel's own stores land in GPU 0's image (fused compute + transfer).
+        mode "copy": tiles are rendered locally in `groups` launches and each finished group is pushed to GPU 0 by the
+        copy engine (mtCopyTilesToPeer) while the next group renders."""
+        if mode not in ("peer_store", "copy"):
+            raise ValueError("mode must be 'peer_store' or 'copy'")
+        self.mode, self.groups = mode, max(1, int(groups))
         self.r = renderer
         self.dist = dist
         self.rank = dist.get_rank()
@@ -73,14 +79,28 @@ class ShardedFrame:
             self.peer.hdr_ptr = self.r.open_peer_image(handles[0])
             # without god rays the mask never leaves the GPU that made it: stores stay local
             self.peer.mask_ptr = self.r.open_peer_image(handles[1]) if self.with_mask else 0
-            self.r.set_cloud_output(self.peer.hdr_ptr, self.peer.mask_ptr or None)
+            if self.mode == "peer_store":
+                self.r.set_cloud_output(self.peer.hdr_ptr, self.peer.mask_ptr or None)
         if self.world > 1:
             self.dist.barrier()
 
     def dispatch(self):
         """Launch this rank's tiles (asynchronous on the renderer's stream)."""
         n = num_tiles(self.r.height, self.tile_rows)
-        self.r.dispatch_cloud_tiles(self.tile_rows, self.rank, n, self.world)
+        if self.mode == "peer_store" or self.rank == 0:
+            self.r.dispatch_cloud_tiles(self.tile_rows, self.rank, n, self.world)
+            return
+        mine = len(range(self.rank, n, self.world))
+        per = (mine + self.groups - 1) // self.groups
+        for g in range(self.groups):
+            first = self.rank + g * per * self.world
+            last = min(n, self.rank + (g + 1) * per * self.world)
+            if first >= last:
+                break
+            self.r.dispatch_cloud_tiles(self.tile_rows, first, last, self.world)
+            self.r.copy_tiles_to_peer(IMAGE_CLOUD_CUR, self.tile_rows, first, last, self.world, self.peer.hdr_ptr)
+            if self.with_mask:
+                self.r.copy_tiles_to_peer(IMAGE_GODRAY_MASK, self.tile_rows, first, last, self.world, self.peer.mask_ptr)
 
     def finish(self):
         """Frame boundary: every rank's stores have landed in rank 0's image."""
@@ -90,7 +110,8 @@ class ShardedFrame:
 
     def close(self):
         if self.rank != 0:
-            self.r.set_cloud_output(None, None)
+            if self.mode == "peer_store":
+                self.r.set_cloud_output(None, None)
             if self.peer.hdr_ptr:
                 self.r.close_peer_image(self.peer.hdr_ptr)
             if self.peer.mask_ptr:
