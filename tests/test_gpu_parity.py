@@ -556,3 +556,23 @@ def test_committed_golden_frame(api, noise):
     assert np.array_equal(dbg["steps"], g["steps"]) and np.array_equal(dbg["jitter_hash"], g["jitter_hash"])
     assert np.array_equal(dbg["accum"], g["accum"]) and np.array_equal(mask, g["mask"])
     check_hdr(hdr, g["hdr"])
+
+
+def test_multi_gpu_sharded_frame_is_bit_identical():
+    """Two or more B200s: the row-tile sharded frame gathered on rank 0 (peer stores and copy-engine pushes) equals the
+    single-GPU frame bit for bit (tools/check_sharded.py under torchrun).  Skipped on a single-GPU box."""
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    import torch
+
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least two GPUs")
+    root = Path(__file__).resolve().parents[1]
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(min(n, 4)),
+                        "--master-addr", "127.0.0.1", "--master-port", "29877", str(root / "tools" / "check_sharded.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("bit-identical to single-GPU: True") == 4
