@@ -79,6 +79,12 @@ typedef struct MtTuning {
     float cloud_speed;         /* CLOUD_SPEED, cloudRayMarch.comp:90  (0.08)                       */
     float cloud_top_offset;    /* CLOUD_TOP_OFFSET, cloudRayMarch.comp:91  (1.0)                   */
     float base_density_factor; /* cloudRayMarch.comp:571  (0.38)                                   */
+    /* Weather-map / cloud-type path.  The reference carries it as commented-out code
+     * (cloudRayMarch.comp:515-525 + getDensityHeightGradientForPoint :475-487) and runs with it OFF; use_weather != 0
+     * restores exactly that block: weather = texture(weatherMapSampler, unskewedSamplePoint.xz * weather_scale),
+     * baseCloud *= heightGradient(relativeHeight, weather.g) * 0.5, coverage = weather.r (instead of `coverage`).   */
+    uint32_t use_weather;      /* 0 (reference behaviour)                                          */
+    float weather_scale;       /* 1.0 = the literal commented code (the map then repeats every unit of the sample point) */
 } MtTuning;
 
 typedef enum MtStorage {

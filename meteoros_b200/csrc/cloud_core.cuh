@@ -98,21 +98,44 @@ MT_DEVICE f3 sky_color(const SkyConst& S, f3 dir)
     return mk3(col[0], col[1], col[2]);
 }
 
-// sampleLowFrequency (cloudRayMarch.comp:499-540): base cloud density with coverage applied.
-MT_DEVICE float low_freq_density(const Tex3D& low, float coverage, P2 pxy, float pz)
+// getDensityHeightGradientForPoint (cloudRayMarch.comp:475-487); only the weather path calls it.
+MT_DEVICE float height_gradient(float h, float cloudType)
 {
+    h = sat1(h);
+    const float stratocumulus = fmaxf(0.0f, remap1(h, 0.0f, 0.25f, 0.0f, 1.0f) * remap1(h, 0.3f, 0.65f, 1.0f, 0.0f));
+    const float stratus = fmaxf(0.0f, remap1(h, 0.0f, 0.1f, 0.0f, 1.0f) * remap1(h, 0.2f, 0.3f, 1.0f, 0.0f));
+    const float a = mix1(stratus, stratocumulus, sat1(cloudType * 2.0f));
+    const float b = mix1(stratocumulus, stratus, sat1((cloudType - 0.5f) * 2.0f));
+    return mix1(a, b, cloudType);
+}
+
+// sampleLowFrequency (cloudRayMarch.comp:499-540): base cloud density with coverage applied.
+// WEATHER = the shader's commented-out block :515-525 restored (MtTuning.use_weather): the weather map is sampled at
+// unskewedSamplePoint.xz, the base cloud is scaled by the height gradient of its cloud type and its red channel
+// replaces the constant coverage -- so neither the empty-cell bitmap (built for one coverage) nor the "nice" division
+// (1 - coverage may be 0) applies on that path.
+template <bool WEATHER>
+MT_DEVICE float low_freq_density(const CloudParams& P, float coverage, P2 pxy, float pz, float ux, float uz, float relH)
+{
+    const Tex3D& low = P.low;
     LinAxis X, Y, Z = lin_axis_repeat(pz, low.d);
     lin_axes_xy(pxy, low.w, low.h, X, Y);
     // provably empty filter cell: the result is exactly +0.  A warp whose lanes all sit in empty cells skips the
     // whole fetch + filter (SIMT: the branch is free when nobody takes it).
-    if (low.occ && !occ_cell_may_be_cloud(low, X.i0, Y.i0, Z.i0)) return 0.0f;
+    if (!WEATHER && low.occ && !occ_cell_may_be_cloud(low, X.i0, Y.i0, Z.i0)) return 0.0f;
     Rgba n = tex3d_rgba_axes(low, X, Y, Z);
     float fbm = sat1((n.g * 0.625f + n.b * 0.25f) + n.a * 0.125f);
     float omin = fbm - 0.9f;
     float base = sat1(div_nice(n.r - omin, 1.0f - omin));  // remapClamped(r, fbm-.9, 1, 0, 1); denominator in [0.9, 1.9]
-    // remapClampedBeforeAndAfter(base, cov, 1, 0, 1) * cov.  base <= cov clamps to cov and yields exactly +0; returning
-    // it here also keeps 0/(1-cov) away from the IEEE division's zero-dividend slow path (85 % of its calls in the
-    // first profile).
+    if (WEATHER) {
+        float wr, wg;
+        tex2d_rg(P.weather, ux * P.tun.weather_scale, uz * P.tun.weather_scale, wr, wg);
+        base *= height_gradient(relH, wg) * 0.5f;
+        coverage = wr;
+        const float v = clamp1(base, coverage, 1.0f);  // remapClampedBeforeAndAfter(base, cov, 1, 0, 1) * cov, IEEE division
+        return sat1((v - coverage) / (1.0f - coverage)) * coverage;
+    }
+    // remapClampedBeforeAndAfter(base, cov, 1, 0, 1) * cov.  base <= cov clamps to cov and yields exactly +0.
     if (!(base > coverage)) return 0.0f;
     float b = sat1(div_nice(base - coverage, 1.0f - coverage));  // coverage in [0, 0.91] (mtSetTuning)
     return b * coverage;
@@ -220,7 +243,7 @@ MT_DEVICE RaySetup cloud_ray_setup(const CloudParams& P, const MarchConst& M, in
 }
 
 // One iteration of the march loop (cloudRayMarch.comp:629-678) at parameter t, without the running sums.
-template <bool COUNT>
+template <bool COUNT, bool WEATHER>
 MT_DEVICE StepSample cloud_step_sample(const CloudParams& P, const MarchConst& M, const RaySetup& R, int jidx, float t,
                                        RayCounters& cnt)
 {
@@ -242,7 +265,7 @@ MT_DEVICE StepSample cloud_step_sample(const CloudParams& P, const MarchConst& M
     float h = div_thickness(fabsf(cosTheta * (lenFromCam - R.lenToInner)));
     // skewSamplePointWithWind (:489-497)
     f3 skew = (sp + ((wind * h) * P.tun.cloud_top_offset) * 0.009f) + M.windSkew;
-    float baseDensity = low_freq_density(P.low, coverage, pk2(skew.x, skew.y), skew.z) * P.tun.base_density_factor;
+    float baseDensity = low_freq_density<WEATHER>(P, coverage, pk2(skew.x, skew.y), skew.z, pos.x, pos.z, h) * P.tun.base_density_factor;
     if (COUNT) cnt.steps++;
     if (baseDensity > 0.0f) {
         if (COUNT) cnt.incloud++;
@@ -259,7 +282,9 @@ MT_DEVICE StepSample cloud_step_sample(const CloudParams& P, const MarchConst& M
             // scalar adds: a mul2 feeding an add2 would be contracted into an FFMA2 (mt_math.cuh)
             P2 lxy = sub2(pk2(pos.x + lo2(off), pos.y + hi2(off)), relxy);
             float lz = (pos.z + (cs.z * R.stepSize) * fi) - relOrigin.z;
-            float cur = low_freq_density(P.low, coverage, div_thickness2(lxy), div_thickness(lz));
+            const P2 sxy = div_thickness2(lxy);
+            const float sz = div_thickness(lz);
+            float cur = low_freq_density<WEATHER>(P, coverage, sxy, sz, lo2(sxy), sz, h);
             if (cur > 0.0f) {
                 if (COUNT) cnt.cone++;
                 dl += erode(1.5f * cur, edge);
@@ -302,7 +327,7 @@ MT_DEVICE void cloud_composite(const RaySetup& R, float accum, float color, F4& 
 }
 
 // One invocation of main(): setup, the sequential march, composite.
-template <bool COUNT, bool DEBUG>
+template <bool COUNT, bool DEBUG, bool WEATHER>
 MT_DEVICE void cloud_ray(const CloudParams& P, const MarchConst& M, int px, int py, int pixelID, F4& hdr, F4& mask,
                          RayCounters& cnt, MtRayDebug* dbg)
 {
@@ -324,7 +349,7 @@ MT_DEVICE void cloud_ray(const CloudParams& P, const MarchConst& M, int px, int 
     for (float t = R.t_in; t < R.t_out && iters < MT_MAX_MARCH_ITERS; t += R.stepSize, ++iters) {
         const int jidx = (pixelID + mt_f2i(t)) & 15;  // int(mod(float(pixelID + int(t)), 16.0)), argument >= 0
         if (DEBUG) jhash = (jhash ^ (unsigned)jidx) * 16777619u;
-        const StepSample S = cloud_step_sample<COUNT>(P, M, R, jidx, t, cnt);
+        const StepSample S = cloud_step_sample<COUNT, WEATHER>(P, M, R, jidx, t, cnt);
         if (cloud_step_combine(S, accum, transmittance, color)) {
             if (COUNT) cnt.early++;
             ++iters;

@@ -79,7 +79,7 @@ cudaError_t mt_launch_occupancy(const Tex3D& low, uint32_t* occ, float coverage,
 
 __device__ __forceinline__ float f16_round(float x) { return __half2float(__float2half_rn(x)); }
 
-template <bool FULL, bool COUNT, bool DEBUG>
+template <bool FULL, bool COUNT, bool DEBUG, bool WEATHER>
 #ifndef MT_BOTTOM_UP
 #define MT_BOTTOM_UP 0  /* A/B at 4K and 8K: no measurable difference (5.09 ms both) */
 #endif
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(128, MT_CLOUD_MINBLOCKS) cloud_raymarch_kernel
     if (valid) {
         F4 hdr, mask;
         const size_t idx = (size_t)py * (size_t)P.W + (size_t)px;
-        cloud_ray<COUNT, DEBUG>(P, M, px, py, pixelID, hdr, mask, cnt, DEBUG ? (P.debug + idx) : nullptr);
+        cloud_ray<COUNT, DEBUG, WEATHER>(P, M, px, py, pixelID, hdr, mask, cnt, DEBUG ? (P.debug + idx) : nullptr);
         if (P.f16_emulate) {
             hdr.x = f16_round(hdr.x); hdr.y = f16_round(hdr.y); hdr.z = f16_round(hdr.z); hdr.w = f16_round(hdr.w);
             mask.x = f16_round(mask.x); mask.y = f16_round(mask.y); mask.z = f16_round(mask.z); mask.w = f16_round(mask.w);
@@ -240,6 +240,7 @@ __global__ void __launch_bounds__(128) cloud_rays_kernel(const __grid_constant__
     if (threadIdx.x == 0) P.ctaSteps[blockIdx.x] = ctaSteps;
 }
 
+template <bool WEATHER>
 __global__ void __launch_bounds__(128, MT_CLOUD_MINBLOCKS) cloud_steps_kernel(const __grid_constant__ CloudParams P)
 {
     const int k = blockIdx.y;
@@ -254,7 +255,7 @@ __global__ void __launch_bounds__(128, MT_CLOUD_MINBLOCKS) cloud_steps_kernel(co
     if (!(t < R.t_out)) return;
     const int jidx = (P.tm.frameCountMod16 + mt_f2i(t)) & 15;
     RayCounters none = { 0u, 0u, 0u, 0u, 0u, 0u };
-    const StepSample S = cloud_step_sample<false>(P, M, R, jidx, t, none);
+    const StepSample S = cloud_step_sample<false, WEATHER>(P, M, R, jidx, t, none);
     P.samples[(size_t)k * ((size_t)gridDim.x * 128) + ray] = make_float2(S.inc, S.energy);
 }
 
@@ -295,7 +296,8 @@ cudaError_t mt_launch_cloud_sixteenth_split(const CloudParams& P, cudaStream_t s
 {
     const unsigned ctas = (unsigned)((P.tx / 8) * (P.ty / 4) / 4);  // tx, ty are multiples of 32
     cloud_rays_kernel<<<ctas, 128, 0, stream>>>(P);
-    cloud_steps_kernel<<<dim3(ctas, MT_STEP_SLICES, 1), 128, 0, stream>>>(P);
+    if (P.tun.use_weather) cloud_steps_kernel<true><<<dim3(ctas, MT_STEP_SLICES, 1), 128, 0, stream>>>(P);
+    else cloud_steps_kernel<false><<<dim3(ctas, MT_STEP_SLICES, 1), 128, 0, stream>>>(P);
     cloud_fold_kernel<<<ctas, 128, 0, stream>>>(P);
     *launches = 3;
     return cudaGetLastError();
@@ -315,14 +317,17 @@ cudaError_t mt_launch_cloud(const CloudParams& P, cudaStream_t stream)
     dim3 block(128, 1, 1);
     if (grid.x == 0 || grid.y == 0) return cudaSuccess;
     const bool count = P.counters != nullptr, debug = P.debug != nullptr;
-    if (P.full) {
-        if (debug) cloud_raymarch_kernel<true, true, true><<<grid, block, 0, stream>>>(P);
-        else if (count) cloud_raymarch_kernel<true, true, false><<<grid, block, 0, stream>>>(P);
-        else cloud_raymarch_kernel<true, false, false><<<grid, block, 0, stream>>>(P);
+    if (P.tun.use_weather) {  // weather path: production variants only (mt_context.cu rejects counters / debug with it)
+        if (P.full) cloud_raymarch_kernel<true, false, false, true><<<grid, block, 0, stream>>>(P);
+        else cloud_raymarch_kernel<false, false, false, true><<<grid, block, 0, stream>>>(P);
+    } else if (P.full) {
+        if (debug) cloud_raymarch_kernel<true, true, true, false><<<grid, block, 0, stream>>>(P);
+        else if (count) cloud_raymarch_kernel<true, true, false, false><<<grid, block, 0, stream>>>(P);
+        else cloud_raymarch_kernel<true, false, false, false><<<grid, block, 0, stream>>>(P);
     } else {
-        if (debug) cloud_raymarch_kernel<false, true, true><<<grid, block, 0, stream>>>(P);
-        else if (count) cloud_raymarch_kernel<false, true, false><<<grid, block, 0, stream>>>(P);
-        else cloud_raymarch_kernel<false, false, false><<<grid, block, 0, stream>>>(P);
+        if (debug) cloud_raymarch_kernel<false, true, true, false><<<grid, block, 0, stream>>>(P);
+        else if (count) cloud_raymarch_kernel<false, true, false, false><<<grid, block, 0, stream>>>(P);
+        else cloud_raymarch_kernel<false, false, false, false><<<grid, block, 0, stream>>>(P);
     }
     return cudaGetLastError();
 }

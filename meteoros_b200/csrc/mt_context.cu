@@ -168,6 +168,8 @@ void mtDefaultTuning(MtTuning* t)
     t->cloud_speed = 0.080f;
     t->cloud_top_offset = 1.0f;
     t->base_density_factor = 0.380f;
+    t->use_weather = 0u;
+    t->weather_scale = 1.0f;
 }
 
 MtStatus mtCreate(const MtConfig* cfg, MtContext** out)
@@ -301,6 +303,7 @@ MtStatus mtSetTuning(MtContext* c, const MtTuning* t)
     if (!c) return MT_ERR_INVALID;
     MT_REQUIRE(c, t != nullptr, "mtSetTuning: null tuning");
     MT_REQUIRE(c, t->coverage >= 0.0f && t->coverage <= 0.91f, "mtSetTuning: coverage must be in [0, 0.91]");
+    MT_REQUIRE(c, t->weather_scale == t->weather_scale, "mtSetTuning: weather_scale is NaN");
     c->tun = *t;
     return MT_OK;
 }
@@ -321,7 +324,7 @@ static MtStatus upload(MtContext* c, int slot, uint32_t w, uint32_t h, uint32_t 
     MT_CUDA(c, cudaMemcpyAsync(c->tex[slot], rgba8, bytes, cudaMemcpyHostToDevice, c->stream));
     cudaFree(c->quads[slot]);
     c->quads[slot] = nullptr;
-    if (slot != MT_TEX_WEATHER) {  // the weather map is never sampled
+    {
         MT_CUDA(c, cudaMalloc(&c->quads[slot], bytes * 4 * ((MT_TEX_BRICKS && d > 1) ? 2 : 1)));
         MT_CUDA(c, mt_launch_build_quads(c->tex[slot], (int)w, (int)h, (int)d, c->quads[slot], c->stream));
         c->launches += 1;
@@ -394,6 +397,14 @@ static MtStatus cloud_dispatch(MtContext* c, int full, const RowTiles* tiles, bo
     P.high.w = c->texw[MT_TEX_HIGH_FREQ]; P.high.h = c->texh[MT_TEX_HIGH_FREQ]; P.high.d = c->texd[MT_TEX_HIGH_FREQ];
     P.curl.texels = c->tex[MT_TEX_CURL];
     P.curl.w = c->texw[MT_TEX_CURL]; P.curl.h = c->texh[MT_TEX_CURL];
+    if (c->tun.use_weather) {
+        if (!c->tex[MT_TEX_WEATHER]) return fail(c, MT_ERR_NOT_READY, "cloud dispatch: use_weather needs the weather map uploaded");
+        if (debug || (c->flags & MT_FLAG_COUNTERS))
+            return fail(c, MT_ERR_INVALID, "cloud dispatch: counters / debug records are not available with use_weather");
+        P.weather.texels = c->tex[MT_TEX_WEATHER];
+        P.weather.quads = (const Quad*)c->quads[MT_TEX_WEATHER];
+        P.weather.w = c->texw[MT_TEX_WEATHER]; P.weather.h = c->texh[MT_TEX_WEATHER];
+    }
     P.low.occ = nullptr;
     P.high.occ = nullptr;
     if (c->occ) {  // (re)build the empty-cell bitmap when the volume or the coverage changed

@@ -67,6 +67,7 @@ struct CloudParams {
     SkyConst sky;
     Tex3D low, high;
     Tex2D curl;
+    Tex2D weather;         // sampled only when tun.use_weather
     const MarchConst* mc;  // device memory, written by cloud_setup_kernel
     F4* hdr;
     F4* mask;

@@ -43,10 +43,12 @@ TUNING_DTYPE = np.dtype(
         ("cloud_speed", "<f4"),
         ("cloud_top_offset", "<f4"),
         ("base_density_factor", "<f4"),
+        ("use_weather", "<u4"),
+        ("weather_scale", "<f4"),
     ]
 )
 assert CAMERA_DTYPE.itemsize == 152 and TIME_DTYPE.itemsize == 76 and SUNSKY_DTYPE.itemsize == 52
-assert TUNING_DTYPE.itemsize == 52
+assert TUNING_DTYPE.itemsize == 60
 
 EARTH_RADIUS = 6371000.0
 ATMOSPHERE_RADIUS_OUTER = EARTH_RADIUS + 20000.0
@@ -62,6 +64,8 @@ def default_tuning() -> np.ndarray:
     t["cloud_speed"] = 0.080
     t["cloud_top_offset"] = 1.0
     t["base_density_factor"] = 0.380
+    t["use_weather"] = 0
+    t["weather_scale"] = 1.0
     return t
 
 

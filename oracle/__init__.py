@@ -187,6 +187,12 @@ def ray_sphere(ro, rd, c, radius):
     return np.array(pt[:], np.float32), np.float32(t.value), bool(valid.value)
 
 
+def density_height_gradient(relative_height, cloud_type):
+    f = lib().mto_density_height_gradient
+    f.restype = C.c_float
+    return float(f(C.c_float(relative_height), C.c_float(cloud_type)))
+
+
 def cloud_grid(W, H):
     tx, ty = C.c_int(), C.c_int()
     lib().mto_cloud_grid(C.c_int(W), C.c_int(H), C.byref(tx), C.byref(ty))

@@ -384,14 +384,35 @@ typedef struct {
     int W, H;
 } CloudEnv;
 
-/* cloudRayMarch.comp:499-540 */
-static float sample_low_frequency(const CloudEnv* e, v3 p)
+/* getDensityHeightGradientForPoint, cloudRayMarch.comp:475-487 (reached only through the weather path below) */
+static float density_height_gradient(float relativeHeight, float cloudType)
+{
+    relativeHeight = clampf(relativeHeight, 0.0f, 1.0f);
+    /* `cumulus` (:479) is computed by the shader but never used */
+    float stratocumulus = fmaxf(0.0f, remapf(relativeHeight, 0.0f, 0.25f, 0.0f, 1.0f) * remapf(relativeHeight, 0.3f, 0.65f, 1.0f, 0.0f));
+    float stratus = fmaxf(0.0f, remapf(relativeHeight, 0.0f, 0.1f, 0.0f, 1.0f) * remapf(relativeHeight, 0.2f, 0.3f, 1.0f, 0.0f));
+    float a = mixf(stratus, stratocumulus, clampf(cloudType * 2.0f, 0.0f, 1.0f));
+    float b = mixf(stratocumulus, stratus, clampf((cloudType - 0.5f) * 2.0f, 0.0f, 1.0f));
+    return mixf(a, b, cloudType);
+}
+
+/* cloudRayMarch.comp:499-540.  With tun->use_weather the commented block :515-525 is live:
+ * weather sampled at unskewedSamplePoint.xz (* weather_scale), base cloud scaled by the height gradient of the
+ * weather's cloud type, coverage taken from the weather's red channel. */
+static float sample_low_frequency(const CloudEnv* e, v3 p, v3 unskewed, float relativeHeight)
 {
     v4 n = tex3d_linear(e->tex->low, e->tex->low_w, e->tex->low_h, e->tex->low_d, p.x, p.y, p.z);
     float fbm = (n.y * 0.625f + n.z * 0.25f) + n.w * 0.125f;
     fbm = clampf(fbm, 0.0f, 1.0f);
     float baseCloud = remap_clamped(n.x, fbm - 0.9f, 1.0f, 0.0f, 1.0f);
     float cov = e->tun->coverage;
+    if (e->tun->use_weather && e->tex->weather) {
+        float ws = e->tun->weather_scale;
+        v4 wd = tex2d_linear(e->tex->weather, e->tex->weather_w, e->tex->weather_h, unskewed.x * ws, unskewed.z * ws);
+        float grad = density_height_gradient(relativeHeight, wd.y);
+        baseCloud *= grad * 0.5f;
+        cov = wd.x;
+    }
     float b = remap_clamped_ba(baseCloud, cov, 1.0f, 0.0f, 1.0f);
     b *= cov;
     return b;
@@ -467,7 +488,7 @@ static float ray_march(const CloudEnv* e, Ray ray, v3 earthCenter, v3 startPos, 
         v3 skewed = add3(samplePoint, scale3(scale3(scale3(wind, relativeHeight), tun->cloud_top_offset), 0.009f));
         skewed = add3(skewed, scale3(scale3(add3(wind, V3(0.0f, 0.1f, 0.0f)), tun->cloud_speed), e->tm->time[1]));
 
-        float baseDensity = sample_low_frequency(e, skewed) * baseDensityFactor;
+        float baseDensity = sample_low_frequency(e, skewed, pos, relativeHeight) * baseDensityFactor;
         if (cnt) cnt->steps++;
         if (dbg) { dbg->steps++; dbg->jitter_hash = (dbg->jitter_hash ^ (uint32_t)_index) * 16777619u; }
 
@@ -480,7 +501,7 @@ static float ray_march(const CloudEnv* e, Ray ray, v3 earthCenter, v3 startPos, 
             for (int i = 0; i < 6; ++i) {
                 v3 lightPos = add3(pos, scale3(scale3(kernel[i], stepSize), (float)i));
                 v3 sl = divs3(sub3(lightPos, V3(earthCenter.x, ATMOSPHERE_RADIUS_INNER - EARTH_RADIUS, earthCenter.z)), ATMOSPHERE_THICKNESS);
-                float cur = sample_low_frequency(e, sl);
+                float cur = sample_low_frequency(e, sl, sl, relativeHeight);
                 if (cur > 0.0f) {
                     if (cnt) cnt->cone_hits++;
                     densityAlongLight += erode_high_frequency(e, 1.5f * cur, skewed, relativeHeight);
@@ -938,6 +959,7 @@ void mto_ray_sphere(const float ro[3], const float rd[3], const float c[3], floa
     *t = is.t;
     *valid = is.valid;
 }
+float mto_density_height_gradient(float relativeHeight, float cloudType) { return density_height_gradient(relativeHeight, cloudType); }
 void mto_cloud_grid(int W, int H, int* threads_x, int* threads_y) { cloud_grid(W, H, threads_x, threads_y); }
 void mto_atmosphere_color(const float dir[3], const float sun_minus_origin[3], float sunIntensity, const float skySun[3], float out[3])
 {

@@ -48,6 +48,7 @@ uint32_t mto_wang_hash(uint32_t u, uint32_t v, uint32_t s);
 void mto_encode_float_rgba(float v, float out[4]);
 void mto_ray_sphere(const float ro[3], const float rd[3], const float c[3], float radius, float point[3], float* t, int* valid);
 void mto_cloud_grid(int W, int H, int* threads_x, int* threads_y);
+float mto_density_height_gradient(float relativeHeight, float cloudType);
 void mto_atmosphere_color(const float dir[3], const float sun_minus_origin[3], float sunIntensity, const float skySun[3], float out[3]);
 
 #ifdef __cplusplus

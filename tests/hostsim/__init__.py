@@ -43,9 +43,10 @@ def cloud(cam, tm, tun, noise, W, H, full, debug_dtype):
     cnt = np.zeros(6, np.uint64)
     dbg = np.zeros((H, W), debug_dtype)
     cam, tm, tun = (np.ascontiguousarray(x) for x in (cam, tm, tun))
-    lo, hi, cu = noise["low"], noise["high"], noise["curl"]
+    lo, hi, cu, we = noise["low"], noise["high"], noise["curl"], noise["weather"]
     lib().hs_cloud(_p(cam), _p(tm), _p(tun), _p(lo), lo.shape[2], lo.shape[1], lo.shape[0], _p(hi), hi.shape[2], hi.shape[1],
-                   hi.shape[0], _p(cu), cu.shape[1], cu.shape[0], W, H, int(full), _p(hdr), _p(mask), _p(cnt), _p(dbg))
+                   hi.shape[0], _p(cu), cu.shape[1], cu.shape[0], _p(we), we.shape[1], we.shape[0], W, H, int(full), _p(hdr),
+                   _p(mask), _p(cnt), _p(dbg))
     keys = ("rays", "rays_marched", "steps", "steps_incloud", "cone_hits", "early_exits")
     return hdr, mask, dict(zip(keys, (int(v) for v in cnt))), dbg
 

@@ -18,7 +18,8 @@ using std::min;
 extern "C" {
 
 int hs_cloud(const MtCameraUBO* cam, const MtTimeUBO* tm, const MtTuning* tun, const uint8_t* low, int lw, int lh, int ld,
-             const uint8_t* high, int hw, int hh, int hd, const uint8_t* curl, int cw, int ch, int W, int H, int full,
+             const uint8_t* high, int hw, int hh, int hd, const uint8_t* curl, int cw, int ch, const uint8_t* weather, int ww, int wh,
+             int W, int H, int full,
              float* hdr, float* mask, unsigned long long* counters, MtRayDebug* debug)
 {
     CloudParams P;
@@ -30,6 +31,7 @@ int hs_cloud(const MtCameraUBO* cam, const MtTimeUBO* tm, const MtTuning* tun, c
     P.low.texels = (const uint32_t*)low; P.low.w = lw; P.low.h = lh; P.low.d = ld;
     P.high.texels = (const uint32_t*)high; P.high.w = hw; P.high.h = hh; P.high.d = hd;
     P.curl.texels = (const uint32_t*)curl; P.curl.w = cw; P.curl.h = ch;
+    P.weather.texels = (const uint32_t*)weather; P.weather.w = ww; P.weather.h = wh;
     // empty-cell bitmap, built exactly like occupancy_build_kernel does
     std::vector<uint32_t> occ;
     if (lw >= 32) {
@@ -78,7 +80,8 @@ int hs_cloud(const MtCameraUBO* cam, const MtTimeUBO* tm, const MtTuning* tun, c
             size_t idx = (size_t)py * W + px;
             MtRayDebug scratch;
             memset(&cnt, 0, sizeof(cnt));
-            cloud_ray<true, true>(P, M, px, py, id, h, m, cnt, debug ? debug + idx : &scratch);
+            if (tun->use_weather) cloud_ray<true, true, true>(P, M, px, py, id, h, m, cnt, debug ? debug + idx : &scratch);
+            else cloud_ray<true, true, false>(P, M, px, py, id, h, m, cnt, debug ? debug + idx : &scratch);
             tot[0] += cnt.rays; tot[1] += cnt.marched; tot[2] += cnt.steps; tot[3] += cnt.incloud; tot[4] += cnt.cone; tot[5] += cnt.early;
             memcpy(hdr + 4 * idx, &h, 16);
             memcpy(mask + 4 * idx, &m, 16);

@@ -194,6 +194,44 @@ def test_cloud_tuning_sweep(api, oracle_mod, noise):
             assert np.array_equal(mask, ref["mask"])
 
 
+@pytest.mark.parametrize("scale", [1.0e-4, 3.7e-5])
+def test_cloud_weather_path(api, oracle_mod, noise, scale):
+    """MtTuning.use_weather (cloudRayMarch.comp:515-525 restored): per-sample coverage and height gradient from the
+    weather map.  Same bars; both dispatch shapes (one launch per ray / step-parallel 1-of-16) go through it."""
+    w, h = 322, 182
+    cam, tm, _, tun = default_scene(w, h, frame_id=4, total_time=21.0, yaw=15.0, pitch=4.0)
+    tun["use_weather"], tun["weather_scale"] = 1, scale
+    ref = oracle_mod.cloud(cam, tm, tun, noise, w, h, full=True, debug=True)
+    assert (ref["debug"]["accum"] > 0).mean() > 0.02
+    with make_renderer(api, noise, w, h) as r:
+        r.set_camera(cam); r.set_time(tm); r.set_tuning(tun)
+        r.dispatch_cloud_full()
+        hdr = r.read_image(api.IMAGE_CLOUD_CUR)
+        mask = r.read_image(api.IMAGE_GODRAY_MASK)
+        check_hdr(hdr, ref["hdr"])
+        assert np.array_equal(mask, ref["mask"])
+        assert np.array_equal(hdr[..., 3], ref["hdr"][..., 3])       # accumulated density: bit-exact
+        # 1-of-16: step-parallel and sequential marches agree bit for bit, and with the oracle's selected pixels
+        r.clear_images(); r.dispatch_cloud()
+        step_par = r.read_image(api.IMAGE_CLOUD_CUR)
+        sel = oracle_mod.cloud(cam, tm, tun, noise, w, h, full=False, hdr=np.zeros((h, w, 4), np.float32))
+        assert np.array_equal(step_par[..., 3], sel["hdr"][..., 3])
+        check_hdr(step_par, sel["hdr"])
+    with make_renderer(api, noise, w, h, flags=api.FLAG_SEQUENTIAL_MARCH) as r:
+        r.set_camera(cam); r.set_time(tm); r.set_tuning(tun)
+        r.dispatch_cloud()
+        assert np.array_equal(r.read_image(api.IMAGE_CLOUD_CUR), step_par)
+        with pytest.raises(api.MeteorosError):
+            r.dispatch_cloud_debug(False) # debug records / counters are not built for the weather variant
+    with api.CloudRenderer(w, h) as r:    # weather requested but never uploaded
+        r.upload_texture_3d(api.TEX_LOW_FREQ, noise["low"]); r.upload_texture_3d(api.TEX_HIGH_FREQ, noise["high"])
+        r.upload_texture_2d(api.TEX_CURL, noise["curl"])
+        r.set_camera(cam); r.set_time(tm); r.set_tuning(tun)
+        with pytest.raises(api.MeteorosError) as e:
+            r.dispatch_cloud()
+        assert e.value.status == 5 and "weather" in str(e.value)
+
+
 def test_cloud_row_tiles_are_bit_identical_to_one_launch(api, noise):
     """Multi-GPU sharding must not change arithmetic: N tile launches == one launch (run here on one device)."""
     w, h = 320, 200  # 200 rows: the last 32-row tile is partial

@@ -124,3 +124,23 @@ def test_static_camera_reprojects_onto_itself(oracle_mod):
     dx = np.abs(xs - np.arange(w)[None, :, None])
     assert dx.max() <= 2 and dy.max() <= 2
     assert (taps >= 0).all() and (taps < w * h).all()
+
+
+@pytest.mark.parametrize("scale", [1.0e-4, 3.7e-5])
+def test_cloud_core_weather_path_bit_identical(oracle_mod, noise, hostsim, scale):
+    """MtTuning.use_weather: cloudRayMarch.comp:515-525 (the commented-out weather block) restored, same bit-exact bar."""
+    w, h = 96, 54
+    cam, tm, _, tun = default_scene(w, h, frame_id=3, total_time=7.5, yaw=20.0, pitch=2.0)
+    tun["use_weather"], tun["weather_scale"] = 1, scale
+    ref = oracle_mod.cloud(cam, tm, tun, noise, w, h, full=True, counters=True, debug=True)
+    hdr, mask, cnt, dbg = hostsim.cloud(cam, tm, tun, noise, w, h, True, oracle_mod.RAY_DEBUG_DTYPE)
+    assert cnt == ref["counters"]
+    for f in oracle_mod.RAY_DEBUG_DTYPE.names:
+        assert np.array_equal(dbg[f], ref["debug"][f]), f
+    assert np.array_equal(mask, ref["mask"])
+    assert np.allclose(hdr, ref["hdr"], rtol=2e-6, atol=0)
+    # the path is live: it changes which rays find cloud
+    tun["use_weather"] = 0
+    base = oracle_mod.cloud(cam, tm, tun, noise, w, h, full=True, debug=True)
+    assert not np.array_equal(base["debug"]["accum"], ref["debug"]["accum"])
+    assert (ref["debug"]["accum"] > 0).mean() > 0.02

@@ -313,3 +313,25 @@ def test_golden_sequence_regression(oracle_mod, noise):
         assert np.abs(ldr.astype(int) - g["ldr"][k].astype(int)).max() <= 1
         cur ^= 1
         cam_old = c
+
+
+def test_density_height_gradient_known_answers(oracle_mod):
+    """getDensityHeightGradientForPoint (cloudRayMarch.comp:475-487), used only by the opt-in weather path."""
+    def remap(v, a, b, c, d):
+        return c + (v - a) / (b - a) * (d - c)
+
+    def ref(h, ct):
+        h = min(max(h, 0.0), 1.0)
+        sc = max(0.0, remap(h, 0.0, 0.25, 0.0, 1.0) * remap(h, 0.3, 0.65, 1.0, 0.0))
+        st = max(0.0, remap(h, 0.0, 0.1, 0.0, 1.0) * remap(h, 0.2, 0.3, 1.0, 0.0))
+        a = st + (sc - st) * min(max(ct * 2.0, 0.0), 1.0)
+        b = sc + (st - sc) * min(max((ct - 0.5) * 2.0, 0.0), 1.0)
+        return a + (b - a) * ct
+
+    g = oracle_mod.density_height_gradient
+    assert g(0.0, 0.0) == 0.0 and g(0.0, 1.0) == 0.0            # nothing at the shell's floor
+    assert g(0.9, 0.3) == 0.0 and g(2.0, 0.5) == 0.0            # above every profile / clamped height
+    assert g(0.1, 0.0) == pytest.approx(2.0, abs=1e-6)          # remap() is unclamped: the falling ramp reads 2 at h = 0.1
+    rng = np.random.default_rng(5)
+    for h, ct in rng.random((200, 2)):
+        assert g(h, ct) == pytest.approx(ref(h, ct), abs=2e-6)
