@@ -186,6 +186,21 @@ class Camera:
     def rotate_about_right(self, deg):
         self._rotate_about(deg, self.right)
 
+    def _translate(self, axis, amt):  # camera.cpp:98-118
+        t = (axis * f32(amt)).astype(f32)
+        self.eye = (self.eye + t).astype(f32)
+        self.ref = (self.ref + t).astype(f32)
+        self.recompute_attributes()
+
+    def translate_along_look(self, amt):
+        self._translate(self.forward, amt)
+
+    def translate_along_right(self, amt):
+        self._translate(self.right, amt)
+
+    def translate_along_up(self, amt):
+        self._translate(self.up, amt)
+
     def ubo(self) -> np.ndarray:  # Camera::UpdateBuffer, camera.cpp:31-42
         u = np.zeros((), CAMERA_DTYPE)
         view = look_at_rh(self.eye, self.ref, self.up)

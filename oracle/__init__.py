@@ -1,7 +1,8 @@
 """CPU parity oracle for meteoros_b200 -- TEST INFRASTRUCTURE ONLY (see oracle/meteoros_oracle.c).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this package.
-PARITY UNPINNED: the reference ships no golden vectors for this path and cannot run here.
+Pinned to the reference's own shader text where /root/reference exists (oracle/refshaders.py,
+tests/test_reference_shaders.py); what a Vulkan driver would add on top stays unpinned.
 """
 from __future__ import annotations
 

@@ -5,10 +5,13 @@
  * by __graft_entry__.smoke() and by bench.py's cpu_baseline / --impl reference legs, and by nothing else:
  * the product library (libmeteoros_b200.so) never links, loads or calls it.
  *
- * PARITY UNPINNED: the reference ships no golden vectors or tests for this path
- * and cannot be run in the build container or on the GPU box (no Vulkan loader/ICD, no glslang, no
- * SPIR-V; section 8c).  The oracle therefore follows the GLSL text op for op, and the only external pins
- * are the input fingerprints and hand-derived known answers in tests/.
+ * PINNING: the reference ships no golden vectors or tests for this path and its
+ * Vulkan application cannot run in the build container or on the GPU box (no loader/ICD, no glslang, no
+ * SPIR-V).  The oracle follows the GLSL text op for op, and is pinned to that text directly: where
+ * /root/reference exists, `make -C oracle refshaders` compiles the five shaders from their own source
+ * (glsl2cpp.py, glm) and tests/test_reference_shaders.py requires this file to reproduce every byte they
+ * store; the .npz fixtures under tests/golden carry reference-shader output to machines without the reference.  Unpinned:
+ * what a Vulkan driver would add (built-in precision, FMA contraction, sampler fixed point) -- DESIGN.md 2.
  *
  * What it restates (paths relative to /root/reference/src/CloudScapes/shaders):
  *   cloudRayMarch.comp:106-132,153-273,295-306,331-388,401-467,489-563,565-688,690-779,824-825  -> mto_cloud
@@ -25,6 +28,7 @@
  *   normalize(v)  = v * (1.0f / sqrt(dot(v,v)))             mix(x,y,a) = x*(1-a) + y*a
  *   clamp(x,l,h)  = min(max(x,l),h)                         fract(x)  = x - floor(x)
  *   round(x)      = round-half-to-even                      int(x)/uint(x) = truncate, saturating, NaN -> 0
+ *   mat4 * vec4   = ((m0*x + m1*y) + m2*z) + m3*w           a local never written reads 0
  *   texture()     = Vulkan linear filter, fp32 weights, see tex3d_linear / tex2d_linear below
  *   exp/pow/acos/cos = libm single precision (these never feed a discrete decision)
  */
@@ -702,14 +706,13 @@ static inline void mask_texel(const float* mask, int W, int H, int x, int y, flo
     const float* p = mask + 4 * ((size_t)y * W + x);
     out[0] = p[0]; out[1] = p[1]; out[2] = p[2]; out[3] = p[3];
 }
-static float mask_decode_bilinear(const float* mask, int W, int H, float s, float t)
+static void mask_bilinear(const float* mask, int W, int H, float s, float t, float acc[4])
 {
     float u = s * (float)W - 0.5f, v = t * (float)H - 0.5f;
     float fu = floorf(u), fv = floorf(v);
     float ax = u - fu, ay = v - fv;
     int x0 = f2i(fu), y0 = f2i(fv);
     float wx[2] = { 1.0f - ax, ax }, wy[2] = { 1.0f - ay, ay };
-    float acc[4] = { 0, 0, 0, 0 };
     int first = 1;
     for (int j = 0; j < 2; ++j)
         for (int i = 0; i < 2; ++i) {
@@ -722,6 +725,11 @@ static float mask_decode_bilinear(const float* mask, int W, int H, float s, floa
             }
             first = 0;
         }
+}
+static float mask_decode_bilinear(const float* mask, int W, int H, float s, float t)
+{
+    float acc[4];
+    mask_bilinear(mask, W, H, s, t, acc);
     /* dot(x, 1/bitEnc) */
     const float d0 = 1.0f / 1.0f, d1 = 1.0f / 255.0f, d2 = 1.0f / 65025.0f, d3 = 1.0f / 16581375.0f;
     return ((acc[0] * d0 + acc[1] * d1) + acc[2] * d2) + acc[3] * d3;
@@ -959,6 +967,11 @@ void mto_ray_sphere(const float ro[3], const float rd[3], const float c[3], floa
     *t = is.t;
     *valid = is.valid;
 }
+/* the fixed-function pieces of the post passes, for oracle/glsl_rt.h (the reference's shaders compiled as C++) */
+void mto_sample2d_f32_border(const float* img, int W, int H, float s, float t, float out[4]) { mask_bilinear(img, W, H, s, t, out); }
+void mto_sample2d_unorm8_border(const uint8_t* img, int W, int H, float s, float t, float out[4]) { ldr_sample_border(img, W, H, s, t, out); }
+void mto_load_unorm8(const uint8_t* img, int W, int H, int x, int y, float out[4]) { ldr_load(img, W, H, x, y, out); }
+uint8_t mto_to_unorm8(float v) { return to_unorm8(v); }
 float mto_density_height_gradient(float relativeHeight, float cloudType) { return density_height_gradient(relativeHeight, cloudType); }
 void mto_cloud_grid(int W, int H, int* threads_x, int* threads_y) { cloud_grid(W, H, threads_x, threads_y); }
 void mto_atmosphere_color(const float dir[3], const float sun_minus_origin[3], float sunIntensity, const float skySun[3], float out[3])

@@ -48,6 +48,10 @@ uint32_t mto_wang_hash(uint32_t u, uint32_t v, uint32_t s);
 void mto_encode_float_rgba(float v, float out[4]);
 void mto_ray_sphere(const float ro[3], const float rd[3], const float c[3], float radius, float point[3], float* t, int* valid);
 void mto_cloud_grid(int W, int H, int* threads_x, int* threads_y);
+void mto_sample2d_f32_border(const float* img, int W, int H, float s, float t, float out[4]);      /* LINEAR, CLAMP_TO_BORDER (0,0,0,1) */
+void mto_sample2d_unorm8_border(const uint8_t* img, int W, int H, float s, float t, float out[4]); /* same, RGBA8 UNORM image  */
+void mto_load_unorm8(const uint8_t* img, int W, int H, int x, int y, float out[4]);               /* imageLoad on an rgba8 image */
+uint8_t mto_to_unorm8(float v);                                                                    /* imageStore conversion      */
 float mto_density_height_gradient(float relativeHeight, float cloudType);
 void mto_atmosphere_color(const float dir[3], const float sun_minus_origin[3], float sunIntensity, const float skySun[3], float out[3]);
 

@@ -428,6 +428,38 @@ def test_txaa_pass_and_reference_live_frame(api, oracle_mod, noise):
             cam_old = c
 
 
+def test_reference_shader_golden_live_sequence(api, noise):
+    """The CUDA frame (mtFrameEx: REPROJ, CLOUD, GODRAYS, TONEMAP, TXAA, swap) against tests/golden/live_sequence_96x54.npz
+    -- sixteen frames written by the REFERENCE'S OWN five shaders (compiled from their text where /root/reference
+    exists; tests/golden/make_goldens.py).  No oracle involved: this is kernel vs reference shader output."""
+    from pathlib import Path
+
+    from meteoros_b200 import scene
+
+    g = np.load(Path(__file__).parent / "golden" / "live_sequence_96x54.npz")
+    assert "reference shaders" in str(g["source"])
+    w, h = 96, 54
+    cam, sc, sky = scene.Camera(w, h), scene.Scene(), scene.Sky()
+    cam_old = cam.ubo()
+    with make_renderer(api, noise, w, h) as r:
+        r.set_sun_and_sky(sky.ubo())
+        for k in range(16):
+            cam.rotate_about_up(0.25)
+            sc.update_time(1 / 60)
+            c, t = cam.ubo(), sc.ubo()
+            r.set_camera(c); r.set_camera_old(cam_old); r.set_time(t)
+            r.frame(with_godrays=True, with_txaa=True)
+            hdr = r.read_image(api.IMAGE_CLOUD_PREV)            # roles swapped at the end of the frame
+            aa = r.read_image(api.IMAGE_LDR_PREV)
+            d = np.abs(aa.astype(np.int32) - g["txaa"][k].astype(np.int32))
+            assert d.max() <= 2 and (d > 0).mean() < 0.02        # SFU exp / pow can move an 8-bit value by one LSB
+            if k == 0:
+                check_hdr(hdr, g["hdr_first"])
+            cam_old = c
+        check_hdr(hdr, g["hdr_last"])
+        assert np.abs(r.read_image(api.IMAGE_GODRAY_MASK) - g["mask_last"]).max() <= MASK_TOL
+
+
 def test_cxx_frame_driver_matches_python_driven_frames(api, noise):
     """mtxRunFrame (the reference main loop in C++) against the same frames driven from Python."""
     import ctypes as C
@@ -579,7 +611,7 @@ def test_full_size_properties_4k(api, noise):
     assert np.array_equal(am[rows[0]:rows[1]], ref["mask"][rows[0]:rows[1]])
 
 
-def test_committed_golden_frame(api, noise):
+def test_committed_golden_frame(api, noise):  # the golden was written by the reference's own cloud shader (make_goldens.py)
     """The CUDA path against the committed golden (tests/golden/cloud_64x36.npz, oracle-generated)."""
     import pathlib
 

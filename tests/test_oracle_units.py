@@ -280,8 +280,9 @@ def test_default_frame_statistics(oracle_mod, noise):
 
 
 def test_golden_frame_regression(oracle_mod, noise):
-    """tests/golden/cloud_64x36.npz was written by tests/golden/make_goldens.py from this oracle; it pins the
-    oracle against accidental edits (it is NOT an external reference vector)."""
+    """tests/golden/cloud_64x36.npz was minted by tests/golden/make_goldens.py from the REFERENCE'S OWN cloud shader
+    (compiled from its text, oracle/refshaders.py) where /root/reference exists; here, on any machine, the oracle must
+    reproduce it (the per-ray records in the file are the oracle's own)."""
     g = np.load(ROOT / "tests" / "golden" / "cloud_64x36.npz")
     w, h = 64, 36
     cam, tm, _, tun = default_scene(w, h, frame_id=int(g["frame_id"]), total_time=float(g["total_time"]), yaw=float(g["yaw"]))
@@ -292,7 +293,7 @@ def test_golden_frame_regression(oracle_mod, noise):
 
 
 def test_golden_sequence_regression(oracle_mod, noise):
-    """Four frames of the full loop (main.cpp:172-194 order) against tests/golden/sequence_96x54.npz."""
+    """Four frames of the full loop (main.cpp:172-194 order) against tests/golden/sequence_96x54.npz (reference shaders)."""
     g = np.load(ROOT / "tests" / "golden" / "sequence_96x54.npz")
     w, h = 96, 54
     cam, sc, sky = scene.Camera(w, h), scene.Scene(), scene.Sky()
@@ -313,6 +314,38 @@ def test_golden_sequence_regression(oracle_mod, noise):
         assert np.abs(ldr.astype(int) - g["ldr"][k].astype(int)).max() <= 1
         cur ^= 1
         cam_old = c
+
+
+def test_golden_live_sequence_all_five_shaders(oracle_mod, noise):
+    """Sixteen frames of REPROJ, CLOUD, GODRAYS, TONEMAP, TXAA chained, against tests/golden/live_sequence_96x54.npz,
+    which the reference's five shaders wrote (tests/golden/make_goldens.py).  Every pixel id 1..15, 0 is exercised."""
+    g = np.load(ROOT / "tests" / "golden" / "live_sequence_96x54.npz")
+    assert "reference shaders" in str(g["source"])
+    w, h = 96, 54
+    cam, sc, sky = scene.Camera(w, h), scene.Scene(), scene.Sky()
+    tun = scene.default_tuning()
+    img = [np.zeros((h, w, 4), np.float32), np.zeros((h, w, 4), np.float32)]
+    mask = np.zeros((h, w, 4), np.float32)
+    hist = np.zeros((h, w, 4), np.uint8)
+    cur, cam_old = 0, cam.ubo()
+    for k in range(16):
+        cam.rotate_about_up(0.25)
+        sc.update_time(1 / 60)
+        c, t = cam.ubo(), sc.ubo()
+        img[cur] = oracle_mod.reproject(c, cam_old, t, img[cur ^ 1])
+        oracle_mod.cloud(c, t, tun, noise, w, h, full=False, hdr=img[cur], mask=mask)
+        img[cur] = oracle_mod.godrays(c, sky.ubo(), mask, img[cur])
+        ldr = oracle_mod.tonemap(t, img[cur])
+        hist = oracle_mod.txaa(c, cam_old, t, ldr, hist)
+        if k == 0:
+            assert np.allclose(img[cur], g["hdr_first"], rtol=1e-5, atol=1e-7)
+        # libm exp / pow may differ in the last ulp across hosts: one LSB of slack on the 8-bit images
+        assert np.abs(ldr.astype(int) - g["ldr"][k].astype(int)).max() <= 1
+        assert np.abs(hist.astype(int) - g["txaa"][k].astype(int)).max() <= 1
+        cur ^= 1
+        cam_old = c
+    assert np.allclose(img[cur ^ 1], g["hdr_last"], rtol=1e-5, atol=1e-7)
+    assert np.abs(mask - g["mask_last"]).max() <= 1.0 / 255.0
 
 
 def test_density_height_gradient_known_answers(oracle_mod):

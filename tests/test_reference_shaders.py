@@ -1,0 +1,134 @@
+"""The oracle against the REFERENCE'S OWN SHADER TEXT, executed on the CPU.
+
+oracle/refshaders.py compiles cloudRayMarch.comp, reprojection.comp and the three post-process fragment shaders from
+the files under /root/reference (a token-level GLSL -> C++ rewrite, g++, the reference's vendored glm) and dispatches
+them as Renderer.cpp does.  Only the fixed-function sampler and the precision of GLSL built-ins are not the
+reference's -- Vulkan leaves both to the device.  With the built-ins fixed as DESIGN.md section 2 fixes them
+("canonical") the oracle must reproduce every byte the shaders store; with glm's own built-ins it must agree to
+rounding.  These tests need the reference tree; the fixtures they pin (tests/golden/*.npz, minted by
+tests/golden/make_goldens.py from these shaders) carry the result to machines without it."""
+import numpy as np
+import pytest
+
+from conftest import default_scene, rel_err
+from oracle import refshaders
+
+pytestmark = pytest.mark.skipif(not refshaders.available(), reason="reference tree not present (GPU box)")
+
+CAMERAS = [  # w, h, frame id, yaw, pitch, total time
+    (96, 54, 1, 0.0, 0.0, 0.016),
+    (130, 70, 7, 12.0, 3.0, 41.5),       # Renderer.cpp:713 grid quirk: columns 128, 129 never marched
+    (200, 112, 14, -30.0, 8.0, 3.25),
+    (64, 36, 0, 0.0, -4.0, 0.0),
+    (160, 90, 9, 75.0, 20.0, 1234.5),
+    (48, 160, 4, 180.0, -10.0, 7.0),     # portrait, looking away from the sun
+]
+
+
+@pytest.mark.parametrize("w,h,fid,yaw,pitch,t", CAMERAS)
+def test_cloud_shader_bit_identical(oracle_mod, noise, w, h, fid, yaw, pitch, t):
+    cam, tm, sky, tun = default_scene(w, h, frame_id=fid, total_time=t, yaw=yaw, pitch=pitch)
+    sentinel = np.full((h, w, 4), -7.0, np.float32)
+    want = refshaders.cloud(cam, tm, sky, noise, w, h, hdr=sentinel.copy(), mask=sentinel.copy())
+    got = oracle_mod.cloud(cam, tm, tun, noise, w, h, full=False, hdr=sentinel.copy(), mask=sentinel.copy())
+    assert np.array_equal(got["hdr"], want["hdr"])       # includes which pixels were written at all
+    assert np.array_equal(got["mask"], want["mask"])
+    assert (want["hdr"][..., 3] != -7.0).sum() > 0
+
+
+def test_cloud_shader_all_sixteen_ids_bit_identical(oracle_mod, noise):
+    w, h = 128, 72
+    cam, tm, sky, tun = default_scene(w, h, frame_id=0, total_time=5.0, yaw=3.0, pitch=1.0)
+    want = refshaders.cloud_full(cam, tm, sky, noise, w, h)
+    got = oracle_mod.cloud(cam, tm, tun, noise, w, h, full=True, counters=True)
+    assert np.array_equal(got["hdr"], want["hdr"]) and np.array_equal(got["mask"], want["mask"])
+    c = got["counters"]
+    assert c["rays_marched"] > 0.3 * w * h and c["steps_incloud"] > 0 and c["cone_hits"] > 0  # every branch of the shader ran
+
+
+@pytest.mark.parametrize("eye_y", [-7400.0, -9000.0, -25000.0])
+def test_cloud_shader_degenerate_cameras(oracle_mod, noise, eye_y):
+    """Eye near, at and above the inner shell (the shader's ray origin is -eye): NaN / empty-interval paths."""
+    from meteoros_b200 import scene
+
+    w, h = 64, 36
+    cam = scene.Camera(w, h, eye=(0.0, eye_y, 2.0), ref=(0.0, eye_y, 1.0))
+    _, tm, sky, tun = default_scene(w, h, frame_id=2, total_time=1.0)
+    want = refshaders.cloud_full(cam.ubo(), tm, sky, noise, w, h)
+    got = oracle_mod.cloud(cam.ubo(), tm, tun, noise, w, h, full=True)
+    assert np.array_equal(got["hdr"], want["hdr"], equal_nan=True) and np.array_equal(got["mask"], want["mask"], equal_nan=True)
+
+
+@pytest.mark.parametrize("yaw_step,pitch_step", [(0.25, 0.0), (-2.0, 0.5), (0.0, 0.0), (15.0, -3.0)])
+def test_reprojection_shader_bit_identical(oracle_mod, yaw_step, pitch_step):
+    w, h = 150, 85                                   # not a multiple of the 32 x 32 work group
+    rng = np.random.default_rng(11)
+    prev = rng.random((h, w, 4), dtype=np.float32)
+    old, tm, _, _ = default_scene(w, h, frame_id=6, total_time=2.0, yaw=10.0, pitch=2.0)
+    cam, _, _, _ = default_scene(w, h, frame_id=6, total_time=2.0, yaw=10.0 + yaw_step, pitch=2.0 + pitch_step)
+    assert np.array_equal(oracle_mod.reproject(cam, old, tm, prev), refshaders.reproject(cam, old, tm, prev))
+
+
+def test_post_shaders_bit_identical(oracle_mod, noise):
+    w, h = 160, 90
+    rng = np.random.default_rng(3)
+    old, tm, sky, tun = default_scene(w, h, frame_id=5, total_time=2.0, yaw=10.0, pitch=2.0)
+    cam, _, _, _ = default_scene(w, h, frame_id=5, total_time=2.0, yaw=10.25, pitch=2.0)
+    frame = oracle_mod.cloud(cam, tm, tun, noise, w, h, full=True)
+    lit = refshaders.godrays(cam, sky, frame["mask"], frame["hdr"])
+    assert np.array_equal(oracle_mod.godrays(cam, sky, frame["mask"], frame["hdr"]), lit)
+    assert (lit != frame["hdr"]).any(axis=-1).mean() > 0.9           # the pass did something everywhere
+    ldr, ldr_f = refshaders.tonemap(tm, lit, want_f32=True)
+    o_ldr, o_f = oracle_mod.tonemap(tm, lit, want_f32=True)
+    assert np.array_equal(o_ldr, ldr) and np.array_equal(o_f, ldr_f)
+    for prev in (rng.integers(0, 256, (h, w, 4), dtype=np.uint8), np.roll(ldr, 2, axis=1), np.full((h, w, 4), 128, np.uint8)):
+        aa, aa_f = refshaders.txaa(cam, old, tm, ldr, prev, want_f32=True)
+        o_aa, o_aa_f = oracle_mod.txaa(cam, old, tm, ldr, prev, want_f32=True)
+        assert np.array_equal(o_aa, aa) and np.array_equal(o_aa_f, aa_f)
+    # sun behind the camera: every fragment of the god-ray shader returns without writing
+    back, _, _, _ = default_scene(w, h, yaw=0.0, pitch=-89.0)
+    assert np.array_equal(refshaders.godrays(back, sky, frame["mask"], frame["hdr"]), oracle_mod.godrays(back, sky, frame["mask"], frame["hdr"]))
+
+
+def test_committed_fixtures_are_what_the_reference_shaders_produce(noise):
+    """tests/golden/{cloud_64x36, sequence_96x54, live_sequence_96x54}.npz regenerate bit for bit from the shaders."""
+    import sys
+    from pathlib import Path
+
+    gold = Path(__file__).parent / "golden"
+    sys.path.insert(0, str(gold))
+    import make_goldens
+
+    g = np.load(gold / "cloud_64x36.npz")
+    cam, tm, sky, _ = default_scene(64, 36, frame_id=int(g["frame_id"]), total_time=float(g["total_time"]), yaw=float(g["yaw"]))
+    ref = refshaders.cloud_full(cam, tm, sky, noise, 64, 36)
+    assert np.array_equal(ref["hdr"], g["hdr"]) and np.array_equal(ref["mask"], g["mask"])
+    s = make_goldens.frame_loop(16, 96, 54, noise, with_txaa=True)       # raises SystemExit if the oracle ever disagrees
+    live = np.load(gold / "live_sequence_96x54.npz")
+    assert np.array_equal(np.stack(s["txaa"]), live["txaa"]) and np.array_equal(np.stack(s["ldr"]), live["ldr"])
+    assert np.array_equal(s["hdr"][-1], live["hdr_last"]) and np.array_equal(s["mask"], live["mask_last"])
+    seq = np.load(gold / "sequence_96x54.npz")
+    assert np.array_equal(np.stack(s["hdr"][:4]), seq["hdr"]) and np.array_equal(np.stack(s["ldr"][:4]), seq["ldr"])
+
+
+def test_glm_builtins_variant_agrees_to_rounding(oracle_mod, noise):
+    """Same shader text, glm's own mix / round / dot / mat*vec instead of the canonical ones: an independent reading of
+    the GLSL built-ins moves radiance by ulps (one pixel in a thousand by more), never the structure of the image."""
+    w, h = 128, 72
+    cam, tm, sky, tun = default_scene(w, h, frame_id=0, total_time=5.0, yaw=3.0, pitch=1.0)
+    want = refshaders.cloud_full(cam, tm, sky, noise, w, h, variant="glm")
+    got = oracle_mod.cloud(cam, tm, tun, noise, w, h, full=True, debug=True)
+    e = rel_err(got["hdr"][..., :3], want["hdr"][..., :3])
+    assert np.quantile(e, 0.999) < 2e-6 and e.max() < 1e-3       # worst pixel (a sample flipping in / out of cloud) is still
+                                                                 # inside the north-star HDR tolerance
+    dec = np.array([1.0, 1 / 255.0, 1 / 65025.0, 1 / 16581375.0])
+    assert np.abs(got["mask"].astype(np.float64) @ dec - want["mask"].astype(np.float64) @ dec).max() < 1e-5   # decoded mask value
+    rng = np.random.default_rng(5)
+    prev = rng.random((h, w, 4), dtype=np.float32)
+    old, _, _, _ = default_scene(w, h, yaw=2.75, pitch=1.0)
+    a, b = oracle_mod.reproject(cam, old, tm, prev), refshaders.reproject(cam, old, tm, prev, variant="glm")
+    assert (a != b).any(axis=-1).mean() < 0.01       # a tap index may flip where round() meets an exact tie
+    lit_a, lit_b = oracle_mod.godrays(cam, sky, got["mask"], got["hdr"]), refshaders.godrays(cam, sky, got["mask"], got["hdr"], variant="glm")
+    assert np.allclose(lit_a, lit_b, rtol=2e-6, atol=1e-7)
+    ldr_a, ldr_b = oracle_mod.tonemap(tm, lit_a), refshaders.tonemap(tm, lit_a, variant="glm")
+    assert np.abs(ldr_a.astype(int) - ldr_b.astype(int)).max() <= 1
