@@ -12,7 +12,8 @@ reprojection) over one synthetic 3840x2160 frame of the default cloudscape = 8 2
   N > 1  weak scaling, no data-path collective: every rank renders its own copy of the 4K frame (independent views,
          BASELINE config 5 style; --sweep varies sun elevation / coverage per rank); value = N * rays / max-over-ranks time.  `--workload frame8k` instead shards
          ONE 7680x4320 frame by cyclic 32-row tiles with stores straight into GPU 0's image over NVLink (config 4).
-  --impl reference   the CPU restatement of the reference shaders (oracle/, OpenMP over all host cores) on a bounded,
+  --impl reference   the reference's Cloud shader compiled for the CPU from its own text (oracle/_ref; else the oracle
+                     restatement), OpenMP over all host cores, on a bounded,
          evenly spread sample of the same frame: the reference's own path needs Vulkan + a window.
 Rank 0 prints ONE JSON line.
 """
@@ -123,42 +124,51 @@ def scene_for_view(view: int, w: int, h: int, sweep: bool = False):
 
 
 def cpu_reference_sample(noise, w, h, target_s=12.0, probe_stride=64):
-    """Times the CPU oracle on every `stride`-th 4-row group of the frame (evenly spread, so ocean / sky / cloud rows
-    are sampled in proportion).  Returns (Mrays/s, cores, description, seconds)."""
+    """Times the reference's Cloud pass on the host cores, on every `stride`-th 4-row group of the frame (evenly spread,
+    so ocean / sky / cloud rows are sampled in proportion).  kind "reference": the reference's OWN shader, compiled from
+    its text into oracle/_ref (built where /root/reference exists; the library travels to the GPU box); kind "port": the
+    oracle restatement, when that library is absent.  Returns (Mrays/s, cores, description, seconds, kind)."""
     import oracle
+    from oracle import refshaders
 
-    cam, tm, _, tun = scene_for_view(0, w, h)
+    cam, tm, sky, tun = scene_for_view(0, w, h)
     hdr = np.zeros((h, w, 4), np.float32)
     mask = np.zeros((h, w, 4), np.float32)
     cores = os.cpu_count() or 1
     groups = (h + 3) // 4
+    kind = "reference" if (refshaders.available() or refshaders.built()) else "port"
 
     def run(stride):
         t0 = time.perf_counter()
-        r = oracle.cloud(cam, tm, tun, noise, w, h, full=True, hdr=hdr, mask=mask, counters=True, group_stride=stride)
-        return time.perf_counter() - t0, r["counters"]["rays"]
+        if kind == "reference":   # 16 dispatches of cloudRayMarch.comp, as Renderer.cpp:701-716 issues each of them
+            refshaders.cloud_full(cam, tm, sky, noise, w, h, hdr=hdr, mask=mask, group_stride=stride)
+            rays = len(range(0, groups, stride)) * 4 * w
+        else:
+            rays = oracle.cloud(cam, tm, tun, noise, w, h, full=True, hdr=hdr, mask=mask, counters=True, group_stride=stride)["counters"]["rays"]
+        return time.perf_counter() - t0, rays
 
     run(max(probe_stride * 4, 1))  # warm the library / page in the volumes
     dt, rays = run(probe_stride)
     est_full = dt * probe_stride
     stride = int(min(max(round(est_full / target_s), 1), groups // 8))
     dt, rays = run(stride)
-    desc = f"every {stride}th 4-row group of the {w}x{h} full-quality frame ({rays} rays), OpenMP x{cores}"
-    return rays / dt / 1e6, cores, desc, dt
+    what = "reference cloudRayMarch.comp compiled from its own text (oracle/_ref, g++ + glm)" if kind == "reference" else "oracle port"
+    desc = f"every {stride}th 4-row group of the {w}x{h} full-quality frame ({rays} rays), {what}, OpenMP x{cores}"
+    return rays / dt / 1e6, cores, desc, dt, kind
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the CPU restatement on the host cores; rank 0 only."""
+    """--impl reference: the reference's Cloud shader on the host cores (oracle/_ref, else the oracle port); rank 0 only."""
     if rank != 0:
         return
     from meteoros_b200 import textures
 
     noise = textures.load_noise()
     w, h = (W4K, H4K)
-    vals, secs, desc, cores = [], [], "", 1
+    vals, secs, desc, cores, kind = [], [], "", 1, "port"
     budget = 150.0 / max(args.steps + args.warmup, 1)
     for i in range(args.warmup + args.steps):
-        v, cores, desc, dt = cpu_reference_sample(noise, w, h, target_s=min(12.0, budget))
+        v, cores, desc, dt, kind = cpu_reference_sample(noise, w, h, target_s=min(12.0, budget))
         if i >= args.warmup:
             vals.append(v)
             secs.append(dt)
@@ -168,10 +178,11 @@ def run_reference(args, rank, world):
         "warmup": args.warmup, "ms_per_step": round(1e3 * statistics.mean(secs), 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "3840x2160 full-quality Cloud pass, default cloudscape (BASELINE config 3)", "sample": desc},
-        "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": cores, "kind": kind, "sample": desc},
         "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "reference shaders need Vulkan + a window and ship no SPIR-V (SURVEY.md 8c): timed arm is the CPU oracle port",
+        "note": "the reference application needs Vulkan + a window and ships no SPIR-V (SURVEY.md 8c); the timed arm is its Cloud "
+                "shader compiled for the CPU from its own text (kind reference) or, without oracle/_ref, the oracle port (kind port)",
     }
     print(json.dumps(line), flush=True)
 
@@ -411,8 +422,8 @@ def main():
     r.close()
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "cloud4k":
-        v, cores, desc, _ = cpu_reference_sample(noise, W4K, H4K, target_s=12.0)
-        line["cpu_baseline"] = {"value": round(v, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
+        v, cores, desc, _, kind = cpu_reference_sample(noise, W4K, H4K, target_s=12.0)
+        line["cpu_baseline"] = {"value": round(v, 4), "unit": UNIT, "cores": cores, "kind": kind, "sample": desc}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -10,7 +10,7 @@ namespace {
 
 extern "C" int mtrefsh_cloud(const void* camera152, const void* time76, const void* sky52, const uint8_t* low, int lw, int lh, int ld,
                              const uint8_t* high, int hw, int hh, int hd, const uint8_t* curl, int cw, int ch, const uint8_t* weather,
-                             int ww, int wh, int W, int H, float* prev, float* hdr, float* mask)
+                             int ww, int wh, int W, int H, float* prev, float* hdr, float* mask, int group_stride)
 {
     static_assert(sizeof(camera) == 152 && sizeof(sunAndSky) == 52, "uniform block layouts");
     memcpy(&camera, camera152, 152);
@@ -28,8 +28,10 @@ extern "C" int mtrefsh_cloud(const void* camera152, const void* time76, const vo
     // Renderer.cpp:711-716: numBlocks = (std::ceil(window / 4) + 32 - 1) / 32 with an integer division inside ceil,
     // converted to uint32_t; 32 x 32 invocations per group (cloudRayMarch.comp:4-5)
     const uint32_t bx = (uint32_t)((std::ceil(W / 4) + 32 - 1) / 32), by = (uint32_t)((std::ceil(H / 4) + 32 - 1) / 32);
+    // group_stride > 1 (bench.py's bounded CPU sample): only every group_stride-th row of invocations (= 4 pixel rows)
+    const int64_t stride = group_stride > 1 ? group_stride : 1;
 #pragma omp parallel for schedule(dynamic, 1)
-    for (int64_t gy = 0; gy < (int64_t)by * 32; ++gy)
+    for (int64_t gy = 0; gy < (int64_t)by * 32; gy += stride)
         for (uint32_t gx = 0; gx < bx * 32; ++gx) {
             gl_GlobalInvocationID = uvec3(gx, (uint32_t)gy, 0u);
             shader_main();

@@ -22,17 +22,31 @@ REFERENCE = Path("/root/reference/src/CloudScapes/shaders/cloudRayMarch.comp")
 _LIBS: dict = {}
 
 
+def _path(variant: str) -> Path:
+    return HERE / "_ref" / ("libmeteoros_refshaders.so" if variant == "canonical" else "libmeteoros_refshaders_glm.so")
+
+
 def available() -> bool:
+    """The reference tree is here: the libraries can be (re)built from the shader sources."""
     return REFERENCE.exists()
+
+
+def built(variant: str = "canonical") -> bool:
+    """A prebuilt library travelled here (the GPU box has oracle/_ref/ but no /root/reference)."""
+    return _path(variant).exists()
 
 
 def lib(variant: str = "canonical") -> C.CDLL:
     if variant not in _LIBS:
-        if not available():
-            raise RuntimeError("the reference tree is not present on this machine")
-        subprocess.run(["make", "-s", "-C", str(HERE), "refshaders"], check=True, capture_output=True)
-        name = "libmeteoros_refshaders.so" if variant == "canonical" else "libmeteoros_refshaders_glm.so"
-        _LIBS[variant] = C.CDLL(str(HERE / "_ref" / name))
+        if available():
+            subprocess.run(["make", "-s", "-C", str(HERE), "refshaders"], check=True, capture_output=True)
+        elif not built(variant):
+            raise RuntimeError("neither the reference tree nor a prebuilt oracle/_ref library is present on this machine")
+        else:
+            from . import lib as oracle_lib
+
+            oracle_lib()   # the shader library links the oracle's sampler: make sure libmeteoros_oracle.so exists here
+        _LIBS[variant] = C.CDLL(str(_path(variant)))
     return _LIBS[variant]
 
 
@@ -44,8 +58,9 @@ def _c(a, dtype=None):
     return np.ascontiguousarray(a, dtype=dtype)
 
 
-def cloud(cam, tm, sky, noise, W, H, hdr=None, mask=None, variant="canonical"):
-    """One dispatch of cloudRayMarch.comp (1 of 16 pixels, id = tm.frameCountMod16).  hdr / mask are modified in place."""
+def cloud(cam, tm, sky, noise, W, H, hdr=None, mask=None, variant="canonical", group_stride=1):
+    """One dispatch of cloudRayMarch.comp (1 of 16 pixels, id = tm.frameCountMod16).  hdr / mask are modified in place.
+    group_stride > 1 runs only every group_stride-th row of invocations (bench.py's bounded CPU sample)."""
     hdr = np.zeros((H, W, 4), np.float32) if hdr is None else hdr
     mask = np.zeros((H, W, 4), np.float32) if mask is None else mask
     prev = np.zeros((H, W, 4), np.float32)   # bound (set 0, binding 1), never read by the shader
@@ -53,18 +68,19 @@ def cloud(cam, tm, sky, noise, W, H, hdr=None, mask=None, variant="canonical"):
     lo, hi, cu, we = (_c(noise[k], np.uint8) for k in ("low", "high", "curl", "weather"))
     rc = lib(variant).mtrefsh_cloud(_p(cam), _p(tm), _p(sky), _p(lo), lo.shape[2], lo.shape[1], lo.shape[0], _p(hi), hi.shape[2],
                                     hi.shape[1], hi.shape[0], _p(cu), cu.shape[1], cu.shape[0], _p(we), we.shape[1], we.shape[0],
-                                    W, H, _p(prev), _p(hdr), _p(mask))
+                                    W, H, _p(prev), _p(hdr), _p(mask), int(group_stride))
     assert rc == 0
     return {"hdr": hdr, "mask": mask}
 
 
-def cloud_full(cam, tm, sky, noise, W, H, variant="canonical"):
+def cloud_full(cam, tm, sky, noise, W, H, variant="canonical", hdr=None, mask=None, group_stride=1):
     """All 16 pixel ids with the same camera / time: what mtDispatchCloudFull computes."""
-    hdr, mask = np.zeros((H, W, 4), np.float32), np.zeros((H, W, 4), np.float32)
+    hdr = np.zeros((H, W, 4), np.float32) if hdr is None else hdr
+    mask = np.zeros((H, W, 4), np.float32) if mask is None else mask
     t = _c(tm).copy()
     for fid in range(16):
         t["frameCountMod16"] = fid
-        cloud(cam, t, sky, noise, W, H, hdr=hdr, mask=mask, variant=variant)
+        cloud(cam, t, sky, noise, W, H, hdr=hdr, mask=mask, variant=variant, group_stride=group_stride)
     return {"hdr": hdr, "mask": mask}
 
 
