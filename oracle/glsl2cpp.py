@@ -17,7 +17,11 @@ The rewrite is token-level and changes no expression:
   * a declaration without an initialiser, `T a, b;`, becomes `T a{}, b{};`: GLSL leaves such a variable undefined (the
     shaders do read one -- raySphereIntersection returns isect.t unwritten when the ray misses); canonical value 0;
   * `void main()` becomes `void shader_main()`.
-Everything else -- every arithmetic expression, branch, loop and constant -- is compiled exactly as the reference wrote it."""
+Everything else -- every arithmetic expression, branch, loop and constant -- is compiled exactly as the reference wrote it.
+
+`--revive-weather` (cloudRayMarch.comp only) additionally un-comments the weather-map block the reference carries as
+dead code (:517-524), takes the coverage from `weather_data.r` as the trailing comment of :529 says, and scales the
+weather sample point by the global `mt_weather_scale` -- the semantics of MtTuning.use_weather."""
 import re
 import sys
 
@@ -34,8 +38,21 @@ def strip_comments(src: str) -> str:
     return re.sub(r"//[^\n]*", "", src)
 
 
-def rewrite(src: str) -> str:
-    src = src.lstrip("﻿")
+def revive_weather(src: str) -> str:
+    dead = r"^(\s*)//\s*(vec2 weatherSamplePoint|vec3 weather_data|float cloudType|float densityHeightGradient|baseCloud \*= densityHeightGradient)"
+    src, n = re.subn(dead, r"\1\2", src, flags=re.M)
+    assert n == 5, n
+    src, n = re.subn(r"float cloud_coverage = 0\.6;// weather_data\.r;", "float cloud_coverage = weather_data.r;", src)
+    assert n == 1, n
+    src, n = re.subn(r"= unskewedSamplePoint\.xz;", "= unskewedSamplePoint.xz * mt_weather_scale;", src)
+    assert n == 1, n
+    return src
+
+
+def rewrite(src: str, weather: bool = False) -> str:
+    src = src.lstrip("\ufeff")
+    if weather:
+        src = revive_weather(src)
     src = strip_comments(src)
     src = re.sub(r"^\s*#\s*(version|extension)[^\n]*", "", src, flags=re.M)
     src = re.sub(r"layout\s*\(\s*local_size[^)]*\)\s*in\s*;", "", src)
@@ -60,9 +77,10 @@ def rewrite(src: str) -> str:
 
 
 if __name__ == "__main__":
-    shader, out = sys.argv[1], sys.argv[2]
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    shader, out = args[0], args[1]
     with open(shader, encoding="utf-8-sig", errors="replace") as f:
-        text = rewrite(f.read())
+        text = rewrite(f.read(), weather="--revive-weather" in sys.argv)
     with open(out, "w") as f:
         f.write(f"// GENERATED by oracle/glsl2cpp.py from {shader} -- build artefact, git-ignored, do not commit.\n")
         f.write(text)

@@ -1,17 +1,34 @@
 // TEST INFRASTRUCTURE -- the reference's Cloud compute shader (cloudRayMarch.comp), compiled by g++ from its own text
 // (oracle/glsl2cpp.py, oracle/glsl_rt.h) and dispatched the way Renderer.cpp:701-716 dispatches it.
+//
+// -DMTREF_WEATHER builds the same file around the shader with its dead weather-map block revived
+// (glsl2cpp.py --revive-weather) and exports mtrefsh_cloud_weather: the pin for MtTuning.use_weather.
 #include "glsl_rt.h"
 
 namespace {
+#ifdef MTREF_WEATHER
+float mt_weather_scale = 1.0f;
+#include "_ref/gen/cloudRayMarch.weather.inc"
+#else
 #include "_ref/gen/cloudRayMarch.comp.inc"
+#endif
 }
 #undef E
 #undef PI
 
-extern "C" int mtrefsh_cloud(const void* camera152, const void* time76, const void* sky52, const uint8_t* low, int lw, int lh, int ld,
+#ifdef MTREF_WEATHER
+#define MTREF_CLOUD_ENTRY mtrefsh_cloud_weather
+#else
+#define MTREF_CLOUD_ENTRY mtrefsh_cloud
+#endif
+
+extern "C" int MTREF_CLOUD_ENTRY(const void* camera152, const void* time76, const void* sky52, const uint8_t* low, int lw, int lh, int ld,
                              const uint8_t* high, int hw, int hh, int hd, const uint8_t* curl, int cw, int ch, const uint8_t* weather,
-                             int ww, int wh, int W, int H, float* prev, float* hdr, float* mask, int group_stride)
+                             int ww, int wh, int W, int H, float* prev, float* hdr, float* mask, int group_stride, float weather_scale)
 {
+#ifdef MTREF_WEATHER
+    mt_weather_scale = weather_scale;
+#endif
     static_assert(sizeof(camera) == 152 && sizeof(sunAndSky) == 52, "uniform block layouts");
     memcpy(&camera, camera152, 152);
     const unsigned char* t = (const unsigned char*)time76;

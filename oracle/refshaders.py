@@ -58,29 +58,31 @@ def _c(a, dtype=None):
     return np.ascontiguousarray(a, dtype=dtype)
 
 
-def cloud(cam, tm, sky, noise, W, H, hdr=None, mask=None, variant="canonical", group_stride=1):
+def cloud(cam, tm, sky, noise, W, H, hdr=None, mask=None, variant="canonical", group_stride=1, weather_scale=None):
     """One dispatch of cloudRayMarch.comp (1 of 16 pixels, id = tm.frameCountMod16).  hdr / mask are modified in place.
-    group_stride > 1 runs only every group_stride-th row of invocations (bench.py's bounded CPU sample)."""
+    group_stride > 1 runs only every group_stride-th row of invocations (bench.py's bounded CPU sample).
+    weather_scale not None runs the shader with its dead weather-map block revived (canonical variant only)."""
     hdr = np.zeros((H, W, 4), np.float32) if hdr is None else hdr
     mask = np.zeros((H, W, 4), np.float32) if mask is None else mask
     prev = np.zeros((H, W, 4), np.float32)   # bound (set 0, binding 1), never read by the shader
     cam, tm, sky = _c(cam), _c(tm), _c(sky)
     lo, hi, cu, we = (_c(noise[k], np.uint8) for k in ("low", "high", "curl", "weather"))
-    rc = lib(variant).mtrefsh_cloud(_p(cam), _p(tm), _p(sky), _p(lo), lo.shape[2], lo.shape[1], lo.shape[0], _p(hi), hi.shape[2],
-                                    hi.shape[1], hi.shape[0], _p(cu), cu.shape[1], cu.shape[0], _p(we), we.shape[1], we.shape[0],
-                                    W, H, _p(prev), _p(hdr), _p(mask), int(group_stride))
+    entry = lib(variant).mtrefsh_cloud if weather_scale is None else lib("canonical").mtrefsh_cloud_weather
+    rc = entry(_p(cam), _p(tm), _p(sky), _p(lo), lo.shape[2], lo.shape[1], lo.shape[0], _p(hi), hi.shape[2], hi.shape[1], hi.shape[0],
+               _p(cu), cu.shape[1], cu.shape[0], _p(we), we.shape[1], we.shape[0], W, H, _p(prev), _p(hdr), _p(mask), int(group_stride),
+               C.c_float(1.0 if weather_scale is None else weather_scale))
     assert rc == 0
     return {"hdr": hdr, "mask": mask}
 
 
-def cloud_full(cam, tm, sky, noise, W, H, variant="canonical", hdr=None, mask=None, group_stride=1):
+def cloud_full(cam, tm, sky, noise, W, H, variant="canonical", hdr=None, mask=None, group_stride=1, weather_scale=None):
     """All 16 pixel ids with the same camera / time: what mtDispatchCloudFull computes."""
     hdr = np.zeros((H, W, 4), np.float32) if hdr is None else hdr
     mask = np.zeros((H, W, 4), np.float32) if mask is None else mask
     t = _c(tm).copy()
     for fid in range(16):
         t["frameCountMod16"] = fid
-        cloud(cam, t, sky, noise, W, H, hdr=hdr, mask=mask, variant=variant, group_stride=group_stride)
+        cloud(cam, t, sky, noise, W, H, hdr=hdr, mask=mask, variant=variant, group_stride=group_stride, weather_scale=weather_scale)
     return {"hdr": hdr, "mask": mask}
 
 

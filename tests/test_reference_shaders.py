@@ -132,3 +132,19 @@ def test_glm_builtins_variant_agrees_to_rounding(oracle_mod, noise):
     assert np.allclose(lit_a, lit_b, rtol=2e-6, atol=1e-7)
     ldr_a, ldr_b = oracle_mod.tonemap(tm, lit_a), refshaders.tonemap(tm, lit_a, variant="glm")
     assert np.abs(ldr_a.astype(int) - ldr_b.astype(int)).max() <= 1
+
+
+@pytest.mark.parametrize("scale", [1.0e-4, 3.7e-5, 1.0])
+def test_weather_path_is_the_shaders_dead_block_revived(oracle_mod, noise, scale):
+    """MtTuning.use_weather = cloudRayMarch.comp with its commented-out weather block (:517-524) live and
+    the coverage read from weather_data.r (:529's trailing comment): glsl2cpp.py --revive-weather builds exactly that
+    from the reference text, and the oracle's weather path reproduces it bit for bit (scale 1.0 = the literal code)."""
+    w, h = 96, 54
+    cam, tm, sky, tun = default_scene(w, h, frame_id=3, total_time=7.5, yaw=20.0, pitch=2.0)
+    tun["use_weather"], tun["weather_scale"] = 1, scale
+    got = oracle_mod.cloud(cam, tm, tun, noise, w, h, full=True, debug=True)
+    want = refshaders.cloud_full(cam, tm, sky, noise, w, h, weather_scale=scale)
+    assert np.array_equal(got["hdr"], want["hdr"]) and np.array_equal(got["mask"], want["mask"])
+    assert (got["debug"]["accum"] > 0).mean() > 0.2
+    plain = refshaders.cloud_full(cam, tm, sky, noise, w, h)
+    assert not np.array_equal(plain["hdr"], want["hdr"])       # the revived block is live
