@@ -67,15 +67,32 @@ def filtered_fetches(c: dict) -> int:
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clock / power / throttle reasons sampled DURING the timed region (B200_PROFILING.md's clocks line).  NVML is polled
+    from a thread every 2 ms (a 4K step is 5 ms: `nvidia-smi -lms` is too slow to land a sample inside a short region);
+    nvidia-smi is the fallback when the NVML binding is unusable."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASON_BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, device: int):
         self.device, self.rows, self.proc, self.thread = device, [], None, None
+        self.nvml, self.handle, self.stop_flag, self.sm_max, self.reason_mask = None, None, threading.Event(), None, 0
 
     def start(self):
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.device)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            pynvml.nvmlDeviceGetClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            return
+        except Exception:  # noqa: BLE001 -- any NVML problem: fall back to the CLI
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "25",
                                           "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -85,6 +102,24 @@ class ClockSampler:
         self.thread = threading.Thread(target=self._read, daemon=True)
         self.thread.start()
 
+    def _poll_nvml(self):
+        n = self.nvml
+        while not self.stop_flag.is_set():
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                try:
+                    pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                except Exception:  # noqa: BLE001
+                    pw = None
+                try:
+                    self.reason_mask |= int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                except Exception:  # noqa: BLE001
+                    pass
+                self.rows.append((sm, pw))
+            except Exception:  # noqa: BLE001
+                pass
+            self.stop_flag.wait(0.002)
+
     def _read(self):
         for line in self.proc.stdout:
             parts = [p.strip() for p in line.split(",")]
@@ -92,6 +127,14 @@ class ClockSampler:
                 self.rows.append(parts)
 
     def stop(self) -> dict:
+        if self.nvml is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=2)
+            sm = [r[0] for r in self.rows]
+            pw = [r[1] for r in self.rows if r[1] is not None]
+            reasons = [k for k, bit in self.REASON_BITS.items() if self.reason_mask & bit]
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.sm_max, "power_w_max": round(max(pw), 2) if pw else None,
+                    "samples": len(self.rows), "reasons": reasons, "source": "nvml, 2 ms period"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -107,7 +150,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(self.rows), "reasons": reasons}
+                "power_w_max": max(pw) if pw else None, "samples": len(self.rows), "reasons": reasons, "source": "nvidia-smi -lms 25"}
 
 
 def scene_for_view(view: int, w: int, h: int, sweep: bool = False):
@@ -187,7 +230,28 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The ONE JSON line goes to the process's real stdout; everything libraries print (NCCL's version banner, torchrun
+    notices) was rerouted to stderr by quiet_stdout()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
+def quiet_stdout():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -197,7 +261,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ctx-flags", type=int, default=0, help="extra MT_FLAG_* bits for A/B runs (e.g. 8 = no quad layout)")
     ap.add_argument("--tile-rows", type=int, default=8, help="frame8k: pixel rows per cyclic tile (multiple of 8)")
-    ap.add_argument("--gather", default="peer_store", choices=["peer_store", "copy"], help="frame8k: kernel peer stores or copy-engine tile pushes")
+    ap.add_argument("--gather", default="peer_store", choices=["peer_store", "copy", "local"],
+                    help="frame8k: kernel peer stores, copy-engine tile pushes, or (diagnostic) no gather at all")
     ap.add_argument("--gather-mask", action="store_true", help="frame8k: also send the god-ray mask tiles to GPU 0 (needed only if god rays run)")
     ap.add_argument("--sweep", action="store_true", help="N>1: rank r renders view r of the sun/coverage sweep")
     args = ap.parse_args()
@@ -357,6 +422,9 @@ def main():
     # ---- max over ranks
     if world > 1:
         t = torch.tensor([dev_ms_total, e2e_s], dtype=torch.float64, device=f"cuda:{local_rank}")
+        per_rank = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(per_rank, t)
+        rank_ms = [round(float(x[0]) / args.steps, 4) for x in per_rank]   # device ms per step of every rank
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_ms_total, e2e_s = float(t[0]), float(t[1])
         cs = torch.tensor([counters[k] for k in ("rays", "rays_marched", "steps", "steps_incloud", "cone_hits", "early_exits")],
@@ -402,6 +470,8 @@ def main():
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
             "work": {k: int(v) for k, v in counters.items()},
         }
+        if world > 1:
+            line["rank_ms"] = rank_ms
         if args.workload == "seq1080p":  # per-pass device time and HBM roofline of the bandwidth passes (SURVEY 8d bytes/pixel)
             px = w * h
             algo = {"reproject": 32 * px, "godrays": 48 * px, "tonemap": 20 * px}
@@ -425,7 +495,7 @@ def main():
         v, cores, desc, _, kind = cpu_reference_sample(noise, W4K, H4K, target_s=12.0)
         line["cpu_baseline"] = {"value": round(v, 4), "unit": UNIT, "cores": cores, "kind": kind, "sample": desc}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

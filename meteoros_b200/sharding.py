@@ -55,9 +55,10 @@ class ShardedFrame:
     def __init__(self, renderer, dist, tile_rows: int = 32, with_mask: bool = True, mode: str = "peer_store", groups: int = 4):
         """mode "peer_store": the march kernel's own stores land in GPU 0's image (fused compute + transfer).
         mode "copy": tiles are rendered locally in `groups` launches and each finished group is pushed to GPU 0 by the
-        copy engine (mtCopyTilesToPeer) while the next group renders."""
-        if mode not in ("peer_store", "copy"):
-            raise ValueError("mode must be 'peer_store' or 'copy'")
+        copy engine (mtCopyTilesToPeer) while the next group renders.
+        mode "local": measurement only -- every rank keeps its tiles (no gather), to separate compute share from transfer."""
+        if mode not in ("peer_store", "copy", "local"):
+            raise ValueError("mode must be 'peer_store', 'copy' or 'local'")
         self.mode, self.groups = mode, max(1, int(groups))
         self.r = renderer
         self.dist = dist
@@ -87,7 +88,7 @@ class ShardedFrame:
     def dispatch(self):
         """Launch this rank's tiles (asynchronous on the renderer's stream)."""
         n = num_tiles(self.r.height, self.tile_rows)
-        if self.mode == "peer_store" or self.rank == 0:
+        if self.mode in ("peer_store", "local") or self.rank == 0:
             self.r.dispatch_cloud_tiles(self.tile_rows, self.rank, n, self.world)
             return
         mine = len(range(self.rank, n, self.world))
