@@ -242,18 +242,20 @@ MT_DEVICE RaySetup cloud_ray_setup(const CloudParams& P, const MarchConst& M, in
     return R;
 }
 
-// One iteration of the march loop (cloudRayMarch.comp:629-678) at parameter t, without the running sums.
+// The sample point of one march iteration and its base density (cloudRayMarch.comp:629-640): everything a step needs
+// before it knows whether it is inside a cloud.
+struct StepBase {
+    f3 pos, skew;
+    float h, baseDensity;
+};
+
 template <bool COUNT, bool WEATHER>
-MT_DEVICE StepSample cloud_step_sample(const CloudParams& P, const MarchConst& M, const RaySetup& R, int jidx, float t,
-                                       RayCounters& cnt)
+MT_DEVICE StepBase cloud_step_base(const CloudParams& P, const MarchConst& M, const RaySetup& R, int jidx, float t, RayCounters& cnt)
 {
-    StepSample S;
-    S.inc = 0.0f;
-    S.energy = -1.0f;
+    StepBase B;
     const f3 origin = M.eyePos, ec = M.earthCenter, dir = R.dir;
     const f3 relOrigin = mk3(ec.x, MT_R_INNER - MT_EARTH_RADIUS, ec.z);
     const f3 wind = mk3(P.tun.wind_direction[0], P.tun.wind_direction[1], P.tun.wind_direction[2]);
-    const float coverage = P.tun.coverage;
     const float* sj = M.stepJitter[jidx >> 1];
     f3 jdir = dir + mk3(sj[0], sj[1], sj[2]);
     f3 pos = origin + jdir * t;
@@ -265,33 +267,57 @@ MT_DEVICE StepSample cloud_step_sample(const CloudParams& P, const MarchConst& M
     float h = div_thickness(fabsf(cosTheta * (lenFromCam - R.lenToInner)));
     // skewSamplePointWithWind (:489-497)
     f3 skew = (sp + ((wind * h) * P.tun.cloud_top_offset) * 0.009f) + M.windSkew;
-    float baseDensity = low_freq_density<WEATHER>(P, coverage, pk2(skew.x, skew.y), skew.z, pos.x, pos.z, h) * P.tun.base_density_factor;
+    B.pos = pos; B.skew = skew; B.h = h;
+    B.baseDensity = low_freq_density<WEATHER>(P, P.tun.coverage, pk2(skew.x, skew.y), skew.z, pos.x, pos.z, h) * P.tun.base_density_factor;
     if (COUNT) cnt.steps++;
-    if (baseDensity > 0.0f) {
-        if (COUNT) cnt.incloud++;
-        float edge = erosion_edge(P.curl, P.high, skew, h);
-        S.inc = erode(baseDensity * 1.4f, edge) * 0.5f;
-        float dl = 0.0f;
-        const P2 relxy = pk2(relOrigin.x, relOrigin.y);
+    return B;
+}
+
+// The in-cloud part of a march iteration (cloudRayMarch.comp:642-672): erosion, the six light-cone samples, light
+// energy.  Call only when B.baseDensity > 0.
+template <bool COUNT, bool WEATHER>
+MT_DEVICE StepSample cloud_step_light(const CloudParams& P, const MarchConst& M, const RaySetup& R, const StepBase& B, RayCounters& cnt)
+{
+    StepSample S;
+    const f3 ec = M.earthCenter, pos = B.pos, skew = B.skew;
+    const f3 relOrigin = mk3(ec.x, MT_R_INNER - MT_EARTH_RADIUS, ec.z);
+    const float coverage = P.tun.coverage, h = B.h, baseDensity = B.baseDensity;
+    if (COUNT) cnt.incloud++;
+    float edge = erosion_edge(P.curl, P.high, skew, h);
+    S.inc = erode(baseDensity * 1.4f, edge) * 0.5f;
+    float dl = 0.0f;
+    const P2 relxy = pk2(relOrigin.x, relOrigin.y);
 #pragma unroll 1
-        for (int i = 0; i < 6; ++i) {  // one copy of the filter in the instruction stream (I-cache)
-            // lightPos = pos + (stepSize * noise_kernel[i]) * i ; sample = (lightPos - relOrigin) / 12500  -- x,y as a pair
-            const float fi = (float)i;
-            const f3 cs = M.coneStep[i];
-            const P2 off = mul2(mul2(pk2(cs.x, cs.y), bc2(R.stepSize)), bc2(fi));
-            // scalar adds: a mul2 feeding an add2 would be contracted into an FFMA2 (mt_math.cuh)
-            P2 lxy = sub2(pk2(pos.x + lo2(off), pos.y + hi2(off)), relxy);
-            float lz = (pos.z + (cs.z * R.stepSize) * fi) - relOrigin.z;
-            const P2 sxy = div_thickness2(lxy);
-            const float sz = div_thickness(lz);
-            float cur = low_freq_density<WEATHER>(P, coverage, sxy, sz, lo2(sxy), sz, h);
-            if (cur > 0.0f) {
-                if (COUNT) cnt.cone++;
-                dl += erode(1.5f * cur, edge);
-            }
+    for (int i = 0; i < 6; ++i) {  // one copy of the filter in the instruction stream (I-cache)
+        // lightPos = pos + (stepSize * noise_kernel[i]) * i ; sample = (lightPos - relOrigin) / 12500  -- x,y as a pair
+        const float fi = (float)i;
+        const f3 cs = M.coneStep[i];
+        const P2 off = mul2(mul2(pk2(cs.x, cs.y), bc2(R.stepSize)), bc2(fi));
+        // scalar adds: a mul2 feeding an add2 would be contracted into an FFMA2 (mt_math.cuh)
+        P2 lxy = sub2(pk2(pos.x + lo2(off), pos.y + hi2(off)), relxy);
+        float lz = (pos.z + (cs.z * R.stepSize) * fi) - relOrigin.z;
+        const P2 sxy = div_thickness2(lxy);
+        const float sz = div_thickness(lz);
+        float cur = low_freq_density<WEATHER>(P, coverage, sxy, sz, lo2(sxy), sz, h);
+        if (cur > 0.0f) {
+            if (COUNT) cnt.cone++;
+            dl += erode(1.5f * cur, edge);
         }
-        S.energy = light_energy(h, dl, baseDensity, R.phase, R.cosAngle);
     }
+    S.energy = light_energy(h, dl, baseDensity, R.phase, R.cosAngle);
+    return S;
+}
+
+// One iteration of the march loop (cloudRayMarch.comp:629-678) at parameter t, without the running sums.
+template <bool COUNT, bool WEATHER>
+MT_DEVICE StepSample cloud_step_sample(const CloudParams& P, const MarchConst& M, const RaySetup& R, int jidx, float t,
+                                       RayCounters& cnt)
+{
+    const StepBase B = cloud_step_base<COUNT, WEATHER>(P, M, R, jidx, t, cnt);
+    if (B.baseDensity > 0.0f) return cloud_step_light<COUNT, WEATHER>(P, M, R, B, cnt);
+    StepSample S;
+    S.inc = 0.0f;
+    S.energy = -1.0f;
     return S;
 }
 

@@ -237,7 +237,10 @@ __global__ void __launch_bounds__(128) cloud_rays_kernel(const __grid_constant__
     n = max(n, __shfl_xor_sync(0xffffffffu, n, 1));
     if ((threadIdx.x & 31) == 0) atomicMax(&ctaSteps, n);
     __syncthreads();
-    if (threadIdx.x == 0) P.ctaSteps[blockIdx.x] = ctaSteps;
+    if (threadIdx.x == 0) {
+        P.ctaSteps[blockIdx.x] = ctaSteps;
+        if (blockIdx.x == 0) *P.itemCount = 0u;  // the in-cloud list of this frame starts empty (cloud_base_kernel runs next)
+    }
 }
 
 template <bool WEATHER>
@@ -256,7 +259,72 @@ __global__ void __launch_bounds__(128, MT_CLOUD_MINBLOCKS) cloud_steps_kernel(co
     const int jidx = (P.tm.frameCountMod16 + mt_f2i(t)) & 15;
     RayCounters none = { 0u, 0u, 0u, 0u, 0u, 0u };
     const StepSample S = cloud_step_sample<false, WEATHER>(P, M, R, jidx, t, none);
-    P.samples[(size_t)k * ((size_t)gridDim.x * 128) + ray] = make_float2(S.inc, S.energy);
+    P.samples[(size_t)k * (size_t)P.rayStride + ray] = make_float2(S.inc, S.energy);
+}
+
+// The step-parallel march in two kernels (-DMT_STEP_COMPACT=1; OFF by default, see the measurement below): lanes of a warp are 32 neighbouring rays at the
+// same step index, and at a cloud's edge only some of them are inside it -- in cloud_steps_kernel the others idle
+// through the ~1 500-instruction lighting part (20.6 of 32 lanes active at 1080p).  So cloud_base_kernel evaluates only
+// the sample point and its base density for every (step, ray), files the misses as (0, -1) and appends the hits to a
+// list (one atomicAdd per warp); cloud_light_kernel then walks that list with every lane busy.  Which thread evaluates a
+// sample does not change its arithmetic, and results are stored by (step, ray), so the output is bit-identical and
+// independent of the list's order (the -m gpu suite passes with it).  Measured (profiles/r1_ab.md): 1080p 183.5 vs 189.4 us,
+// but 4K 664.8 vs 627.7 us -- the step-parallel march is latency bound, not issue bound, and the list walk adds a
+// dependent load chain (item -> ray record -> t -> sample point) while saving instructions that were not the limit.
+#ifndef MT_STEP_COMPACT
+#define MT_STEP_COMPACT 0
+#endif
+#define MT_ITEM_RAY_BITS 26
+
+template <bool WEATHER>
+__global__ void __launch_bounds__(128, MT_CLOUD_MINBLOCKS) cloud_base_kernel(const __grid_constant__ CloudParams P)
+{
+    const int k = blockIdx.y;
+    if (k >= __ldg(P.ctaSteps + blockIdx.x)) return;  // whole CTA idle for this slice (uniform: taken by all 128 threads)
+    __shared__ MarchConst M;
+    stage_march_const(M, P.mc);
+    const size_t ray = (size_t)blockIdx.x * 128 + threadIdx.x;
+    const RaySetup R = reinterpret_cast<const RaySetup*>(P.rays)[ray];
+    float t = R.t_in;
+    for (int i = 0; i < k; ++i) t += R.stepSize;  // the same k roundings the sequential loop performs
+    const bool live = R.branch == 2 && t < R.t_out;
+    bool hit = false;
+    if (live) {
+        const int jidx = (P.tm.frameCountMod16 + mt_f2i(t)) & 15;
+        RayCounters none = { 0u, 0u, 0u, 0u, 0u, 0u };
+        hit = cloud_step_base<false, WEATHER>(P, M, R, jidx, t, none).baseDensity > 0.0f;
+        if (!hit) P.samples[(size_t)k * (size_t)P.rayStride + ray] = make_float2(0.0f, -1.0f);
+    }
+    const unsigned hits = __ballot_sync(0xffffffffu, hit);
+    if (hits) {
+        const int lane = threadIdx.x & 31, leader = __ffs(hits) - 1;
+        unsigned at = 0u;
+        if (lane == leader) at = atomicAdd(P.itemCount, (unsigned)__popc(hits));
+        at = __shfl_sync(0xffffffffu, at, leader);
+        if (hit) P.items[at + __popc(hits & ((1u << lane) - 1u))] = ((unsigned)k << MT_ITEM_RAY_BITS) | (unsigned)ray;
+    }
+}
+
+template <bool WEATHER>
+__global__ void __launch_bounds__(128, MT_CLOUD_MINBLOCKS) cloud_light_kernel(const __grid_constant__ CloudParams P)
+{
+    __shared__ MarchConst M;
+    stage_march_const(M, P.mc);
+    const unsigned n = *reinterpret_cast<const volatile unsigned*>(P.itemCount);
+    const unsigned step = gridDim.x * 128u;
+    for (unsigned i = blockIdx.x * 128u + threadIdx.x; i < n; i += step) {
+        const unsigned item = __ldg(P.items + i);
+        const int k = (int)(item >> MT_ITEM_RAY_BITS);
+        const size_t ray = item & ((1u << MT_ITEM_RAY_BITS) - 1u);
+        const RaySetup R = reinterpret_cast<const RaySetup*>(P.rays)[ray];
+        float t = R.t_in;
+        for (int j = 0; j < k; ++j) t += R.stepSize;
+        const int jidx = (P.tm.frameCountMod16 + mt_f2i(t)) & 15;
+        RayCounters none = { 0u, 0u, 0u, 0u, 0u, 0u };
+        const StepBase B = cloud_step_base<false, WEATHER>(P, M, R, jidx, t, none);   // same arithmetic: B.baseDensity > 0 again
+        const StepSample S = cloud_step_light<false, WEATHER>(P, M, R, B, none);
+        P.samples[(size_t)k * (size_t)P.rayStride + ray] = make_float2(S.inc, S.energy);
+    }
 }
 
 __global__ void __launch_bounds__(128) cloud_fold_kernel(const __grid_constant__ CloudParams P)
@@ -267,7 +335,7 @@ __global__ void __launch_bounds__(128) cloud_fold_kernel(const __grid_constant__
     int px, py, pixelID;
     bool valid;
     sixteenth_pixel(P, px, py, pixelID, valid);
-    const size_t stride = (size_t)gridDim.x * 128;
+    const size_t stride = (size_t)P.rayStride;
     int n = 0;  // number of march iterations: the t sequence of the sequential loop
     for (float t = R.t_in; t < R.t_out && n < MT_STEP_SLICES; t += R.stepSize) ++n;
     float accum = 0.0f, transmittance = 1.0f, color = 0.0f;
@@ -292,14 +360,36 @@ __global__ void __launch_bounds__(128) cloud_fold_kernel(const __grid_constant__
     store_pixel(P, (size_t)py * P.W + px, hdr, mask);
 }
 
-cudaError_t mt_launch_cloud_sixteenth_split(const CloudParams& P, cudaStream_t stream, int* launches)
+cudaError_t mt_launch_cloud_sixteenth_split(const CloudParams& P0, cudaStream_t stream, int* launches)
 {
+    CloudParams P = P0;
     const unsigned ctas = (unsigned)((P.tx / 8) * (P.ty / 4) / 4);  // tx, ty are multiples of 32
+    P.rayStride = (int)(ctas * 128u);
+    if ((size_t)P.rayStride > ((size_t)1 << MT_ITEM_RAY_BITS)) return cudaErrorInvalidValue;
     cloud_rays_kernel<<<ctas, 128, 0, stream>>>(P);
-    if (P.tun.use_weather) cloud_steps_kernel<true><<<dim3(ctas, MT_STEP_SLICES, 1), 128, 0, stream>>>(P);
-    else cloud_steps_kernel<false><<<dim3(ctas, MT_STEP_SLICES, 1), 128, 0, stream>>>(P);
-    cloud_fold_kernel<<<ctas, 128, 0, stream>>>(P);
+    const dim3 slices(ctas, MT_STEP_SLICES, 1);
+#if MT_STEP_COMPACT
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const unsigned walkers = (unsigned)sms * MT_CLOUD_MINBLOCKS;   // one resident wave walks the whole list
+    if (P.tun.use_weather) {
+        cloud_base_kernel<true><<<slices, 128, 0, stream>>>(P);
+        cloud_light_kernel<true><<<walkers, 128, 0, stream>>>(P);
+    } else {
+        cloud_base_kernel<false><<<slices, 128, 0, stream>>>(P);
+        cloud_light_kernel<false><<<walkers, 128, 0, stream>>>(P);
+    }
+    *launches = 4;
+#else
+    if (P.tun.use_weather) cloud_steps_kernel<true><<<slices, 128, 0, stream>>>(P);
+    else cloud_steps_kernel<false><<<slices, 128, 0, stream>>>(P);
     *launches = 3;
+#endif
+    cloud_fold_kernel<<<ctas, 128, 0, stream>>>(P);
     return cudaGetLastError();
 }
 

@@ -41,6 +41,8 @@ struct MtContext {
     void* rays = nullptr;         // step-parallel 1/16 path: RaySetup per ray (lazily allocated)
     float2* samples = nullptr;    //   and (inc, energy) per (step, ray)
     int* ctaSteps = nullptr;      //   and the per-CTA maximum step count
+    unsigned* items = nullptr;    //   and the compacted in-cloud (step, ray) list + its length
+    unsigned* itemCount = nullptr;
     MtRayDebug* debug = nullptr;  // lazily allocated W*H records
     int* taps = nullptr;          // lazily allocated W*H*10
     MtCameraUBO cam, camOld;
@@ -114,7 +116,8 @@ static void free_images(MtContext* c)
     cudaFree(c->ldr[0]); cudaFree(c->ldr[1]); cudaFree(c->ldrScratch);
     c->ldr[0] = c->ldr[1] = c->ldrScratch = nullptr;
     cudaFree(c->debug); cudaFree(c->taps); cudaFree(c->maskDecoded); cudaFree(c->rays); cudaFree(c->samples); cudaFree(c->ctaSteps);
-    c->maskDecoded = nullptr; c->rays = nullptr; c->samples = nullptr; c->ctaSteps = nullptr;
+    cudaFree(c->items); cudaFree(c->itemCount);
+    c->maskDecoded = nullptr; c->rays = nullptr; c->samples = nullptr; c->ctaSteps = nullptr; c->items = nullptr; c->itemCount = nullptr;
     c->hdr[0] = c->hdr[1] = c->mask = nullptr;
     c->debug = nullptr; c->taps = nullptr;
 }
@@ -442,10 +445,14 @@ static MtStatus cloud_dispatch(MtContext* c, int full, const RowTiles* tiles, bo
         MT_CUDA(c, cudaMalloc(&c->rays, nrays * 64));
         MT_CUDA(c, cudaMalloc((void**)&c->samples, nrays * 64 * sizeof(float2)));
         MT_CUDA(c, cudaMalloc((void**)&c->ctaSteps, (nrays / 128 + 1) * sizeof(int)));
+        MT_CUDA(c, cudaMalloc((void**)&c->items, nrays * 64 * sizeof(unsigned)));
+        MT_CUDA(c, cudaMalloc((void**)&c->itemCount, sizeof(unsigned)));
     }
     P.rays = c->rays;
     P.samples = c->samples;
     P.ctaSteps = c->ctaSteps;
+    P.items = c->items;
+    P.itemCount = c->itemCount;
     wait_pending_read(c, P.hdr);
     wait_pending_read(c, P.mask);
     MT_CUDA(c, mt_launch_cloud_setup(P, c->mc, c->stream));

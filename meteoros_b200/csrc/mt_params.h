@@ -82,6 +82,9 @@ struct CloudParams {
     void* rays;                    // RaySetup[tx*ty], tile-major
     float2* samples;               // [MT_STEP_SLICES][tx*ty] (inc, energy)
     int* ctaSteps;                 // per 128-ray CTA: the largest step count among its rays (0 = all horizon-culled)
+    unsigned* items;               // compacted in-cloud (step, ray) pairs: step << 26 | ray, in no particular order
+    unsigned* itemCount;           // how many of them (zeroed by cloud_rays_kernel, filled by cloud_base_kernel)
+    int rayStride;                 // rays per sample slice = 128 * CTAs of the ray grid
 };
 
 struct ReprojParams {
