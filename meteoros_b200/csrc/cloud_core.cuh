@@ -185,7 +185,8 @@ struct RaySetup {
     float lenToInner, cosAngle, phase;
     f3 bg;           // Preetham sky * max(.62, dir.y)
     int branch;      // 0 ocean, 1 sky band, 2 march
-    int pad[3];
+    int nsteps;      // step-parallel path only: iterations of the march loop (cloud_rays_kernel fills it in)
+    int pad[2];
 };
 
 static_assert(sizeof(RaySetup) == 64, "RaySetup is the 64-byte per-ray record of the step-parallel path");

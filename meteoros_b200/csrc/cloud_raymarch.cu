@@ -227,8 +227,14 @@ __global__ void __launch_bounds__(128) cloud_rays_kernel(const __grid_constant__
         const RaySetup R = cloud_ray_setup(P, M, px, py, pixelID, hdr);
         *rec = R;
         if (R.branch != 2) store_pixel(P, (size_t)py * P.W + px, hdr, mask);  // ocean / sky band: final
-        else
-            for (float t = R.t_in; t < R.t_out && n < MT_STEP_SLICES; t += R.stepSize) ++n;  // this ray's step count
+        else {
+            // the march loop's own t sequence (t += stepSize, one rounding per step), filed per step: a sample's thread
+            // reads its t_k instead of repeating k dependent additions
+            float* tk = reinterpret_cast<float*>(P.samples + ((size_t)blockIdx.x * 128 + threadIdx.x));
+            const size_t stride2 = 2 * (size_t)gridDim.x * 128;
+            for (float t = R.t_in; t < R.t_out && n < MT_STEP_SLICES; t += R.stepSize) tk[(size_t)(n++) * stride2] = t;
+        }
+        rec->nsteps = n;
     }
     // the largest step count of the CTA's 128 rays: slices beyond it (and every slice of a horizon-culled CTA) have
     // nothing to do, and cloud_steps_kernel learns that from one load
@@ -243,23 +249,25 @@ __global__ void __launch_bounds__(128) cloud_rays_kernel(const __grid_constant__
     }
 }
 
+#ifndef MT_STEPS_MINBLOCKS
+#define MT_STEPS_MINBLOCKS 12  /* 39 registers, no spills: 48 warps per SM; the step-parallel march is latency bound (profiles/r1_ab.md) */
+#endif
 template <bool WEATHER>
-__global__ void __launch_bounds__(128, MT_CLOUD_MINBLOCKS) cloud_steps_kernel(const __grid_constant__ CloudParams P)
+__global__ void __launch_bounds__(128, MT_STEPS_MINBLOCKS) cloud_steps_kernel(const __grid_constant__ CloudParams P)
 {
     const int k = blockIdx.y;
     if (k >= __ldg(P.ctaSteps + blockIdx.x)) return;  // whole CTA idle for this slice (uniform: taken by all 128 threads)
     __shared__ MarchConst M;
     stage_march_const(M, P.mc);
     const size_t ray = (size_t)blockIdx.x * 128 + threadIdx.x;
+    float2* slot = P.samples + ((size_t)k * (size_t)P.rayStride + ray);
+    const float t = __ldg(reinterpret_cast<const float*>(slot));  // t_k as the sequential loop rounds it (cloud_rays_kernel)
     const RaySetup R = reinterpret_cast<const RaySetup*>(P.rays)[ray];
-    if (R.branch != 2) return;
-    float t = R.t_in;
-    for (int i = 0; i < k; ++i) t += R.stepSize;  // the same k roundings the sequential loop performs
-    if (!(t < R.t_out)) return;
+    if (R.branch != 2 || k >= R.nsteps) return;
     const int jidx = (P.tm.frameCountMod16 + mt_f2i(t)) & 15;
     RayCounters none = { 0u, 0u, 0u, 0u, 0u, 0u };
     const StepSample S = cloud_step_sample<false, WEATHER>(P, M, R, jidx, t, none);
-    P.samples[(size_t)k * (size_t)P.rayStride + ray] = make_float2(S.inc, S.energy);
+    *slot = make_float2(S.inc, S.energy);
 }
 
 // The step-parallel march in two kernels (-DMT_STEP_COMPACT=1; OFF by default, see the measurement below): lanes of a warp are 32 neighbouring rays at the
@@ -336,8 +344,7 @@ __global__ void __launch_bounds__(128) cloud_fold_kernel(const __grid_constant__
     bool valid;
     sixteenth_pixel(P, px, py, pixelID, valid);
     const size_t stride = (size_t)P.rayStride;
-    int n = 0;  // number of march iterations: the t sequence of the sequential loop
-    for (float t = R.t_in; t < R.t_out && n < MT_STEP_SLICES; t += R.stepSize) ++n;
+    const int n = R.nsteps;  // number of march iterations (cloud_rays_kernel ran the t sequence of the sequential loop)
     float accum = 0.0f, transmittance = 1.0f, color = 0.0f;
     bool stop = false;
     // the fold is the only sequential part; its loads do not depend on the running sums, so fetch eight steps at a time
