@@ -114,15 +114,16 @@ MT_DEVICE float mask_decode(const float* dec, int W, int H, P2 st)
 {
     const P2 m = mul2(st, pk2((float)W, (float)H));
     const float ux = lo2(m) - 0.5f, uy = hi2(m) - 0.5f;  // scalar: mul2 -> sub2 would be contracted (mt_math.cuh)
-    int x0 = mt_floor2i(ux), y0 = mt_floor2i(uy);
+    const int x0 = mt_floor2i(ux), y0 = mt_floor2i(uy);
     const P2 a1 = sub2(pk2(ux, uy), pk2((float)x0, (float)y0));  // (ax, ay)
     const P2 a0 = sub2(bc2(1.0f), a1);                  // (1-ax, 1-ay)
-    // uv stays inside [0,1] (the march runs from the pixel towards the clamped sun position), so x0 in [-1, W-1]
-    x0 = min(max(x0, -1), W - 1);
-    y0 = min(max(y0, -1), H - 1);
-    const unsigned pitch = (unsigned)(W + 2);
-    const float* __restrict__ p = dec + ((unsigned)(y0 + 1) * pitch + (unsigned)(x0 + 1));
-    float a = MT_LDG(p), b = MT_LDG(p + 1), c = MT_LDG(p + pitch), d = MT_LDG(p + pitch + 1);
+    // No clamp: the march runs from the pixel centre towards the sun position, which main() clamps to [0,1]
+    // (postProcess_GodRays.frag:90), so u*W - 0.5 lies in [-0.5, W - 0.5] and floor() in [-1, W-1] -- the ring.  The 100
+    // roundings of `uv -= delta` move u*W by < 0.05 texel even at W = 7680, against a margin of 0.5.
+    const int pitch = W + 2;
+    const float* __restrict__ texel00 = dec + pitch + 1;          // loop invariant: image texel (0, 0) inside the ring
+    const int i0 = y0 * pitch + x0, i1 = i0 + pitch;              // signed 32-bit offsets (>= -pitch - 1): one IMAD.WIDE per row
+    float a = MT_LDG(texel00 + i0), b = MT_LDG(texel00 + i0 + 1), c = MT_LDG(texel00 + i1), d = MT_LDG(texel00 + i1 + 1);
     const float ax = lo2(a1), ay = hi2(a1), bx = lo2(a0), by = hi2(a0);
     float w00 = bx * by, w01 = ax * by, w10 = bx * ay, w11 = ax * ay;
     return fmaf(w11, d, fmaf(w10, c, fmaf(w01, b, w00 * a)));
