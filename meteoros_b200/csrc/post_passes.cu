@@ -68,7 +68,16 @@ __global__ void __launch_bounds__(256) mask_decode_kernel(const __grid_constant_
     P.decoded[(size_t)(y + 1) * (size_t)(P.W + 2) + (size_t)(x + 1)] = d;
 }
 
-// ---- God rays: a warp is an 8x4 pixel tile so the footprint of tap i stays within a few cache lines ---------------
+// ---- God rays: 100 bilinear taps per pixel on the decoded scalar image; the kernel is bound by L1 wavefronts and issue
+// slots together (profiles/r1_passes_1080p.md), so the warp's pixel footprint decides how many 128-byte lines each of the
+// four loads of a tap touches.  MT_GODRAY_LOG2W: a warp is a (1 << LOG2W) x (32 >> LOG2W) pixel tile (3: 8x4, 4: 16x2, 5: 32x1).
+#ifndef MT_GODRAY_LOG2W
+#define MT_GODRAY_LOG2W 5  /* 1080p: 278.9 us (8x4), 246.1 us (16x2), 244.1 us (32x1) -- profiles/r1_ab.md */
+#endif
+#define MT_GODRAY_WW (1 << MT_GODRAY_LOG2W)
+#define MT_GODRAY_WH (32 >> MT_GODRAY_LOG2W)
+#define MT_GODRAY_CTA_W (MT_GODRAY_LOG2W == 5 ? 32 : 2 * MT_GODRAY_WW)                  /* 16, 32, 32 */
+#define MT_GODRAY_CTA_H (MT_GODRAY_LOG2W == 5 ? 4 : 2 * MT_GODRAY_WH)                   /*  8,  4,  4 */
 __global__ void __launch_bounds__(128) godrays_kernel(const __grid_constant__ GodRayParams P)
 {
     __shared__ GodRayFrame frame;
@@ -76,8 +85,9 @@ __global__ void __launch_bounds__(128) godrays_kernel(const __grid_constant__ Go
     __syncthreads();
     if (frame.blend < 0.0f) return;  // sun behind the camera: the fragment shader returns before any store
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int x = blockIdx.x * 16 + ((warp & 1) << 3) + (lane & 7);
-    const int y = blockIdx.y * 8 + ((warp >> 1) << 2) + (lane >> 3);
+    const int wx = MT_GODRAY_LOG2W == 5 ? 0 : (warp & 1), wy = MT_GODRAY_LOG2W == 5 ? warp : (warp >> 1);
+    const int x = blockIdx.x * MT_GODRAY_CTA_W + wx * MT_GODRAY_WW + (lane & (MT_GODRAY_WW - 1));
+    const int y = blockIdx.y * MT_GODRAY_CTA_H + wy * MT_GODRAY_WH + (lane >> MT_GODRAY_LOG2W);
     if (x >= P.W || y >= P.H) return;
     F4 g = godray_pixel(P, frame, x, y);
     float4* px = reinterpret_cast<float4*>(P.hdr) + ((size_t)y * P.W + x);
@@ -133,7 +143,7 @@ cudaError_t mt_launch_godrays(const GodRayParams& P, cudaStream_t stream)
     mask_decode_kernel<<<dgrid, 256, 0, stream>>>(P);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    dim3 grid((unsigned)((P.W + 15) / 16), (unsigned)((P.H + 7) / 8), 1);
+    dim3 grid((unsigned)((P.W + MT_GODRAY_CTA_W - 1) / MT_GODRAY_CTA_W), (unsigned)((P.H + MT_GODRAY_CTA_H - 1) / MT_GODRAY_CTA_H), 1);
     godrays_kernel<<<grid, 128, 0, stream>>>(P);
     return cudaGetLastError();
 }
