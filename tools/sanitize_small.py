@@ -31,3 +31,26 @@ with api.CloudRenderer(w, h) as r:  # step-parallel 1/16 path
     r.set_camera(cam.ubo()); r.set_camera_old(old); r.set_time(sc.ubo())
     r.dispatch_cloud()
     print("mean", float(np.nanmean(r.read_image(api.IMAGE_CLOUD_CUR))))
+# god rays walk from every pixel to the clamped sun position without clamping the taps (post_core.cuh::mask_decode):
+# sweep the sun over the frame's interior, edges and corners, and past them
+for wh in ((130, 70), (33, 17), (64, 36)):
+    with api.CloudRenderer(*wh) as r:
+        r.upload_noise(textures.load_noise())
+        r.set_sun_and_sky(sky.ubo())
+        for yaw in (0.0, 35.0, -35.0, 90.0, 179.0):
+            for pitch in (0.0, 30.0, 60.0, 89.0, -30.0):
+                c = scene.Camera(*wh)
+                c.rotate_about_up(yaw)
+                if pitch:
+                    c.rotate_about_right(pitch)
+                r.set_camera(c.ubo()); r.set_camera_old(c.ubo()); r.set_time(sc.ubo())
+                r.frame(True, True)
+        r.synchronize()
+tun = scene.default_tuning()
+tun["use_weather"], tun["weather_scale"] = 1, 1.0e-4
+with api.CloudRenderer(w, h) as r:  # weather variants of the march kernels
+    r.upload_noise(textures.load_noise())
+    r.set_camera(cam.ubo()); r.set_camera_old(old); r.set_time(sc.ubo()); r.set_tuning(tun)
+    r.dispatch_cloud()
+    r.dispatch_cloud_full()
+    print("weather mean", float(np.nanmean(r.read_image(api.IMAGE_CLOUD_CUR))))
