@@ -343,6 +343,38 @@ def test_godrays_and_tonemap(api, oracle_mod, noise):
         assert np.array_equal(out, ref["hdr"])
 
 
+@pytest.mark.parametrize("w,h", [(160, 90), (33, 17)])
+def test_godrays_sun_position_sweep(api, oracle_mod, w, h):
+    """The taps walk from the pixel centre to the clamped sun position and are not clamped themselves (they provably stay
+    inside the decoded image's one-texel ring): sun inside the frame, on every edge and corner, behind the camera."""
+    from meteoros_b200 import scene
+
+    rng = np.random.default_rng(w)
+    hdr = rng.random((h, w, 4), dtype=np.float32)
+    mask = rng.random((h, w, 4), dtype=np.float32)      # every texel non-trivial, incl. the ones next to the ring
+    sky = scene.Sky().ubo()
+    lit = 0
+    with api.CloudRenderer(w, h) as r:
+        r.set_sun_and_sky(sky)
+        for yaw in (0.0, 35.0, -35.0, 90.0, 179.0):
+            for pitch in (0.0, 30.0, 60.0, 89.0, -30.0):
+                c = scene.Camera(w, h)
+                c.rotate_about_up(yaw)
+                if pitch:
+                    c.rotate_about_right(pitch)
+                cam = c.ubo()
+                r.set_camera(cam)
+                r.write_image(api.IMAGE_CLOUD_CUR, hdr)
+                r.write_image(api.IMAGE_GODRAY_MASK, mask)
+                r.dispatch_god_rays()
+                got = r.read_image(api.IMAGE_CLOUD_CUR)
+                want = oracle_mod.godrays(cam, sky, mask, hdr)
+                lit += int((want != hdr).any())
+                added_err = np.abs((got - hdr.astype(np.float64)) - (want - hdr.astype(np.float64)))
+                assert (added_err <= 2e-5 * np.abs(want - hdr) + 2.5e-7 * np.abs(hdr)).all(), (yaw, pitch)
+    assert 5 <= lit < 25        # both outcomes of the blend < 0 test occurred
+
+
 def test_sixteen_frame_pan_sequence(api, oracle_mod, noise):
     """BASELINE config 2 at reduced size: 16 frames, 0.25 deg/frame pan, REPROJ + CLOUD + GODRAYS + TONEMAP + swap."""
     from meteoros_b200 import scene
