@@ -172,8 +172,9 @@ __global__ void __launch_bounds__(128, MT_CLOUD_MINBLOCKS) cloud_raymarch_kernel
 // kernel is latency bound there (0.41 ms, IPC 0.23 per scheduler).  But a march step depends on the steps before it
 // only through three running sums; the sample itself (position, densities, light cone, light energy) needs just t_k,
 // and t_k = t_in + stepSize + ... + stepSize is k additions.  So: (1) one thread per ray does castRay / horizon
-// branches / shells and files a 64-byte record; (2) one thread per (ray, step) recomputes t_k with the same k
-// additions and evaluates the sample -- 64x more parallelism, the same arithmetic; (3) one thread per ray folds the
+// branches / shells, files a 64-byte record and runs the loop's t sequence once, filing every t_k; (2) one thread per
+// (ray, step) reads its t_k (the very value the sequential loop holds after k additions) and evaluates the sample --
+// 64x more parallelism, the same arithmetic; (3) one thread per ray folds the
 // samples in step order (the only sequential part, ~8 instructions per step) and composites.  Every value is produced
 // by the same device functions in the same order as in the monolithic kernel, so the output is bit-identical.
 // ---------------------------------------------------------------------------------------------------------------------

@@ -148,3 +148,31 @@ def test_weather_path_is_the_shaders_dead_block_revived(oracle_mod, noise, scale
     assert (got["debug"]["accum"] > 0).mean() > 0.2
     plain = refshaders.cloud_full(cam, tm, sky, noise, w, h)
     assert not np.array_equal(plain["hdr"], want["hdr"])       # the revived block is live
+
+
+def test_kernel_cores_against_the_reference_shaders_directly(noise):
+    """No oracle in between: the CUDA kernels' per-pixel cores (meteoros_b200/csrc/*_core.cuh compiled for the host,
+    tests/hostsim) against the reference's own shader text.  Masks, reprojected images, tone-mapped and TXAA bytes are
+    identical; radiance agrees to the ulps the kernels' documented re-associations allow (cos(acos x) := x, decode-then-
+    filter god rays)."""
+    from tests_hostsim_loader import hostsim as _fixture  # noqa: F401  (the fixture function; call the module directly)
+    import hostsim
+
+    oracle_debug = np.dtype([("dir", "<f4", (3,)), ("t_in", "<f4"), ("t_out", "<f4"), ("step_size", "<f4"), ("branch", "<i4"),
+                             ("steps", "<i4"), ("jitter_hash", "<u4"), ("accum", "<f4")])
+    w, h = 128, 72
+    old, tm, sky, tun = default_scene(w, h, frame_id=11, total_time=5.0, yaw=3.0, pitch=1.0)
+    cam, _, _, _ = default_scene(w, h, frame_id=11, total_time=5.0, yaw=3.25, pitch=1.0)
+    want = refshaders.cloud_full(cam, tm, sky, noise, w, h)
+    hdr, mask, _, _ = hostsim.cloud(cam, tm, tun, noise, w, h, True, oracle_debug)
+    assert np.array_equal(mask, want["mask"])
+    assert np.array_equal(hdr[..., 3], want["hdr"][..., 3]) and np.allclose(hdr, want["hdr"], rtol=2e-6, atol=0)
+    rng = np.random.default_rng(8)
+    prev = rng.random((h, w, 4), dtype=np.float32)
+    assert np.array_equal(hostsim.reproject(cam, old, tm, prev)[0], refshaders.reproject(cam, old, tm, prev))
+    lit = hostsim.godrays(cam, sky["lightColor"][:3], want["mask"], want["hdr"])
+    assert np.allclose(lit, refshaders.godrays(cam, sky, want["mask"], want["hdr"]), rtol=1e-6, atol=0)
+    ldr = refshaders.tonemap(tm, want["hdr"])
+    assert np.array_equal(hostsim.tonemap(tm, want["hdr"]), ldr)
+    hist = np.roll(ldr, 3, axis=1)
+    assert np.array_equal(hostsim.txaa(cam, old, tm, ldr, hist), refshaders.txaa(cam, old, tm, ldr, hist))
