@@ -234,6 +234,12 @@ MT_API MtStatus mtImageDevicePtr(MtContext* ctx, MtImage which, void** dev_ptr);
  * context's own images), e.g. a peer-mapped image on GPU 0 so that row tiles land there through NVLink stores
  * straight from the kernel epilogue.  NULL restores the context's own image.                                  */
 MT_API MtStatus mtSetCloudOutput(MtContext* ctx, void* hdr_dev_ptr, void* mask_dev_ptr);
+/* Gather by forwarding: with a peer image set here (mtOpenPeerImage pointer, same dimensions; NULL = off), every
+ * mtDispatchCloudTiles keeps the march kernel's stores in this context's own HDR image and launches, on a high-priority
+ * side stream, a small kernel that pushes each row tile into the peer image as soon as the march has finished it -- the
+ * transfer overlaps the march tile by tile and no marching warp waits on NVLink.  mtJoinCopies orders the main stream
+ * after it; mtSynchronize waits for it.  The god-ray mask stays local.  Ignored while mtSetCloudOutput is in effect.   */
+MT_API MtStatus mtSetCloudForward(MtContext* ctx, void* peer_hdr_dev_ptr);
 /* CUDA IPC plumbing for one-process-per-GPU sharding: export this context's image, map a peer's. 64-byte handles. */
 MT_API MtStatus mtExportImageHandle(MtContext* ctx, MtImage which, uint8_t handle[64]);
 MT_API MtStatus mtOpenPeerImage(MtContext* ctx, const uint8_t handle[64], void** dev_ptr);

@@ -91,6 +91,7 @@ PROTOTYPES = {
     "mtClearImages": (C.c_int, [C.c_void_p]),
     "mtImageDevicePtr": (C.c_int, [C.c_void_p, C.c_int, c_void_pp]),
     "mtSetCloudOutput": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mtSetCloudForward": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mtExportImageHandle": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "mtOpenPeerImage": (C.c_int, [C.c_void_p, C.c_void_p, c_void_pp]),
     "mtClosePeerImage": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -234,6 +234,10 @@ class CloudRenderer:
     def set_cloud_output(self, hdr_ptr: int | None, mask_ptr: int | None):
         self._check(self._lib.mtSetCloudOutput(self._h, C.c_void_p(hdr_ptr or 0), C.c_void_p(mask_ptr or 0)), "mtSetCloudOutput")
 
+
+    def set_cloud_forward(self, hdr_ptr):
+        """Gather by forwarding: finished row tiles of dispatch_cloud_tiles are pushed to this peer image by a side kernel."""
+        self._check(self._lib.mtSetCloudForward(self._h, C.c_void_p(hdr_ptr or 0)), "mtSetCloudForward")
     def export_image_handle(self, which: int) -> bytes:
         buf = (C.c_uint8 * 64)()
         self._check(self._lib.mtExportImageHandle(self._h, which, buf), "mtExportImageHandle")

@@ -90,6 +90,7 @@ __global__ void __launch_bounds__(128, MT_CLOUD_MINBLOCKS) cloud_raymarch_kernel
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int px, py, pixelID;
+    int doneSlot = 0;  // FULL: index of this CTA's row tile within the launch (tile_forward_kernel's completion counters)
     bool valid;
     if (FULL) {
         // warp = MT_WARP_SHAPE ray tile (default 16x2: two 256-byte rows per float4 store), CTA = MT_CTA_W x MT_CTA_H rays
@@ -116,6 +117,7 @@ __global__ void __launch_bounds__(128, MT_CLOUD_MINBLOCKS) cloud_raymarch_kernel
         const int by = (int)blockIdx.y;
 #endif
         const int ltile = by / bpt;
+        doneSlot = ltile;
         const int tile = P.rows.tile_begin + ltile * P.rows.tile_stride;
         px = blockIdx.x * MT_CTA_W + lx;
         py = tile * P.rows.tile_rows + (by - ltile * bpt) * MT_CTA_H + ly;
@@ -153,6 +155,11 @@ __global__ void __launch_bounds__(128, MT_CLOUD_MINBLOCKS) cloud_raymarch_kernel
         }
         reinterpret_cast<float4*>(P.hdr)[idx] = make_float4(hdr.x, hdr.y, hdr.z, hdr.w);
         reinterpret_cast<float4*>(P.mask)[idx] = make_float4(mask.x, mask.y, mask.z, mask.w);
+    }
+    if (FULL && !COUNT && !DEBUG && P.tileDone) {  // uniform: tell tile_forward_kernel that this CTA's pixels are in memory
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) atomicAdd(P.tileDone + doneSlot, 1u);
     }
     if (COUNT) {
         unsigned v[6] = { cnt.rays, cnt.marched, cnt.steps, cnt.incloud, cnt.cone, cnt.early };
@@ -398,6 +405,51 @@ cudaError_t mt_launch_cloud_sixteenth_split(const CloudParams& P0, cudaStream_t 
     *launches = 3;
 #endif
     cloud_fold_kernel<<<ctas, 128, 0, stream>>>(P);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Gather by forwarding (mtSetCloudForward): the march kernel keeps its stores local -- a marching warp never waits on
+// NVLink -- and counts finished CTAs per row tile; this small kernel, launched on a high-priority stream beside it,
+// waits for each of its tiles to complete and pushes it into the peer image with 16-byte loads / stores.  A handful of
+// CTAs is enough: a rank moves ~66 MB of an 8K frame in the ~2.5 ms its share takes to march.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tile_forward_kernel(const float4* __restrict__ src, float4* __restrict__ dst, int W, int H,
+                                                           RowTiles rows, const unsigned* tileDone, unsigned ctasPerTile)
+{
+    for (int lt = blockIdx.x; lt < rows.tile_count; lt += gridDim.x) {
+        if (threadIdx.x == 0) {
+            const volatile unsigned* done = tileDone + lt;
+            while (*done < ctasPerTile) __nanosleep(256);
+            __threadfence();
+        }
+        __syncthreads();
+        const size_t tile = (size_t)rows.tile_begin + (size_t)lt * (size_t)rows.tile_stride;
+        const size_t r0 = tile * (size_t)rows.tile_rows;
+        const size_t r1 = r0 + (size_t)rows.tile_rows < (size_t)H ? r0 + (size_t)rows.tile_rows : (size_t)H;
+        const float4* s = src + r0 * (size_t)W;
+        float4* d = dst + r0 * (size_t)W;
+        const size_t n = (r1 - r0) * (size_t)W;
+        for (size_t i = threadIdx.x; i < n; i += 1024) {  // four independent 16-byte loads in flight per thread
+            float4 v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (i + 256 * j < n) v[j] = __ldcg(s + i + 256 * j);  // L2: the pixels were written by other SMs
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (i + 256 * j < n) d[i + 256 * j] = v[j];
+        }
+        __syncthreads();
+    }
+}
+
+cudaError_t mt_launch_tile_forward(const void* src, void* dst, int W, int H, const RowTiles& rows, const unsigned* tileDone,
+                                   int ctas, cudaStream_t stream)
+{
+    if (rows.tile_count <= 0) return cudaSuccess;
+    const unsigned ctasPerTile = (unsigned)((W + MT_CTA_W - 1) / MT_CTA_W) * (unsigned)(rows.tile_rows / MT_CTA_H);
+    const int grid = ctas < rows.tile_count ? ctas : rows.tile_count;
+    tile_forward_kernel<<<grid, 256, 0, stream>>>((const float4*)src, (float4*)dst, W, H, rows, tileDone, ctasPerTile);
     return cudaGetLastError();
 }
 

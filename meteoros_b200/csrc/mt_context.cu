@@ -23,6 +23,11 @@ struct MtContext {
     uint32_t flags = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copyStream = nullptr;   // mtReadImageAsync
+    cudaStream_t fwdStream = nullptr;    // mtSetCloudForward: high-priority stream of tile_forward_kernel
+    cudaEvent_t fwdArmEv = nullptr, fwdDoneEv = nullptr;
+    void* forwardHdr = nullptr;          //   peer image the finished row tiles are pushed to (NULL = off)
+    unsigned* tileDone = nullptr;        //   per-tile completion counters
+    bool fwdBusy = false;
     cudaEvent_t producedEv = nullptr;    // main stream -> copy stream
     struct PendingRead { const void* dev; cudaEvent_t done; bool active; } pending[4] = {};
     F4* hdr[2] = { nullptr, nullptr };
@@ -229,6 +234,10 @@ void mtDestroy(MtContext* c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->copyStream) { cudaStreamSynchronize(c->copyStream); cudaStreamDestroy(c->copyStream); }
+    if (c->fwdStream) { cudaStreamSynchronize(c->fwdStream); cudaStreamDestroy(c->fwdStream); }
+    if (c->fwdArmEv) cudaEventDestroy(c->fwdArmEv);
+    if (c->fwdDoneEv) cudaEventDestroy(c->fwdDoneEv);
+    cudaFree(c->tileDone);
     if (c->producedEv) cudaEventDestroy(c->producedEv);
     for (auto& p : c->pending)
         if (p.done) cudaEventDestroy(p.done);
@@ -458,6 +467,20 @@ static MtStatus cloud_dispatch(MtContext* c, int full, const RowTiles* tiles, bo
     MT_CUDA(c, mt_launch_cloud_setup(P, c->mc, c->stream));
     pass_begin(c, MT_PASS_CLOUD);
     int n = 1;
+    // gather by forwarding: full-quality row-tile launches keep their stores local and a side kernel pushes finished tiles
+    const bool forward = full && tiles && c->forwardHdr && !debug && !P.counters && !c->outHdr;
+    P.tileDone = nullptr;
+    if (forward) {
+        if (c->fwdBusy) MT_CUDA(c, cudaStreamWaitEvent(c->stream, c->fwdDoneEv, 0));  // the previous frame's tiles have left
+        MT_CUDA(c, cudaMemsetAsync(c->tileDone, 0, (size_t)P.rows.tile_count * sizeof(unsigned), c->stream));
+        MT_CUDA(c, cudaEventRecord(c->fwdArmEv, c->stream));
+        MT_CUDA(c, cudaStreamWaitEvent(c->fwdStream, c->fwdArmEv, 0));
+        MT_CUDA(c, mt_launch_tile_forward(P.hdr, c->forwardHdr, c->W, c->H, P.rows, c->tileDone, 8, c->fwdStream));
+        MT_CUDA(c, cudaEventRecord(c->fwdDoneEv, c->fwdStream));
+        c->fwdBusy = true;
+        P.tileDone = c->tileDone;
+        n = 2;
+    }
     if (split) MT_CUDA(c, mt_launch_cloud_sixteenth_split(P, c->stream, &n));
     else MT_CUDA(c, mt_launch_cloud(P, c->stream));
     pass_end(c, MT_PASS_CLOUD);
@@ -643,6 +666,8 @@ MtStatus mtSynchronize(MtContext* c)
     MT_CUDA(c, cudaSetDevice(c->device));
     MT_CUDA(c, cudaStreamSynchronize(c->stream));
     MT_CUDA(c, cudaStreamSynchronize(c->copyStream));
+    if (c->fwdStream) MT_CUDA(c, cudaStreamSynchronize(c->fwdStream));
+    c->fwdBusy = false;
     for (auto& p : c->pending) p.active = false;
     return MT_OK;
 }
@@ -712,6 +737,7 @@ MtStatus mtJoinCopies(MtContext* c)
     MT_CUDA(c, cudaSetDevice(c->device));
     MT_CUDA(c, cudaEventRecord(c->producedEv, c->copyStream));
     MT_CUDA(c, cudaStreamWaitEvent(c->stream, c->producedEv, 0));
+    if (c->fwdBusy) MT_CUDA(c, cudaStreamWaitEvent(c->stream, c->fwdDoneEv, 0));  // the tile forwarder of the last dispatch
     return MT_OK;
 }
 MtStatus mtWriteImage(MtContext* c, MtImage which, const void* host, size_t bytes)
@@ -749,6 +775,23 @@ MtStatus mtSetCloudOutput(MtContext* c, void* hdr, void* mask)
     if (!c) return MT_ERR_INVALID;
     c->outHdr = (F4*)hdr;
     c->outMask = (F4*)mask;
+    return MT_OK;
+}
+MtStatus mtSetCloudForward(MtContext* c, void* peer_hdr)
+{
+    if (!c) return MT_ERR_INVALID;
+    MT_CUDA(c, cudaSetDevice(c->device));
+    if (peer_hdr && !c->fwdStream) {
+        int lo = 0, hi = 0;
+        MT_CUDA(c, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        MT_CUDA(c, cudaStreamCreateWithPriority(&c->fwdStream, cudaStreamNonBlocking, hi));  // its few CTAs go first when a slot frees
+        MT_CUDA(c, cudaEventCreateWithFlags(&c->fwdArmEv, cudaEventDisableTiming));
+        MT_CUDA(c, cudaEventCreateWithFlags(&c->fwdDoneEv, cudaEventDisableTiming));
+        MT_CUDA(c, cudaMalloc((void**)&c->tileDone, ((size_t)c->H / 8 + 2) * sizeof(unsigned)));
+    }
+    if (c->fwdStream) MT_CUDA(c, cudaStreamSynchronize(c->fwdStream));
+    c->fwdBusy = false;
+    c->forwardHdr = peer_hdr;
     return MT_OK;
 }
 MtStatus mtExportImageHandle(MtContext* c, MtImage which, uint8_t handle[64])

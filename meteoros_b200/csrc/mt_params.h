@@ -85,6 +85,7 @@ struct CloudParams {
     unsigned* items;               // compacted in-cloud (step, ray) pairs: step << 26 | ray, in no particular order
     unsigned* itemCount;           // how many of them (zeroed by cloud_rays_kernel, filled by cloud_base_kernel)
     int rayStride;                 // rays per sample slice = 128 * CTAs of the ray grid
+    unsigned* tileDone;            // full-quality row-tile launches with forwarding (mtSetCloudForward): CTAs finished per tile
 };
 
 struct ReprojParams {

@@ -278,6 +278,41 @@ def test_cloud_output_redirect_and_ipc_roundtrip(api, noise):
         assert len(a.export_image_handle(api.IMAGE_CLOUD_CUR)) == 64
 
 
+@pytest.mark.parametrize("w,h,tile_rows", [(480, 270, 8), (322, 182, 16), (1920, 1080, 8)])
+def test_cloud_forward_pushes_finished_tiles(api, noise, w, h, tile_rows):
+    """mtSetCloudForward: the march kernel stores locally and counts finished CTAs per row tile; the side kernel pushes each
+    finished tile to the "peer" image (here a second context's image on the same device).  Three frames in a row, then
+    every other tile only: the destination receives exactly the dispatched tiles, bit-identical to one full launch."""
+    from meteoros_b200 import sharding
+
+    cam, tm, _, tun = default_scene(w, h, frame_id=2, total_time=4.0, yaw=5.0)
+    n = sharding.num_tiles(h, tile_rows)
+    with make_renderer(api, noise, w, h) as a, make_renderer(api, noise, w, h) as b:
+        for r in (a, b):
+            r.set_camera(cam); r.set_time(tm)
+        a.dispatch_cloud_full()
+        want = a.read_image(api.IMAGE_CLOUD_CUR)
+        b.set_cloud_forward(a.image_device_ptr(api.IMAGE_CLOUD_PREV))
+        for _ in range(3):
+            b.dispatch_cloud_tiles(tile_rows, 0, n, 1)
+        b.join_copies()
+        b.synchronize()
+        assert np.array_equal(a.read_image(api.IMAGE_CLOUD_PREV), want)
+        assert np.array_equal(b.read_image(api.IMAGE_CLOUD_CUR), want)      # the stores stayed local as well
+        a.clear_images(); b.clear_images()
+        b.dispatch_cloud_tiles(tile_rows, 1, n, 2)                          # odd tiles only
+        b.synchronize()
+        got = a.read_image(api.IMAGE_CLOUD_PREV)
+        for t in range(n):
+            r0, r1 = sharding.rows_of_tile(h, tile_rows, t)
+            assert np.array_equal(got[r0:r1], want[r0:r1]) if t % 2 else not got[r0:r1].any()
+        b.set_cloud_forward(None)
+        a.clear_images()
+        b.dispatch_cloud_tiles(tile_rows, 0, n, 1)
+        b.synchronize()
+        assert not a.read_image(api.IMAGE_CLOUD_PREV).any()                 # off again: nothing leaves the context
+
+
 def test_reprojection_indices_and_image(api, oracle_mod):
     from meteoros_b200 import scene
 

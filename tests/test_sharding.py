@@ -58,6 +58,9 @@ class StubRenderer:
     def set_cloud_output(self, hdr, mask):
         self.output = (hdr, mask)
 
+    def set_cloud_forward(self, hdr):
+        self.calls.append(("forward", hdr))
+
     def dispatch_cloud_tiles(self, tile_rows, begin, end, stride):
         self.calls.append(("tiles", tile_rows, begin, end, stride))
 
@@ -81,7 +84,13 @@ def _worker(rank, world, port, q):
         sf.finish()
         out_during = r.output
         sf.close()
-        q.put((rank, r.calls, out_during, r.output))
+        # gather by forwarding: stores stay local, the peer image is handed to the side kernel instead
+        r2 = StubRenderer(rank, 270)
+        sf2 = sharding.ShardedFrame(r2, dist, tile_rows=16, with_mask=False, mode="forward")
+        sf2.dispatch()
+        sf2.finish()
+        sf2.close()
+        q.put((rank, r.calls + [("second",)] + r2.calls + [("out2", r2.output)], out_during, r.output))
     finally:
         dist.destroy_process_group()
 
@@ -114,3 +123,10 @@ def test_sharded_frame_handle_exchange_gloo():
     assert ("close", 0x1000) in calls1 and ("close", 0x3000) in calls1
     n = sharding.num_tiles(270, 16)
     assert ("tiles", 16, 0, n, 2) in calls0 and ("tiles", 16, 1, n, 2) in calls1
+    # forward mode: rank 1 arms the forwarder with rank 0's HDR image, never redirects its stores, disarms on close
+    second1 = calls1[calls1.index(("second",)):]
+    assert ("forward", 0x1000) in second1 and second1.index(("forward", 0x1000)) < second1.index(("tiles", 16, 1, n, 2))
+    assert ("forward", None) in second1 and ("out2", (None, None)) in second1
+    assert not any(c[0] == "forward" for c in calls0)
+    with pytest.raises(ValueError):
+        sharding.ShardedFrame(StubRenderer(0, 270), None, with_mask=True, mode="forward")

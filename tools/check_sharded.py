@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Multi-GPU correctness check (run under torchrun with 2+ ranks): the row-tile sharded frame gathered on rank 0 --
-by kernel peer stores and by copy-engine pushes -- must be bit-identical to the single-GPU frame."""
+by kernel peer stores, by copy-engine pushes and by the tile-forwarding side kernel -- must be bit-identical to the
+single-GPU frame.  Each mode runs three frames in a row so that frame-to-frame hazards would show."""
 import os
 import sys
 from pathlib import Path
@@ -19,14 +20,15 @@ w, h = 1920, 1080
 cam, sc = scene.Camera(w, h), scene.Scene()
 sc.update_time(1 / 60)
 ok = True
-for mode in ("peer_store", "copy"):
-    for with_mask in (True, False):
+for mode in ("peer_store", "copy", "forward"):
+    for with_mask in ((False,) if mode == "forward" else (True, False)):
         with api.CloudRenderer(w, h, device=local) as r:
             r.upload_noise(textures.load_noise())
             r.set_camera(cam.ubo()); r.set_time(sc.ubo())
             sf = sharding.ShardedFrame(r, dist, tile_rows=8, with_mask=with_mask, mode=mode)
-            sf.dispatch()
-            sf.finish()
+            for _ in range(3):
+                sf.dispatch()
+                sf.finish()
             if rank == 0:
                 got_hdr, got_mask = r.read_image(api.IMAGE_CLOUD_CUR), r.read_image(api.IMAGE_GODRAY_MASK)
             sf.close()
