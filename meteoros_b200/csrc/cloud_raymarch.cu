@@ -414,16 +414,25 @@ cudaError_t mt_launch_cloud_sixteenth_split(const CloudParams& P0, cudaStream_t 
 // waits for each of its tiles to complete and pushes it into the peer image with 16-byte loads / stores.  A handful of
 // CTAs is enough: a rank moves ~66 MB of an 8K frame in the ~2.5 ms its share takes to march.
 // ---------------------------------------------------------------------------------------------------------------------
+//
+// The wait is bounded (~seconds): should the march kernel never run beside this one, the kernel flags the overrun in
+// the word after the last counter and leaves instead of hanging the device; mtSynchronize reports it.
+#define MT_FORWARD_MAX_POLLS (1u << 24)
 __global__ void __launch_bounds__(256) tile_forward_kernel(const float4* __restrict__ src, float4* __restrict__ dst, int W, int H,
-                                                           RowTiles rows, const unsigned* tileDone, unsigned ctasPerTile)
+                                                           RowTiles rows, unsigned* tileDone, unsigned ctasPerTile)
 {
+    __shared__ int timedOut;
     for (int lt = blockIdx.x; lt < rows.tile_count; lt += gridDim.x) {
         if (threadIdx.x == 0) {
             const volatile unsigned* done = tileDone + lt;
-            while (*done < ctasPerTile) __nanosleep(256);
+            unsigned polls = 0;
+            while (*done < ctasPerTile && polls < MT_FORWARD_MAX_POLLS) { __nanosleep(256); ++polls; }
+            timedOut = *done < ctasPerTile;
+            if (timedOut) atomicExch(tileDone + rows.tile_count, 1u);
             __threadfence();
         }
         __syncthreads();
+        if (timedOut) return;
         const size_t tile = (size_t)rows.tile_begin + (size_t)lt * (size_t)rows.tile_stride;
         const size_t r0 = tile * (size_t)rows.tile_rows;
         const size_t r1 = r0 + (size_t)rows.tile_rows < (size_t)H ? r0 + (size_t)rows.tile_rows : (size_t)H;
@@ -443,7 +452,7 @@ __global__ void __launch_bounds__(256) tile_forward_kernel(const float4* __restr
     }
 }
 
-cudaError_t mt_launch_tile_forward(const void* src, void* dst, int W, int H, const RowTiles& rows, const unsigned* tileDone,
+cudaError_t mt_launch_tile_forward(const void* src, void* dst, int W, int H, const RowTiles& rows, unsigned* tileDone,
                                    int ctas, cudaStream_t stream)
 {
     if (rows.tile_count <= 0) return cudaSuccess;

@@ -28,6 +28,8 @@ struct MtContext {
     void* forwardHdr = nullptr;          //   peer image the finished row tiles are pushed to (NULL = off)
     unsigned* tileDone = nullptr;        //   per-tile completion counters
     bool fwdBusy = false;
+    bool fwdCheck = false;               //   a forwarder ran since the last mtSynchronize: read its overrun flag there
+    int fwdTiles = 0;
     cudaEvent_t producedEv = nullptr;    // main stream -> copy stream
     struct PendingRead { const void* dev; cudaEvent_t done; bool active; } pending[4] = {};
     F4* hdr[2] = { nullptr, nullptr };
@@ -122,6 +124,9 @@ static void free_images(MtContext* c)
     c->ldr[0] = c->ldr[1] = c->ldrScratch = nullptr;
     cudaFree(c->debug); cudaFree(c->taps); cudaFree(c->maskDecoded); cudaFree(c->rays); cudaFree(c->samples); cudaFree(c->ctaSteps);
     cudaFree(c->items); cudaFree(c->itemCount);
+    if (c->fwdStream) cudaStreamSynchronize(c->fwdStream);
+    cudaFree(c->tileDone);
+    c->tileDone = nullptr; c->fwdBusy = false; c->fwdCheck = false;
     c->maskDecoded = nullptr; c->rays = nullptr; c->samples = nullptr; c->ctaSteps = nullptr; c->items = nullptr; c->itemCount = nullptr;
     c->hdr[0] = c->hdr[1] = c->mask = nullptr;
     c->debug = nullptr; c->taps = nullptr;
@@ -234,10 +239,9 @@ void mtDestroy(MtContext* c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->copyStream) { cudaStreamSynchronize(c->copyStream); cudaStreamDestroy(c->copyStream); }
-    if (c->fwdStream) { cudaStreamSynchronize(c->fwdStream); cudaStreamDestroy(c->fwdStream); }
+    if (c->fwdStream) { cudaStreamSynchronize(c->fwdStream); cudaStreamDestroy(c->fwdStream); c->fwdStream = nullptr; }
     if (c->fwdArmEv) cudaEventDestroy(c->fwdArmEv);
     if (c->fwdDoneEv) cudaEventDestroy(c->fwdDoneEv);
-    cudaFree(c->tileDone);
     if (c->producedEv) cudaEventDestroy(c->producedEv);
     for (auto& p : c->pending)
         if (p.done) cudaEventDestroy(p.done);
@@ -471,18 +475,25 @@ static MtStatus cloud_dispatch(MtContext* c, int full, const RowTiles* tiles, bo
     const bool forward = full && tiles && c->forwardHdr && !debug && !P.counters && !c->outHdr;
     P.tileDone = nullptr;
     if (forward) {
+        if (!c->tileDone) MT_CUDA(c, cudaMalloc((void**)&c->tileDone, ((size_t)c->H / 8 + 2) * sizeof(unsigned)));  // freed by mtResize
         if (c->fwdBusy) MT_CUDA(c, cudaStreamWaitEvent(c->stream, c->fwdDoneEv, 0));  // the previous frame's tiles have left
-        MT_CUDA(c, cudaMemsetAsync(c->tileDone, 0, (size_t)P.rows.tile_count * sizeof(unsigned), c->stream));
+        MT_CUDA(c, cudaMemsetAsync(c->tileDone, 0, ((size_t)P.rows.tile_count + 1) * sizeof(unsigned), c->stream));
         MT_CUDA(c, cudaEventRecord(c->fwdArmEv, c->stream));
-        MT_CUDA(c, cudaStreamWaitEvent(c->fwdStream, c->fwdArmEv, 0));
-        MT_CUDA(c, mt_launch_tile_forward(P.hdr, c->forwardHdr, c->W, c->H, P.rows, c->tileDone, 8, c->fwdStream));
-        MT_CUDA(c, cudaEventRecord(c->fwdDoneEv, c->fwdStream));
-        c->fwdBusy = true;
         P.tileDone = c->tileDone;
         n = 2;
     }
     if (split) MT_CUDA(c, mt_launch_cloud_sixteenth_split(P, c->stream, &n));
     else MT_CUDA(c, mt_launch_cloud(P, c->stream));
+    if (forward) {
+        // Submitted AFTER the march kernel it waits on: streams can share a hardware work queue (CUDA_DEVICE_MAX_CONNECTIONS),
+        // and a spinning kernel queued ahead of the kernel that feeds it would then never be fed.
+        MT_CUDA(c, cudaStreamWaitEvent(c->fwdStream, c->fwdArmEv, 0));
+        MT_CUDA(c, mt_launch_tile_forward(P.hdr, c->forwardHdr, c->W, c->H, P.rows, c->tileDone, 8, c->fwdStream));
+        MT_CUDA(c, cudaEventRecord(c->fwdDoneEv, c->fwdStream));
+        c->fwdBusy = true;
+        c->fwdCheck = true;
+        c->fwdTiles = P.rows.tile_count;
+    }
     pass_end(c, MT_PASS_CLOUD);
     c->launches += 1 + (uint64_t)n;
     return MT_OK;
@@ -669,6 +680,12 @@ MtStatus mtSynchronize(MtContext* c)
     if (c->fwdStream) MT_CUDA(c, cudaStreamSynchronize(c->fwdStream));
     c->fwdBusy = false;
     for (auto& p : c->pending) p.active = false;
+    if (c->fwdCheck) {
+        c->fwdCheck = false;
+        unsigned overrun = 0;
+        MT_CUDA(c, cudaMemcpy(&overrun, c->tileDone + c->fwdTiles, sizeof(unsigned), cudaMemcpyDeviceToHost));
+        if (overrun) return fail(c, MT_ERR_CUDA, "mtSynchronize: the tile forwarder gave up waiting for the march kernel (tiles not delivered)");
+    }
     return MT_OK;
 }
 
@@ -787,7 +804,6 @@ MtStatus mtSetCloudForward(MtContext* c, void* peer_hdr)
         MT_CUDA(c, cudaStreamCreateWithPriority(&c->fwdStream, cudaStreamNonBlocking, hi));  // its few CTAs go first when a slot frees
         MT_CUDA(c, cudaEventCreateWithFlags(&c->fwdArmEv, cudaEventDisableTiming));
         MT_CUDA(c, cudaEventCreateWithFlags(&c->fwdDoneEv, cudaEventDisableTiming));
-        MT_CUDA(c, cudaMalloc((void**)&c->tileDone, ((size_t)c->H / 8 + 2) * sizeof(unsigned)));
     }
     if (c->fwdStream) MT_CUDA(c, cudaStreamSynchronize(c->fwdStream));
     c->fwdBusy = false;

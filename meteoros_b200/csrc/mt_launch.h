@@ -7,7 +7,7 @@
 
 cudaError_t mt_launch_cloud_setup(const CloudParams& P, MarchConst* out, cudaStream_t stream);
 cudaError_t mt_launch_cloud(const CloudParams& P, cudaStream_t stream);
-cudaError_t mt_launch_tile_forward(const void* src, void* dst, int W, int H, const RowTiles& rows, const unsigned* tileDone,
+cudaError_t mt_launch_tile_forward(const void* src, void* dst, int W, int H, const RowTiles& rows, unsigned* tileDone,
                                    int ctas, cudaStream_t stream);
 cudaError_t mt_launch_cloud_sixteenth_split(const CloudParams& P, cudaStream_t stream, int* launches);
 cudaError_t mt_launch_build_quads(const uint32_t* texels, int w, int h, int d, void* quads, cudaStream_t stream);
