@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """TEST INFRASTRUCTURE -- mechanical GLSL 4.50 -> C++ rewrite of the reference's shaders, so that g++ compiles the
 reference's OWN shader text (read from /root/reference at build time, never copied into this repo) against glm, the
-GLSL-semantics vector library the reference itself vendors.  oracle/Makefile target `refshaders` runs this and builds
-oracle/_ref/libmeteoros_refshaders.so; oracle/glsl_rt.h supplies what a Vulkan device would: samplers, storage
+GLSL-semantics vector library the reference itself vendors.  oracle/Makefile target `refshaders` runs this into a
+scratch directory under /tmp (removed after the compile) and builds oracle/_ref/libmeteoros_refshaders.so; oracle/glsl_rt.h supplies what a Vulkan device would: samplers, storage
 images, gl_GlobalInvocationID, the dispatch loop.
 
 The rewrite is token-level and changes no expression:
@@ -82,5 +82,5 @@ if __name__ == "__main__":
     with open(shader, encoding="utf-8-sig", errors="replace") as f:
         text = rewrite(f.read(), weather="--revive-weather" in sys.argv)
     with open(out, "w") as f:
-        f.write(f"// GENERATED by oracle/glsl2cpp.py from {shader} -- build artefact, git-ignored, do not commit.\n")
+        f.write(f"// GENERATED by oracle/glsl2cpp.py from {shader} -- scratch build input, never to be committed.\n")
         f.write(text)

@@ -8,9 +8,9 @@
 namespace {
 #ifdef MTREF_WEATHER
 float mt_weather_scale = 1.0f;
-#include "_ref/gen/cloudRayMarch.weather.inc"
+#include "cloudRayMarch.weather.inc"
 #else
-#include "_ref/gen/cloudRayMarch.comp.inc"
+#include "cloudRayMarch.comp.inc"
 #endif
 }
 #undef E

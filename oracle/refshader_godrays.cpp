@@ -4,7 +4,7 @@
 #include "glsl_rt.h"
 
 namespace {
-#include "_ref/gen/postProcess_GodRays.frag.inc"
+#include "postProcess_GodRays.frag.inc"
 }
 
 extern "C" int mtrefsh_godrays(const void* camera152, const void* sky52, int W, int H, const float* mask, float* hdr)

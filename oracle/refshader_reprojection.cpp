@@ -3,7 +3,7 @@
 #include "glsl_rt.h"
 
 namespace {
-#include "_ref/gen/reprojection.comp.inc"
+#include "reprojection.comp.inc"
 }
 
 extern "C" int mtrefsh_reproject(const void* camera152, const void* cameraOld152, const void* time76, int W, int H, float* prev, float* cur)

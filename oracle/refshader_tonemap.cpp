@@ -4,7 +4,7 @@
 #include "glsl_rt.h"
 
 namespace {
-#include "_ref/gen/postProcess_ToneMap.frag.inc"
+#include "postProcess_ToneMap.frag.inc"
 }
 
 extern "C" int mtrefsh_tonemap(const void* time76, int W, int H, const float* hdr, uint8_t* ldr, float* ldr_f32)

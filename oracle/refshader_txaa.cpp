@@ -4,7 +4,7 @@
 #include "glsl_rt.h"
 
 namespace {
-#include "_ref/gen/postProcess_TXAA.frag.inc"
+#include "postProcess_TXAA.frag.inc"
 }
 
 extern "C" int mtrefsh_txaa(const void* camera152, const void* cameraOld152, const void* time76, int W, int H, const uint8_t* cur,
