@@ -176,3 +176,42 @@ def test_kernel_cores_against_the_reference_shaders_directly(noise):
     assert np.array_equal(hostsim.tonemap(tm, want["hdr"]), ldr)
     hist = np.roll(ldr, 3, axis=1)
     assert np.array_equal(hostsim.txaa(cam, old, tm, ldr, hist), refshaders.txaa(cam, old, tm, ldr, hist))
+
+
+def test_randomised_scenes_all_five_shaders(oracle_mod, noise):
+    """Forty random cameras (position inside, between and above the shells, any heading, fov 20..100 degrees), frame
+    ids, times and window sizes: the oracle against the reference shader text, every pass, byte for byte."""
+    from meteoros_b200 import scene
+
+    rng = np.random.default_rng(2024)
+    marched = 0
+    for trial in range(40):
+        w, h = int(rng.integers(9, 70)), int(rng.integers(9, 50))
+        eye = (float(rng.uniform(-3e3, 3e3)), float(-rng.choice([0.0, 10.0, 5e3, 7.4e3, 9e3, 1.9e4, 3e4])), float(rng.uniform(-3e3, 3e3)))
+        cam = scene.Camera(w, h, eye=eye, ref=(eye[0], eye[1], eye[2] - 1.0), fovy=float(rng.uniform(20.0, 100.0)))
+        cam.rotate_about_up(float(rng.uniform(-180.0, 180.0)))
+        cam.rotate_about_right(float(rng.uniform(-60.0, 85.0)))
+        old = cam.ubo()
+        cam.rotate_about_up(float(rng.uniform(-3.0, 3.0)))
+        cam.translate_along_look(float(rng.uniform(-50.0, 50.0)))
+        new = cam.ubo()
+        sc, sky, tun = scene.Scene(), scene.Sky().ubo(), scene.default_tuning()
+        sc.time["time"] = (0.016, float(rng.uniform(0.0, 500.0)))
+        sc.time["frameCountMod16"] = int(rng.integers(0, 16))
+        tm = sc.ubo()
+        prev = rng.random((h, w, 4), dtype=np.float32)
+        cur_ref = refshaders.reproject(new, old, tm, prev)
+        assert np.array_equal(oracle_mod.reproject(new, old, tm, prev), cur_ref, equal_nan=True), trial
+        mask_ref = np.zeros((h, w, 4), np.float32)
+        hdr_o, mask_o = cur_ref.copy(), mask_ref.copy()
+        refshaders.cloud(new, tm, sky, noise, w, h, hdr=cur_ref, mask=mask_ref)
+        r = oracle_mod.cloud(new, tm, tun, noise, w, h, full=False, hdr=hdr_o, mask=mask_o, counters=True)
+        marched += r["counters"]["rays_marched"]
+        assert np.array_equal(hdr_o, cur_ref, equal_nan=True) and np.array_equal(mask_o, mask_ref, equal_nan=True), trial
+        lit_ref = refshaders.godrays(new, sky, mask_ref, cur_ref)
+        assert np.array_equal(oracle_mod.godrays(new, sky, mask_ref, cur_ref), lit_ref, equal_nan=True), trial
+        ldr_ref = refshaders.tonemap(tm, lit_ref)
+        assert np.array_equal(oracle_mod.tonemap(tm, lit_ref), ldr_ref), trial
+        hist = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+        assert np.array_equal(oracle_mod.txaa(new, old, tm, ldr_ref, hist), refshaders.txaa(new, old, tm, ldr_ref, hist)), trial
+    assert marched > 1000       # the sweep did march clouds, not only ocean and sky
