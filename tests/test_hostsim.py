@@ -144,3 +144,40 @@ def test_cloud_core_weather_path_bit_identical(oracle_mod, noise, hostsim, scale
     base = oracle_mod.cloud(cam, tm, tun, noise, w, h, full=True, debug=True)
     assert not np.array_equal(base["debug"]["accum"], ref["debug"]["accum"])
     assert (ref["debug"]["accum"] > 0).mean() > 0.02
+
+
+def test_randomised_scenes_kernel_cores(oracle_mod, noise, hostsim):
+    """Sixty random cameras -- eye inside, between and above the cloud shells, any heading, fov 20..100 degrees -- frame
+    ids, times and window sizes: the kernels' per-pixel cores against the oracle (which tests/test_reference_shaders.py holds
+    to the reference's shader text on the same kind of sweep)."""
+    from meteoros_b200 import scene
+
+    rng = np.random.default_rng(77)
+    marched = 0
+    for trial in range(60):
+        w, h = int(rng.integers(9, 70)), int(rng.integers(9, 50))
+        ey = float(-rng.choice([0.0, 10.0, 5e3, 7.4e3, 7.6e3, 9e3, 1.9e4, 2.1e4, 3e4]))
+        eye = (float(rng.uniform(-3e3, 3e3)), ey, float(rng.uniform(-3e3, 3e3)))
+        cam = scene.Camera(w, h, eye=eye, ref=(eye[0], eye[1], eye[2] - 1.0), fovy=float(rng.uniform(20.0, 100.0)))
+        cam.rotate_about_up(float(rng.uniform(-180.0, 180.0)))
+        cam.rotate_about_right(float(rng.uniform(-60.0, 85.0)))
+        old = cam.ubo()
+        cam.rotate_about_up(float(rng.uniform(-3.0, 3.0)))
+        cam.translate_along_look(float(rng.uniform(-50.0, 50.0)))
+        new = cam.ubo()
+        sc, tun = scene.Scene(), scene.default_tuning()
+        sc.time["time"] = (0.016, float(rng.uniform(0.0, 500.0)))
+        sc.time["frameCountMod16"] = int(rng.integers(0, 16))
+        tm = sc.ubo()
+        ref = oracle_mod.cloud(new, tm, tun, noise, w, h, full=True, debug=True, counters=True)
+        hdr, mask, cnt, dbg = hostsim.cloud(new, tm, tun, noise, w, h, True, oracle_mod.RAY_DEBUG_DTYPE)
+        marched += cnt["rays_marched"]
+        assert cnt == ref["counters"], trial
+        assert np.array_equal(mask, ref["mask"], equal_nan=True) and np.array_equal(dbg["accum"], ref["debug"]["accum"], equal_nan=True), trial
+        assert np.allclose(hdr, ref["hdr"], rtol=2e-6, atol=0, equal_nan=True), trial
+        prev = rng.random((h, w, 4), dtype=np.float32)
+        assert np.array_equal(hostsim.reproject(new, old, tm, prev)[0], oracle_mod.reproject(new, old, tm, prev), equal_nan=True), trial
+        ldr = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+        hist = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+        assert np.array_equal(hostsim.txaa(new, old, tm, ldr, hist), oracle_mod.txaa(new, old, tm, ldr, hist)), trial
+    assert marched > 10000
