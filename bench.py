@@ -392,7 +392,10 @@ def main():
     # ---- end-to-end region: host uniforms in, finished frame out to pinned host memory, every step.  The read-back of
     # frame k runs on the context's copy stream while frame k+1 renders into the other ping-pong image (mtReadImageAsync).
     seq = args.workload == "seq1080p"
-    out_which = api.IMAGE_LDR_PREV if seq else api.IMAGE_CLOUD_PREV  # after the swap: the frame just finished
+    # after the swap: the frame just finished.  The sharded 8K frame does not swap: the peers store into the one image GPU 0
+    # exported, so every frame is gathered in, and read back from, IMAGE_CLOUD_CUR (the next dispatch waits for the read).
+    sharded = args.workload == "frame8k"
+    out_which = api.IMAGE_LDR_PREV if seq else (api.IMAGE_CLOUD_CUR if sharded else api.IMAGE_CLOUD_PREV)
     nbytes = w * h * (4 if seq else 16)
     pinned = [torch.empty(nbytes, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
     h2d = int(cam.nbytes + tm.nbytes + tun.nbytes + sky.nbytes)
@@ -404,7 +407,7 @@ def main():
         step()
         if args.workload == "frame8k" and world > 1:
             shard.finish()
-        if not seq:
+        if not seq and not sharded:
             r.swap_ping_pong()  # mtFrame swaps by itself
         if e2e_read:
             r.read_image_async(out_which, pinned[i & 1].data_ptr(), nbytes)
