@@ -215,9 +215,22 @@ MT_DEVICE TxaaFrame txaa_frame(const TxaaParams& P)
 struct C4 {
     float c[4];
 };
+// MT_TXAA_FAST (off by default: not yet timed on a GPU): bytes become floats without the quarter-rate conversion pipe --
+// __byte_perm builds 0x4B0000bb = 2^23 + b, subtracting 2^23 is exact -- and interior pixels skip the 13 bounds tests.
+// Same values, same order of operations: bit-identical by construction.
+#ifndef MT_TXAA_FAST
+#define MT_TXAA_FAST 0
+#endif
 MT_DEVICE C4 ldr_unpack(uint32_t t)
 {
     C4 r;
+#if MT_TXAA_FAST && !defined(MT_HOSTSIM)
+    r.c[0] = (__uint_as_float(__byte_perm(t, 0x4B000000u, 0x7650)) - 8388608.0f) * (1.0f / 255.0f);
+    r.c[1] = (__uint_as_float(__byte_perm(t, 0x4B000000u, 0x7651)) - 8388608.0f) * (1.0f / 255.0f);
+    r.c[2] = (__uint_as_float(__byte_perm(t, 0x4B000000u, 0x7652)) - 8388608.0f) * (1.0f / 255.0f);
+    r.c[3] = (__uint_as_float(__byte_perm(t, 0x4B000000u, 0x7653)) - 8388608.0f) * (1.0f / 255.0f);
+    return r;
+#endif
     r.c[0] = (float)(t & 0xffu) * (1.0f / 255.0f);
     r.c[1] = (float)((t >> 8) & 0xffu) * (1.0f / 255.0f);
     r.c[2] = (float)((t >> 16) & 0xffu) * (1.0f / 255.0f);
@@ -271,8 +284,14 @@ MT_DEVICE uint32_t txaa_pixel(const TxaaParams& P, const TxaaFrame& F, int x, in
 
     // 3x3 neighbourhood of the tone-mapped frame (order: tl tc tr ml mc mr bl bc br)
     C4 n[9];
+    if (MT_TXAA_FAST && x >= 1 && y >= 1 && x < P.W - 1 && y < P.H - 1) {  // interior: no bounds tests
+        const uint32_t* row = P.cur + ((unsigned)(y - 1) * (unsigned)P.W + (unsigned)(x - 1));
 #pragma unroll
-    for (int k = 0; k < 9; ++k) n[k] = ldr_load(P.cur, P.W, P.H, x + (k % 3) - 1, y + (k / 3) - 1);
+        for (int k = 0; k < 9; ++k) n[k] = ldr_unpack(MT_LDG(row + (unsigned)(k / 3) * (unsigned)P.W + (unsigned)(k % 3)));
+    } else {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) n[k] = ldr_load(P.cur, P.W, P.H, x + (k % 3) - 1, y + (k / 3) - 1);
+    }
     float cmin[4], cmax[4], cavg[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -297,8 +316,15 @@ MT_DEVICE uint32_t txaa_pixel(const TxaaParams& P, const TxaaFrame& F, int x, in
         const float fu = floorf(tu), fv = floorf(tv);
         const float ax = tu - fu, ay = tv - fv;
         const int x0 = mt_f2i(fu), y0 = mt_f2i(fv);
-        const C4 a = ldr_border_texel(P.prev, P.W, P.H, x0, y0), b = ldr_border_texel(P.prev, P.W, P.H, x0 + 1, y0);
-        const C4 c2 = ldr_border_texel(P.prev, P.W, P.H, x0, y0 + 1), d = ldr_border_texel(P.prev, P.W, P.H, x0 + 1, y0 + 1);
+        C4 a, b, c2, d;
+        if (MT_TXAA_FAST && x0 >= 0 && y0 >= 0 && x0 < P.W - 1 && y0 < P.H - 1) {  // all four texels inside the image
+            const uint32_t* q00 = P.prev + ((unsigned)y0 * (unsigned)P.W + (unsigned)x0);
+            a = ldr_unpack(MT_LDG(q00)); b = ldr_unpack(MT_LDG(q00 + 1));
+            c2 = ldr_unpack(MT_LDG(q00 + P.W)); d = ldr_unpack(MT_LDG(q00 + P.W + 1));
+        } else {
+            a = ldr_border_texel(P.prev, P.W, P.H, x0, y0); b = ldr_border_texel(P.prev, P.W, P.H, x0 + 1, y0);
+            c2 = ldr_border_texel(P.prev, P.W, P.H, x0, y0 + 1); d = ldr_border_texel(P.prev, P.W, P.H, x0 + 1, y0 + 1);
+        }
         const float w00 = (1.0f - ax) * (1.0f - ay), w01 = ax * (1.0f - ay), w10 = (1.0f - ax) * ay, w11 = ax * ay;
 #pragma unroll
         for (int c = 0; c < 4; ++c) prevc[c] = fmaf(w11, d.c[c], fmaf(w10, c2.c[c], fmaf(w01, b.c[c], w00 * a.c[c])));
