@@ -10,6 +10,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -33,6 +34,10 @@ bool read_file(const char* path, std::vector<uint8_t>& out)
 }
 
 // ---- TGA -----------------------------------------------------------------------------------------------------------
+// A malformed or hostile file must be rejected, never crash the host: dimensions are bounded, every allocation is bounded
+// by what the bytes actually present could decode to, and the C entry points catch whatever is left (bad_alloc).
+constexpr int MT_MAX_IMAGE_DIM = 16384;
+
 bool decode_tga(const uint8_t* d, size_t n, std::vector<uint8_t>& rgba, int& w, int& h)
 {
     if (n < 18) return false;
@@ -41,10 +46,15 @@ bool decode_tga(const uint8_t* d, size_t n, std::vector<uint8_t>& rgba, int& w, 
     h = d[14] | (d[15] << 8);
     const int bpp = d[16], desc = d[17];
     if (cmaptype != 0 || (type != 2 && type != 10) || (bpp != 24 && bpp != 32) || w <= 0 || h <= 0) return false;
+    if (w > MT_MAX_IMAGE_DIM || h > MT_MAX_IMAGE_DIM) return false;
     const int bytes = bpp / 8;
     size_t pos = 18 + (size_t)idlen;
-    rgba.assign((size_t)w * h * 4, 255);
     const size_t npix = (size_t)w * h;
+    if (pos > n) return false;
+    // raw: every pixel is in the file; RLE: a packet of 1 + bytes input bytes yields at most 128 pixels
+    const size_t avail = n - pos;
+    if (type == 2 ? npix * (size_t)bytes > avail : npix > (avail / (size_t)(1 + bytes) + 1) * 128) return false;
+    rgba.assign(npix * 4, 255);
     size_t i = 0;
     auto put = [&](size_t k, const uint8_t* px) {  // file order is BGR(A)
         const size_t row = k / w, col = k % w;
@@ -128,7 +138,7 @@ struct Huffman {
         return -1;
     }
 };
-bool inflate_raw(const uint8_t* src, size_t n, std::vector<uint8_t>& out)
+bool inflate_raw(const uint8_t* src, size_t n, std::vector<uint8_t>& out, size_t max_out)
 {
     static const uint16_t lbase[29] = { 3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258 };
     static const uint16_t lext[29] = { 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0 };
@@ -145,7 +155,7 @@ bool inflate_raw(const uint8_t* src, size_t n, std::vector<uint8_t>& out)
             if (br.pos + 4 > n) return false;
             const unsigned len = src[br.pos] | (src[br.pos + 1] << 8);
             br.pos += 4;
-            if (br.pos + len > n) return false;
+            if (br.pos + len > n || out.size() + len > max_out) return false;
             out.insert(out.end(), src + br.pos, src + br.pos + len);
             br.pos += len;
             continue;
@@ -190,8 +200,10 @@ bool inflate_raw(const uint8_t* src, size_t n, std::vector<uint8_t>& out)
         for (;;) {
             int sym = lit.decode(br);
             if (sym < 0 || !br.ok) return false;
-            if (sym < 256) out.push_back((uint8_t)sym);
-            else if (sym == 256) break;
+            if (sym < 256) {
+                if (out.size() >= max_out) return false;
+                out.push_back((uint8_t)sym);
+            } else if (sym == 256) break;
             else {
                 sym -= 257;
                 if (sym >= 29) return false;
@@ -199,7 +211,7 @@ bool inflate_raw(const uint8_t* src, size_t n, std::vector<uint8_t>& out)
                 const int ds = dist.decode(br);
                 if (ds < 0 || ds >= 30) return false;
                 const size_t d = dbase[ds] + br.bits(dext[ds]);
-                if (d > out.size()) return false;
+                if (d > out.size() || out.size() + len > max_out) return false;
                 const size_t start = out.size() - d;
                 for (size_t k = 0; k < len; ++k) out.push_back(out[start + k]);
             }
@@ -234,6 +246,7 @@ bool decode_png(const uint8_t* d, size_t n, std::vector<uint8_t>& rgba, int& w, 
         pos += 12 + (size_t)len;
     }
     if (!have_hdr || w <= 0 || h <= 0 || (depth != 8 && depth != 16)) return false;
+    if (w > MT_MAX_IMAGE_DIM || h > MT_MAX_IMAGE_DIM) return false;
     int chans;
     switch (ctype) {
         case 0: chans = 1; break;
@@ -243,11 +256,13 @@ bool decode_png(const uint8_t* d, size_t n, std::vector<uint8_t>& rgba, int& w, 
         default: return false;  // palette images are not used by the reference
     }
     if (z.size() < 6) return false;
-    std::vector<uint8_t> raw;
-    raw.reserve(((size_t)w * chans * (depth / 8) + 1) * h);
-    if (!inflate_raw(z.data() + 2, z.size() - 2, raw)) return false;  // skip the 2-byte zlib header; adler32 not checked
     const size_t bpp = (size_t)chans * (depth / 8), stride = (size_t)w * bpp;
-    if (raw.size() < (stride + 1) * (size_t)h) return false;
+    const size_t need = (stride + 1) * (size_t)h;
+    if (need / 1032 > z.size()) return false;  // deflate cannot expand by more than 1032:1: the pixels are not in this file
+    std::vector<uint8_t> raw;
+    raw.reserve(need);
+    if (!inflate_raw(z.data() + 2, z.size() - 2, raw, need)) return false;  // skip the 2-byte zlib header; adler32 not checked
+    if (raw.size() < need) return false;
     std::vector<uint8_t> prev(stride, 0), cur(stride);
     rgba.assign((size_t)w * h * 4, 255);
     for (int y = 0; y < h; ++y) {
@@ -304,84 +319,107 @@ bool decode_any(const char* path, std::vector<uint8_t>& rgba, int& w, int& h)
     return decode_png(file.data(), file.size(), rgba, w, h) || decode_tga(file.data(), file.size(), rgba, w, h);
 }
 
+// No exception may cross the C boundary: allocation failure becomes MT_ERR_OOM, anything else MT_ERR_INVALID.
+template <class F>
+MtStatus guarded(F&& body) noexcept
+{
+    try {
+        return body();
+    } catch (const std::bad_alloc&) {
+        return MT_ERR_OOM;
+    } catch (...) {
+        return MT_ERR_INVALID;
+    }
+}
+
 }  // namespace
 
 extern "C" {
 
 MtStatus mtxDecodeImage(const uint8_t* file_bytes, size_t n, int is_png, uint8_t* rgba8_out, size_t out_bytes, uint32_t* w, uint32_t* h)
 {
-    if (!file_bytes || !w || !h) return MT_ERR_INVALID;
-    std::vector<uint8_t> px;
-    int iw = 0, ih = 0;
-    const bool ok = is_png ? decode_png(file_bytes, n, px, iw, ih) : decode_tga(file_bytes, n, px, iw, ih);
-    if (!ok) return MT_ERR_INVALID;
-    *w = (uint32_t)iw;
-    *h = (uint32_t)ih;
-    if (rgba8_out) {
-        if (out_bytes < px.size()) return MT_ERR_INVALID;
-        std::memcpy(rgba8_out, px.data(), px.size());
-    }
-    return MT_OK;
+    return guarded([&]() -> MtStatus {
+        if (!file_bytes || !w || !h) return MT_ERR_INVALID;
+        std::vector<uint8_t> px;
+        int iw = 0, ih = 0;
+        const bool ok = is_png ? decode_png(file_bytes, n, px, iw, ih) : decode_tga(file_bytes, n, px, iw, ih);
+        if (!ok) return MT_ERR_INVALID;
+        *w = (uint32_t)iw;
+        *h = (uint32_t)ih;
+        if (rgba8_out) {
+            if (out_bytes < px.size()) return MT_ERR_INVALID;
+            std::memcpy(rgba8_out, px.data(), px.size());
+        }
+        return MT_OK;
+    });
 }
 
 MtStatus mtxLoadImageFile(const char* path, uint8_t* rgba8_out, size_t out_bytes, uint32_t* w, uint32_t* h)
 {
-    if (!path || !w || !h) return MT_ERR_INVALID;
-    std::vector<uint8_t> px;
-    int iw = 0, ih = 0;
-    if (!decode_any(path, px, iw, ih)) return MT_ERR_INVALID;
-    *w = (uint32_t)iw;
-    *h = (uint32_t)ih;
-    if (rgba8_out) {
-        if (out_bytes < px.size()) return MT_ERR_INVALID;
-        std::memcpy(rgba8_out, px.data(), px.size());
-    }
-    return MT_OK;
+    return guarded([&]() -> MtStatus {
+        if (!path || !w || !h) return MT_ERR_INVALID;
+        std::vector<uint8_t> px;
+        int iw = 0, ih = 0;
+        if (!decode_any(path, px, iw, ih)) return MT_ERR_INVALID;
+        *w = (uint32_t)iw;
+        *h = (uint32_t)ih;
+        if (rgba8_out) {
+            if (out_bytes < px.size()) return MT_ERR_INVALID;
+            std::memcpy(rgba8_out, px.data(), px.size());
+        }
+        return MT_OK;
+    });
 }
 
 MtStatus mtxLoadVolumeFromSlices(const char* folder, const char* base_name, const char* extension, uint32_t w, uint32_t h, uint32_t d,
                                  uint8_t* rgba8_out, size_t out_bytes)
 {
-    if (!folder || !base_name || !extension || !rgba8_out) return MT_ERR_INVALID;
-    const size_t slice = (size_t)w * h * 4;
-    if (out_bytes < slice * d) return MT_ERR_INVALID;
-    for (uint32_t z = 0; z < d; ++z) {  // ImageLoadingUtility.cpp:87-98
-        const std::string path = std::string(folder) + base_name + "(" + std::to_string(z + 1) + ")" + extension;
-        std::vector<uint8_t> px;
-        int iw = 0, ih = 0;
-        if (!decode_any(path.c_str(), px, iw, ih) || (uint32_t)iw != w || (uint32_t)ih != h) return MT_ERR_INVALID;
-        std::memcpy(rgba8_out + slice * z, px.data(), slice);
-    }
-    return MT_OK;
+    return guarded([&]() -> MtStatus {
+        if (!folder || !base_name || !extension || !rgba8_out) return MT_ERR_INVALID;
+        const size_t slice = (size_t)w * h * 4;
+        if (out_bytes < slice * d) return MT_ERR_INVALID;
+        for (uint32_t z = 0; z < d; ++z) {  // ImageLoadingUtility.cpp:87-98
+            const std::string path = std::string(folder) + base_name + "(" + std::to_string(z + 1) + ")" + extension;
+            std::vector<uint8_t> px;
+            int iw = 0, ih = 0;
+            if (!decode_any(path.c_str(), px, iw, ih) || (uint32_t)iw != w || (uint32_t)ih != h) return MT_ERR_INVALID;
+            std::memcpy(rgba8_out + slice * z, px.data(), slice);
+        }
+        return MT_OK;
+    });
 }
 
 // ".mtvol": "MTVOL001" + u32 w, h, d (little endian) + u32 reserved, then w*h*d*4 bytes of RGBA8.
 MtStatus mtxSaveVolume(const char* path, uint32_t w, uint32_t h, uint32_t d, const uint8_t* rgba8)
 {
-    if (!path || !rgba8 || !w || !h || !d) return MT_ERR_INVALID;
-    FILE* f = std::fopen(path, "wb");
-    if (!f) return MT_ERR_INVALID;
-    const uint32_t hdr[4] = { w, h, d, 0 };
-    const size_t n = (size_t)w * h * d * 4;
-    const bool ok = std::fwrite("MTVOL001", 1, 8, f) == 8 && std::fwrite(hdr, 4, 4, f) == 4 && std::fwrite(rgba8, 1, n, f) == n;
-    std::fclose(f);
-    return ok ? MT_OK : MT_ERR_INVALID;
+    return guarded([&]() -> MtStatus {
+        if (!path || !rgba8 || !w || !h || !d) return MT_ERR_INVALID;
+        FILE* f = std::fopen(path, "wb");
+        if (!f) return MT_ERR_INVALID;
+        const uint32_t hdr[4] = { w, h, d, 0 };
+        const size_t n = (size_t)w * h * d * 4;
+        const bool ok = std::fwrite("MTVOL001", 1, 8, f) == 8 && std::fwrite(hdr, 4, 4, f) == 4 && std::fwrite(rgba8, 1, n, f) == n;
+        std::fclose(f);
+        return ok ? MT_OK : MT_ERR_INVALID;
+    });
 }
 MtStatus mtxLoadVolume(const char* path, uint8_t* rgba8_out, size_t out_bytes, uint32_t* w, uint32_t* h, uint32_t* d)
 {
-    if (!path || !w || !h || !d) return MT_ERR_INVALID;
-    FILE* f = std::fopen(path, "rb");
-    if (!f) return MT_ERR_INVALID;
-    char magic[8];
-    uint32_t hdr[4];
-    bool ok = std::fread(magic, 1, 8, f) == 8 && !std::memcmp(magic, "MTVOL001", 8) && std::fread(hdr, 4, 4, f) == 4;
-    if (ok) {
-        *w = hdr[0]; *h = hdr[1]; *d = hdr[2];
-        const size_t n = (size_t)hdr[0] * hdr[1] * hdr[2] * 4;
-        if (rgba8_out) ok = out_bytes >= n && std::fread(rgba8_out, 1, n, f) == n;
-    }
-    std::fclose(f);
-    return ok ? MT_OK : MT_ERR_INVALID;
+    return guarded([&]() -> MtStatus {
+        if (!path || !w || !h || !d) return MT_ERR_INVALID;
+        FILE* f = std::fopen(path, "rb");
+        if (!f) return MT_ERR_INVALID;
+        char magic[8];
+        uint32_t hdr[4];
+        bool ok = std::fread(magic, 1, 8, f) == 8 && !std::memcmp(magic, "MTVOL001", 8) && std::fread(hdr, 4, 4, f) == 4;
+        if (ok) {
+            *w = hdr[0]; *h = hdr[1]; *d = hdr[2];
+            const size_t n = (size_t)hdr[0] * hdr[1] * hdr[2] * 4;
+            if (rgba8_out) ok = out_bytes >= n && std::fread(rgba8_out, 1, n, f) == n;
+        }
+        std::fclose(f);
+        return ok ? MT_OK : MT_ERR_INVALID;
+    });
 }
 
 }  // extern "C"

@@ -79,3 +79,55 @@ def test_volume_cache_roundtrip(tmp_path):
     assert lib.mtxLoadVolume(path, back.ctypes.data, back.nbytes, C.byref(w), C.byref(h), C.byref(d)) == 0
     assert np.array_equal(back, vol)
     assert lib.mtxLoadVolume(str(tmp_path / "missing.mtvol").encode(), None, 0, C.byref(w), C.byref(h), C.byref(d)) == 1
+
+
+def test_decoders_reject_malformed_files():
+    """Corrupt, truncated and hostile files (size fields of 2^31, pixel data missing, garbage deflate streams) must come
+    back as an error status -- never an exception across the C boundary, a crash or an unbounded allocation.
+    tools/fuzz_assets.cpp is the long-running ASan / UBSan version of this loop."""
+    from PIL import Image
+
+    lib = _lib.load()
+    rng = np.random.default_rng(1)
+
+    def enc(arr, fmt, **kw):
+        b = io.BytesIO()
+        Image.fromarray(arr).save(b, fmt, **kw)
+        return b.getvalue()
+
+    seeds = [(enc(rng.integers(0, 256, (9, 17, 4), dtype=np.uint8), "PNG"), 1), (enc(rng.integers(0, 256, (8, 8, 3), dtype=np.uint8), "PNG"), 1),
+             (enc(rng.integers(0, 256, (7, 5), dtype=np.uint8), "PNG"), 1),
+             (enc(rng.integers(0, 256, (16, 16, 4), dtype=np.uint8), "TGA", compression="tga_rle"), 0),
+             (enc(rng.integers(0, 256, (5, 9, 4), dtype=np.uint8), "TGA"), 0)]
+
+    def decode(data, is_png):
+        w, h = C.c_uint32(), C.c_uint32()
+        st = lib.mtxDecodeImage(data, len(data), is_png, None, 0, C.byref(w), C.byref(h))
+        if st != 0:
+            return st
+        assert w.value <= 16384 and h.value <= 16384
+        out = np.zeros((h.value, w.value, 4), np.uint8)
+        return lib.mtxDecodeImage(data, len(data), is_png, out.ctypes.data, out.nbytes, C.byref(w), C.byref(h))
+
+    # the case that used to abort the process: a PNG / TGA header announcing a 2^31-pixel-wide image
+    png = bytearray(seeds[0][0]); png[16:20] = (0x7F, 0xFF, 0xFF, 0xFF)
+    tga = bytearray(seeds[4][0]); tga[12:16] = (0xFF, 0xFF, 0xFF, 0xFF)
+    assert decode(bytes(png), 1) != 0 and decode(bytes(tga), 0) != 0
+    ok = 0
+    for it in range(4000):
+        data, is_png = seeds[it % len(seeds)]
+        b = bytearray(data)
+        mode = it % 4
+        if mode == 0:
+            for _ in range(int(rng.integers(1, 6))):
+                b[int(rng.integers(0, len(b)))] = int(rng.integers(0, 256))
+        elif mode == 1:
+            b = b[:int(rng.integers(0, len(b)))]
+        elif mode == 2:
+            i = int(rng.integers(0, len(b)))
+            b[i:i] = bytes(rng.integers(0, 256, int(rng.integers(1, 9)), dtype=np.uint8))
+        else:
+            i = int(rng.integers(0, max(1, len(b) - 4)))
+            b[i:i + 4] = int(rng.integers(0, 2**32)).to_bytes(4, "big")
+        ok += decode(bytes(b), is_png) == 0
+    assert 0 < ok < 4000          # some mutations only touch pixel data; most must be rejected cleanly
