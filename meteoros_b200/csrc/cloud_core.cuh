@@ -211,7 +211,8 @@ MT_DEVICE RaySetup cloud_ray_setup(const CloudParams& P, const MarchConst& M, in
     R.dir = dir;
     R.t_in = R.t_out = R.stepSize = R.lenToInner = R.cosAngle = R.phase = 0.0f;
     R.bg = mk3(0.0f, 0.0f, 0.0f);
-    R.pad[0] = R.pad[1] = R.pad[2] = 0;
+    R.nsteps = 0;
+    R.pad[0] = R.pad[1] = 0;
     const float dotUp = (0.0f * dir.x + 1.0f * dir.y) + 0.0f * dir.z;
     hdr.w = 1.0f;
     if (dotUp < 0.0f) {  // ocean (:718-729)
