@@ -458,7 +458,9 @@ static MtStatus cloud_dispatch(MtContext* c, int full, const RowTiles* tiles, bo
         MT_CUDA(c, cudaMalloc(&c->rays, nrays * 64));
         MT_CUDA(c, cudaMalloc((void**)&c->samples, nrays * 64 * sizeof(float2)));
         MT_CUDA(c, cudaMalloc((void**)&c->ctaSteps, (nrays / 128 + 1) * sizeof(int)));
-        MT_CUDA(c, cudaMalloc((void**)&c->items, nrays * 64 * sizeof(unsigned)));
+#if MT_STEP_COMPACT
+        MT_CUDA(c, cudaMalloc((void**)&c->items, nrays * 64 * sizeof(unsigned)));   // only the compacting variant lists (step, ray) pairs
+#endif
         MT_CUDA(c, cudaMalloc((void**)&c->itemCount, sizeof(unsigned)));
     }
     P.rays = c->rays;

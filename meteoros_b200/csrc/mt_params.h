@@ -53,6 +53,11 @@ struct MarchConst {
 };
 #define MT_MARCHCONST_WORDS (sizeof(MarchConst) / 4)
 
+// In-cloud compaction of the step-parallel march (cloud_raymarch.cu): measured, slower at 4K, off (profiles/r1_ab.md).
+#ifndef MT_STEP_COMPACT
+#define MT_STEP_COMPACT 0
+#endif
+
 struct RowTiles {  // which pixel rows this launch covers (multi-GPU row-tile shards); default = whole image
     int tile_rows;    // rows per tile (multiple of the block height)
     int tile_begin;   // first tile owned
