@@ -150,6 +150,12 @@ static MtStatus alloc_images(MtContext* c)
     return MT_OK;
 }
 
+// No exception crosses the C boundary (std::string / std::vector members can throw): every MtStatus entry point is a
+// function-try-block ending in MT_NOTHROW.
+#define MT_NOTHROW                                      \
+    catch (const std::bad_alloc&) { return MT_ERR_OOM; } \
+    catch (...) { return MT_ERR_INVALID; }
+
 extern "C" {
 
 uint32_t mtAbiVersion(void) { return MT_ABI_VERSION; }
@@ -186,7 +192,7 @@ void mtDefaultTuning(MtTuning* t)
 }
 
 MtStatus mtCreate(const MtConfig* cfg, MtContext** out)
-{
+try {
     if (!cfg || !out) return MT_ERR_INVALID;
     *out = nullptr;
     if (cfg->struct_size != sizeof(MtConfig) || cfg->width == 0 || cfg->height == 0 || cfg->width > 32768 ||
@@ -231,7 +237,7 @@ MtStatus mtCreate(const MtConfig* cfg, MtContext** out)
     }
     *out = c;
     return MT_OK;
-}
+} MT_NOTHROW
 
 void mtDestroy(MtContext* c)
 {
@@ -264,7 +270,7 @@ void mtDestroy(MtContext* c)
 const char* mtGetLastError(const MtContext* c) { return c ? c->err.c_str() : "null context"; }
 
 MtStatus mtResize(MtContext* c, uint32_t w, uint32_t h)
-{
+try {
     if (!c) return MT_ERR_INVALID;
     MT_REQUIRE(c, w > 0 && h > 0 && w <= 32768 && h <= 32768, "mtResize: bad size");
     MT_CUDA(c, cudaSetDevice(c->device));
@@ -274,55 +280,55 @@ MtStatus mtResize(MtContext* c, uint32_t w, uint32_t h)
     c->H = (int)h;
     c->outHdr = c->outMask = nullptr;
     return alloc_images(c);
-}
+} MT_NOTHROW
 
 MtStatus mtSetCamera(MtContext* c, const MtCameraUBO* u)
-{
+try {
     if (!c) return MT_ERR_INVALID;
     MT_REQUIRE(c, u != nullptr, "mtSetCamera: null ubo");
     c->cam = *u;
     c->haveCam = true;
     return MT_OK;
-}
+} MT_NOTHROW
 MtStatus mtSetCameraOld(MtContext* c, const MtCameraUBO* u)
-{
+try {
     if (!c) return MT_ERR_INVALID;
     MT_REQUIRE(c, u != nullptr, "mtSetCameraOld: null ubo");
     c->camOld = *u;
     c->haveCamOld = true;
     return MT_OK;
-}
+} MT_NOTHROW
 MtStatus mtSetTime(MtContext* c, const MtTimeUBO* u)
-{
+try {
     if (!c) return MT_ERR_INVALID;
     MT_REQUIRE(c, u != nullptr, "mtSetTime: null ubo");
     MT_REQUIRE(c, u->frameCountMod16 >= 0 && u->frameCountMod16 < 16, "mtSetTime: frameCountMod16 outside 0..15");
     c->tm = *u;
     c->haveTime = true;
     return MT_OK;
-}
+} MT_NOTHROW
 MtStatus mtSetSunAndSky(MtContext* c, const MtSunAndSkyUBO* u)
-{
+try {
     if (!c) return MT_ERR_INVALID;
     MT_REQUIRE(c, u != nullptr, "mtSetSunAndSky: null ubo");
     c->sky = *u;
     return MT_OK;
-}
+} MT_NOTHROW
 MtStatus mtSetKeyPressQuery(MtContext* c, int32_t k)
-{
+try {
     if (!c) return MT_ERR_INVALID;
     c->key = k;  // bound at set 5 of the cloud pipeline, never read by the shader (Renderer.cpp:706)
     return MT_OK;
-}
+} MT_NOTHROW
 MtStatus mtSetTuning(MtContext* c, const MtTuning* t)
-{
+try {
     if (!c) return MT_ERR_INVALID;
     MT_REQUIRE(c, t != nullptr, "mtSetTuning: null tuning");
     MT_REQUIRE(c, t->coverage >= 0.0f && t->coverage <= 0.91f, "mtSetTuning: coverage must be in [0, 0.91]");
     MT_REQUIRE(c, t->weather_scale == t->weather_scale, "mtSetTuning: weather_scale is NaN");
     c->tun = *t;
     return MT_OK;
-}
+} MT_NOTHROW
 
 static MtStatus upload(MtContext* c, int slot, uint32_t w, uint32_t h, uint32_t d, const uint8_t* rgba8)
 {
@@ -356,17 +362,17 @@ static MtStatus upload(MtContext* c, int slot, uint32_t w, uint32_t h, uint32_t 
     return MT_OK;
 }
 MtStatus mtUploadTexture3D(MtContext* c, MtTextureSlot slot, uint32_t w, uint32_t h, uint32_t d, const uint8_t* rgba8)
-{
+try {
     if (!c) return MT_ERR_INVALID;
     MT_REQUIRE(c, slot == MT_TEX_LOW_FREQ || slot == MT_TEX_HIGH_FREQ, "mtUploadTexture3D: slot is not a 3D texture");
     return upload(c, (int)slot, w, h, d, rgba8);
-}
+} MT_NOTHROW
 MtStatus mtUploadTexture2D(MtContext* c, MtTextureSlot slot, uint32_t w, uint32_t h, const uint8_t* rgba8)
-{
+try {
     if (!c) return MT_ERR_INVALID;
     MT_REQUIRE(c, slot == MT_TEX_CURL || slot == MT_TEX_WEATHER, "mtUploadTexture2D: slot is not a 2D texture");
     return upload(c, (int)slot, w, h, 1, rgba8);
-}
+} MT_NOTHROW
 
 // ---- dispatch helpers ---------------------------------------------------------------------------------------------
 static void copy_cam(CamU& d, const MtCameraUBO& s)
@@ -502,17 +508,17 @@ static MtStatus cloud_dispatch(MtContext* c, int full, const RowTiles* tiles, bo
 }
 
 MtStatus mtDispatchCloud(MtContext* c)
-{
+try {
     if (!c) return MT_ERR_INVALID;
     return cloud_dispatch(c, 0, nullptr, false);
-}
+} MT_NOTHROW
 MtStatus mtDispatchCloudFull(MtContext* c)
-{
+try {
     if (!c) return MT_ERR_INVALID;
     return cloud_dispatch(c, 1, nullptr, false);
-}
+} MT_NOTHROW
 MtStatus mtDispatchCloudTiles(MtContext* c, uint32_t tile_rows, uint32_t tile_begin, uint32_t tile_end, uint32_t tile_stride)
-{
+try {
     if (!c) return MT_ERR_INVALID;
     MT_REQUIRE(c, tile_rows >= 8 && tile_rows % 8 == 0, "mtDispatchCloudTiles: tile_rows must be a positive multiple of 8");
     MT_REQUIRE(c, tile_stride >= 1, "mtDispatchCloudTiles: tile_stride must be >= 1");
@@ -525,9 +531,9 @@ MtStatus mtDispatchCloudTiles(MtContext* c, uint32_t tile_rows, uint32_t tile_be
     t.tile_count = tile_begin < tile_end ? (int)((tile_end - tile_begin + tile_stride - 1) / tile_stride) : 0;
     if (t.tile_count == 0) return MT_OK;
     return cloud_dispatch(c, 1, &t, false);
-}
+} MT_NOTHROW
 MtStatus mtDispatchCloudDebug(MtContext* c, int full, MtRayDebug* out, size_t out_bytes)
-{
+try {
     if (!c) return MT_ERR_INVALID;
     size_t need = (size_t)c->W * c->H * sizeof(MtRayDebug);
     MT_REQUIRE(c, out != nullptr && out_bytes >= need, "mtDispatchCloudDebug: output buffer too small");
@@ -536,7 +542,7 @@ MtStatus mtDispatchCloudDebug(MtContext* c, int full, MtRayDebug* out, size_t ou
     MT_CUDA(c, cudaMemcpyAsync(out, c->debug, need, cudaMemcpyDeviceToHost, c->stream));
     MT_CUDA(c, cudaStreamSynchronize(c->stream));
     return MT_OK;
-}
+} MT_NOTHROW
 
 static MtStatus reproject_dispatch(MtContext* c, bool debug)
 {
@@ -565,12 +571,12 @@ static MtStatus reproject_dispatch(MtContext* c, bool debug)
     return MT_OK;
 }
 MtStatus mtDispatchReprojection(MtContext* c)
-{
+try {
     if (!c) return MT_ERR_INVALID;
     return reproject_dispatch(c, false);
-}
+} MT_NOTHROW
 MtStatus mtDispatchReprojectionDebug(MtContext* c, int32_t* taps, size_t taps_bytes)
-{
+try {
     if (!c) return MT_ERR_INVALID;
     size_t need = (size_t)c->W * c->H * 10 * sizeof(int32_t);
     MT_REQUIRE(c, taps != nullptr && taps_bytes >= need, "mtDispatchReprojectionDebug: output buffer too small");
@@ -579,10 +585,10 @@ MtStatus mtDispatchReprojectionDebug(MtContext* c, int32_t* taps, size_t taps_by
     MT_CUDA(c, cudaMemcpyAsync(taps, c->taps, need, cudaMemcpyDeviceToHost, c->stream));
     MT_CUDA(c, cudaStreamSynchronize(c->stream));
     return MT_OK;
-}
+} MT_NOTHROW
 
 MtStatus mtDispatchGodRays(MtContext* c)
-{
+try {
     if (!c) return MT_ERR_INVALID;
     if (!c->haveCam) return fail(c, MT_ERR_NOT_READY, "god-ray dispatch: camera uniform not set");
     MT_CUDA(c, cudaSetDevice(c->device));
@@ -601,10 +607,10 @@ MtStatus mtDispatchGodRays(MtContext* c)
     pass_end(c, MT_PASS_GODRAYS);
     c->launches += 2;  // mask_decode_kernel + godrays_kernel
     return MT_OK;
-}
+} MT_NOTHROW
 
 MtStatus mtDispatchToneMap(MtContext* c)
-{
+try {
     if (!c) return MT_ERR_INVALID;
     if (!c->haveTime) return fail(c, MT_ERR_NOT_READY, "tone-map dispatch: time uniform not set");
     MT_CUDA(c, cudaSetDevice(c->device));
@@ -620,10 +626,10 @@ MtStatus mtDispatchToneMap(MtContext* c)
     pass_end(c, MT_PASS_TONEMAP);
     c->launches += 1;
     return MT_OK;
-}
+} MT_NOTHROW
 
 MtStatus mtDispatchTXAA(MtContext* c)
-{
+try {
     if (!c) return MT_ERR_INVALID;
     if (!c->haveCam || !c->haveCamOld || !c->haveTime)
         return fail(c, MT_ERR_NOT_READY, "TXAA dispatch: camera, cameraOld and time uniforms must be set");
@@ -647,17 +653,17 @@ MtStatus mtDispatchTXAA(MtContext* c)
     c->ldr[c->cur] = c->ldrScratch;
     c->ldrScratch = t;
     return MT_OK;
-}
+} MT_NOTHROW
 
 MtStatus mtSwapPingPong(MtContext* c)
-{
+try {
     if (!c) return MT_ERR_INVALID;
     c->cur ^= 1;
     return MT_OK;
-}
+} MT_NOTHROW
 
 MtStatus mtFrameEx(MtContext* c, uint32_t passes)
-{
+try {
     if (!c) return MT_ERR_INVALID;
     MT_REQUIRE(c, !(passes & MT_FRAME_TXAA) || (passes & MT_FRAME_TONEMAP), "mtFrameEx: TXAA needs the tone-map pass");
     MtStatus st;
@@ -667,14 +673,14 @@ MtStatus mtFrameEx(MtContext* c, uint32_t passes)
     if ((passes & MT_FRAME_TONEMAP) && (st = mtDispatchToneMap(c)) != MT_OK) return st;
     if ((passes & MT_FRAME_TXAA) && (st = mtDispatchTXAA(c)) != MT_OK) return st;
     return mtSwapPingPong(c);
-}
+} MT_NOTHROW
 MtStatus mtFrame(MtContext* c, int with_godrays)
-{
+try {
     return mtFrameEx(c, MT_FRAME_TONEMAP | (with_godrays ? MT_FRAME_GODRAYS : 0u));
-}
+} MT_NOTHROW
 
 MtStatus mtSynchronize(MtContext* c)
-{
+try {
     if (!c) return MT_ERR_INVALID;
     MT_CUDA(c, cudaSetDevice(c->device));
     MT_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -689,17 +695,17 @@ MtStatus mtSynchronize(MtContext* c)
         if (overrun) return fail(c, MT_ERR_CUDA, "mtSynchronize: the tile forwarder gave up waiting for the march kernel (tiles not delivered)");
     }
     return MT_OK;
-}
+} MT_NOTHROW
 
 // ---- images -------------------------------------------------------------------------------------------------------
 MtStatus mtImageBytes(const MtContext* c, MtImage which, size_t* bytes)
-{
+try {
     if (!c || !bytes || (int)which < 0 || (int)which > MT_IMAGE_LDR_PREV) return MT_ERR_INVALID;
     *bytes = image_bytes(c, which);
     return MT_OK;
-}
+} MT_NOTHROW
 MtStatus mtReadImageRows(MtContext* c, MtImage which, uint32_t row_begin, uint32_t row_end, void* host, size_t bytes)
-{
+try {
     if (!c) return MT_ERR_INVALID;
     MT_REQUIRE(c, (int)which >= 0 && (int)which <= MT_IMAGE_LDR_PREV && host != nullptr, "mtReadImageRows: bad arguments");
     MT_REQUIRE(c, row_begin <= row_end && row_end <= (uint32_t)c->H, "mtReadImageRows: bad row range");
@@ -711,14 +717,14 @@ MtStatus mtReadImageRows(MtContext* c, MtImage which, uint32_t row_begin, uint32
     if (need) MT_CUDA(c, cudaMemcpyAsync(host, src, need, cudaMemcpyDeviceToHost, c->stream));
     MT_CUDA(c, cudaStreamSynchronize(c->stream));
     return MT_OK;
-}
+} MT_NOTHROW
 MtStatus mtReadImage(MtContext* c, MtImage which, void* host, size_t bytes)
-{
+try {
     if (!c) return MT_ERR_INVALID;
     return mtReadImageRows(c, which, 0, (uint32_t)c->H, host, bytes);
-}
+} MT_NOTHROW
 MtStatus mtReadImageAsync(MtContext* c, MtImage which, void* host, size_t bytes)
-{
+try {
     if (!c) return MT_ERR_INVALID;
     MT_REQUIRE(c, (int)which >= 0 && (int)which <= MT_IMAGE_LDR_PREV && host != nullptr, "mtReadImageAsync: bad arguments");
     MT_REQUIRE(c, bytes >= image_bytes(c, which), "mtReadImageAsync: host buffer too small");
@@ -741,26 +747,26 @@ MtStatus mtReadImageAsync(MtContext* c, MtImage which, void* host, size_t bytes)
     slot->dev = dev;
     slot->active = true;
     return MT_OK;
-}
+} MT_NOTHROW
 MtStatus mtWaitReads(MtContext* c)
-{
+try {
     if (!c) return MT_ERR_INVALID;
     MT_CUDA(c, cudaSetDevice(c->device));
     MT_CUDA(c, cudaStreamSynchronize(c->copyStream));
     for (auto& p : c->pending) p.active = false;
     return MT_OK;
-}
+} MT_NOTHROW
 MtStatus mtJoinCopies(MtContext* c)
-{
+try {
     if (!c) return MT_ERR_INVALID;
     MT_CUDA(c, cudaSetDevice(c->device));
     MT_CUDA(c, cudaEventRecord(c->producedEv, c->copyStream));
     MT_CUDA(c, cudaStreamWaitEvent(c->stream, c->producedEv, 0));
     if (c->fwdBusy) MT_CUDA(c, cudaStreamWaitEvent(c->stream, c->fwdDoneEv, 0));  // the tile forwarder of the last dispatch
     return MT_OK;
-}
+} MT_NOTHROW
 MtStatus mtWriteImage(MtContext* c, MtImage which, const void* host, size_t bytes)
-{
+try {
     if (!c) return MT_ERR_INVALID;
     MT_REQUIRE(c, (int)which >= 0 && (int)which <= MT_IMAGE_LDR_PREV && host != nullptr, "mtWriteImage: bad arguments");
     MT_REQUIRE(c, bytes == image_bytes(c, which), "mtWriteImage: size must equal the image size");
@@ -768,9 +774,9 @@ MtStatus mtWriteImage(MtContext* c, MtImage which, const void* host, size_t byte
     wait_pending_read(c, image_ptr(c, which));
     MT_CUDA(c, cudaMemcpyAsync(image_ptr(c, which), host, bytes, cudaMemcpyHostToDevice, c->stream));
     return MT_OK;
-}
+} MT_NOTHROW
 MtStatus mtClearImages(MtContext* c)
-{
+try {
     if (!c) return MT_ERR_INVALID;
     MT_CUDA(c, cudaSetDevice(c->device));
     for (auto& p : c->pending)
@@ -782,22 +788,22 @@ MtStatus mtClearImages(MtContext* c)
     MT_CUDA(c, cudaMemsetAsync(c->ldr[0], 0, px * 4, c->stream));
     MT_CUDA(c, cudaMemsetAsync(c->ldr[1], 0, px * 4, c->stream));
     return MT_OK;
-}
+} MT_NOTHROW
 MtStatus mtImageDevicePtr(MtContext* c, MtImage which, void** p)
-{
+try {
     if (!c || !p || (int)which < 0 || (int)which > MT_IMAGE_LDR_PREV) return MT_ERR_INVALID;
     *p = image_ptr(c, which);
     return MT_OK;
-}
+} MT_NOTHROW
 MtStatus mtSetCloudOutput(MtContext* c, void* hdr, void* mask)
-{
+try {
     if (!c) return MT_ERR_INVALID;
     c->outHdr = (F4*)hdr;
     c->outMask = (F4*)mask;
     return MT_OK;
-}
+} MT_NOTHROW
 MtStatus mtSetCloudForward(MtContext* c, void* peer_hdr)
-{
+try {
     if (!c) return MT_ERR_INVALID;
     MT_CUDA(c, cudaSetDevice(c->device));
     if (peer_hdr && !c->fwdStream) {
@@ -811,9 +817,9 @@ MtStatus mtSetCloudForward(MtContext* c, void* peer_hdr)
     c->fwdBusy = false;
     c->forwardHdr = peer_hdr;
     return MT_OK;
-}
+} MT_NOTHROW
 MtStatus mtExportImageHandle(MtContext* c, MtImage which, uint8_t handle[64])
-{
+try {
     if (!c) return MT_ERR_INVALID;
     MT_REQUIRE(c, handle != nullptr && (int)which >= 0 && (int)which <= MT_IMAGE_LDR_PREV, "mtExportImageHandle: bad arguments");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
@@ -822,9 +828,9 @@ MtStatus mtExportImageHandle(MtContext* c, MtImage which, uint8_t handle[64])
     MT_CUDA(c, cudaIpcGetMemHandle(&h, image_ptr(c, which)));
     memcpy(handle, &h, 64);
     return MT_OK;
-}
+} MT_NOTHROW
 MtStatus mtOpenPeerImage(MtContext* c, const uint8_t handle[64], void** p)
-{
+try {
     if (!c) return MT_ERR_INVALID;
     MT_REQUIRE(c, handle != nullptr && p != nullptr, "mtOpenPeerImage: bad arguments");
     MT_CUDA(c, cudaSetDevice(c->device));
@@ -832,9 +838,9 @@ MtStatus mtOpenPeerImage(MtContext* c, const uint8_t handle[64], void** p)
     memcpy(&h, handle, 64);
     MT_CUDA(c, cudaIpcOpenMemHandle(p, h, cudaIpcMemLazyEnablePeerAccess));
     return MT_OK;
-}
+} MT_NOTHROW
 MtStatus mtClosePeerImage(MtContext* c, void* p)
-{
+try {
     if (!c) return MT_ERR_INVALID;
     MT_CUDA(c, cudaSetDevice(c->device));
     MT_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -842,11 +848,11 @@ MtStatus mtClosePeerImage(MtContext* c, void* p)
     if (c->outMask == p) c->outMask = nullptr;
     MT_CUDA(c, cudaIpcCloseMemHandle(p));
     return MT_OK;
-}
+} MT_NOTHROW
 
 MtStatus mtCopyTilesToPeer(MtContext* c, MtImage which, uint32_t tile_rows, uint32_t tile_begin, uint32_t tile_end,
                            uint32_t tile_stride, void* peer)
-{
+try {
     if (!c) return MT_ERR_INVALID;
     MT_REQUIRE(c, peer != nullptr && (int)which >= 0 && (int)which <= MT_IMAGE_LDR_PREV, "mtCopyTilesToPeer: bad arguments");
     MT_REQUIRE(c, tile_rows >= 1 && tile_stride >= 1, "mtCopyTilesToPeer: bad tiling");
@@ -862,11 +868,11 @@ MtStatus mtCopyTilesToPeer(MtContext* c, MtImage which, uint32_t tile_rows, uint
         MT_CUDA(c, cudaMemcpyAsync((char*)peer + pitch * r0, src + pitch * r0, pitch * (r1 - r0), cudaMemcpyDeviceToDevice, c->copyStream));
     }
     return MT_OK;
-}
+} MT_NOTHROW
 
 // ---- measurement --------------------------------------------------------------------------------------------------
 MtStatus mtGetCounters(MtContext* c, MtCounters* out, int reset)
-{
+try {
     if (!c) return MT_ERR_INVALID;
     MT_REQUIRE(c, out != nullptr, "mtGetCounters: null output");
     MT_CUDA(c, cudaSetDevice(c->device));
@@ -877,9 +883,9 @@ MtStatus mtGetCounters(MtContext* c, MtCounters* out, int reset)
     out->steps_incloud = v[3]; out->cone_hits = v[4]; out->early_exits = v[5];
     if (reset) MT_CUDA(c, cudaMemsetAsync(c->counters, 0, sizeof(v), c->stream));
     return MT_OK;
-}
+} MT_NOTHROW
 MtStatus mtLastPassMs(MtContext* c, MtPass pass, float* ms)
-{
+try {
     if (!c) return MT_ERR_INVALID;
     MT_REQUIRE(c, ms != nullptr && (int)pass >= 0 && (int)pass < MT_PASS_COUNT, "mtLastPassMs: bad arguments");
     MT_REQUIRE(c, (c->flags & MT_FLAG_PASS_TIMING_INTERNAL) && c->evValid[pass], "mtLastPassMs: pass timing not enabled or pass never ran");
@@ -887,15 +893,15 @@ MtStatus mtLastPassMs(MtContext* c, MtPass pass, float* ms)
     MT_CUDA(c, cudaEventSynchronize(c->ev[pass][1]));
     MT_CUDA(c, cudaEventElapsedTime(ms, c->ev[pass][0], c->ev[pass][1]));
     return MT_OK;
-}
+} MT_NOTHROW
 MtStatus mtStreamHandle(MtContext* c, void** s)
-{
+try {
     if (!c || !s) return MT_ERR_INVALID;
     *s = (void*)c->stream;
     return MT_OK;
-}
+} MT_NOTHROW
 MtStatus mtEventRecord(MtContext* c, uint32_t slot)
-{
+try {
     if (!c) return MT_ERR_INVALID;
     MT_REQUIRE(c, slot < MT_USER_EVENTS, "mtEventRecord: slot out of range");
     MT_CUDA(c, cudaSetDevice(c->device));
@@ -903,9 +909,9 @@ MtStatus mtEventRecord(MtContext* c, uint32_t slot)
     MT_CUDA(c, cudaEventRecord(c->userEv[slot], c->stream));
     c->userEvValid[slot] = true;
     return MT_OK;
-}
+} MT_NOTHROW
 MtStatus mtEventElapsedMs(MtContext* c, uint32_t from, uint32_t to, float* ms)
-{
+try {
     if (!c) return MT_ERR_INVALID;
     MT_REQUIRE(c, ms != nullptr && from < MT_USER_EVENTS && to < MT_USER_EVENTS, "mtEventElapsedMs: bad arguments");
     MT_REQUIRE(c, c->userEvValid[from] && c->userEvValid[to], "mtEventElapsedMs: event slot never recorded");
@@ -913,9 +919,9 @@ MtStatus mtEventElapsedMs(MtContext* c, uint32_t from, uint32_t to, float* ms)
     MT_CUDA(c, cudaEventSynchronize(c->userEv[to]));
     MT_CUDA(c, cudaEventElapsedTime(ms, c->userEv[from], c->userEv[to]));
     return MT_OK;
-}
+} MT_NOTHROW
 MtStatus mtFlushL2(MtContext* c, size_t bytes)
-{
+try {
     if (!c) return MT_ERR_INVALID;
     MT_CUDA(c, cudaSetDevice(c->device));
     const size_t unit = (size_t)256 << 20;
@@ -930,9 +936,9 @@ MtStatus mtFlushL2(MtContext* c, size_t bytes)
     }
     MT_CUDA(c, cudaMemsetAsync(c->flushBuf, 0, want, c->stream));
     return MT_OK;
-}
+} MT_NOTHROW
 MtStatus mtMeasureFp32Peak(MtContext* c, float* gflops)
-{
+try {
     if (!c) return MT_ERR_INVALID;
     MT_REQUIRE(c, gflops != nullptr, "mtMeasureFp32Peak: null output");
     MT_CUDA(c, cudaSetDevice(c->device));
@@ -962,7 +968,7 @@ MtStatus mtMeasureFp32Peak(MtContext* c, float* gflops)
     cudaEventDestroy(e1);
     *gflops = best;
     return MT_OK;
-}
+} MT_NOTHROW
 uint64_t mtLaunchCount(const MtContext* c) { return c ? c->launches : 0; }
 
 }  // extern "C"
