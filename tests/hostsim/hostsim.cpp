@@ -54,18 +54,18 @@ int hs_cloud(const MtCameraUBO* cam, const MtTimeUBO* tm, const MtTuning* tun, c
     P.W = W; P.H = H;
     P.tx = (((W / 4) + 31) / 32) * 32;
     P.ty = (((H / 4) + 31) / 32) * 32;
-    P.full = full;
+    P.full = full == 1;
     MarchConst M;
     cloud_frame_setup(P.cam, P.tm, P.tun, M);
     cloud_frame_jitter(P.tm, W, H, M);
     RayCounters cnt = { 0, 0, 0, 0, 0, 0 };
     unsigned long long tot[6] = { 0, 0, 0, 0, 0, 0 };
-    const int gw = full ? W : P.tx, gh = full ? H : P.ty;
+    const int gw = full == 1 ? W : P.tx, gh = full == 1 ? H : P.ty;  // full: 0 = 1-of-16, 1 = all pixels, 2 = 1-of-16 step-parallel
     for (int gy = 0; gy < gh; ++gy)
         for (int gx = 0; gx < gw; ++gx) {
             int px, py, id;
             bool valid;
-            if (full) {
+            if (full == 1) {
                 px = gx; py = gy;
                 id = ((px & 3) << 2) | (py & 3);
                 valid = px < W && py < H && (px >> 2) < P.tx && (py >> 2) < P.ty;
@@ -80,6 +80,34 @@ int hs_cloud(const MtCameraUBO* cam, const MtTimeUBO* tm, const MtTuning* tun, c
             size_t idx = (size_t)py * W + px;
             MtRayDebug scratch;
             memset(&cnt, 0, sizeof(cnt));
+            if (full == 2) {
+                // The step-parallel decomposition of the 1-of-16 dispatch (cloud_rays_kernel / cloud_steps_kernel /
+                // cloud_fold_kernel), with the same device functions: the ray record and its filed t sequence, every
+                // (ray, step) sample evaluated on its own -- last step first, to make the independence explicit -- and
+                // the fold in step order.
+                m.x = m.y = m.z = m.w = 0.0f;
+                RaySetup R = cloud_ray_setup(P, M, px, py, id, h);
+                if (R.branch == 2) {
+                    float tk[MT_STEP_SLICES];
+                    int n = 0;
+                    for (float t = R.t_in; t < R.t_out && n < MT_STEP_SLICES; t += R.stepSize) tk[n++] = t;
+                    R.nsteps = n;
+                    StepSample S[MT_STEP_SLICES];
+                    RayCounters none = { 0, 0, 0, 0, 0, 0 };
+                    for (int k = n - 1; k >= 0; --k) {
+                        const int jidx = (P.tm.frameCountMod16 + mt_f2i(tk[k])) & 15;
+                        S[k] = tun->use_weather ? cloud_step_sample<false, true>(P, M, R, jidx, tk[k], none)
+                                                : cloud_step_sample<false, false>(P, M, R, jidx, tk[k], none);
+                    }
+                    float accum = 0.0f, transmittance = 1.0f, color = 0.0f;
+                    for (int k = 0; k < R.nsteps; ++k)
+                        if (cloud_step_combine(S[k], accum, transmittance, color)) break;
+                    cloud_composite(R, accum, color, h, m);
+                }
+                memcpy(hdr + 4 * idx, &h, 16);
+                memcpy(mask + 4 * idx, &m, 16);
+                continue;
+            }
             if (tun->use_weather) cloud_ray<true, true, true>(P, M, px, py, id, h, m, cnt, debug ? debug + idx : &scratch);
             else cloud_ray<true, true, false>(P, M, px, py, id, h, m, cnt, debug ? debug + idx : &scratch);
             tot[0] += cnt.rays; tot[1] += cnt.marched; tot[2] += cnt.steps; tot[3] += cnt.incloud; tot[4] += cnt.cone; tot[5] += cnt.early;

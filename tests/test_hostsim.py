@@ -181,3 +181,18 @@ def test_randomised_scenes_kernel_cores(oracle_mod, noise, hostsim):
         hist = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
         assert np.array_equal(hostsim.txaa(new, old, tm, ldr, hist), oracle_mod.txaa(new, old, tm, ldr, hist)), trial
     assert marched > 10000
+
+
+@pytest.mark.parametrize("w,h,fid,yaw,pitch,weather", [(200, 112, 14, -30.0, 8.0, False), (130, 70, 7, 12.0, 3.0, False),
+                                                     (96, 54, 3, 20.0, 2.0, True), (64, 36, 0, 0.0, -4.0, False)])
+def test_step_parallel_decomposition_equals_sequential_march(oracle_mod, noise, hostsim, w, h, fid, yaw, pitch, weather):
+    """The 1-of-16 dispatch runs as rays -> independent (ray, step) samples -> fold on the GPU (cloud_raymarch.cu).  The
+    same decomposition with the same device functions on the host -- samples evaluated last step first -- gives the
+    sequential march's bytes (on the GPU: test_sixteenth_step_parallel_equals_sequential)."""
+    cam, tm, _, tun = default_scene(w, h, frame_id=fid, total_time=9.0, yaw=yaw, pitch=pitch)
+    if weather:
+        tun["use_weather"], tun["weather_scale"] = 1, 1.0e-4
+    seq_hdr, seq_mask, _, _ = hostsim.cloud(cam, tm, tun, noise, w, h, 0, oracle_mod.RAY_DEBUG_DTYPE)
+    par_hdr, par_mask, _, _ = hostsim.cloud(cam, tm, tun, noise, w, h, 2, oracle_mod.RAY_DEBUG_DTYPE)
+    assert np.array_equal(seq_hdr, par_hdr) and np.array_equal(seq_mask, par_mask)
+    assert seq_mask.any()
