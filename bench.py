@@ -177,7 +177,16 @@ def cpu_reference_sample(noise, w, h, target_s=12.0, probe_stride=64):
     cam, tm, sky, tun = scene_for_view(0, w, h)
     hdr = np.zeros((h, w, 4), np.float32)
     mask = np.zeros((h, w, 4), np.float32)
-    cores = os.cpu_count() or 1
+    # torchrun exports OMP_NUM_THREADS=1 to every rank: ask for every core this process may run on, and report the team
+    # size OpenMP really forms (one libgomp per process, so this also governs oracle/_ref's loops)
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    olib = oracle.lib()
+    olib.mto_set_num_threads(int(avail))
+    cores = int(olib.mto_num_threads())
+    assert cores == avail or avail == 1, f"OpenMP formed a team of {cores} threads, {avail} cores are available"
     groups = (h + 3) // 4
     kind = "reference" if (refshaders.available() or refshaders.built()) else "port"
 
@@ -230,6 +239,76 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def sharded_8k_record(args, api, sharding, torch, dist, world, rank, local_rank, noise, steps):
+    """BASELINE config 4 beside the N>1 views line: ONE 7680x4320 full-quality frame cut into cyclic row tiles over the
+    ranks and gathered on GPU 0 over NVLink, timed like the headline (events on each rank's stream, L2 flushed, max over
+    ranks) against the same frame on rank 0 alone, measured in the same run; the gathered frame is compared bit for bit
+    with the single-GPU frame.  Returns the record on rank 0 (None elsewhere)."""
+    w, h = 7680, 4320
+    cam, tm, sky, tun = scene_for_view(0, w, h)
+    r8 = api.CloudRenderer(w, h, device=local_rank, storage=args.storage)
+    r8.upload_noise(noise)
+    r8.set_camera(cam); r8.set_camera_old(cam); r8.set_time(tm); r8.set_sun_and_sky(sky); r8.set_tuning(tun)
+
+    def sync_all():
+        r8.synchronize()
+        torch.cuda.synchronize()
+        dist.barrier()
+
+    single_ms, ref_frame = 0.0, None
+    if rank == 0:  # the whole frame on one GPU: the denominator of the speed-up
+        for _ in range(3):
+            r8.dispatch_cloud_full()
+        ms = []
+        for _ in range(steps):
+            r8.flush_l2(0)
+            r8.event_record(2)
+            r8.dispatch_cloud_full()
+            r8.event_record(3)
+            ms.append(r8.event_elapsed_ms(2, 3))
+        single_ms = float(statistics.mean(ms))
+        ref_frame = r8.read_image(api.IMAGE_CLOUD_CUR)
+        r8.clear_images()  # a tile that never arrives must not pass the comparison below
+    sync_all()
+    shard = sharding.ShardedFrame(r8, dist, tile_rows=args.tile_rows, with_mask=args.gather_mask, mode=args.gather)
+    for _ in range(3):
+        shard.dispatch()
+        shard.finish()
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms = []
+    for _ in range(steps):
+        r8.flush_l2(0)
+        dist.barrier()  # every rank starts the frame together
+        r8.event_record(2)
+        shard.dispatch()
+        if args.gather in ("copy", "forward"):
+            r8.join_copies()  # the interval ends when this rank's tile pushes have landed
+        r8.event_record(3)
+        shard.finish()
+        ms.append(r8.event_elapsed_ms(2, 3))
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([float(statistics.mean(ms))], dtype=torch.float64, device=f"cuda:{local_rank}")
+    per_rank = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(per_rank, t)
+    rec = None
+    if rank == 0:
+        got = r8.read_image(api.IMAGE_CLOUD_CUR)
+        frame_ms = max(float(x[0]) for x in per_rank)
+        rec = {
+            "workload": f"7680x4320 full-quality frame, cyclic {args.tile_rows}-row tiles over {world} GPUs, HDR gathered on GPU 0 over NVLink (BASELINE config 4)",
+            "ms_per_frame": round(frame_ms, 4), "single_gpu_ms": round(single_ms, 4), "speedup": round(single_ms / frame_ms, 3),
+            "mrays_per_s": round(w * h / (frame_ms * 1e-3) / 1e6, 1), "rank_ms": [round(float(x[0]), 4) for x in per_rank],
+            "gather": args.gather, "gather_mask": bool(args.gather_mask), "tile_rows": args.tile_rows, "steps": steps, "scaling": "strong",
+            "bit_identical_to_single_gpu": bool(np.array_equal(got, ref_frame)), "storage": "f16" if args.storage else "f32", "clocks": clocks,
+        }
+    shard.close()
+    r8.close()
+    return rec
+
+
 _REAL_STDOUT = None
 
 
@@ -266,6 +345,8 @@ def main():
                          "timed at 8 GPUs), or (diagnostic) no gather at all")
     ap.add_argument("--gather-mask", action="store_true", help="frame8k: also send the god-ray mask tiles to GPU 0 (needed only if god rays run)")
     ap.add_argument("--sweep", action="store_true", help="N>1: rank r renders view r of the sun/coverage sweep")
+    ap.add_argument("--no-sharded-8k", action="store_true", help="N>1 default workload: skip the sharded_8k sub-record (config 4)")
+    ap.add_argument("--storage", type=int, default=0, help="image storage: 0 = RGBA32F (default), 1 = binary16-rounded values in RGBA32F")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -311,7 +392,7 @@ def main():
         counters = rc.counters()
         fp32_peak_gflops = rc.measure_fp32_peak_gflops()
 
-    r = api.CloudRenderer(w, h, device=local_rank, flags=(api.FLAG_PASS_TIMING if args.workload == "seq1080p" else 0) | args.ctx_flags)
+    r = api.CloudRenderer(w, h, device=local_rank, storage=args.storage, flags=(api.FLAG_PASS_TIMING if args.workload == "seq1080p" else 0) | args.ctx_flags)
     r.upload_noise(noise)
     r.set_camera(cam); r.set_camera_old(cam); r.set_time(tm); r.set_sun_and_sky(sky); r.set_tuning(tun)
     from meteoros_b200 import scene as _scene
@@ -400,6 +481,8 @@ def main():
     pinned = [torch.empty(nbytes, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
     h2d = int(cam.nbytes + tm.nbytes + tun.nbytes + sky.nbytes)
     e2e_read = (rank == 0) or args.workload != "frame8k"
+    read_mask = args.workload in ("cloud4k", "views256") or (sharded and args.gather_mask)
+    pinned_mask = [torch.empty(nbytes, dtype=torch.uint8, pin_memory=True) for _ in range(2)] if read_mask else None
 
     def e2e_step(i):
         if not seq:
@@ -411,6 +494,8 @@ def main():
             r.swap_ping_pong()  # mtFrame swaps by itself
         if e2e_read:
             r.read_image_async(out_which, pinned[i & 1].data_ptr(), nbytes)
+            if read_mask:  # the Cloud pass has two outputs (cloudRayMarch.comp:824-825): HDR colour and the god-ray image
+                r.read_image_async(api.IMAGE_GODRAY_MASK, pinned_mask[i & 1].data_ptr(), nbytes)
 
     for i in range(2):
         e2e_step(i)
@@ -458,6 +543,7 @@ def main():
                 "bound": "fp32-issue", "kernel": "cloud_raymarch_kernel", "achieved": round(ach_tflops, 3),
                 "peak": round(fp32_peak_gflops / 1e3, 3), "unit": "TFLOP/s", "frac": round(ach_tflops / (fp32_peak_gflops / 1e3), 4),
                 "peak_source": "measured FP32 FMA micro-benchmark (mtMeasureFp32Peak) on this GPU; no tensor work in this path",
+                "peak_check": "filled below",
                 "algorithmic_gflop_per_launch": round(flop / 1e9, 3), "filtered_fetches_per_launch": filtered_fetches(counters),
                 "gfetch_per_s": round(filtered_fetches(counters) / (kern_ms * 1e-3) / 1e9, 3), "traffic": ncu_traffic_bytes(),
                 "hbm": {"bound": "hbm", "achieved": round(hbm_ach, 2), "peak": hbm_peak, "unit": "GB/s", "frac": round(hbm_ach / hbm_peak, 5),
@@ -469,7 +555,8 @@ def main():
             "scaling": "strong" if (args.workload == "frame8k") else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload, "rays_per_step": int(rays_total_per_step), "l2": "flushed between timed steps (256 MiB memset)",
                        "noise": "reference noise volumes (tests/golden/noise_volumes.npz)", "parallelism": f"row-tiles x{world}" if args.workload == "frame8k" else f"views x{world}"},
-            "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(nbytes if e2e_read else 0),
+            "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int((nbytes * (2 if read_mask else 1)) if e2e_read else 0),
+                    "reads": ("HDR colour + god-ray image" if read_mask else ("LDR frame" if seq else "HDR colour (the god-ray image stays on its GPU unless --gather-mask)")),
                     "ms_per_step": round(1e3 * e2e_s / args.steps, 4)},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
             "work": {k: int(v) for k, v in counters.items()},
@@ -493,8 +580,21 @@ def main():
 
     if shard is not None and world > 1:
         shard.close()
+    sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
     r.close()
 
+    if world > 1 and args.workload == "cloud4k" and not args.no_sharded_8k:
+        rec = sharded_8k_record(args, api, sharding, torch, dist, world, rank, local_rank, noise, steps=max(args.steps, 10))
+        if rank == 0:
+            line["sharded_8k"] = rec
+
+    if rank == 0 and line.get("roofline"):
+        # cross-check of the probe: SMs x 128 FP32 lanes x 2 flop x the SM clock observed under load
+        mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 0.0
+        nominal = sm_count * 128 * 2 * float(mhz) * 1e6 / 1e12
+        line["roofline"]["peak_check"] = {"sm_count": sm_count, "sm_mhz": mhz, "nominal_tflops": round(nominal, 2),
+                                          "probe_over_nominal": round((fp32_peak_gflops / 1e3) / nominal, 4) if nominal else None,
+                                          "frac_vs_nominal": round(line["roofline"]["achieved"] / nominal, 4) if nominal else None}
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "cloud4k":
         v, cores, desc, _, kind = cpu_reference_sample(noise, W4K, H4K, target_s=12.0)
         line["cpu_baseline"] = {"value": round(v, 4), "unit": UNIT, "cores": cores, "kind": kind, "sample": desc}

@@ -119,7 +119,11 @@ typedef enum MtImage {
     MT_IMAGE_CLOUD_CUR = 0,   /* currentFrameResultImage   RGBA32F, W*H*16 bytes */
     MT_IMAGE_CLOUD_PREV = 1,  /* previousFrameResultImage  RGBA32F               */
     MT_IMAGE_GODRAY_MASK = 2, /* godRaysCreationDataImage  RGBA32F               */
-    MT_IMAGE_LDR = 3,         /* currentFrameTexture: tone-mapped (then TXAA'd) frame, RGBA8 UNORM, W*H*4 (Renderer.cpp:1442) */
+    MT_IMAGE_LDR = 3,         /* currentFrameTexture: tone-mapped (then TXAA'd) frame, W*H*4.  Stored here as RGBA8 UNORM -- what
+                               * the shaders declare (`rgba8`, postProcess_ToneMap.frag:5); the reference CREATES the image as
+                               * R8G8B8A8_SNORM (Renderer.cpp:1442-1445), a declared/actual mismatch that is deliberately not
+                               * reproduced (INTEGRATION.md "Deviations").  The device pointer behind LDR / LDR_PREV changes
+                               * after every mtDispatchTXAA / mtFrame: re-query mtImageDevicePtr per frame.              */
     MT_IMAGE_LDR_PREV = 4     /* previousFrameTexture: the LDR frame presented last frame (Renderer.cpp:1445)              */
 } MtImage;
 
@@ -164,7 +168,11 @@ MT_API void mtDefaultTuning(MtTuning* out);
 MT_API MtStatus mtCreate(const MtConfig* cfg, MtContext** out);
 MT_API void mtDestroy(MtContext* ctx);                 /* Renderer::~Renderer (Renderer.cpp:40-87) */
 MT_API const char* mtGetLastError(const MtContext* ctx);/* text of the last non-OK status; "" if none */
-MT_API MtStatus mtResize(MtContext* ctx, uint32_t width, uint32_t height); /* Renderer::RecreateOnResize (Renderer.cpp:598-611) */
+/* Renderer::RecreateOnResize (Renderer.cpp:598-611).  Transactional: on failure (MT_ERR_OOM / MT_ERR_CUDA) the context keeps its
+ * old size and images and stays usable.  On success images start as zeros, and everything that referred to the old images is
+ * dropped: mtSetCloudOutput / mtSetCloudForward are cleared, device pointers from mtImageDevicePtr and handles from
+ * mtExportImageHandle are stale -- peers must close, re-export and re-open them. */
+MT_API MtStatus mtResize(MtContext* ctx, uint32_t width, uint32_t height);
 
 /* ---- uniforms: copied at call time (reference: memcpy into the mapped UBO) ---------------- */
 MT_API MtStatus mtSetCamera(MtContext* ctx, const MtCameraUBO* ubo);      /* Camera::CopyToGPUMemory, camera.cpp:50-53; set 2 / set 1 */

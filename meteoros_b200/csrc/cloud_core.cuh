@@ -174,8 +174,6 @@ MT_DEVICE void encode_mask(float v, F4& o)
     o.x = e0 - e1 * k; o.y = e1 - e2 * k; o.z = e2 - e3 * k; o.w = e3 - e3 * 0.0f;
 }
 
-#define MT_MAX_MARCH_ITERS 128  /* maxSteps <= 60; guards degenerate shells (also in the oracle) */
-#define MT_STEP_SLICES 64       /* step-parallel path: slices launched per ray (maxSteps <= 58 + fp slack) */
 
 // Everything about one ray that does not change along the march (castRay, the horizon branches, the two shell
 // intersections, the phase function).  64 bytes: also the record the step-parallel path keeps per ray.

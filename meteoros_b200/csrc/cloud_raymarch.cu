@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(128, MT_STEPS_MINBLOCKS) cloud_steps_kernel(co
     stage_march_const(M, P.mc);
     const size_t ray = (size_t)blockIdx.x * 128 + threadIdx.x;
     float2* slot = P.samples + ((size_t)k * (size_t)P.rayStride + ray);
-    const float t = __ldg(reinterpret_cast<const float*>(slot));  // t_k as the sequential loop rounds it (cloud_rays_kernel)
+    const float t = *reinterpret_cast<const float*>(slot);  // t_k as the sequential loop rounds it (cloud_rays_kernel); plain load: the slot is overwritten below
     const RaySetup R = reinterpret_cast<const RaySetup*>(P.rays)[ray];
     if (R.branch != 2 || k >= R.nsteps) return;
     const int jidx = (P.tm.frameCountMod16 + mt_f2i(t)) & 15;

@@ -36,6 +36,7 @@ struct MtContext {
     int cur = 0;  // index of the image that currently plays "currentFrameResultImage"
     F4* mask = nullptr;
     float* maskDecoded = nullptr;  // (W+2) x (H+2): scratch of the god-ray pass
+    F4* maskStage = nullptr;       // device snapshot of the mask behind mtReadImageAsync (lazily allocated)
     uint32_t* ldr[2] = { nullptr, nullptr };  // ping-pong with the HDR images (same `cur`)
     uint32_t* ldrScratch = nullptr;           // TXAA output, swapped with ldr[cur] after the pass
     uint32_t* tex[4] = { nullptr, nullptr, nullptr, nullptr };
@@ -117,36 +118,80 @@ static void wait_pending_read(MtContext* c, const void* dev)
 }
 static bool is_pow2(uint32_t v) { return v && !(v & (v - 1)); }
 
+// The per-size device images of a context.  Allocated as a group so that mtCreate / mtResize are transactional: either
+// every image of the new size exists, or nothing changed.
+struct ImageSet {
+    F4* hdr[2] = { nullptr, nullptr };
+    F4* mask = nullptr;
+    uint32_t* ldr[2] = { nullptr, nullptr };
+    uint32_t* ldrScratch = nullptr;
+    float* maskDecoded = nullptr;
+};
+static void free_image_set(ImageSet& s)
+{
+    cudaFree(s.hdr[0]); cudaFree(s.hdr[1]); cudaFree(s.mask);
+    cudaFree(s.ldr[0]); cudaFree(s.ldr[1]); cudaFree(s.ldrScratch); cudaFree(s.maskDecoded);
+    s = ImageSet();
+}
+static cudaError_t alloc_image_set(ImageSet& s, int W, int H, cudaStream_t stream)
+{
+    const size_t px = (size_t)W * (size_t)H;
+    cudaError_t e;
+    if ((e = cudaMalloc((void**)&s.hdr[0], px * 16)) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void**)&s.hdr[1], px * 16)) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void**)&s.mask, px * 16)) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void**)&s.ldr[0], px * 4)) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void**)&s.ldr[1], px * 4)) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void**)&s.ldrScratch, px * 4)) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void**)&s.maskDecoded, (size_t)(W + 2) * (size_t)(H + 2) * sizeof(float))) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(s.hdr[0], 0, px * 16, stream)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(s.hdr[1], 0, px * 16, stream)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(s.mask, 0, px * 16, stream)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(s.ldr[0], 0, px * 4, stream)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(s.ldr[1], 0, px * 4, stream)) != cudaSuccess) return e;
+    return cudaMemsetAsync(s.ldrScratch, 0, px * 4, stream);
+}
+
+// Everything whose size or meaning depends on W x H: the images, the lazily allocated scratch of the step-parallel
+// march / debug records, and all state that refers to the old images (output redirection, forwarding, pending reads).
 static void free_images(MtContext* c)
 {
-    cudaFree(c->hdr[0]); cudaFree(c->hdr[1]); cudaFree(c->mask);
-    cudaFree(c->ldr[0]); cudaFree(c->ldr[1]); cudaFree(c->ldrScratch);
-    c->ldr[0] = c->ldr[1] = c->ldrScratch = nullptr;
-    cudaFree(c->debug); cudaFree(c->taps); cudaFree(c->maskDecoded); cudaFree(c->rays); cudaFree(c->samples); cudaFree(c->ctaSteps);
-    cudaFree(c->items); cudaFree(c->itemCount);
     if (c->fwdStream) cudaStreamSynchronize(c->fwdStream);
-    cudaFree(c->tileDone);
-    c->tileDone = nullptr; c->fwdBusy = false; c->fwdCheck = false;
-    c->maskDecoded = nullptr; c->rays = nullptr; c->samples = nullptr; c->ctaSteps = nullptr; c->items = nullptr; c->itemCount = nullptr;
+    ImageSet old;
+    old.hdr[0] = c->hdr[0]; old.hdr[1] = c->hdr[1]; old.mask = c->mask;
+    old.ldr[0] = c->ldr[0]; old.ldr[1] = c->ldr[1]; old.ldrScratch = c->ldrScratch; old.maskDecoded = c->maskDecoded;
+    free_image_set(old);
+    c->ldr[0] = c->ldr[1] = c->ldrScratch = nullptr;
     c->hdr[0] = c->hdr[1] = c->mask = nullptr;
+    c->maskDecoded = nullptr;
+    cudaFree(c->debug); cudaFree(c->taps); cudaFree(c->rays); cudaFree(c->samples); cudaFree(c->ctaSteps);
+    cudaFree(c->items); cudaFree(c->itemCount);
+    cudaFree(c->tileDone);
+    cudaFree(c->maskStage);
+    c->maskStage = nullptr;
+    c->tileDone = nullptr; c->fwdBusy = false; c->fwdCheck = false; c->fwdTiles = 0;
+    c->forwardHdr = nullptr;            // mapped for the old size: the peer must re-export, the caller re-arm (mtSetCloudForward)
+    c->outHdr = c->outMask = nullptr;   // same for mtSetCloudOutput
+    for (auto& p : c->pending) p.active = false;
+    c->rays = nullptr; c->samples = nullptr; c->ctaSteps = nullptr; c->items = nullptr; c->itemCount = nullptr;
     c->debug = nullptr; c->taps = nullptr;
+}
+static void adopt_images(MtContext* c, const ImageSet& s)
+{
+    c->hdr[0] = s.hdr[0]; c->hdr[1] = s.hdr[1]; c->mask = s.mask;
+    c->ldr[0] = s.ldr[0]; c->ldr[1] = s.ldr[1]; c->ldrScratch = s.ldrScratch; c->maskDecoded = s.maskDecoded;
+    c->cur = 0;
 }
 static MtStatus alloc_images(MtContext* c)
 {
-    size_t px = (size_t)c->W * (size_t)c->H;
-    MT_CUDA(c, cudaMalloc((void**)&c->hdr[0], px * 16));
-    MT_CUDA(c, cudaMalloc((void**)&c->hdr[1], px * 16));
-    MT_CUDA(c, cudaMalloc((void**)&c->mask, px * 16));
-    MT_CUDA(c, cudaMalloc((void**)&c->ldr[0], px * 4));
-    MT_CUDA(c, cudaMalloc((void**)&c->ldr[1], px * 4));
-    MT_CUDA(c, cudaMalloc((void**)&c->ldrScratch, px * 4));
-    MT_CUDA(c, cudaMalloc((void**)&c->maskDecoded, (size_t)(c->W + 2) * (size_t)(c->H + 2) * sizeof(float)));
-    MT_CUDA(c, cudaMemsetAsync(c->hdr[0], 0, px * 16, c->stream));
-    MT_CUDA(c, cudaMemsetAsync(c->hdr[1], 0, px * 16, c->stream));
-    MT_CUDA(c, cudaMemsetAsync(c->mask, 0, px * 16, c->stream));
-    MT_CUDA(c, cudaMemsetAsync(c->ldr[0], 0, px * 4, c->stream));
-    MT_CUDA(c, cudaMemsetAsync(c->ldr[1], 0, px * 4, c->stream));
-    c->cur = 0;
+    ImageSet s;
+    const cudaError_t e = alloc_image_set(s, c->W, c->H, c->stream);
+    if (e != cudaSuccess) {
+        free_image_set(s);
+        (void)cudaGetLastError();
+        return cuda_fail(c, e, "image allocation");
+    }
+    adopt_images(c, s);
     return MT_OK;
 }
 
@@ -275,11 +320,24 @@ try {
     MT_REQUIRE(c, w > 0 && h > 0 && w <= 32768 && h <= 32768, "mtResize: bad size");
     MT_CUDA(c, cudaSetDevice(c->device));
     MT_CUDA(c, cudaStreamSynchronize(c->stream));
+    MT_CUDA(c, cudaStreamSynchronize(c->copyStream));
+    // Transactional: the images of the new size are allocated BEFORE anything of the old size is released.  On failure the
+    // context keeps its old size, images and peer state and stays fully usable (the caller sees MT_ERR_OOM / MT_ERR_CUDA).
+    ImageSet s;
+    const cudaError_t e = alloc_image_set(s, (int)w, (int)h, c->stream);
+    if (e != cudaSuccess) {
+        free_image_set(s);
+        (void)cudaGetLastError();
+        return cuda_fail(c, e, "mtResize: image allocation (context unchanged)");
+    }
+    // Success: drop everything tied to the old size.  Output redirection (mtSetCloudOutput), forwarding (mtSetCloudForward)
+    // and exported IPC handles referred to images of the old size: they are cleared here, and peers must re-export /
+    // re-open their handles and re-arm (include/meteoros_b200.h, mtResize).
     free_images(c);
     c->W = (int)w;
     c->H = (int)h;
-    c->outHdr = c->outMask = nullptr;
-    return alloc_images(c);
+    adopt_images(c, s);
+    return MT_OK;
 } MT_NOTHROW
 
 MtStatus mtSetCamera(MtContext* c, const MtCameraUBO* u)
@@ -459,15 +517,15 @@ static MtStatus cloud_dispatch(MtContext* c, int full, const RowTiles* tiles, bo
     }
     // the 1-of-16 dispatch runs step-parallel (cloud_raymarch.cu) unless counters / debug records are wanted
     const bool split = !full && !debug && !P.counters && !(c->flags & MT_FLAG_SEQUENTIAL_MARCH);
-    if (split && !c->samples) {
+    if (split) {  // lazily allocated, each pointer tested by itself: a failed allocation leaves no orphan behind
         const size_t nrays = (size_t)P.tx * (size_t)P.ty;
-        MT_CUDA(c, cudaMalloc(&c->rays, nrays * 64));
-        MT_CUDA(c, cudaMalloc((void**)&c->samples, nrays * 64 * sizeof(float2)));
-        MT_CUDA(c, cudaMalloc((void**)&c->ctaSteps, (nrays / 128 + 1) * sizeof(int)));
+        if (!c->rays) MT_CUDA(c, cudaMalloc(&c->rays, nrays * 64));
+        if (!c->samples) MT_CUDA(c, cudaMalloc((void**)&c->samples, nrays * MT_STEP_SLICES * sizeof(float2)));
+        if (!c->ctaSteps) MT_CUDA(c, cudaMalloc((void**)&c->ctaSteps, (nrays / 128 + 1) * sizeof(int)));
 #if MT_STEP_COMPACT
-        MT_CUDA(c, cudaMalloc((void**)&c->items, nrays * 64 * sizeof(unsigned)));   // only the compacting variant lists (step, ray) pairs
+        if (!c->items) MT_CUDA(c, cudaMalloc((void**)&c->items, nrays * MT_STEP_SLICES * sizeof(unsigned)));   // only the compacting variant lists (step, ray) pairs
 #endif
-        MT_CUDA(c, cudaMalloc((void**)&c->itemCount, sizeof(unsigned)));
+        if (!c->itemCount) MT_CUDA(c, cudaMalloc((void**)&c->itemCount, sizeof(unsigned)));
     }
     P.rays = c->rays;
     P.samples = c->samples;
@@ -730,6 +788,15 @@ try {
     MT_REQUIRE(c, bytes >= image_bytes(c, which), "mtReadImageAsync: host buffer too small");
     MT_CUDA(c, cudaSetDevice(c->device));
     const void* dev = image_ptr(c, which);
+    if (which == MT_IMAGE_GODRAY_MASK) {
+        // The god-ray mask is not ping-ponged (a 1-of-16 dispatch updates it in place), so a read-back straight from it would
+        // make the next Cloud dispatch wait for PCIe.  Snapshot it device-to-device on the main stream (HBM speed) and read
+        // the snapshot back on the copy stream instead.
+        if (!c->maskStage) MT_CUDA(c, cudaMalloc((void**)&c->maskStage, image_bytes(c, which)));
+        wait_pending_read(c, c->maskStage);  // the previous snapshot has left the device
+        MT_CUDA(c, cudaMemcpyAsync(c->maskStage, dev, image_bytes(c, which), cudaMemcpyDeviceToDevice, c->stream));
+        dev = c->maskStage;
+    }
     MtContext::PendingRead* slot = nullptr;
     for (auto& p : c->pending)
         if (p.active && p.dev == dev) slot = &p;     // a second read of the same image re-uses its slot
@@ -787,6 +854,7 @@ try {
     MT_CUDA(c, cudaMemsetAsync(c->mask, 0, px * 16, c->stream));
     MT_CUDA(c, cudaMemsetAsync(c->ldr[0], 0, px * 4, c->stream));
     MT_CUDA(c, cudaMemsetAsync(c->ldr[1], 0, px * 4, c->stream));
+    MT_CUDA(c, cudaMemsetAsync(c->ldrScratch, 0, px * 4, c->stream));
     return MT_OK;
 } MT_NOTHROW
 MtStatus mtImageDevicePtr(MtContext* c, MtImage which, void** p)

@@ -23,6 +23,9 @@ struct float2 { float x, y; };
 #define MT_CTA_H 8
 #endif
 
+#define MT_MAX_MARCH_ITERS 128  /* maxSteps <= 60; guards degenerate shells (also in the oracle) */
+#define MT_STEP_SLICES 64       /* step-parallel path: slices launched per ray (maxSteps <= 58 + fp slack) */
+
 struct F4 {  // 16-byte pixel; float4 on the device
     float x, y, z, w;
 };

@@ -37,8 +37,40 @@
 #include <stdlib.h>
 #include <string.h>
 
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
 #include "../include/meteoros_b200.h"
 #include "meteoros_oracle.h"
+
+/* Host threads of the OpenMP loops below.  torchrun exports OMP_NUM_THREADS=1 to every rank; the timing legs of bench.py
+ * set the count explicitly and report what the runtime really uses (one libgomp per process: the setting also governs
+ * oracle/_ref's loops). */
+int mto_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
+int mto_num_threads(void)
+{
+#ifdef _OPENMP
+    int n = 1;
+#pragma omp parallel
+    {
+#pragma omp single
+        n = omp_get_num_threads();
+    }
+    return n;
+#else
+    return 1;
+#endif
+}
 
 /* ------------------------------------------------------------------------------------------------ */
 /* small vector helpers, fp32, fixed evaluation order                                                */

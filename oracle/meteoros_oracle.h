@@ -41,6 +41,10 @@ int mto_tonemap(const MtTimeUBO* tm, int W, int H, const float* hdr, uint8_t* ld
 int mto_txaa(const MtCameraUBO* cam, const MtCameraUBO* camOld, const MtTimeUBO* tm, int W, int H, const uint8_t* cur,
              const uint8_t* prev, uint8_t* out, float* out_f32);
 
+/* OpenMP team size: set (n > 0) / query the threads the loops above really run on (bench.py's CPU timing legs). */
+int mto_set_num_threads(int n);
+int mto_num_threads(void);
+
 /* unit-test hooks */
 void mto_sample3d(const uint8_t* vol, int W, int H, int D, float s, float t, float r, float out[4]);
 void mto_sample2d(const uint8_t* img, int W, int H, float s, float t, float out[4]);
