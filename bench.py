@@ -236,7 +236,7 @@ def run_reference(args, rank, world):
         "note": "the reference application needs Vulkan + a window and ships no SPIR-V (SURVEY.md 8c); the timed arm is its Cloud "
                 "shader compiled for the CPU from its own text (kind reference) or, without oracle/_ref, the oracle port (kind port)",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)  # the process's real stdout (quiet_stdout rerouted fd 1 to stderr for library chatter)
 
 
 def sharded_8k_record(args, api, sharding, torch, dist, world, rank, local_rank, noise, steps):
