@@ -114,16 +114,41 @@ MT_DEVICE float height_gradient(float h, float cloudType)
 // unskewedSamplePoint.xz, the base cloud is scaled by the height gradient of its cloud type and its red channel
 // replaces the constant coverage -- so neither the empty-cell bitmap (built for one coverage) nor the "nice" division
 // (1 - coverage may be 0) applies on that path.
-template <bool WEATHER>
+// STD = the textures have the reference's extents (low 128^3, high 32^3, curl 128^2: Sky.cpp:31-50), which the host checks
+// per dispatch: the extents become immediates (no constant-bank loads, shifts instead of multiplies in the addressing).
+template <bool STD>
+MT_DEVICE Tex3D std_low(const Tex3D& t)
+{
+    Tex3D r = t;
+    if (STD) r.w = r.h = r.d = 128;
+    return r;
+}
+template <bool STD>
+MT_DEVICE Tex3D std_high(const Tex3D& t)
+{
+    Tex3D r = t;
+    if (STD) r.w = r.h = r.d = 32;
+    return r;
+}
+template <bool STD>
+MT_DEVICE Tex2D std_curl(const Tex2D& t)
+{
+    Tex2D r = t;
+    if (STD) r.w = r.h = 128;
+    return r;
+}
+
+template <bool WEATHER, bool STD>
 MT_DEVICE float low_freq_density(const CloudParams& P, float coverage, P2 pxy, float pz, float ux, float uz, float relH)
 {
-    const Tex3D& low = P.low;
+    const Tex3D low = std_low<STD>(P.low);
     LinAxis X, Y, Z = lin_axis_repeat(pz, low.d);
     lin_axes_xy(pxy, low.w, low.h, X, Y);
+    const unsigned cell = tex_cell(low, X.i0, Y.i0, Z.i0);
     // provably empty filter cell: the result is exactly +0.  A warp whose lanes all sit in empty cells skips the
     // whole fetch + filter (SIMT: the branch is free when nobody takes it).
-    if (!WEATHER && low.occ && !occ_cell_may_be_cloud(low, X.i0, Y.i0, Z.i0)) return 0.0f;
-    Rgba n = tex3d_rgba_axes(low, X, Y, Z);
+    if (!WEATHER && low.occ && !occ_cell_may_be_cloud(low, cell)) return 0.0f;
+    Rgba n = tex3d_rgba_axes(low, X, Y, Z, cell);
     float fbm = sat1((n.g * 0.625f + n.b * 0.25f) + n.a * 0.125f);
     float omin = fbm - 0.9f;
     float base = sat1(div_nice(n.r - omin, 1.0f - omin));  // remapClamped(r, fbm-.9, 1, 0, 1); denominator in [0.9, 1.9]
@@ -249,7 +274,7 @@ struct StepBase {
     float h, baseDensity;
 };
 
-template <bool COUNT, bool WEATHER>
+template <bool COUNT, bool WEATHER, bool STD>
 MT_DEVICE StepBase cloud_step_base(const CloudParams& P, const MarchConst& M, const RaySetup& R, int jidx, float t, RayCounters& cnt)
 {
     StepBase B;
@@ -268,37 +293,56 @@ MT_DEVICE StepBase cloud_step_base(const CloudParams& P, const MarchConst& M, co
     // skewSamplePointWithWind (:489-497)
     f3 skew = (sp + ((wind * h) * P.tun.cloud_top_offset) * 0.009f) + M.windSkew;
     B.pos = pos; B.skew = skew; B.h = h;
-    B.baseDensity = low_freq_density<WEATHER>(P, P.tun.coverage, pk2(skew.x, skew.y), skew.z, pos.x, pos.z, h) * P.tun.base_density_factor;
+    B.baseDensity = low_freq_density<WEATHER, STD>(P, P.tun.coverage, pk2(skew.x, skew.y), skew.z, pos.x, pos.z, h) * P.tun.base_density_factor;
     if (COUNT) cnt.steps++;
     return B;
 }
 
 // The in-cloud part of a march iteration (cloudRayMarch.comp:642-672): erosion, the six light-cone samples, light
 // energy.  Call only when B.baseDensity > 0.
-template <bool COUNT, bool WEATHER>
-MT_DEVICE StepSample cloud_step_light(const CloudParams& P, const MarchConst& M, const RaySetup& R, const StepBase& B, RayCounters& cnt)
+// The six light-cone offsets of one ray, (stepSize * noise_kernel[i]) * i, are the same at every step: the one-thread-per-ray
+// kernel computes them once per ray into shared memory (xy pairs and z, [i][thread]: conflict-free) and each in-cloud step
+// reads them back -- two loads instead of a float conversion and four multiplies per cone sample, the same values.
+struct ConeOffsets {
+    const P2* xy;     // this thread's first pair; the pair of sample i is xy[i * stride]   (null: compute per step)
+    const float* z;
+    int stride;
+};
+MT_DEVICE void cone_offset(const MarchConst& M, float stepSize, int i, P2& xy, float& z)
+{
+    const float fi = (float)i;
+    const f3 cs = M.coneStep[i];
+    xy = mul2(mul2(pk2(cs.x, cs.y), bc2(stepSize)), bc2(fi));
+    z = (cs.z * stepSize) * fi;
+}
+
+template <bool COUNT, bool WEATHER, bool STD>
+MT_DEVICE StepSample cloud_step_light(const CloudParams& P, const MarchConst& M, const RaySetup& R, const StepBase& B, RayCounters& cnt,
+                                      const ConeOffsets& CO)
 {
     StepSample S;
     const f3 ec = M.earthCenter, pos = B.pos, skew = B.skew;
     const f3 relOrigin = mk3(ec.x, MT_R_INNER - MT_EARTH_RADIUS, ec.z);
     const float coverage = P.tun.coverage, h = B.h, baseDensity = B.baseDensity;
     if (COUNT) cnt.incloud++;
-    float edge = erosion_edge(P.curl, P.high, skew, h);
+    float edge = erosion_edge(std_curl<STD>(P.curl), std_high<STD>(P.high), skew, h);
     S.inc = erode(baseDensity * 1.4f, edge) * 0.5f;
     float dl = 0.0f;
     const P2 relxy = pk2(relOrigin.x, relOrigin.y);
 #pragma unroll 1
     for (int i = 0; i < 6; ++i) {  // one copy of the filter in the instruction stream (I-cache)
         // lightPos = pos + (stepSize * noise_kernel[i]) * i ; sample = (lightPos - relOrigin) / 12500  -- x,y as a pair
-        const float fi = (float)i;
-        const f3 cs = M.coneStep[i];
-        const P2 off = mul2(mul2(pk2(cs.x, cs.y), bc2(R.stepSize)), bc2(fi));
-        // scalar adds: a mul2 feeding an add2 would be contracted into an FFMA2 (mt_math.cuh)
-        P2 lxy = sub2(pk2(pos.x + lo2(off), pos.y + hi2(off)), relxy);
-        float lz = (pos.z + (cs.z * R.stepSize) * fi) - relOrigin.z;
+        P2 off;
+        float offz;
+        if (CO.xy) { off = CO.xy[i * CO.stride]; offz = CO.z[i * CO.stride]; }
+        else cone_offset(M, R.stepSize, i, off, offz);
+        // the offset products are separate values (memory or scalar adds): a mul2 feeding an add2 would be contracted into
+        // an FFMA2 (mt_math.cuh)
+        P2 lxy = sub2(CO.xy ? add2(pk2(pos.x, pos.y), off) : pk2(pos.x + lo2(off), pos.y + hi2(off)), relxy);
+        float lz = (pos.z + offz) - relOrigin.z;
         const P2 sxy = div_thickness2(lxy);
         const float sz = div_thickness(lz);
-        float cur = low_freq_density<WEATHER>(P, coverage, sxy, sz, lo2(sxy), sz, h);
+        float cur = low_freq_density<WEATHER, STD>(P, coverage, sxy, sz, lo2(sxy), sz, h);
         if (cur > 0.0f) {
             if (COUNT) cnt.cone++;
             dl += erode(1.5f * cur, edge);
@@ -309,12 +353,12 @@ MT_DEVICE StepSample cloud_step_light(const CloudParams& P, const MarchConst& M,
 }
 
 // One iteration of the march loop (cloudRayMarch.comp:629-678) at parameter t, without the running sums.
-template <bool COUNT, bool WEATHER>
+template <bool COUNT, bool WEATHER, bool STD>
 MT_DEVICE StepSample cloud_step_sample(const CloudParams& P, const MarchConst& M, const RaySetup& R, int jidx, float t,
-                                       RayCounters& cnt)
+                                       RayCounters& cnt, const ConeOffsets& CO)
 {
-    const StepBase B = cloud_step_base<COUNT, WEATHER>(P, M, R, jidx, t, cnt);
-    if (B.baseDensity > 0.0f) return cloud_step_light<COUNT, WEATHER>(P, M, R, B, cnt);
+    const StepBase B = cloud_step_base<COUNT, WEATHER, STD>(P, M, R, jidx, t, cnt);
+    if (B.baseDensity > 0.0f) return cloud_step_light<COUNT, WEATHER, STD>(P, M, R, B, cnt, CO);
     StepSample S;
     S.inc = 0.0f;
     S.energy = -1.0f;
@@ -353,9 +397,9 @@ MT_DEVICE void cloud_composite(const RaySetup& R, float accum, float color, F4& 
 }
 
 // One invocation of main(): setup, the sequential march, composite.
-template <bool COUNT, bool DEBUG, bool WEATHER>
+template <bool COUNT, bool DEBUG, bool WEATHER, bool STD>
 MT_DEVICE void cloud_ray(const CloudParams& P, const MarchConst& M, int px, int py, int pixelID, F4& hdr, F4& mask,
-                         RayCounters& cnt, MtRayDebug* dbg)
+                         RayCounters& cnt, MtRayDebug* dbg, P2* coneXY, float* coneZ, int coneStride)
 {
     mask.x = mask.y = mask.z = mask.w = 0.0f;
     const RaySetup R = cloud_ray_setup(P, M, px, py, pixelID, hdr);
@@ -367,6 +411,12 @@ MT_DEVICE void cloud_ray(const CloudParams& P, const MarchConst& M, int px, int 
     }
     if (R.branch != 2) return;
 
+    ConeOffsets CO;
+    CO.xy = coneXY; CO.z = coneZ; CO.stride = coneStride;
+    if (coneXY) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) cone_offset(M, R.stepSize, i, coneXY[i * coneStride], coneZ[i * coneStride]);
+    }
     float accum = 0.0f, transmittance = 1.0f, color = 0.0f;
     unsigned jhash = 2166136261u;
     int iters = 0;
@@ -375,7 +425,7 @@ MT_DEVICE void cloud_ray(const CloudParams& P, const MarchConst& M, int px, int 
     for (float t = R.t_in; t < R.t_out && iters < MT_MAX_MARCH_ITERS; t += R.stepSize, ++iters) {
         const int jidx = (pixelID + mt_f2i(t)) & 15;  // int(mod(float(pixelID + int(t)), 16.0)), argument >= 0
         if (DEBUG) jhash = (jhash ^ (unsigned)jidx) * 16777619u;
-        const StepSample S = cloud_step_sample<COUNT, WEATHER>(P, M, R, jidx, t, cnt);
+        const StepSample S = cloud_step_sample<COUNT, WEATHER, STD>(P, M, R, jidx, t, cnt, CO);
         if (cloud_step_combine(S, accum, transmittance, color)) {
             if (COUNT) cnt.early++;
             ++iters;

@@ -79,12 +79,15 @@ cudaError_t mt_launch_occupancy(const Tex3D& low, uint32_t* occ, float coverage,
 
 __device__ __forceinline__ float f16_round(float x) { return __half2float(__float2half_rn(x)); }
 
-template <bool FULL, bool COUNT, bool DEBUG, bool WEATHER>
+template <bool FULL, bool COUNT, bool DEBUG, bool WEATHER, bool STD>
 #ifndef MT_BOTTOM_UP
 #define MT_BOTTOM_UP 0  /* A/B at 4K and 8K: no measurable difference (5.09 ms both) */
 #endif
 #ifndef MT_CLOUD_MINBLOCKS
 #define MT_CLOUD_MINBLOCKS 8  /* 64 registers/thread: 8 CTAs = 32 warps per SM (profiles/r1_cloud_ab.md) */
+#endif
+#ifndef MT_CONE_CACHE
+#define MT_CONE_CACHE 1       /* per-ray light-cone offsets in shared memory (9 KB per CTA) */
 #endif
 __global__ void __launch_bounds__(128, MT_CLOUD_MINBLOCKS) cloud_raymarch_kernel(const __grid_constant__ CloudParams P)
 {
@@ -144,11 +147,21 @@ __global__ void __launch_bounds__(128, MT_CLOUD_MINBLOCKS) cloud_raymarch_kernel
         reinterpret_cast<float*>(&M)[threadIdx.x] = __ldg(reinterpret_cast<const float*>(P.mc) + threadIdx.x);
     __syncthreads();
 
+    // per-ray light-cone offsets (cloud_core.cuh, ConeOffsets): [sample][thread], written once per marching ray
+#if MT_CONE_CACHE
+    __shared__ P2 coneXY[6][128];
+    __shared__ float coneZ[6][128];
+    P2* const cxy = &coneXY[0][threadIdx.x];
+    float* const cz = &coneZ[0][threadIdx.x];
+#else
+    P2* const cxy = nullptr;
+    float* const cz = nullptr;
+#endif
     RayCounters cnt = { 0u, 0u, 0u, 0u, 0u, 0u };
     if (valid) {
         F4 hdr, mask;
         const size_t idx = (size_t)py * (size_t)P.W + (size_t)px;
-        cloud_ray<COUNT, DEBUG, WEATHER>(P, M, px, py, pixelID, hdr, mask, cnt, DEBUG ? (P.debug + idx) : nullptr);
+        cloud_ray<COUNT, DEBUG, WEATHER, STD>(P, M, px, py, pixelID, hdr, mask, cnt, DEBUG ? (P.debug + idx) : nullptr, cxy, cz, 128);
         if (P.f16_emulate) {
             hdr.x = f16_round(hdr.x); hdr.y = f16_round(hdr.y); hdr.z = f16_round(hdr.z); hdr.w = f16_round(hdr.w);
             mask.x = f16_round(mask.x); mask.y = f16_round(mask.y); mask.z = f16_round(mask.z); mask.w = f16_round(mask.w);
@@ -260,7 +273,7 @@ __global__ void __launch_bounds__(128) cloud_rays_kernel(const __grid_constant__
 #ifndef MT_STEPS_MINBLOCKS
 #define MT_STEPS_MINBLOCKS 12  /* 39 registers, no spills: 48 warps per SM; the step-parallel march is latency bound (profiles/r1_ab.md) */
 #endif
-template <bool WEATHER>
+template <bool WEATHER, bool STD>
 __global__ void __launch_bounds__(128, MT_STEPS_MINBLOCKS) cloud_steps_kernel(const __grid_constant__ CloudParams P)
 {
     const int k = blockIdx.y;
@@ -274,7 +287,8 @@ __global__ void __launch_bounds__(128, MT_STEPS_MINBLOCKS) cloud_steps_kernel(co
     if (R.branch != 2 || k >= R.nsteps) return;
     const int jidx = (P.tm.frameCountMod16 + mt_f2i(t)) & 15;
     RayCounters none = { 0u, 0u, 0u, 0u, 0u, 0u };
-    const StepSample S = cloud_step_sample<false, WEATHER>(P, M, R, jidx, t, none);
+    const ConeOffsets noCache = { nullptr, nullptr, 0 };  // one thread per (ray, step): nothing to share
+    const StepSample S = cloud_step_sample<false, WEATHER, STD>(P, M, R, jidx, t, none, noCache);
     *slot = make_float2(S.inc, S.energy);
 }
 
@@ -292,7 +306,7 @@ __global__ void __launch_bounds__(128, MT_STEPS_MINBLOCKS) cloud_steps_kernel(co
 #endif
 #define MT_ITEM_RAY_BITS 26
 
-template <bool WEATHER>
+template <bool WEATHER, bool STD>
 __global__ void __launch_bounds__(128, MT_CLOUD_MINBLOCKS) cloud_base_kernel(const __grid_constant__ CloudParams P)
 {
     const int k = blockIdx.y;
@@ -308,7 +322,7 @@ __global__ void __launch_bounds__(128, MT_CLOUD_MINBLOCKS) cloud_base_kernel(con
     if (live) {
         const int jidx = (P.tm.frameCountMod16 + mt_f2i(t)) & 15;
         RayCounters none = { 0u, 0u, 0u, 0u, 0u, 0u };
-        hit = cloud_step_base<false, WEATHER>(P, M, R, jidx, t, none).baseDensity > 0.0f;
+        hit = cloud_step_base<false, WEATHER, STD>(P, M, R, jidx, t, none).baseDensity > 0.0f;
         if (!hit) P.samples[(size_t)k * (size_t)P.rayStride + ray] = make_float2(0.0f, -1.0f);
     }
     const unsigned hits = __ballot_sync(0xffffffffu, hit);
@@ -321,7 +335,7 @@ __global__ void __launch_bounds__(128, MT_CLOUD_MINBLOCKS) cloud_base_kernel(con
     }
 }
 
-template <bool WEATHER>
+template <bool WEATHER, bool STD>
 __global__ void __launch_bounds__(128, MT_CLOUD_MINBLOCKS) cloud_light_kernel(const __grid_constant__ CloudParams P)
 {
     __shared__ MarchConst M;
@@ -337,8 +351,9 @@ __global__ void __launch_bounds__(128, MT_CLOUD_MINBLOCKS) cloud_light_kernel(co
         for (int j = 0; j < k; ++j) t += R.stepSize;
         const int jidx = (P.tm.frameCountMod16 + mt_f2i(t)) & 15;
         RayCounters none = { 0u, 0u, 0u, 0u, 0u, 0u };
-        const StepBase B = cloud_step_base<false, WEATHER>(P, M, R, jidx, t, none);   // same arithmetic: B.baseDensity > 0 again
-        const StepSample S = cloud_step_light<false, WEATHER>(P, M, R, B, none);
+        const StepBase B = cloud_step_base<false, WEATHER, STD>(P, M, R, jidx, t, none);   // same arithmetic: B.baseDensity > 0 again
+        const ConeOffsets noCache = { nullptr, nullptr, 0 };
+        const StepSample S = cloud_step_light<false, WEATHER, STD>(P, M, R, B, none, noCache);
         P.samples[(size_t)k * (size_t)P.rayStride + ray] = make_float2(S.inc, S.energy);
     }
 }
@@ -375,6 +390,13 @@ __global__ void __launch_bounds__(128) cloud_fold_kernel(const __grid_constant__
     store_pixel(P, (size_t)py * P.W + px, hdr, mask);
 }
 
+// the reference's texture extents (Sky.cpp:31-50): the STD kernels carry them as immediates
+static bool mt_std_dims(const CloudParams& P)
+{
+    return P.low.w == 128 && P.low.h == 128 && P.low.d == 128 && P.high.w == 32 && P.high.h == 32 && P.high.d == 32 &&
+           P.curl.w == 128 && P.curl.h == 128;
+}
+
 cudaError_t mt_launch_cloud_sixteenth_split(const CloudParams& P0, cudaStream_t stream, int* launches)
 {
     CloudParams P = P0;
@@ -383,6 +405,7 @@ cudaError_t mt_launch_cloud_sixteenth_split(const CloudParams& P0, cudaStream_t 
     if ((size_t)P.rayStride > ((size_t)1 << MT_ITEM_RAY_BITS)) return cudaErrorInvalidValue;
     cloud_rays_kernel<<<ctas, 128, 0, stream>>>(P);
     const dim3 slices(ctas, MT_STEP_SLICES, 1);
+    const bool std_dims = mt_std_dims(P);
 #if MT_STEP_COMPACT
     static int sms = 0;
     if (!sms) {
@@ -392,16 +415,20 @@ cudaError_t mt_launch_cloud_sixteenth_split(const CloudParams& P0, cudaStream_t 
     }
     const unsigned walkers = (unsigned)sms * MT_CLOUD_MINBLOCKS;   // one resident wave walks the whole list
     if (P.tun.use_weather) {
-        cloud_base_kernel<true><<<slices, 128, 0, stream>>>(P);
-        cloud_light_kernel<true><<<walkers, 128, 0, stream>>>(P);
+        cloud_base_kernel<true, false><<<slices, 128, 0, stream>>>(P);
+        cloud_light_kernel<true, false><<<walkers, 128, 0, stream>>>(P);
+    } else if (std_dims) {
+        cloud_base_kernel<false, true><<<slices, 128, 0, stream>>>(P);
+        cloud_light_kernel<false, true><<<walkers, 128, 0, stream>>>(P);
     } else {
-        cloud_base_kernel<false><<<slices, 128, 0, stream>>>(P);
-        cloud_light_kernel<false><<<walkers, 128, 0, stream>>>(P);
+        cloud_base_kernel<false, false><<<slices, 128, 0, stream>>>(P);
+        cloud_light_kernel<false, false><<<walkers, 128, 0, stream>>>(P);
     }
     *launches = 4;
 #else
-    if (P.tun.use_weather) cloud_steps_kernel<true><<<slices, 128, 0, stream>>>(P);
-    else cloud_steps_kernel<false><<<slices, 128, 0, stream>>>(P);
+    if (P.tun.use_weather) cloud_steps_kernel<true, false><<<slices, 128, 0, stream>>>(P);
+    else if (std_dims) cloud_steps_kernel<false, true><<<slices, 128, 0, stream>>>(P);
+    else cloud_steps_kernel<false, false><<<slices, 128, 0, stream>>>(P);
     *launches = 3;
 #endif
     cloud_fold_kernel<<<ctas, 128, 0, stream>>>(P);
@@ -476,17 +503,19 @@ cudaError_t mt_launch_cloud(const CloudParams& P, cudaStream_t stream)
     dim3 block(128, 1, 1);
     if (grid.x == 0 || grid.y == 0) return cudaSuccess;
     const bool count = P.counters != nullptr, debug = P.debug != nullptr;
+    const bool std_dims = mt_std_dims(P);
     if (P.tun.use_weather) {  // weather path: production variants only (mt_context.cu rejects counters / debug with it)
-        if (P.full) cloud_raymarch_kernel<true, false, false, true><<<grid, block, 0, stream>>>(P);
-        else cloud_raymarch_kernel<false, false, false, true><<<grid, block, 0, stream>>>(P);
+        if (P.full) cloud_raymarch_kernel<true, false, false, true, false><<<grid, block, 0, stream>>>(P);
+        else cloud_raymarch_kernel<false, false, false, true, false><<<grid, block, 0, stream>>>(P);
     } else if (P.full) {
-        if (debug) cloud_raymarch_kernel<true, true, true, false><<<grid, block, 0, stream>>>(P);
-        else if (count) cloud_raymarch_kernel<true, true, false, false><<<grid, block, 0, stream>>>(P);
-        else cloud_raymarch_kernel<true, false, false, false><<<grid, block, 0, stream>>>(P);
+        if (debug) cloud_raymarch_kernel<true, true, true, false, false><<<grid, block, 0, stream>>>(P);
+        else if (count) cloud_raymarch_kernel<true, true, false, false, false><<<grid, block, 0, stream>>>(P);
+        else if (std_dims) cloud_raymarch_kernel<true, false, false, false, true><<<grid, block, 0, stream>>>(P);
+        else cloud_raymarch_kernel<true, false, false, false, false><<<grid, block, 0, stream>>>(P);
     } else {
-        if (debug) cloud_raymarch_kernel<false, true, true, false><<<grid, block, 0, stream>>>(P);
-        else if (count) cloud_raymarch_kernel<false, true, false, false><<<grid, block, 0, stream>>>(P);
-        else cloud_raymarch_kernel<false, false, false, false><<<grid, block, 0, stream>>>(P);
+        if (debug) cloud_raymarch_kernel<false, true, true, false, false><<<grid, block, 0, stream>>>(P);
+        else if (count) cloud_raymarch_kernel<false, true, false, false, false><<<grid, block, 0, stream>>>(P);
+        else cloud_raymarch_kernel<false, false, false, false, false><<<grid, block, 0, stream>>>(P);
     }
     return cudaGetLastError();
 }

@@ -55,10 +55,13 @@ struct LinAxis {
     float w0, w1;
 };
 
+// index of filter cell (x0, y0, z0): addresses the quad copy and (>> 5, & 31) the empty-cell bitmap
+MT_DEVICE unsigned tex_cell(const Tex3D& T, unsigned x0, unsigned y0, unsigned z0) { return (z0 * (unsigned)T.h + y0) * (unsigned)T.w + x0; }
+
 MT_DEVICE LinAxis lin_axis_repeat(float s, int n)
 {
     LinAxis a;
-    float u = s * (float)n - 0.5f;
+    float u = fmaf(s, (float)n, -0.5f);  // == s*n - 0.5 bit for bit: n is a power of two, the product is never rounded
     int fi = mt_floor2i(u);   // F2I.FLOOR (XU) ...
     float fl = (float)fi;     // ... and I2FP back (ALU): == floorf(u) for |u| < 2^24, one XU op instead of two
     a.w1 = u - fl;
@@ -71,10 +74,10 @@ MT_DEVICE LinAxis lin_axis_repeat(float s, int n)
 // x and y axes of one sample computed as a pair (FMUL2 / FADD2), identical per-component arithmetic
 MT_DEVICE void lin_axes_xy(P2 st, int nx, int ny, LinAxis& X, LinAxis& Y)
 {
-    const P2 m = mul2(st, pk2((float)nx, (float)ny));
-    const float ux = lo2(m) - 0.5f, uy = hi2(m) - 0.5f;  // scalar: mul2 -> sub2 would be contracted (mt_math.cuh)
+    const P2 u = fma2(st, pk2((float)nx, (float)ny), bc2(-0.5f));  // exact product (power-of-two extent): == s*n - 0.5
+    const float ux = lo2(u), uy = hi2(u);
     int fx = mt_floor2i(ux), fy = mt_floor2i(uy);
-    P2 w1 = sub2(pk2(ux, uy), pk2((float)fx, (float)fy));
+    P2 w1 = sub2(u, pk2((float)fx, (float)fy));
     P2 w0 = sub2(bc2(1.0f), w1);
     X.w1 = lo2(w1); X.w0 = lo2(w0);
     Y.w1 = hi2(w1); Y.w0 = hi2(w0);
@@ -132,7 +135,7 @@ MT_DEVICE Weights8 filter_weights(const LinAxis& X, const LinAxis& Y, const LinA
     fma2(bc2(lo2(w.w10)), CH(t100), fma2(bc2(hi2(w.w01)), CH(t011), fma2(bc2(lo2(w.w01)), CH(t010),                      \
     fma2(bc2(hi2(w.w00)), CH(t001), mul2(bc2(lo2(w.w00)), CH(t000)))))))))
 
-MT_DEVICE Rgba tex3d_rgba_axes(const Tex3D& T, const LinAxis& X, const LinAxis& Y, const LinAxis& Z)
+MT_DEVICE Rgba tex3d_rgba_axes(const Tex3D& T, const LinAxis& X, const LinAxis& Y, const LinAxis& Z, unsigned cell)
 {
     // 32-bit unsigned texel offsets from one uniform base: no 64-bit pointer arithmetic per texel
     const unsigned W = (unsigned)T.w, H = (unsigned)T.h;
@@ -140,12 +143,13 @@ MT_DEVICE Rgba tex3d_rgba_axes(const Tex3D& T, const LinAxis& X, const LinAxis& 
 #if MT_TEX_QUADS
     {
 #if MT_TEX_BRICKS  // 3D: the cell's 2x2x2 texels are 32 contiguous bytes (8x the memory)
-        const Quad* bp = T.quads + 2u * ((Z.i0 * H + Y.i0) * W + X.i0);
+        const Quad* bp = T.quads + 2u * cell;
         const Quad q0 = MT_LDG_QUAD(bp);
         const Quad q1 = MT_LDG_QUAD(bp + 1);
 #else
-        const Quad q0 = MT_LDG_QUAD(T.quads + ((Z.i0 * H + Y.i0) * W + X.i0));
-        const Quad q1 = MT_LDG_QUAD(T.quads + ((Z.i1 * H + Y.i0) * W + X.i0));
+        // slice z1 = (z0 + 1) mod d: one slice further, wrapped by masking the cell index (w*h*d is a power of two)
+        const Quad q0 = MT_LDG_QUAD(T.quads + cell);
+        const Quad q1 = MT_LDG_QUAD(T.quads + ((cell + W * H) & (W * H * (unsigned)T.d - 1u)));
 #endif
         t000 = q0.x; t001 = q0.y; t010 = q0.z; t011 = q0.w;
         t100 = q1.x; t101 = q1.y; t110 = q1.z; t111 = q1.w;
@@ -172,7 +176,7 @@ MT_DEVICE Rgba tex3d_rgba_axes(const Tex3D& T, const LinAxis& X, const LinAxis& 
 MT_DEVICE Rgba tex3d_rgba(const Tex3D& T, float s, float t, float r)
 {
     LinAxis X = lin_axis_repeat(s, T.w), Y = lin_axis_repeat(t, T.h), Z = lin_axis_repeat(r, T.d);
-    return tex3d_rgba_axes(T, X, Y, Z);
+    return tex3d_rgba_axes(T, X, Y, Z, tex_cell(T, X.i0, Y.i0, Z.i0));
 }
 
 // ---- empty-cell map of the low-frequency volume ----------------------------------------------------------------------
@@ -190,11 +194,13 @@ MT_DEVICE bool occ_texel_may_be_cloud(uint32_t texel, float coverage)
     float L = r * (1.0f / 255.0f) - (1.0f - coverage) * fbm;
     return L > (1.9f * coverage - 0.9f) - MT_OCC_MARGIN;
 }
-MT_DEVICE bool occ_cell_may_be_cloud(const Tex3D& T, unsigned x0, unsigned y0, unsigned z0)
+// cell = (z0*h + y0)*w + x0: the bitmap is x fastest, 32 cells per word, and w is a multiple of 32 -- so the word is
+// cell >> 5 and the bit cell & 31 (the shift instruction takes the low five bits by itself).  The same cell index
+// addresses the quad copy, so the test costs a shift, a load and a bit test on top of the fetch's own addressing.
+MT_DEVICE bool occ_cell_may_be_cloud(const Tex3D& T, unsigned cell)
 {
-    const unsigned wpr = (unsigned)T.w >> 5;  // words per row
-    uint32_t word = MT_LDG(T.occ + ((z0 * (unsigned)T.h + y0) * wpr + (x0 >> 5)));
-    return (word >> (x0 & 31u)) & 1u;
+    const uint32_t word = MT_LDG(T.occ + (cell >> 5));
+    return (word >> (cell & 31u)) & 1u;
 }
 
 // Same filter, only the first three channels (the high-frequency volume's alpha is never read).
@@ -210,8 +216,9 @@ MT_DEVICE Rgba tex3d_rgb(const Tex3D& T, float s, float t, float r)
         const Quad q0 = MT_LDG_QUAD(bp);
         const Quad q1 = MT_LDG_QUAD(bp + 1);
 #else
-        const Quad q0 = MT_LDG_QUAD(T.quads + ((Z.i0 * H + Y.i0) * W + X.i0));
-        const Quad q1 = MT_LDG_QUAD(T.quads + ((Z.i1 * H + Y.i0) * W + X.i0));
+        const unsigned cell = (Z.i0 * H + Y.i0) * W + X.i0;
+        const Quad q0 = MT_LDG_QUAD(T.quads + cell);
+        const Quad q1 = MT_LDG_QUAD(T.quads + ((cell + W * H) & (W * H * (unsigned)T.d - 1u)));
 #endif
         t000 = q0.x; t001 = q0.y; t010 = q0.z; t011 = q0.w;
         t100 = q1.x; t101 = q1.y; t110 = q1.z; t111 = q1.w;

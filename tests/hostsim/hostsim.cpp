@@ -79,6 +79,8 @@ int hs_cloud(const MtCameraUBO* cam, const MtTimeUBO* tm, const MtTuning* tun, c
             F4 h, m;
             size_t idx = (size_t)py * W + px;
             MtRayDebug scratch;
+            P2 coneXY[6];   // the kernel's per-ray light-cone offset cache (shared memory there), stride 1 here
+            float coneZ[6];
             memset(&cnt, 0, sizeof(cnt));
             if (full == 2) {
                 // The step-parallel decomposition of the 1-of-16 dispatch (cloud_rays_kernel / cloud_steps_kernel /
@@ -94,10 +96,11 @@ int hs_cloud(const MtCameraUBO* cam, const MtTimeUBO* tm, const MtTuning* tun, c
                     R.nsteps = n;
                     StepSample S[MT_STEP_SLICES];
                     RayCounters none = { 0, 0, 0, 0, 0, 0 };
+                    const ConeOffsets noCache = { nullptr, nullptr, 0 };
                     for (int k = n - 1; k >= 0; --k) {
                         const int jidx = (P.tm.frameCountMod16 + mt_f2i(tk[k])) & 15;
-                        S[k] = tun->use_weather ? cloud_step_sample<false, true>(P, M, R, jidx, tk[k], none)
-                                                : cloud_step_sample<false, false>(P, M, R, jidx, tk[k], none);
+                        S[k] = tun->use_weather ? cloud_step_sample<false, true, false>(P, M, R, jidx, tk[k], none, noCache)
+                                                : cloud_step_sample<false, false, false>(P, M, R, jidx, tk[k], none, noCache);
                     }
                     float accum = 0.0f, transmittance = 1.0f, color = 0.0f;
                     for (int k = 0; k < R.nsteps; ++k)
@@ -108,8 +111,10 @@ int hs_cloud(const MtCameraUBO* cam, const MtTimeUBO* tm, const MtTuning* tun, c
                 memcpy(mask + 4 * idx, &m, 16);
                 continue;
             }
-            if (tun->use_weather) cloud_ray<true, true, true>(P, M, px, py, id, h, m, cnt, debug ? debug + idx : &scratch);
-            else cloud_ray<true, true, false>(P, M, px, py, id, h, m, cnt, debug ? debug + idx : &scratch);
+            if (tun->use_weather) cloud_ray<true, true, true, false>(P, M, px, py, id, h, m, cnt, debug ? debug + idx : &scratch, coneXY, coneZ, 1);
+            else if (lw == 128 && lh == 128 && ld == 128 && hw == 32 && hh == 32 && hd == 32 && cw == 128 && ch == 128)  // STD: extents as immediates
+                cloud_ray<true, true, false, true>(P, M, px, py, id, h, m, cnt, debug ? debug + idx : &scratch, coneXY, coneZ, 1);
+            else cloud_ray<true, true, false, false>(P, M, px, py, id, h, m, cnt, debug ? debug + idx : &scratch, nullptr, nullptr, 0);
             tot[0] += cnt.rays; tot[1] += cnt.marched; tot[2] += cnt.steps; tot[3] += cnt.incloud; tot[4] += cnt.cone; tot[5] += cnt.early;
             memcpy(hdr + 4 * idx, &h, 16);
             memcpy(mask + 4 * idx, &m, 16);

@@ -102,7 +102,7 @@ extern "C" int ws_run(const MtCameraUBO* cam, const MtTimeUBO* tm, const MtTunin
                         int id = ((px & 3) << 2) | (py & 3);
                         const int jidx = (id + mt_f2i(t[l])) & 15;
                         RayCounters none = {0,0,0,0,0,0};
-                        StepBase B = cloud_step_base<false, false>(P, M, R[l], jidx, t[l], none);
+                        StepBase B = cloud_step_base<false, false, false>(P, M, R[l], jidx, t[l], none);
                         StepSample smp; smp.inc = 0; smp.energy = -1;
                         if (B.baseDensity > 0.0f) {
                             hits++;
@@ -118,13 +118,13 @@ extern "C" int ws_run(const MtCameraUBO* cam, const MtTimeUBO* tm, const MtTunin
                                 float sx = div_thickness(lx), sy = div_thickness(ly), sz = div_thickness(lz);
                                 LinAxis X = lin_axis_repeat(sx, lw), Y = lin_axis_repeat(sy, lh), Z = lin_axis_repeat(sz, ld);
                                 cone_l[i]++;
-                                if (occ_cell_may_be_cloud(P.low, X.i0, Y.i0, Z.i0)) {
+                                if (occ_cell_may_be_cloud(P.low, tex_cell(P.low, X.i0, Y.i0, Z.i0))) {
                                     cone_ne[i]++;
-                                    float cur = low_freq_density<false>(P, P.tun.coverage, pk2(sx, sy), sz, sx, sz, B.h);
+                                    float cur = low_freq_density<false, false>(P, P.tun.coverage, pk2(sx, sy), sz, sx, sz, B.h);
                                     if (cur > 0.0f) cone_h[i]++;
                                 }
                             }
-                            smp = cloud_step_light<false, false>(P, M, R[l], B, none);
+                            { const ConeOffsets noCache = { nullptr, nullptr, 0 }; smp = cloud_step_light<false, false, false>(P, M, R[l], B, none, noCache); }
                         }
                         if (cloud_step_combine(smp, accum[l], tr[l], col[l])) { live[l] = false; early[l] = true; }
                         else {
