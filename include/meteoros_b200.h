@@ -105,6 +105,9 @@ typedef struct MtConfig {
 #define MT_FLAG_COUNTERS 1u    /* cloud pass also accumulates MtCounters (slower; for work accounting) */
 #define MT_FLAG_PASS_TIMING 2u /* bracket every pass with CUDA events so mtLastPassMs works               */
 #define MT_FLAG_SEQUENTIAL_MARCH 4u /* 1-of-16 dispatch: one kernel, one thread per ray (default: step-parallel) */
+#define MT_FLAG_NO_CONE_RF 16u      /* light-cone samples through the canonical four-channel filter instead of the (r, F) form of
+                                     * the low-frequency volume (saves its 4 bytes/cell copy; bit-identical decisions either way,
+                                     * radiance equal to rounding).  Must be set before the low-frequency texture is uploaded. */
 
 /* Texture slots = set 1 of the cloud pipeline (Renderer.cpp:1110-1114, cloudRayMarch.comp:9-12). */
 typedef enum MtTextureSlot {

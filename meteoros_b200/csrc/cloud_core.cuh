@@ -11,6 +11,11 @@
 
 #include "mt_params.h"
 
+// MT_CONE_RF: light-cone samples from the (r, F) form of the low-frequency volume (low_freq_density_cone)
+#ifndef MT_CONE_RF
+#define MT_CONE_RF 1
+#endif
+
 struct RayCounters {
     unsigned rays, marched, steps, incloud, cone, early;
 };
@@ -39,6 +44,8 @@ MT_DEVICE void cloud_frame_setup(const CamU& cam, const TimeU& tm, const MtTunin
     for (int i = 0; i < 6; ++i) m.coneStep[i] = (xc * K[i][0] + l * K[i][1]) + zc * K[i][2];
     f3 wind = mk3(tun.wind_direction[0], tun.wind_direction[1], tun.wind_direction[2]);
     m.windSkew = ((wind + mk3(0.0f, 0.1f, 0.0f)) * tun.cloud_speed) * tm.time[1];
+    m.covDen = 1.0f - tun.coverage;
+    m.covRcp = nice_rcp(m.covDen);
 }
 
 // The two Halton look-ups of the shader (getJitterOffset, cloudRayMarch.comp:114-132) have only eight distinct
@@ -139,7 +146,7 @@ MT_DEVICE Tex2D std_curl(const Tex2D& t)
 }
 
 template <bool WEATHER, bool STD>
-MT_DEVICE float low_freq_density(const CloudParams& P, float coverage, P2 pxy, float pz, float ux, float uz, float relH)
+MT_DEVICE float low_freq_density(const CloudParams& P, const MarchConst& M, float coverage, P2 pxy, float pz, float ux, float uz, float relH)
 {
     const Tex3D low = std_low<STD>(P.low);
     LinAxis X, Y, Z = lin_axis_repeat(pz, low.d);
@@ -162,8 +169,35 @@ MT_DEVICE float low_freq_density(const CloudParams& P, float coverage, P2 pxy, f
     }
     // remapClampedBeforeAndAfter(base, cov, 1, 0, 1) * cov.  base <= cov clamps to cov and yields exactly +0.
     if (!(base > coverage)) return 0.0f;
-    float b = sat1(div_nice(base - coverage, 1.0f - coverage));  // coverage in [0, 0.91] (mtSetTuning)
+    float b = sat1(div_nice_r(base - coverage, M.covDen, M.covRcp));  // coverage in [0, 0.91] (mtSetTuning); divisor prepared per frame
     return b * coverage;
+}
+
+// sampleLowFrequency for a LIGHT-CONE sample (cloudRayMarch.comp:658-665): the same function of the same sample point, but
+// its result only feeds the cone density (radiance), so it is evaluated from the (r, F) form of the volume (mt_tex.cuh);
+// whenever the remapped base density comes within MT_RF_GUARD of the coverage threshold the canonical four-channel
+// evaluation decides instead.  Sign decisions (and with them MtCounters.cone_hits) are exactly the canonical ones; values
+// differ by rounding (< 4e-6 relative in the density, < 1e-5 in a pixel against the 1e-3 bar).
+template <bool STD>
+MT_DEVICE float low_freq_density_cone(const CloudParams& P, const MarchConst& M, float coverage, P2 pxy, float pz)
+{
+    const Tex3D low = std_low<STD>(P.low);
+    LinAxis X, Y, Z = lin_axis_repeat(pz, low.d);
+    lin_axes_xy(pxy, low.w, low.h, X, Y);
+    const unsigned cell = tex_cell(low, X.i0, Y.i0, Z.i0);
+    if (low.occ && !occ_cell_may_be_cloud(low, cell)) return 0.0f;
+    const P2 rf = tex3d_rf_axes(low, X, Y, Z, cell);
+    float fbm = sat1(hi2(rf));  // F sits three bits lower than r in its word: the common 2^13 / 255 already divides it by 8
+    float omin = fbm - 0.9f;
+    float base = sat1(div_nice(lo2(rf) - omin, 1.0f - omin));
+    if (fabsf(base - coverage) <= MT_RF_GUARD) {  // too close to call from the one-channel fbm: canonical evaluation
+        const Rgba n = tex3d_rgba_axes(low, X, Y, Z, cell);
+        fbm = sat1((n.g * 0.625f + n.b * 0.25f) + n.a * 0.125f);
+        omin = fbm - 0.9f;
+        base = sat1(div_nice(n.r - omin, 1.0f - omin));
+    }
+    if (!(base > coverage)) return 0.0f;
+    return sat1(div_nice_r(base - coverage, M.covDen, M.covRcp)) * coverage;
 }
 
 // The part of erodeCloudWithHighFrequency (cloudRayMarch.comp:542-563) that depends only on the march sample:
@@ -293,7 +327,7 @@ MT_DEVICE StepBase cloud_step_base(const CloudParams& P, const MarchConst& M, co
     // skewSamplePointWithWind (:489-497)
     f3 skew = (sp + ((wind * h) * P.tun.cloud_top_offset) * 0.009f) + M.windSkew;
     B.pos = pos; B.skew = skew; B.h = h;
-    B.baseDensity = low_freq_density<WEATHER, STD>(P, P.tun.coverage, pk2(skew.x, skew.y), skew.z, pos.x, pos.z, h) * P.tun.base_density_factor;
+    B.baseDensity = low_freq_density<WEATHER, STD>(P, M, P.tun.coverage, pk2(skew.x, skew.y), skew.z, pos.x, pos.z, h) * P.tun.base_density_factor;
     if (COUNT) cnt.steps++;
     return B;
 }
@@ -342,7 +376,9 @@ MT_DEVICE StepSample cloud_step_light(const CloudParams& P, const MarchConst& M,
         float lz = (pos.z + offz) - relOrigin.z;
         const P2 sxy = div_thickness2(lxy);
         const float sz = div_thickness(lz);
-        float cur = low_freq_density<WEATHER, STD>(P, coverage, sxy, sz, lo2(sxy), sz, h);
+        float cur;
+        if (MT_CONE_RF && !WEATHER && P.low.rfquads) cur = low_freq_density_cone<STD>(P, M, coverage, sxy, sz);
+        else cur = low_freq_density<WEATHER, STD>(P, M, coverage, sxy, sz, lo2(sxy), sz, h);
         if (cur > 0.0f) {
             if (COUNT) cnt.cone++;
             dl += erode(1.5f * cur, edge);

@@ -63,6 +63,24 @@ __global__ void __launch_bounds__(256) build_quads_kernel(const uint32_t* __rest
 #endif
     q[i] = make_uint4(t[r0 + x], t[r0 + x1], t[r1 + x], t[r1 + x1]);
 }
+// the same quads of (r, F) words (mt_tex.cuh, rf_pack): the light-cone samples' form of the low-frequency volume
+__global__ void __launch_bounds__(256) build_rf_quads_kernel(const uint32_t* __restrict__ t, int w, int h, int d, uint4* __restrict__ q)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned n = (unsigned)w * (unsigned)h * (unsigned)d;
+    if (i >= n) return;
+    const unsigned x = i % (unsigned)w, y = (i / (unsigned)w) % (unsigned)h, z = i / ((unsigned)w * (unsigned)h);
+    const unsigned x1 = (x + 1u) & (unsigned)(w - 1), y1 = (y + 1u) & (unsigned)(h - 1);
+    const unsigned r0 = (z * h + y) * w, r1 = (z * h + y1) * w;
+    q[i] = make_uint4(rf_pack(t[r0 + x]), rf_pack(t[r0 + x1]), rf_pack(t[r1 + x]), rf_pack(t[r1 + x1]));
+}
+cudaError_t mt_launch_build_rf_quads(const uint32_t* texels, int w, int h, int d, void* quads, cudaStream_t stream)
+{
+    const unsigned n = (unsigned)w * (unsigned)h * (unsigned)d;
+    build_rf_quads_kernel<<<(n + 255) / 256, 256, 0, stream>>>(texels, w, h, d, (uint4*)quads);
+    return cudaGetLastError();
+}
+
 cudaError_t mt_launch_build_quads(const uint32_t* texels, int w, int h, int d, void* quads, cudaStream_t stream)
 {
     const unsigned n = (unsigned)w * (unsigned)h * (unsigned)d;

@@ -41,6 +41,7 @@ struct MtContext {
     uint32_t* ldrScratch = nullptr;           // TXAA output, swapped with ldr[cur] after the pass
     uint32_t* tex[4] = { nullptr, nullptr, nullptr, nullptr };
     void* quads[4] = { nullptr, nullptr, nullptr, nullptr };  // per-cell 2x2 texel quads (mt_tex.cuh), built at upload
+    void* rfQuads = nullptr;      // low-frequency volume only: the quads in (r, F) form for the light-cone samples
     int texw[4] = { 0, 0, 0, 0 }, texh[4] = { 0, 0, 0, 0 }, texd[4] = { 0, 0, 0, 0 };
     MarchConst* mc = nullptr;
     uint32_t* occ = nullptr;      // empty-cell bitmap of the low-frequency volume (mt_tex.cuh)
@@ -298,6 +299,7 @@ void mtDestroy(MtContext* c)
         if (p.done) cudaEventDestroy(p.done);
     free_images(c);
     for (int i = 0; i < 4; ++i) { cudaFree(c->tex[i]); cudaFree(c->quads[i]); }
+    cudaFree(c->rfQuads);
     cudaFree(c->mc);
     cudaFree(c->occ);
     cudaFree(c->counters);
@@ -409,6 +411,15 @@ static MtStatus upload(MtContext* c, int slot, uint32_t w, uint32_t h, uint32_t 
         MT_CUDA(c, mt_launch_build_quads(c->tex[slot], (int)w, (int)h, (int)d, c->quads[slot], c->stream));
         c->launches += 1;
     }
+    if (slot == MT_TEX_LOW_FREQ) {
+        cudaFree(c->rfQuads);
+        c->rfQuads = nullptr;
+        if (!(c->flags & MT_FLAG_NO_CONE_RF)) {
+            MT_CUDA(c, cudaMalloc(&c->rfQuads, bytes * 4));
+            MT_CUDA(c, mt_launch_build_rf_quads(c->tex[slot], (int)w, (int)h, (int)d, c->rfQuads, c->stream));
+            c->launches += 1;
+        }
+    }
     MT_CUDA(c, cudaStreamSynchronize(c->stream));  // the caller may free its buffer on return
     c->texw[slot] = (int)w; c->texh[slot] = (int)h; c->texd[slot] = (int)d;
     if (slot == MT_TEX_LOW_FREQ) {
@@ -469,6 +480,7 @@ static MtStatus cloud_dispatch(MtContext* c, int full, const RowTiles* tiles, bo
     P.tun = c->tun;
     mt_host_sky_const(c->cam, c->tun, P.sky);
     P.low.quads = (const Quad*)c->quads[MT_TEX_LOW_FREQ];
+    P.low.rfquads = (const Quad*)c->rfQuads;
     P.high.quads = (const Quad*)c->quads[MT_TEX_HIGH_FREQ];
     P.curl.quads = (const Quad*)c->quads[MT_TEX_CURL];
     P.low.texels = c->tex[MT_TEX_LOW_FREQ];

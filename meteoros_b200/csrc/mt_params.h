@@ -53,6 +53,7 @@ struct MarchConst {
     f3 coneStep[6];                     // noise_kernel[i] (unscaled)
     float rayJitter[8][2];              // getJitterOffset(id, dim): (halton_x / W, halton_y / H) for id/2 = 0..7
     float stepJitter[8][4];             // per-step direction offset (jx, (jx+jy)*1.18, jy, 0), j = halton / 75
+    float covDen, covRcp;               // 1 - coverage and its refined reciprocal (nice_rcp): divisor of the coverage remap
 };
 #define MT_MARCHCONST_WORDS (sizeof(MarchConst) / 4)
 

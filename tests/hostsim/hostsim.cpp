@@ -29,6 +29,7 @@ int hs_cloud(const MtCameraUBO* cam, const MtTimeUBO* tm, const MtTuning* tun, c
     P.tun = *tun;
     mt_host_sky_const(*cam, *tun, P.sky);
     P.low.texels = (const uint32_t*)low; P.low.w = lw; P.low.h = lh; P.low.d = ld;
+    P.low.rfquads = (const Quad*)P.low.texels;  // non-null = light-cone samples take the (r, F) path; the host build packs (r, F) per texel on the fly
     P.high.texels = (const uint32_t*)high; P.high.w = hw; P.high.h = hh; P.high.d = hd;
     P.curl.texels = (const uint32_t*)curl; P.curl.w = cw; P.curl.h = ch;
     P.weather.texels = (const uint32_t*)weather; P.weather.w = ww; P.weather.h = wh;

@@ -120,7 +120,7 @@ extern "C" int ws_run(const MtCameraUBO* cam, const MtTimeUBO* tm, const MtTunin
                                 cone_l[i]++;
                                 if (occ_cell_may_be_cloud(P.low, tex_cell(P.low, X.i0, Y.i0, Z.i0))) {
                                     cone_ne[i]++;
-                                    float cur = low_freq_density<false, false>(P, P.tun.coverage, pk2(sx, sy), sz, sx, sz, B.h);
+                                    float cur = low_freq_density<false, false>(P, M, P.tun.coverage, pk2(sx, sy), sz, sx, sz, B.h);
                                     if (cur > 0.0f) cone_h[i]++;
                                 }
                             }
