@@ -340,7 +340,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ctx-flags", type=int, default=0, help="extra MT_FLAG_* bits for A/B runs (e.g. 8 = no quad layout)")
     ap.add_argument("--tile-rows", type=int, default=8, help="frame8k: pixel rows per cyclic tile (multiple of 8)")
-    ap.add_argument("--gather", default="peer_store", choices=["peer_store", "copy", "forward", "local"],
+    ap.add_argument("--gather", default="peer_store", choices=["peer_store", "bulk_store", "copy", "forward", "local"],
                     help="frame8k: kernel peer stores (default), copy-engine tile pushes, a tile-forwarding side kernel (correct, not yet "
                          "timed at 8 GPUs), or (diagnostic) no gather at all")
     ap.add_argument("--gather-mask", action="store_true", help="frame8k: also send the god-ray mask tiles to GPU 0 (needed only if god rays run)")

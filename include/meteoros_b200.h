@@ -105,6 +105,7 @@ typedef struct MtConfig {
 #define MT_FLAG_COUNTERS 1u    /* cloud pass also accumulates MtCounters (slower; for work accounting) */
 #define MT_FLAG_PASS_TIMING 2u /* bracket every pass with CUDA events so mtLastPassMs works               */
 #define MT_FLAG_SEQUENTIAL_MARCH 4u /* 1-of-16 dispatch: one kernel, one thread per ray (default: step-parallel) */
+#define MT_FLAG_TOP_DOWN 8u         /* full-quality launches walk their row tiles top-down (default: from the horizon upwards, ocean last) */
 #define MT_FLAG_NO_CONE_RF 16u      /* light-cone samples through the canonical four-channel filter instead of the (r, F) form of
                                      * the low-frequency volume (saves its 4 bytes/cell copy; bit-identical decisions either way,
                                      * radiance equal to rounding).  Must be set before the low-frequency texture is uploaded. */
@@ -251,6 +252,13 @@ MT_API MtStatus mtSetCloudOutput(MtContext* ctx, void* hdr_dev_ptr, void* mask_d
  * transfer overlaps the march tile by tile and no marching warp waits on NVLink.  mtJoinCopies orders the main stream
  * after it; mtSynchronize waits for it.  The god-ray mask stays local.  Ignored while mtSetCloudOutput is in effect.   */
 MT_API MtStatus mtSetCloudForward(MtContext* ctx, void* peer_hdr_dev_ptr);
+/* How the full-quality Cloud kernel stores its HDR pixels (extension; matters when mtSetCloudOutput points at a peer GPU):
+ * MT_STORE_DIRECT  one 16-byte st.global per ray from the marching warp;
+ * MT_STORE_BULK    a warp stages its 16x2 pixels in shared memory and two bulk asynchronous copies (cp.async.bulk, the TMA
+ *                  engine) carry the two 256-byte row segments to the image -- the warp only waits until the engine has READ
+ *                  the staging buffer, never for the remote write.  Same bytes either way.                                   */
+typedef enum MtStoreMode { MT_STORE_DIRECT = 0, MT_STORE_BULK = 1 } MtStoreMode;
+MT_API MtStatus mtSetCloudStoreMode(MtContext* ctx, MtStoreMode mode);
 /* CUDA IPC plumbing for one-process-per-GPU sharding: export this context's image, map a peer's. 64-byte handles. */
 MT_API MtStatus mtExportImageHandle(MtContext* ctx, MtImage which, uint8_t handle[64]);
 MT_API MtStatus mtOpenPeerImage(MtContext* ctx, const uint8_t handle[64], void** dev_ptr);

@@ -92,6 +92,7 @@ PROTOTYPES = {
     "mtImageDevicePtr": (C.c_int, [C.c_void_p, C.c_int, c_void_pp]),
     "mtSetCloudOutput": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "mtSetCloudForward": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mtSetCloudStoreMode": (C.c_int, [C.c_void_p, C.c_int]),
     "mtExportImageHandle": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "mtOpenPeerImage": (C.c_int, [C.c_void_p, C.c_void_p, c_void_pp]),
     "mtClosePeerImage": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -21,6 +21,7 @@ TEX_LOW_FREQ, TEX_HIGH_FREQ, TEX_CURL, TEX_WEATHER = 0, 1, 2, 3
 IMAGE_CLOUD_CUR, IMAGE_CLOUD_PREV, IMAGE_GODRAY_MASK, IMAGE_LDR, IMAGE_LDR_PREV = 0, 1, 2, 3, 4
 PASS_REPROJECT, PASS_CLOUD, PASS_GODRAYS, PASS_TONEMAP, PASS_TXAA = 0, 1, 2, 3, 4
 FRAME_GODRAYS, FRAME_TONEMAP, FRAME_TXAA = 1, 2, 4
+STORE_DIRECT, STORE_BULK = 0, 1
 
 RAY_DEBUG_DTYPE = np.dtype(
     [
@@ -238,6 +239,10 @@ class CloudRenderer:
     def set_cloud_forward(self, hdr_ptr):
         """Gather by forwarding: finished row tiles of dispatch_cloud_tiles are pushed to this peer image by a side kernel."""
         self._check(self._lib.mtSetCloudForward(self._h, C.c_void_p(hdr_ptr or 0)), "mtSetCloudForward")
+    def set_cloud_store_mode(self, mode: int):
+        """0 = direct 16-byte stores, 1 = staged bulk asynchronous copies (see the header)."""
+        self._check(self._lib.mtSetCloudStoreMode(self._h, int(mode)), "mtSetCloudStoreMode")
+
     def export_image_handle(self, which: int) -> bytes:
         buf = (C.c_uint8 * 64)()
         self._check(self._lib.mtExportImageHandle(self._h, which, buf), "mtExportImageHandle")

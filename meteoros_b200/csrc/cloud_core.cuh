@@ -11,7 +11,7 @@
 
 #include "mt_params.h"
 
-// MT_CONE_RF: light-cone samples from the (r, F) form of the low-frequency volume (low_freq_density_cone)
+// MT_CONE_RF: light-cone samples from the (r, F) form of the low-frequency volume (cone_density_rf)
 #ifndef MT_CONE_RF
 #define MT_CONE_RF 1
 #endif
@@ -121,23 +121,24 @@ MT_DEVICE float height_gradient(float h, float cloudType)
 // unskewedSamplePoint.xz, the base cloud is scaled by the height gradient of its cloud type and its red channel
 // replaces the constant coverage -- so neither the empty-cell bitmap (built for one coverage) nor the "nice" division
 // (1 - coverage may be 0) applies on that path.
-// STD = the textures have the reference's extents (low 128^3, high 32^3, curl 128^2: Sky.cpp:31-50), which the host checks
+// STD != 0: the textures have the reference's extents (low 128^3, high 32^3, curl 128^2: Sky.cpp:31-50), which the host checks
 // per dispatch: the extents become immediates (no constant-bank loads, shifts instead of multiplies in the addressing).
-template <bool STD>
+// STD == 2 additionally selects the software-pipelined light-cone loop (one-thread-per-ray kernels: ConeOffsets.stage is set).
+template <int STD>
 MT_DEVICE Tex3D std_low(const Tex3D& t)
 {
     Tex3D r = t;
     if (STD) r.w = r.h = r.d = 128;
     return r;
 }
-template <bool STD>
+template <int STD>
 MT_DEVICE Tex3D std_high(const Tex3D& t)
 {
     Tex3D r = t;
     if (STD) r.w = r.h = r.d = 32;
     return r;
 }
-template <bool STD>
+template <int STD>
 MT_DEVICE Tex2D std_curl(const Tex2D& t)
 {
     Tex2D r = t;
@@ -145,7 +146,7 @@ MT_DEVICE Tex2D std_curl(const Tex2D& t)
     return r;
 }
 
-template <bool WEATHER, bool STD>
+template <bool WEATHER, int STD>
 MT_DEVICE float low_freq_density(const CloudParams& P, const MarchConst& M, float coverage, P2 pxy, float pz, float ux, float uz, float relH)
 {
     const Tex3D low = std_low<STD>(P.low);
@@ -178,20 +179,16 @@ MT_DEVICE float low_freq_density(const CloudParams& P, const MarchConst& M, floa
 // whenever the remapped base density comes within MT_RF_GUARD of the coverage threshold the canonical four-channel
 // evaluation decides instead.  Sign decisions (and with them MtCounters.cone_hits) are exactly the canonical ones; values
 // differ by rounding (< 4e-6 relative in the density, < 1e-5 in a pixel against the 1e-3 bar).
-template <bool STD>
-MT_DEVICE float low_freq_density_cone(const CloudParams& P, const MarchConst& M, float coverage, P2 pxy, float pz)
+// density of a cone sample from its filtered (r, fbm) pair; `exact` re-evaluates through the canonical filter inside the guard band
+template <int STD>
+MT_DEVICE float cone_density_rf(const CloudParams& P, const MarchConst& M, float coverage, P2 rf, const LinAxis& X, const LinAxis& Y,
+                                const LinAxis& Z, unsigned cell)
 {
-    const Tex3D low = std_low<STD>(P.low);
-    LinAxis X, Y, Z = lin_axis_repeat(pz, low.d);
-    lin_axes_xy(pxy, low.w, low.h, X, Y);
-    const unsigned cell = tex_cell(low, X.i0, Y.i0, Z.i0);
-    if (low.occ && !occ_cell_may_be_cloud(low, cell)) return 0.0f;
-    const P2 rf = tex3d_rf_axes(low, X, Y, Z, cell);
     float fbm = sat1(hi2(rf));  // F sits three bits lower than r in its word: the common 2^13 / 255 already divides it by 8
     float omin = fbm - 0.9f;
     float base = sat1(div_nice(lo2(rf) - omin, 1.0f - omin));
     if (fabsf(base - coverage) <= MT_RF_GUARD) {  // too close to call from the one-channel fbm: canonical evaluation
-        const Rgba n = tex3d_rgba_axes(low, X, Y, Z, cell);
+        const Rgba n = tex3d_rgba_axes(std_low<STD>(P.low), X, Y, Z, cell);
         fbm = sat1((n.g * 0.625f + n.b * 0.25f) + n.a * 0.125f);
         omin = fbm - 0.9f;
         base = sat1(div_nice(n.r - omin, 1.0f - omin));
@@ -199,7 +196,6 @@ MT_DEVICE float low_freq_density_cone(const CloudParams& P, const MarchConst& M,
     if (!(base > coverage)) return 0.0f;
     return sat1(div_nice_r(base - coverage, M.covDen, M.covRcp)) * coverage;
 }
-
 // The part of erodeCloudWithHighFrequency (cloudRayMarch.comp:542-563) that depends only on the march sample:
 // returns high_freq_modifier * 0.005, the lower edge of the final remap.
 MT_DEVICE float erosion_edge(const Tex2D& curl, const Tex3D& high, f3 p, float h)
@@ -308,7 +304,7 @@ struct StepBase {
     float h, baseDensity;
 };
 
-template <bool COUNT, bool WEATHER, bool STD>
+template <bool COUNT, bool WEATHER, int STD>
 MT_DEVICE StepBase cloud_step_base(const CloudParams& P, const MarchConst& M, const RaySetup& R, int jidx, float t, RayCounters& cnt)
 {
     StepBase B;
@@ -341,7 +337,46 @@ struct ConeOffsets {
     const P2* xy;     // this thread's first pair; the pair of sample i is xy[i * stride]   (null: compute per step)
     const float* z;
     int stride;
+    unsigned stage;   // shared-memory byte address of this thread's staging slots for the pipelined cone loop (0: none);
+                      // slot (s, k) = stage + (2 * s + k) * stageStride: stage s in {0, 1}, k = slice z0 / z1 quad
+    unsigned stageStride;
 };
+
+// MT_CONE_PIPE: software-pipelined light-cone loop (device only).  A cone sample is: position -> cell -> two 16-byte quad
+// loads (L2 latency: the rays of an SM walk 32 MB) -> filter.  One thread per ray has no second sample in flight, so every
+// cone sample paid that latency in full (long-scoreboard stalls, profiles/r2_cloud_*.md).  Here sample i+1's quads are
+// requested with cp.async (global -> this thread's own shared slot, no registers held) BEFORE sample i is filtered.  The
+// empty-cell test moves behind the load: bit 0 of the cell's first (r, F) word carries the flag (occupancy_build_kernel
+// writes it), so no separate bitmap load and no second dependent round trip.  Same arithmetic, same order: bit-identical.
+// Measured at 4K (profiles/r2_ab.md): 4.69 ms with cp.async.ca, 4.61 ms with .cg, against 4.48 ms for the plain loop -- the
+// unconditional quad loads of the 43 % empty-cell samples and the extra LSU traffic (LDGSTS + LDS) cost more than the hidden
+// latency buys (L1/TEX throughput was 48 % before).  OFF by default; kept as the A/B evidence.
+#ifndef MT_CONE_PIPE
+#define MT_CONE_PIPE 0
+#endif
+#ifndef MT_CONE_PIPE_CG
+#define MT_CONE_PIPE_CG 0
+#endif
+#if !defined(MT_HOSTSIM)
+__device__ __forceinline__ void cp_async16(unsigned dst, const void* src)
+{
+#if MT_CONE_PIPE_CG
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");  // L2 only
+#else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ Quad lds_quad(unsigned addr)
+{
+    Quad q;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(addr) : "memory");
+    return q;
+}
+#endif
+
 MT_DEVICE void cone_offset(const MarchConst& M, float stepSize, int i, P2& xy, float& z)
 {
     const float fi = (float)i;
@@ -350,7 +385,29 @@ MT_DEVICE void cone_offset(const MarchConst& M, float stepSize, int i, P2& xy, f
     z = (cs.z * stepSize) * fi;
 }
 
-template <bool COUNT, bool WEATHER, bool STD>
+// position of cone sample i in texture space and its filter axes / cell
+template <int STD>
+MT_DEVICE void cone_axes(const CloudParams& P, const MarchConst& M, const ConeOffsets& CO, f3 pos, f3 relOrigin, float stepSize, int i,
+                         P2& sxy, float& sz, LinAxis& X, LinAxis& Y, LinAxis& Z, unsigned& cell)
+{
+    // lightPos = pos + (stepSize * noise_kernel[i]) * i ; sample = (lightPos - relOrigin) / 12500  -- x,y as a pair
+    P2 off;
+    float offz;
+    if (CO.xy) { off = CO.xy[i * CO.stride]; offz = CO.z[i * CO.stride]; }
+    else cone_offset(M, stepSize, i, off, offz);
+    // the offset products are separate values (memory or scalar adds): a mul2 feeding an add2 would be contracted into
+    // an FFMA2 (mt_math.cuh)
+    const P2 lxy = sub2(CO.xy ? add2(pk2(pos.x, pos.y), off) : pk2(pos.x + lo2(off), pos.y + hi2(off)), pk2(relOrigin.x, relOrigin.y));
+    const float lz = (pos.z + offz) - relOrigin.z;
+    sxy = div_thickness2(lxy);
+    sz = div_thickness(lz);
+    const Tex3D low = std_low<STD>(P.low);
+    Z = lin_axis_repeat(sz, low.d);
+    lin_axes_xy(sxy, low.w, low.h, X, Y);
+    cell = tex_cell(low, X.i0, Y.i0, Z.i0);
+}
+
+template <bool COUNT, bool WEATHER, int STD>
 MT_DEVICE StepSample cloud_step_light(const CloudParams& P, const MarchConst& M, const RaySetup& R, const StepBase& B, RayCounters& cnt,
                                       const ConeOffsets& CO)
 {
@@ -362,26 +419,70 @@ MT_DEVICE StepSample cloud_step_light(const CloudParams& P, const MarchConst& M,
     float edge = erosion_edge(std_curl<STD>(P.curl), std_high<STD>(P.high), skew, h);
     S.inc = erode(baseDensity * 1.4f, edge) * 0.5f;
     float dl = 0.0f;
-    const P2 relxy = pk2(relOrigin.x, relOrigin.y);
+#if !defined(MT_HOSTSIM) && MT_CONE_PIPE
+    if (STD == 2 && MT_CONE_RF && !WEATHER) {  // STD kernels are only launched with the (r, F) quads present (mt_std_dims)
+        const Tex3D low = std_low<STD>(P.low);
+        const unsigned wrap = (unsigned)low.w * (unsigned)low.h * (unsigned)low.d - 1u, slice = (unsigned)low.w * (unsigned)low.h;
+        P2 sxy;
+        float sz;
+        LinAxis X, Y, Z;
+        unsigned cell;
+        cone_axes<STD>(P, M, CO, pos, relOrigin, R.stepSize, 0, sxy, sz, X, Y, Z, cell);
+        cp_async16(CO.stage, low.rfquads + cell);
+        cp_async16(CO.stage + CO.stageStride, low.rfquads + ((cell + slice) & wrap));
+        cp_async_commit();
 #pragma unroll 1
-    for (int i = 0; i < 6; ++i) {  // one copy of the filter in the instruction stream (I-cache)
-        // lightPos = pos + (stepSize * noise_kernel[i]) * i ; sample = (lightPos - relOrigin) / 12500  -- x,y as a pair
-        P2 off;
-        float offz;
-        if (CO.xy) { off = CO.xy[i * CO.stride]; offz = CO.z[i * CO.stride]; }
-        else cone_offset(M, R.stepSize, i, off, offz);
-        // the offset products are separate values (memory or scalar adds): a mul2 feeding an add2 would be contracted into
-        // an FFMA2 (mt_math.cuh)
-        P2 lxy = sub2(CO.xy ? add2(pk2(pos.x, pos.y), off) : pk2(pos.x + lo2(off), pos.y + hi2(off)), relxy);
-        float lz = (pos.z + offz) - relOrigin.z;
-        const P2 sxy = div_thickness2(lxy);
-        const float sz = div_thickness(lz);
-        float cur;
-        if (MT_CONE_RF && !WEATHER && P.low.rfquads) cur = low_freq_density_cone<STD>(P, M, coverage, sxy, sz);
-        else cur = low_freq_density<WEATHER, STD>(P, M, coverage, sxy, sz, lo2(sxy), sz, h);
-        if (cur > 0.0f) {
-            if (COUNT) cnt.cone++;
-            dl += erode(1.5f * cur, edge);
+        for (int i = 0; i < 6; ++i) {
+            LinAxis Xn = X, Yn = Y, Zn = Z;
+            unsigned celln = cell;
+            const unsigned cur_slot = CO.stage + (unsigned)(i & 1) * (2u * CO.stageStride);
+            if (i < 5) {  // request sample i+1's quads, then wait for sample i's only
+                const unsigned nxt_slot = CO.stage + (unsigned)((i + 1) & 1) * (2u * CO.stageStride);
+                cone_axes<STD>(P, M, CO, pos, relOrigin, R.stepSize, i + 1, sxy, sz, Xn, Yn, Zn, celln);
+                cp_async16(nxt_slot, low.rfquads + celln);
+                cp_async16(nxt_slot + CO.stageStride, low.rfquads + ((celln + slice) & wrap));
+                cp_async_commit();
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            const Quad q0 = lds_quad(cur_slot);
+            if (q0.x & 1u) {  // the cell may hold cloud (flag written with the empty-cell bitmap); else the density is exactly +0
+                const Quad q1 = lds_quad(cur_slot + CO.stageStride);
+                const Weights8 w = filter_weights(X, Y, Z);
+                const uint32_t t000 = q0.x, t001 = q0.y, t010 = q0.z, t011 = q0.w, t100 = q1.x, t101 = q1.y, t110 = q1.z, t111 = q1.w;
+                const P2 rf = mul2(MT_ACC2(MT_RFP), bc2(MT_INV255));
+                const float cur = cone_density_rf<STD>(P, M, coverage, rf, X, Y, Z, cell);
+                if (cur > 0.0f) {
+                    if (COUNT) cnt.cone++;
+                    dl += erode(1.5f * cur, edge);
+                }
+            }
+            X = Xn; Y = Yn; Z = Zn; cell = celln;
+        }
+    } else
+#endif
+    {
+#pragma unroll 1
+        for (int i = 0; i < 6; ++i) {  // one copy of the filter in the instruction stream (I-cache)
+            P2 sxy;
+            float sz;
+            LinAxis X, Y, Z;
+            unsigned cell;
+            float cur;
+            if (STD && MT_CONE_RF && !WEATHER) {
+                cone_axes<STD>(P, M, CO, pos, relOrigin, R.stepSize, i, sxy, sz, X, Y, Z, cell);
+                const Tex3D low = std_low<STD>(P.low);
+                cur = (low.occ && !occ_cell_may_be_cloud(low, cell)) ? 0.0f
+                      : cone_density_rf<STD>(P, M, coverage, tex3d_rf_axes(low, X, Y, Z, cell), X, Y, Z, cell);
+            } else {
+                cone_axes<STD>(P, M, CO, pos, relOrigin, R.stepSize, i, sxy, sz, X, Y, Z, cell);
+                cur = low_freq_density<WEATHER, STD>(P, M, coverage, sxy, sz, lo2(sxy), sz, h);
+            }
+            if (cur > 0.0f) {
+                if (COUNT) cnt.cone++;
+                dl += erode(1.5f * cur, edge);
+            }
         }
     }
     S.energy = light_energy(h, dl, baseDensity, R.phase, R.cosAngle);
@@ -389,7 +490,7 @@ MT_DEVICE StepSample cloud_step_light(const CloudParams& P, const MarchConst& M,
 }
 
 // One iteration of the march loop (cloudRayMarch.comp:629-678) at parameter t, without the running sums.
-template <bool COUNT, bool WEATHER, bool STD>
+template <bool COUNT, bool WEATHER, int STD>
 MT_DEVICE StepSample cloud_step_sample(const CloudParams& P, const MarchConst& M, const RaySetup& R, int jidx, float t,
                                        RayCounters& cnt, const ConeOffsets& CO)
 {
@@ -433,9 +534,10 @@ MT_DEVICE void cloud_composite(const RaySetup& R, float accum, float color, F4& 
 }
 
 // One invocation of main(): setup, the sequential march, composite.
-template <bool COUNT, bool DEBUG, bool WEATHER, bool STD>
+template <bool COUNT, bool DEBUG, bool WEATHER, int STD>
 MT_DEVICE void cloud_ray(const CloudParams& P, const MarchConst& M, int px, int py, int pixelID, F4& hdr, F4& mask,
-                         RayCounters& cnt, MtRayDebug* dbg, P2* coneXY, float* coneZ, int coneStride)
+                         RayCounters& cnt, MtRayDebug* dbg, P2* coneXY, float* coneZ, int coneStride, unsigned coneStage = 0u,
+                         unsigned coneStageStride = 0u)
 {
     mask.x = mask.y = mask.z = mask.w = 0.0f;
     const RaySetup R = cloud_ray_setup(P, M, px, py, pixelID, hdr);
@@ -449,6 +551,7 @@ MT_DEVICE void cloud_ray(const CloudParams& P, const MarchConst& M, int px, int 
 
     ConeOffsets CO;
     CO.xy = coneXY; CO.z = coneZ; CO.stride = coneStride;
+    CO.stage = coneStage; CO.stageStride = coneStageStride;
     if (coneXY) {
 #pragma unroll
         for (int i = 0; i < 6; ++i) cone_offset(M, R.stepSize, i, coneXY[i * coneStride], coneZ[i * coneStride]);

@@ -21,7 +21,9 @@ __global__ void cloud_setup_kernel(CamU cam, TimeU tm, MtTuning tun, int W, int 
 }
 
 // One thread per 32 cells (one output word): bit x of the word = any of the cell's eight corner texels may carry cloud.
-__global__ void __launch_bounds__(256) occupancy_build_kernel(Tex3D T, uint32_t* occ, float coverage)
+// Where the (r, F) quads exist, bit 0 of each cell's first word repeats the cell's bit (the pipelined cone loop reads it
+// from the quad it has loaded anyway).
+__global__ void __launch_bounds__(256) occupancy_build_kernel(Tex3D T, uint32_t* occ, float coverage, uint4* rfq)
 {
     const unsigned wpr = (unsigned)T.w >> 5;
     const unsigned nwords = wpr * (unsigned)T.h * (unsigned)T.d;
@@ -39,6 +41,10 @@ __global__ void __launch_bounds__(256) occupancy_build_kernel(Tex3D T, uint32_t*
             any = any || occ_texel_may_be_cloud(__ldg(T.texels + rows[r] + x), coverage) ||
                   occ_texel_may_be_cloud(__ldg(T.texels + rows[r] + x1), coverage);
         bits |= (any ? 1u : 0u) << k;
+        if (rfq) {
+            uint32_t* w0 = &rfq[(z * (unsigned)T.h + y) * (unsigned)T.w + x].x;
+            *w0 = (*w0 & ~1u) | (any ? 1u : 0u);
+        }
     }
     occ[wi] = bits;
 }
@@ -72,7 +78,8 @@ __global__ void __launch_bounds__(256) build_rf_quads_kernel(const uint32_t* __r
     const unsigned x = i % (unsigned)w, y = (i / (unsigned)w) % (unsigned)h, z = i / ((unsigned)w * (unsigned)h);
     const unsigned x1 = (x + 1u) & (unsigned)(w - 1), y1 = (y + 1u) & (unsigned)(h - 1);
     const unsigned r0 = (z * h + y) * w, r1 = (z * h + y1) * w;
-    q[i] = make_uint4(rf_pack(t[r0 + x]), rf_pack(t[r0 + x1]), rf_pack(t[r1 + x]), rf_pack(t[r1 + x1]));
+    // bit 0 of the first word = "this cell may hold cloud" (set; occupancy_build_kernel clears it per coverage where it can)
+    q[i] = make_uint4(rf_pack(t[r0 + x]) | 1u, rf_pack(t[r0 + x1]), rf_pack(t[r1 + x]), rf_pack(t[r1 + x1]));
 }
 cudaError_t mt_launch_build_rf_quads(const uint32_t* texels, int w, int h, int d, void* quads, cudaStream_t stream)
 {
@@ -91,16 +98,13 @@ cudaError_t mt_launch_build_quads(const uint32_t* texels, int w, int h, int d, v
 cudaError_t mt_launch_occupancy(const Tex3D& low, uint32_t* occ, float coverage, cudaStream_t stream)
 {
     const unsigned nwords = (unsigned)(low.w >> 5) * (unsigned)low.h * (unsigned)low.d;
-    occupancy_build_kernel<<<(nwords + 255) / 256, 256, 0, stream>>>(low, occ, coverage);
+    occupancy_build_kernel<<<(nwords + 255) / 256, 256, 0, stream>>>(low, occ, coverage, (uint4*)low.rfquads);
     return cudaGetLastError();
 }
 
 __device__ __forceinline__ float f16_round(float x) { return __half2float(__float2half_rn(x)); }
 
 template <bool FULL, bool COUNT, bool DEBUG, bool WEATHER, bool STD>
-#ifndef MT_BOTTOM_UP
-#define MT_BOTTOM_UP 0  /* A/B at 4K and 8K: no measurable difference (5.09 ms both) */
-#endif
 #ifndef MT_CLOUD_MINBLOCKS
 #define MT_CLOUD_MINBLOCKS 8  /* 64 registers/thread: 8 CTAs = 32 warps per SM (profiles/r1_cloud_ab.md) */
 #endif
@@ -129,19 +133,17 @@ __global__ void __launch_bounds__(128, MT_CLOUD_MINBLOCKS) cloud_raymarch_kernel
         const int ly = ((warp >> 1) << 2) + (lane >> 3);
 #endif
         const int bpt = P.rows.tile_rows / MT_CTA_H;            // CTAs per row tile, vertically
-#if MT_BOTTOM_UP
-        // CTAs are dispatched in blockIdx order: start at the bottom of the frame, so that the trivial ocean rows and
-        // then the heaviest rows (just above the horizon: most steps) go first and the kernel's tail is made of the
-        // lightest marching rows (zenith) instead of the heaviest
-        const int by = (int)gridDim.y - 1 - (int)blockIdx.y;
-#else
+        // CTAs are dispatched in blockIdx order.  The owned tiles above the horizon are walked from the horizon upwards
+        // (RowTiles.heavy_first): the rows with the most march steps start first, the zenith rows later and the ocean /
+        // sky-band tiles, which retire in ~100 instructions, last.
         const int by = (int)blockIdx.y;
-#endif
-        const int ltile = by / bpt;
+        int ltile = by / bpt;
+        const int inTile = by - ltile * bpt;
+        if (ltile < P.rows.heavy_first) ltile = P.rows.heavy_first - 1 - ltile;
         doneSlot = ltile;
         const int tile = P.rows.tile_begin + ltile * P.rows.tile_stride;
         px = blockIdx.x * MT_CTA_W + lx;
-        py = tile * P.rows.tile_rows + (by - ltile * bpt) * MT_CTA_H + ly;
+        py = tile * P.rows.tile_rows + inTile * MT_CTA_H + ly;
         pixelID = ((px & 3) << 2) | (py & 3);                   // id = pX*4 + pY with (pX,pY) = (px%4, py%4)
         valid = px < P.W && py < P.H && (px >> 2) < P.tx && (py >> 2) < P.ty;
     } else {
@@ -175,16 +177,43 @@ __global__ void __launch_bounds__(128, MT_CLOUD_MINBLOCKS) cloud_raymarch_kernel
     P2* const cxy = nullptr;
     float* const cz = nullptr;
 #endif
+    // staging slots of the pipelined cone loop (cloud_core.cuh, MT_CONE_PIPE): [stage][z0 / z1 quad][thread], 16 bytes each
+#if MT_CONE_PIPE
+    __shared__ uint4 coneStage[2][2][128];
+    const unsigned cstage = (unsigned)__cvta_generic_to_shared(&coneStage[0][0][threadIdx.x]);
+    const unsigned cstride = 128u * 16u;
+#else
+    const unsigned cstage = 0u, cstride = 0u;
+#endif
+    // staging of the bulk-store epilogue (mtSetCloudStoreMode): one 16x2 pixel tile per warp, row-major = lane order
+    __shared__ __align__(128) float4 outStage[4][32];
     RayCounters cnt = { 0u, 0u, 0u, 0u, 0u, 0u };
+    const bool bulk = FULL && MT_WARP_SHAPE == 1 && P.bulkStore && __all_sync(0xffffffffu, valid);  // warp-uniform
     if (valid) {
         F4 hdr, mask;
         const size_t idx = (size_t)py * (size_t)P.W + (size_t)px;
-        cloud_ray<COUNT, DEBUG, WEATHER, STD>(P, M, px, py, pixelID, hdr, mask, cnt, DEBUG ? (P.debug + idx) : nullptr, cxy, cz, 128);
+        cloud_ray<COUNT, DEBUG, WEATHER, (STD ? (MT_CONE_PIPE ? 2 : 1) : 0)>(P, M, px, py, pixelID, hdr, mask, cnt, DEBUG ? (P.debug + idx) : nullptr, cxy, cz, 128,
+                                                                           cstage, cstride);
         if (P.f16_emulate) {
             hdr.x = f16_round(hdr.x); hdr.y = f16_round(hdr.y); hdr.z = f16_round(hdr.z); hdr.w = f16_round(hdr.w);
             mask.x = f16_round(mask.x); mask.y = f16_round(mask.y); mask.z = f16_round(mask.z); mask.w = f16_round(mask.w);
         }
-        reinterpret_cast<float4*>(P.hdr)[idx] = make_float4(hdr.x, hdr.y, hdr.z, hdr.w);
+        if (bulk) {
+            // The marching warp must not wait on a remote write: its 32 pixels go to shared memory, and lanes 0 and 16 each
+            // hand one 256-byte row segment to the bulk-copy engine, then wait only until the engine has read the buffer.
+            outStage[warp][lane] = make_float4(hdr.x, hdr.y, hdr.z, hdr.w);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the async proxy
+            __syncwarp();
+            if ((lane & 15) == 0) {
+                const unsigned src = (unsigned)__cvta_generic_to_shared(&outStage[warp][lane]);
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 256;" ::"l"(reinterpret_cast<float4*>(P.hdr) + idx), "r"(src)
+                             : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
+        } else {
+            reinterpret_cast<float4*>(P.hdr)[idx] = make_float4(hdr.x, hdr.y, hdr.z, hdr.w);
+        }
         reinterpret_cast<float4*>(P.mask)[idx] = make_float4(mask.x, mask.y, mask.z, mask.w);
     }
     if (FULL && !COUNT && !DEBUG && P.tileDone) {  // uniform: tell tile_forward_kernel that this CTA's pixels are in memory
@@ -305,7 +334,7 @@ __global__ void __launch_bounds__(128, MT_STEPS_MINBLOCKS) cloud_steps_kernel(co
     if (R.branch != 2 || k >= R.nsteps) return;
     const int jidx = (P.tm.frameCountMod16 + mt_f2i(t)) & 15;
     RayCounters none = { 0u, 0u, 0u, 0u, 0u, 0u };
-    const ConeOffsets noCache = { nullptr, nullptr, 0 };  // one thread per (ray, step): nothing to share
+    const ConeOffsets noCache = { nullptr, nullptr, 0, 0u, 0u };  // one thread per (ray, step): nothing to share
     const StepSample S = cloud_step_sample<false, WEATHER, STD>(P, M, R, jidx, t, none, noCache);
     *slot = make_float2(S.inc, S.energy);
 }
@@ -370,7 +399,7 @@ __global__ void __launch_bounds__(128, MT_CLOUD_MINBLOCKS) cloud_light_kernel(co
         const int jidx = (P.tm.frameCountMod16 + mt_f2i(t)) & 15;
         RayCounters none = { 0u, 0u, 0u, 0u, 0u, 0u };
         const StepBase B = cloud_step_base<false, WEATHER, STD>(P, M, R, jidx, t, none);   // same arithmetic: B.baseDensity > 0 again
-        const ConeOffsets noCache = { nullptr, nullptr, 0 };
+        const ConeOffsets noCache = { nullptr, nullptr, 0, 0u, 0u };
         const StepSample S = cloud_step_light<false, WEATHER, STD>(P, M, R, B, none, noCache);
         P.samples[(size_t)k * (size_t)P.rayStride + ray] = make_float2(S.inc, S.energy);
     }
@@ -408,11 +437,12 @@ __global__ void __launch_bounds__(128) cloud_fold_kernel(const __grid_constant__
     store_pixel(P, (size_t)py * P.W + px, hdr, mask);
 }
 
-// the reference's texture extents (Sky.cpp:31-50): the STD kernels carry them as immediates
+// the reference's texture extents (Sky.cpp:31-50): the STD kernels carry them as immediates and take the light-cone samples
+// from the (r, F) quads (MT_FLAG_NO_CONE_RF or other extents: the generic kernels, canonical filter throughout)
 static bool mt_std_dims(const CloudParams& P)
 {
     return P.low.w == 128 && P.low.h == 128 && P.low.d == 128 && P.high.w == 32 && P.high.h == 32 && P.high.d == 32 &&
-           P.curl.w == 128 && P.curl.h == 128;
+           P.curl.w == 128 && P.curl.h == 128 && (!MT_CONE_RF || P.low.rfquads != nullptr);  // STD also means: (r, F) quads exist
 }
 
 cudaError_t mt_launch_cloud_sixteenth_split(const CloudParams& P0, cudaStream_t stream, int* launches)
@@ -467,7 +497,8 @@ __global__ void __launch_bounds__(256) tile_forward_kernel(const float4* __restr
                                                            RowTiles rows, unsigned* tileDone, unsigned ctasPerTile)
 {
     __shared__ int timedOut;
-    for (int lt = blockIdx.x; lt < rows.tile_count; lt += gridDim.x) {
+    for (int j = blockIdx.x; j < rows.tile_count; j += gridDim.x) {
+        const int lt = j < rows.heavy_first ? rows.heavy_first - 1 - j : j;  // the order the march kernel issues its tiles in
         if (threadIdx.x == 0) {
             const volatile unsigned* done = tileDone + lt;
             unsigned polls = 0;
@@ -525,10 +556,19 @@ cudaError_t mt_launch_cloud(const CloudParams& P, cudaStream_t stream)
     if (P.tun.use_weather) {  // weather path: production variants only (mt_context.cu rejects counters / debug with it)
         if (P.full) cloud_raymarch_kernel<true, false, false, true, false><<<grid, block, 0, stream>>>(P);
         else cloud_raymarch_kernel<false, false, false, true, false><<<grid, block, 0, stream>>>(P);
+    } else if (std_dims) {  // counting / debug variants follow the production kernel's path: same pixels
+        if (P.full) {
+            if (debug) cloud_raymarch_kernel<true, true, true, false, true><<<grid, block, 0, stream>>>(P);
+            else if (count) cloud_raymarch_kernel<true, true, false, false, true><<<grid, block, 0, stream>>>(P);
+            else cloud_raymarch_kernel<true, false, false, false, true><<<grid, block, 0, stream>>>(P);
+        } else {
+            if (debug) cloud_raymarch_kernel<false, true, true, false, true><<<grid, block, 0, stream>>>(P);
+            else if (count) cloud_raymarch_kernel<false, true, false, false, true><<<grid, block, 0, stream>>>(P);
+            else cloud_raymarch_kernel<false, false, false, false, true><<<grid, block, 0, stream>>>(P);
+        }
     } else if (P.full) {
         if (debug) cloud_raymarch_kernel<true, true, true, false, false><<<grid, block, 0, stream>>>(P);
         else if (count) cloud_raymarch_kernel<true, true, false, false, false><<<grid, block, 0, stream>>>(P);
-        else if (std_dims) cloud_raymarch_kernel<true, false, false, false, true><<<grid, block, 0, stream>>>(P);
         else cloud_raymarch_kernel<true, false, false, false, false><<<grid, block, 0, stream>>>(P);
     } else {
         if (debug) cloud_raymarch_kernel<false, true, true, false, false><<<grid, block, 0, stream>>>(P);

@@ -60,6 +60,7 @@ struct MtContext {
     MtTuning tun;
     int32_t key = 0;
     bool haveCam = false, haveCamOld = false, haveTime = false;
+    int storeMode = 0;     // mtSetCloudStoreMode
     F4* outHdr = nullptr;  // mtSetCloudOutput overrides
     F4* outMask = nullptr;
     cudaEvent_t ev[MT_PASS_COUNT][2] = {};
@@ -515,10 +516,34 @@ static MtStatus cloud_dispatch(MtContext* c, int full, const RowTiles* tiles, bo
     P.ty = (((c->H / 4) + 31) / 32) * 32;
     P.full = full;
     P.f16_emulate = c->storage == MT_STORAGE_F16_EMULATE;
+    P.bulkStore = c->storeMode == (int)MT_STORE_BULK;
     if (tiles) P.rows = *tiles;
-    else {
-        P.rows.tile_rows = round_up(full ? c->H : P.ty, 8);
+    else if (full) {  // whole frame = every 8-row tile, so that the launch-order heuristic below applies to it as well
+        P.rows.tile_rows = 8;
+        P.rows.tile_begin = 0; P.rows.tile_stride = 1; P.rows.tile_count = (c->H + 7) / 8;
+    } else {
+        P.rows.tile_rows = round_up(P.ty, 8);
         P.rows.tile_begin = 0; P.rows.tile_stride = 1; P.rows.tile_count = 1;
+    }
+    P.rows.heavy_first = 0;
+    if (full && !(c->flags & MT_FLAG_TOP_DOWN)) {
+        // first pixel row whose centre-column ray no longer marches (dir.y < 0.06, cloudRayMarch.comp:730): castRay of
+        // camera.cpp's basis with nx = 0.  A heuristic for the launch order only -- any value renders the same image.
+        const float* v = c->cam.view;
+        const float upy = v[5], looky = -v[6], tany = c->cam.tanFovBy2[1];
+        const float upl = sqrtf(v[1] * v[1] + v[5] * v[5] + v[9] * v[9]), lookl = sqrtf(v[2] * v[2] + v[6] * v[6] + v[10] * v[10]);
+        int yh = c->H;
+        for (int y = 0; y < c->H; ++y) {
+            const float ny = (1.0f - (float)y / (float)c->H) * 2.0f - 1.0f;
+            const float dx = 0.0f, dy = looky / (lookl > 0 ? lookl : 1.0f) + (upy / (upl > 0 ? upl : 1.0f)) * ny * tany;
+            const float dz2 = 1.0f + (ny * tany) * (ny * tany);  // |look + up * ny * tany|^2 for an orthonormal basis
+            (void)dx;
+            if (dy / sqrtf(dz2) < 0.06f) { yh = y; break; }
+        }
+        int m = 0;
+        for (int k = 0; k < P.rows.tile_count; ++k)
+            if ((P.rows.tile_begin + k * P.rows.tile_stride) * P.rows.tile_rows < yh) m = k + 1;
+        P.rows.heavy_first = m;
     }
     P.counters = (debug || (c->flags & MT_FLAG_COUNTERS)) ? c->counters : nullptr;
     P.debug = nullptr;
@@ -880,6 +905,13 @@ try {
     if (!c) return MT_ERR_INVALID;
     c->outHdr = (F4*)hdr;
     c->outMask = (F4*)mask;
+    return MT_OK;
+} MT_NOTHROW
+MtStatus mtSetCloudStoreMode(MtContext* c, MtStoreMode mode)
+try {
+    if (!c) return MT_ERR_INVALID;
+    MT_REQUIRE(c, mode == MT_STORE_DIRECT || mode == MT_STORE_BULK, "mtSetCloudStoreMode: unknown mode");
+    c->storeMode = (int)mode;
     return MT_OK;
 } MT_NOTHROW
 MtStatus mtSetCloudForward(MtContext* c, void* peer_hdr)

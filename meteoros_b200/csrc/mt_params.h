@@ -67,6 +67,9 @@ struct RowTiles {  // which pixel rows this launch covers (multi-GPU row-tile sh
     int tile_begin;   // first tile owned
     int tile_stride;  // distance between owned tiles
     int tile_count;   // number of owned tiles
+    int heavy_first;  // launch order: the first `heavy_first` owned tiles (those above the horizon) are issued LAST-TO-FIRST, i.e.
+                      // from the horizon upwards -- most march steps first, zenith rows later, ocean rows at the very end -- so that
+                      // the kernel's tail is made of its cheapest CTAs (matters when a GPU renders 1/8 of a frame); 0 = top-down
 };
 
 struct CloudParams {
@@ -84,6 +87,7 @@ struct CloudParams {
     int tx, ty;  // threads of the reference dispatch (Renderer.cpp:713-716)
     int full;    // 0: one id (tm.frameCountMod16) -- 1: all sixteen
     int f16_emulate;
+    int bulkStore;   // full-quality kernel: HDR pixels leave through shared memory + cp.async.bulk (mtSetCloudStoreMode)
     RowTiles rows;
     unsigned long long* counters;  // 6 x u64 or null
     MtRayDebug* debug;             // W*H records or null

@@ -54,13 +54,15 @@ class ShardedFrame:
 
     def __init__(self, renderer, dist, tile_rows: int = 32, with_mask: bool = True, mode: str = "peer_store", groups: int = 4):
         """mode "peer_store": the march kernel's own stores land in GPU 0's image (fused compute + transfer).
+        mode "bulk_store": the same, but a warp's 16x2 pixels leave through shared memory and two bulk asynchronous copies
+        (cp.async.bulk, mtSetCloudStoreMode): the marching warp never waits for the remote write.
         mode "copy": tiles are rendered locally in `groups` launches and each finished group is pushed to GPU 0 by the
         copy engine (mtCopyTilesToPeer) while the next group renders.
         mode "forward": the march kernel stores locally and counts finished CTAs per tile; a small side kernel on a
         high-priority stream pushes each finished tile to GPU 0 (mtSetCloudForward) -- no marching warp waits on NVLink.
         mode "local": measurement only -- every rank keeps its tiles (no gather), to separate compute share from transfer."""
-        if mode not in ("peer_store", "copy", "forward", "local"):
-            raise ValueError("mode must be 'peer_store', 'copy', 'forward' or 'local'")
+        if mode not in ("peer_store", "bulk_store", "copy", "forward", "local"):
+            raise ValueError("mode must be 'peer_store', 'bulk_store', 'copy', 'forward' or 'local'")
         if mode == "forward" and with_mask:
             raise ValueError("mode 'forward' gathers the HDR image only (with_mask=False)")
         self.mode, self.groups = mode, max(1, int(groups))
@@ -84,8 +86,10 @@ class ShardedFrame:
             self.peer.hdr_ptr = self.r.open_peer_image(handles[0])
             # without god rays the mask never leaves the GPU that made it: stores stay local
             self.peer.mask_ptr = self.r.open_peer_image(handles[1]) if self.with_mask else 0
-            if self.mode == "peer_store":
+            if self.mode in ("peer_store", "bulk_store"):
                 self.r.set_cloud_output(self.peer.hdr_ptr, self.peer.mask_ptr or None)
+                if self.mode == "bulk_store":
+                    self.r.set_cloud_store_mode(1)
             elif self.mode == "forward":
                 self.r.set_cloud_forward(self.peer.hdr_ptr)
         if self.world > 1:
@@ -94,7 +98,7 @@ class ShardedFrame:
     def dispatch(self):
         """Launch this rank's tiles (asynchronous on the renderer's stream)."""
         n = num_tiles(self.r.height, self.tile_rows)
-        if self.mode in ("peer_store", "forward", "local") or self.rank == 0:
+        if self.mode in ("peer_store", "bulk_store", "forward", "local") or self.rank == 0:
             self.r.dispatch_cloud_tiles(self.tile_rows, self.rank, n, self.world)
             return
         mine = len(range(self.rank, n, self.world))
@@ -117,8 +121,10 @@ class ShardedFrame:
 
     def close(self):
         if self.rank != 0:
-            if self.mode == "peer_store":
+            if self.mode in ("peer_store", "bulk_store"):
                 self.r.set_cloud_output(None, None)
+                if self.mode == "bulk_store":
+                    self.r.set_cloud_store_mode(0)
             elif self.mode == "forward":
                 self.r.set_cloud_forward(None)
             if self.peer.hdr_ptr:

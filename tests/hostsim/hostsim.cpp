@@ -56,6 +56,7 @@ int hs_cloud(const MtCameraUBO* cam, const MtTimeUBO* tm, const MtTuning* tun, c
     P.tx = (((W / 4) + 31) / 32) * 32;
     P.ty = (((H / 4) + 31) / 32) * 32;
     P.full = full == 1;
+    const bool std_dims = lw == 128 && lh == 128 && ld == 128 && hw == 32 && hh == 32 && hd == 32 && cw == 128 && ch == 128;
     MarchConst M;
     cloud_frame_setup(P.cam, P.tm, P.tun, M);
     cloud_frame_jitter(P.tm, W, H, M);
@@ -97,11 +98,12 @@ int hs_cloud(const MtCameraUBO* cam, const MtTimeUBO* tm, const MtTuning* tun, c
                     R.nsteps = n;
                     StepSample S[MT_STEP_SLICES];
                     RayCounters none = { 0, 0, 0, 0, 0, 0 };
-                    const ConeOffsets noCache = { nullptr, nullptr, 0 };
+                    const ConeOffsets noCache = { nullptr, nullptr, 0, 0u, 0u };
                     for (int k = n - 1; k >= 0; --k) {
                         const int jidx = (P.tm.frameCountMod16 + mt_f2i(tk[k])) & 15;
-                        S[k] = tun->use_weather ? cloud_step_sample<false, true, false>(P, M, R, jidx, tk[k], none, noCache)
-                                                : cloud_step_sample<false, false, false>(P, M, R, jidx, tk[k], none, noCache);
+                        S[k] = tun->use_weather ? cloud_step_sample<false, true, 0>(P, M, R, jidx, tk[k], none, noCache)
+                                 : std_dims     ? cloud_step_sample<false, false, 1>(P, M, R, jidx, tk[k], none, noCache)   // as cloud_steps_kernel<false, true>
+                                                : cloud_step_sample<false, false, 0>(P, M, R, jidx, tk[k], none, noCache);
                     }
                     float accum = 0.0f, transmittance = 1.0f, color = 0.0f;
                     for (int k = 0; k < R.nsteps; ++k)
@@ -112,10 +114,10 @@ int hs_cloud(const MtCameraUBO* cam, const MtTimeUBO* tm, const MtTuning* tun, c
                 memcpy(mask + 4 * idx, &m, 16);
                 continue;
             }
-            if (tun->use_weather) cloud_ray<true, true, true, false>(P, M, px, py, id, h, m, cnt, debug ? debug + idx : &scratch, coneXY, coneZ, 1);
-            else if (lw == 128 && lh == 128 && ld == 128 && hw == 32 && hh == 32 && hd == 32 && cw == 128 && ch == 128)  // STD: extents as immediates
-                cloud_ray<true, true, false, true>(P, M, px, py, id, h, m, cnt, debug ? debug + idx : &scratch, coneXY, coneZ, 1);
-            else cloud_ray<true, true, false, false>(P, M, px, py, id, h, m, cnt, debug ? debug + idx : &scratch, nullptr, nullptr, 0);
+            if (tun->use_weather) cloud_ray<true, true, true, 0>(P, M, px, py, id, h, m, cnt, debug ? debug + idx : &scratch, coneXY, coneZ, 1);
+            else if (std_dims)  // STD: extents as immediates, light-cone samples from the (r, F) form
+                cloud_ray<true, true, false, 1>(P, M, px, py, id, h, m, cnt, debug ? debug + idx : &scratch, coneXY, coneZ, 1);
+            else cloud_ray<true, true, false, 0>(P, M, px, py, id, h, m, cnt, debug ? debug + idx : &scratch, nullptr, nullptr, 0);
             tot[0] += cnt.rays; tot[1] += cnt.marched; tot[2] += cnt.steps; tot[3] += cnt.incloud; tot[4] += cnt.cone; tot[5] += cnt.early;
             memcpy(hdr + 4 * idx, &h, 16);
             memcpy(mask + 4 * idx, &m, 16);

@@ -278,6 +278,33 @@ def test_cloud_output_redirect_and_ipc_roundtrip(api, noise):
         assert len(a.export_image_handle(api.IMAGE_CLOUD_CUR)) == 64
 
 
+@pytest.mark.parametrize("w,h", [(480, 270), (322, 182), (1920, 1080)])
+def test_cloud_bulk_store_mode_is_bit_identical(api, noise, w, h):
+    """mtSetCloudStoreMode(MT_STORE_BULK): a warp's pixels leave through shared memory and cp.async.bulk copies -- into the
+    context's own image and into a "peer" image (a second context on this device) -- and are the bytes of the direct stores,
+    also where a tile is partial (322 = 20 * 16 + 2 columns, 182 = 22 * 8 + 6 rows) and for row-tile shards."""
+    cam, tm, _, tun = default_scene(w, h, frame_id=5, total_time=2.0, yaw=-8.0)
+    with make_renderer(api, noise, w, h) as a, make_renderer(api, noise, w, h) as b:
+        for r in (a, b):
+            r.set_camera(cam); r.set_time(tm)
+        a.dispatch_cloud_full()
+        want, want_mask = a.read_image(api.IMAGE_CLOUD_CUR), a.read_image(api.IMAGE_GODRAY_MASK)
+        b.set_cloud_store_mode(api.STORE_BULK)
+        b.dispatch_cloud_full()
+        assert np.array_equal(b.read_image(api.IMAGE_CLOUD_CUR), want)
+        assert np.array_equal(b.read_image(api.IMAGE_GODRAY_MASK), want_mask)
+        b.clear_images()
+        b.set_cloud_output(a.image_device_ptr(api.IMAGE_CLOUD_PREV), None)
+        n = (h + 7) // 8
+        for rank in range(3):
+            b.dispatch_cloud_tiles(8, rank, n, 3)
+        b.synchronize()
+        assert np.array_equal(a.read_image(api.IMAGE_CLOUD_PREV), want)
+        assert not b.read_image(api.IMAGE_CLOUD_CUR).any()
+        b.set_cloud_output(None, None)
+        b.set_cloud_store_mode(api.STORE_DIRECT)
+
+
 @pytest.mark.parametrize("w,h,tile_rows", [(480, 270, 8), (322, 182, 16), (1920, 1080, 8)])
 def test_cloud_forward_pushes_finished_tiles(api, noise, w, h, tile_rows):
     """mtSetCloudForward: the march kernel stores locally and counts finished CTAs per row tile; the side kernel pushes each
