@@ -1,0 +1,32 @@
+#!/bin/bash
+# One multi-GPU measurement session (run under gpurun --gpus N): the driver's own N>1 command (views + sharded_8k sub-record),
+# the reference arm under torchrun, the sharded 8K frame with every gather mode, and the bit-identity test.
+#   gpurun --gpus N -- bash tools/multigpu_session.sh N [tag]
+N=${1:-2}; TAG=${2:-r2}
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
+$TR --master-port 29501 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/${TAG}_n${N}_default.json 2> gpurun_out/${TAG}_n${N}_default.err
+python - <<PY
+import json
+try:
+    d = json.load(open("gpurun_out/${TAG}_n${N}_default.json"))
+    print("default N=$N: views", d["value"], "Mrays/s", d["ms_per_step"], "ms; e2e", d["e2e"]["value"])
+    print("  sharded_8k:", json.dumps(d.get("sharded_8k")))
+except Exception as e:
+    print("default run failed:", e); print(open("gpurun_out/${TAG}_n${N}_default.err").read()[-1500:])
+PY
+for G in peer_store bulk_store forward local; do
+  $TR --master-port 29502 bench.py --gpus $N --steps 10 --warmup 3 --workload frame8k --gather $G > gpurun_out/${TAG}_n${N}_8k_$G.json 2> gpurun_out/${TAG}_n${N}_8k_$G.err
+  python - <<PY
+import json
+try:
+    d = json.load(open("gpurun_out/${TAG}_n${N}_8k_$G.json"))
+    print("frame8k N=$N $G:", d["ms_per_step"], "ms", "rank_ms", d.get("rank_ms"), "clock samples", d["clocks"].get("samples"))
+except Exception as e:
+    print("frame8k $G failed:", e); print(open("gpurun_out/${TAG}_n${N}_8k_$G.err").read()[-800:])
+PY
+done
+OMP_NUM_THREADS=1 $TR --master-port 29503 bench.py --gpus $N --impl reference --steps 1 --warmup 0 > gpurun_out/${TAG}_n${N}_ref.json 2> gpurun_out/${TAG}_n${N}_ref.err
+python -c "import json; d=json.load(open('gpurun_out/${TAG}_n${N}_ref.json')); print('reference arm under torchrun:', d['value'], 'Mrays/s, cores', d['cpu_baseline']['cores'])"
+python -m pytest tests/test_gpu_parity.py -m gpu -q -k multi_gpu 2>&1 | tail -2
