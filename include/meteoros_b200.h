@@ -104,7 +104,9 @@ typedef struct MtConfig {
 
 #define MT_FLAG_COUNTERS 1u    /* cloud pass also accumulates MtCounters (slower; for work accounting) */
 #define MT_FLAG_PASS_TIMING 2u /* bracket every pass with CUDA events so mtLastPassMs works               */
-#define MT_FLAG_SEQUENTIAL_MARCH 4u /* 1-of-16 dispatch: one kernel, one thread per ray (default: step-parallel) */
+#define MT_FLAG_SEQUENTIAL_MARCH 4u /* 1-of-16 dispatch: one kernel, one thread per ray (default: step-parallel, one fused kernel) */
+#define MT_FLAG_SPLIT_MARCH 32u     /* 1-of-16 dispatch: the three-kernel step-parallel form (rays / steps / fold through 512 B of
+                                     * global scratch per ray; kept for A/B, profiles/r2_ab.md)                                   */
 #define MT_FLAG_TOP_DOWN 8u         /* full-quality launches walk their row tiles top-down (default: from the horizon upwards, ocean last) */
 #define MT_FLAG_NO_CONE_RF 16u      /* light-cone samples through the canonical four-channel filter instead of the (r, F) form of
                                      * the low-frequency volume (saves its 4 bytes/cell copy; bit-identical decisions either way,

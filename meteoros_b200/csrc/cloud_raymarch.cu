@@ -445,6 +445,103 @@ static bool mt_std_dims(const CloudParams& P)
            P.curl.w == 128 && P.curl.h == 128 && (!MT_CONE_RF || P.low.rfquads != nullptr);  // STD also means: (r, F) quads exist
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// The 1-of-16 dispatch in ONE kernel (default).  The three-kernel form above pays for its parallelism with HBM: every
+// (ray, step) sample travels through a [64][rays] scratch array (71 MB at 1080p, 54 MB of DRAM reads per frame for a pass
+// that outputs 4 MB, profiles/r1_passes_1080p.md) and with two extra launches.  Here a CTA of eight warps owns one 8x4
+// ray tile from start to finish and the samples never leave shared memory:
+//   A  warp 0, one lane per ray: castRay / horizon branches / shells (cloud_ray_setup) and the march loop's own t
+//      sequence, into shared memory (RaySetup[32], t[64][32]); ocean / sky-band pixels are stored right away;
+//   B  all eight warps: warp w evaluates steps w, w+8, ... of the 32 rays (lane = ray), each sample from the filed t_k --
+//      the value the sequential loop holds after k roundings -- into (inc, energy)[64][32];
+//   C  warp 0 folds each ray's samples in step order, composites and stores.
+// 26 KB of shared memory per CTA instead of 80 MB of global scratch; the same device functions in the same order as the
+// sequential kernel, so the image is bit-identical (test_sixteenth_step_parallel_equals_sequential).  While warp 0 of one
+// CTA is in A or C, the other resident CTAs of the SM (six) are in B.
+// ---------------------------------------------------------------------------------------------------------------------
+#define MT_S16_WARPS 8
+#ifndef MT_S16_MINBLOCKS
+#define MT_S16_MINBLOCKS 6
+#endif
+template <bool WEATHER, bool STD>
+__global__ void __launch_bounds__(32 * MT_S16_WARPS, MT_S16_MINBLOCKS) cloud_sixteenth_kernel(const __grid_constant__ CloudParams P)
+{
+    __shared__ MarchConst M;
+    __shared__ RaySetup rays[32];
+    __shared__ float tk[MT_STEP_SLICES][32];
+    __shared__ float2 smp[MT_STEP_SLICES][32];
+    __shared__ int tileSteps;
+    stage_march_const(M, P.mc);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // the CTA's ray tile: 8x4 rays of the (tx, ty) grid, tiles row-major
+    const int tilesX = P.tx >> 3;
+    const int tyi = (int)blockIdx.x / tilesX, txi = (int)blockIdx.x - tyi * tilesX;
+    const int gx = txi * 8 + (lane & 7), gy = tyi * 4 + (lane >> 3);
+    const int pixelID = P.tm.frameCountMod16;
+    const int px = gx * 4 + (pixelID >> 2), py = gy * 4 + (pixelID & 3);
+    const bool valid = gx < P.tx && gy < P.ty && px < P.W && py < P.H;
+    if (warp == 0) {  // ---- A
+        int n = 0;
+        if (!valid) {
+            rays[lane].branch = -1;
+            rays[lane].nsteps = 0;
+        } else {
+            F4 hdr, mask;
+            mask.x = mask.y = mask.z = mask.w = 0.0f;
+            RaySetup R = cloud_ray_setup(P, M, px, py, pixelID, hdr);
+            if (R.branch != 2) store_pixel(P, (size_t)py * P.W + px, hdr, mask);  // ocean / sky band: final
+            else
+                for (float t = R.t_in; t < R.t_out && n < MT_STEP_SLICES; t += R.stepSize) tk[n++][lane] = t;
+            R.nsteps = n;
+            rays[lane] = R;
+        }
+        n = max(n, __shfl_xor_sync(0xffffffffu, n, 16)); n = max(n, __shfl_xor_sync(0xffffffffu, n, 8));
+        n = max(n, __shfl_xor_sync(0xffffffffu, n, 4));  n = max(n, __shfl_xor_sync(0xffffffffu, n, 2));
+        n = max(n, __shfl_xor_sync(0xffffffffu, n, 1));
+        if (lane == 0) tileSteps = n;
+    }
+    __syncthreads();
+    const int nmax = tileSteps;
+    if (nmax == 0) return;  // horizon-culled tile (uniform)
+    const RaySetup& R = rays[lane];
+    {   // ---- B
+        const int mine = R.branch == 2 ? R.nsteps : 0;
+        const ConeOffsets noCache = { nullptr, nullptr, 0, 0u, 0u };  // a thread visits ~7 steps of its ray: not worth a cache
+        RayCounters none = { 0u, 0u, 0u, 0u, 0u, 0u };
+        for (int k = warp; k < nmax; k += MT_S16_WARPS) {
+            if (k < mine) {
+                const float t = tk[k][lane];
+                const int jidx = (pixelID + mt_f2i(t)) & 15;
+                const StepSample S = cloud_step_sample<false, WEATHER, (STD ? 1 : 0)>(P, M, R, jidx, t, none, noCache);
+                smp[k][lane] = make_float2(S.inc, S.energy);
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 0 && R.branch == 2) {  // ---- C
+        const int n = R.nsteps;
+        float accum = 0.0f, transmittance = 1.0f, color = 0.0f;
+        for (int k = 0; k < n; ++k) {
+            const float2 v = smp[k][lane];
+            StepSample S;
+            S.inc = v.x; S.energy = v.y;
+            if (cloud_step_combine(S, accum, transmittance, color)) break;
+        }
+        F4 hdr, mask;
+        cloud_composite(R, accum, color, hdr, mask);
+        store_pixel(P, (size_t)py * P.W + px, hdr, mask);
+    }
+}
+
+cudaError_t mt_launch_cloud_sixteenth_fused(const CloudParams& P, cudaStream_t stream)
+{
+    const unsigned tiles = (unsigned)((P.tx / 8) * (P.ty / 4));  // tx, ty are multiples of 32
+    if (P.tun.use_weather) cloud_sixteenth_kernel<true, false><<<tiles, 32 * MT_S16_WARPS, 0, stream>>>(P);
+    else if (mt_std_dims(P)) cloud_sixteenth_kernel<false, true><<<tiles, 32 * MT_S16_WARPS, 0, stream>>>(P);
+    else cloud_sixteenth_kernel<false, false><<<tiles, 32 * MT_S16_WARPS, 0, stream>>>(P);
+    return cudaGetLastError();
+}
+
 cudaError_t mt_launch_cloud_sixteenth_split(const CloudParams& P0, cudaStream_t stream, int* launches)
 {
     CloudParams P = P0;

@@ -553,7 +553,8 @@ static MtStatus cloud_dispatch(MtContext* c, int full, const RowTiles* tiles, bo
         P.debug = c->debug;
     }
     // the 1-of-16 dispatch runs step-parallel (cloud_raymarch.cu) unless counters / debug records are wanted
-    const bool split = !full && !debug && !P.counters && !(c->flags & MT_FLAG_SEQUENTIAL_MARCH);
+    const bool stepParallel = !full && !debug && !P.counters && !(c->flags & MT_FLAG_SEQUENTIAL_MARCH);
+    const bool split = stepParallel && (c->flags & MT_FLAG_SPLIT_MARCH);  // the three-kernel form (global scratch); default: one fused kernel
     if (split) {  // lazily allocated, each pointer tested by itself: a failed allocation leaves no orphan behind
         const size_t nrays = (size_t)P.tx * (size_t)P.ty;
         if (!c->rays) MT_CUDA(c, cudaMalloc(&c->rays, nrays * 64));
@@ -586,6 +587,7 @@ static MtStatus cloud_dispatch(MtContext* c, int full, const RowTiles* tiles, bo
         n = 2;
     }
     if (split) MT_CUDA(c, mt_launch_cloud_sixteenth_split(P, c->stream, &n));
+    else if (stepParallel) MT_CUDA(c, mt_launch_cloud_sixteenth_fused(P, c->stream));
     else MT_CUDA(c, mt_launch_cloud(P, c->stream));
     if (forward) {
         // Submitted AFTER the march kernel it waits on: streams can share a hardware work queue (CUDA_DEVICE_MAX_CONNECTIONS),

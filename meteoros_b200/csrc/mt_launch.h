@@ -10,6 +10,7 @@ cudaError_t mt_launch_cloud(const CloudParams& P, cudaStream_t stream);
 cudaError_t mt_launch_tile_forward(const void* src, void* dst, int W, int H, const RowTiles& rows, unsigned* tileDone,
                                    int ctas, cudaStream_t stream);
 cudaError_t mt_launch_cloud_sixteenth_split(const CloudParams& P, cudaStream_t stream, int* launches);
+cudaError_t mt_launch_cloud_sixteenth_fused(const CloudParams& P, cudaStream_t stream);
 cudaError_t mt_launch_build_quads(const uint32_t* texels, int w, int h, int d, void* quads, cudaStream_t stream);
 cudaError_t mt_launch_build_rf_quads(const uint32_t* texels, int w, int h, int d, void* quads, cudaStream_t stream);
 cudaError_t mt_launch_occupancy(const Tex3D& low, uint32_t* occ, float coverage, cudaStream_t stream);

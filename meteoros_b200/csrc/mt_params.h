@@ -23,8 +23,11 @@ struct float2 { float x, y; };
 #define MT_CTA_H 8
 #endif
 
-#define MT_MAX_MARCH_ITERS 128  /* maxSteps <= 60; guards degenerate shells (also in the oracle) */
-#define MT_STEP_SLICES 64       /* step-parallel path: slices launched per ray (maxSteps <= 58 + fp slack) */
+/* One cap on the march loop for every path -- the sequential kernels, the step-parallel 1-of-16 kernels and the oracle.  The
+ * shader's own bound is maxSteps <= 60 (cloudRayMarch.comp:585), i.e. at most 61 iterations of `t += stepSize`; 59 is the most
+ * any camera of the test suite produces.  The cap only guards degenerate shells and is never reached. */
+#define MT_MAX_MARCH_ITERS 64
+#define MT_STEP_SLICES MT_MAX_MARCH_ITERS  /* step-parallel paths: sample slots per ray */
 
 struct F4 {  // 16-byte pixel; float4 on the device
     float x, y, z, w;

@@ -503,8 +503,9 @@ static float ray_march(const CloudEnv* e, Ray ray, v3 earthCenter, v3 startPos, 
     const v3 wind = V3(tun->wind_direction[0], tun->wind_direction[1], tun->wind_direction[2]);
     const float lengthToInner = length3(sub3(startPos, ray.origin));
 
-    int iters = 0; /* maxSteps <= 60; the cap only guards degenerate shells (same cap in the CUDA kernel) */
-    for (float t = start_t; t < end_t && iters < 128; t += stepSize, ++iters) {
+    int iters = 0; /* maxSteps <= 60, so at most 61 iterations; the cap only guards degenerate shells and is never reached
+                    * (MT_MAX_MARCH_ITERS: the same cap in every CUDA path) */
+    for (float t = start_t; t < end_t && iters < 64; t += stepSize, ++iters) {
         /* int(mod(float(pixelID + int(t)), 16.0)) */
         float fi = (float)(pixelID + f2i(t));
         int _index = f2i(fi - 16.0f * floorf(fi / 16.0f));

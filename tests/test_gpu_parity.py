@@ -739,4 +739,5 @@ def test_multi_gpu_sharded_frame_is_bit_identical():
                         "--master-addr", "127.0.0.1", "--master-port", "29877", str(root / "tools" / "check_sharded.py")],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert r.stdout.count("bit-identical to single-GPU: True") == 4
+    # peer_store, bulk_store and copy with and without the mask, forward without: seven gathered frames, all identical
+    assert r.stdout.count("bit-identical to single-GPU: True") == 7 and "single-GPU: False" not in r.stdout, r.stdout[-2000:]

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Multi-GPU correctness check (run under torchrun with 2+ ranks): the row-tile sharded frame gathered on rank 0 --
-by kernel peer stores, by copy-engine pushes and by the tile-forwarding side kernel -- must be bit-identical to the
+by kernel peer stores (direct and through cp.async.bulk), by copy-engine pushes and by the tile-forwarding side kernel -- must be bit-identical to the
 single-GPU frame.  Each mode runs three frames in a row so that frame-to-frame hazards would show."""
 import os
 import sys
@@ -20,7 +20,7 @@ w, h = 1920, 1080
 cam, sc = scene.Camera(w, h), scene.Scene()
 sc.update_time(1 / 60)
 ok = True
-for mode in ("peer_store", "copy", "forward"):
+for mode in ("peer_store", "bulk_store", "copy", "forward"):
     for with_mask in ((False,) if mode == "forward" else (True, False)):
         with api.CloudRenderer(w, h, device=local) as r:
             r.upload_noise(textures.load_noise())

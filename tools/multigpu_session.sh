@@ -16,17 +16,24 @@ try:
 except Exception as e:
     print("default run failed:", e); print(open("gpurun_out/${TAG}_n${N}_default.err").read()[-1500:])
 PY
-for G in peer_store bulk_store forward local; do
-  $TR --master-port 29502 bench.py --gpus $N --steps 10 --warmup 3 --workload frame8k --gather $G > gpurun_out/${TAG}_n${N}_8k_$G.json 2> gpurun_out/${TAG}_n${N}_8k_$G.err
+run8k() {  # name, extra args
+  NAME=$1; shift
+  $TR --master-port 29502 bench.py --gpus $N --steps 10 --warmup 3 --workload frame8k "$@" > gpurun_out/${TAG}_n${N}_8k_$NAME.json 2> gpurun_out/${TAG}_n${N}_8k_$NAME.err
   python - <<PY
 import json
 try:
-    d = json.load(open("gpurun_out/${TAG}_n${N}_8k_$G.json"))
-    print("frame8k N=$N $G:", d["ms_per_step"], "ms", "rank_ms", d.get("rank_ms"), "clock samples", d["clocks"].get("samples"))
+    d = json.load(open("gpurun_out/${TAG}_n${N}_8k_$NAME.json"))
+    print("frame8k N=$N $NAME:", d["ms_per_step"], "ms", "rank_ms", d.get("rank_ms"), "clock samples", d["clocks"].get("samples"))
 except Exception as e:
-    print("frame8k $G failed:", e); print(open("gpurun_out/${TAG}_n${N}_8k_$G.err").read()[-800:])
+    print("frame8k $NAME failed:", e); print(open("gpurun_out/${TAG}_n${N}_8k_$NAME.err").read()[-800:])
 PY
-done
+}
+run8k peer_store --gather peer_store
+run8k bulk_store --gather bulk_store
+run8k local --gather local
+run8k peer_topdown --gather peer_store --ctx-flags 8
+run8k peer_rows32 --gather peer_store --tile-rows 32
+if [ "$FORWARD" = "1" ]; then run8k forward --gather forward; fi
 OMP_NUM_THREADS=1 $TR --master-port 29503 bench.py --gpus $N --impl reference --steps 1 --warmup 0 > gpurun_out/${TAG}_n${N}_ref.json 2> gpurun_out/${TAG}_n${N}_ref.err
 python -c "import json; d=json.load(open('gpurun_out/${TAG}_n${N}_ref.json')); print('reference arm under torchrun:', d['value'], 'Mrays/s, cores', d['cpu_baseline']['cores'])"
 python -m pytest tests/test_gpu_parity.py -m gpu -q -k multi_gpu 2>&1 | tail -2
