@@ -477,7 +477,7 @@ def main():
     # exported, so every frame is gathered in, and read back from, IMAGE_CLOUD_CUR (the next dispatch waits for the read).
     sharded = args.workload == "frame8k"
     out_which = api.IMAGE_LDR_PREV if seq else (api.IMAGE_CLOUD_CUR if sharded else api.IMAGE_CLOUD_PREV)
-    nbytes = w * h * (4 if seq else 16)
+    nbytes = w * h * (4 if seq else (8 if args.storage == 2 else 16))
     pinned = [torch.empty(nbytes, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
     h2d = int(cam.nbytes + tm.nbytes + tun.nbytes + sky.nbytes)
     e2e_read = (rank == 0) or args.workload != "frame8k"
@@ -508,6 +508,34 @@ def main():
     barrier()
     e2e_s = time.perf_counter() - t0
 
+    # ---- the same end-to-end loop with RGBA16F images (MT_STORAGE_F16: the reference's own image format, Renderer.cpp:1431-1440):
+    # half the bytes over PCIe.  Reported beside the RGBA32F figure (north_star names RGBA32F as the output), cloud4k only.
+    e2e16_s, nbytes16 = None, w * h * 8
+    if args.workload == "cloud4k" and args.storage != 2:
+        r16 = api.CloudRenderer(w, h, device=local_rank, storage=2, flags=args.ctx_flags)
+        r16.upload_noise(noise)
+        pin16 = [torch.empty(nbytes16, dtype=torch.uint8, pin_memory=True) for _ in range(4)]
+
+        def e2e16_step(i):
+            r16.set_camera(cam); r16.set_time(tm); r16.set_tuning(tun); r16.set_sun_and_sky(sky)
+            r16.dispatch_cloud_full()
+            r16.swap_ping_pong()
+            r16.read_image_async(api.IMAGE_CLOUD_PREV, pin16[i & 1].data_ptr(), nbytes16)
+            r16.read_image_async(api.IMAGE_GODRAY_MASK, pin16[2 + (i & 1)].data_ptr(), nbytes16)
+
+        for i in range(2):
+            e2e16_step(i)
+        r16.wait_reads()
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            e2e16_step(i)
+        r16.wait_reads()
+        r16.synchronize()
+        barrier()
+        e2e16_s = time.perf_counter() - t0
+        r16.close()
+
     # ---- max over ranks
     if world > 1:
         t = torch.tensor([dev_ms_total, e2e_s], dtype=torch.float64, device=f"cuda:{local_rank}")
@@ -516,6 +544,10 @@ def main():
         rank_ms = [round(float(x[0]) / args.steps, 4) for x in per_rank]   # device ms per step of every rank
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_ms_total, e2e_s = float(t[0]), float(t[1])
+        if e2e16_s is not None:
+            t16 = torch.tensor([e2e16_s], dtype=torch.float64, device=f"cuda:{local_rank}")
+            dist.all_reduce(t16, op=dist.ReduceOp.MAX)
+            e2e16_s = float(t16[0])
         cs = torch.tensor([counters[k] for k in ("rays", "rays_marched", "steps", "steps_incloud", "cone_hits", "early_exits")],
                           dtype=torch.float64, device=f"cuda:{local_rank}")
         dist.all_reduce(cs, op=dist.ReduceOp.SUM)
@@ -558,6 +590,10 @@ def main():
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int((nbytes * (2 if read_mask else 1)) if e2e_read else 0),
                     "reads": ("HDR colour + god-ray image" if read_mask else ("LDR frame" if seq else "HDR colour (the god-ray image stays on its GPU unless --gather-mask)")),
                     "ms_per_step": round(1e3 * e2e_s / args.steps, 4)},
+            "e2e_f16": None if e2e16_s is None else {
+                "value": round(rays_total_per_step * args.steps / e2e16_s / 1e6, 2), "unit": UNIT, "ms_per_step": round(1e3 * e2e16_s / args.steps, 4),
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(2 * nbytes16), "storage": "MT_STORAGE_F16: RGBA16F images, the reference's own format (Renderer.cpp:1431-1440)",
+                "reads": "HDR colour + god-ray image"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
             "work": {k: int(v) for k, v in counters.items()},
         }

@@ -89,8 +89,12 @@ typedef struct MtTuning {
 
 typedef enum MtStorage {
     MT_STORAGE_F32 = 0,         /* HDR + mask images are RGBA32F (what the shaders declare, reprojection.comp:10-11) */
-    MT_STORAGE_F16_EMULATE = 1  /* values are rounded through binary16 at every store, like the reference's
+    MT_STORAGE_F16_EMULATE = 1, /* values are rounded through binary16 at every store, like the reference's
                                    R16G16B16A16_SFLOAT images (Renderer.cpp:1431-1440); memory stays RGBA32F */
+    MT_STORAGE_F16 = 2          /* HDR + mask images ARE RGBA16F (8 bytes / pixel), the reference's actual format
+                                   (Renderer.cpp:1431-1440): the same values as F16_EMULATE in half the HBM, NVLink and PCIe
+                                   bytes.  mtReadImage / mtWriteImage / mtImageBytes then speak RGBA16F for the three float
+                                   images; the width must be even for mtSetCloudForward. */
 } MtStorage;
 
 typedef struct MtConfig {
@@ -105,6 +109,8 @@ typedef struct MtConfig {
 #define MT_FLAG_COUNTERS 1u    /* cloud pass also accumulates MtCounters (slower; for work accounting) */
 #define MT_FLAG_PASS_TIMING 2u /* bracket every pass with CUDA events so mtLastPassMs works               */
 #define MT_FLAG_SEQUENTIAL_MARCH 4u /* 1-of-16 dispatch: one kernel, one thread per ray (default: step-parallel, one fused kernel) */
+#define MT_FLAG_NO_FUSED_TONEMAP 64u /* mtFrame / mtFrameEx: run god rays and tone map as two passes (default: the god-ray kernel tone-maps
+                                     * the pixel it has just finished; same bytes)                                               */
 #define MT_FLAG_SPLIT_MARCH 32u     /* 1-of-16 dispatch: the three-kernel step-parallel form (rays / steps / fold through 512 B of
                                      * global scratch per ray; kept for A/B, profiles/r2_ab.md)                                   */
 #define MT_FLAG_TOP_DOWN 8u         /* full-quality launches walk their row tiles top-down (default: from the horizon upwards, ocean last) */
@@ -122,7 +128,7 @@ typedef enum MtTextureSlot {
 
 /* Images = Renderer::CreateResources (Renderer.cpp:1428-1447).  CUR/PREV are the ping-pong ROLES at call time. */
 typedef enum MtImage {
-    MT_IMAGE_CLOUD_CUR = 0,   /* currentFrameResultImage   RGBA32F, W*H*16 bytes */
+    MT_IMAGE_CLOUD_CUR = 0,   /* currentFrameResultImage   RGBA32F, W*H*16 bytes (RGBA16F, W*H*8, with MT_STORAGE_F16) */
     MT_IMAGE_CLOUD_PREV = 1,  /* previousFrameResultImage  RGBA32F               */
     MT_IMAGE_GODRAY_MASK = 2, /* godRaysCreationDataImage  RGBA32F               */
     MT_IMAGE_LDR = 3,         /* currentFrameTexture: tone-mapped (then TXAA'd) frame, W*H*4.  Stored here as RGBA8 UNORM -- what

@@ -15,7 +15,7 @@ from . import _lib
 from .scene import CAMERA_DTYPE, SUNSKY_DTYPE, TIME_DTYPE, TUNING_DTYPE
 
 MT_OK = 0
-STORAGE_F32, STORAGE_F16_EMULATE = 0, 1
+STORAGE_F32, STORAGE_F16_EMULATE, STORAGE_F16 = 0, 1, 2
 FLAG_COUNTERS, FLAG_PASS_TIMING, FLAG_SEQUENTIAL_MARCH, FLAG_TOP_DOWN, FLAG_NO_CONE_RF, FLAG_SPLIT_MARCH = 1, 2, 4, 8, 16, 32
 TEX_LOW_FREQ, TEX_HIGH_FREQ, TEX_CURL, TEX_WEATHER = 0, 1, 2, 3
 IMAGE_CLOUD_CUR, IMAGE_CLOUD_PREV, IMAGE_GODRAY_MASK, IMAGE_LDR, IMAGE_LDR_PREV = 0, 1, 2, 3, 4
@@ -57,6 +57,7 @@ class CloudRenderer:
     def __init__(self, width: int, height: int, device: int = 0, storage: int = STORAGE_F32, flags: int = 0):
         self._lib = _lib.load()
         self.width, self.height = int(width), int(height)
+        self.storage = int(storage)
         cfg = _lib.MtConfig(C.sizeof(_lib.MtConfig), self.width, self.height, int(device), int(storage), int(flags))
         h = C.c_void_p()
         st = self._lib.mtCreate(C.byref(cfg), C.byref(h))
@@ -183,7 +184,9 @@ class CloudRenderer:
 
     # ---- images ---------------------------------------------------------------------------------------------
     def _image_shape(self, which: int):
-        return (self.height, self.width, 4), (np.uint8 if which in (IMAGE_LDR, IMAGE_LDR_PREV) else np.float32)
+        if which in (IMAGE_LDR, IMAGE_LDR_PREV):
+            return (self.height, self.width, 4), np.uint8
+        return (self.height, self.width, 4), (np.float16 if self.storage == STORAGE_F16 else np.float32)
 
     def read_image(self, which: int, out: np.ndarray | None = None) -> np.ndarray:
         shape, dt = self._image_shape(which)

@@ -212,12 +212,15 @@ MT_DEVICE float erosion_edge(const Tex2D& curl, const Tex3D& high, f3 p, float h
 MT_DEVICE float erode(float base, float edge) { return div_nice(base - edge, 1.0f - edge); }  // remap(base, edge, 1, 0, 1); edge in [0, 0.005]
 
 // GetLightEnergy (cloudRayMarch.comp:331-388), live branch only.
+// Radiance only (no decision reads it): the three remaps divide by constants (1 - 0.7, 0.85 - 0.3, 0.34 - 0.07), written as
+// multiplications by the reciprocal -- one instruction instead of the ~9 of an IEEE division, one ulp apart at most.
+MT_DEVICE float remap_rcp(float v, float omin, float rcpRange, float nmin, float nmax) { return nmin + (((v - omin) * rcpRange) * (nmax - nmin)); }
 MT_DEVICE float light_energy(float h, float dl, float ds, float phase, float cosa)
 {
     float p = MT_EXPF(-dl);
-    float att = fmaxf(remap1(cosa, 0.7f, 1.0f, p, p * 0.25f), p);
-    float depth = 0.05f + MT_POWF(ds, clamp1(remap1(h * 0.125f, 0.3f, 0.85f, 0.5f, 2.0f), 0.5f, 2.0f));
-    float vert = MT_POWF(clamp1(remap1(h * 1.5f, 0.07f, 0.34f, 0.1f, 1.0f), 0.1f, 1.0f), 0.8f);
+    float att = fmaxf(remap_rcp(cosa, 0.7f, 1.0f / (1.0f - 0.7f), p, p * 0.25f), p);
+    float depth = 0.05f + MT_POWF(ds, clamp1(remap_rcp(h * 0.125f, 0.3f, 1.0f / (0.85f - 0.3f), 0.5f, 2.0f), 0.5f, 2.0f));
+    float vert = MT_POWF(clamp1(remap_rcp(h * 1.5f, 0.07f, 1.0f / (0.34f - 0.07f), 0.1f, 1.0f), 0.1f, 1.0f), 0.8f);
     return (((att * p) * (depth * vert)) * phase) * 5.0f;
 }
 

@@ -11,6 +11,7 @@
 
 #include "cloud_core.cuh"
 #include "mt_launch.h"
+#include "mt_pixel.cuh"
 
 __global__ void cloud_setup_kernel(CamU cam, TimeU tm, MtTuning tun, int W, int H, MarchConst* out)
 {
@@ -102,7 +103,6 @@ cudaError_t mt_launch_occupancy(const Tex3D& low, uint32_t* occ, float coverage,
     return cudaGetLastError();
 }
 
-__device__ __forceinline__ float f16_round(float x) { return __half2float(__float2half_rn(x)); }
 
 template <bool FULL, bool COUNT, bool DEBUG, bool WEATHER, bool STD>
 #ifndef MT_CLOUD_MINBLOCKS
@@ -133,13 +133,12 @@ __global__ void __launch_bounds__(128, MT_CLOUD_MINBLOCKS) cloud_raymarch_kernel
         const int ly = ((warp >> 1) << 2) + (lane >> 3);
 #endif
         const int bpt = P.rows.tile_rows / MT_CTA_H;            // CTAs per row tile, vertically
-        // CTAs are dispatched in blockIdx order.  The owned tiles above the horizon are walked from the horizon upwards
-        // (RowTiles.heavy_first): the rows with the most march steps start first, the zenith rows later and the ocean /
-        // sky-band tiles, which retire in ~100 instructions, last.
+        // CTAs are dispatched in blockIdx order; mt_tile_order (mt_params.h) walks the marching tiles from the horizon upwards
+        // and interleaves the ocean / sky-band tiles with them.
         const int by = (int)blockIdx.y;
-        int ltile = by / bpt;
-        const int inTile = by - ltile * bpt;
-        if (ltile < P.rows.heavy_first) ltile = P.rows.heavy_first - 1 - ltile;
+        const int jtile = by / bpt;
+        const int inTile = by - jtile * bpt;
+        const int ltile = mt_tile_order(P.rows, jtile);
         doneSlot = ltile;
         const int tile = P.rows.tile_begin + ltile * P.rows.tile_stride;
         px = blockIdx.x * MT_CTA_W + lx;
@@ -194,27 +193,35 @@ __global__ void __launch_bounds__(128, MT_CLOUD_MINBLOCKS) cloud_raymarch_kernel
         const size_t idx = (size_t)py * (size_t)P.W + (size_t)px;
         cloud_ray<COUNT, DEBUG, WEATHER, (STD ? (MT_CONE_PIPE ? 2 : 1) : 0)>(P, M, px, py, pixelID, hdr, mask, cnt, DEBUG ? (P.debug + idx) : nullptr, cxy, cz, 128,
                                                                            cstage, cstride);
-        if (P.f16_emulate) {
-            hdr.x = f16_round(hdr.x); hdr.y = f16_round(hdr.y); hdr.z = f16_round(hdr.z); hdr.w = f16_round(hdr.w);
-            mask.x = f16_round(mask.x); mask.y = f16_round(mask.y); mask.z = f16_round(mask.z); mask.w = f16_round(mask.w);
-        }
+        const float4 h4 = make_float4(hdr.x, hdr.y, hdr.z, hdr.w);
         if (bulk) {
             // The marching warp must not wait on a remote write: its 32 pixels go to shared memory, and lanes 0 and 16 each
-            // hand one 256-byte row segment to the bulk-copy engine, then wait only until the engine has read the buffer.
-            outStage[warp][lane] = make_float4(hdr.x, hdr.y, hdr.z, hdr.w);
+            // hand one row segment (256 bytes, 128 in RGBA16F) to the bulk-copy engine, then wait only until the engine has
+            // read the buffer.
+            unsigned src;
+            if (P.storage == MT_PX_F16) {
+                reinterpret_cast<uint2*>(&outStage[warp][0])[lane] = px_pack_f16(h4);
+                src = (unsigned)__cvta_generic_to_shared(reinterpret_cast<uint2*>(&outStage[warp][0]) + lane);
+            } else {
+                outStage[warp][lane] = P.storage == MT_PX_F16_EMULATE ? px_round_f16(h4) : h4;
+                src = (unsigned)__cvta_generic_to_shared(&outStage[warp][lane]);
+            }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the async proxy
             __syncwarp();
             if ((lane & 15) == 0) {
-                const unsigned src = (unsigned)__cvta_generic_to_shared(&outStage[warp][lane]);
-                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 256;" ::"l"(reinterpret_cast<float4*>(P.hdr) + idx), "r"(src)
-                             : "memory");
+                if (P.storage == MT_PX_F16)
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 128;" ::"l"(reinterpret_cast<uint2*>(P.hdr) + idx), "r"(src)
+                                 : "memory");
+                else
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 256;" ::"l"(reinterpret_cast<float4*>(P.hdr) + idx), "r"(src)
+                                 : "memory");
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             }
         } else {
-            reinterpret_cast<float4*>(P.hdr)[idx] = make_float4(hdr.x, hdr.y, hdr.z, hdr.w);
+            px_store(P.hdr, idx, h4, P.storage);
         }
-        reinterpret_cast<float4*>(P.mask)[idx] = make_float4(mask.x, mask.y, mask.z, mask.w);
+        px_store(P.mask, idx, make_float4(mask.x, mask.y, mask.z, mask.w), P.storage);
     }
     if (FULL && !COUNT && !DEBUG && P.tileDone) {  // uniform: tell tile_forward_kernel that this CTA's pixels are in memory
         __threadfence();
@@ -267,12 +274,8 @@ __device__ __forceinline__ void stage_march_const(MarchConst& M, const MarchCons
 
 __device__ __forceinline__ void store_pixel(const CloudParams& P, size_t idx, F4 hdr, F4 mask)
 {
-    if (P.f16_emulate) {
-        hdr.x = f16_round(hdr.x); hdr.y = f16_round(hdr.y); hdr.z = f16_round(hdr.z); hdr.w = f16_round(hdr.w);
-        mask.x = f16_round(mask.x); mask.y = f16_round(mask.y); mask.z = f16_round(mask.z); mask.w = f16_round(mask.w);
-    }
-    reinterpret_cast<float4*>(P.hdr)[idx] = make_float4(hdr.x, hdr.y, hdr.z, hdr.w);
-    reinterpret_cast<float4*>(P.mask)[idx] = make_float4(mask.x, mask.y, mask.z, mask.w);
+    px_store(P.hdr, idx, make_float4(hdr.x, hdr.y, hdr.z, hdr.w), P.storage);
+    px_store(P.mask, idx, make_float4(mask.x, mask.y, mask.z, mask.w), P.storage);
 }
 
 __global__ void __launch_bounds__(128) cloud_rays_kernel(const __grid_constant__ CloudParams P)
@@ -590,12 +593,13 @@ cudaError_t mt_launch_cloud_sixteenth_split(const CloudParams& P0, cudaStream_t 
 // The wait is bounded (~seconds): should the march kernel never run beside this one, the kernel flags the overrun in
 // the word after the last counter and leaves instead of hanging the device; mtSynchronize reports it.
 #define MT_FORWARD_MAX_POLLS (1u << 24)
-__global__ void __launch_bounds__(256) tile_forward_kernel(const float4* __restrict__ src, float4* __restrict__ dst, int W, int H,
+// W16 = 16-byte words per image row (W for RGBA32F, W / 2 for RGBA16F; W is even there: mtSetCloudForward checks)
+__global__ void __launch_bounds__(256) tile_forward_kernel(const float4* __restrict__ src, float4* __restrict__ dst, int W16, int H,
                                                            RowTiles rows, unsigned* tileDone, unsigned ctasPerTile)
 {
     __shared__ int timedOut;
     for (int j = blockIdx.x; j < rows.tile_count; j += gridDim.x) {
-        const int lt = j < rows.heavy_first ? rows.heavy_first - 1 - j : j;  // the order the march kernel issues its tiles in
+        const int lt = mt_tile_order(rows, j);  // the order the march kernel issues its tiles in
         if (threadIdx.x == 0) {
             const volatile unsigned* done = tileDone + lt;
             unsigned polls = 0;
@@ -609,9 +613,9 @@ __global__ void __launch_bounds__(256) tile_forward_kernel(const float4* __restr
         const size_t tile = (size_t)rows.tile_begin + (size_t)lt * (size_t)rows.tile_stride;
         const size_t r0 = tile * (size_t)rows.tile_rows;
         const size_t r1 = r0 + (size_t)rows.tile_rows < (size_t)H ? r0 + (size_t)rows.tile_rows : (size_t)H;
-        const float4* s = src + r0 * (size_t)W;
-        float4* d = dst + r0 * (size_t)W;
-        const size_t n = (r1 - r0) * (size_t)W;
+        const float4* s = src + r0 * (size_t)W16;
+        float4* d = dst + r0 * (size_t)W16;
+        const size_t n = (r1 - r0) * (size_t)W16;
         for (size_t i = threadIdx.x; i < n; i += 1024) {  // four independent 16-byte loads in flight per thread
             float4 v[4];
 #pragma unroll
@@ -625,13 +629,13 @@ __global__ void __launch_bounds__(256) tile_forward_kernel(const float4* __restr
     }
 }
 
-cudaError_t mt_launch_tile_forward(const void* src, void* dst, int W, int H, const RowTiles& rows, unsigned* tileDone,
+cudaError_t mt_launch_tile_forward(const void* src, void* dst, int W, int H, int bytesPerPixel, const RowTiles& rows, unsigned* tileDone,
                                    int ctas, cudaStream_t stream)
 {
     if (rows.tile_count <= 0) return cudaSuccess;
     const unsigned ctasPerTile = (unsigned)((W + MT_CTA_W - 1) / MT_CTA_W) * (unsigned)(rows.tile_rows / MT_CTA_H);
     const int grid = ctas < rows.tile_count ? ctas : rows.tile_count;
-    tile_forward_kernel<<<grid, 256, 0, stream>>>((const float4*)src, (float4*)dst, W, H, rows, tileDone, ctasPerTile);
+    tile_forward_kernel<<<grid, 256, 0, stream>>>((const float4*)src, (float4*)dst, W * bytesPerPixel / 16, H, rows, tileDone, ctasPerTile);
     return cudaGetLastError();
 }
 

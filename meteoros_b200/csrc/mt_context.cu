@@ -35,7 +35,7 @@ struct MtContext {
     F4* hdr[2] = { nullptr, nullptr };
     int cur = 0;  // index of the image that currently plays "currentFrameResultImage"
     F4* mask = nullptr;
-    float* maskDecoded = nullptr;  // (W+2) x (H+2): scratch of the god-ray pass
+    float2* maskDecoded = nullptr; // (W+2) x (H+2) pairs: scratch of the god-ray pass
     F4* maskStage = nullptr;       // device snapshot of the mask behind mtReadImageAsync (lazily allocated)
     uint32_t* ldr[2] = { nullptr, nullptr };  // ping-pong with the HDR images (same `cur`)
     uint32_t* ldrScratch = nullptr;           // TXAA output, swapped with ldr[cur] after the pass
@@ -93,11 +93,12 @@ static MtStatus cuda_fail(MtContext* c, cudaError_t e, const char* what)
         if (!(cond)) return fail((c), MT_ERR_INVALID, (msg)); \
     } while (0)
 
-static size_t image_bytes(const MtContext* c, MtImage w)
+static size_t hdr_pixel_bytes(uint32_t storage) { return storage == MT_STORAGE_F16 ? 8 : 16; }
+static size_t pixel_bytes(const MtContext* c, MtImage w)
 {
-    size_t px = (size_t)c->W * (size_t)c->H;
-    return (w == MT_IMAGE_LDR || w == MT_IMAGE_LDR_PREV) ? px * 4 : px * 16;
+    return (w == MT_IMAGE_LDR || w == MT_IMAGE_LDR_PREV) ? 4 : hdr_pixel_bytes(c->storage);
 }
+static size_t image_bytes(const MtContext* c, MtImage w) { return (size_t)c->W * (size_t)c->H * pixel_bytes(c, w); }
 static void* image_ptr(MtContext* c, MtImage w)
 {
     switch (w) {
@@ -127,7 +128,7 @@ struct ImageSet {
     F4* mask = nullptr;
     uint32_t* ldr[2] = { nullptr, nullptr };
     uint32_t* ldrScratch = nullptr;
-    float* maskDecoded = nullptr;
+    float2* maskDecoded = nullptr;
 };
 static void free_image_set(ImageSet& s)
 {
@@ -135,20 +136,20 @@ static void free_image_set(ImageSet& s)
     cudaFree(s.ldr[0]); cudaFree(s.ldr[1]); cudaFree(s.ldrScratch); cudaFree(s.maskDecoded);
     s = ImageSet();
 }
-static cudaError_t alloc_image_set(ImageSet& s, int W, int H, cudaStream_t stream)
+static cudaError_t alloc_image_set(ImageSet& s, int W, int H, size_t hb, cudaStream_t stream)  // hb: bytes per HDR / mask pixel
 {
     const size_t px = (size_t)W * (size_t)H;
     cudaError_t e;
-    if ((e = cudaMalloc((void**)&s.hdr[0], px * 16)) != cudaSuccess) return e;
-    if ((e = cudaMalloc((void**)&s.hdr[1], px * 16)) != cudaSuccess) return e;
-    if ((e = cudaMalloc((void**)&s.mask, px * 16)) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void**)&s.hdr[0], px * hb)) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void**)&s.hdr[1], px * hb)) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void**)&s.mask, px * hb)) != cudaSuccess) return e;
     if ((e = cudaMalloc((void**)&s.ldr[0], px * 4)) != cudaSuccess) return e;
     if ((e = cudaMalloc((void**)&s.ldr[1], px * 4)) != cudaSuccess) return e;
     if ((e = cudaMalloc((void**)&s.ldrScratch, px * 4)) != cudaSuccess) return e;
-    if ((e = cudaMalloc((void**)&s.maskDecoded, (size_t)(W + 2) * (size_t)(H + 2) * sizeof(float))) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(s.hdr[0], 0, px * 16, stream)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(s.hdr[1], 0, px * 16, stream)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(s.mask, 0, px * 16, stream)) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void**)&s.maskDecoded, (size_t)(W + 2) * (size_t)(H + 2) * sizeof(float2))) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(s.hdr[0], 0, px * hb, stream)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(s.hdr[1], 0, px * hb, stream)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(s.mask, 0, px * hb, stream)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(s.ldr[0], 0, px * 4, stream)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(s.ldr[1], 0, px * 4, stream)) != cudaSuccess) return e;
     return cudaMemsetAsync(s.ldrScratch, 0, px * 4, stream);
@@ -187,7 +188,7 @@ static void adopt_images(MtContext* c, const ImageSet& s)
 static MtStatus alloc_images(MtContext* c)
 {
     ImageSet s;
-    const cudaError_t e = alloc_image_set(s, c->W, c->H, c->stream);
+    const cudaError_t e = alloc_image_set(s, c->W, c->H, hdr_pixel_bytes(c->storage), c->stream);
     if (e != cudaSuccess) {
         free_image_set(s);
         (void)cudaGetLastError();
@@ -243,7 +244,7 @@ try {
     if (!cfg || !out) return MT_ERR_INVALID;
     *out = nullptr;
     if (cfg->struct_size != sizeof(MtConfig) || cfg->width == 0 || cfg->height == 0 || cfg->width > 32768 ||
-        cfg->height > 32768 || cfg->storage > MT_STORAGE_F16_EMULATE)
+        cfg->height > 32768 || cfg->storage > MT_STORAGE_F16)
         return MT_ERR_INVALID;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || cfg->device < 0 || cfg->device >= ndev) return MT_ERR_CUDA;
@@ -327,7 +328,7 @@ try {
     // Transactional: the images of the new size are allocated BEFORE anything of the old size is released.  On failure the
     // context keeps its old size, images and peer state and stays fully usable (the caller sees MT_ERR_OOM / MT_ERR_CUDA).
     ImageSet s;
-    const cudaError_t e = alloc_image_set(s, (int)w, (int)h, c->stream);
+    const cudaError_t e = alloc_image_set(s, (int)w, (int)h, hdr_pixel_bytes(c->storage), c->stream);
     if (e != cudaSuccess) {
         free_image_set(s);
         (void)cudaGetLastError();
@@ -515,7 +516,7 @@ static MtStatus cloud_dispatch(MtContext* c, int full, const RowTiles* tiles, bo
     P.tx = (((c->W / 4) + 31) / 32) * 32;  // Renderer.cpp:713-714
     P.ty = (((c->H / 4) + 31) / 32) * 32;
     P.full = full;
-    P.f16_emulate = c->storage == MT_STORAGE_F16_EMULATE;
+    P.storage = (int)c->storage;
     P.bulkStore = c->storeMode == (int)MT_STORE_BULK;
     if (tiles) P.rows = *tiles;
     else if (full) {  // whole frame = every 8-row tile, so that the launch-order heuristic below applies to it as well
@@ -593,7 +594,7 @@ static MtStatus cloud_dispatch(MtContext* c, int full, const RowTiles* tiles, bo
         // Submitted AFTER the march kernel it waits on: streams can share a hardware work queue (CUDA_DEVICE_MAX_CONNECTIONS),
         // and a spinning kernel queued ahead of the kernel that feeds it would then never be fed.
         MT_CUDA(c, cudaStreamWaitEvent(c->fwdStream, c->fwdArmEv, 0));
-        MT_CUDA(c, mt_launch_tile_forward(P.hdr, c->forwardHdr, c->W, c->H, P.rows, c->tileDone, 8, c->fwdStream));
+        MT_CUDA(c, mt_launch_tile_forward(P.hdr, c->forwardHdr, c->W, c->H, (int)hdr_pixel_bytes(c->storage), P.rows, c->tileDone, 8, c->fwdStream));
         MT_CUDA(c, cudaEventRecord(c->fwdDoneEv, c->fwdStream));
         c->fwdBusy = true;
         c->fwdCheck = true;
@@ -654,7 +655,7 @@ static MtStatus reproject_dispatch(MtContext* c, bool debug)
     P.prev = c->hdr[c->cur ^ 1];
     P.cur = c->hdr[c->cur];
     P.W = c->W; P.H = c->H;
-    P.f16_emulate = c->storage == MT_STORAGE_F16_EMULATE;
+    P.storage = (int)c->storage;
     P.taps = nullptr;
     if (debug) {
         if (!c->taps) MT_CUDA(c, cudaMalloc((void**)&c->taps, (size_t)c->W * c->H * 10 * sizeof(int)));
@@ -684,10 +685,17 @@ try {
     return MT_OK;
 } MT_NOTHROW
 
-MtStatus mtDispatchGodRays(MtContext* c)
-try {
-    if (!c) return MT_ERR_INVALID;
+static unsigned tonemap_seed(const MtContext* c)
+{
+    const float ty = c->tm.time[1];  // uint(time.y): truncate, saturate, NaN -> 0
+    return (ty != ty || ty <= 0.0f) ? 0u : (ty >= 4294967296.0f ? 0xffffffffu : (unsigned)ty);
+}
+// fuse_tonemap: the god-ray kernel also tone-maps the pixel it has just finished (mtFrameEx with both passes): one read of
+// the HDR image less, one launch less.  The LDR bytes are those of mtDispatchToneMap run after mtDispatchGodRays.
+static MtStatus godrays_dispatch(MtContext* c, bool fuse_tonemap)
+{
     if (!c->haveCam) return fail(c, MT_ERR_NOT_READY, "god-ray dispatch: camera uniform not set");
+    if (fuse_tonemap && !c->haveTime) return fail(c, MT_ERR_NOT_READY, "tone-map dispatch: time uniform not set");
     MT_CUDA(c, cudaSetDevice(c->device));
     GodRayParams P;
     memset(&P, 0, sizeof(P));
@@ -697,13 +705,25 @@ try {
     P.decoded = c->maskDecoded;
     P.hdr = c->hdr[c->cur];
     P.W = c->W; P.H = c->H;
-    P.f16_emulate = c->storage == MT_STORAGE_F16_EMULATE;
+    P.storage = (int)c->storage;
+    P.ldr = fuse_tonemap ? c->ldr[c->cur] : nullptr;
+    P.seed = tonemap_seed(c);
     wait_pending_read(c, P.hdr);
+    if (fuse_tonemap) wait_pending_read(c, P.ldr);
     pass_begin(c, MT_PASS_GODRAYS);
     MT_CUDA(c, mt_launch_godrays(P, c->stream));
     pass_end(c, MT_PASS_GODRAYS);
+    if (fuse_tonemap) {  // mtLastPassMs(MT_PASS_TONEMAP) reads 0: its work is inside the god-ray pass
+        pass_begin(c, MT_PASS_TONEMAP);
+        pass_end(c, MT_PASS_TONEMAP);
+    }
     c->launches += 2;  // mask_decode_kernel + godrays_kernel
     return MT_OK;
+}
+MtStatus mtDispatchGodRays(MtContext* c)
+try {
+    if (!c) return MT_ERR_INVALID;
+    return godrays_dispatch(c, false);
 } MT_NOTHROW
 
 MtStatus mtDispatchToneMap(MtContext* c)
@@ -712,11 +732,11 @@ try {
     if (!c->haveTime) return fail(c, MT_ERR_NOT_READY, "tone-map dispatch: time uniform not set");
     MT_CUDA(c, cudaSetDevice(c->device));
     ToneMapParams P;
+    P.storage = (int)c->storage;
     P.hdr = c->hdr[c->cur];
     P.ldr = c->ldr[c->cur];
     P.W = c->W; P.H = c->H;
-    float ty = c->tm.time[1];  // uint(time.y): truncate, saturate, NaN -> 0
-    P.seed = (ty != ty || ty <= 0.0f) ? 0u : (ty >= 4294967296.0f ? 0xffffffffu : (unsigned)ty);
+    P.seed = tonemap_seed(c);
     wait_pending_read(c, P.ldr);
     pass_begin(c, MT_PASS_TONEMAP);
     MT_CUDA(c, mt_launch_tonemap(P, c->stream));
@@ -766,8 +786,9 @@ try {
     MtStatus st;
     if ((st = reproject_dispatch(c, false)) != MT_OK) return st;
     if ((st = cloud_dispatch(c, 0, nullptr, false)) != MT_OK) return st;
-    if ((passes & MT_FRAME_GODRAYS) && (st = mtDispatchGodRays(c)) != MT_OK) return st;
-    if ((passes & MT_FRAME_TONEMAP) && (st = mtDispatchToneMap(c)) != MT_OK) return st;
+    const bool fused = (passes & MT_FRAME_GODRAYS) && (passes & MT_FRAME_TONEMAP) && !(c->flags & MT_FLAG_NO_FUSED_TONEMAP);
+    if ((passes & MT_FRAME_GODRAYS) && (st = godrays_dispatch(c, fused)) != MT_OK) return st;
+    if ((passes & MT_FRAME_TONEMAP) && !fused && (st = mtDispatchToneMap(c)) != MT_OK) return st;
     if ((passes & MT_FRAME_TXAA) && (st = mtDispatchTXAA(c)) != MT_OK) return st;
     return mtSwapPingPong(c);
 } MT_NOTHROW
@@ -806,7 +827,7 @@ try {
     if (!c) return MT_ERR_INVALID;
     MT_REQUIRE(c, (int)which >= 0 && (int)which <= MT_IMAGE_LDR_PREV && host != nullptr, "mtReadImageRows: bad arguments");
     MT_REQUIRE(c, row_begin <= row_end && row_end <= (uint32_t)c->H, "mtReadImageRows: bad row range");
-    size_t pitch = (size_t)c->W * ((which == MT_IMAGE_LDR || which == MT_IMAGE_LDR_PREV) ? 4 : 16);
+    size_t pitch = (size_t)c->W * pixel_bytes(c, which);
     size_t need = pitch * (row_end - row_begin);
     MT_REQUIRE(c, bytes >= need, "mtReadImageRows: host buffer too small");
     MT_CUDA(c, cudaSetDevice(c->device));
@@ -888,9 +909,10 @@ try {
     for (auto& p : c->pending)
         if (p.active) wait_pending_read(c, p.dev);
     size_t px = (size_t)c->W * c->H;
-    MT_CUDA(c, cudaMemsetAsync(c->hdr[0], 0, px * 16, c->stream));
-    MT_CUDA(c, cudaMemsetAsync(c->hdr[1], 0, px * 16, c->stream));
-    MT_CUDA(c, cudaMemsetAsync(c->mask, 0, px * 16, c->stream));
+    const size_t hb = hdr_pixel_bytes(c->storage);
+    MT_CUDA(c, cudaMemsetAsync(c->hdr[0], 0, px * hb, c->stream));
+    MT_CUDA(c, cudaMemsetAsync(c->hdr[1], 0, px * hb, c->stream));
+    MT_CUDA(c, cudaMemsetAsync(c->mask, 0, px * hb, c->stream));
     MT_CUDA(c, cudaMemsetAsync(c->ldr[0], 0, px * 4, c->stream));
     MT_CUDA(c, cudaMemsetAsync(c->ldr[1], 0, px * 4, c->stream));
     MT_CUDA(c, cudaMemsetAsync(c->ldrScratch, 0, px * 4, c->stream));
@@ -920,6 +942,7 @@ MtStatus mtSetCloudForward(MtContext* c, void* peer_hdr)
 try {
     if (!c) return MT_ERR_INVALID;
     MT_CUDA(c, cudaSetDevice(c->device));
+    MT_REQUIRE(c, !peer_hdr || c->storage != MT_STORAGE_F16 || (c->W % 2) == 0, "mtSetCloudForward: RGBA16F rows must be a multiple of 16 bytes (even width)");
     if (peer_hdr && !c->fwdStream) {
         int lo = 0, hi = 0;
         MT_CUDA(c, cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -971,7 +994,7 @@ try {
     MT_REQUIRE(c, peer != nullptr && (int)which >= 0 && (int)which <= MT_IMAGE_LDR_PREV, "mtCopyTilesToPeer: bad arguments");
     MT_REQUIRE(c, tile_rows >= 1 && tile_stride >= 1, "mtCopyTilesToPeer: bad tiling");
     MT_CUDA(c, cudaSetDevice(c->device));
-    const size_t pitch = (size_t)c->W * ((which == MT_IMAGE_LDR || which == MT_IMAGE_LDR_PREV) ? 4 : 16);
+    const size_t pitch = (size_t)c->W * pixel_bytes(c, which);
     const char* src = (const char*)image_ptr(c, which);
     const uint32_t ntiles = ((uint32_t)c->H + tile_rows - 1) / tile_rows;
     if (tile_end > ntiles) tile_end = ntiles;

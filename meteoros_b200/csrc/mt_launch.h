@@ -7,7 +7,7 @@
 
 cudaError_t mt_launch_cloud_setup(const CloudParams& P, MarchConst* out, cudaStream_t stream);
 cudaError_t mt_launch_cloud(const CloudParams& P, cudaStream_t stream);
-cudaError_t mt_launch_tile_forward(const void* src, void* dst, int W, int H, const RowTiles& rows, unsigned* tileDone,
+cudaError_t mt_launch_tile_forward(const void* src, void* dst, int W, int H, int bytesPerPixel, const RowTiles& rows, unsigned* tileDone,
                                    int ctas, cudaStream_t stream);
 cudaError_t mt_launch_cloud_sixteenth_split(const CloudParams& P, cudaStream_t stream, int* launches);
 cudaError_t mt_launch_cloud_sixteenth_fused(const CloudParams& P, cudaStream_t stream);

@@ -70,10 +70,24 @@ struct RowTiles {  // which pixel rows this launch covers (multi-GPU row-tile sh
     int tile_begin;   // first tile owned
     int tile_stride;  // distance between owned tiles
     int tile_count;   // number of owned tiles
-    int heavy_first;  // launch order: the first `heavy_first` owned tiles (those above the horizon) are issued LAST-TO-FIRST, i.e.
-                      // from the horizon upwards -- most march steps first, zenith rows later, ocean rows at the very end -- so that
-                      // the kernel's tail is made of its cheapest CTAs (matters when a GPU renders 1/8 of a frame); 0 = top-down
+    int heavy_first;  // launch order (mt_tile_order): the first `heavy_first` owned tiles lie above the horizon and march; they are
+                      // issued from the horizon upwards -- most march steps first, zenith rows last -- so that the kernel's tail is
+                      // made of its cheapest marching CTAs (matters when a GPU renders 1/8 of a frame), and the remaining tiles
+                      // (sky band, ocean: ~100 instructions per CTA, but the same 32 bytes per pixel to store) are INTERLEAVED with
+                      // them one for one, so that their stores -- half of the frame's bytes -- spread over the whole kernel instead of
+                      // arriving as one burst at its end (a burst the NVLink gather of an 8-GPU frame then waits for); 0 = top-down
 };
+
+// j-th tile in launch order -> index among the owned tiles
+MT_DEVICE int mt_tile_order(const RowTiles& r, int j)
+{
+    const int m = r.heavy_first, l = r.tile_count - m;  // marching tiles, light tiles
+    if (m <= 0) return j;
+    const int pairs = m < l ? m : l;
+    if (j < 2 * pairs) return (j & 1) ? m + (j >> 1) : m - 1 - (j >> 1);
+    const int k = j - 2 * pairs;                       // what is left of the longer list
+    return m > l ? m - 1 - (pairs + k) : m + pairs + k;
+}
 
 struct CloudParams {
     CamU cam;
@@ -89,7 +103,7 @@ struct CloudParams {
     int W, H;
     int tx, ty;  // threads of the reference dispatch (Renderer.cpp:713-716)
     int full;    // 0: one id (tm.frameCountMod16) -- 1: all sixteen
-    int f16_emulate;
+    int storage;     // MtStorage of the HDR / mask images (mt_pixel.cuh)
     int bulkStore;   // full-quality kernel: HDR pixels leave through shared memory + cp.async.bulk (mtSetCloudStoreMode)
     RowTiles rows;
     unsigned long long* counters;  // 6 x u64 or null
@@ -110,7 +124,7 @@ struct ReprojParams {
     const F4* prev;
     F4* cur;
     int W, H;
-    int f16_emulate;
+    int storage;  // MtStorage of the HDR / mask images (mt_pixel.cuh)
     int* taps;  // debug: 10 per pixel, or null
 };
 
@@ -118,10 +132,14 @@ struct GodRayParams {
     CamU cam;
     float lightColor[3];
     const F4* mask;     // encoded god-ray mask (RGBA32F)
-    float* decoded;     // (W+2) x (H+2) floats: the mask decoded per texel, ringed by the sampler's border value
+    float2* decoded;    // (W+2) x (H+2) pairs (d(x, y), d(x+1, y)): the mask decoded per texel, ringed by the sampler's border value
+    const float2* tapRow0;  // decoded + (W+2) + 1 - MT_FLOOR_MAGIC_BITS: image texel (0, 0), biased for post_core.cuh's magic floor
+    const float2* tapRow1;  // ... one row further
     F4* hdr;
     int W, H;
-    int f16_emulate;
+    int storage;  // MtStorage of the HDR / mask images (mt_pixel.cuh)
+    uint32_t* ldr;      // non-null: the tone map is fused into this pass's store (mtFrameEx with both passes): packed RGBA8 out
+    unsigned seed;      //   uint(time.y) of the tone map's dither
 };
 
 struct TxaaParams {
@@ -134,6 +152,7 @@ struct TxaaParams {
 };
 
 struct ToneMapParams {
+    int storage;    // MtStorage of the HDR image (mt_pixel.cuh)
     const F4* hdr;
     uint32_t* ldr;  // packed RGBA8
     int W, H;

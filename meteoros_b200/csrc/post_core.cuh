@@ -106,27 +106,54 @@ MT_DEVICE float mask_texel_decode(F4 t)
 
 // extract32fFromRGBA8f (postProcess_GodRays.frag:39-43).  The shader filters the four ENCODED channels bilinearly and
 // then takes the dot product with 1/bitEnc; both steps are linear, so the kernel decodes each texel once
-// (mask_decode_kernel, 16 B read -> 4 B written per pixel) and filters the decoded scalar: 16 instead of 64 bytes
-// and 4 instead of 16 multiply-adds per tap, 100 taps per pixel.  The two orders agree to rounding (~1e-7 relative on
-// a term that is itself <= 2.5 % of the pixel); no decision depends on it.  `dec` is the (W+2) x (H+2) decoded image
-// whose one-texel ring holds the border value, so the taps need no bounds tests.
-MT_DEVICE float mask_decode(const float* dec, int W, int H, P2 st)
+// (mask_decode_kernel) and filters the decoded scalar: 100 taps per pixel.  The god-ray term is radiance only -- no decision
+// depends on it -- and at most 2.5 % of the pixel, so it is held to "equal to rounding" (tests: <= 2e-5 of the term), not to
+// bit-exactness; what is kept exact is the tap POSITION sequence (uv -= delta, 100 roundings, then * dim - 0.5 in two
+// roundings), because a tap position off by one ulp moves a tap by 1e-4 texel, which a high-contrast mask turns into 1e-4.
+// `dec` is the (W+2) x (H+2) decoded image whose one-texel ring holds the border value, so the taps need no bounds tests;
+// each element is the PAIR (d(x, y), d(x+1, y)), so a tap is two 8-byte loads.  Per tap (device): the floor of both
+// coordinates comes from ONE packed add in round-down mode against 1.5 * 2^23 (the integer lands in the low mantissa bits,
+// the float floor is the same value minus the constant) -- no F2I / I2F on the quarter-rate pipe; the filter is
+// a + ay (c - a) on both columns at once, then in x: ~19 instructions per tap instead of 31 (profiles/r2_passes_1080p.md).
+#define MT_FLOOR_MAGIC 12582912.0f     /* 1.5 * 2^23: x + MAGIC rounded down = MAGIC + floor(x) for |x| < 2^22 */
+#define MT_FLOOR_MAGIC_BITS 0x4B400000
+MT_DEVICE float mask_decode(const GodRayParams& P, P2 st)
 {
+    const float2* dec = P.decoded;
+    const int W = P.W, H = P.H;
     const P2 m = mul2(st, pk2((float)W, (float)H));
     const float ux = lo2(m) - 0.5f, uy = hi2(m) - 0.5f;  // scalar: mul2 -> sub2 would be contracted (mt_math.cuh)
-    const int x0 = mt_floor2i(ux), y0 = mt_floor2i(uy);
-    const P2 a1 = sub2(pk2(ux, uy), pk2((float)x0, (float)y0));  // (ax, ay)
-    const P2 a0 = sub2(bc2(1.0f), a1);                  // (1-ax, 1-ay)
     // No clamp: the march runs from the pixel centre towards the sun position, which main() clamps to [0,1]
     // (postProcess_GodRays.frag:90), so u*W - 0.5 lies in [-0.5, W - 0.5] and floor() in [-1, W-1] -- the ring.  The 100
     // roundings of `uv -= delta` move u*W by < 0.05 texel even at W = 7680, against a margin of 0.5.
     const int pitch = W + 2;
-    const float* __restrict__ texel00 = dec + pitch + 1;          // loop invariant: image texel (0, 0) inside the ring
-    const int i0 = y0 * pitch + x0, i1 = i0 + pitch;              // signed 32-bit offsets (>= -pitch - 1): one IMAD.WIDE per row
-    float a = MT_LDG(texel00 + i0), b = MT_LDG(texel00 + i0 + 1), c = MT_LDG(texel00 + i1), d = MT_LDG(texel00 + i1 + 1);
-    const float ax = lo2(a1), ay = hi2(a1), bx = lo2(a0), by = hi2(a0);
-    float w00 = bx * by, w01 = ax * by, w10 = bx * ay, w11 = ax * ay;
-    return fmaf(w11, d, fmaf(w10, c, fmaf(w01, b, w00 * a)));
+#if defined(MT_HOSTSIM)
+    const float fx = floorf(ux), fy = floorf(uy);
+    const int x0 = (int)fx, y0 = (int)fy;
+    const P2 fl = pk2(fx, fy);
+    const float2* texel00 = dec + pitch + 1;                      // image texel (0, 0) inside the ring
+    const int i0 = y0 * pitch + x0;
+#else
+    P2 t;
+    asm("add.rm.f32x2 %0, %1, %2;" : "=l"(t) : "l"(pk2(ux, uy)), "l"(bc2(MT_FLOOR_MAGIC)));
+    const P2 fl = sub2(t, bc2(MT_FLOOR_MAGIC));                   // exact
+    const int xb = (int)(unsigned)t, y0 = (int)(unsigned)(t >> 32) - MT_FLOOR_MAGIC_BITS;
+    // the host passes the two row bases (image texel (0, 0) and (0, 1) inside the ring, the x bias of the magic constant
+    // folded in): two opaque loop-invariant pointers, one IMAD.WIDE per load instead of 64-bit pointer arithmetic
+    (void)dec;
+    const float2* texel00 = P.tapRow0;
+    const int i0 = y0 * pitch + xb;                               // < 2^31: xb <= 0x4B400000 + W, y0 * pitch <= 33e6 at 8K
+#endif
+    const P2 a1 = sub2(pk2(ux, uy), fl);                          // (ax, ay)
+#if defined(MT_HOSTSIM)
+    const float2* row1 = texel00 + pitch;
+#else
+    const float2* row1 = P.tapRow1;
+#endif
+    const float2 top = MT_LDG(texel00 + i0), bot = MT_LDG(row1 + i0);
+    const P2 t2 = pk2(top.x, top.y), b2 = pk2(bot.x, bot.y);      // the pairs as loaded: (x0, x0+1) of each row
+    const P2 lr = fma2(bc2(hi2(a1)), sub2(b2, t2), t2);           // both columns filtered in y: a + ay (c - a)
+    return fmaf(lo2(a1), hi2(lr) - lo2(lr), lo2(lr));             // then in x
 }
 
 // The radial accumulation of one fragment; returns the colour to ADD to the HDR pixel (already * blend).
@@ -142,8 +169,9 @@ MT_DEVICE F4 godray_pixel(const GodRayParams& P, const GodRayFrame& G, int x, in
     // per tap instead of seven instructions; the reordering moves the result by ~1e-7 of a term that is at most 2.5 %
     // of the pixel (radiance only, no decision depends on it).
     float sum = 0.0f;
+#pragma unroll 4
     for (int i = 0; i < 100; ++i) {
-        sum += mask_decode(P.decoded, P.W, P.H, uv);
+        sum += mask_decode(P, uv);
         uv = sub2(uv, duv);
     }
     F4 o;

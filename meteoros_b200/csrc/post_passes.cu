@@ -6,13 +6,8 @@
 #include <cuda_runtime.h>
 
 #include "mt_launch.h"
+#include "mt_pixel.cuh"
 #include "post_core.cuh"
-
-__device__ __forceinline__ float f16_round(float x) { return __half2float(__float2half_rn(x)); }
-__device__ __forceinline__ float4 f16_round4(float4 v)
-{
-    return make_float4(f16_round(v.x), f16_round(v.y), f16_round(v.z), f16_round(v.w));
-}
 
 // ---- Reprojection: 32x8 pixels per CTA, a warp is one 32-pixel row segment (512 contiguous bytes per access) -----
 // Instruction-issue bound, not HBM bound: every pixel casts a ray, intersects the inner shell, normalises twice, takes
@@ -32,40 +27,42 @@ __global__ void __launch_bounds__(256) reproject_kernel(const __grid_constant__ 
     if (x >= P.W || y >= P.H) return;
     int taps[10];
     reproject_taps(P, frame, su[threadIdx.x & 31], sv[threadIdx.x >> 5], taps);
-    const float4* prev = reinterpret_cast<const float4*>(P.prev);
     P2 axy = pk2(0.0f, 0.0f), azw = pk2(0.0f, 0.0f);
 #pragma unroll
     for (int i = 0; i < 10; ++i) {
-        const float4 t = __ldg(prev + taps[i]);
+        const float4 t = px_load_ro(P.prev, (size_t)taps[i], P.storage);
         axy = add2(axy, pk2(t.x, t.y));
         azw = add2(azw, pk2(t.z, t.w));
     }
     axy = MT_DIV_CONST2(axy, 10.0f);
     azw = MT_DIV_CONST2(azw, 10.0f);
-    float4 acc = make_float4(lo2(axy), hi2(axy), lo2(azw), hi2(azw));
-    if (P.f16_emulate) acc = f16_round4(acc);
+    const float4 acc = make_float4(lo2(axy), hi2(axy), lo2(azw), hi2(azw));
     const size_t idx = (size_t)y * P.W + x;
-    reinterpret_cast<float4*>(P.cur)[idx] = acc;
+    px_store(P.cur, idx, acc, P.storage);
     if (P.taps) {
 #pragma unroll
         for (int i = 0; i < 10; ++i) P.taps[idx * 10 + i] = taps[i];
     }
 }
 
-// ---- God-ray mask decode: (W+2) x (H+2) scalar image, ring = border value.  16 B in, 4 B out per pixel. ----------------
+// ---- God-ray mask decode: (W+2) x (H+2) image of pairs (d(x, y), d(x+1, y)), ring = border value.  16 B in, 8 B out per pixel.
+__device__ __forceinline__ float mask_decoded_at(const GodRayParams& P, int x, int y)
+{
+    if (x < 0 || y < 0 || x >= P.W || y >= P.H) return MT_MASK_BORDER_DECODED;
+    const float4 v = px_load_ro(P.mask, (size_t)y * P.W + x, P.storage);
+    F4 t;
+    t.x = v.x; t.y = v.y; t.z = v.z; t.w = v.w;
+    return mask_texel_decode(t);
+}
 __global__ void __launch_bounds__(256) mask_decode_kernel(const __grid_constant__ GodRayParams P)
 {
     const int x = blockIdx.x * 32 + (threadIdx.x & 31) - 1;  // -1 .. W
     const int y = blockIdx.y * 8 + (threadIdx.x >> 5) - 1;   // -1 .. H
+    const float d = mask_decoded_at(P, x, y);                // outside the image (and outside the ring): the border value
+    float dn = __shfl_down_sync(0xffffffffu, d, 1);          // the right-hand neighbour is the next lane's texel ...
+    if ((threadIdx.x & 31) == 31) dn = mask_decoded_at(P, x + 1, y);  // ... except at the end of the warp's row segment
     if (x > P.W || y > P.H) return;
-    float d = MT_MASK_BORDER_DECODED;
-    if (x >= 0 && y >= 0 && x < P.W && y < P.H) {
-        float4 v = __ldg(reinterpret_cast<const float4*>(P.mask) + ((size_t)y * P.W + x));
-        F4 t;
-        t.x = v.x; t.y = v.y; t.z = v.z; t.w = v.w;
-        d = mask_texel_decode(t);
-    }
-    P.decoded[(size_t)(y + 1) * (size_t)(P.W + 2) + (size_t)(x + 1)] = d;
+    P.decoded[(size_t)(y + 1) * (size_t)(P.W + 2) + (size_t)(x + 1)] = make_float2(d, dn);
 }
 
 // ---- God rays: 100 bilinear taps per pixel on the decoded scalar image; the kernel is bound by L1 wavefronts and issue
@@ -83,18 +80,28 @@ __global__ void __launch_bounds__(128) godrays_kernel(const __grid_constant__ Go
     __shared__ GodRayFrame frame;
     if (threadIdx.x == 0) frame = godray_frame(P.cam);
     __syncthreads();
-    if (frame.blend < 0.0f) return;  // sun behind the camera: the fragment shader returns before any store
+    const bool lit = !(frame.blend < 0.0f);  // sun behind the camera: the fragment shader returns before any store
+    if (!lit && !P.ldr) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wx = MT_GODRAY_LOG2W == 5 ? 0 : (warp & 1), wy = MT_GODRAY_LOG2W == 5 ? warp : (warp >> 1);
     const int x = blockIdx.x * MT_GODRAY_CTA_W + wx * MT_GODRAY_WW + (lane & (MT_GODRAY_WW - 1));
     const int y = blockIdx.y * MT_GODRAY_CTA_H + wy * MT_GODRAY_WH + (lane >> MT_GODRAY_LOG2W);
     if (x >= P.W || y >= P.H) return;
-    F4 g = godray_pixel(P, frame, x, y);
-    float4* px = reinterpret_cast<float4*>(P.hdr) + ((size_t)y * P.W + x);
-    float4 c = *px;
-    c.x += g.x; c.y += g.y; c.z += g.z; c.w += g.w;
-    if (P.f16_emulate) c = f16_round4(c);
-    *px = c;
+    const size_t idx = (size_t)y * P.W + x;
+    float4 c = px_load(P.hdr, idx, P.storage);
+    if (lit) {
+        F4 g = godray_pixel(P, frame, x, y);
+        c.x += g.x; c.y += g.y; c.z += g.z; c.w += g.w;
+        if (P.storage != MT_PX_F32) c = px_round_f16(c);  // the tone map below reads the stored value
+        px_store(P.hdr, idx, c, P.storage);
+    }
+    if (P.ldr) {  // fused tone map (uniform): the finished pixel is in registers -- no second 16-byte read of the image
+        ToneMapParams T;
+        T.storage = P.storage; T.hdr = nullptr; T.ldr = P.ldr; T.W = P.W; T.H = P.H; T.seed = P.seed;
+        F4 in;
+        in.x = c.x; in.y = c.y; in.z = c.z; in.w = c.w;
+        P.ldr[idx] = tonemap_pixel(T, in, x, y);
+    }
 }
 
 // ---- Tone map: one pixel per thread, 16 B in / 4 B out ------------------------------------------------------------
@@ -104,7 +111,7 @@ __global__ void __launch_bounds__(256) tonemap_kernel(const __grid_constant__ To
     const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
     if (x >= P.W || y >= P.H) return;
     const size_t idx = (size_t)y * P.W + x;
-    float4 v = __ldg(reinterpret_cast<const float4*>(P.hdr) + idx);
+    const float4 v = px_load_ro(P.hdr, idx, P.storage);
     F4 in;
     in.x = v.x; in.y = v.y; in.z = v.z; in.w = v.w;
     P.ldr[idx] = tonemap_pixel(P, in, x, y);
@@ -137,8 +144,13 @@ cudaError_t mt_launch_reproject(const ReprojParams& P, cudaStream_t stream)
     reproject_kernel<<<grid, 256, 0, stream>>>(P);
     return cudaGetLastError();
 }
-cudaError_t mt_launch_godrays(const GodRayParams& P, cudaStream_t stream)
+cudaError_t mt_launch_godrays(const GodRayParams& P0, cudaStream_t stream)
 {
+    GodRayParams P = P0;
+    // biased row bases of the tap loads (post_core.cuh, mask_decode): never dereferenced without the index added back
+    P.tapRow0 = reinterpret_cast<const float2*>(reinterpret_cast<uintptr_t>(P.decoded) +
+                                                ((intptr_t)(P.W + 2) + 1 - (intptr_t)MT_FLOOR_MAGIC_BITS) * (intptr_t)sizeof(float2));
+    P.tapRow1 = reinterpret_cast<const float2*>(reinterpret_cast<uintptr_t>(P.tapRow0) + (intptr_t)(P.W + 2) * (intptr_t)sizeof(float2));
     dim3 dgrid((unsigned)((P.W + 2 + 31) / 32), (unsigned)((P.H + 2 + 7) / 8), 1);
     mask_decode_kernel<<<dgrid, 256, 0, stream>>>(P);
     cudaError_t e = cudaGetLastError();

@@ -163,9 +163,16 @@ int hs_godrays(const MtCameraUBO* cam, const float* lightColor, int W, int H, co
     P.lightColor[0] = lightColor[0]; P.lightColor[1] = lightColor[1]; P.lightColor[2] = lightColor[2];
     P.mask = (const F4*)mask;
     P.W = W; P.H = H;
-    std::vector<float> dec((size_t)(W + 2) * (H + 2), MT_MASK_BORDER_DECODED);
+    std::vector<float> dec1((size_t)(W + 2) * (H + 2), MT_MASK_BORDER_DECODED);
     for (int y = 0; y < H; ++y)
-        for (int x = 0; x < W; ++x) dec[(size_t)(y + 1) * (W + 2) + (x + 1)] = mask_texel_decode(P.mask[(size_t)y * W + x]);
+        for (int x = 0; x < W; ++x) dec1[(size_t)(y + 1) * (W + 2) + (x + 1)] = mask_texel_decode(P.mask[(size_t)y * W + x]);
+    std::vector<float2> dec((size_t)(W + 2) * (H + 2));   // pairs (d(x, y), d(x+1, y)), as mask_decode_kernel writes them
+    for (int y = 0; y < H + 2; ++y)
+        for (int x = 0; x < W + 2; ++x) {
+            const size_t i = (size_t)y * (W + 2) + x;
+            dec[i].x = dec1[i];
+            dec[i].y = x + 1 < W + 2 ? dec1[i + 1] : MT_MASK_BORDER_DECODED;
+        }
     P.decoded = dec.data();
     GodRayFrame G = godray_frame(P.cam);
     if (G.blend < 0.0f) return 0;
@@ -181,6 +188,7 @@ int hs_godrays(const MtCameraUBO* cam, const float* lightColor, int W, int H, co
 int hs_tonemap(const MtTimeUBO* tm, int W, int H, const float* hdr, uint32_t* ldr)
 {
     ToneMapParams P;
+    P.storage = 0;
     P.hdr = (const F4*)hdr;
     P.ldr = ldr;
     P.W = W; P.H = H;

@@ -600,6 +600,64 @@ def test_f16_storage_emulation(api, oracle_mod, noise):
     assert rel_err(hdr[finite], want[finite]).max() <= 2e-3               # at most one binary16 ulp apart
 
 
+def test_f16_storage(api, oracle_mod, noise):
+    """MT_STORAGE_F16: the HDR / mask images are RGBA16F in memory (the reference's VK_FORMAT_R16G16B16A16_SFLOAT,
+    Renderer.cpp:1431-1440), 8 bytes per pixel through every pass, over mtRead/WriteImage, the bulk-store epilogue and the
+    tile forwarder.  Bars: (1) the same values as MT_STORAGE_F16_EMULATE, bit for bit, through a 6-frame sequence of all
+    passes; (2) the Cloud pass within one binary16 ulp of the oracle's frame rounded to binary16, mask likewise."""
+    from meteoros_b200 import scene
+
+    w, h = 320, 184
+    cam, sc, sky = scene.Camera(w, h), scene.Scene(), scene.Sky()
+    frames = {}
+    for storage in (api.STORAGE_F16_EMULATE, api.STORAGE_F16):
+        cam, sc = scene.Camera(w, h), scene.Scene()
+        out = []
+        with make_renderer(api, noise, w, h, storage=storage) as r:
+            assert r.read_image(api.IMAGE_CLOUD_CUR).nbytes == w * h * (8 if storage == api.STORAGE_F16 else 16)
+            r.set_sun_and_sky(sky.ubo())
+            old = cam.ubo()
+            for f in range(6):
+                cam.rotate_about_up(0.25)
+                sc.update_time(1 / 60)
+                r.set_camera(cam.ubo()); r.set_camera_old(old); r.set_time(sc.ubo())
+                r.frame(with_godrays=True, with_txaa=True)
+                old = cam.ubo()
+                out.append((r.read_image(api.IMAGE_CLOUD_PREV).astype(np.float32), r.read_image(api.IMAGE_GODRAY_MASK).astype(np.float32),
+                            r.read_image(api.IMAGE_LDR_PREV)))
+            # full-quality dispatch: direct stores, the bulk-store epilogue, and the forwarder into a second context's image
+            r.dispatch_cloud_full()
+            full = r.read_image(api.IMAGE_CLOUD_CUR)
+            r.set_cloud_store_mode(api.STORE_BULK)
+            r.clear_images()
+            r.dispatch_cloud_full()
+            assert np.array_equal(r.read_image(api.IMAGE_CLOUD_CUR), full)
+            r.set_cloud_store_mode(api.STORE_DIRECT)
+            with make_renderer(api, noise, w, h, storage=storage) as peer:
+                r.set_cloud_forward(peer.image_device_ptr(api.IMAGE_CLOUD_CUR))
+                r.dispatch_cloud_tiles(8, 0, (h + 7) // 8, 1)
+                r.join_copies(); r.synchronize()
+                assert np.array_equal(peer.read_image(api.IMAGE_CLOUD_CUR), full)
+                r.set_cloud_forward(None)
+            out.append((full.astype(np.float32),))
+        frames[storage] = out
+    for a, b in zip(frames[api.STORAGE_F16_EMULATE], frames[api.STORAGE_F16]):
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+    # against the oracle: its Cloud frame rounded to binary16, at most one binary16 ulp (2^-10 relative) apart
+    tun = scene.default_tuning()
+    ref = oracle_mod.cloud(cam.ubo(), sc.ubo(), tun, noise, w, h, full=True)
+    with make_renderer(api, noise, w, h, storage=api.STORAGE_F16) as r:
+        r.set_camera(cam.ubo()); r.set_time(sc.ubo())
+        r.dispatch_cloud_full()
+        hdr, mask = r.read_image(api.IMAGE_CLOUD_CUR), r.read_image(api.IMAGE_GODRAY_MASK)
+    assert hdr.dtype == np.float16
+    want = ref["hdr"].astype(np.float16).astype(np.float32)
+    assert rel_err(hdr.astype(np.float32), want).max() <= 2.0 ** -10
+    assert (hdr.astype(np.float32) != want).mean() < 1e-3          # in fact equal except where the fp32 values straddle a tie
+    assert np.array_equal(mask, ref["mask"].astype(np.float16))      # the mask is bit-exact before rounding, hence after
+
+
 def test_async_readback_overlaps_next_frame(api, noise):
     """mtReadImageAsync: frame k is copied out on the copy stream while frame k+1 renders into the other ping-pong
     image; a third frame that re-uses the first image must wait for its copy."""
