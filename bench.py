@@ -239,14 +239,15 @@ def run_reference(args, rank, world):
     emit(line)  # the process's real stdout (quiet_stdout rerouted fd 1 to stderr for library chatter)
 
 
-def sharded_8k_record(args, api, sharding, torch, dist, world, rank, local_rank, noise, steps):
+def sharded_8k_record(args, api, sharding, torch, dist, world, rank, local_rank, noise, steps, storage=None):
     """BASELINE config 4 beside the N>1 views line: ONE 7680x4320 full-quality frame cut into cyclic row tiles over the
     ranks and gathered on GPU 0 over NVLink, timed like the headline (events on each rank's stream, L2 flushed, max over
     ranks) against the same frame on rank 0 alone, measured in the same run; the gathered frame is compared bit for bit
     with the single-GPU frame.  Returns the record on rank 0 (None elsewhere)."""
     w, h = 7680, 4320
+    storage = args.storage if storage is None else storage
     cam, tm, sky, tun = scene_for_view(0, w, h)
-    r8 = api.CloudRenderer(w, h, device=local_rank, storage=args.storage)
+    r8 = api.CloudRenderer(w, h, device=local_rank, storage=storage)
     r8.upload_noise(noise)
     r8.set_camera(cam); r8.set_camera_old(cam); r8.set_time(tm); r8.set_sun_and_sky(sky); r8.set_tuning(tun)
 
@@ -302,7 +303,9 @@ def sharded_8k_record(args, api, sharding, torch, dist, world, rank, local_rank,
             "ms_per_frame": round(frame_ms, 4), "single_gpu_ms": round(single_ms, 4), "speedup": round(single_ms / frame_ms, 3),
             "mrays_per_s": round(w * h / (frame_ms * 1e-3) / 1e6, 1), "rank_ms": [round(float(x[0]), 4) for x in per_rank],
             "gather": args.gather, "gather_mask": bool(args.gather_mask), "tile_rows": args.tile_rows, "steps": steps, "scaling": "strong",
-            "bit_identical_to_single_gpu": bool(np.array_equal(got, ref_frame)), "storage": "f16" if args.storage else "f32", "clocks": clocks,
+            "bit_identical_to_single_gpu": bool(np.array_equal(got, ref_frame)),
+            "storage": {0: "RGBA32F", 1: "RGBA32F holding binary16 values", 2: "RGBA16F (the reference's own image format, Renderer.cpp:1431-1440)"}[storage],
+            "gathered_bytes": int(w * h * (8 if storage == 2 else 16) * (world - 1) // world), "clocks": clocks,
         }
     shard.close()
     r8.close()
@@ -621,8 +624,10 @@ def main():
 
     if world > 1 and args.workload == "cloud4k" and not args.no_sharded_8k:
         rec = sharded_8k_record(args, api, sharding, torch, dist, world, rank, local_rank, noise, steps=max(args.steps, 10))
+        rec16 = sharded_8k_record(args, api, sharding, torch, dist, world, rank, local_rank, noise, steps=max(args.steps, 10), storage=2) if args.storage != 2 else None
         if rank == 0:
             line["sharded_8k"] = rec
+            line["sharded_8k_f16"] = rec16
 
     if rank == 0 and line.get("roofline"):
         # cross-check of the probe: SMs x 128 FP32 lanes x 2 flop x the SM clock observed under load

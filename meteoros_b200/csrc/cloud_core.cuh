@@ -253,7 +253,28 @@ struct StepSample {
     float energy;  // GetLightEnergy(...)    (mixed into the transmittance); < 0 marks "baseDensity <= 0"
 };
 
+// The ray direction of castRay for pixel (px, py) -- the first lines of cloud_ray_setup, for callers that need the
+// direction (and from it the background) without the rest.
+MT_DEVICE f3 cloud_ray_dir(const CloudParams& P, const MarchConst& M, int px, int py, int pixelID)
+{
+    float u = (float)px / (float)P.W;
+    float v = 1.0f - (float)py / (float)P.H;
+    const float jx = M.rayJitter[pixelID >> 1][0], jy = M.rayJitter[pixelID >> 1][1];
+    RayBasis B;
+    B.right = M.basisRight; B.up = M.basisUp; B.look = M.basisLook;
+    return cast_ray_dir(P.cam, B, M.eyePos, u, v, jx, jy);
+}
+// background of a ray that is not ocean: Preetham sky * max(.62, dir.y) (cloudRayMarch.comp:731-733)
+MT_DEVICE f3 cloud_ray_background(const CloudParams& P, f3 dir)
+{
+    const float dotUp = (0.0f * dir.x + 1.0f * dir.y) + 0.0f * dir.z;
+    return sky_color(P.sky, dir) * fmaxf(0.620f, dotUp);
+}
+
 // castRay + branches (cloudRayMarch.comp:690-753).  For branch 0/1 `hdr` is final; mask is zero.
+// WITH_BG = false leaves the background (R.bg, and hdr of a sky-band pixel) to the caller: the fused 1-of-16 kernel
+// evaluates the Preetham sky in a second warp beside the geometry.
+template <bool WITH_BG = true>
 MT_DEVICE RaySetup cloud_ray_setup(const CloudParams& P, const MarchConst& M, int px, int py, int pixelID, F4& hdr)
 {
     RaySetup R;
@@ -279,7 +300,7 @@ MT_DEVICE RaySetup cloud_ray_setup(const CloudParams& P, const MarchConst& M, in
         R.branch = 0;
         return R;
     }
-    R.bg = sky_color(P.sky, dir) * fmaxf(0.620f, dotUp);
+    if (WITH_BG) R.bg = sky_color(P.sky, dir) * fmaxf(0.620f, dotUp);
     if (dotUp < 0.06f) {  // sky band below the cloud fade-out (:730-740)
         hdr.x = R.bg.x; hdr.y = R.bg.y; hdr.z = R.bg.z;
         R.branch = 1;
@@ -473,6 +494,20 @@ MT_DEVICE StepSample cloud_step_light(const CloudParams& P, const MarchConst& M,
             LinAxis X, Y, Z;
             unsigned cell;
             float cur;
+#if MT_HW_FILTER && !defined(MT_HOSTSIM)
+            if (STD && !WEATHER) {  // A/B: the texture unit filters the cone sample (profiles/r2_ab.md); same empty-cell test
+                cone_axes<STD>(P, M, CO, pos, relOrigin, R.stepSize, i, sxy, sz, X, Y, Z, cell);
+                const Tex3D low = std_low<STD>(P.low);
+                cur = 0.0f;
+                if (!low.occ || occ_cell_may_be_cloud(low, cell)) {
+                    const float4 n = tex3D<float4>((cudaTextureObject_t)P.low.hwtex, lo2(sxy), hi2(sxy), sz);
+                    const float fbm = sat1((n.y * 0.625f + n.z * 0.25f) + n.w * 0.125f);
+                    const float omin = fbm - 0.9f;
+                    const float base = sat1(div_nice(n.x - omin, 1.0f - omin));
+                    if (base > coverage) cur = sat1(div_nice_r(base - coverage, M.covDen, M.covRcp)) * coverage;
+                }
+            } else
+#endif
             if (STD && MT_CONE_RF && !WEATHER) {
                 cone_axes<STD>(P, M, CO, pos, relOrigin, R.stepSize, i, sxy, sz, X, Y, Z, cell);
                 const Tex3D low = std_low<STD>(P.low);

@@ -473,12 +473,15 @@ __global__ void __launch_bounds__(32 * MT_S16_WARPS, MT_S16_MINBLOCKS) cloud_six
     __shared__ RaySetup rays[32];
     __shared__ float tk[MT_STEP_SLICES][32];
     __shared__ float2 smp[MT_STEP_SLICES][32];
+    __shared__ f3 bgs[32];
     __shared__ int tileSteps;
     stage_march_const(M, P.mc);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // the CTA's ray tile: 8x4 rays of the (tx, ty) grid, tiles row-major
+    // the CTA's ray tile: 8x4 rays of the (tx, ty) grid; rows of tiles in mt_tile_order: the marching rows from the horizon
+    // upwards first, interleaved with the ocean rows -- the kernel is about two waves of CTAs, so what runs last decides its tail
     const int tilesX = P.tx >> 3;
-    const int tyi = (int)blockIdx.x / tilesX, txi = (int)blockIdx.x - tyi * tilesX;
+    const int jrow = (int)blockIdx.x / tilesX, txi = (int)blockIdx.x - jrow * tilesX;
+    const int tyi = mt_tile_order(P.rows, jrow);
     const int gx = txi * 8 + (lane & 7), gy = tyi * 4 + (lane >> 3);
     const int pixelID = P.tm.frameCountMod16;
     const int px = gx * 4 + (pixelID >> 2), py = gy * 4 + (pixelID & 3);
@@ -491,9 +494,9 @@ __global__ void __launch_bounds__(32 * MT_S16_WARPS, MT_S16_MINBLOCKS) cloud_six
         } else {
             F4 hdr, mask;
             mask.x = mask.y = mask.z = mask.w = 0.0f;
-            RaySetup R = cloud_ray_setup(P, M, px, py, pixelID, hdr);
-            if (R.branch != 2) store_pixel(P, (size_t)py * P.W + px, hdr, mask);  // ocean / sky band: final
-            else
+            RaySetup R = cloud_ray_setup<false>(P, M, px, py, pixelID, hdr);  // geometry only: the sky is warp 1's
+            if (R.branch == 0) store_pixel(P, (size_t)py * P.W + px, hdr, mask);  // ocean: final
+            else if (R.branch == 2)
                 for (float t = R.t_in; t < R.t_out && n < MT_STEP_SLICES; t += R.stepSize) tk[n++][lane] = t;
             R.nsteps = n;
             rays[lane] = R;
@@ -502,6 +505,20 @@ __global__ void __launch_bounds__(32 * MT_S16_WARPS, MT_S16_MINBLOCKS) cloud_six
         n = max(n, __shfl_xor_sync(0xffffffffu, n, 4));  n = max(n, __shfl_xor_sync(0xffffffffu, n, 2));
         n = max(n, __shfl_xor_sync(0xffffffffu, n, 1));
         if (lane == 0) tileSteps = n;
+    } else if (warp == 1 && valid) {  // ---- A, beside warp 0: the background (Preetham sky, a dozen pow / exp) of the same 32 rays
+        const f3 dir = cloud_ray_dir(P, M, px, py, pixelID);   // the same castRay: the same bits
+        const float dotUp = (0.0f * dir.x + 1.0f * dir.y) + 0.0f * dir.z;
+        if (!(dotUp < 0.0f)) {
+            const f3 bg = cloud_ray_background(P, dir);
+            if (dotUp < 0.06f) {  // sky band below the cloud fade-out: final (cloudRayMarch.comp:730-740)
+                F4 hdr, mask;
+                hdr.x = bg.x; hdr.y = bg.y; hdr.z = bg.z; hdr.w = 1.0f;
+                mask.x = mask.y = mask.z = mask.w = 0.0f;
+                store_pixel(P, (size_t)py * P.W + px, hdr, mask);
+            } else {
+                bgs[lane] = bg;
+            }
+        }
     }
     __syncthreads();
     const int nmax = tileSteps;
@@ -531,7 +548,9 @@ __global__ void __launch_bounds__(32 * MT_S16_WARPS, MT_S16_MINBLOCKS) cloud_six
             if (cloud_step_combine(S, accum, transmittance, color)) break;
         }
         F4 hdr, mask;
-        cloud_composite(R, accum, color, hdr, mask);
+        RaySetup Rc = R;
+        Rc.bg = bgs[lane];
+        cloud_composite(Rc, accum, color, hdr, mask);
         store_pixel(P, (size_t)py * P.W + px, hdr, mask);
     }
 }

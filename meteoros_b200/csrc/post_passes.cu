@@ -14,6 +14,8 @@
 // seven IEEE divisions and ten dependent-address taps (~350 instructions for 32 bytes of compulsory traffic).  What
 // does not depend on the pixel is computed once per CTA (frame constants, x/W for the CTA's 32 columns, y/H for its 8
 // rows); coordinates and the float4 accumulation run on fp32x2 pairs; the final /10 is the exact 3-instruction division.
+// ST = the storage format as a compile-time constant (mt_pixel.cuh): the per-load format test folds away
+template <int ST>
 __global__ void __launch_bounds__(256) reproject_kernel(const __grid_constant__ ReprojParams P)
 {
     __shared__ ReprojFrame frame;
@@ -30,7 +32,7 @@ __global__ void __launch_bounds__(256) reproject_kernel(const __grid_constant__ 
     P2 axy = pk2(0.0f, 0.0f), azw = pk2(0.0f, 0.0f);
 #pragma unroll
     for (int i = 0; i < 10; ++i) {
-        const float4 t = px_load_ro(P.prev, (size_t)taps[i], P.storage);
+        const float4 t = px_load_ro(P.prev, (size_t)taps[i], ST);
         axy = add2(axy, pk2(t.x, t.y));
         azw = add2(azw, pk2(t.z, t.w));
     }
@@ -38,7 +40,7 @@ __global__ void __launch_bounds__(256) reproject_kernel(const __grid_constant__ 
     azw = MT_DIV_CONST2(azw, 10.0f);
     const float4 acc = make_float4(lo2(axy), hi2(axy), lo2(azw), hi2(azw));
     const size_t idx = (size_t)y * P.W + x;
-    px_store(P.cur, idx, acc, P.storage);
+    px_store(P.cur, idx, acc, ST);
     if (P.taps) {
 #pragma unroll
         for (int i = 0; i < 10; ++i) P.taps[idx * 10 + i] = taps[i];
@@ -46,21 +48,23 @@ __global__ void __launch_bounds__(256) reproject_kernel(const __grid_constant__ 
 }
 
 // ---- God-ray mask decode: (W+2) x (H+2) image of pairs (d(x, y), d(x+1, y)), ring = border value.  16 B in, 8 B out per pixel.
+template <int ST>
 __device__ __forceinline__ float mask_decoded_at(const GodRayParams& P, int x, int y)
 {
     if (x < 0 || y < 0 || x >= P.W || y >= P.H) return MT_MASK_BORDER_DECODED;
-    const float4 v = px_load_ro(P.mask, (size_t)y * P.W + x, P.storage);
+    const float4 v = px_load_ro(P.mask, (size_t)y * P.W + x, ST);
     F4 t;
     t.x = v.x; t.y = v.y; t.z = v.z; t.w = v.w;
     return mask_texel_decode(t);
 }
+template <int ST>
 __global__ void __launch_bounds__(256) mask_decode_kernel(const __grid_constant__ GodRayParams P)
 {
     const int x = blockIdx.x * 32 + (threadIdx.x & 31) - 1;  // -1 .. W
     const int y = blockIdx.y * 8 + (threadIdx.x >> 5) - 1;   // -1 .. H
-    const float d = mask_decoded_at(P, x, y);                // outside the image (and outside the ring): the border value
+    const float d = mask_decoded_at<ST>(P, x, y);                // outside the image (and outside the ring): the border value
     float dn = __shfl_down_sync(0xffffffffu, d, 1);          // the right-hand neighbour is the next lane's texel ...
-    if ((threadIdx.x & 31) == 31) dn = mask_decoded_at(P, x + 1, y);  // ... except at the end of the warp's row segment
+    if ((threadIdx.x & 31) == 31) dn = mask_decoded_at<ST>(P, x + 1, y);  // ... except at the end of the warp's row segment
     if (x > P.W || y > P.H) return;
     P.decoded[(size_t)(y + 1) * (size_t)(P.W + 2) + (size_t)(x + 1)] = make_float2(d, dn);
 }
@@ -75,6 +79,7 @@ __global__ void __launch_bounds__(256) mask_decode_kernel(const __grid_constant_
 #define MT_GODRAY_WH (32 >> MT_GODRAY_LOG2W)
 #define MT_GODRAY_CTA_W (MT_GODRAY_LOG2W == 5 ? 32 : 2 * MT_GODRAY_WW)                  /* 16, 32, 32 */
 #define MT_GODRAY_CTA_H (MT_GODRAY_LOG2W == 5 ? 4 : 2 * MT_GODRAY_WH)                   /*  8,  4,  4 */
+template <int ST>
 __global__ void __launch_bounds__(128) godrays_kernel(const __grid_constant__ GodRayParams P)
 {
     __shared__ GodRayFrame frame;
@@ -88,12 +93,12 @@ __global__ void __launch_bounds__(128) godrays_kernel(const __grid_constant__ Go
     const int y = blockIdx.y * MT_GODRAY_CTA_H + wy * MT_GODRAY_WH + (lane >> MT_GODRAY_LOG2W);
     if (x >= P.W || y >= P.H) return;
     const size_t idx = (size_t)y * P.W + x;
-    float4 c = px_load(P.hdr, idx, P.storage);
+    float4 c = px_load(P.hdr, idx, ST);
     if (lit) {
         F4 g = godray_pixel(P, frame, x, y);
         c.x += g.x; c.y += g.y; c.z += g.z; c.w += g.w;
-        if (P.storage != MT_PX_F32) c = px_round_f16(c);  // the tone map below reads the stored value
-        px_store(P.hdr, idx, c, P.storage);
+        if (ST != MT_PX_F32) c = px_round_f16(c);  // the tone map below reads the stored value
+        px_store(P.hdr, idx, c, ST);
     }
     if (P.ldr) {  // fused tone map (uniform): the finished pixel is in registers -- no second 16-byte read of the image
         ToneMapParams T;
@@ -105,13 +110,14 @@ __global__ void __launch_bounds__(128) godrays_kernel(const __grid_constant__ Go
 }
 
 // ---- Tone map: one pixel per thread, 16 B in / 4 B out ------------------------------------------------------------
+template <int ST>
 __global__ void __launch_bounds__(256) tonemap_kernel(const __grid_constant__ ToneMapParams P)
 {
     const int x = blockIdx.x * 32 + (threadIdx.x & 31);
     const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
     if (x >= P.W || y >= P.H) return;
     const size_t idx = (size_t)y * P.W + x;
-    const float4 v = px_load_ro(P.hdr, idx, P.storage);
+    const float4 v = px_load_ro(P.hdr, idx, ST);
     F4 in;
     in.x = v.x; in.y = v.y; in.z = v.z; in.w = v.w;
     P.ldr[idx] = tonemap_pixel(P, in, x, y);
@@ -141,7 +147,9 @@ cudaError_t mt_launch_txaa(const TxaaParams& P, cudaStream_t stream)
 cudaError_t mt_launch_reproject(const ReprojParams& P, cudaStream_t stream)
 {
     dim3 grid((unsigned)((P.W + 31) / 32), (unsigned)((P.H + 7) / 8), 1);
-    reproject_kernel<<<grid, 256, 0, stream>>>(P);
+    if (P.storage == MT_PX_F16) reproject_kernel<MT_PX_F16><<<grid, 256, 0, stream>>>(P);
+    else if (P.storage == MT_PX_F16_EMULATE) reproject_kernel<MT_PX_F16_EMULATE><<<grid, 256, 0, stream>>>(P);
+    else reproject_kernel<MT_PX_F32><<<grid, 256, 0, stream>>>(P);
     return cudaGetLastError();
 }
 cudaError_t mt_launch_godrays(const GodRayParams& P0, cudaStream_t stream)
@@ -152,17 +160,21 @@ cudaError_t mt_launch_godrays(const GodRayParams& P0, cudaStream_t stream)
                                                 ((intptr_t)(P.W + 2) + 1 - (intptr_t)MT_FLOOR_MAGIC_BITS) * (intptr_t)sizeof(float2));
     P.tapRow1 = reinterpret_cast<const float2*>(reinterpret_cast<uintptr_t>(P.tapRow0) + (intptr_t)(P.W + 2) * (intptr_t)sizeof(float2));
     dim3 dgrid((unsigned)((P.W + 2 + 31) / 32), (unsigned)((P.H + 2 + 7) / 8), 1);
-    mask_decode_kernel<<<dgrid, 256, 0, stream>>>(P);
+    if (P.storage == MT_PX_F16) mask_decode_kernel<MT_PX_F16><<<dgrid, 256, 0, stream>>>(P);
+    else mask_decode_kernel<MT_PX_F32><<<dgrid, 256, 0, stream>>>(P);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     dim3 grid((unsigned)((P.W + MT_GODRAY_CTA_W - 1) / MT_GODRAY_CTA_W), (unsigned)((P.H + MT_GODRAY_CTA_H - 1) / MT_GODRAY_CTA_H), 1);
-    godrays_kernel<<<grid, 128, 0, stream>>>(P);
+    if (P.storage == MT_PX_F16) godrays_kernel<MT_PX_F16><<<grid, 128, 0, stream>>>(P);
+    else if (P.storage == MT_PX_F16_EMULATE) godrays_kernel<MT_PX_F16_EMULATE><<<grid, 128, 0, stream>>>(P);
+    else godrays_kernel<MT_PX_F32><<<grid, 128, 0, stream>>>(P);
     return cudaGetLastError();
 }
 cudaError_t mt_launch_tonemap(const ToneMapParams& P, cudaStream_t stream)
 {
     dim3 grid((unsigned)((P.W + 31) / 32), (unsigned)((P.H + 7) / 8), 1);
-    tonemap_kernel<<<grid, 256, 0, stream>>>(P);
+    if (P.storage == MT_PX_F16) tonemap_kernel<MT_PX_F16><<<grid, 256, 0, stream>>>(P);
+    else tonemap_kernel<MT_PX_F32><<<grid, 256, 0, stream>>>(P);
     return cudaGetLastError();
 }
 
