@@ -328,6 +328,12 @@ struct StepBase {
     float h, baseDensity;
 };
 
+// MT_BASE_PACKED: the x, y components of the per-step vector arithmetic as fp32x2 pairs (one issue slot for two IEEE operations;
+// the kernel is issue bound).  Every operation is the same IEEE operation on the same operands -- a product that feeds an
+// addition is added with scalar FADDs, never mul2 -> add2 (mt_math.cuh) -- so the result is bit-identical to the scalar form.
+#ifndef MT_BASE_PACKED
+#define MT_BASE_PACKED 1
+#endif
 template <bool COUNT, bool WEATHER, int STD>
 MT_DEVICE StepBase cloud_step_base(const CloudParams& P, const MarchConst& M, const RaySetup& R, int jidx, float t, RayCounters& cnt)
 {
@@ -336,6 +342,36 @@ MT_DEVICE StepBase cloud_step_base(const CloudParams& P, const MarchConst& M, co
     const f3 relOrigin = mk3(ec.x, MT_R_INNER - MT_EARTH_RADIUS, ec.z);
     const f3 wind = mk3(P.tun.wind_direction[0], P.tun.wind_direction[1], P.tun.wind_direction[2]);
     const float* sj = M.stepJitter[jidx >> 1];
+#if MT_BASE_PACKED
+    // pos = origin + (dir + jitter) * t
+    const P2 jxy = add2(pk2(dir.x, dir.y), pk2(sj[0], sj[1]));
+    const float jz = dir.z + sj[2];
+    const P2 mxy = mul2(jxy, bc2(t));
+    const f3 pos = mk3(origin.x + lo2(mxy), origin.y + hi2(mxy), origin.z + jz * t);
+    const P2 pxy = pk2(pos.x, pos.y);
+    // sp = ((pos - relOrigin) / 12500) / 8
+    const P2 spxy = mul2(div_thickness2(sub2(pxy, pk2(relOrigin.x, relOrigin.y))), bc2(0.125f));
+    const float spz = div_thickness(pos.z - relOrigin.z) * 0.125f;
+    // getRelativeHeightInAtmosphere (:171-186)
+    const P2 cxy = sub2(pxy, pk2(origin.x, origin.y));                // pos - origin
+    const float cz = pos.z - origin.z;
+    const P2 c2 = mul2(cxy, cxy);
+    const float lenFromCam = sqrt_nice((lo2(c2) + hi2(c2)) + cz * cz);  // 2e4 .. 3e5 m
+    const P2 exy = sub2(pxy, pk2(ec.x, ec.y));                        // pos - earth centre, ~6.4e6 m
+    const float ez = pos.z - ec.z;
+    const P2 e2 = mul2(exy, exy);
+    const float rinv = div_nice(1.0f, sqrt_nice((lo2(e2) + hi2(e2)) + ez * ez));
+    const P2 nxy = mul2(mul2(exy, bc2(rinv)), pk2(dir.x, dir.y));     // dir * normalize(pos - ec), x and y
+    const float cosTheta = (lo2(nxy) + hi2(nxy)) + dir.z * (ez * rinv);
+    const float h = div_thickness(fabsf(cosTheta * (lenFromCam - R.lenToInner)));
+    // skewSamplePointWithWind (:489-497): (sp + ((wind * h) * offset) * 0.009) + windSkew
+    const P2 wxy = mul2(mul2(mul2(pk2(wind.x, wind.y), bc2(h)), bc2(P.tun.cloud_top_offset)), bc2(0.009f));
+    const float wz = ((wind.z * h) * P.tun.cloud_top_offset) * 0.009f;
+    const P2 skxy = add2(pk2(lo2(spxy) + lo2(wxy), hi2(spxy) + hi2(wxy)), pk2(M.windSkew.x, M.windSkew.y));
+    const f3 skew = mk3(lo2(skxy), hi2(skxy), (spz + wz) + M.windSkew.z);
+    B.pos = pos; B.skew = skew; B.h = h;
+    B.baseDensity = low_freq_density<WEATHER, STD>(P, M, P.tun.coverage, skxy, skew.z, pos.x, pos.z, h) * P.tun.base_density_factor;
+#else
     f3 jdir = dir + mk3(sj[0], sj[1], sj[2]);
     f3 pos = origin + jdir * t;
     f3 rp = pos - relOrigin;
@@ -348,6 +384,7 @@ MT_DEVICE StepBase cloud_step_base(const CloudParams& P, const MarchConst& M, co
     f3 skew = (sp + ((wind * h) * P.tun.cloud_top_offset) * 0.009f) + M.windSkew;
     B.pos = pos; B.skew = skew; B.h = h;
     B.baseDensity = low_freq_density<WEATHER, STD>(P, M, P.tun.coverage, pk2(skew.x, skew.y), skew.z, pos.x, pos.z, h) * P.tun.base_density_factor;
+#endif
     if (COUNT) cnt.steps++;
     return B;
 }
@@ -355,11 +392,10 @@ MT_DEVICE StepBase cloud_step_base(const CloudParams& P, const MarchConst& M, co
 // The in-cloud part of a march iteration (cloudRayMarch.comp:642-672): erosion, the six light-cone samples, light
 // energy.  Call only when B.baseDensity > 0.
 // The six light-cone offsets of one ray, (stepSize * noise_kernel[i]) * i, are the same at every step: the one-thread-per-ray
-// kernel computes them once per ray into shared memory (xy pairs and z, [i][thread]: conflict-free) and each in-cloud step
-// reads them back -- two loads instead of a float conversion and four multiplies per cone sample, the same values.
+// kernel computes them once per ray into shared memory ((x, y, z, -) per sample, [i][thread]: conflict-free) and each in-cloud
+// step reads them back -- one 16-byte load instead of a float conversion and four multiplies per cone sample, the same values.
 struct ConeOffsets {
-    const P2* xy;     // this thread's first pair; the pair of sample i is xy[i * stride]   (null: compute per step)
-    const float* z;
+    const F4* xyz;    // this thread's first offset (x, y, z, -); the offset of sample i is xyz[i * stride]   (null: compute per step)
     int stride;
     unsigned stage;   // shared-memory byte address of this thread's staging slots for the pipelined cone loop (0: none);
                       // slot (s, k) = stage + (2 * s + k) * stageStride: stage s in {0, 1}, k = slice z0 / z1 quad
@@ -417,11 +453,14 @@ MT_DEVICE void cone_axes(const CloudParams& P, const MarchConst& M, const ConeOf
     // lightPos = pos + (stepSize * noise_kernel[i]) * i ; sample = (lightPos - relOrigin) / 12500  -- x,y as a pair
     P2 off;
     float offz;
-    if (CO.xy) { off = CO.xy[i * CO.stride]; offz = CO.z[i * CO.stride]; }
-    else cone_offset(M, stepSize, i, off, offz);
+    if (CO.xyz) {  // one 16-byte shared load
+        const F4 o = CO.xyz[i * CO.stride];
+        off = pk2(o.x, o.y);
+        offz = o.z;
+    } else cone_offset(M, stepSize, i, off, offz);
     // the offset products are separate values (memory or scalar adds): a mul2 feeding an add2 would be contracted into
     // an FFMA2 (mt_math.cuh)
-    const P2 lxy = sub2(CO.xy ? add2(pk2(pos.x, pos.y), off) : pk2(pos.x + lo2(off), pos.y + hi2(off)), pk2(relOrigin.x, relOrigin.y));
+    const P2 lxy = sub2(CO.xyz ? add2(pk2(pos.x, pos.y), off) : pk2(pos.x + lo2(off), pos.y + hi2(off)), pk2(relOrigin.x, relOrigin.y));
     const float lz = (pos.z + offz) - relOrigin.z;
     sxy = div_thickness2(lxy);
     sz = div_thickness(lz);
@@ -574,7 +613,7 @@ MT_DEVICE void cloud_composite(const RaySetup& R, float accum, float color, F4& 
 // One invocation of main(): setup, the sequential march, composite.
 template <bool COUNT, bool DEBUG, bool WEATHER, int STD>
 MT_DEVICE void cloud_ray(const CloudParams& P, const MarchConst& M, int px, int py, int pixelID, F4& hdr, F4& mask,
-                         RayCounters& cnt, MtRayDebug* dbg, P2* coneXY, float* coneZ, int coneStride, unsigned coneStage = 0u,
+                         RayCounters& cnt, MtRayDebug* dbg, F4* coneXYZ, int coneStride, unsigned coneStage = 0u,
                          unsigned coneStageStride = 0u)
 {
     mask.x = mask.y = mask.z = mask.w = 0.0f;
@@ -588,11 +627,17 @@ MT_DEVICE void cloud_ray(const CloudParams& P, const MarchConst& M, int px, int 
     if (R.branch != 2) return;
 
     ConeOffsets CO;
-    CO.xy = coneXY; CO.z = coneZ; CO.stride = coneStride;
+    CO.xyz = coneXYZ; CO.stride = coneStride;
     CO.stage = coneStage; CO.stageStride = coneStageStride;
-    if (coneXY) {
+    if (coneXYZ) {
 #pragma unroll
-        for (int i = 0; i < 6; ++i) cone_offset(M, R.stepSize, i, coneXY[i * coneStride], coneZ[i * coneStride]);
+        for (int i = 0; i < 6; ++i) {
+            P2 oxy;
+            F4 o;
+            cone_offset(M, R.stepSize, i, oxy, o.z);
+            o.x = lo2(oxy); o.y = hi2(oxy); o.w = 0.0f;
+            coneXYZ[i * coneStride] = o;
+        }
     }
     float accum = 0.0f, transmittance = 1.0f, color = 0.0f;
     unsigned jhash = 2166136261u;

@@ -109,7 +109,7 @@ template <bool FULL, bool COUNT, bool DEBUG, bool WEATHER, bool STD>
 #define MT_CLOUD_MINBLOCKS 8  /* 64 registers/thread: 8 CTAs = 32 warps per SM (profiles/r1_cloud_ab.md) */
 #endif
 #ifndef MT_CONE_CACHE
-#define MT_CONE_CACHE 1       /* per-ray light-cone offsets in shared memory (9 KB per CTA) */
+#define MT_CONE_CACHE 1       /* per-ray light-cone offsets in shared memory (12 KB per CTA) */
 #endif
 __global__ void __launch_bounds__(128, MT_CLOUD_MINBLOCKS) cloud_raymarch_kernel(const __grid_constant__ CloudParams P)
 {
@@ -168,13 +168,10 @@ __global__ void __launch_bounds__(128, MT_CLOUD_MINBLOCKS) cloud_raymarch_kernel
 
     // per-ray light-cone offsets (cloud_core.cuh, ConeOffsets): [sample][thread], written once per marching ray
 #if MT_CONE_CACHE
-    __shared__ P2 coneXY[6][128];
-    __shared__ float coneZ[6][128];
-    P2* const cxy = &coneXY[0][threadIdx.x];
-    float* const cz = &coneZ[0][threadIdx.x];
+    __shared__ F4 coneXYZ[6][128];
+    F4* const cxyz = &coneXYZ[0][threadIdx.x];
 #else
-    P2* const cxy = nullptr;
-    float* const cz = nullptr;
+    F4* const cxyz = nullptr;
 #endif
     // staging slots of the pipelined cone loop (cloud_core.cuh, MT_CONE_PIPE): [stage][z0 / z1 quad][thread], 16 bytes each
 #if MT_CONE_PIPE
@@ -191,7 +188,7 @@ __global__ void __launch_bounds__(128, MT_CLOUD_MINBLOCKS) cloud_raymarch_kernel
     if (valid) {
         F4 hdr, mask;
         const size_t idx = (size_t)py * (size_t)P.W + (size_t)px;
-        cloud_ray<COUNT, DEBUG, WEATHER, (STD ? (MT_CONE_PIPE ? 2 : 1) : 0)>(P, M, px, py, pixelID, hdr, mask, cnt, DEBUG ? (P.debug + idx) : nullptr, cxy, cz, 128,
+        cloud_ray<COUNT, DEBUG, WEATHER, (STD ? (MT_CONE_PIPE ? 2 : 1) : 0)>(P, M, px, py, pixelID, hdr, mask, cnt, DEBUG ? (P.debug + idx) : nullptr, cxyz, 128,
                                                                            cstage, cstride);
         const float4 h4 = make_float4(hdr.x, hdr.y, hdr.z, hdr.w);
         if (bulk) {
@@ -337,7 +334,7 @@ __global__ void __launch_bounds__(128, MT_STEPS_MINBLOCKS) cloud_steps_kernel(co
     if (R.branch != 2 || k >= R.nsteps) return;
     const int jidx = (P.tm.frameCountMod16 + mt_f2i(t)) & 15;
     RayCounters none = { 0u, 0u, 0u, 0u, 0u, 0u };
-    const ConeOffsets noCache = { nullptr, nullptr, 0, 0u, 0u };  // one thread per (ray, step): nothing to share
+    const ConeOffsets noCache = { nullptr, 0, 0u, 0u };  // one thread per (ray, step): nothing to share
     const StepSample S = cloud_step_sample<false, WEATHER, STD>(P, M, R, jidx, t, none, noCache);
     *slot = make_float2(S.inc, S.energy);
 }
@@ -402,7 +399,7 @@ __global__ void __launch_bounds__(128, MT_CLOUD_MINBLOCKS) cloud_light_kernel(co
         const int jidx = (P.tm.frameCountMod16 + mt_f2i(t)) & 15;
         RayCounters none = { 0u, 0u, 0u, 0u, 0u, 0u };
         const StepBase B = cloud_step_base<false, WEATHER, STD>(P, M, R, jidx, t, none);   // same arithmetic: B.baseDensity > 0 again
-        const ConeOffsets noCache = { nullptr, nullptr, 0, 0u, 0u };
+        const ConeOffsets noCache = { nullptr, 0, 0u, 0u };
         const StepSample S = cloud_step_light<false, WEATHER, STD>(P, M, R, B, none, noCache);
         P.samples[(size_t)k * (size_t)P.rayStride + ray] = make_float2(S.inc, S.energy);
     }
@@ -526,7 +523,7 @@ __global__ void __launch_bounds__(32 * MT_S16_WARPS, MT_S16_MINBLOCKS) cloud_six
     const RaySetup& R = rays[lane];
     {   // ---- B
         const int mine = R.branch == 2 ? R.nsteps : 0;
-        const ConeOffsets noCache = { nullptr, nullptr, 0, 0u, 0u };  // a thread visits ~7 steps of its ray: not worth a cache
+        const ConeOffsets noCache = { nullptr, 0, 0u, 0u };  // a thread visits ~7 steps of its ray: not worth a cache
         RayCounters none = { 0u, 0u, 0u, 0u, 0u, 0u };
         for (int k = warp; k < nmax; k += MT_S16_WARPS) {
             if (k < mine) {

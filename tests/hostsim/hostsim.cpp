@@ -81,8 +81,7 @@ int hs_cloud(const MtCameraUBO* cam, const MtTimeUBO* tm, const MtTuning* tun, c
             F4 h, m;
             size_t idx = (size_t)py * W + px;
             MtRayDebug scratch;
-            P2 coneXY[6];   // the kernel's per-ray light-cone offset cache (shared memory there), stride 1 here
-            float coneZ[6];
+            F4 coneXYZ[6];  // the kernel's per-ray light-cone offset cache (shared memory there), stride 1 here
             memset(&cnt, 0, sizeof(cnt));
             if (full == 2) {
                 // The step-parallel decomposition of the 1-of-16 dispatch (cloud_rays_kernel / cloud_steps_kernel /
@@ -98,7 +97,7 @@ int hs_cloud(const MtCameraUBO* cam, const MtTimeUBO* tm, const MtTuning* tun, c
                     R.nsteps = n;
                     StepSample S[MT_STEP_SLICES];
                     RayCounters none = { 0, 0, 0, 0, 0, 0 };
-                    const ConeOffsets noCache = { nullptr, nullptr, 0, 0u, 0u };
+                    const ConeOffsets noCache = { nullptr, 0, 0u, 0u };
                     for (int k = n - 1; k >= 0; --k) {
                         const int jidx = (P.tm.frameCountMod16 + mt_f2i(tk[k])) & 15;
                         S[k] = tun->use_weather ? cloud_step_sample<false, true, 0>(P, M, R, jidx, tk[k], none, noCache)
@@ -114,10 +113,10 @@ int hs_cloud(const MtCameraUBO* cam, const MtTimeUBO* tm, const MtTuning* tun, c
                 memcpy(mask + 4 * idx, &m, 16);
                 continue;
             }
-            if (tun->use_weather) cloud_ray<true, true, true, 0>(P, M, px, py, id, h, m, cnt, debug ? debug + idx : &scratch, coneXY, coneZ, 1);
+            if (tun->use_weather) cloud_ray<true, true, true, 0>(P, M, px, py, id, h, m, cnt, debug ? debug + idx : &scratch, coneXYZ, 1);
             else if (std_dims)  // STD: extents as immediates, light-cone samples from the (r, F) form
-                cloud_ray<true, true, false, 1>(P, M, px, py, id, h, m, cnt, debug ? debug + idx : &scratch, coneXY, coneZ, 1);
-            else cloud_ray<true, true, false, 0>(P, M, px, py, id, h, m, cnt, debug ? debug + idx : &scratch, nullptr, nullptr, 0);
+                cloud_ray<true, true, false, 1>(P, M, px, py, id, h, m, cnt, debug ? debug + idx : &scratch, coneXYZ, 1);
+            else cloud_ray<true, true, false, 0>(P, M, px, py, id, h, m, cnt, debug ? debug + idx : &scratch, nullptr, 0);
             tot[0] += cnt.rays; tot[1] += cnt.marched; tot[2] += cnt.steps; tot[3] += cnt.incloud; tot[4] += cnt.cone; tot[5] += cnt.early;
             memcpy(hdr + 4 * idx, &h, 16);
             memcpy(mask + 4 * idx, &m, 16);

@@ -13,6 +13,8 @@ try:
     d = json.load(open("gpurun_out/${TAG}_n${N}_default.json"))
     print("default N=$N: views", d["value"], "Mrays/s", d["ms_per_step"], "ms; e2e", d["e2e"]["value"])
     print("  sharded_8k:", json.dumps(d.get("sharded_8k")))
+    print("  sharded_8k_f16:", json.dumps(d.get("sharded_8k_f16")))
+    print("  e2e_f16:", json.dumps(d.get("e2e_f16")))
 except Exception as e:
     print("default run failed:", e); print(open("gpurun_out/${TAG}_n${N}_default.err").read()[-1500:])
 PY
@@ -28,6 +30,11 @@ except Exception as e:
     print("frame8k $NAME failed:", e); print(open("gpurun_out/${TAG}_n${N}_8k_$NAME.err").read()[-800:])
 PY
 }
+if [ "$LEAN" = "1" ]; then
+  run8k local --gather local
+  run8k peer_rows32 --gather peer_store --tile-rows 32
+  exit 0
+fi
 run8k peer_store --gather peer_store
 run8k bulk_store --gather bulk_store
 run8k local --gather local
