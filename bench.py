@@ -312,6 +312,28 @@ def sharded_8k_record(args, api, sharding, torch, dist, world, rank, local_rank,
     return rec
 
 
+def bind_to_gpu_numa_node(device: int):
+    """One process per GPU on a two-socket host: run this rank on the CPUs next to its GPU (NVML's ideal CPU set) BEFORE any
+    pinned host buffer is allocated, so that first touch places the buffers on the GPU's own NUMA node.  Eight ranks reading
+    133-265 MB per step back into one node's memory are limited by that node (~90 GB/s in aggregate, round 1); spread over
+    both nodes each GPU keeps its own PCIe link busy.  Best effort: returns a description or None."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return f"{len(cpus)} CPUs near GPU {device} ({min(cpus)}..{max(cpus)})"
+    except Exception:  # noqa: BLE001 -- no NVML, no affinity support: keep the default placement
+        return None
+
+
 _REAL_STDOUT = None
 
 
@@ -365,6 +387,7 @@ def main():
 
     from meteoros_b200 import api, sharding, textures
 
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -602,6 +625,7 @@ def main():
         }
         if world > 1:
             line["rank_ms"] = rank_ms
+            line["e2e"]["host_placement"] = numa or "default (no NUMA binding)"
         if args.workload == "seq1080p":  # per-pass device time and HBM roofline of the bandwidth passes (SURVEY 8d bytes/pixel)
             px = w * h
             algo = {"reproject": 32 * px, "godrays": 48 * px, "tonemap": 20 * px}

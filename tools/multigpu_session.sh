@@ -30,6 +30,7 @@ except Exception as e:
     print("frame8k $NAME failed:", e); print(open("gpurun_out/${TAG}_n${N}_8k_$NAME.err").read()[-800:])
 PY
 }
+if [ "$LEAN" = "2" ]; then exit 0; fi
 if [ "$LEAN" = "1" ]; then
   run8k local --gather local
   run8k peer_rows32 --gather peer_store --tile-rows 32
