@@ -508,7 +508,8 @@ def main():
     h2d = int(cam.nbytes + tm.nbytes + tun.nbytes + sky.nbytes)
     e2e_read = (rank == 0) or args.workload != "frame8k"
     read_mask = args.workload in ("cloud4k", "views256") or (sharded and args.gather_mask)
-    pinned_mask = [torch.empty(nbytes, dtype=torch.uint8, pin_memory=True) for _ in range(2)] if read_mask else None
+    grey_bytes = w * h * 4  # one float per pixel: the decoded god-ray value (mtReadGodRayGreyAsync)
+    pinned_mask = [torch.empty(grey_bytes, dtype=torch.uint8, pin_memory=True) for _ in range(2)] if read_mask else None
 
     def e2e_step(i):
         if not seq:
@@ -520,8 +521,8 @@ def main():
             r.swap_ping_pong()  # mtFrame swaps by itself
         if e2e_read:
             r.read_image_async(out_which, pinned[i & 1].data_ptr(), nbytes)
-            if read_mask:  # the Cloud pass has two outputs (cloudRayMarch.comp:824-825): HDR colour and the god-ray image
-                r.read_image_async(api.IMAGE_GODRAY_MASK, pinned_mask[i & 1].data_ptr(), nbytes)
+            if read_mask:  # the Cloud pass has two outputs (cloudRayMarch.comp:824-825): HDR colour and the grey-scale god-ray image
+                r.read_godray_grey_async(pinned_mask[i & 1].data_ptr(), grey_bytes)
 
     for i in range(2):
         e2e_step(i)
@@ -540,14 +541,14 @@ def main():
     if args.workload == "cloud4k" and args.storage != 2:
         r16 = api.CloudRenderer(w, h, device=local_rank, storage=2, flags=args.ctx_flags)
         r16.upload_noise(noise)
-        pin16 = [torch.empty(nbytes16, dtype=torch.uint8, pin_memory=True) for _ in range(4)]
+        pin16 = [torch.empty(nbytes16, dtype=torch.uint8, pin_memory=True) for _ in range(2)] + [torch.empty(w * h * 4, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
 
         def e2e16_step(i):
             r16.set_camera(cam); r16.set_time(tm); r16.set_tuning(tun); r16.set_sun_and_sky(sky)
             r16.dispatch_cloud_full()
             r16.swap_ping_pong()
             r16.read_image_async(api.IMAGE_CLOUD_PREV, pin16[i & 1].data_ptr(), nbytes16)
-            r16.read_image_async(api.IMAGE_GODRAY_MASK, pin16[2 + (i & 1)].data_ptr(), nbytes16)
+            r16.read_godray_grey_async(pin16[2 + (i & 1)].data_ptr(), w * h * 4)
 
         for i in range(2):
             e2e16_step(i)
@@ -613,13 +614,13 @@ def main():
             "scaling": "strong" if (args.workload == "frame8k") else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload, "rays_per_step": int(rays_total_per_step), "l2": "flushed between timed steps (256 MiB memset)",
                        "noise": "reference noise volumes (tests/golden/noise_volumes.npz)", "parallelism": f"row-tiles x{world}" if args.workload == "frame8k" else f"views x{world}"},
-            "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int((nbytes * (2 if read_mask else 1)) if e2e_read else 0),
-                    "reads": ("HDR colour + god-ray image" if read_mask else ("LDR frame" if seq else "HDR colour (the god-ray image stays on its GPU unless --gather-mask)")),
+            "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int((nbytes + (grey_bytes if read_mask else 0)) if e2e_read else 0),
+                    "reads": ("HDR colour (RGBA) + grey-scale god-ray image (one float per pixel, decoded on the device)" if read_mask else ("LDR frame" if seq else "HDR colour (the god-ray image stays on its GPU unless --gather-mask)")),
                     "ms_per_step": round(1e3 * e2e_s / args.steps, 4)},
             "e2e_f16": None if e2e16_s is None else {
                 "value": round(rays_total_per_step * args.steps / e2e16_s / 1e6, 2), "unit": UNIT, "ms_per_step": round(1e3 * e2e16_s / args.steps, 4),
-                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(2 * nbytes16), "storage": "MT_STORAGE_F16: RGBA16F images, the reference's own format (Renderer.cpp:1431-1440)",
-                "reads": "HDR colour + god-ray image"},
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(nbytes16 + w * h * 4), "storage": "MT_STORAGE_F16: RGBA16F images, the reference's own format (Renderer.cpp:1431-1440)",
+                "reads": "HDR colour (RGBA16F) + grey-scale god-ray image (one float per pixel)"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
             "work": {k: int(v) for k, v in counters.items()},
         }

@@ -244,6 +244,12 @@ MT_API MtStatus mtReadImageRows(MtContext* ctx, MtImage which, uint32_t row_begi
  * pinned; it is valid after mtWaitReads (or mtSynchronize).  With the ping-pong swap this hides the read-back of frame k
  * behind the rendering of frame k+1.                                                                                  */
 MT_API MtStatus mtReadImageAsync(MtContext* ctx, MtImage which, void* host, size_t bytes);
+/* The god-ray image as one float per pixel (extension): the value the Cloud shader spreads over four channels with
+ * EncodeFloatRGBA (cloudRayMarch.comp:106-112, 824-825), decoded on the device with the god-ray shader's own dot product
+ * (postProcess_GodRays.frag:39-43) and read back like mtReadImageAsync -- W*H*4 bytes instead of W*H*16.  The god-ray image
+ * is not ping-ponged, so both this and mtReadImageAsync(MT_IMAGE_GODRAY_MASK) copy from a device-side snapshot: the next
+ * Cloud dispatch never waits for PCIe.                                                                                   */
+MT_API MtStatus mtReadGodRayGreyAsync(MtContext* ctx, float* host, size_t bytes);
 MT_API MtStatus mtWaitReads(MtContext* ctx);
 /* Device-side join: work issued to the context after this call waits for every copy issued so far (no host sync). */
 MT_API MtStatus mtJoinCopies(MtContext* ctx);

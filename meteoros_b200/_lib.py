@@ -85,6 +85,7 @@ PROTOTYPES = {
     "mtReadImage": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
     "mtReadImageRows": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t]),
     "mtReadImageAsync": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
+    "mtReadGodRayGreyAsync": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "mtWaitReads": (C.c_int, [C.c_void_p]),
     "mtJoinCopies": (C.c_int, [C.c_void_p]),
     "mtWriteImage": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),

@@ -221,6 +221,16 @@ class CloudRenderer:
         """D2H on the copy stream, overlapping later dispatches; valid after wait_reads()."""
         self._check(self._lib.mtReadImageAsync(self._h, which, C.c_void_p(host_ptr), nbytes), "mtReadImageAsync")
 
+    def read_godray_grey_async(self, host_ptr: int, nbytes: int):
+        """The god-ray image as one float32 per pixel (decoded on the device), D2H on the copy stream; valid after wait_reads()."""
+        self._check(self._lib.mtReadGodRayGreyAsync(self._h, C.c_void_p(host_ptr), nbytes), "mtReadGodRayGreyAsync")
+
+    def read_godray_grey(self) -> np.ndarray:
+        out = np.empty((self.height, self.width), np.float32)
+        self.read_godray_grey_async(out.ctypes.data, out.nbytes)
+        self.wait_reads()
+        return out
+
     def wait_reads(self):
         self._check(self._lib.mtWaitReads(self._h), "mtWaitReads")
 

@@ -37,6 +37,7 @@ struct MtContext {
     F4* mask = nullptr;
     float2* maskDecoded = nullptr; // (W+2) x (H+2) pairs: scratch of the god-ray pass
     F4* maskStage = nullptr;       // device snapshot of the mask behind mtReadImageAsync (lazily allocated)
+    float* greyStage = nullptr;    // the decoded one-float-per-pixel god-ray image behind mtReadGodRayGreyAsync (lazily allocated)
     uint32_t* ldr[2] = { nullptr, nullptr };  // ping-pong with the HDR images (same `cur`)
     uint32_t* ldrScratch = nullptr;           // TXAA output, swapped with ldr[cur] after the pass
     uint32_t* tex[4] = { nullptr, nullptr, nullptr, nullptr };
@@ -175,7 +176,9 @@ static void free_images(MtContext* c)
     cudaFree(c->items); cudaFree(c->itemCount);
     cudaFree(c->tileDone);
     cudaFree(c->maskStage);
+    cudaFree(c->greyStage);
     c->maskStage = nullptr;
+    c->greyStage = nullptr;
     c->tileDone = nullptr; c->fwdBusy = false; c->fwdCheck = false; c->fwdTiles = 0;
     c->forwardHdr = nullptr;            // mapped for the old size: the peer must re-export, the caller re-arm (mtSetCloudForward)
     c->outHdr = c->outMask = nullptr;   // same for mtSetCloudOutput
@@ -875,6 +878,27 @@ try {
     if (!c) return MT_ERR_INVALID;
     return mtReadImageRows(c, which, 0, (uint32_t)c->H, host, bytes);
 } MT_NOTHROW
+// shared tail of the asynchronous reads: `dev` (already valid on the main stream) -> host on the copy stream
+static MtStatus async_read_tail(MtContext* c, const void* dev, void* host, size_t bytes)
+{
+    MtContext::PendingRead* slot = nullptr;
+    for (auto& p : c->pending)
+        if (p.active && p.dev == dev) slot = &p;     // a second read of the same image re-uses its slot
+    for (auto& p : c->pending)
+        if (!slot && !p.active) slot = &p;
+    if (!slot) {                                     // all slots busy: retire the oldest by waiting for the copy stream
+        MT_CUDA(c, cudaStreamSynchronize(c->copyStream));
+        for (auto& p : c->pending) p.active = false;
+        slot = &c->pending[0];
+    }
+    MT_CUDA(c, cudaEventRecord(c->producedEv, c->stream));
+    MT_CUDA(c, cudaStreamWaitEvent(c->copyStream, c->producedEv, 0));
+    MT_CUDA(c, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, c->copyStream));
+    MT_CUDA(c, cudaEventRecord(slot->done, c->copyStream));
+    slot->dev = dev;
+    slot->active = true;
+    return MT_OK;
+}
 MtStatus mtReadImageAsync(MtContext* c, MtImage which, void* host, size_t bytes)
 try {
     if (!c) return MT_ERR_INVALID;
@@ -891,23 +915,24 @@ try {
         MT_CUDA(c, cudaMemcpyAsync(c->maskStage, dev, image_bytes(c, which), cudaMemcpyDeviceToDevice, c->stream));
         dev = c->maskStage;
     }
-    MtContext::PendingRead* slot = nullptr;
-    for (auto& p : c->pending)
-        if (p.active && p.dev == dev) slot = &p;     // a second read of the same image re-uses its slot
-    for (auto& p : c->pending)
-        if (!slot && !p.active) slot = &p;
-    if (!slot) {                                     // all slots busy: retire the oldest by waiting for the copy stream
-        MT_CUDA(c, cudaStreamSynchronize(c->copyStream));
-        for (auto& p : c->pending) p.active = false;
-        slot = &c->pending[0];
-    }
-    MT_CUDA(c, cudaEventRecord(c->producedEv, c->stream));
-    MT_CUDA(c, cudaStreamWaitEvent(c->copyStream, c->producedEv, 0));
-    MT_CUDA(c, cudaMemcpyAsync(host, dev, image_bytes(c, which), cudaMemcpyDeviceToHost, c->copyStream));
-    MT_CUDA(c, cudaEventRecord(slot->done, c->copyStream));
-    slot->dev = dev;
-    slot->active = true;
-    return MT_OK;
+    return async_read_tail(c, dev, host, image_bytes(c, which));
+} MT_NOTHROW
+MtStatus mtReadGodRayGreyAsync(MtContext* c, float* host, size_t bytes)
+try {
+    if (!c) return MT_ERR_INVALID;
+    const size_t need = (size_t)c->W * (size_t)c->H * sizeof(float);
+    MT_REQUIRE(c, host != nullptr && bytes >= need, "mtReadGodRayGreyAsync: host buffer too small");
+    MT_CUDA(c, cudaSetDevice(c->device));
+    if (!c->greyStage) MT_CUDA(c, cudaMalloc((void**)&c->greyStage, need));
+    wait_pending_read(c, c->greyStage);  // the previous decoded image has left the device
+    GodRayParams P;
+    memset(&P, 0, sizeof(P));
+    P.mask = c->mask;
+    P.W = c->W; P.H = c->H;
+    P.storage = (int)c->storage;
+    MT_CUDA(c, mt_launch_mask_grey(P, c->greyStage, c->stream));
+    c->launches += 1;
+    return async_read_tail(c, c->greyStage, host, need);
 } MT_NOTHROW
 MtStatus mtWaitReads(MtContext* c)
 try {

@@ -16,6 +16,7 @@ cudaError_t mt_launch_build_rf_quads(const uint32_t* texels, int w, int h, int d
 cudaError_t mt_launch_occupancy(const Tex3D& low, uint32_t* occ, float coverage, cudaStream_t stream);
 cudaError_t mt_launch_reproject(const ReprojParams& P, cudaStream_t stream);
 cudaError_t mt_launch_godrays(const GodRayParams& P, cudaStream_t stream);
+cudaError_t mt_launch_mask_grey(const GodRayParams& P, float* out, cudaStream_t stream);
 cudaError_t mt_launch_tonemap(const ToneMapParams& P, cudaStream_t stream);
 cudaError_t mt_launch_txaa(const TxaaParams& P, cudaStream_t stream);
 cudaError_t mt_launch_fma_probe(float* sink, int blocks, int iters, cudaStream_t stream);

@@ -69,6 +69,25 @@ __global__ void __launch_bounds__(256) mask_decode_kernel(const __grid_constant_
     P.decoded[(size_t)(y + 1) * (size_t)(P.W + 2) + (size_t)(x + 1)] = make_float2(d, dn);
 }
 
+// ---- The god-ray image as what it is -- one float per pixel ("grey-scale", the value EncodeFloatRGBA spread over four
+// channels, cloudRayMarch.comp:106-112): decoded with the god-ray shader's own dot product (postProcess_GodRays.frag:39-43).
+// 4 bytes per pixel for a host that wants the image, instead of 16 (mtReadGodRayGreyAsync).
+template <int ST>
+__global__ void __launch_bounds__(256) mask_grey_kernel(const __grid_constant__ GodRayParams P, float* __restrict__ out)
+{
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= P.W || y >= P.H) return;
+    out[(size_t)y * P.W + x] = mask_decoded_at<ST>(P, x, y);
+}
+cudaError_t mt_launch_mask_grey(const GodRayParams& P, float* out, cudaStream_t stream)
+{
+    dim3 grid((unsigned)((P.W + 31) / 32), (unsigned)((P.H + 7) / 8), 1);
+    if (P.storage == MT_PX_F16) mask_grey_kernel<MT_PX_F16><<<grid, 256, 0, stream>>>(P, out);
+    else mask_grey_kernel<MT_PX_F32><<<grid, 256, 0, stream>>>(P, out);
+    return cudaGetLastError();
+}
+
 // ---- God rays: 100 bilinear taps per pixel on the decoded scalar image; the kernel is bound by L1 wavefronts and issue
 // slots together (profiles/r1_passes_1080p.md), so the warp's pixel footprint decides how many 128-byte lines each of the
 // four loads of a tap touches.  MT_GODRAY_LOG2W: a warp is a (1 << LOG2W) x (32 >> LOG2W) pixel tile (3: 8x4, 4: 16x2, 5: 32x1).

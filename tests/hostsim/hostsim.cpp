@@ -125,6 +125,16 @@ int hs_cloud(const MtCameraUBO* cam, const MtTimeUBO* tm, const MtTuning* tun, c
     return 0;
 }
 
+// launch order of the row tiles (mt_params.h): j-th tile issued -> index among the owned tiles
+int hs_tile_order(int heavy_first, int tile_count, int j)
+{
+    RowTiles r;
+    memset(&r, 0, sizeof(r));
+    r.heavy_first = heavy_first;
+    r.tile_count = tile_count;
+    return mt_tile_order(r, j);
+}
+
 int hs_reproject(const MtCameraUBO* cam, const MtCameraUBO* camOld, const MtTimeUBO* tm, int W, int H, const float* prev,
                  float* cur, int* taps_out)
 {

@@ -658,6 +658,35 @@ def test_f16_storage(api, oracle_mod, noise):
     assert np.array_equal(mask, ref["mask"].astype(np.float16))      # the mask is bit-exact before rounding, hence after
 
 
+def test_godray_grey_readback(api, oracle_mod, noise):
+    """mtReadGodRayGreyAsync: the god-ray image as one float per pixel = the shader's own decode of the four encoded channels
+    (postProcess_GodRays.frag:39-43), bit for bit, for both storage formats; a later Cloud dispatch does not disturb a read
+    that is still in flight (it copies from a snapshot)."""
+    w, h = 256, 144
+    cam, tm, _, tun = default_scene(w, h, frame_id=4, total_time=6.0)
+    ref = oracle_mod.cloud(cam, tm, tun, noise, w, h, full=True)["mask"]
+
+    def decode(m):  # ((x * 1 + y / 255) + z / 65025) + w / 16581375, every operation in binary32
+        m = m.astype(np.float32)
+        k = [np.float32(1.0), np.float32(1.0) / np.float32(255.0), np.float32(1.0) / np.float32(65025.0), np.float32(1.0) / np.float32(16581375.0)]
+        return ((m[..., 0] * k[0] + m[..., 1] * k[1]) + m[..., 2] * k[2]) + m[..., 3] * k[3]
+
+    for storage in (api.STORAGE_F32, api.STORAGE_F16):
+        with make_renderer(api, noise, w, h, storage=storage) as r:
+            r.set_camera(cam); r.set_time(tm)
+            r.dispatch_cloud_full()
+            grey = r.read_godray_grey()
+            want = decode(ref if storage == api.STORAGE_F32 else ref.astype(np.float16))
+            assert grey.dtype == np.float32 and grey.shape == (h, w)
+            assert np.array_equal(grey, want)
+            assert np.array_equal(decode(r.read_image(api.IMAGE_GODRAY_MASK)), grey)
+            out = np.empty((h, w), np.float32)
+            r.read_godray_grey_async(out.ctypes.data, out.nbytes)
+            r.clear_images()              # overwrites the mask while the read may still be in flight
+            r.wait_reads()
+            assert np.array_equal(out, want)
+
+
 def test_async_readback_overlaps_next_frame(api, noise):
     """mtReadImageAsync: frame k is copied out on the copy stream while frame k+1 renders into the other ping-pong
     image; a third frame that re-uses the first image must wait for its copy."""

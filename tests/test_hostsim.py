@@ -196,3 +196,23 @@ def test_step_parallel_decomposition_equals_sequential_march(oracle_mod, noise, 
     par_hdr, par_mask, _, _ = hostsim.cloud(cam, tm, tun, noise, w, h, 2, oracle_mod.RAY_DEBUG_DTYPE)
     assert np.array_equal(seq_hdr, par_hdr) and np.array_equal(seq_mask, par_mask)
     assert seq_mask.any()
+
+
+def test_tile_launch_order_is_a_permutation_that_interleaves_light_tiles(hostsim):
+    """mt_tile_order (mt_params.h): every owned tile is issued exactly once; the marching tiles go from the horizon upwards
+    (index heavy_first-1 down to 0) and the light tiles (sky band, ocean) are slotted in one for one, so that neither the
+    heaviest CTAs nor the bulk of the stores end up in the kernel's tail."""
+    lib = hostsim.lib()
+    for n in list(range(1, 40)) + [135, 270, 540]:
+        for m in sorted({0, 1, n // 3, n // 2, n - 1, n}):
+            if not (0 <= m <= n):
+                continue
+            order = [lib.hs_tile_order(m, n, j) for j in range(n)]
+            assert sorted(order) == list(range(n)), (m, n)
+            heavy = [t for t in order if t < m]
+            assert heavy == list(range(m - 1, -1, -1))                  # horizon first, zenith last
+            light = [t for t in order if t >= m]
+            assert light == list(range(m, n))                           # sky band, then ocean, top-down
+            if m and n - m:
+                first = order[: 2 * min(m, n - m)]
+                assert all((t < m) == (k % 2 == 0) for k, t in enumerate(first))  # strictly alternating while both last
