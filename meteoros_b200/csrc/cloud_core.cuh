@@ -402,38 +402,32 @@ struct ConeOffsets {
     unsigned stageStride;
 };
 
-// MT_CONE_PIPE: software-pipelined light-cone loop (device only).  A cone sample is: position -> cell -> two 16-byte quad
-// loads (L2 latency: the rays of an SM walk 32 MB) -> filter.  One thread per ray has no second sample in flight, so every
-// cone sample paid that latency in full (long-scoreboard stalls, profiles/r2_cloud_*.md).  Here sample i+1's quads are
-// requested with cp.async (global -> this thread's own shared slot, no registers held) BEFORE sample i is filtered.  The
-// empty-cell test moves behind the load: bit 0 of the cell's first (r, F) word carries the flag (occupancy_build_kernel
-// writes it), so no separate bitmap load and no second dependent round trip.  Same arithmetic, same order: bit-identical.
-// Measured at 4K (profiles/r2_ab.md): 4.69 ms with cp.async.ca, 4.61 ms with .cg, against 4.48 ms for the plain loop -- the
-// unconditional quad loads of the 43 % empty-cell samples and the extra LSU traffic (LDGSTS + LDS) cost more than the hidden
-// latency buys (L1/TEX throughput was 48 % before).  OFF by default; kept as the A/B evidence.
+// MT_CONE_PIPE: software-pipelined light-cone loop (device only, one-thread-per-ray kernels).  A cone sample is a dependent
+// chain: position -> cell -> bitmap word -> brick load (L2 latency: the rays of an SM walk 64 MB) -> filter -> two divisions.
+// One thread per ray has no second sample in flight, so each of the six samples of a step pays both memory round trips in
+// full (3.1 long-scoreboard stall cycles per issued instruction, profiles/r2_cloud_final.md).  Here sample i+1's brick is
+// requested -- one unconditional 256-bit load into eight registers -- BEFORE sample i is filtered, and the empty-cell test
+// moves behind the load: bit 0 of the brick's first word carries the cell's flag (occupancy_build_kernel writes it), so the
+// bitmap load and its dependent round trip disappear.  Same arithmetic in the same order: bit-identical.
+// (Round 2 first built this with cp.async into shared staging slots: 4.69 / 4.61 ms against 4.48 ms for the plain loop --
+// LDGSTS + LDS per sample cost more LSU work than the hidden latency bought; profiles/r2_ab.md.)
 #ifndef MT_CONE_PIPE
-#define MT_CONE_PIPE 0
+#define MT_CONE_PIPE 1
 #endif
-#ifndef MT_CONE_PIPE_CG
-#define MT_CONE_PIPE_CG 0
+#if MT_CONE_PIPE && !MT_RF_BRICKS
+#error "the pipelined cone loop loads the (r, F) bricks: build it with MT_RF_BRICKS=1"
 #endif
 #if !defined(MT_HOSTSIM)
-__device__ __forceinline__ void cp_async16(unsigned dst, const void* src)
+struct Brick {
+    uint32_t t[8];  // t000 t001 t010 t011 t100 t101 t110 t111
+};
+__device__ __forceinline__ Brick ldg_brick(const Quad* bricks, unsigned cell)
 {
-#if MT_CONE_PIPE_CG
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");  // L2 only
-#else
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-#endif
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ Quad lds_quad(unsigned addr)
-{
-    Quad q;
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(addr) : "memory");
-    return q;
+    Brick b;
+    asm volatile("ld.global.nc.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(b.t[0]), "=r"(b.t[1]), "=r"(b.t[2]), "=r"(b.t[3]), "=r"(b.t[4]), "=r"(b.t[5]), "=r"(b.t[6]), "=r"(b.t[7])
+                 : "l"(bricks + 2u * cell));
+    return b;
 }
 #endif
 
@@ -483,45 +477,35 @@ MT_DEVICE StepSample cloud_step_light(const CloudParams& P, const MarchConst& M,
     S.inc = erode(baseDensity * 1.4f, edge) * 0.5f;
     float dl = 0.0f;
 #if !defined(MT_HOSTSIM) && MT_CONE_PIPE
-    if (STD == 2 && MT_CONE_RF && !WEATHER) {  // STD kernels are only launched with the (r, F) quads present (mt_std_dims)
+    if (STD == 2 && MT_CONE_RF && !WEATHER) {  // STD kernels are only launched with the (r, F) bricks present (mt_std_dims)
         const Tex3D low = std_low<STD>(P.low);
-        const unsigned wrap = (unsigned)low.w * (unsigned)low.h * (unsigned)low.d - 1u, slice = (unsigned)low.w * (unsigned)low.h;
         P2 sxy;
         float sz;
         LinAxis X, Y, Z;
         unsigned cell;
         cone_axes<STD>(P, M, CO, pos, relOrigin, R.stepSize, 0, sxy, sz, X, Y, Z, cell);
-        cp_async16(CO.stage, low.rfquads + cell);
-        cp_async16(CO.stage + CO.stageStride, low.rfquads + ((cell + slice) & wrap));
-        cp_async_commit();
+        Brick cur = ldg_brick(low.rfquads, cell);
 #pragma unroll 1
         for (int i = 0; i < 6; ++i) {
             LinAxis Xn = X, Yn = Y, Zn = Z;
             unsigned celln = cell;
-            const unsigned cur_slot = CO.stage + (unsigned)(i & 1) * (2u * CO.stageStride);
-            if (i < 5) {  // request sample i+1's quads, then wait for sample i's only
-                const unsigned nxt_slot = CO.stage + (unsigned)((i + 1) & 1) * (2u * CO.stageStride);
+            Brick nxt = cur;
+            if (i < 5) {  // request sample i+1's brick before sample i is filtered
                 cone_axes<STD>(P, M, CO, pos, relOrigin, R.stepSize, i + 1, sxy, sz, Xn, Yn, Zn, celln);
-                cp_async16(nxt_slot, low.rfquads + celln);
-                cp_async16(nxt_slot + CO.stageStride, low.rfquads + ((celln + slice) & wrap));
-                cp_async_commit();
-                cp_async_wait<1>();
-            } else {
-                cp_async_wait<0>();
+                nxt = ldg_brick(low.rfquads, celln);
             }
-            const Quad q0 = lds_quad(cur_slot);
-            if (q0.x & 1u) {  // the cell may hold cloud (flag written with the empty-cell bitmap); else the density is exactly +0
-                const Quad q1 = lds_quad(cur_slot + CO.stageStride);
+            if (cur.t[0] & 1u) {  // the cell may hold cloud (flag written with the empty-cell bitmap); else the density is exactly +0
                 const Weights8 w = filter_weights(X, Y, Z);
-                const uint32_t t000 = q0.x, t001 = q0.y, t010 = q0.z, t011 = q0.w, t100 = q1.x, t101 = q1.y, t110 = q1.z, t111 = q1.w;
+                const uint32_t t000 = cur.t[0], t001 = cur.t[1], t010 = cur.t[2], t011 = cur.t[3], t100 = cur.t[4], t101 = cur.t[5],
+                               t110 = cur.t[6], t111 = cur.t[7];
                 const P2 rf = mul2(MT_ACC2(MT_RFP), bc2(MT_INV255));
-                const float cur = cone_density_rf<STD>(P, M, coverage, rf, X, Y, Z, cell);
-                if (cur > 0.0f) {
+                const float dens = cone_density_rf<STD>(P, M, coverage, rf, X, Y, Z, cell);
+                if (dens > 0.0f) {
                     if (COUNT) cnt.cone++;
-                    dl += erode(1.5f * cur, edge);
+                    dl += erode(1.5f * dens, edge);
                 }
             }
-            X = Xn; Y = Yn; Z = Zn; cell = celln;
+            X = Xn; Y = Yn; Z = Zn; cell = celln; cur = nxt;
         }
     } else
 #endif

@@ -42,10 +42,14 @@ __global__ void __launch_bounds__(256) occupancy_build_kernel(Tex3D T, uint32_t*
             any = any || occ_texel_may_be_cloud(__ldg(T.texels + rows[r] + x), coverage) ||
                   occ_texel_may_be_cloud(__ldg(T.texels + rows[r] + x1), coverage);
         bits |= (any ? 1u : 0u) << k;
-        if (rfq) {
-            uint32_t* w0 = &rfq[(z * (unsigned)T.h + y) * (unsigned)T.w + x].x;
+#if MT_CONE_PIPE
+        if (rfq) {  // the pipelined cone loop reads the cell's flag from the brick it has loaded: bit 0 of the first word
+            uint32_t* w0 = &rfq[2u * ((z * (unsigned)T.h + y) * (unsigned)T.w + x)].x;
             *w0 = (*w0 & ~1u) | (any ? 1u : 0u);
         }
+#else
+        (void)rfq;
+#endif
     }
     occ[wi] = bits;
 }
@@ -79,6 +83,16 @@ __global__ void __launch_bounds__(256) build_rf_quads_kernel(const uint32_t* __r
     const unsigned x = i % (unsigned)w, y = (i / (unsigned)w) % (unsigned)h, z = i / ((unsigned)w * (unsigned)h);
     const unsigned x1 = (x + 1u) & (unsigned)(w - 1), y1 = (y + 1u) & (unsigned)(h - 1);
     const unsigned r0 = (z * h + y) * w, r1 = (z * h + y1) * w;
+#if MT_RF_BRICKS
+    {   // the cell's two slices back to back: 32 bytes, one 256-bit load per light-cone sample
+        const unsigned z1 = (z + 1u) & (unsigned)(d - 1);
+        const unsigned s0 = (z1 * h + y) * w, s1 = (z1 * h + y1) * w;
+        // bit 0 of the first word = "this cell may hold cloud" (set; occupancy_build_kernel clears it per coverage where it can)
+        q[2 * i] = make_uint4(rf_pack(t[r0 + x]) | 1u, rf_pack(t[r0 + x1]), rf_pack(t[r1 + x]), rf_pack(t[r1 + x1]));
+        q[2 * i + 1] = make_uint4(rf_pack(t[s0 + x]), rf_pack(t[s0 + x1]), rf_pack(t[s1 + x]), rf_pack(t[s1 + x1]));
+        return;
+    }
+#endif
     // bit 0 of the first word = "this cell may hold cloud" (set; occupancy_build_kernel clears it per coverage where it can)
     q[i] = make_uint4(rf_pack(t[r0 + x]) | 1u, rf_pack(t[r0 + x1]), rf_pack(t[r1 + x]), rf_pack(t[r1 + x1]));
 }
@@ -173,14 +187,7 @@ __global__ void __launch_bounds__(128, MT_CLOUD_MINBLOCKS) cloud_raymarch_kernel
 #else
     F4* const cxyz = nullptr;
 #endif
-    // staging slots of the pipelined cone loop (cloud_core.cuh, MT_CONE_PIPE): [stage][z0 / z1 quad][thread], 16 bytes each
-#if MT_CONE_PIPE
-    __shared__ uint4 coneStage[2][2][128];
-    const unsigned cstage = (unsigned)__cvta_generic_to_shared(&coneStage[0][0][threadIdx.x]);
-    const unsigned cstride = 128u * 16u;
-#else
     const unsigned cstage = 0u, cstride = 0u;
-#endif
     // staging of the bulk-store epilogue (mtSetCloudStoreMode): one 16x2 pixel tile per warp, row-major = lane order
     __shared__ __align__(128) float4 outStage[4][32];
     RayCounters cnt = { 0u, 0u, 0u, 0u, 0u, 0u };

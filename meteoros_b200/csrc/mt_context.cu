@@ -428,7 +428,7 @@ static MtStatus upload(MtContext* c, int slot, uint32_t w, uint32_t h, uint32_t 
         cudaFree(c->rfQuads);
         c->rfQuads = nullptr;
         if (!(c->flags & MT_FLAG_NO_CONE_RF)) {
-            MT_CUDA(c, cudaMalloc(&c->rfQuads, bytes * 4));
+            MT_CUDA(c, cudaMalloc(&c->rfQuads, bytes * 4 * (MT_RF_BRICKS ? 2 : 1)));
             MT_CUDA(c, mt_launch_build_rf_quads(c->tex[slot], (int)w, (int)h, (int)d, c->rfQuads, c->stream));
             c->launches += 1;
         }

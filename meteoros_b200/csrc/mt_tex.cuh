@@ -27,6 +27,12 @@
 #ifndef MT_TEX_BRICKS
 #define MT_TEX_BRICKS 0
 #endif
+// MT_RF_BRICKS: the (r, F) copy of the low-frequency volume holds, per filter cell, the cell's 2x2x2 texels in 32 contiguous
+// bytes (both slices' quads), fetched with ONE 256-bit load (LDG.E.256, new on sm_100) -- one sector and one LSU request per
+// light-cone sample instead of two (64 MB instead of 32 MB; with the RGBA quads 97 MB of the 126 MB L2).
+#ifndef MT_RF_BRICKS
+#define MT_RF_BRICKS 1
+#endif
 // MT_HW_FILTER=1: A/B build (tools/ab_bench.sh, profiles/r2_ab.md) in which the light-cone samples go through the texture unit's
 // own trilinear filter (tex3D, 9-bit weights) instead of the exact fp32 filter.  Never the default: it cannot meet the parity bar.
 #ifndef MT_HW_FILTER
@@ -210,7 +216,14 @@ MT_DEVICE P2 tex3d_rf_axes(const Tex3D& T, const LinAxis& X, const LinAxis& Y, c
 {
     const unsigned W = (unsigned)T.w, H = (unsigned)T.h;
     uint32_t t000, t001, t010, t011, t100, t101, t110, t111;
-#if MT_TEX_QUADS
+#if MT_TEX_QUADS && MT_RF_BRICKS
+    {
+        (void)W; (void)H;
+        asm("ld.global.nc.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+            : "=r"(t000), "=r"(t001), "=r"(t010), "=r"(t011), "=r"(t100), "=r"(t101), "=r"(t110), "=r"(t111)
+            : "l"(T.rfquads + 2u * cell));
+    }
+#elif MT_TEX_QUADS
     {
         const Quad q0 = MT_LDG_QUAD(T.rfquads + cell);
         const Quad q1 = MT_LDG_QUAD(T.rfquads + ((cell + W * H) & (W * H * (unsigned)T.d - 1u)));
