@@ -467,6 +467,9 @@ static bool mt_std_dims(const CloudParams& P)
 // CTA is in A or C, the other resident CTAs of the SM (six) are in B.
 // ---------------------------------------------------------------------------------------------------------------------
 #define MT_S16_WARPS 8
+#ifndef MT_S16_CONE
+#define MT_S16_CONE 1  /* 1: plain (r, F) cone loop; 2: the software-pipelined, unrolled one of the full-quality kernel */
+#endif
 #ifndef MT_S16_MINBLOCKS
 #define MT_S16_MINBLOCKS 6
 #endif
@@ -536,7 +539,7 @@ __global__ void __launch_bounds__(32 * MT_S16_WARPS, MT_S16_MINBLOCKS) cloud_six
             if (k < mine) {
                 const float t = tk[k][lane];
                 const int jidx = (pixelID + mt_f2i(t)) & 15;
-                const StepSample S = cloud_step_sample<false, WEATHER, (STD ? 1 : 0)>(P, M, R, jidx, t, none, noCache);
+                const StepSample S = cloud_step_sample<false, WEATHER, (STD ? MT_S16_CONE : 0)>(P, M, R, jidx, t, none, noCache);
                 smp[k][lane] = make_float2(S.inc, S.energy);
             }
         }
