@@ -414,17 +414,29 @@ struct ConeOffsets {
 #ifndef MT_CONE_PIPE
 #define MT_CONE_PIPE 1
 #endif
-#if MT_CONE_PIPE && !MT_RF_BRICKS
-#error "the pipelined cone loop loads the (r, F) bricks: build it with MT_RF_BRICKS=1"
+
+#ifndef MT_BRICK_EVICT_LAST
+#define MT_BRICK_EVICT_LAST 1
 #endif
 #if !defined(MT_HOSTSIM)
 struct Brick {
     uint32_t t[8];  // t000 t001 t010 t011 t100 t101 t110 t111
 };
-__device__ __forceinline__ Brick ldg_brick(const Quad* bricks, unsigned cell)
+__device__ __forceinline__ Brick ldg_brick(const Quad* bricks, unsigned cell, unsigned slice, unsigned wrap)
 {
     Brick b;
+#if !MT_RF_BRICKS  // quad layout: the two slices' quads are two 16-byte loads (32 MB instead of 64 MB of (r, F) data)
+    const Quad q0 = __ldg(bricks + cell), q1 = __ldg(bricks + ((cell + slice) & wrap));
+    b.t[0] = q0.x; b.t[1] = q0.y; b.t[2] = q0.z; b.t[3] = q0.w;
+    b.t[4] = q1.x; b.t[5] = q1.y; b.t[6] = q1.z; b.t[7] = q1.w;
+    return b;
+#endif
+    (void)slice; (void)wrap;
+#if MT_BRICK_EVICT_LAST   // the bricks are what every ray samples six times per in-cloud step: last to leave the L2
+    asm volatile("ld.global.nc.L2::evict_last.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+#else
     asm volatile("ld.global.nc.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+#endif
                  : "=r"(b.t[0]), "=r"(b.t[1]), "=r"(b.t[2]), "=r"(b.t[3]), "=r"(b.t[4]), "=r"(b.t[5]), "=r"(b.t[6]), "=r"(b.t[7])
                  : "l"(bricks + 2u * cell));
     return b;
@@ -484,7 +496,8 @@ MT_DEVICE StepSample cloud_step_light(const CloudParams& P, const MarchConst& M,
         LinAxis X, Y, Z;
         unsigned cell;
         cone_axes<STD>(P, M, CO, pos, relOrigin, R.stepSize, 0, sxy, sz, X, Y, Z, cell);
-        Brick cur = ldg_brick(low.rfquads, cell);
+        const unsigned wrap = (unsigned)low.w * (unsigned)low.h * (unsigned)low.d - 1u, slice = (unsigned)low.w * (unsigned)low.h;
+        Brick cur = ldg_brick(low.rfquads, cell, slice, wrap);
 #ifndef MT_CONE_UNROLL
 #define MT_CONE_UNROLL 6  /* 4K: 4.204 (1), 4.144 (2), 4.137 (3), 4.043 ms (6): no loop-carried register rotation, constant offsets */
 #endif
@@ -497,7 +510,7 @@ MT_DEVICE StepSample cloud_step_light(const CloudParams& P, const MarchConst& M,
             Brick nxt = cur;
             if (i < 5) {  // request sample i+1's brick before sample i is filtered
                 cone_axes<STD>(P, M, CO, pos, relOrigin, R.stepSize, i + 1, sxy, sz, Xn, Yn, Zn, celln);
-                nxt = ldg_brick(low.rfquads, celln);
+                nxt = ldg_brick(low.rfquads, celln, slice, wrap);
             }
             if (cur.t[0] & 1u) {  // the cell may hold cloud (flag written with the empty-cell bitmap); else the density is exactly +0
                 const Weights8 w = filter_weights(X, Y, Z);

@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(256) occupancy_build_kernel(Tex3D T, uint32_t*
         bits |= (any ? 1u : 0u) << k;
 #if MT_CONE_PIPE
         if (rfq) {  // the pipelined cone loop reads the cell's flag from the brick it has loaded: bit 0 of the first word
-            uint32_t* w0 = &rfq[2u * ((z * (unsigned)T.h + y) * (unsigned)T.w + x)].x;
+            uint32_t* w0 = &rfq[(MT_RF_BRICKS ? 2u : 1u) * ((z * (unsigned)T.h + y) * (unsigned)T.w + x)].x;
             *w0 = (*w0 & ~1u) | (any ? 1u : 0u);
         }
 #else
@@ -121,6 +121,9 @@ cudaError_t mt_launch_occupancy(const Tex3D& low, uint32_t* occ, float coverage,
 template <bool FULL, bool COUNT, bool DEBUG, bool WEATHER, bool STD>
 #ifndef MT_CLOUD_MINBLOCKS
 #define MT_CLOUD_MINBLOCKS 8  /* 64 registers/thread: 8 CTAs = 32 warps per SM (profiles/r1_cloud_ab.md) */
+#endif
+#ifndef MT_STREAM_STORES
+#define MT_STREAM_STORES 1    /* full-quality kernel: HDR / mask stores carry the evict-first hint (mt_pixel.cuh) */
 #endif
 #ifndef MT_CONE_CACHE
 #define MT_CONE_CACHE 1       /* per-ray light-cone offsets in shared memory (12 KB per CTA) */
@@ -222,10 +225,13 @@ __global__ void __launch_bounds__(128, MT_CLOUD_MINBLOCKS) cloud_raymarch_kernel
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             }
+        } else if (FULL && MT_STREAM_STORES) {
+            px_store_streaming(P.hdr, idx, h4, P.storage);
         } else {
             px_store(P.hdr, idx, h4, P.storage);
         }
-        px_store(P.mask, idx, make_float4(mask.x, mask.y, mask.z, mask.w), P.storage);
+        if (FULL && MT_STREAM_STORES) px_store_streaming(P.mask, idx, make_float4(mask.x, mask.y, mask.z, mask.w), P.storage);
+        else px_store(P.mask, idx, make_float4(mask.x, mask.y, mask.z, mask.w), P.storage);
     }
     if (FULL && !COUNT && !DEBUG && P.tileDone) {  // uniform: tell tile_forward_kernel that this CTA's pixels are in memory
         __threadfence();

@@ -51,3 +51,17 @@ __device__ __forceinline__ void px_store(void* img, size_t idx, float4 v, int st
         reinterpret_cast<float4*>(img)[idx] = v;
     }
 }
+
+// The same store with the evict-first ("streaming") hint: for the full-quality Cloud pass, whose 32 bytes per pixel (265 MB at
+// 4K) are written once and not read again by the kernel -- routed through the L2 like ordinary stores they evict the 100 MB of
+// noise copies every ray samples (ncu: 1.5 GB of DRAM reads per 4K launch with plain stores, profiles/r2_ab.md section 1).
+__device__ __forceinline__ void px_store_streaming(void* img, size_t idx, float4 v, int storage)
+{
+    if (storage == MT_PX_F16) {
+        const uint2 h = px_pack_f16(v);
+        __stcs(reinterpret_cast<uint2*>(img) + idx, h);
+    } else {
+        if (storage == MT_PX_F16_EMULATE) v = px_round_f16(v);
+        __stcs(reinterpret_cast<float4*>(img) + idx, v);
+    }
+}
