@@ -123,7 +123,7 @@ MT_DEVICE float height_gradient(float h, float cloudType)
 // (1 - coverage may be 0) applies on that path.
 // STD != 0: the textures have the reference's extents (low 128^3, high 32^3, curl 128^2: Sky.cpp:31-50), which the host checks
 // per dispatch: the extents become immediates (no constant-bank loads, shifts instead of multiplies in the addressing).
-// STD == 2 additionally selects the software-pipelined light-cone loop (one-thread-per-ray kernels: ConeOffsets.stage is set).
+// STD == 2 additionally selects the software-pipelined, unrolled light-cone loop (the one-thread-per-ray kernels).
 template <int STD>
 MT_DEVICE Tex3D std_low(const Tex3D& t)
 {
@@ -397,9 +397,6 @@ MT_DEVICE StepBase cloud_step_base(const CloudParams& P, const MarchConst& M, co
 struct ConeOffsets {
     const F4* xyz;    // this thread's first offset (x, y, z, -); the offset of sample i is xyz[i * stride]   (null: compute per step)
     int stride;
-    unsigned stage;   // shared-memory byte address of this thread's staging slots for the pipelined cone loop (0: none);
-                      // slot (s, k) = stage + (2 * s + k) * stageStride: stage s in {0, 1}, k = slice z0 / z1 quad
-    unsigned stageStride;
 };
 
 // MT_CONE_PIPE: software-pipelined light-cone loop (device only, one-thread-per-ray kernels).  A cone sample is a dependent
@@ -615,8 +612,7 @@ MT_DEVICE void cloud_composite(const RaySetup& R, float accum, float color, F4& 
 // One invocation of main(): setup, the sequential march, composite.
 template <bool COUNT, bool DEBUG, bool WEATHER, int STD>
 MT_DEVICE void cloud_ray(const CloudParams& P, const MarchConst& M, int px, int py, int pixelID, F4& hdr, F4& mask,
-                         RayCounters& cnt, MtRayDebug* dbg, F4* coneXYZ, int coneStride, unsigned coneStage = 0u,
-                         unsigned coneStageStride = 0u)
+                         RayCounters& cnt, MtRayDebug* dbg, F4* coneXYZ, int coneStride)
 {
     mask.x = mask.y = mask.z = mask.w = 0.0f;
     const RaySetup R = cloud_ray_setup(P, M, px, py, pixelID, hdr);
@@ -630,7 +626,6 @@ MT_DEVICE void cloud_ray(const CloudParams& P, const MarchConst& M, int px, int 
 
     ConeOffsets CO;
     CO.xyz = coneXYZ; CO.stride = coneStride;
-    CO.stage = coneStage; CO.stageStride = coneStageStride;
     if (coneXYZ) {
 #pragma unroll
         for (int i = 0; i < 6; ++i) {

@@ -190,7 +190,6 @@ __global__ void __launch_bounds__(128, MT_CLOUD_MINBLOCKS) cloud_raymarch_kernel
 #else
     F4* const cxyz = nullptr;
 #endif
-    const unsigned cstage = 0u, cstride = 0u;
     // staging of the bulk-store epilogue (mtSetCloudStoreMode): one 16x2 pixel tile per warp, row-major = lane order
     __shared__ __align__(128) float4 outStage[4][32];
     RayCounters cnt = { 0u, 0u, 0u, 0u, 0u, 0u };
@@ -198,8 +197,7 @@ __global__ void __launch_bounds__(128, MT_CLOUD_MINBLOCKS) cloud_raymarch_kernel
     if (valid) {
         F4 hdr, mask;
         const size_t idx = (size_t)py * (size_t)P.W + (size_t)px;
-        cloud_ray<COUNT, DEBUG, WEATHER, (STD ? (MT_CONE_PIPE ? 2 : 1) : 0)>(P, M, px, py, pixelID, hdr, mask, cnt, DEBUG ? (P.debug + idx) : nullptr, cxyz, 128,
-                                                                           cstage, cstride);
+        cloud_ray<COUNT, DEBUG, WEATHER, (STD ? (MT_CONE_PIPE ? 2 : 1) : 0)>(P, M, px, py, pixelID, hdr, mask, cnt, DEBUG ? (P.debug + idx) : nullptr, cxyz, 128);
         const float4 h4 = make_float4(hdr.x, hdr.y, hdr.z, hdr.w);
         if (bulk) {
             // The marching warp must not wait on a remote write: its 32 pixels go to shared memory, and lanes 0 and 16 each
@@ -347,7 +345,7 @@ __global__ void __launch_bounds__(128, MT_STEPS_MINBLOCKS) cloud_steps_kernel(co
     if (R.branch != 2 || k >= R.nsteps) return;
     const int jidx = (P.tm.frameCountMod16 + mt_f2i(t)) & 15;
     RayCounters none = { 0u, 0u, 0u, 0u, 0u, 0u };
-    const ConeOffsets noCache = { nullptr, 0, 0u, 0u };  // one thread per (ray, step): nothing to share
+    const ConeOffsets noCache = { nullptr, 0 };  // one thread per (ray, step): nothing to share
     const StepSample S = cloud_step_sample<false, WEATHER, STD>(P, M, R, jidx, t, none, noCache);
     *slot = make_float2(S.inc, S.energy);
 }
@@ -412,7 +410,7 @@ __global__ void __launch_bounds__(128, MT_CLOUD_MINBLOCKS) cloud_light_kernel(co
         const int jidx = (P.tm.frameCountMod16 + mt_f2i(t)) & 15;
         RayCounters none = { 0u, 0u, 0u, 0u, 0u, 0u };
         const StepBase B = cloud_step_base<false, WEATHER, STD>(P, M, R, jidx, t, none);   // same arithmetic: B.baseDensity > 0 again
-        const ConeOffsets noCache = { nullptr, 0, 0u, 0u };
+        const ConeOffsets noCache = { nullptr, 0 };
         const StepSample S = cloud_step_light<false, WEATHER, STD>(P, M, R, B, none, noCache);
         P.samples[(size_t)k * (size_t)P.rayStride + ray] = make_float2(S.inc, S.energy);
     }
@@ -539,7 +537,7 @@ __global__ void __launch_bounds__(32 * MT_S16_WARPS, MT_S16_MINBLOCKS) cloud_six
     const RaySetup& R = rays[lane];
     {   // ---- B
         const int mine = R.branch == 2 ? R.nsteps : 0;
-        const ConeOffsets noCache = { nullptr, 0, 0u, 0u };  // a thread visits ~7 steps of its ray: not worth a cache
+        const ConeOffsets noCache = { nullptr, 0 };  // a thread visits ~7 steps of its ray: not worth a cache
         RayCounters none = { 0u, 0u, 0u, 0u, 0u, 0u };
         for (int k = warp; k < nmax; k += MT_S16_WARPS) {
             if (k < mine) {

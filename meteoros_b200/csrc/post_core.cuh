@@ -117,6 +117,25 @@ MT_DEVICE float mask_texel_decode(F4 t)
 // a + ay (c - a) on both columns at once, then in x: ~19 instructions per tap instead of 31 (profiles/r2_passes_1080p.md).
 #define MT_FLOOR_MAGIC 12582912.0f     /* 1.5 * 2^23: x + MAGIC rounded down = MAGIC + floor(x) for |x| < 2^22 */
 #define MT_FLOOR_MAGIC_BITS 0x4B400000
+#ifndef MT_GODRAY_SCALAR
+#define MT_GODRAY_SCALAR 0
+#endif
+#if MT_GODRAY_SCALAR && !defined(MT_HOSTSIM)
+// A/B: the same tap with scalar instructions only (is the FMA pipe, which executes an fp32x2 instruction in two passes, the limit?)
+MT_DEVICE float mask_decode(const GodRayParams& P, P2 st)
+{
+    const float mx = lo2(st) * (float)P.W, my = hi2(st) * (float)P.H;
+    const float ux = mx - 0.5f, uy = my - 0.5f;
+    float tx, ty;
+    asm("add.rm.f32 %0, %1, %2;" : "=f"(tx) : "f"(ux), "f"(MT_FLOOR_MAGIC));
+    asm("add.rm.f32 %0, %1, %2;" : "=f"(ty) : "f"(uy), "f"(MT_FLOOR_MAGIC));
+    const float ax = ux - (tx - MT_FLOOR_MAGIC), ay = uy - (ty - MT_FLOOR_MAGIC);
+    const int i0 = (__float_as_int(ty) - MT_FLOOR_MAGIC_BITS) * (P.W + 2) + __float_as_int(tx);
+    const float2 top = MT_LDG(P.tapRow0 + i0), bot = MT_LDG(P.tapRow1 + i0);
+    const float l = fmaf(ay, bot.x - top.x, top.x), r = fmaf(ay, bot.y - top.y, top.y);
+    return fmaf(ax, r - l, l);
+}
+#else
 MT_DEVICE float mask_decode(const GodRayParams& P, P2 st)
 {
     const float2* dec = P.decoded;
@@ -155,6 +174,7 @@ MT_DEVICE float mask_decode(const GodRayParams& P, P2 st)
     const P2 lr = fma2(bc2(hi2(a1)), sub2(b2, t2), t2);           // both columns filtered in y: a + ay (c - a)
     return fmaf(lo2(a1), hi2(lr) - lo2(lr), lo2(lr));             // then in x
 }
+#endif
 
 // The radial accumulation of one fragment; returns the colour to ADD to the HDR pixel (already * blend).
 MT_DEVICE F4 godray_pixel(const GodRayParams& P, const GodRayFrame& G, int x, int y)
@@ -169,7 +189,12 @@ MT_DEVICE F4 godray_pixel(const GodRayParams& P, const GodRayFrame& G, int x, in
     // per tap instead of seven instructions; the reordering moves the result by ~1e-7 of a term that is at most 2.5 %
     // of the pixel (radiance only, no decision depends on it).
     float sum = 0.0f;
-#pragma unroll 4
+#ifndef MT_GODRAY_UNROLL
+#define MT_GODRAY_UNROLL 4
+#endif
+#define MT_GR_PRAGMA_(x) _Pragma(#x)
+#define MT_GR_UNROLL_(n) MT_GR_PRAGMA_(unroll n)
+    MT_GR_UNROLL_(MT_GODRAY_UNROLL)
     for (int i = 0; i < 100; ++i) {
         sum += mask_decode(P, uv);
         uv = sub2(uv, duv);

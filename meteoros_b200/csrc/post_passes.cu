@@ -97,9 +97,12 @@ cudaError_t mt_launch_mask_grey(const GodRayParams& P, float* out, cudaStream_t 
 #define MT_GODRAY_WW (1 << MT_GODRAY_LOG2W)
 #define MT_GODRAY_WH (32 >> MT_GODRAY_LOG2W)
 #define MT_GODRAY_CTA_W (MT_GODRAY_LOG2W == 5 ? 32 : 2 * MT_GODRAY_WW)                  /* 16, 32, 32 */
-#define MT_GODRAY_CTA_H (MT_GODRAY_LOG2W == 5 ? 4 : 2 * MT_GODRAY_WH)                   /*  8,  4,  4 */
+#ifndef MT_GODRAY_WARPS
+#define MT_GODRAY_WARPS 4   /* warps (= pixel rows for 32x1 warps) per CTA */
+#endif
+#define MT_GODRAY_CTA_H (MT_GODRAY_LOG2W == 5 ? MT_GODRAY_WARPS : 2 * MT_GODRAY_WH)     /*  8,  4,  4 */
 template <int ST>
-__global__ void __launch_bounds__(128) godrays_kernel(const __grid_constant__ GodRayParams P)
+__global__ void __launch_bounds__(MT_GODRAY_LOG2W == 5 ? 32 * MT_GODRAY_WARPS : 128) godrays_kernel(const __grid_constant__ GodRayParams P)
 {
     __shared__ GodRayFrame frame;
     if (threadIdx.x == 0) frame = godray_frame(P.cam);
@@ -184,9 +187,10 @@ cudaError_t mt_launch_godrays(const GodRayParams& P0, cudaStream_t stream)
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     dim3 grid((unsigned)((P.W + MT_GODRAY_CTA_W - 1) / MT_GODRAY_CTA_W), (unsigned)((P.H + MT_GODRAY_CTA_H - 1) / MT_GODRAY_CTA_H), 1);
-    if (P.storage == MT_PX_F16) godrays_kernel<MT_PX_F16><<<grid, 128, 0, stream>>>(P);
-    else if (P.storage == MT_PX_F16_EMULATE) godrays_kernel<MT_PX_F16_EMULATE><<<grid, 128, 0, stream>>>(P);
-    else godrays_kernel<MT_PX_F32><<<grid, 128, 0, stream>>>(P);
+    const unsigned threads = MT_GODRAY_LOG2W == 5 ? 32 * MT_GODRAY_WARPS : 128;
+    if (P.storage == MT_PX_F16) godrays_kernel<MT_PX_F16><<<grid, threads, 0, stream>>>(P);
+    else if (P.storage == MT_PX_F16_EMULATE) godrays_kernel<MT_PX_F16_EMULATE><<<grid, threads, 0, stream>>>(P);
+    else godrays_kernel<MT_PX_F32><<<grid, threads, 0, stream>>>(P);
     return cudaGetLastError();
 }
 cudaError_t mt_launch_tonemap(const ToneMapParams& P, cudaStream_t stream)

@@ -97,7 +97,7 @@ int hs_cloud(const MtCameraUBO* cam, const MtTimeUBO* tm, const MtTuning* tun, c
                     R.nsteps = n;
                     StepSample S[MT_STEP_SLICES];
                     RayCounters none = { 0, 0, 0, 0, 0, 0 };
-                    const ConeOffsets noCache = { nullptr, 0, 0u, 0u };
+                    const ConeOffsets noCache = { nullptr, 0 };
                     for (int k = n - 1; k >= 0; --k) {
                         const int jidx = (P.tm.frameCountMod16 + mt_f2i(tk[k])) & 15;
                         S[k] = tun->use_weather ? cloud_step_sample<false, true, 0>(P, M, R, jidx, tk[k], none, noCache)

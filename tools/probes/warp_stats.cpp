@@ -124,7 +124,7 @@ extern "C" int ws_run(const MtCameraUBO* cam, const MtTimeUBO* tm, const MtTunin
                                     if (cur > 0.0f) cone_h[i]++;
                                 }
                             }
-                            { const ConeOffsets noCache = { nullptr, 0, 0u, 0u }; smp = cloud_step_light<false, false, false>(P, M, R[l], B, none, noCache); }
+                            { const ConeOffsets noCache = { nullptr, 0 }; smp = cloud_step_light<false, false, false>(P, M, R[l], B, none, noCache); }
                         }
                         if (cloud_step_combine(smp, accum[l], tr[l], col[l])) { live[l] = false; early[l] = true; }
                         else {
