@@ -46,6 +46,7 @@ MT_DEVICE void cloud_frame_setup(const CamU& cam, const TimeU& tm, const MtTunin
     m.windSkew = ((wind + mk3(0.0f, 0.1f, 0.0f)) * tun.cloud_speed) * tm.time[1];
     m.covDen = 1.0f - tun.coverage;
     m.covRcp = nice_rcp(m.covDen);
+    m.covScale = tun.coverage / m.covDen;  // coverage in [0, 0.91]
 }
 
 // The two Halton look-ups of the shader (getJitterOffset, cloudRayMarch.comp:114-132) have only eight distinct
@@ -196,6 +197,42 @@ MT_DEVICE float cone_density_rf(const CloudParams& P, const MarchConst& M, float
     if (!(base > coverage)) return 0.0f;
     return sat1(div_nice_r(base - coverage, M.covDen, M.covRcp)) * coverage;
 }
+MT_DEVICE float erode(float base, float edge) { return div_nice(base - edge, 1.0f - edge); }  // remap(base, edge, 1, 0, 1); edge in [0, 0.005]
+// The whole contribution of one light-cone sample to the cone density, erode(1.5 * density, edge) or 0 (cloudRayMarch.comp:
+// 658-667), from its filtered (r, fbm) pair.  Radiance only, so outside the guard band nothing here needs the canonical
+// roundings: the threshold test base > coverage is taken in its division-free form q > coverage * d (q = r - (fbm - .9),
+// d = 1.9 - fbm > 0), the base density is q * rcp(d) with the SFU reciprocal, the coverage remap is one multiplication by
+// coverage / (1 - coverage) (no clamp: base <= 1) and the erosion remap one FMA-style pair with the step's reciprocal of
+// 1 - edge -- about 15 instructions instead of 29.  Inside the guard band (|q - coverage * d| <= MT_RF_GUARD * d, i.e. the base
+// density within 8e-6 of the threshold, four times what the (r, F) filter and this arithmetic can be off by) the canonical
+// four-channel evaluation decides AND supplies the value.  `hit` = the canonical `density > 0`.
+template <int STD>
+MT_DEVICE float cone_term_rf(const CloudParams& P, const MarchConst& M, float coverage, P2 rf, const LinAxis& X, const LinAxis& Y,
+                             const LinAxis& Z, unsigned cell, float edge, float edgeRcp, bool& hit)
+{
+    const float fbm = sat1(hi2(rf));
+    const float omin = fbm - 0.9f;
+    const float d = 1.0f - omin, q = lo2(rf) - omin;
+    const float diff = q - coverage * d;
+    if (fabsf(diff) <= MT_RF_GUARD * d) {  // too close to call: the canonical evaluation, values included
+        const float dens = cone_density_rf<STD>(P, M, coverage, rf, X, Y, Z, cell);
+        hit = dens > 0.0f;
+        return hit ? erode(1.5f * dens, edge) : 0.0f;
+    }
+    hit = false;
+    if (!(diff > 0.0f)) return 0.0f;
+#if defined(MT_HOSTSIM)
+    const float base = fminf(q / d, 1.0f);
+#else
+    float rd;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rd) : "f"(d));
+    const float base = fminf(q * rd, 1.0f);
+#endif
+    const float dens = (base - coverage) * M.covScale;
+    hit = dens > 0.0f;  // coverage == 0 scales every density to 0: no hit, as in the shader
+    return hit ? (1.5f * dens - edge) * edgeRcp : 0.0f;
+}
+
 // The part of erodeCloudWithHighFrequency (cloudRayMarch.comp:542-563) that depends only on the march sample:
 // returns high_freq_modifier * 0.005, the lower edge of the final remap.
 MT_DEVICE float erosion_edge(const Tex2D& curl, const Tex3D& high, f3 p, float h)
@@ -209,7 +246,6 @@ MT_DEVICE float erosion_edge(const Tex2D& curl, const Tex3D& high, f3 p, float h
     float m = sat1(mix1(fbm, 1.0f - fbm, sat1(h * 2.0f)));
     return m * 0.005f;
 }
-MT_DEVICE float erode(float base, float edge) { return div_nice(base - edge, 1.0f - edge); }  // remap(base, edge, 1, 0, 1); edge in [0, 0.005]
 
 // GetLightEnergy (cloudRayMarch.comp:331-388), live branch only.
 // Radiance only (no decision reads it): the three remaps divide by constants (1 - 0.7, 0.85 - 0.3, 0.34 - 0.07), written as
@@ -485,6 +521,7 @@ MT_DEVICE StepSample cloud_step_light(const CloudParams& P, const MarchConst& M,
     float edge = erosion_edge(std_curl<STD>(P.curl), std_high<STD>(P.high), skew, h);
     S.inc = erode(baseDensity * 1.4f, edge) * 0.5f;
     float dl = 0.0f;
+    const float edgeRcp = nice_rcp(1.0f - edge);  // the step's erosion divisor, shared by the six cone samples (radiance only)
 #if !defined(MT_HOSTSIM) && MT_CONE_PIPE
     if (STD == 2 && MT_CONE_RF && !WEATHER) {  // STD kernels are only launched with the (r, F) bricks present (mt_std_dims)
         const Tex3D low = std_low<STD>(P.low);
@@ -514,11 +551,10 @@ MT_DEVICE StepSample cloud_step_light(const CloudParams& P, const MarchConst& M,
                 const uint32_t t000 = cur.t[0], t001 = cur.t[1], t010 = cur.t[2], t011 = cur.t[3], t100 = cur.t[4], t101 = cur.t[5],
                                t110 = cur.t[6], t111 = cur.t[7];
                 const P2 rf = mul2(MT_ACC2(MT_RFP), bc2(MT_INV255));
-                const float dens = cone_density_rf<STD>(P, M, coverage, rf, X, Y, Z, cell);
-                if (dens > 0.0f) {
-                    if (COUNT) cnt.cone++;
-                    dl += erode(1.5f * dens, edge);
-                }
+                bool hit;
+                const float term = cone_term_rf<STD>(P, M, coverage, rf, X, Y, Z, cell, edge, edgeRcp, hit);
+                if (COUNT && hit) cnt.cone++;
+                dl += term;  // + 0 where the sample holds no cloud: the same sum
             }
             X = Xn; Y = Yn; Z = Zn; cell = celln; cur = nxt;
         }
@@ -532,6 +568,16 @@ MT_DEVICE StepSample cloud_step_light(const CloudParams& P, const MarchConst& M,
             LinAxis X, Y, Z;
             unsigned cell;
             float cur;
+            if (STD && MT_CONE_RF && !WEATHER && !MT_HW_FILTER) {  // the plain (r, F) loop: the same per-sample term as the pipelined one
+                cone_axes<STD>(P, M, CO, pos, relOrigin, R.stepSize, i, sxy, sz, X, Y, Z, cell);
+                const Tex3D low = std_low<STD>(P.low);
+                if (!low.occ || occ_cell_may_be_cloud(low, cell)) {
+                    bool hit;
+                    dl += cone_term_rf<STD>(P, M, coverage, tex3d_rf_axes(low, X, Y, Z, cell), X, Y, Z, cell, edge, edgeRcp, hit);
+                    if (COUNT && hit) cnt.cone++;
+                }
+                continue;
+            }
 #if MT_HW_FILTER && !defined(MT_HOSTSIM)
             if (STD && !WEATHER) {  // A/B: the texture unit filters the cone sample (profiles/r2_ab.md); same empty-cell test
                 cone_axes<STD>(P, M, CO, pos, relOrigin, R.stepSize, i, sxy, sz, X, Y, Z, cell);

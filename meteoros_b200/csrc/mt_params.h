@@ -57,6 +57,7 @@ struct MarchConst {
     float rayJitter[8][2];              // getJitterOffset(id, dim): (halton_x / W, halton_y / H) for id/2 = 0..7
     float stepJitter[8][4];             // per-step direction offset (jx, (jx+jy)*1.18, jy, 0), j = halton / 75
     float covDen, covRcp;               // 1 - coverage and its refined reciprocal (nice_rcp): divisor of the coverage remap
+    float covScale;                     // coverage / (1 - coverage): the coverage remap of a light-cone sample as one multiplication
 };
 #define MT_MARCHCONST_WORDS (sizeof(MarchConst) / 4)
 
