@@ -1,19 +1,24 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the cloud hot path (BASELINE.json: raymarched Mrays/s at 3840x2160).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cloud4k|frame8k|seq1080p]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cloud4k|frame8k|seq1080p|views256]
 
 A step = one full-quality Cloud pass (mtDispatchCloudFull: all sixteen pixel ids, max steps, full light cone, no
 reprojection) over one synthetic 3840x2160 frame of the default cloudscape = 8 294 400 rays (BASELINE config 3).
   value  device-timed Mrays/s: CUDA events on the context's stream around each dispatch, inputs resident in HBM,
          L2 evicted between steps (mtFlushL2 writes 256 MiB), summed over exactly K steps, max over ranks.
-  e2e    the same metric through the public C-ABI call sequence with host buffers: uniforms from host memory in, the
-         RGBA32F HDR frame read back into pinned host memory, every step, wall-clock between synchronisations.
+  e2e    the same metric through the public C-ABI call sequence with host buffers: uniforms from host memory in; the
+         RGBA32F HDR frame AND the god-ray image (one float per pixel, mtReadGodRayGreyAsync) read back into pinned host
+         memory, every step, wall-clock between synchronisations.  e2e_f16: the same with RGBA16F images (MT_STORAGE_F16,
+         the reference's own image format).
   N > 1  weak scaling, no data-path collective: every rank renders its own copy of the 4K frame (independent views,
-         BASELINE config 5 style; --sweep varies sun elevation / coverage per rank); value = N * rays / max-over-ranks time.  `--workload frame8k` instead shards
-         ONE 7680x4320 frame by cyclic 32-row tiles with stores straight into GPU 0's image over NVLink (config 4).
+         BASELINE config 5 style; --sweep varies sun elevation / coverage per rank); value = N * rays / max-over-ranks time.
+         The same line carries `sharded_8k` (and `sharded_8k_f16`): ONE 7680x4320 frame cut into cyclic 8-row tiles over the
+         ranks, HDR tiles stored straight into GPU 0's image over NVLink by the march kernel (BASELINE config 4), timed
+         against the same frame on rank 0 alone in the same run, gathered frame compared bit for bit with the single-GPU
+         frame.  `--workload frame8k` runs only that, with --gather / --tile-rows variants.
   --impl reference   the reference's Cloud shader compiled for the CPU from its own text (oracle/_ref; else the oracle
-                     restatement), OpenMP over all host cores, on a bounded,
+         restatement), OpenMP over all host cores (team size set explicitly and reported as measured), on a bounded,
          evenly spread sample of the same frame: the reference's own path needs Vulkan + a window.
 Rank 0 prints ONE JSON line.
 """
@@ -239,6 +244,46 @@ def run_reference(args, rank, world):
     emit(line)  # the process's real stdout (quiet_stdout rerouted fd 1 to stderr for library chatter)
 
 
+def views256_record(args, api, sharding, torch, dist, world, rank, local_rank, noise, batches=3):
+    """BASELINE config 5 beside the headline: 256 full-quality 1920x1080 views -- 16 sun elevations x 16 coverages -- round-robin
+    over the ranks, no communication.  Device-timed per batch (events on each rank's stream), max over ranks.  Every change of
+    coverage rebuilds the empty-cell bitmap (and the cell flags inside the (r, F) bricks) on the device, inside the timed region."""
+    w, h = 1920, 1080
+    cam, tm, sky, _ = scene_for_view(0, w, h)
+    mine = [scene_for_view(v, w, h, sweep=True)[3] for v in sharding.views_of_rank(256, world, rank)]
+    r = api.CloudRenderer(w, h, device=local_rank, storage=args.storage)
+    r.upload_noise(noise)
+    r.set_camera(cam); r.set_camera_old(cam); r.set_time(tm); r.set_sun_and_sky(sky)
+
+    def batch():
+        for vt in mine:
+            r.set_tuning(vt)
+            r.dispatch_cloud_full()
+
+    batch()
+    r.synchronize()
+    ms = []
+    for _ in range(batches):
+        if dist is not None:
+            torch.cuda.synchronize()
+            dist.barrier()
+        r.event_record(4)
+        batch()
+        r.event_record(5)
+        ms.append(r.event_elapsed_ms(4, 5))
+    r.close()
+    t_ms = float(statistics.mean(ms))
+    if dist is not None:
+        t = torch.tensor([t_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_ms = float(t[0])
+    if rank != 0:
+        return None
+    return {"workload": "256 full-quality 1920x1080 views: 16 sun elevations (5..85 deg) x 16 coverages (0.3..0.9), round-robin over the ranks (BASELINE config 5)",
+            "ms_per_batch": round(t_ms, 3), "ms_per_view": round(t_ms / (256 / world), 4), "mrays_per_s": round(256 * w * h / (t_ms * 1e-3) / 1e6, 1),
+            "views_per_rank": 256 // world, "batches": batches, "scaling": "strong"}
+
+
 def sharded_8k_record(args, api, sharding, torch, dist, world, rank, local_rank, noise, steps, storage=None):
     """BASELINE config 4 beside the N>1 views line: ONE 7680x4320 full-quality frame cut into cyclic row tiles over the
     ranks and gathered on GPU 0 over NVLink, timed like the headline (events on each rank's stream, L2 flushed, max over
@@ -370,6 +415,7 @@ def main():
                          "timed at 8 GPUs), or (diagnostic) no gather at all")
     ap.add_argument("--gather-mask", action="store_true", help="frame8k: also send the god-ray mask tiles to GPU 0 (needed only if god rays run)")
     ap.add_argument("--sweep", action="store_true", help="N>1: rank r renders view r of the sun/coverage sweep")
+    ap.add_argument("--no-views256", action="store_true", help="default workload: skip the views256 sub-record (config 5)")
     ap.add_argument("--no-sharded-8k", action="store_true", help="N>1 default workload: skip the sharded_8k sub-record (config 4)")
     ap.add_argument("--storage", type=int, default=0, help="image storage: 0 = RGBA32F (default), 1 = binary16-rounded values in RGBA32F")
     args = ap.parse_args()
@@ -646,6 +692,11 @@ def main():
         shard.close()
     sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
     r.close()
+
+    if args.workload == "cloud4k" and not args.no_views256:
+        rec = views256_record(args, api, sharding, torch, dist if world > 1 else None, world, rank, local_rank, noise)
+        if rank == 0:
+            line["views256"] = rec
 
     if world > 1 and args.workload == "cloud4k" and not args.no_sharded_8k:
         rec = sharded_8k_record(args, api, sharding, torch, dist, world, rank, local_rank, noise, steps=max(args.steps, 10))

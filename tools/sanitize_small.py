@@ -54,3 +54,35 @@ with api.CloudRenderer(w, h) as r:  # weather variants of the march kernels
     r.dispatch_cloud()
     r.dispatch_cloud_full()
     print("weather mean", float(np.nanmean(r.read_image(api.IMAGE_CLOUD_CUR))))
+# round 2: RGBA16F storage through every pass, the bulk-store epilogue, the forwarder, the one-float god-ray read-back, the
+# three-kernel 1-of-16 form (MT_FLAG_SPLIT_MARCH) and the canonical cone filter (MT_FLAG_NO_CONE_RF)
+for storage in (api.STORAGE_F16, api.STORAGE_F16_EMULATE):
+    with api.CloudRenderer(w, h, storage=storage) as r, api.CloudRenderer(w, h, storage=storage) as peer:
+        r.upload_noise(textures.load_noise())
+        r.set_sun_and_sky(sky.ubo())
+        for f in range(2):
+            cam.rotate_about_up(0.25)
+            sc.update_time(1 / 60)
+            r.set_camera(cam.ubo()); r.set_camera_old(old); r.set_time(sc.ubo())
+            r.frame(True, True)
+            old = cam.ubo()
+        r.set_cloud_store_mode(api.STORE_BULK)
+        r.dispatch_cloud_full()
+        r.set_cloud_output(peer.image_device_ptr(api.IMAGE_CLOUD_CUR), None)
+        r.dispatch_cloud_tiles(8, 0, 9, 1)
+        r.set_cloud_output(None, None)
+        r.set_cloud_store_mode(api.STORE_DIRECT)
+        if w % 2 == 0 or storage != api.STORAGE_F16:
+            r.set_cloud_forward(peer.image_device_ptr(api.IMAGE_CLOUD_PREV))
+            r.dispatch_cloud_tiles(8, 0, 9, 1)
+            r.join_copies(); r.synchronize()
+            r.set_cloud_forward(None)
+        print("grey mean", float(r.read_godray_grey().mean()), "storage", storage)
+for flags in (api.FLAG_SPLIT_MARCH, api.FLAG_NO_CONE_RF, api.FLAG_TOP_DOWN | api.FLAG_NO_FUSED_TONEMAP):
+    with api.CloudRenderer(w, h, flags=flags) as r:
+        r.upload_noise(textures.load_noise())
+        r.set_sun_and_sky(sky.ubo())
+        r.set_camera(cam.ubo()); r.set_camera_old(old); r.set_time(sc.ubo())
+        r.frame(True, True)
+        r.dispatch_cloud_full()
+        print("flags", flags, "mean", float(np.nanmean(r.read_image(api.IMAGE_CLOUD_CUR))))
