@@ -10,6 +10,9 @@ has, are stored too).  The fixtures travel to the GPU box; the reference does no
   cloud_64x36.npz          one full-quality cloud frame (all 16 pixel ids): HDR, god-ray mask, per-ray records
   sequence_96x54.npz       4 frames of REPROJ, CLOUD, GODRAYS, TONEMAP with a 0.25 degree pan (main.cpp:172-194)
   live_sequence_96x54.npz  16 frames of all five shaders chained: REPROJ, CLOUD, GODRAYS, TONEMAP, TXAA
+  cloud_fullsize_digests.npz  the full-quality cloud frame at BASELINE's own sizes (1920x1080 and 3840x2160) as digests small enough
+                           to commit: CRC-32 of every pixel row of the god-ray mask and of alpha (bit-exact quantities), every
+                           8th / 16th pixel of the HDR colour, and float64 row sums of the HDR colour
 """
 import sys
 from pathlib import Path
@@ -70,6 +73,18 @@ def frame_loop(n_frames, w, h, noise, with_txaa):
     return out
 
 
+def frame_digests(hdr, mask, sub):
+    """What tests/test_gpu_fullsize.py::test_reference_shader_digests_at_full_size recomputes from the CUDA frame."""
+    import zlib
+
+    return {
+        "mask_crc": np.array([zlib.crc32(np.ascontiguousarray(mask[y]).tobytes()) for y in range(mask.shape[0])], np.uint32),
+        "alpha_crc": np.array([zlib.crc32(np.ascontiguousarray(hdr[y, :, 3]).tobytes()) for y in range(hdr.shape[0])], np.uint32),
+        "hdr_sub": np.ascontiguousarray(hdr[::sub, ::sub, :3]),
+        "hdr_rowsum": hdr[..., :3].astype(np.float64).sum(axis=1),
+    }
+
+
 def main():
     if not refshaders.available():
         raise SystemExit("the reference tree is not present: fixtures can only be minted where /root/reference exists")
@@ -92,6 +107,16 @@ def main():
     s = frame_loop(16, 96, 54, noise, with_txaa=True)
     np.savez_compressed(gold / "live_sequence_96x54.npz", txaa=np.stack(s["txaa"]), ldr=np.stack(s["ldr"]),
                         hdr_last=s["hdr"][-1], hdr_first=s["hdr"][0], mask_last=s["mask"], source=SOURCE)
+    out = {"source": SOURCE}
+    for (w, h, sub) in ((1920, 1080, 8), (3840, 2160, 16)):
+        cam, tm, sky, tun = default_scene(w, h)
+        ref = refshaders.cloud_full(cam, tm, sky, noise, w, h)
+        r = oracle.cloud(cam, tm, tun, noise, w, h, full=True)
+        same(ref["hdr"], r["hdr"], f"{w}x{h} HDR"); same(ref["mask"], r["mask"], f"{w}x{h} mask")
+        for k, v in frame_digests(ref["hdr"], ref["mask"], sub).items():
+            out[f"{k}_{w}x{h}"] = v
+        out[f"sub_{w}x{h}"] = sub
+    np.savez_compressed(gold / "cloud_fullsize_digests.npz", **out)
     print("goldens written from the reference shaders")
 
 

@@ -179,3 +179,31 @@ def test_config5_sweep_views_1080p(api, oracle_mod, noise, view):
         r.dispatch_cloud_full()
         e = check_frame(r.read_image(api.IMAGE_CLOUD_CUR), r.read_image(api.IMAGE_GODRAY_MASK), ref, f"view {view}")
     print(f"view {view}: coverage {float(tun['coverage']):.2f}, HDR max rel err {e:.2e}")
+
+
+@pytest.mark.parametrize("w,h", [(1920, 1080), (3840, 2160)])
+def test_reference_shader_digests_at_full_size(api, noise, w, h):
+    """The CUDA frame against the REFERENCE'S OWN Cloud shader at BASELINE's sizes, without the oracle in between:
+    tests/golden/cloud_fullsize_digests.npz was written by cloudRayMarch.comp compiled from its text (make_goldens.py; the
+    full frames are 66 / 265 MB, so what is committed is a CRC-32 of every pixel row of the god-ray mask and of alpha -- the
+    bit-exact quantities -- every 8th / 16th pixel of the colour, and float64 row sums of the colour)."""
+    import pathlib
+    import zlib
+
+    g = np.load(pathlib.Path(__file__).parent / "golden" / "cloud_fullsize_digests.npz")
+    sub = int(g[f"sub_{w}x{h}"])
+    cam, tm, _, tun = default_scene(w, h)
+    with make_renderer(api, noise, w, h) as r:
+        r.set_camera(cam); r.set_time(tm); r.set_tuning(tun)
+        r.dispatch_cloud_full()
+        hdr, mask = r.read_image(api.IMAGE_CLOUD_CUR), r.read_image(api.IMAGE_GODRAY_MASK)
+    mask_crc = np.array([zlib.crc32(mask[y].tobytes()) for y in range(h)], np.uint32)
+    alpha_crc = np.array([zlib.crc32(np.ascontiguousarray(hdr[y, :, 3]).tobytes()) for y in range(h)], np.uint32)
+    assert np.array_equal(mask_crc, g[f"mask_crc_{w}x{h}"]), "god-ray mask: some pixel row differs from the reference shader's"
+    assert np.array_equal(alpha_crc, g[f"alpha_crc_{w}x{h}"])
+    want = g[f"hdr_sub_{w}x{h}"]
+    e = rel_err(hdr[::sub, ::sub, :3], want)
+    assert e.max() <= HDR_MAX_REL and psnr(hdr[::sub, ::sub, :3], want) >= HDR_MIN_PSNR
+    rows = hdr[..., :3].astype(np.float64).sum(axis=1)
+    assert np.allclose(rows, g[f"hdr_rowsum_{w}x{h}"], rtol=1e-5, atol=1e-7)   # every pixel enters a row sum
+    print(f"{w}x{h}: mask + alpha rows CRC-equal to the reference shader, sampled HDR max rel err {e.max():.2e}")

@@ -368,3 +368,24 @@ def test_density_height_gradient_known_answers(oracle_mod):
     rng = np.random.default_rng(5)
     for h, ct in rng.random((200, 2)):
         assert g(h, ct) == pytest.approx(ref(h, ct), abs=2e-6)
+
+
+def test_golden_fullsize_digests_1080p(oracle_mod, noise):
+    """The oracle against the digests the reference's Cloud shader left of its 1920x1080 frame (tests/golden/
+    cloud_fullsize_digests.npz, written by make_goldens.py where /root/reference exists): mask and alpha rows CRC-equal,
+    sampled colour and row sums equal bit for bit (the oracle is an op-for-op restatement)."""
+    import pathlib
+    import zlib
+
+    from conftest import default_scene
+
+    w, h = 1920, 1080
+    g = np.load(pathlib.Path(__file__).parent / "golden" / "cloud_fullsize_digests.npz")
+    cam, tm, _, tun = default_scene(w, h)
+    r = oracle_mod.cloud(cam, tm, tun, noise, w, h, full=True)
+    sub = int(g[f"sub_{w}x{h}"])
+    assert np.array_equal(np.array([zlib.crc32(r["mask"][y].tobytes()) for y in range(h)], np.uint32), g[f"mask_crc_{w}x{h}"])
+    assert np.array_equal(np.array([zlib.crc32(np.ascontiguousarray(r["hdr"][y, :, 3]).tobytes()) for y in range(h)], np.uint32),
+                          g[f"alpha_crc_{w}x{h}"])
+    assert np.array_equal(r["hdr"][::sub, ::sub, :3], g[f"hdr_sub_{w}x{h}"])
+    assert np.array_equal(r["hdr"][..., :3].astype(np.float64).sum(axis=1), g[f"hdr_rowsum_{w}x{h}"])
