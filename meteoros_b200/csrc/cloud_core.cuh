@@ -20,8 +20,8 @@ struct RayCounters {
     unsigned rays, marched, steps, incloud, cone, early;
 };
 
-// cloud_setup: the per-frame MarchConst (cloudRayMarch.comp:199-207, 585-624, 489-497).
-MT_DEVICE void cloud_frame_setup(const CamU& cam, const TimeU& tm, const MtTuning& tun, MarchConst& m)
+// cloud_frame_setup (host, per dispatch; hostsim): the per-frame MarchConst (cloudRayMarch.comp:199-207, 585-624, 489-497).
+MT_HD void cloud_frame_setup(const CamU& cam, const TimeU& tm, const MtTuning& tun, MarchConst& m)
 {
     RayBasis b = ray_basis(cam);
     m.basisRight = b.right;
@@ -45,13 +45,12 @@ MT_DEVICE void cloud_frame_setup(const CamU& cam, const TimeU& tm, const MtTunin
     f3 wind = mk3(tun.wind_direction[0], tun.wind_direction[1], tun.wind_direction[2]);
     m.windSkew = ((wind + mk3(0.0f, 0.1f, 0.0f)) * tun.cloud_speed) * tm.time[1];
     m.covDen = 1.0f - tun.coverage;
-    m.covRcp = nice_rcp(m.covDen);
     m.covScale = tun.coverage / m.covDen;  // coverage in [0, 0.91]
 }
 
 // The two Halton look-ups of the shader (getJitterOffset, cloudRayMarch.comp:114-132) have only eight distinct
 // results per frame each; tabulate them so that the march loop does no division and no divergent constant fetch.
-MT_DEVICE void cloud_frame_jitter(const TimeU& tm, int W, int H, MarchConst& m)
+MT_HD void cloud_frame_jitter(const TimeU& tm, int W, int H, MarchTabs& m)
 {
     for (int hj = 0; hj < 8; ++hj) {
         int hx = hj < 4 ? hj : hj + 4;  // haltonSeq1/2 for index < 4, haltonSeq3/4 otherwise
@@ -125,6 +124,8 @@ MT_DEVICE float height_gradient(float h, float cloudType)
 // STD != 0: the textures have the reference's extents (low 128^3, high 32^3, curl 128^2: Sky.cpp:31-50), which the host checks
 // per dispatch: the extents become immediates (no constant-bank loads, shifts instead of multiplies in the addressing).
 // STD == 2 additionally selects the software-pipelined, unrolled light-cone loop (the one-thread-per-ray kernels).
+// the STD kernels floor their filter coordinates with the magic constant (mt_tex.cuh); the host launches them only inside its range
+#define MT_STD_MAGIC(STD) ((STD) != 0 && MT_MAGIC_FLOOR != 0)
 template <int STD>
 MT_DEVICE Tex3D std_low(const Tex3D& t)
 {
@@ -148,16 +149,33 @@ MT_DEVICE Tex2D std_curl(const Tex2D& t)
 }
 
 template <bool WEATHER, int STD>
-MT_DEVICE float low_freq_density(const CloudParams& P, const MarchConst& M, float coverage, P2 pxy, float pz, float ux, float uz, float relH)
+MT_DEVICE float low_freq_density(const CloudParams& P, const MarchConst& M, float covRcp, float coverage, P2 pxy, float pz, float ux, float uz, float relH)
 {
     const Tex3D low = std_low<STD>(P.low);
-    LinAxis X, Y, Z = lin_axis_repeat(pz, low.d);
-    lin_axes_xy(pxy, low.w, low.h, X, Y);
+    LinAxis X, Y, Z = lin_axis_repeat<MT_STD_MAGIC(STD)>(pz, low.d);
+    lin_axes_xy<MT_STD_MAGIC(STD)>(pxy, low.w, low.h, X, Y);
     const unsigned cell = tex_cell(low, X.i0, Y.i0, Z.i0);
     // provably empty filter cell: the result is exactly +0.  A warp whose lanes all sit in empty cells skips the
     // whole fetch + filter (SIMT: the branch is free when nobody takes it).
+#if MT_TEX_QUADS && !MT_TEX_BRICKS && !defined(MT_HOSTSIM)
+    Rgba n;
+    if (STD == 3 && !WEATHER && low.occ) {
+        // latency-bound callers (the step-parallel 1-of-16 kernel): the cell's quads are requested TOGETHER with its bitmap word
+        // instead of after it -- one memory round trip per march sample instead of two, at the price of 32 unused bytes for an
+        // empty cell
+        const uint32_t word = MT_LDG(low.occ + (cell >> 5));
+        const Quad q0 = MT_LDG_QUAD(low.quads + cell);
+        const Quad q1 = MT_LDG_QUAD(low.quads + ((cell + 128u * 128u) & (128u * 128u * 128u - 1u)));
+        if (!((word >> (cell & 31u)) & 1u)) return 0.0f;
+        n = tex3d_rgba_quads(q0, q1, X, Y, Z);
+    } else {
+        if (!WEATHER && low.occ && !occ_cell_may_be_cloud(low, cell)) return 0.0f;
+        n = tex3d_rgba_axes(low, X, Y, Z, cell);
+    }
+#else
     if (!WEATHER && low.occ && !occ_cell_may_be_cloud(low, cell)) return 0.0f;
     Rgba n = tex3d_rgba_axes(low, X, Y, Z, cell);
+#endif
     float fbm = sat1((n.g * 0.625f + n.b * 0.25f) + n.a * 0.125f);
     float omin = fbm - 0.9f;
     float base = sat1(div_nice(n.r - omin, 1.0f - omin));  // remapClamped(r, fbm-.9, 1, 0, 1); denominator in [0.9, 1.9]
@@ -171,7 +189,7 @@ MT_DEVICE float low_freq_density(const CloudParams& P, const MarchConst& M, floa
     }
     // remapClampedBeforeAndAfter(base, cov, 1, 0, 1) * cov.  base <= cov clamps to cov and yields exactly +0.
     if (!(base > coverage)) return 0.0f;
-    float b = sat1(div_nice_r(base - coverage, M.covDen, M.covRcp));  // coverage in [0, 0.91] (mtSetTuning); divisor prepared per frame
+    float b = sat1(div_nice_r(base - coverage, M.covDen, covRcp));  // coverage in [0, 0.91] (mtSetTuning); reciprocal prepared per ray
     return b * coverage;
 }
 
@@ -182,7 +200,7 @@ MT_DEVICE float low_freq_density(const CloudParams& P, const MarchConst& M, floa
 // differ by rounding (< 4e-6 relative in the density, < 1e-5 in a pixel against the 1e-3 bar).
 // density of a cone sample from its filtered (r, fbm) pair; `exact` re-evaluates through the canonical filter inside the guard band
 template <int STD>
-MT_DEVICE float cone_density_rf(const CloudParams& P, const MarchConst& M, float coverage, P2 rf, const LinAxis& X, const LinAxis& Y,
+MT_DEVICE float cone_density_rf(const CloudParams& P, const MarchConst& M, float covRcp, float coverage, P2 rf, const LinAxis& X, const LinAxis& Y,
                                 const LinAxis& Z, unsigned cell)
 {
     float fbm = sat1(hi2(rf));  // F sits three bits lower than r in its word: the common 2^13 / 255 already divides it by 8
@@ -195,7 +213,7 @@ MT_DEVICE float cone_density_rf(const CloudParams& P, const MarchConst& M, float
         base = sat1(div_nice(n.r - omin, 1.0f - omin));
     }
     if (!(base > coverage)) return 0.0f;
-    return sat1(div_nice_r(base - coverage, M.covDen, M.covRcp)) * coverage;
+    return sat1(div_nice_r(base - coverage, M.covDen, covRcp)) * coverage;
 }
 MT_DEVICE float erode(float base, float edge) { return div_nice(base - edge, 1.0f - edge); }  // remap(base, edge, 1, 0, 1); edge in [0, 0.005]
 // The whole contribution of one light-cone sample to the cone density, erode(1.5 * density, edge) or 0 (cloudRayMarch.comp:
@@ -207,7 +225,7 @@ MT_DEVICE float erode(float base, float edge) { return div_nice(base - edge, 1.0
 // density within 8e-6 of the threshold, four times what the (r, F) filter and this arithmetic can be off by) the canonical
 // four-channel evaluation decides AND supplies the value.  `hit` = the canonical `density > 0`.
 template <int STD>
-MT_DEVICE float cone_term_rf(const CloudParams& P, const MarchConst& M, float coverage, P2 rf, const LinAxis& X, const LinAxis& Y,
+MT_DEVICE float cone_term_rf(const CloudParams& P, const MarchConst& M, float covRcp, float coverage, P2 rf, const LinAxis& X, const LinAxis& Y,
                              const LinAxis& Z, unsigned cell, float edge, float edgeRcp, bool& hit)
 {
     const float fbm = sat1(hi2(rf));
@@ -215,7 +233,7 @@ MT_DEVICE float cone_term_rf(const CloudParams& P, const MarchConst& M, float co
     const float d = 1.0f - omin, q = lo2(rf) - omin;
     const float diff = q - coverage * d;
     if (fabsf(diff) <= MT_RF_GUARD * d) {  // too close to call: the canonical evaluation, values included
-        const float dens = cone_density_rf<STD>(P, M, coverage, rf, X, Y, Z, cell);
+        const float dens = cone_density_rf<STD>(P, M, covRcp, coverage, rf, X, Y, Z, cell);
         hit = dens > 0.0f;
         return hit ? erode(1.5f * dens, edge) : 0.0f;
     }
@@ -235,13 +253,14 @@ MT_DEVICE float cone_term_rf(const CloudParams& P, const MarchConst& M, float co
 
 // The part of erodeCloudWithHighFrequency (cloudRayMarch.comp:542-563) that depends only on the march sample:
 // returns high_freq_modifier * 0.005, the lower edge of the final remap.
+template <bool MAGIC>
 MT_DEVICE float erosion_edge(const Tex2D& curl, const Tex3D& high, f3 p, float h)
 {
     float cr, cg;
-    tex2d_rg(curl, p.x, p.y, cr, cg);
+    tex2d_rg<MAGIC>(curl, p.x, p.y, cr, cg);
     float px = p.x + (cr * (1.0f - h)) * 0.5f;
     float py = p.y + (cg * (1.0f - h)) * 0.5f;
-    Rgba n = tex3d_rgb(high, px, py, p.z);
+    Rgba n = tex3d_rgb<MAGIC>(high, px, py, p.z);
     float fbm = (n.r * 0.625f + n.g * 0.25f) + n.b * 0.125f;
     float m = sat1(mix1(fbm, 1.0f - fbm, sat1(h * 2.0f)));
     return m * 0.005f;
@@ -278,7 +297,8 @@ struct RaySetup {
     f3 bg;           // Preetham sky * max(.62, dir.y)
     int branch;      // 0 ocean, 1 sky band, 2 march
     int nsteps;      // step-parallel path only: iterations of the march loop (cloud_rays_kernel fills it in)
-    int pad[2];
+    float covRcp;    // refined reciprocal of 1 - coverage (nice_rcp: the device's own MUFU.RCP + Newton step, hence per ray, not per frame)
+    int pad;
 };
 
 static_assert(sizeof(RaySetup) == 64, "RaySetup is the 64-byte per-ray record of the step-parallel path");
@@ -291,11 +311,11 @@ struct StepSample {
 
 // The ray direction of castRay for pixel (px, py) -- the first lines of cloud_ray_setup, for callers that need the
 // direction (and from it the background) without the rest.
-MT_DEVICE f3 cloud_ray_dir(const CloudParams& P, const MarchConst& M, int px, int py, int pixelID)
+MT_DEVICE f3 cloud_ray_dir(const CloudParams& P, const MarchConst& M, const MarchTabs& J, int px, int py, int pixelID)
 {
     float u = (float)px / (float)P.W;
     float v = 1.0f - (float)py / (float)P.H;
-    const float jx = M.rayJitter[pixelID >> 1][0], jy = M.rayJitter[pixelID >> 1][1];
+    const float jx = J.rayJitter[pixelID >> 1][0], jy = J.rayJitter[pixelID >> 1][1];
     RayBasis B;
     B.right = M.basisRight; B.up = M.basisUp; B.look = M.basisLook;
     return cast_ray_dir(P.cam, B, M.eyePos, u, v, jx, jy);
@@ -311,12 +331,12 @@ MT_DEVICE f3 cloud_ray_background(const CloudParams& P, f3 dir)
 // WITH_BG = false leaves the background (R.bg, and hdr of a sky-band pixel) to the caller: the fused 1-of-16 kernel
 // evaluates the Preetham sky in a second warp beside the geometry.
 template <bool WITH_BG = true>
-MT_DEVICE RaySetup cloud_ray_setup(const CloudParams& P, const MarchConst& M, int px, int py, int pixelID, F4& hdr)
+MT_DEVICE RaySetup cloud_ray_setup(const CloudParams& P, const MarchConst& M, const MarchTabs& J, int px, int py, int pixelID, F4& hdr)
 {
     RaySetup R;
     float u = (float)px / (float)P.W;
     float v = 1.0f - (float)py / (float)P.H;
-    const float jx = M.rayJitter[pixelID >> 1][0], jy = M.rayJitter[pixelID >> 1][1];
+    const float jx = J.rayJitter[pixelID >> 1][0], jy = J.rayJitter[pixelID >> 1][1];
     RayBasis B;
     B.right = M.basisRight; B.up = M.basisUp; B.look = M.basisLook;
     const f3 origin = M.eyePos;
@@ -325,7 +345,8 @@ MT_DEVICE RaySetup cloud_ray_setup(const CloudParams& P, const MarchConst& M, in
     R.t_in = R.t_out = R.stepSize = R.lenToInner = R.cosAngle = R.phase = 0.0f;
     R.bg = mk3(0.0f, 0.0f, 0.0f);
     R.nsteps = 0;
-    R.pad[0] = R.pad[1] = 0;
+    R.covRcp = 0.0f;
+    R.pad = 0;
     const float dotUp = (0.0f * dir.x + 1.0f * dir.y) + 0.0f * dir.z;
     hdr.w = 1.0f;
     if (dotUp < 0.0f) {  // ocean (:718-729)
@@ -343,6 +364,7 @@ MT_DEVICE RaySetup cloud_ray_setup(const CloudParams& P, const MarchConst& M, in
         return R;
     }
     R.branch = 2;
+    R.covRcp = nice_rcp(M.covDen);
     // shells (:750-753) and the per-ray constants of rayMarch (:567-590)
     const f3 ec = M.earthCenter;
     ShellHit hin = ray_shell(origin, dir, ec, MT_R_INNER);
@@ -371,13 +393,13 @@ struct StepBase {
 #define MT_BASE_PACKED 1
 #endif
 template <bool COUNT, bool WEATHER, int STD>
-MT_DEVICE StepBase cloud_step_base(const CloudParams& P, const MarchConst& M, const RaySetup& R, int jidx, float t, RayCounters& cnt)
+MT_DEVICE StepBase cloud_step_base(const CloudParams& P, const MarchConst& M, const MarchTabs& J, const RaySetup& R, int jidx, float t, RayCounters& cnt)
 {
     StepBase B;
     const f3 origin = M.eyePos, ec = M.earthCenter, dir = R.dir;
     const f3 relOrigin = mk3(ec.x, MT_R_INNER - MT_EARTH_RADIUS, ec.z);
     const f3 wind = mk3(P.tun.wind_direction[0], P.tun.wind_direction[1], P.tun.wind_direction[2]);
-    const float* sj = M.stepJitter[jidx >> 1];
+    const float* sj = J.stepJitter[jidx >> 1];
 #if MT_BASE_PACKED
     // pos = origin + (dir + jitter) * t
     const P2 jxy = add2(pk2(dir.x, dir.y), pk2(sj[0], sj[1]));
@@ -406,7 +428,7 @@ MT_DEVICE StepBase cloud_step_base(const CloudParams& P, const MarchConst& M, co
     const P2 skxy = add2(pk2(lo2(spxy) + lo2(wxy), hi2(spxy) + hi2(wxy)), pk2(M.windSkew.x, M.windSkew.y));
     const f3 skew = mk3(lo2(skxy), hi2(skxy), (spz + wz) + M.windSkew.z);
     B.pos = pos; B.skew = skew; B.h = h;
-    B.baseDensity = low_freq_density<WEATHER, STD>(P, M, P.tun.coverage, skxy, skew.z, pos.x, pos.z, h) * P.tun.base_density_factor;
+    B.baseDensity = low_freq_density<WEATHER, STD>(P, M, R.covRcp, P.tun.coverage, skxy, skew.z, pos.x, pos.z, h) * P.tun.base_density_factor;
 #else
     f3 jdir = dir + mk3(sj[0], sj[1], sj[2]);
     f3 pos = origin + jdir * t;
@@ -419,7 +441,7 @@ MT_DEVICE StepBase cloud_step_base(const CloudParams& P, const MarchConst& M, co
     // skewSamplePointWithWind (:489-497)
     f3 skew = (sp + ((wind * h) * P.tun.cloud_top_offset) * 0.009f) + M.windSkew;
     B.pos = pos; B.skew = skew; B.h = h;
-    B.baseDensity = low_freq_density<WEATHER, STD>(P, M, P.tun.coverage, pk2(skew.x, skew.y), skew.z, pos.x, pos.z, h) * P.tun.base_density_factor;
+    B.baseDensity = low_freq_density<WEATHER, STD>(P, M, R.covRcp, P.tun.coverage, pk2(skew.x, skew.y), skew.z, pos.x, pos.z, h) * P.tun.base_density_factor;
 #endif
     if (COUNT) cnt.steps++;
     return B;
@@ -430,6 +452,9 @@ MT_DEVICE StepBase cloud_step_base(const CloudParams& P, const MarchConst& M, co
 // The six light-cone offsets of one ray, (stepSize * noise_kernel[i]) * i, are the same at every step: the one-thread-per-ray
 // kernel computes them once per ray into shared memory ((x, y, z, -) per sample, [i][thread]: conflict-free) and each in-cloud
 // step reads them back -- one 16-byte load instead of a float conversion and four multiplies per cone sample, the same values.
+#ifndef MT_CONE_SKIP0
+#define MT_CONE_SKIP0 0  /* 4K: 3.621 ms without, 3.633 ms with: not worth the special case */
+#endif
 struct ConeOffsets {
     const F4* xyz;    // this thread's first offset (x, y, z, -); the offset of sample i is xyz[i * stride]   (null: compute per step)
     int stride;
@@ -471,7 +496,7 @@ __device__ __forceinline__ Brick ldg_brick(const Quad* bricks, unsigned cell, un
     asm volatile("ld.global.nc.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
 #endif
                  : "=r"(b.t[0]), "=r"(b.t[1]), "=r"(b.t[2]), "=r"(b.t[3]), "=r"(b.t[4]), "=r"(b.t[5]), "=r"(b.t[6]), "=r"(b.t[7])
-                 : "l"(bricks + 2u * cell));
+                 : "l"(reinterpret_cast<const char*>(bricks) + (size_t)cell * 32u));  // one IMAD.WIDE (2u * cell would be a separate 32-bit add)
     return b;
 }
 #endif
@@ -492,20 +517,33 @@ MT_DEVICE void cone_axes(const CloudParams& P, const MarchConst& M, const ConeOf
     // lightPos = pos + (stepSize * noise_kernel[i]) * i ; sample = (lightPos - relOrigin) / 12500  -- x,y as a pair
     P2 off;
     float offz;
-    if (CO.xyz) {  // one 16-byte shared load
-        const F4 o = CO.xyz[i * CO.stride];
-        off = pk2(o.x, o.y);
-        offz = o.z;
-    } else cone_offset(M, stepSize, i, off, offz);
-    // the offset products are separate values (memory or scalar adds): a mul2 feeding an add2 would be contracted into
-    // an FFMA2 (mt_math.cuh)
-    const P2 lxy = sub2(CO.xyz ? add2(pk2(pos.x, pos.y), off) : pk2(pos.x + lo2(off), pos.y + hi2(off)), pk2(relOrigin.x, relOrigin.y));
-    const float lz = (pos.z + offz) - relOrigin.z;
+    P2 lxy;
+    float lz;
+    if (MT_CONE_SKIP0 && CO.xyz && i == 0) {
+        // sample 0's offset is (stepSize * kernel[0]) * 0 = +-0 and pos + (+-0) == pos: no load, no add (a -0 component of pos would
+        // come out as +0 in the canonical form; it is subtracted from or divided into the same value either way)
+        lxy = sub2(pk2(pos.x, pos.y), pk2(relOrigin.x, relOrigin.y));
+        lz = pos.z - relOrigin.z;
+    } else {
+        if (CO.xyz) {  // ONE 16-byte shared load (the cache is 16-byte aligned: cloud_raymarch.cu)
+#if defined(MT_HOSTSIM)
+            const F4 o = CO.xyz[i * CO.stride];
+#else
+            const float4 o = *reinterpret_cast<const float4*>(CO.xyz + i * CO.stride);
+#endif
+            off = pk2(o.x, o.y);
+            offz = o.z;
+        } else cone_offset(M, stepSize, i, off, offz);
+        // the offset products are separate values (memory or scalar adds): a mul2 feeding an add2 would be contracted into
+        // an FFMA2 (mt_math.cuh)
+        lxy = sub2(CO.xyz ? add2(pk2(pos.x, pos.y), off) : pk2(pos.x + lo2(off), pos.y + hi2(off)), pk2(relOrigin.x, relOrigin.y));
+        lz = (pos.z + offz) - relOrigin.z;
+    }
     sxy = div_thickness2(lxy);
     sz = div_thickness(lz);
     const Tex3D low = std_low<STD>(P.low);
-    Z = lin_axis_repeat(sz, low.d);
-    lin_axes_xy(sxy, low.w, low.h, X, Y);
+    Z = lin_axis_repeat<MT_STD_MAGIC(STD)>(sz, low.d);
+    lin_axes_xy<MT_STD_MAGIC(STD)>(sxy, low.w, low.h, X, Y);
     cell = tex_cell(low, X.i0, Y.i0, Z.i0);
 }
 
@@ -518,7 +556,7 @@ MT_DEVICE StepSample cloud_step_light(const CloudParams& P, const MarchConst& M,
     const f3 relOrigin = mk3(ec.x, MT_R_INNER - MT_EARTH_RADIUS, ec.z);
     const float coverage = P.tun.coverage, h = B.h, baseDensity = B.baseDensity;
     if (COUNT) cnt.incloud++;
-    float edge = erosion_edge(std_curl<STD>(P.curl), std_high<STD>(P.high), skew, h);
+    float edge = erosion_edge<MT_STD_MAGIC(STD)>(std_curl<STD>(P.curl), std_high<STD>(P.high), skew, h);
     S.inc = erode(baseDensity * 1.4f, edge) * 0.5f;
     float dl = 0.0f;
     const float edgeRcp = nice_rcp(1.0f - edge);  // the step's erosion divisor, shared by the six cone samples (radiance only)
@@ -547,12 +585,11 @@ MT_DEVICE StepSample cloud_step_light(const CloudParams& P, const MarchConst& M,
                 nxt = ldg_brick(low.rfquads, celln, slice, wrap);
             }
             if (cur.t[0] & 1u) {  // the cell may hold cloud (flag written with the empty-cell bitmap); else the density is exactly +0
-                const Weights8 w = filter_weights(X, Y, Z);
                 const uint32_t t000 = cur.t[0], t001 = cur.t[1], t010 = cur.t[2], t011 = cur.t[3], t100 = cur.t[4], t101 = cur.t[5],
                                t110 = cur.t[6], t111 = cur.t[7];
-                const P2 rf = mul2(MT_ACC2(MT_RFP), bc2(MT_INV255));
+                const P2 rf = rf_filter(t000, t001, t010, t011, t100, t101, t110, t111, X, Y, Z);
                 bool hit;
-                const float term = cone_term_rf<STD>(P, M, coverage, rf, X, Y, Z, cell, edge, edgeRcp, hit);
+                const float term = cone_term_rf<STD>(P, M, R.covRcp, coverage, rf, X, Y, Z, cell, edge, edgeRcp, hit);
                 if (COUNT && hit) cnt.cone++;
                 dl += term;  // + 0 where the sample holds no cloud: the same sum
             }
@@ -571,9 +608,25 @@ MT_DEVICE StepSample cloud_step_light(const CloudParams& P, const MarchConst& M,
             if (STD && MT_CONE_RF && !WEATHER && !MT_HW_FILTER) {  // the plain (r, F) loop: the same per-sample term as the pipelined one
                 cone_axes<STD>(P, M, CO, pos, relOrigin, R.stepSize, i, sxy, sz, X, Y, Z, cell);
                 const Tex3D low = std_low<STD>(P.low);
+#if !defined(MT_HOSTSIM) && MT_CONE_PIPE && MT_RF_BRICKS
+                if (STD == 3) {
+                    // brick first: the cell's empty flag is bit 0 of the brick's first word (occupancy_build_kernel), so a sample
+                    // is ONE memory round trip (256-bit load, then flag test and filter) instead of bitmap word -> brick.  The
+                    // step-parallel 1-of-16 kernel is latency bound on exactly that chain (profiles/r2_passes_1080p.md: 12 % of
+                    // its stall samples wait for the brick, 8 % for the bitmap word before it).
+                    const Brick b = ldg_brick(low.rfquads, cell, 0u, 0u);
+                    if (b.t[0] & 1u) {
+                        bool hit;
+                        dl += cone_term_rf<STD>(P, M, R.covRcp, coverage, rf_filter(b.t[0], b.t[1], b.t[2], b.t[3], b.t[4], b.t[5], b.t[6], b.t[7], X, Y, Z),
+                                                X, Y, Z, cell, edge, edgeRcp, hit);
+                        if (COUNT && hit) cnt.cone++;
+                    }
+                    continue;
+                }
+#endif
                 if (!low.occ || occ_cell_may_be_cloud(low, cell)) {
                     bool hit;
-                    dl += cone_term_rf<STD>(P, M, coverage, tex3d_rf_axes(low, X, Y, Z, cell), X, Y, Z, cell, edge, edgeRcp, hit);
+                    dl += cone_term_rf<STD>(P, M, R.covRcp, coverage, tex3d_rf_axes(low, X, Y, Z, cell), X, Y, Z, cell, edge, edgeRcp, hit);
                     if (COUNT && hit) cnt.cone++;
                 }
                 continue;
@@ -588,7 +641,7 @@ MT_DEVICE StepSample cloud_step_light(const CloudParams& P, const MarchConst& M,
                     const float fbm = sat1((n.y * 0.625f + n.z * 0.25f) + n.w * 0.125f);
                     const float omin = fbm - 0.9f;
                     const float base = sat1(div_nice(n.x - omin, 1.0f - omin));
-                    if (base > coverage) cur = sat1(div_nice_r(base - coverage, M.covDen, M.covRcp)) * coverage;
+                    if (base > coverage) cur = sat1(div_nice_r(base - coverage, M.covDen, R.covRcp)) * coverage;
                 }
             } else
 #endif
@@ -596,10 +649,10 @@ MT_DEVICE StepSample cloud_step_light(const CloudParams& P, const MarchConst& M,
                 cone_axes<STD>(P, M, CO, pos, relOrigin, R.stepSize, i, sxy, sz, X, Y, Z, cell);
                 const Tex3D low = std_low<STD>(P.low);
                 cur = (low.occ && !occ_cell_may_be_cloud(low, cell)) ? 0.0f
-                      : cone_density_rf<STD>(P, M, coverage, tex3d_rf_axes(low, X, Y, Z, cell), X, Y, Z, cell);
+                      : cone_density_rf<STD>(P, M, R.covRcp, coverage, tex3d_rf_axes(low, X, Y, Z, cell), X, Y, Z, cell);
             } else {
                 cone_axes<STD>(P, M, CO, pos, relOrigin, R.stepSize, i, sxy, sz, X, Y, Z, cell);
-                cur = low_freq_density<WEATHER, STD>(P, M, coverage, sxy, sz, lo2(sxy), sz, h);
+                cur = low_freq_density<WEATHER, STD>(P, M, R.covRcp, coverage, sxy, sz, lo2(sxy), sz, h);
             }
             if (cur > 0.0f) {
                 if (COUNT) cnt.cone++;
@@ -613,10 +666,10 @@ MT_DEVICE StepSample cloud_step_light(const CloudParams& P, const MarchConst& M,
 
 // One iteration of the march loop (cloudRayMarch.comp:629-678) at parameter t, without the running sums.
 template <bool COUNT, bool WEATHER, int STD>
-MT_DEVICE StepSample cloud_step_sample(const CloudParams& P, const MarchConst& M, const RaySetup& R, int jidx, float t,
+MT_DEVICE StepSample cloud_step_sample(const CloudParams& P, const MarchConst& M, const MarchTabs& J, const RaySetup& R, int jidx, float t,
                                        RayCounters& cnt, const ConeOffsets& CO)
 {
-    const StepBase B = cloud_step_base<COUNT, WEATHER, STD>(P, M, R, jidx, t, cnt);
+    const StepBase B = cloud_step_base<COUNT, WEATHER, STD>(P, M, J, R, jidx, t, cnt);
     if (B.baseDensity > 0.0f) return cloud_step_light<COUNT, WEATHER, STD>(P, M, R, B, cnt, CO);
     StepSample S;
     S.inc = 0.0f;
@@ -657,11 +710,11 @@ MT_DEVICE void cloud_composite(const RaySetup& R, float accum, float color, F4& 
 
 // One invocation of main(): setup, the sequential march, composite.
 template <bool COUNT, bool DEBUG, bool WEATHER, int STD>
-MT_DEVICE void cloud_ray(const CloudParams& P, const MarchConst& M, int px, int py, int pixelID, F4& hdr, F4& mask,
+MT_DEVICE void cloud_ray(const CloudParams& P, const MarchConst& M, const MarchTabs& J, int px, int py, int pixelID, F4& hdr, F4& mask,
                          RayCounters& cnt, MtRayDebug* dbg, F4* coneXYZ, int coneStride)
 {
     mask.x = mask.y = mask.z = mask.w = 0.0f;
-    const RaySetup R = cloud_ray_setup(P, M, px, py, pixelID, hdr);
+    const RaySetup R = cloud_ray_setup(P, M, J, px, py, pixelID, hdr);
     if (COUNT) cnt.rays++;
     if (DEBUG) {
         dbg->dir[0] = R.dir.x; dbg->dir[1] = R.dir.y; dbg->dir[2] = R.dir.z;
@@ -690,7 +743,7 @@ MT_DEVICE void cloud_ray(const CloudParams& P, const MarchConst& M, int px, int 
     for (float t = R.t_in; t < R.t_out && iters < MT_MAX_MARCH_ITERS; t += R.stepSize, ++iters) {
         const int jidx = (pixelID + mt_f2i(t)) & 15;  // int(mod(float(pixelID + int(t)), 16.0)), argument >= 0
         if (DEBUG) jhash = (jhash ^ (unsigned)jidx) * 16777619u;
-        const StepSample S = cloud_step_sample<COUNT, WEATHER, STD>(P, M, R, jidx, t, cnt, CO);
+        const StepSample S = cloud_step_sample<COUNT, WEATHER, STD>(P, M, J, R, jidx, t, cnt, CO);
         if (cloud_step_combine(S, accum, transmittance, color)) {
             if (COUNT) cnt.early++;
             ++iters;

@@ -13,13 +13,28 @@
 #include "mt_launch.h"
 #include "mt_pixel.cuh"
 
-__global__ void cloud_setup_kernel(CamU cam, TimeU tm, MtTuning tun, int W, int H, MarchConst* out)
-{
-    MarchConst m;
-    cloud_frame_setup(cam, tm, tun, m);
-    cloud_frame_jitter(tm, W, H, m);
-    *out = m;
-}
+// The per-frame constants (MarchConst, mt_params.h) arrive in the parameter block: M is a reference into the constant bank.  The
+// two jitter tables are indexed per lane, so every CTA stages them (48 words) in shared memory.  MT_MC_PARAM=0 is the A/B
+// form: the whole block staged in shared memory, as rounds 1 and 2 did from a device buffer.
+#ifndef MT_MC_PARAM
+#define MT_MC_PARAM 1
+#endif
+#if MT_MC_PARAM
+#define MT_MARCH_CONST(P)                                                                                                          \
+    __shared__ MarchTabs J;                                                                                                        \
+    if (threadIdx.x < MT_MARCHTABS_WORDS)                                                                                          \
+        reinterpret_cast<float*>(&J)[threadIdx.x] = reinterpret_cast<const float*>(&(P).mc.tabs)[threadIdx.x];                    \
+    __syncthreads();                                                                                                               \
+    const MarchConst& M = (P).mc
+#else
+#define MT_MARCH_CONST(P)                                                                                                          \
+    __shared__ MarchConst Ms;                                                                                                      \
+    if (threadIdx.x < sizeof(MarchConst) / 4)                                                                                      \
+        reinterpret_cast<float*>(&Ms)[threadIdx.x] = reinterpret_cast<const float*>(&(P).mc)[threadIdx.x];                        \
+    __syncthreads();                                                                                                               \
+    const MarchConst& M = Ms;                                                                                                      \
+    const MarchTabs& J = Ms.tabs
+#endif
 
 // One thread per 32 cells (one output word): bit x of the word = any of the cell's eight corner texels may carry cloud.
 // Where the (r, F) quads exist, bit 0 of each cell's first word repeats the cell's bit (the pipelined cone loop reads it
@@ -177,15 +192,11 @@ __global__ void __launch_bounds__(128, MT_CLOUD_MINBLOCKS) cloud_raymarch_kernel
         valid = gx < P.tx && gy < P.ty && px < P.W && py < P.H; // imageStore outside the image is dropped
     }
 
-    // stage the per-frame constants: read as warp-uniform (broadcast) or 8-way indexed LDS from here on
-    __shared__ MarchConst M;
-    if (threadIdx.x < MT_MARCHCONST_WORDS)
-        reinterpret_cast<float*>(&M)[threadIdx.x] = __ldg(reinterpret_cast<const float*>(P.mc) + threadIdx.x);
-    __syncthreads();
+    MT_MARCH_CONST(P);
 
     // per-ray light-cone offsets (cloud_core.cuh, ConeOffsets): [sample][thread], written once per marching ray
 #if MT_CONE_CACHE
-    __shared__ F4 coneXYZ[6][128];
+    __shared__ __align__(16) F4 coneXYZ[6][128];
     F4* const cxyz = &coneXYZ[0][threadIdx.x];
 #else
     F4* const cxyz = nullptr;
@@ -197,7 +208,7 @@ __global__ void __launch_bounds__(128, MT_CLOUD_MINBLOCKS) cloud_raymarch_kernel
     if (valid) {
         F4 hdr, mask;
         const size_t idx = (size_t)py * (size_t)P.W + (size_t)px;
-        cloud_ray<COUNT, DEBUG, WEATHER, (STD ? (MT_CONE_PIPE ? 2 : 1) : 0)>(P, M, px, py, pixelID, hdr, mask, cnt, DEBUG ? (P.debug + idx) : nullptr, cxyz, 128);
+        cloud_ray<COUNT, DEBUG, WEATHER, (STD ? (MT_CONE_PIPE ? 2 : 1) : 0)>(P, M, J, px, py, pixelID, hdr, mask, cnt, DEBUG ? (P.debug + idx) : nullptr, cxyz, 128);
         const float4 h4 = make_float4(hdr.x, hdr.y, hdr.z, hdr.w);
         if (bulk) {
             // The marching warp must not wait on a remote write: its 32 pixels go to shared memory, and lanes 0 and 16 each
@@ -273,13 +284,6 @@ __device__ __forceinline__ void sixteenth_pixel(const CloudParams& P, int& px, i
     valid = gx < P.tx && gy < P.ty && px < P.W && py < P.H;
 }
 
-__device__ __forceinline__ void stage_march_const(MarchConst& M, const MarchConst* src)
-{
-    if (threadIdx.x < MT_MARCHCONST_WORDS)
-        reinterpret_cast<float*>(&M)[threadIdx.x] = __ldg(reinterpret_cast<const float*>(src) + threadIdx.x);
-    __syncthreads();
-}
-
 __device__ __forceinline__ void store_pixel(const CloudParams& P, size_t idx, F4 hdr, F4 mask)
 {
     px_store(P.hdr, idx, make_float4(hdr.x, hdr.y, hdr.z, hdr.w), P.storage);
@@ -288,8 +292,7 @@ __device__ __forceinline__ void store_pixel(const CloudParams& P, size_t idx, F4
 
 __global__ void __launch_bounds__(128) cloud_rays_kernel(const __grid_constant__ CloudParams P)
 {
-    __shared__ MarchConst M;
-    stage_march_const(M, P.mc);
+    MT_MARCH_CONST(P);
     int px, py, pixelID;
     bool valid;
     sixteenth_pixel(P, px, py, pixelID, valid);
@@ -303,7 +306,7 @@ __global__ void __launch_bounds__(128) cloud_rays_kernel(const __grid_constant__
     } else {
         F4 hdr, mask;
         mask.x = mask.y = mask.z = mask.w = 0.0f;
-        const RaySetup R = cloud_ray_setup(P, M, px, py, pixelID, hdr);
+        const RaySetup R = cloud_ray_setup(P, M, J, px, py, pixelID, hdr);
         *rec = R;
         if (R.branch != 2) store_pixel(P, (size_t)py * P.W + px, hdr, mask);  // ocean / sky band: final
         else {
@@ -336,8 +339,7 @@ __global__ void __launch_bounds__(128, MT_STEPS_MINBLOCKS) cloud_steps_kernel(co
 {
     const int k = blockIdx.y;
     if (k >= __ldg(P.ctaSteps + blockIdx.x)) return;  // whole CTA idle for this slice (uniform: taken by all 128 threads)
-    __shared__ MarchConst M;
-    stage_march_const(M, P.mc);
+    MT_MARCH_CONST(P);
     const size_t ray = (size_t)blockIdx.x * 128 + threadIdx.x;
     float2* slot = P.samples + ((size_t)k * (size_t)P.rayStride + ray);
     const float t = *reinterpret_cast<const float*>(slot);  // t_k as the sequential loop rounds it (cloud_rays_kernel); plain load: the slot is overwritten below
@@ -346,7 +348,7 @@ __global__ void __launch_bounds__(128, MT_STEPS_MINBLOCKS) cloud_steps_kernel(co
     const int jidx = (P.tm.frameCountMod16 + mt_f2i(t)) & 15;
     RayCounters none = { 0u, 0u, 0u, 0u, 0u, 0u };
     const ConeOffsets noCache = { nullptr, 0 };  // one thread per (ray, step): nothing to share
-    const StepSample S = cloud_step_sample<false, WEATHER, STD>(P, M, R, jidx, t, none, noCache);
+    const StepSample S = cloud_step_sample<false, WEATHER, STD>(P, M, J, R, jidx, t, none, noCache);
     *slot = make_float2(S.inc, S.energy);
 }
 
@@ -369,8 +371,7 @@ __global__ void __launch_bounds__(128, MT_CLOUD_MINBLOCKS) cloud_base_kernel(con
 {
     const int k = blockIdx.y;
     if (k >= __ldg(P.ctaSteps + blockIdx.x)) return;  // whole CTA idle for this slice (uniform: taken by all 128 threads)
-    __shared__ MarchConst M;
-    stage_march_const(M, P.mc);
+    MT_MARCH_CONST(P);
     const size_t ray = (size_t)blockIdx.x * 128 + threadIdx.x;
     const RaySetup R = reinterpret_cast<const RaySetup*>(P.rays)[ray];
     float t = R.t_in;
@@ -380,7 +381,7 @@ __global__ void __launch_bounds__(128, MT_CLOUD_MINBLOCKS) cloud_base_kernel(con
     if (live) {
         const int jidx = (P.tm.frameCountMod16 + mt_f2i(t)) & 15;
         RayCounters none = { 0u, 0u, 0u, 0u, 0u, 0u };
-        hit = cloud_step_base<false, WEATHER, STD>(P, M, R, jidx, t, none).baseDensity > 0.0f;
+        hit = cloud_step_base<false, WEATHER, STD>(P, M, J, R, jidx, t, none).baseDensity > 0.0f;
         if (!hit) P.samples[(size_t)k * (size_t)P.rayStride + ray] = make_float2(0.0f, -1.0f);
     }
     const unsigned hits = __ballot_sync(0xffffffffu, hit);
@@ -396,8 +397,7 @@ __global__ void __launch_bounds__(128, MT_CLOUD_MINBLOCKS) cloud_base_kernel(con
 template <bool WEATHER, bool STD>
 __global__ void __launch_bounds__(128, MT_CLOUD_MINBLOCKS) cloud_light_kernel(const __grid_constant__ CloudParams P)
 {
-    __shared__ MarchConst M;
-    stage_march_const(M, P.mc);
+    MT_MARCH_CONST(P);
     const unsigned n = *reinterpret_cast<const volatile unsigned*>(P.itemCount);
     const unsigned step = gridDim.x * 128u;
     for (unsigned i = blockIdx.x * 128u + threadIdx.x; i < n; i += step) {
@@ -409,7 +409,7 @@ __global__ void __launch_bounds__(128, MT_CLOUD_MINBLOCKS) cloud_light_kernel(co
         for (int j = 0; j < k; ++j) t += R.stepSize;
         const int jidx = (P.tm.frameCountMod16 + mt_f2i(t)) & 15;
         RayCounters none = { 0u, 0u, 0u, 0u, 0u, 0u };
-        const StepBase B = cloud_step_base<false, WEATHER, STD>(P, M, R, jidx, t, none);   // same arithmetic: B.baseDensity > 0 again
+        const StepBase B = cloud_step_base<false, WEATHER, STD>(P, M, J, R, jidx, t, none);   // same arithmetic: B.baseDensity > 0 again
         const ConeOffsets noCache = { nullptr, 0 };
         const StepSample S = cloud_step_light<false, WEATHER, STD>(P, M, R, B, none, noCache);
         P.samples[(size_t)k * (size_t)P.rayStride + ray] = make_float2(S.inc, S.energy);
@@ -450,10 +450,28 @@ __global__ void __launch_bounds__(128) cloud_fold_kernel(const __grid_constant__
 
 // the reference's texture extents (Sky.cpp:31-50): the STD kernels carry them as immediates and take the light-cone samples
 // from the (r, F) quads (MT_FLAG_NO_CONE_RF or other extents: the generic kernels, canonical filter throughout)
+// ... and floor their filter coordinates with the magic constant (mt_tex.cuh), exact for |u| < 2^22.  A conservative bound on
+// every texture coordinate of the frame from its constants: ray length T (an eye inside the inner shell marches at most
+// ~250 km, dir.y >= 0.06; otherwise eye altitude + two shell diameters), sample position <= 1.1 T / 12500, relative height
+// <= T / 12500, wind skew = height * |wind| * |cloud_top_offset| * 0.009 + |windSkew|; times the largest extent (128), with a
+// factor two to spare.  Frames outside it (an eye millions of metres up, a wind drift of tens of thousands of periods)
+// run the generic kernels.
+static bool mt_magic_floor_ok(const CloudParams& P)
+{
+    if (!MT_MAGIC_FLOOR) return true;
+    const float ey = P.mc.eyePos.y;
+    if (!(fabsf(ey) < 1e8f)) return false;  // also NaN
+    const float T = (ey > -1000.0f && ey < 7000.0f) ? 3.0e5f : fabsf(ey) + 1.3e7f;
+    const float wind = fabsf(P.tun.wind_direction[0]) + fabsf(P.tun.wind_direction[1]) + fabsf(P.tun.wind_direction[2]);
+    const float drift = fmaxf(fabsf(P.mc.windSkew.x), fmaxf(fabsf(P.mc.windSkew.y), fabsf(P.mc.windSkew.z)));
+    const float smax = 1.1f * T / 12500.0f + (T / 12500.0f) * wind * fabsf(P.tun.cloud_top_offset) * 0.009f + drift + 2.0f;
+    return smax * 128.0f < 2097152.0f;  // 2^21; !(NaN < x)
+}
 static bool mt_std_dims(const CloudParams& P)
 {
     return P.low.w == 128 && P.low.h == 128 && P.low.d == 128 && P.high.w == 32 && P.high.h == 32 && P.high.d == 32 &&
-           P.curl.w == 128 && P.curl.h == 128 && (!MT_CONE_RF || P.low.rfquads != nullptr);  // STD also means: (r, F) quads exist
+           P.curl.w == 128 && P.curl.h == 128 && (!MT_CONE_RF || P.low.rfquads != nullptr) &&  // STD also means: (r, F) quads exist
+           mt_magic_floor_ok(P);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -472,7 +490,7 @@ static bool mt_std_dims(const CloudParams& P)
 // ---------------------------------------------------------------------------------------------------------------------
 #define MT_S16_WARPS 8
 #ifndef MT_S16_CONE
-#define MT_S16_CONE 1  /* 1: plain (r, F) cone loop; 2: the software-pipelined, unrolled one of the full-quality kernel */
+#define MT_S16_CONE 3  /* 1080p: 139.7 (1), 135.6 us (3); 1: plain (r, F) cone loop; 2: the software-pipelined, unrolled one of the full-quality kernel; 3: plain loop, brick first (flag in the brick) */
 #endif
 #ifndef MT_S16_MINBLOCKS
 #define MT_S16_MINBLOCKS 6
@@ -480,13 +498,12 @@ static bool mt_std_dims(const CloudParams& P)
 template <bool WEATHER, bool STD>
 __global__ void __launch_bounds__(32 * MT_S16_WARPS, MT_S16_MINBLOCKS) cloud_sixteenth_kernel(const __grid_constant__ CloudParams P)
 {
-    __shared__ MarchConst M;
     __shared__ RaySetup rays[32];
     __shared__ float tk[MT_STEP_SLICES][32];
     __shared__ float2 smp[MT_STEP_SLICES][32];
     __shared__ f3 bgs[32];
     __shared__ int tileSteps;
-    stage_march_const(M, P.mc);
+    MT_MARCH_CONST(P);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // the CTA's ray tile: 8x4 rays of the (tx, ty) grid; rows of tiles in mt_tile_order: the marching rows from the horizon
     // upwards first, interleaved with the ocean rows -- the kernel is about two waves of CTAs, so what runs last decides its tail
@@ -505,7 +522,7 @@ __global__ void __launch_bounds__(32 * MT_S16_WARPS, MT_S16_MINBLOCKS) cloud_six
         } else {
             F4 hdr, mask;
             mask.x = mask.y = mask.z = mask.w = 0.0f;
-            RaySetup R = cloud_ray_setup<false>(P, M, px, py, pixelID, hdr);  // geometry only: the sky is warp 1's
+            RaySetup R = cloud_ray_setup<false>(P, M, J, px, py, pixelID, hdr);  // geometry only: the sky is warp 1's
             if (R.branch == 0) store_pixel(P, (size_t)py * P.W + px, hdr, mask);  // ocean: final
             else if (R.branch == 2)
                 for (float t = R.t_in; t < R.t_out && n < MT_STEP_SLICES; t += R.stepSize) tk[n++][lane] = t;
@@ -517,7 +534,7 @@ __global__ void __launch_bounds__(32 * MT_S16_WARPS, MT_S16_MINBLOCKS) cloud_six
         n = max(n, __shfl_xor_sync(0xffffffffu, n, 1));
         if (lane == 0) tileSteps = n;
     } else if (warp == 1 && valid) {  // ---- A, beside warp 0: the background (Preetham sky, a dozen pow / exp) of the same 32 rays
-        const f3 dir = cloud_ray_dir(P, M, px, py, pixelID);   // the same castRay: the same bits
+        const f3 dir = cloud_ray_dir(P, M, J, px, py, pixelID);   // the same castRay: the same bits
         const float dotUp = (0.0f * dir.x + 1.0f * dir.y) + 0.0f * dir.z;
         if (!(dotUp < 0.0f)) {
             const f3 bg = cloud_ray_background(P, dir);
@@ -543,7 +560,7 @@ __global__ void __launch_bounds__(32 * MT_S16_WARPS, MT_S16_MINBLOCKS) cloud_six
             if (k < mine) {
                 const float t = tk[k][lane];
                 const int jidx = (pixelID + mt_f2i(t)) & 15;
-                const StepSample S = cloud_step_sample<false, WEATHER, (STD ? MT_S16_CONE : 0)>(P, M, R, jidx, t, none, noCache);
+                const StepSample S = cloud_step_sample<false, WEATHER, (STD ? MT_S16_CONE : 0)>(P, M, J, R, jidx, t, none, noCache);
                 smp[k][lane] = make_float2(S.inc, S.energy);
             }
         }
@@ -666,12 +683,6 @@ cudaError_t mt_launch_tile_forward(const void* src, void* dst, int W, int H, int
     const unsigned ctasPerTile = (unsigned)((W + MT_CTA_W - 1) / MT_CTA_W) * (unsigned)(rows.tile_rows / MT_CTA_H);
     const int grid = ctas < rows.tile_count ? ctas : rows.tile_count;
     tile_forward_kernel<<<grid, 256, 0, stream>>>((const float4*)src, (float4*)dst, W * bytesPerPixel / 16, H, rows, tileDone, ctasPerTile);
-    return cudaGetLastError();
-}
-
-cudaError_t mt_launch_cloud_setup(const CloudParams& P, MarchConst* out, cudaStream_t stream)
-{
-    cloud_setup_kernel<<<1, 1, 0, stream>>>(P.cam, P.tm, P.tun, P.W, P.H, out);
     return cudaGetLastError();
 }
 

@@ -9,8 +9,11 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <vector>
 
+#include "cloud_core.cuh"
 #include "mt_host_consts.h"
+#include "post_core.cuh"
 #include "mt_launch.h"
 
 #define MT_FLAG_PASS_TIMING_INTERNAL MT_FLAG_PASS_TIMING
@@ -35,7 +38,8 @@ struct MtContext {
     F4* hdr[2] = { nullptr, nullptr };
     int cur = 0;  // index of the image that currently plays "currentFrameResultImage"
     F4* mask = nullptr;
-    float2* maskDecoded = nullptr; // (W+2) x (H+2) pairs: scratch of the god-ray pass
+    float2* maskDecoded = nullptr; // pitch x (H+2) pairs: scratch of the god-ray pass
+    float* uvTab = nullptr;        // per-size uv table of the post passes (mt_params.h)
     F4* maskStage = nullptr;       // device snapshot of the mask behind mtReadImageAsync (lazily allocated)
     float* greyStage = nullptr;    // the decoded one-float-per-pixel god-ray image behind mtReadGodRayGreyAsync (lazily allocated)
     uint32_t* ldr[2] = { nullptr, nullptr };  // ping-pong with the HDR images (same `cur`)
@@ -48,7 +52,6 @@ struct MtContext {
     cudaTextureObject_t hwTex = 0;
 #endif
     int texw[4] = { 0, 0, 0, 0 }, texh[4] = { 0, 0, 0, 0 }, texd[4] = { 0, 0, 0, 0 };
-    MarchConst* mc = nullptr;
     uint32_t* occ = nullptr;      // empty-cell bitmap of the low-frequency volume (mt_tex.cuh)
     float occCoverage = -1.0f;    // coverage the bitmap was built for; < 0 = stale
     unsigned long long* counters = nullptr;
@@ -134,11 +137,12 @@ struct ImageSet {
     uint32_t* ldr[2] = { nullptr, nullptr };
     uint32_t* ldrScratch = nullptr;
     float2* maskDecoded = nullptr;
+    float* uvTab = nullptr;  // mt_params.h: x / W, y / H, (x + .5) / W, (y + .5) / H
 };
 static void free_image_set(ImageSet& s)
 {
     cudaFree(s.hdr[0]); cudaFree(s.hdr[1]); cudaFree(s.mask);
-    cudaFree(s.ldr[0]); cudaFree(s.ldr[1]); cudaFree(s.ldrScratch); cudaFree(s.maskDecoded);
+    cudaFree(s.ldr[0]); cudaFree(s.ldr[1]); cudaFree(s.ldrScratch); cudaFree(s.maskDecoded); cudaFree(s.uvTab);
     s = ImageSet();
 }
 static cudaError_t alloc_image_set(ImageSet& s, int W, int H, size_t hb, cudaStream_t stream)  // hb: bytes per HDR / mask pixel
@@ -151,7 +155,14 @@ static cudaError_t alloc_image_set(ImageSet& s, int W, int H, size_t hb, cudaStr
     if ((e = cudaMalloc((void**)&s.ldr[0], px * 4)) != cudaSuccess) return e;
     if ((e = cudaMalloc((void**)&s.ldr[1], px * 4)) != cudaSuccess) return e;
     if ((e = cudaMalloc((void**)&s.ldrScratch, px * 4)) != cudaSuccess) return e;
-    if ((e = cudaMalloc((void**)&s.maskDecoded, (size_t)(W + 2) * (size_t)(H + 2) * sizeof(float2))) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void**)&s.maskDecoded, mt_godray_pitch(W) * (size_t)(H + 2) * sizeof(float2))) != cudaSuccess) return e;
+    {   // the uv table: the kernels' own operands, divided here (IEEE, as the shaders' in_uv / pixelPos arithmetic)
+        std::vector<float> uv((size_t)2 * (W + H));
+        for (int x = 0; x < W; ++x) { uv[x] = (float)x / (float)W; uv[(size_t)W + H + x] = ((float)x + 0.5f) / (float)W; }
+        for (int y = 0; y < H; ++y) { uv[(size_t)W + y] = (float)y / (float)H; uv[(size_t)2 * W + H + y] = ((float)y + 0.5f) / (float)H; }
+        if ((e = cudaMalloc((void**)&s.uvTab, uv.size() * sizeof(float))) != cudaSuccess) return e;
+        if ((e = cudaMemcpy(s.uvTab, uv.data(), uv.size() * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess) return e;  // synchronous: `uv` dies here
+    }
     if ((e = cudaMemsetAsync(s.hdr[0], 0, px * hb, stream)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(s.hdr[1], 0, px * hb, stream)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(s.mask, 0, px * hb, stream)) != cudaSuccess) return e;
@@ -167,11 +178,12 @@ static void free_images(MtContext* c)
     if (c->fwdStream) cudaStreamSynchronize(c->fwdStream);
     ImageSet old;
     old.hdr[0] = c->hdr[0]; old.hdr[1] = c->hdr[1]; old.mask = c->mask;
-    old.ldr[0] = c->ldr[0]; old.ldr[1] = c->ldr[1]; old.ldrScratch = c->ldrScratch; old.maskDecoded = c->maskDecoded;
+    old.ldr[0] = c->ldr[0]; old.ldr[1] = c->ldr[1]; old.ldrScratch = c->ldrScratch; old.maskDecoded = c->maskDecoded; old.uvTab = c->uvTab;
     free_image_set(old);
     c->ldr[0] = c->ldr[1] = c->ldrScratch = nullptr;
     c->hdr[0] = c->hdr[1] = c->mask = nullptr;
     c->maskDecoded = nullptr;
+    c->uvTab = nullptr;
     cudaFree(c->debug); cudaFree(c->taps); cudaFree(c->rays); cudaFree(c->samples); cudaFree(c->ctaSteps);
     cudaFree(c->items); cudaFree(c->itemCount);
     cudaFree(c->tileDone);
@@ -189,7 +201,7 @@ static void free_images(MtContext* c)
 static void adopt_images(MtContext* c, const ImageSet& s)
 {
     c->hdr[0] = s.hdr[0]; c->hdr[1] = s.hdr[1]; c->mask = s.mask;
-    c->ldr[0] = s.ldr[0]; c->ldr[1] = s.ldr[1]; c->ldrScratch = s.ldrScratch; c->maskDecoded = s.maskDecoded;
+    c->ldr[0] = s.ldr[0]; c->ldr[1] = s.ldr[1]; c->ldrScratch = s.ldrScratch; c->maskDecoded = s.maskDecoded; c->uvTab = s.uvTab;
     c->cur = 0;
 }
 static MtStatus alloc_images(MtContext* c)
@@ -282,7 +294,6 @@ try {
         }
         if (st != MT_OK) break;
         if ((st = alloc_images(c)) != MT_OK) break;
-        if (cudaMalloc((void**)&c->mc, sizeof(MarchConst)) != cudaSuccess) { st = MT_ERR_OOM; break; }
         if (cudaMalloc((void**)&c->counters, 8 * sizeof(unsigned long long)) != cudaSuccess) { st = MT_ERR_OOM; break; }
         if (cudaMemsetAsync(c->counters, 0, 8 * sizeof(unsigned long long), c->stream) != cudaSuccess) { st = MT_ERR_CUDA; break; }
     } while (0);
@@ -313,7 +324,6 @@ void mtDestroy(MtContext* c)
     if (c->hwTex) cudaDestroyTextureObject(c->hwTex);
     if (c->hwArray) cudaFreeArray(c->hwArray);
 #endif
-    cudaFree(c->mc);
     cudaFree(c->occ);
     cudaFree(c->counters);
     cudaFree(c->flushBuf);
@@ -545,7 +555,10 @@ static MtStatus cloud_dispatch(MtContext* c, int full, const RowTiles* tiles, bo
         }
         P.low.occ = c->occ;
     }
-    P.mc = c->mc;
+    // the per-frame constants of the march, evaluated here (cloud_core.cuh: __host__ __device__, IEEE operations without
+    // contraction on both sides) and passed in the parameter block
+    cloud_frame_setup(P.cam, P.tm, P.tun, P.mc);
+    cloud_frame_jitter(P.tm, c->W, c->H, P.mc.tabs);
     P.hdr = c->outHdr ? c->outHdr : c->hdr[c->cur];
     P.mask = c->outMask ? c->outMask : c->mask;
     P.W = c->W; P.H = c->H;
@@ -610,7 +623,6 @@ static MtStatus cloud_dispatch(MtContext* c, int full, const RowTiles* tiles, bo
     P.itemCount = c->itemCount;
     wait_pending_read(c, P.hdr);
     wait_pending_read(c, P.mask);
-    MT_CUDA(c, mt_launch_cloud_setup(P, c->mc, c->stream));
     pass_begin(c, MT_PASS_CLOUD);
     int n = 1;
     // gather by forwarding: full-quality row-tile launches keep their stores local and a side kernel pushes finished tiles
@@ -638,7 +650,7 @@ static MtStatus cloud_dispatch(MtContext* c, int full, const RowTiles* tiles, bo
         c->fwdTiles = P.rows.tile_count;
     }
     pass_end(c, MT_PASS_CLOUD);
-    c->launches += 1 + (uint64_t)n;
+    c->launches += (uint64_t)n;
     return MT_OK;
 }
 
@@ -693,6 +705,8 @@ static MtStatus reproject_dispatch(MtContext* c, bool debug)
     P.cur = c->hdr[c->cur];
     P.W = c->W; P.H = c->H;
     P.storage = (int)c->storage;
+    P.frame = reproject_frame(P);
+    P.uv = c->uvTab;
     P.taps = nullptr;
     if (debug) {
         if (!c->taps) MT_CUDA(c, cudaMalloc((void**)&c->taps, (size_t)c->W * c->H * 10 * sizeof(int)));
@@ -745,6 +759,8 @@ static MtStatus godrays_dispatch(MtContext* c, bool fuse_tonemap)
     P.storage = (int)c->storage;
     P.ldr = fuse_tonemap ? c->ldr[c->cur] : nullptr;
     P.seed = tonemap_seed(c);
+    P.frame = godray_frame(P.cam);
+    P.uv = c->uvTab;
     wait_pending_read(c, P.hdr);
     if (fuse_tonemap) wait_pending_read(c, P.ldr);
     pass_begin(c, MT_PASS_GODRAYS);
@@ -797,6 +813,8 @@ try {
     P.prev = c->ldr[c->cur ^ 1];
     P.out = c->ldrScratch;
     P.W = c->W; P.H = c->H;
+    P.frame = txaa_frame(P);
+    P.uv = c->uvTab;
     wait_pending_read(c, P.out);
     pass_begin(c, MT_PASS_TXAA);
     MT_CUDA(c, mt_launch_txaa(P, c->stream));

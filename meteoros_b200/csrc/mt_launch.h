@@ -5,7 +5,6 @@
 
 #include "mt_params.h"
 
-cudaError_t mt_launch_cloud_setup(const CloudParams& P, MarchConst* out, cudaStream_t stream);
 cudaError_t mt_launch_cloud(const CloudParams& P, cudaStream_t stream);
 cudaError_t mt_launch_tile_forward(const void* src, void* dst, int W, int H, int bytesPerPixel, const RowTiles& rows, unsigned* tileDone,
                                    int ctas, cudaStream_t stream);

@@ -44,9 +44,18 @@ struct SkyConst {
     float yDotMix;     // clamp((1 - sunDir.y)^5, 0, 1)
 };
 
-// Per-frame constants of the march that feed discrete decisions; computed on the device by cloud_setup_kernel
-// with the canonical operation order (cloudRayMarch.comp:114-132, 199-207, 585-624, 489-497), then staged in
-// shared memory by every CTA of the march kernel (broadcast LDS instead of registers).
+// Per-frame constants of the march that feed discrete decisions, in the canonical operation order (cloudRayMarch.comp:114-132,
+// 199-207, 585-624, 489-497).  Round 1 / 2 evaluated them in a one-thread kernel and every CTA staged them in shared memory;
+// the compiler then kept the ones the march loop reads in registers and spilled them (six LDL per march step,
+// profiles/r2_cloud_final.md).  Now the HOST evaluates them per dispatch (cloud_frame_setup is __host__ __device__: IEEE
+// + - * / sqrt without contraction on both sides, the same bits -- the GPU parity tests hold the decisions they feed to the
+// oracle's) and they travel in the kernel's parameter block: every use is a constant-bank operand, no register, no load, no
+// setup launch.  Only the two jitter tables, which a lane indexes by its own pixel id / step, are staged in shared memory
+// (a divergent constant-bank index would serialise).
+struct MarchTabs {
+    float rayJitter[8][2];              // getJitterOffset(id, dim): (halton_x / W, halton_y / H) for id/2 = 0..7
+    float stepJitter[8][4];             // per-step direction offset (jx, (jx+jy)*1.18, jy, 0), j = halton / 75
+};
 struct MarchConst {
     f3 basisRight, basisUp, basisLook;  // castRay basis
     f3 eyePos;                          // -camera.eye
@@ -54,12 +63,11 @@ struct MarchConst {
     f3 lightDir;                        // normalize(SUN_LOCATION - origin)
     f3 windSkew;                        // ((WIND_DIRECTION + (0,.1,0)) * CLOUD_SPEED) * time.y
     f3 coneStep[6];                     // noise_kernel[i] (unscaled)
-    float rayJitter[8][2];              // getJitterOffset(id, dim): (halton_x / W, halton_y / H) for id/2 = 0..7
-    float stepJitter[8][4];             // per-step direction offset (jx, (jx+jy)*1.18, jy, 0), j = halton / 75
-    float covDen, covRcp;               // 1 - coverage and its refined reciprocal (nice_rcp): divisor of the coverage remap
+    float covDen;                       // 1 - coverage: divisor of the coverage remap (its refined reciprocal is per ray: RaySetup.covRcp)
     float covScale;                     // coverage / (1 - coverage): the coverage remap of a light-cone sample as one multiplication
+    MarchTabs tabs;
 };
-#define MT_MARCHCONST_WORDS (sizeof(MarchConst) / 4)
+#define MT_MARCHTABS_WORDS (sizeof(MarchTabs) / 4)
 
 // In-cloud compaction of the step-parallel march (cloud_raymarch.cu): measured, slower at 4K, off (profiles/r1_ab.md).
 #ifndef MT_STEP_COMPACT
@@ -98,7 +106,7 @@ struct CloudParams {
     Tex3D low, high;
     Tex2D curl;
     Tex2D weather;         // sampled only when tun.use_weather
-    const MarchConst* mc;  // device memory, written by cloud_setup_kernel
+    MarchConst mc;         // per-frame constants, evaluated by the host (mt_context.cu, cloud_frame_setup)
     F4* hdr;
     F4* mask;
     int W, H;
@@ -119,9 +127,37 @@ struct CloudParams {
     unsigned* tileDone;            // full-quality row-tile launches with forwarding (mtSetCloudForward): CTAs finished per tile
 };
 
+// Per-frame values of the post passes.  Like MarchConst they are evaluated by the HOST per dispatch (reproject_frame, godray_frame,
+// txaa_frame in post_core.cuh are __host__ __device__: the same IEEE operations, the same bits) and travel in the parameter
+// block.  Rounds 1 and 2 had thread 0 of every CTA evaluate them into shared memory -- a ~300-instruction serial prologue,
+// seven IEEE divisions deep, behind a barrier the other 255 threads waited at (4.6 barrier-stall cycles per issued instruction
+// in reproject_kernel, profiles/r2_passes_1080p.md).
+struct ReprojFrame {  // reprojection.comp:203-211: camera basis, ray origin, the unit-sphere origin of the inner-shell intersection
+    RayBasis basis;   // (raySphereIntersection's rO, identical for every pixel) and its C term, this shader's Halton offset
+    f3 eye, ec, o;
+    float C;
+    float jx, jy;
+    float uMax, vMax;  // (dim - 1) / dim: old_uv inside [0, max] keeps every tap inside the image (reproject_taps, fast path)
+};
+struct GodRayFrame {  // per-frame values of postProcess_GodRays.frag:74-91
+    float blend;      // dot(normalize(sun - eye), camForward); < 0 => the pass writes nothing
+    float sunx, suny; // clamped screen-space sun position
+};
+struct TxaaFrame {  // per-frame: like ReprojFrame, but with the Cloud pass's Halton variant (postProcess_TXAA.frag:63-82)
+    RayBasis basis;
+    f3 eye, ec, o;
+    float C;
+    float jx, jy;
+};
+// uv table of a W x H context (built by the host at mtCreate / mtResize: IEEE divisions, the kernels' own operands):
+//   [0, W) x / W    [W, W+H) y / H    [W+H, 2W+H) (x + .5) / W    [2W+H, 2W+2H) (y + .5) / H
+// so that a pixel's uv is two loads instead of two IEEE divisions (or a per-CTA staging pass behind a barrier).
+
 struct ReprojParams {
     CamU cam, camOld;
     TimeU tm;
+    ReprojFrame frame;
+    const float* uv;   // uv table (above)
     const F4* prev;
     F4* cur;
     int W, H;
@@ -131,11 +167,17 @@ struct ReprojParams {
 
 struct GodRayParams {
     CamU cam;
+    GodRayFrame frame;
+    const float* uv;    // uv table (above)
     float lightColor[3];
     const F4* mask;     // encoded god-ray mask (RGBA32F)
-    float2* decoded;    // (W+2) x (H+2) pairs (d(x, y), d(x+1, y)): the mask decoded per texel, ringed by the sampler's border value
-    const float2* tapRow0;  // decoded + (W+2) + 1 - MT_FLOOR_MAGIC_BITS: image texel (0, 0), biased for post_core.cuh's magic floor
+    float2* decoded;    // pitch x (H+2) pairs (d(x, y), d(x+1, y)): the mask decoded per texel, ringed by the sampler's border value
+    int pitch;          // elements per row of `decoded`: a power of two >= W + 2 on the device (mt_godray_log2pitch), W + 2 otherwise
+    int log2pitch;      // 0: pitch is not a power of two (images wider than 8190 pixels, host simulation)
+    const float2* tapRow0;  // generic path: decoded + pitch + 1 - MT_FLOOR_MAGIC_BITS: image texel (0, 0), biased for post_core.cuh's magic floor
     const float2* tapRow1;  // ... one row further
+    const char* tapBase;    // power-of-two pitch: image texel (0, 0) minus what the magic constant's bits add to the byte offset
+    const char* tapBaseWide; // the same for a 64-bit byte offset (A/B build MT_GODRAY_WIDE)
     F4* hdr;
     int W, H;
     int storage;  // MtStorage of the HDR / mask images (mt_pixel.cuh)
@@ -143,9 +185,25 @@ struct GodRayParams {
     unsigned seed;      //   uint(time.y) of the tone map's dither
 };
 
+// Row pitch of the decoded god-ray mask: the smallest power of two >= W + 2, at least 2^10 -- the tap address is then
+// (floor(y) << k) + floor(x), one LEA, and the second row a constant byte offset (post_core.cuh).  0 = too wide, generic addressing.
+#ifndef MT_GODRAY_POW2
+#define MT_GODRAY_POW2 1
+#endif
+static inline int mt_godray_log2pitch(int W)
+{
+    if (!MT_GODRAY_POW2) return 0;
+    for (int k = 10; k <= 13; ++k)
+        if ((1 << k) >= W + 2) return k;
+    return 0;
+}
+static inline size_t mt_godray_pitch(int W) { const int k = mt_godray_log2pitch(W); return k ? (size_t)1 << k : (size_t)W + 2; }
+
 struct TxaaParams {
     CamU cam, camOld;
     TimeU tm;
+    TxaaFrame frame;
+    const float* uv;       // uv table (above)
     const uint32_t* cur;   // tone-mapped LDR of this frame (RGBA8)
     const uint32_t* prev;  // presented LDR of the previous frame
     uint32_t* out;         // result (becomes this frame's LDR image)

@@ -73,10 +73,28 @@ struct LinAxis {
 // index of filter cell (x0, y0, z0): addresses the quad copy and (>> 5, & 31) the empty-cell bitmap
 MT_DEVICE unsigned tex_cell(const Tex3D& T, unsigned x0, unsigned y0, unsigned z0) { return (z0 * (unsigned)T.h + y0) * (unsigned)T.w + x0; }
 
+// MAGIC (device, STD kernels): floor(u) without the conversion pipe.  u + 1.5 * 2^23 in round-down mode leaves floor(u) in the
+// low mantissa bits (two's complement below the hidden bits, so `& (n - 1)` is the REPEAT wrap as before) and, minus the
+// constant, as a float -- exactly floorf(u) for |u| < 2^22; x and y share ONE packed add.  The same floor, the same
+// subtraction: bit-identical weights and indices.  The host selects these kernels only when the frame's constants keep every
+// texture coordinate far inside that range (mt_std_dims, cloud_raymarch.cu).  F2I.FLOOR + I2FP per axis before: 2.5 % + 2.3 %
+// of the march kernel's instructions, the former on the quarter-rate pipe (profiles/r2_cloud_final.md).
+template <bool MAGIC = false>
 MT_DEVICE LinAxis lin_axis_repeat(float s, int n)
 {
     LinAxis a;
     float u = fmaf(s, (float)n, -0.5f);  // == s*n - 0.5 bit for bit: n is a power of two, the product is never rounded
+#if !defined(MT_HOSTSIM)
+    if (MAGIC) {
+        float t;
+        asm("add.rm.f32 %0, %1, %2;" : "=f"(t) : "f"(u), "f"(MT_FLOOR_MAGIC));
+        a.w1 = u - (t - MT_FLOOR_MAGIC);
+        a.w0 = 1.0f - a.w1;
+        a.i0 = __float_as_uint(t) & (unsigned)(n - 1);
+        a.i1 = (a.i0 + 1u) & (unsigned)(n - 1);
+        return a;
+    }
+#endif
     int fi = mt_floor2i(u);   // F2I.FLOOR (XU) ...
     float fl = (float)fi;     // ... and I2FP back (ALU): == floorf(u) for |u| < 2^24, one XU op instead of two
     a.w1 = u - fl;
@@ -87,9 +105,23 @@ MT_DEVICE LinAxis lin_axis_repeat(float s, int n)
 }
 
 // x and y axes of one sample computed as a pair (FMUL2 / FADD2), identical per-component arithmetic
+template <bool MAGIC = false>
 MT_DEVICE void lin_axes_xy(P2 st, int nx, int ny, LinAxis& X, LinAxis& Y)
 {
     const P2 u = fma2(st, pk2((float)nx, (float)ny), bc2(-0.5f));  // exact product (power-of-two extent): == s*n - 0.5
+#if !defined(MT_HOSTSIM)
+    if (MAGIC) {
+        P2 t;
+        asm("add.rm.f32x2 %0, %1, %2;" : "=l"(t) : "l"(u), "l"(bc2(MT_FLOOR_MAGIC)));
+        const P2 w1 = sub2(u, sub2(t, bc2(MT_FLOOR_MAGIC)));
+        const P2 w0 = sub2(bc2(1.0f), w1);
+        X.w1 = lo2(w1); X.w0 = lo2(w0);
+        Y.w1 = hi2(w1); Y.w0 = hi2(w0);
+        X.i0 = (unsigned)t & (unsigned)(nx - 1); X.i1 = (X.i0 + 1u) & (unsigned)(nx - 1);
+        Y.i0 = (unsigned)(t >> 32) & (unsigned)(ny - 1); Y.i1 = (Y.i0 + 1u) & (unsigned)(ny - 1);
+        return;
+    }
+#endif
     const float ux = lo2(u), uy = hi2(u);
     int fx = mt_floor2i(ux), fy = mt_floor2i(uy);
     P2 w1 = sub2(u, pk2((float)fx, (float)fy));
@@ -149,6 +181,18 @@ MT_DEVICE Weights8 filter_weights(const LinAxis& X, const LinAxis& Y, const LinA
     fma2(bc2(hi2(w.w11)), CH(t111), fma2(bc2(lo2(w.w11)), CH(t110), fma2(bc2(hi2(w.w10)), CH(t101),                      \
     fma2(bc2(lo2(w.w10)), CH(t100), fma2(bc2(hi2(w.w01)), CH(t011), fma2(bc2(lo2(w.w01)), CH(t010),                      \
     fma2(bc2(hi2(w.w00)), CH(t001), mul2(bc2(lo2(w.w00)), CH(t000)))))))))
+
+// the canonical four-channel filter of a cell whose two slices' quads are already in registers
+MT_DEVICE Rgba tex3d_rgba_quads(const Quad& q0, const Quad& q1, const LinAxis& X, const LinAxis& Y, const LinAxis& Z)
+{
+    const uint32_t t000 = q0.x, t001 = q0.y, t010 = q0.z, t011 = q0.w, t100 = q1.x, t101 = q1.y, t110 = q1.z, t111 = q1.w;
+    const Weights8 w = filter_weights(X, Y, Z);
+    const P2 rg = mul2(MT_ACC2(MT_RG), bc2(MT_INV255));
+    const P2 ba = mul2(MT_ACC2(MT_BA), bc2(MT_INV255));
+    Rgba o;
+    o.r = lo2(rg); o.g = hi2(rg); o.b = lo2(ba); o.a = hi2(ba);
+    return o;
+}
 
 MT_DEVICE Rgba tex3d_rgba_axes(const Tex3D& T, const LinAxis& X, const LinAxis& Y, const LinAxis& Z, unsigned cell)
 {
@@ -211,6 +255,30 @@ MT_DEVICE uint32_t rf_pack(uint32_t t)
 #define MT_F13(t) __uint_as_float((t) & 0x00ffe000u)
 #endif
 #define MT_RFP(t) pk2(MT_B3(t), MT_F13(t))
+// MT_CONE_LERP: the (r, F) pair is radiance only and its decisions are guarded (cloud_core.cuh, cone_term_rf), so it is filtered
+// as seven nested lerps a + f (b - a) on the raw denormal-scaled words: no weight products, 15 packed operations instead of 19
+// and a dependent chain of three lerps instead of eight multiply-adds.  Differences and lerps are multiples of 2^-149 = 2^-16
+// of one byte step, so each lerp is within 6e-8 of full scale of the exact one: < 2e-7 in (r, fbm) (measured 1.6e-7 against
+// the real-number filter, tests/test_exact_tricks.py), inside what MT_RF_GUARD allows.  Every (r, F) fetch of every kernel goes
+// through this one function, so the step-parallel and the sequential march stay bit-identical to each other.
+#ifndef MT_CONE_LERP
+#define MT_CONE_LERP 1
+#endif
+MT_DEVICE P2 rf_filter(uint32_t t000, uint32_t t001, uint32_t t010, uint32_t t011, uint32_t t100, uint32_t t101, uint32_t t110,
+                       uint32_t t111, const LinAxis& X, const LinAxis& Y, const LinAxis& Z)
+{
+#if MT_CONE_LERP
+    const P2 fx = bc2(X.w1), fy = bc2(Y.w1), fz = bc2(Z.w1);
+    const P2 p000 = MT_RFP(t000), p010 = MT_RFP(t010), p100 = MT_RFP(t100), p110 = MT_RFP(t110);
+    const P2 l00 = fma2(fx, sub2(MT_RFP(t001), p000), p000), l01 = fma2(fx, sub2(MT_RFP(t011), p010), p010);
+    const P2 l10 = fma2(fx, sub2(MT_RFP(t101), p100), p100), l11 = fma2(fx, sub2(MT_RFP(t111), p110), p110);
+    const P2 m0 = fma2(fy, sub2(l01, l00), l00), m1 = fma2(fy, sub2(l11, l10), l10);
+    return mul2(fma2(fz, sub2(m1, m0), m0), bc2((float)(0x1p133 / 255.0)));  // undoes the 2^-133 of the byte placement (2^133 is no binary32)
+#else
+    const Weights8 w = filter_weights(X, Y, Z);
+    return mul2(MT_ACC2(MT_RFP), bc2(MT_INV255));
+#endif
+}
 // returns (r, fbm) of the filtered sample, both already divided by 255 (and F by 8)
 MT_DEVICE P2 tex3d_rf_axes(const Tex3D& T, const LinAxis& X, const LinAxis& Y, const LinAxis& Z, unsigned cell)
 {
@@ -242,8 +310,7 @@ MT_DEVICE P2 tex3d_rf_axes(const Tex3D& T, const LinAxis& X, const LinAxis& Y, c
         t110 = rf_pack(MT_LDG(tx + (r11 + X.i0))); t111 = rf_pack(MT_LDG(tx + (r11 + X.i1)));
     }
 #endif
-    const Weights8 w = filter_weights(X, Y, Z);
-    return mul2(MT_ACC2(MT_RFP), bc2(MT_INV255));
+    return rf_filter(t000, t001, t010, t011, t100, t101, t110, t111, X, Y, Z);
 }
 
 MT_DEVICE Rgba tex3d_rgba(const Tex3D& T, float s, float t, float r)
@@ -277,9 +344,11 @@ MT_DEVICE bool occ_cell_may_be_cloud(const Tex3D& T, unsigned cell)
 }
 
 // Same filter, only the first three channels (the high-frequency volume's alpha is never read).
+template <bool MAGIC = false>
 MT_DEVICE Rgba tex3d_rgb(const Tex3D& T, float s, float t, float r)
 {
-    LinAxis X = lin_axis_repeat(s, T.w), Y = lin_axis_repeat(t, T.h), Z = lin_axis_repeat(r, T.d);
+    LinAxis X, Y, Z = lin_axis_repeat<MAGIC>(r, T.d);
+    lin_axes_xy<MAGIC>(pk2(s, t), T.w, T.h, X, Y);
     const unsigned W = (unsigned)T.w, H = (unsigned)T.h;
     uint32_t t000, t001, t010, t011, t100, t101, t110, t111;
 #if MT_TEX_QUADS
@@ -318,9 +387,11 @@ MT_DEVICE Rgba tex3d_rgb(const Tex3D& T, float s, float t, float r)
 }
 
 // Bilinear, first two channels (curl noise: only .xy is read, cloudRayMarch.comp:545-546).
+template <bool MAGIC = false>
 MT_DEVICE void tex2d_rg(const Tex2D& T, float s, float t, float& r, float& g)
 {
-    LinAxis X = lin_axis_repeat(s, T.w), Y = lin_axis_repeat(t, T.h);
+    LinAxis X, Y;
+    lin_axes_xy<MAGIC>(pk2(s, t), T.w, T.h, X, Y);
     const unsigned W = (unsigned)T.w;
     uint32_t t00, t01, t10, t11;
 #if MT_TEX_QUADS

@@ -5,16 +5,8 @@
 #include "mt_params.h"
 
 // ---- Reprojection ------------------------------------------------------------------------------------------------
-// Per-frame values of reprojection.comp:203-211: camera basis, ray origin, the unit-sphere origin of the inner-shell
-// intersection (raySphereIntersection's rO, identical for every pixel) and its C term, this shader's Halton offset.
-struct ReprojFrame {
-    RayBasis basis;
-    f3 eye, ec, o;
-    float C;
-    float jx, jy;
-};
-
-MT_DEVICE ReprojFrame reproject_frame(const ReprojParams& P)
+// ReprojFrame (mt_params.h): the per-frame values of reprojection.comp:203-211, evaluated by the host per dispatch.
+MT_HD ReprojFrame reproject_frame(const ReprojParams& P)
 {
     ReprojFrame F;
     F.basis = ray_basis(P.cam);
@@ -26,10 +18,26 @@ MT_DEVICE ReprojFrame reproject_frame(const ReprojParams& P)
     const int hj = (P.tm.frameCountMod16 >> 1) & 3;
     F.jx = P.tm.halton[hj] / (float)P.W;
     F.jy = P.tm.halton[4 + hj] / (float)P.H;
+    F.uMax = ((float)P.W - 1.0f) / (float)P.W;
+    F.vMax = ((float)P.H - 1.0f) / (float)P.H;
     return F;
 }
 
-// Returns the ten clamped tap positions (linear index y*W + x) of the pixel whose uv is (u, v) = (x/W, y/H).
+// Returns the ten clamped tap positions (linear index y*W + x, plus MT_TAP_BIAS) of the pixel whose uv is (u, v) = (x/W, y/H).
+// Device fast path (MT_REPROJ_FAST): a tap lies between old_uv and uv, so when old_uv is inside [0, (dim-1)/dim] no tap can
+// round outside the image and the four integer clamps per tap are dead; ivec2(round(c)) then comes from adding 2^23 (the
+// integer lands in the low mantissa bits, round-half-even like F2I.RN) instead of two conversions on the quarter-rate pipe:
+// 12 instead of 16 instructions per tap, the same indices.  The sums are scalar adds: a packed add fed by the packed
+// multiply would be contracted into one FFMA2 (mt_math.cuh) and round c * dim + 2^23 once instead of twice.  Every index carries
+// the bias the fast path leaves in it (0x4B000000, the bits of 2^23); the kernel takes it out of the image's base address.
+#ifndef MT_REPROJ_FAST
+#define MT_REPROJ_FAST 1
+#endif
+#if defined(MT_HOSTSIM) || !MT_REPROJ_FAST
+#define MT_TAP_BIAS 0
+#else
+#define MT_TAP_BIAS 0x4B000000
+#endif
 MT_DEVICE void reproject_taps(const ReprojParams& P, const ReprojFrame& F, float u, float v, int taps[10])
 {
     const float fw = (float)P.W, fh = (float)P.H;  // no y flip here (reprojection.comp:200-201)
@@ -56,6 +64,21 @@ MT_DEVICE void reproject_taps(const ReprojParams& P, const ReprojFrame& F, float
     const float old_u = (q.x / P.cam.tanFovBy2[0]) * 0.5f + 0.5f;
     const float old_v = (q.y / P.cam.tanFovBy2[1]) * 0.5f + 0.5f;
     const P2 mv = pk2(old_u - u, old_v - v), dim = pk2(fw, fh);
+#if !defined(MT_HOSTSIM) && MT_REPROJ_FAST
+    // (dim - 1) / dim rounded: old * dim <= dim - 1 + 5e-4 and the taps' own roundings move them by < 1e-3 of a pixel,
+    // so every tap rounds into [0, dim - 1]; NaN fails the comparisons
+    if (old_u >= 0.0f && old_u <= F.uMax && old_v >= 0.0f && old_v <= F.vMax) {
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+            const float f = (float)i / 10.0f;
+            const P2 b = mul2(mv, bc2(f));
+            const P2 c = mul2(pk2(old_u - lo2(b), old_v - hi2(b)), dim);
+            const unsigned tx = __float_as_uint(lo2(c) + 8388608.0f), ty = __float_as_uint(hi2(c) + 8388608.0f);
+            taps[i] = (int)((ty & 0x007fffffu) * (unsigned)P.W + tx);  // cy * W + cx + MT_TAP_BIAS
+        }
+        return;
+    }
+#endif
 #pragma unroll
     for (int i = 0; i < 10; ++i) {
         const float f = (float)i / 10.0f;
@@ -64,17 +87,12 @@ MT_DEVICE void reproject_taps(const ReprojParams& P, const ReprojFrame& F, float
         const P2 c = mul2(pk2(old_u - lo2(b), old_v - hi2(b)), dim);
         const int cx = min(max(mt_round2i(lo2(c)), 0), P.W - 1);
         const int cy = min(max(mt_round2i(hi2(c)), 0), P.H - 1);
-        taps[i] = cy * P.W + cx;
+        taps[i] = cy * P.W + cx + MT_TAP_BIAS;
     }
 }
 
 // ---- God rays ----------------------------------------------------------------------------------------------------
-struct GodRayFrame {  // per-frame values of postProcess_GodRays.frag:74-91
-    float blend;      // dot(normalize(sun - eye), camForward); < 0 => the pass writes nothing
-    float sunx, suny; // clamped screen-space sun position
-};
-
-MT_DEVICE GodRayFrame godray_frame(const CamU& cam)
+MT_HD GodRayFrame godray_frame(const CamU& cam)
 {
     GodRayFrame g;
     f3 toSun = norm3(mk3(0.0f, 1.0f, 0.0f) - mk3(cam.eye[0], cam.eye[1], cam.eye[2]));
@@ -115,13 +133,15 @@ MT_DEVICE float mask_texel_decode(F4 t)
 // coordinates comes from ONE packed add in round-down mode against 1.5 * 2^23 (the integer lands in the low mantissa bits,
 // the float floor is the same value minus the constant) -- no F2I / I2F on the quarter-rate pipe; the filter is
 // a + ay (c - a) on both columns at once, then in x: ~19 instructions per tap instead of 31 (profiles/r2_passes_1080p.md).
-#define MT_FLOOR_MAGIC 12582912.0f     /* 1.5 * 2^23: x + MAGIC rounded down = MAGIC + floor(x) for |x| < 2^22 */
-#define MT_FLOOR_MAGIC_BITS 0x4B400000
+#ifndef MT_GODRAY_WIDE
+#define MT_GODRAY_WIDE 0
+#endif
 #ifndef MT_GODRAY_SCALAR
 #define MT_GODRAY_SCALAR 0
 #endif
 #if MT_GODRAY_SCALAR && !defined(MT_HOSTSIM)
 // A/B: the same tap with scalar instructions only (is the FMA pipe, which executes an fp32x2 instruction in two passes, the limit?)
+template <int K>
 MT_DEVICE float mask_decode(const GodRayParams& P, P2 st)
 {
     const float mx = lo2(st) * (float)P.W, my = hi2(st) * (float)P.H;
@@ -136,6 +156,7 @@ MT_DEVICE float mask_decode(const GodRayParams& P, P2 st)
     return fmaf(ax, r - l, l);
 }
 #else
+template <int K>
 MT_DEVICE float mask_decode(const GodRayParams& P, P2 st)
 {
     const float2* dec = P.decoded;
@@ -145,7 +166,7 @@ MT_DEVICE float mask_decode(const GodRayParams& P, P2 st)
     // No clamp: the march runs from the pixel centre towards the sun position, which main() clamps to [0,1]
     // (postProcess_GodRays.frag:90), so u*W - 0.5 lies in [-0.5, W - 0.5] and floor() in [-1, W-1] -- the ring.  The 100
     // roundings of `uv -= delta` move u*W by < 0.05 texel even at W = 7680, against a margin of 0.5.
-    const int pitch = W + 2;
+    const int pitch = P.pitch;
 #if defined(MT_HOSTSIM)
     const float fx = floorf(ux), fy = floorf(uy);
     const int x0 = (int)fx, y0 = (int)fy;
@@ -156,6 +177,27 @@ MT_DEVICE float mask_decode(const GodRayParams& P, P2 st)
     P2 t;
     asm("add.rm.f32x2 %0, %1, %2;" : "=l"(t) : "l"(pk2(ux, uy)), "l"(bc2(MT_FLOOR_MAGIC)));
     const P2 fl = sub2(t, bc2(MT_FLOOR_MAGIC));                   // exact
+    if (K > 0) {
+        // Power-of-two pitch 2^K (K >= 10): the bits of t.y are 0x4B400000 + floor(y), and 0x4B400000 << K vanishes mod 2^32, so
+        // (t.y << K) + t.x = (floor(y) << K) + floor(x) + 0x4B400000 in ONE LEA; times eight (mod 2^32) that is the texel's byte
+        // offset plus the constant 0x5A000000, which the host has subtracted from the base.  The second row is an immediate
+        // offset of the same address: one address computation on the ALU pipe (LEA + carry) for both loads, where the generic
+        // path spends IADD3 + IMAD + 2 x IMAD.WIDE -- the latter three on the FMA-heavy pipe, the kernel's busiest (70 %,
+        // profiles/r2_passes_1080p.md) because the packed fp32x2 instructions live there as well.
+        unsigned tx, ty;
+        asm("mov.b64 {%0, %1}, %2;" : "=r"(tx), "=r"(ty) : "l"(t));
+        const unsigned i0 = (ty << K) + tx;
+#if MT_GODRAY_WIDE   // A/B: one IMAD.WIDE (FMA-heavy pipe) instead of LEA + carry (ALU pipe)
+        const char* p = P.tapBaseWide + (size_t)i0 * 8u;
+#else
+        const char* p = P.tapBase + (i0 << 3);
+#endif
+        const float2 top = MT_LDG(reinterpret_cast<const float2*>(p)), bot = MT_LDG(reinterpret_cast<const float2*>(p + ((size_t)8 << K)));
+        const P2 a1 = sub2(pk2(ux, uy), fl);                      // (ax, ay)
+        const P2 t2 = pk2(top.x, top.y), b2 = pk2(bot.x, bot.y);
+        const P2 lr = fma2(bc2(hi2(a1)), sub2(b2, t2), t2);
+        return fmaf(lo2(a1), hi2(lr) - lo2(lr), lo2(lr));
+    }
     const int xb = (int)(unsigned)t, y0 = (int)(unsigned)(t >> 32) - MT_FLOOR_MAGIC_BITS;
     // the host passes the two row bases (image texel (0, 0) and (0, 1) inside the ring, the x bias of the magic constant
     // folded in): two opaque loop-invariant pointers, one IMAD.WIDE per load instead of 64-bit pointer arithmetic
@@ -177,10 +219,17 @@ MT_DEVICE float mask_decode(const GodRayParams& P, P2 st)
 #endif
 
 // The radial accumulation of one fragment; returns the colour to ADD to the HDR pixel (already * blend).
+template <int K>
+MT_DEVICE F4 godray_pixel_uv(const GodRayParams& P, const GodRayFrame& G, float u, float v);
+template <int K = 0>
 MT_DEVICE F4 godray_pixel(const GodRayParams& P, const GodRayFrame& G, int x, int y)
 {
-    const float u = ((float)x + 0.5f) / (float)P.W;
-    const float v = ((float)y + 0.5f) / (float)P.H;
+    return godray_pixel_uv<K>(P, G, ((float)x + 0.5f) / (float)P.W, ((float)y + 0.5f) / (float)P.H);
+}
+// (u, v) = the fragment's uv, ((x + .5) / W, (y + .5) / H): the kernel reads it from the context's uv table
+template <int K>
+MT_DEVICE F4 godray_pixel_uv(const GodRayParams& P, const GodRayFrame& G, float u, float v)
+{
     const float du = ((u - G.sunx) / 100.0f) * 1.0f;
     const float dv = ((v - G.suny) / 100.0f) * 1.0f;
     P2 uv = pk2(u, v);
@@ -196,7 +245,7 @@ MT_DEVICE F4 godray_pixel(const GodRayParams& P, const GodRayFrame& G, int x, in
 #define MT_GR_UNROLL_(n) MT_GR_PRAGMA_(unroll n)
     MT_GR_UNROLL_(MT_GODRAY_UNROLL)
     for (int i = 0; i < 100; ++i) {
-        sum += mask_decode(P, uv);
+        sum += mask_decode<K>(P, uv);
         uv = sub2(uv, duv);
     }
     F4 o;
@@ -244,13 +293,7 @@ MT_DEVICE unsigned tonemap_pixel(const ToneMapParams& P, F4 in, int x, int y)
 }
 
 // ---- TXAA (postProcess_TXAA.frag:171-270) ---------------------------------------------------------------
-struct TxaaFrame {  // per-frame: like ReprojFrame, but with the Cloud pass's Halton variant (postProcess_TXAA.frag:63-82)
-    RayBasis basis;
-    f3 eye, ec, o;
-    float C;
-    float jx, jy;
-};
-MT_DEVICE TxaaFrame txaa_frame(const TxaaParams& P)
+MT_HD TxaaFrame txaa_frame(const TxaaParams& P)
 {
     TxaaFrame F;
     F.basis = ray_basis(P.cam);

@@ -18,21 +18,18 @@
 template <int ST>
 __global__ void __launch_bounds__(256) reproject_kernel(const __grid_constant__ ReprojParams P)
 {
-    __shared__ ReprojFrame frame;
-    __shared__ float su[32], sv[8];
-    if (threadIdx.x == 0) frame = reproject_frame(P);
-    if (threadIdx.x >= 32 && threadIdx.x < 64) su[threadIdx.x - 32] = (float)(blockIdx.x * 32 + (threadIdx.x - 32)) / (float)P.W;
-    if (threadIdx.x >= 64 && threadIdx.x < 72) sv[threadIdx.x - 64] = (float)(blockIdx.y * 8 + (threadIdx.x - 64)) / (float)P.H;
-    __syncthreads();
     const int x = blockIdx.x * 32 + (threadIdx.x & 31);
     const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
     if (x >= P.W || y >= P.H) return;
     int taps[10];
-    reproject_taps(P, frame, su[threadIdx.x & 31], sv[threadIdx.x >> 5], taps);
+    // frame constants from the parameter block, (x / W, y / H) from the context's uv table: no shared memory, no barrier
+    reproject_taps(P, P.frame, __ldg(P.uv + x), __ldg(P.uv + P.W + y), taps);
     P2 axy = pk2(0.0f, 0.0f), azw = pk2(0.0f, 0.0f);
+    // the tap indices carry MT_TAP_BIAS (post_core.cuh): taken out of the base address, never dereferenced without an index
+    const char* prevB = reinterpret_cast<const char*>(P.prev) - (size_t)MT_TAP_BIAS * (ST == MT_PX_F16 ? 8u : 16u);
 #pragma unroll
     for (int i = 0; i < 10; ++i) {
-        const float4 t = px_load_ro(P.prev, (size_t)taps[i], ST);
+        const float4 t = px_load_ro(prevB, (size_t)(unsigned)taps[i], ST);
         axy = add2(axy, pk2(t.x, t.y));
         azw = add2(azw, pk2(t.z, t.w));
     }
@@ -43,7 +40,7 @@ __global__ void __launch_bounds__(256) reproject_kernel(const __grid_constant__ 
     px_store(P.cur, idx, acc, ST);
     if (P.taps) {
 #pragma unroll
-        for (int i = 0; i < 10; ++i) P.taps[idx * 10 + i] = taps[i];
+        for (int i = 0; i < 10; ++i) P.taps[idx * 10 + i] = taps[i] - MT_TAP_BIAS;
     }
 }
 
@@ -66,7 +63,7 @@ __global__ void __launch_bounds__(256) mask_decode_kernel(const __grid_constant_
     float dn = __shfl_down_sync(0xffffffffu, d, 1);          // the right-hand neighbour is the next lane's texel ...
     if ((threadIdx.x & 31) == 31) dn = mask_decoded_at<ST>(P, x + 1, y);  // ... except at the end of the warp's row segment
     if (x > P.W || y > P.H) return;
-    P.decoded[(size_t)(y + 1) * (size_t)(P.W + 2) + (size_t)(x + 1)] = make_float2(d, dn);
+    P.decoded[(size_t)(y + 1) * (size_t)P.pitch + (size_t)(x + 1)] = make_float2(d, dn);
 }
 
 // ---- The god-ray image as what it is -- one float per pixel ("grey-scale", the value EncodeFloatRGBA spread over four
@@ -101,12 +98,10 @@ cudaError_t mt_launch_mask_grey(const GodRayParams& P, float* out, cudaStream_t 
 #define MT_GODRAY_WARPS 4   /* warps (= pixel rows for 32x1 warps) per CTA */
 #endif
 #define MT_GODRAY_CTA_H (MT_GODRAY_LOG2W == 5 ? MT_GODRAY_WARPS : 2 * MT_GODRAY_WH)     /*  8,  4,  4 */
-template <int ST>
+template <int ST, int K>
 __global__ void __launch_bounds__(MT_GODRAY_LOG2W == 5 ? 32 * MT_GODRAY_WARPS : 128) godrays_kernel(const __grid_constant__ GodRayParams P)
 {
-    __shared__ GodRayFrame frame;
-    if (threadIdx.x == 0) frame = godray_frame(P.cam);
-    __syncthreads();
+    const GodRayFrame& frame = P.frame;
     const bool lit = !(frame.blend < 0.0f);  // sun behind the camera: the fragment shader returns before any store
     if (!lit && !P.ldr) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -117,7 +112,7 @@ __global__ void __launch_bounds__(MT_GODRAY_LOG2W == 5 ? 32 * MT_GODRAY_WARPS : 
     const size_t idx = (size_t)y * P.W + x;
     float4 c = px_load(P.hdr, idx, ST);
     if (lit) {
-        F4 g = godray_pixel(P, frame, x, y);
+        F4 g = godray_pixel_uv<K>(P, frame, __ldg(P.uv + P.W + P.H + x), __ldg(P.uv + 2 * P.W + P.H + y));
         c.x += g.x; c.y += g.y; c.z += g.z; c.w += g.w;
         if (ST != MT_PX_F32) c = px_round_f16(c);  // the tone map below reads the stored value
         px_store(P.hdr, idx, c, ST);
@@ -148,16 +143,10 @@ __global__ void __launch_bounds__(256) tonemap_kernel(const __grid_constant__ To
 // ---- TXAA: one pixel per thread; 9 neighbour + 4 history texels are L1 hits, compulsory traffic 4 + 4 + 4 B/pixel ----
 __global__ void __launch_bounds__(256) txaa_kernel(const __grid_constant__ TxaaParams P)
 {
-    __shared__ TxaaFrame frame;
-    __shared__ float su[32], sv[8];
-    if (threadIdx.x == 0) frame = txaa_frame(P);
-    if (threadIdx.x >= 32 && threadIdx.x < 64) su[threadIdx.x - 32] = ((float)(blockIdx.x * 32 + (threadIdx.x - 32)) + 0.5f) / (float)P.W;
-    if (threadIdx.x >= 64 && threadIdx.x < 72) sv[threadIdx.x - 64] = ((float)(blockIdx.y * 8 + (threadIdx.x - 64)) + 0.5f) / (float)P.H;
-    __syncthreads();
     const int x = blockIdx.x * 32 + (threadIdx.x & 31);
     const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
     if (x >= P.W || y >= P.H) return;
-    P.out[(size_t)y * P.W + x] = txaa_pixel(P, frame, x, y, su[threadIdx.x & 31], sv[threadIdx.x >> 5]);
+    P.out[(size_t)y * P.W + x] = txaa_pixel(P, P.frame, x, y, __ldg(P.uv + P.W + P.H + x), __ldg(P.uv + 2 * P.W + P.H + y));
 }
 cudaError_t mt_launch_txaa(const TxaaParams& P, cudaStream_t stream)
 {
@@ -174,13 +163,26 @@ cudaError_t mt_launch_reproject(const ReprojParams& P, cudaStream_t stream)
     else reproject_kernel<MT_PX_F32><<<grid, 256, 0, stream>>>(P);
     return cudaGetLastError();
 }
+template <int K>
+static void mt_launch_godrays_k(const GodRayParams& P, dim3 grid, unsigned threads, cudaStream_t stream)
+{
+    if (P.storage == MT_PX_F16) godrays_kernel<MT_PX_F16, K><<<grid, threads, 0, stream>>>(P);
+    else if (P.storage == MT_PX_F16_EMULATE) godrays_kernel<MT_PX_F16_EMULATE, K><<<grid, threads, 0, stream>>>(P);
+    else godrays_kernel<MT_PX_F32, K><<<grid, threads, 0, stream>>>(P);
+}
 cudaError_t mt_launch_godrays(const GodRayParams& P0, cudaStream_t stream)
 {
     GodRayParams P = P0;
-    // biased row bases of the tap loads (post_core.cuh, mask_decode): never dereferenced without the index added back
+    P.log2pitch = mt_godray_log2pitch(P.W);
+    P.pitch = (int)mt_godray_pitch(P.W);  // the context allocates `decoded` with this pitch (mt_context.cu)
+    // biased bases of the tap loads (post_core.cuh, mask_decode): never dereferenced without the index added back
     P.tapRow0 = reinterpret_cast<const float2*>(reinterpret_cast<uintptr_t>(P.decoded) +
-                                                ((intptr_t)(P.W + 2) + 1 - (intptr_t)MT_FLOOR_MAGIC_BITS) * (intptr_t)sizeof(float2));
-    P.tapRow1 = reinterpret_cast<const float2*>(reinterpret_cast<uintptr_t>(P.tapRow0) + (intptr_t)(P.W + 2) * (intptr_t)sizeof(float2));
+                                                ((intptr_t)P.pitch + 1 - (intptr_t)MT_FLOOR_MAGIC_BITS) * (intptr_t)sizeof(float2));
+    P.tapRow1 = reinterpret_cast<const float2*>(reinterpret_cast<uintptr_t>(P.tapRow0) + (intptr_t)P.pitch * (intptr_t)sizeof(float2));
+    P.tapBase = reinterpret_cast<const char*>(reinterpret_cast<uintptr_t>(P.decoded) + ((intptr_t)P.pitch + 1) * (intptr_t)sizeof(float2) -
+                                              (intptr_t)(uint32_t)((uint32_t)MT_FLOOR_MAGIC_BITS << 3));
+    P.tapBaseWide = reinterpret_cast<const char*>(reinterpret_cast<uintptr_t>(P.decoded) + ((intptr_t)P.pitch + 1) * (intptr_t)sizeof(float2) -
+                                                  (intptr_t)MT_FLOOR_MAGIC_BITS * 8);
     dim3 dgrid((unsigned)((P.W + 2 + 31) / 32), (unsigned)((P.H + 2 + 7) / 8), 1);
     if (P.storage == MT_PX_F16) mask_decode_kernel<MT_PX_F16><<<dgrid, 256, 0, stream>>>(P);
     else mask_decode_kernel<MT_PX_F32><<<dgrid, 256, 0, stream>>>(P);
@@ -188,9 +190,13 @@ cudaError_t mt_launch_godrays(const GodRayParams& P0, cudaStream_t stream)
     if (e != cudaSuccess) return e;
     dim3 grid((unsigned)((P.W + MT_GODRAY_CTA_W - 1) / MT_GODRAY_CTA_W), (unsigned)((P.H + MT_GODRAY_CTA_H - 1) / MT_GODRAY_CTA_H), 1);
     const unsigned threads = MT_GODRAY_LOG2W == 5 ? 32 * MT_GODRAY_WARPS : 128;
-    if (P.storage == MT_PX_F16) godrays_kernel<MT_PX_F16><<<grid, threads, 0, stream>>>(P);
-    else if (P.storage == MT_PX_F16_EMULATE) godrays_kernel<MT_PX_F16_EMULATE><<<grid, threads, 0, stream>>>(P);
-    else godrays_kernel<MT_PX_F32><<<grid, threads, 0, stream>>>(P);
+    switch (P.log2pitch) {
+    case 10: mt_launch_godrays_k<10>(P, grid, threads, stream); break;
+    case 11: mt_launch_godrays_k<11>(P, grid, threads, stream); break;
+    case 12: mt_launch_godrays_k<12>(P, grid, threads, stream); break;
+    case 13: mt_launch_godrays_k<13>(P, grid, threads, stream); break;
+    default: mt_launch_godrays_k<0>(P, grid, threads, stream); break;
+    }
     return cudaGetLastError();
 }
 cudaError_t mt_launch_tonemap(const ToneMapParams& P, cudaStream_t stream)

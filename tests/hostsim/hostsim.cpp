@@ -59,7 +59,8 @@ int hs_cloud(const MtCameraUBO* cam, const MtTimeUBO* tm, const MtTuning* tun, c
     const bool std_dims = lw == 128 && lh == 128 && ld == 128 && hw == 32 && hh == 32 && hd == 32 && cw == 128 && ch == 128;
     MarchConst M;
     cloud_frame_setup(P.cam, P.tm, P.tun, M);
-    cloud_frame_jitter(P.tm, W, H, M);
+    cloud_frame_jitter(P.tm, W, H, M.tabs);
+    const MarchTabs& J = M.tabs;
     RayCounters cnt = { 0, 0, 0, 0, 0, 0 };
     unsigned long long tot[6] = { 0, 0, 0, 0, 0, 0 };
     const int gw = full == 1 ? W : P.tx, gh = full == 1 ? H : P.ty;  // full: 0 = 1-of-16, 1 = all pixels, 2 = 1-of-16 step-parallel
@@ -89,7 +90,7 @@ int hs_cloud(const MtCameraUBO* cam, const MtTimeUBO* tm, const MtTuning* tun, c
                 // (ray, step) sample evaluated on its own -- last step first, to make the independence explicit -- and
                 // the fold in step order.
                 m.x = m.y = m.z = m.w = 0.0f;
-                RaySetup R = cloud_ray_setup(P, M, px, py, id, h);
+                RaySetup R = cloud_ray_setup(P, M, J, px, py, id, h);
                 if (R.branch == 2) {
                     float tk[MT_STEP_SLICES];
                     int n = 0;
@@ -100,9 +101,9 @@ int hs_cloud(const MtCameraUBO* cam, const MtTimeUBO* tm, const MtTuning* tun, c
                     const ConeOffsets noCache = { nullptr, 0 };
                     for (int k = n - 1; k >= 0; --k) {
                         const int jidx = (P.tm.frameCountMod16 + mt_f2i(tk[k])) & 15;
-                        S[k] = tun->use_weather ? cloud_step_sample<false, true, 0>(P, M, R, jidx, tk[k], none, noCache)
-                                 : std_dims     ? cloud_step_sample<false, false, 1>(P, M, R, jidx, tk[k], none, noCache)   // as cloud_steps_kernel<false, true>
-                                                : cloud_step_sample<false, false, 0>(P, M, R, jidx, tk[k], none, noCache);
+                        S[k] = tun->use_weather ? cloud_step_sample<false, true, 0>(P, M, J, R, jidx, tk[k], none, noCache)
+                                 : std_dims     ? cloud_step_sample<false, false, 1>(P, M, J, R, jidx, tk[k], none, noCache)   // as cloud_steps_kernel<false, true>
+                                                : cloud_step_sample<false, false, 0>(P, M, J, R, jidx, tk[k], none, noCache);
                     }
                     float accum = 0.0f, transmittance = 1.0f, color = 0.0f;
                     for (int k = 0; k < R.nsteps; ++k)
@@ -113,10 +114,10 @@ int hs_cloud(const MtCameraUBO* cam, const MtTimeUBO* tm, const MtTuning* tun, c
                 memcpy(mask + 4 * idx, &m, 16);
                 continue;
             }
-            if (tun->use_weather) cloud_ray<true, true, true, 0>(P, M, px, py, id, h, m, cnt, debug ? debug + idx : &scratch, coneXYZ, 1);
+            if (tun->use_weather) cloud_ray<true, true, true, 0>(P, M, J, px, py, id, h, m, cnt, debug ? debug + idx : &scratch, coneXYZ, 1);
             else if (std_dims)  // STD: extents as immediates, light-cone samples from the (r, F) form
-                cloud_ray<true, true, false, 1>(P, M, px, py, id, h, m, cnt, debug ? debug + idx : &scratch, coneXYZ, 1);
-            else cloud_ray<true, true, false, 0>(P, M, px, py, id, h, m, cnt, debug ? debug + idx : &scratch, nullptr, 0);
+                cloud_ray<true, true, false, 1>(P, M, J, px, py, id, h, m, cnt, debug ? debug + idx : &scratch, coneXYZ, 1);
+            else cloud_ray<true, true, false, 0>(P, M, J, px, py, id, h, m, cnt, debug ? debug + idx : &scratch, nullptr, 0);
             tot[0] += cnt.rays; tot[1] += cnt.marched; tot[2] += cnt.steps; tot[3] += cnt.incloud; tot[4] += cnt.cone; tot[5] += cnt.early;
             memcpy(hdr + 4 * idx, &h, 16);
             memcpy(mask + 4 * idx, &m, 16);
@@ -183,6 +184,7 @@ int hs_godrays(const MtCameraUBO* cam, const float* lightColor, int W, int H, co
             dec[i].y = x + 1 < W + 2 ? dec1[i + 1] : MT_MASK_BORDER_DECODED;
         }
     P.decoded = dec.data();
+    P.pitch = W + 2;
     GodRayFrame G = godray_frame(P.cam);
     if (G.blend < 0.0f) return 0;
     for (int y = 0; y < H; ++y)

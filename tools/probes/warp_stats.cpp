@@ -57,7 +57,8 @@ extern "C" int ws_run(const MtCameraUBO* cam, const MtTimeUBO* tm, const MtTunin
     P.full = 1;
     MarchConst M;
     cloud_frame_setup(P.cam, P.tm, P.tun, M);
-    cloud_frame_jitter(P.tm, W, H, M);
+    cloud_frame_jitter(P.tm, W, H, M.tabs);
+    const MarchTabs& J = M.tabs;
     Stats S;
     memset(&S, 0, sizeof(S));
     const int lanes = tile_w * tile_h;  // 32
@@ -78,7 +79,7 @@ extern "C" int ws_run(const MtCameraUBO* cam, const MtTimeUBO* tm, const MtTunin
                     if (px >= W || py >= H) continue;
                     F4 hdr;
                     int id = ((px & 3) << 2) | (py & 3);
-                    R[l] = cloud_ray_setup(P, M, px, py, id, hdr);
+                    R[l] = cloud_ray_setup(P, M, J, px, py, id, hdr);
                     if (R[l].branch != 2) continue;
                     t[l] = R[l].t_in; accum[l] = 0; tr[l] = 1; col[l] = 0;
                     live[l] = t[l] < R[l].t_out;
@@ -102,7 +103,7 @@ extern "C" int ws_run(const MtCameraUBO* cam, const MtTimeUBO* tm, const MtTunin
                         int id = ((px & 3) << 2) | (py & 3);
                         const int jidx = (id + mt_f2i(t[l])) & 15;
                         RayCounters none = {0,0,0,0,0,0};
-                        StepBase B = cloud_step_base<false, false, false>(P, M, R[l], jidx, t[l], none);
+                        StepBase B = cloud_step_base<false, false, false>(P, M, J, R[l], jidx, t[l], none);
                         StepSample smp; smp.inc = 0; smp.energy = -1;
                         if (B.baseDensity > 0.0f) {
                             hits++;
@@ -120,7 +121,7 @@ extern "C" int ws_run(const MtCameraUBO* cam, const MtTimeUBO* tm, const MtTunin
                                 cone_l[i]++;
                                 if (occ_cell_may_be_cloud(P.low, tex_cell(P.low, X.i0, Y.i0, Z.i0))) {
                                     cone_ne[i]++;
-                                    float cur = low_freq_density<false, false>(P, M, P.tun.coverage, pk2(sx, sy), sz, sx, sz, B.h);
+                                    float cur = low_freq_density<false, false>(P, M, R[l].covRcp, P.tun.coverage, pk2(sx, sy), sz, sx, sz, B.h);
                                     if (cur > 0.0f) cone_h[i]++;
                                 }
                             }
