@@ -16,6 +16,9 @@
 #define MT_CONE_RF 1
 #endif
 
+#ifndef MT_SPEC_QUADS_FULL
+#define MT_SPEC_QUADS_FULL 0  /* A/B: the full-quality kernel also requests a march sample's quads together with its bitmap word */
+#endif
 struct RayCounters {
     unsigned rays, marched, steps, incloud, cone, early;
 };
@@ -159,7 +162,7 @@ MT_DEVICE float low_freq_density(const CloudParams& P, const MarchConst& M, floa
     // whole fetch + filter (SIMT: the branch is free when nobody takes it).
 #if MT_TEX_QUADS && !MT_TEX_BRICKS && !defined(MT_HOSTSIM)
     Rgba n;
-    if (STD == 3 && !WEATHER && low.occ) {
+    if ((STD == 3 || (STD == 2 && MT_SPEC_QUADS_FULL)) && !WEATHER && low.occ) {
         // latency-bound callers (the step-parallel 1-of-16 kernel): the cell's quads are requested TOGETHER with its bitmap word
         // instead of after it -- one memory round trip per march sample instead of two, at the price of 32 unused bytes for an
         // empty cell
@@ -379,6 +382,24 @@ MT_DEVICE RaySetup cloud_ray_setup(const CloudParams& P, const MarchConst& M, co
     return R;
 }
 
+#ifndef MT_PACK_ITERS
+#define MT_PACK_ITERS 1
+#endif
+#ifndef MT_PARK_BG
+#if defined(MT_HOSTSIM)
+#define MT_PARK_BG 0
+#else
+#define MT_PARK_BG 1
+#endif
+#endif
+#ifndef MT_CONE_SKIP0
+#define MT_CONE_SKIP0 0  /* 4K: 3.621 ms without, 3.633 ms with: not worth the special case */
+#endif
+struct ConeOffsets {
+    const F4* xyz;    // this thread's first offset (x, y, z, -); the offset of sample i is xyz[i * stride]   (null: compute per step)
+    int stride;
+};
+
 // The sample point of one march iteration and its base density (cloudRayMarch.comp:629-640): everything a step needs
 // before it knows whether it is inside a cloud.
 struct StepBase {
@@ -393,13 +414,15 @@ struct StepBase {
 #define MT_BASE_PACKED 1
 #endif
 template <bool COUNT, bool WEATHER, int STD>
-MT_DEVICE StepBase cloud_step_base(const CloudParams& P, const MarchConst& M, const MarchTabs& J, const RaySetup& R, int jidx, float t, RayCounters& cnt)
+MT_DEVICE StepBase cloud_step_base(const CloudParams& P, const MarchConst& M, const float* sj, const RaySetup& R, float t, RayCounters& cnt,
+                                    const ConeOffsets& CO)
 {
     StepBase B;
+    // parked per-ray values (cloud_ray): an LDS instead of a register the compiler would spill to local memory
+    const float lenToInner = (MT_PARK_BG && CO.xyz) ? CO.xyz[5 * CO.stride].w : R.lenToInner;
     const f3 origin = M.eyePos, ec = M.earthCenter, dir = R.dir;
     const f3 relOrigin = mk3(ec.x, MT_R_INNER - MT_EARTH_RADIUS, ec.z);
     const f3 wind = mk3(P.tun.wind_direction[0], P.tun.wind_direction[1], P.tun.wind_direction[2]);
-    const float* sj = J.stepJitter[jidx >> 1];
 #if MT_BASE_PACKED
     // pos = origin + (dir + jitter) * t
     const P2 jxy = add2(pk2(dir.x, dir.y), pk2(sj[0], sj[1]));
@@ -421,7 +444,7 @@ MT_DEVICE StepBase cloud_step_base(const CloudParams& P, const MarchConst& M, co
     const float rinv = div_nice(1.0f, sqrt_nice((lo2(e2) + hi2(e2)) + ez * ez));
     const P2 nxy = mul2(mul2(exy, bc2(rinv)), pk2(dir.x, dir.y));     // dir * normalize(pos - ec), x and y
     const float cosTheta = (lo2(nxy) + hi2(nxy)) + dir.z * (ez * rinv);
-    const float h = div_thickness(fabsf(cosTheta * (lenFromCam - R.lenToInner)));
+    const float h = div_thickness(fabsf(cosTheta * (lenFromCam - lenToInner)));
     // skewSamplePointWithWind (:489-497): (sp + ((wind * h) * offset) * 0.009) + windSkew
     const P2 wxy = mul2(mul2(mul2(pk2(wind.x, wind.y), bc2(h)), bc2(P.tun.cloud_top_offset)), bc2(0.009f));
     const float wz = ((wind.z * h) * P.tun.cloud_top_offset) * 0.009f;
@@ -437,7 +460,7 @@ MT_DEVICE StepBase cloud_step_base(const CloudParams& P, const MarchConst& M, co
     // getRelativeHeightInAtmosphere (:171-186)
     float lenFromCam = len3_nice(pos - origin);          // 2e4 .. 3e5 m
     float cosTheta = dot3(dir, norm3_nice(pos - ec));    // ~6.4e6 m
-    float h = div_thickness(fabsf(cosTheta * (lenFromCam - R.lenToInner)));
+    float h = div_thickness(fabsf(cosTheta * (lenFromCam - lenToInner)));
     // skewSamplePointWithWind (:489-497)
     f3 skew = (sp + ((wind * h) * P.tun.cloud_top_offset) * 0.009f) + M.windSkew;
     B.pos = pos; B.skew = skew; B.h = h;
@@ -452,13 +475,6 @@ MT_DEVICE StepBase cloud_step_base(const CloudParams& P, const MarchConst& M, co
 // The six light-cone offsets of one ray, (stepSize * noise_kernel[i]) * i, are the same at every step: the one-thread-per-ray
 // kernel computes them once per ray into shared memory ((x, y, z, -) per sample, [i][thread]: conflict-free) and each in-cloud
 // step reads them back -- one 16-byte load instead of a float conversion and four multiplies per cone sample, the same values.
-#ifndef MT_CONE_SKIP0
-#define MT_CONE_SKIP0 0  /* 4K: 3.621 ms without, 3.633 ms with: not worth the special case */
-#endif
-struct ConeOffsets {
-    const F4* xyz;    // this thread's first offset (x, y, z, -); the offset of sample i is xyz[i * stride]   (null: compute per step)
-    int stride;
-};
 
 // MT_CONE_PIPE: software-pipelined light-cone loop (device only, one-thread-per-ray kernels).  A cone sample is a dependent
 // chain: position -> cell -> bitmap word -> brick load (L2 latency: the rays of an SM walk 64 MB) -> filter -> two divisions.
@@ -660,21 +676,30 @@ MT_DEVICE StepSample cloud_step_light(const CloudParams& P, const MarchConst& M,
             }
         }
     }
-    S.energy = light_energy(h, dl, baseDensity, R.phase, R.cosAngle);
+    const bool parked = MT_PARK_BG && CO.xyz;
+    S.energy = light_energy(h, dl, baseDensity, parked ? CO.xyz[3 * CO.stride].w : R.phase, parked ? CO.xyz[4 * CO.stride].w : R.cosAngle);
     return S;
 }
 
 // One iteration of the march loop (cloudRayMarch.comp:629-678) at parameter t, without the running sums.
 template <bool COUNT, bool WEATHER, int STD>
-MT_DEVICE StepSample cloud_step_sample(const CloudParams& P, const MarchConst& M, const MarchTabs& J, const RaySetup& R, int jidx, float t,
-                                       RayCounters& cnt, const ConeOffsets& CO)
+MT_DEVICE StepSample cloud_step_sample_sj(const CloudParams& P, const MarchConst& M, const float* sj, const RaySetup& R, float t,
+                                          RayCounters& cnt, const ConeOffsets& CO)
 {
-    const StepBase B = cloud_step_base<COUNT, WEATHER, STD>(P, M, J, R, jidx, t, cnt);
+    const StepBase B = cloud_step_base<COUNT, WEATHER, STD>(P, M, sj, R, t, cnt, CO);
     if (B.baseDensity > 0.0f) return cloud_step_light<COUNT, WEATHER, STD>(P, M, R, B, cnt, CO);
     StepSample S;
     S.inc = 0.0f;
     S.energy = -1.0f;
     return S;
+}
+
+// jidx = int(mod(float(pixelID + int(t)), 16.0)) selects the step's jitter (cloudRayMarch.comp:629-631): entry jidx / 2 of the table
+template <bool COUNT, bool WEATHER, int STD>
+MT_DEVICE StepSample cloud_step_sample(const CloudParams& P, const MarchConst& M, const MarchTabs& J, const RaySetup& R, int jidx, float t,
+                                       RayCounters& cnt, const ConeOffsets& CO)
+{
+    return cloud_step_sample_sj<COUNT, WEATHER, STD>(P, M, J.stepJitter[jidx >> 1], R, t, cnt, CO);
 }
 
 // Running sums of the march (cloudRayMarch.comp:648, 674-684).  Returns true when the loop must stop.
@@ -732,6 +757,12 @@ MT_DEVICE void cloud_ray(const CloudParams& P, const MarchConst& M, const MarchT
             F4 o;
             cone_offset(M, R.stepSize, i, oxy, o.z);
             o.x = lo2(oxy); o.y = hi2(oxy); o.w = 0.0f;
+#if MT_PARK_BG
+            // the spare components carry what the ray needs once per step or only after the march (background colour, phase,
+            // cos of the sun angle, distance to the inner shell): an LDS where the compiler would otherwise spill a register to
+            // local memory -- the loop runs at the register limit (64)
+            o.w = i == 0 ? R.bg.x : i == 1 ? R.bg.y : i == 2 ? R.bg.z : i == 3 ? R.phase : i == 4 ? R.cosAngle : R.lenToInner;
+#endif
             coneXYZ[i * coneStride] = o;
         }
     }
@@ -740,6 +771,23 @@ MT_DEVICE void cloud_ray(const CloudParams& P, const MarchConst& M, const MarchT
     int iters = 0;
     if (COUNT) cnt.marched++;
     if (DEBUG) { dbg->t_in = R.t_in; dbg->t_out = R.t_out; dbg->step_size = R.stepSize; }
+#if !defined(MT_HOSTSIM)
+    if (MT_PACK_ITERS && !DEBUG) {
+        // ONE register for the iteration count and the pixel id: st = iters << 8 | pixelID << 3.  The cap is st < 64 << 8, and the
+        // step's jitter entry, byte offset ((pixelID + int(t)) & 15) / 2 * 16 = ((pixelID << 3) + (int(t) << 3)) & 0x70, is one
+        // shift-add and one mask on st -- before, the pixel id was spilled and every step began with its reload from local memory.
+        unsigned st = (unsigned)pixelID << 3;
+        for (float t = R.t_in; t < R.t_out && st < ((unsigned)MT_MAX_MARCH_ITERS << 8); t += R.stepSize, st += 256u) {
+            const unsigned off = (st + ((unsigned)mt_f2i(t) << 3)) & 0x70u;
+            const float* sj = reinterpret_cast<const float*>(reinterpret_cast<const char*>(&J.stepJitter[0][0]) + off);
+            const StepSample S = cloud_step_sample_sj<COUNT, WEATHER, STD>(P, M, sj, R, t, cnt, CO);
+            if (cloud_step_combine(S, accum, transmittance, color)) {
+                if (COUNT) cnt.early++;
+                break;
+            }
+        }
+    } else
+#endif
     for (float t = R.t_in; t < R.t_out && iters < MT_MAX_MARCH_ITERS; t += R.stepSize, ++iters) {
         const int jidx = (pixelID + mt_f2i(t)) & 15;  // int(mod(float(pixelID + int(t)), 16.0)), argument >= 0
         if (DEBUG) jhash = (jhash ^ (unsigned)jidx) * 16777619u;
@@ -751,5 +799,14 @@ MT_DEVICE void cloud_ray(const CloudParams& P, const MarchConst& M, const MarchT
         }
     }
     if (DEBUG) { dbg->steps = iters; dbg->jitter_hash = jhash; dbg->accum = accum; }
+#if MT_PARK_BG
+    if (coneXYZ) {
+        RaySetup Rc;
+        Rc.dir = R.dir;
+        Rc.bg = mk3(coneXYZ[0].w, coneXYZ[coneStride].w, coneXYZ[2 * coneStride].w);
+        cloud_composite(Rc, accum, color, hdr, mask);
+        return;
+    }
+#endif
     cloud_composite(R, accum, color, hdr, mask);
 }

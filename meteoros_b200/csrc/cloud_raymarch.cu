@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(128, MT_CLOUD_MINBLOCKS) cloud_base_kernel(con
     if (live) {
         const int jidx = (P.tm.frameCountMod16 + mt_f2i(t)) & 15;
         RayCounters none = { 0u, 0u, 0u, 0u, 0u, 0u };
-        hit = cloud_step_base<false, WEATHER, STD>(P, M, J, R, jidx, t, none).baseDensity > 0.0f;
+        hit = cloud_step_base<false, WEATHER, STD>(P, M, J.stepJitter[jidx >> 1], R, t, none, ConeOffsets{ nullptr, 0 }).baseDensity > 0.0f;
         if (!hit) P.samples[(size_t)k * (size_t)P.rayStride + ray] = make_float2(0.0f, -1.0f);
     }
     const unsigned hits = __ballot_sync(0xffffffffu, hit);
@@ -409,8 +409,8 @@ __global__ void __launch_bounds__(128, MT_CLOUD_MINBLOCKS) cloud_light_kernel(co
         for (int j = 0; j < k; ++j) t += R.stepSize;
         const int jidx = (P.tm.frameCountMod16 + mt_f2i(t)) & 15;
         RayCounters none = { 0u, 0u, 0u, 0u, 0u, 0u };
-        const StepBase B = cloud_step_base<false, WEATHER, STD>(P, M, J, R, jidx, t, none);   // same arithmetic: B.baseDensity > 0 again
         const ConeOffsets noCache = { nullptr, 0 };
+        const StepBase B = cloud_step_base<false, WEATHER, STD>(P, M, J.stepJitter[jidx >> 1], R, t, none, noCache);   // same arithmetic: B.baseDensity > 0 again
         const StepSample S = cloud_step_light<false, WEATHER, STD>(P, M, R, B, none, noCache);
         P.samples[(size_t)k * (size_t)P.rayStride + ray] = make_float2(S.inc, S.energy);
     }
@@ -488,7 +488,9 @@ static bool mt_std_dims(const CloudParams& P)
 // sequential kernel, so the image is bit-identical (test_sixteenth_step_parallel_equals_sequential).  While warp 0 of one
 // CTA is in A or C, the other resident CTAs of the SM (six) are in B.
 // ---------------------------------------------------------------------------------------------------------------------
+#ifndef MT_S16_WARPS
 #define MT_S16_WARPS 8
+#endif
 #ifndef MT_S16_CONE
 #define MT_S16_CONE 3  /* 1080p: 139.7 (1), 135.6 us (3); 1: plain (r, F) cone loop; 2: the software-pipelined, unrolled one of the full-quality kernel; 3: plain loop, brick first (flag in the brick) */
 #endif

@@ -15,6 +15,8 @@
 // does not depend on the pixel is computed once per CTA (frame constants, x/W for the CTA's 32 columns, y/H for its 8
 // rows); coordinates and the float4 accumulation run on fp32x2 pairs; the final /10 is the exact 3-instruction division.
 // ST = the storage format as a compile-time constant (mt_pixel.cuh): the per-load format test folds away
+// No minimum-blocks bound here (unlike the god-ray kernel): with one, ptxas spends 56 / 53 registers on these two kernels and
+// they get slower (reprojection 38.5 -> 42.5 us, TXAA 55.3 -> 57.4 us at 1080p); both are issue bound, not latency bound.
 template <int ST>
 __global__ void __launch_bounds__(256) reproject_kernel(const __grid_constant__ ReprojParams P)
 {
@@ -99,7 +101,14 @@ cudaError_t mt_launch_mask_grey(const GodRayParams& P, float* out, cudaStream_t 
 #endif
 #define MT_GODRAY_CTA_H (MT_GODRAY_LOG2W == 5 ? MT_GODRAY_WARPS : 2 * MT_GODRAY_WH)     /*  8,  4,  4 */
 template <int ST, int K>
-__global__ void __launch_bounds__(MT_GODRAY_LOG2W == 5 ? 32 * MT_GODRAY_WARPS : 128) godrays_kernel(const __grid_constant__ GodRayParams P)
+// A minimum-blocks launch bound of ANY value changes ptxas' schedule of the tap loop: without one it keeps the kernel at 36
+// registers by consuming each tap's two loads before it issues the next tap's (two loads in flight per thread, 11.7
+// long-scoreboard stall cycles per issue); with one it hoists the eight loads of the four unrolled taps (56 registers):
+// 199 -> 177 us at 1080p.  Grouping the taps by hand (2 / 4 / 5 taps' loads, then their filters) measures the same or worse.
+#ifndef MT_GODRAY_MINBLOCKS
+#define MT_GODRAY_MINBLOCKS 1
+#endif
+__global__ void __launch_bounds__(MT_GODRAY_LOG2W == 5 ? 32 * MT_GODRAY_WARPS : 128, MT_GODRAY_MINBLOCKS) godrays_kernel(const __grid_constant__ GodRayParams P)
 {
     const GodRayFrame& frame = P.frame;
     const bool lit = !(frame.blend < 0.0f);  // sun behind the camera: the fragment shader returns before any store

@@ -103,7 +103,7 @@ extern "C" int ws_run(const MtCameraUBO* cam, const MtTimeUBO* tm, const MtTunin
                         int id = ((px & 3) << 2) | (py & 3);
                         const int jidx = (id + mt_f2i(t[l])) & 15;
                         RayCounters none = {0,0,0,0,0,0};
-                        StepBase B = cloud_step_base<false, false, false>(P, M, J, R[l], jidx, t[l], none);
+                        StepBase B = cloud_step_base<false, false, false>(P, M, J.stepJitter[jidx >> 1], R[l], t[l], none, ConeOffsets{ nullptr, 0 });
                         StepSample smp; smp.inc = 0; smp.energy = -1;
                         if (B.baseDensity > 0.0f) {
                             hits++;
