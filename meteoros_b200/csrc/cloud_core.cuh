@@ -572,10 +572,7 @@ MT_DEVICE StepSample cloud_step_light(const CloudParams& P, const MarchConst& M,
     const f3 relOrigin = mk3(ec.x, MT_R_INNER - MT_EARTH_RADIUS, ec.z);
     const float coverage = P.tun.coverage, h = B.h, baseDensity = B.baseDensity;
     if (COUNT) cnt.incloud++;
-    float edge = erosion_edge<MT_STD_MAGIC(STD)>(std_curl<STD>(P.curl), std_high<STD>(P.high), skew, h);
-    S.inc = erode(baseDensity * 1.4f, edge) * 0.5f;
     float dl = 0.0f;
-    const float edgeRcp = nice_rcp(1.0f - edge);  // the step's erosion divisor, shared by the six cone samples (radiance only)
 #if !defined(MT_HOSTSIM) && MT_CONE_PIPE
     if (STD == 2 && MT_CONE_RF && !WEATHER) {  // STD kernels are only launched with the (r, F) bricks present (mt_std_dims)
         const Tex3D low = std_low<STD>(P.low);
@@ -583,9 +580,14 @@ MT_DEVICE StepSample cloud_step_light(const CloudParams& P, const MarchConst& M,
         float sz;
         LinAxis X, Y, Z;
         unsigned cell;
+        // sample 0's brick is requested before the erosion fetches in the source; ptxas schedules the load (and a prefetch in its
+        // place) behind them all the same, so 3.7 % of the kernel's stall samples still sit on the first brick's flag test
         cone_axes<STD>(P, M, CO, pos, relOrigin, R.stepSize, 0, sxy, sz, X, Y, Z, cell);
         const unsigned wrap = (unsigned)low.w * (unsigned)low.h * (unsigned)low.d - 1u, slice = (unsigned)low.w * (unsigned)low.h;
         Brick cur = ldg_brick(low.rfquads, cell, slice, wrap);
+        const float edge = erosion_edge<MT_STD_MAGIC(STD)>(std_curl<STD>(P.curl), std_high<STD>(P.high), skew, h);
+        S.inc = erode(baseDensity * 1.4f, edge) * 0.5f;
+        const float edgeRcp = nice_rcp(1.0f - edge);  // the step's erosion divisor, shared by the six cone samples (radiance only)
 #ifndef MT_CONE_UNROLL
 #define MT_CONE_UNROLL 6  /* 4K: 4.204 (1), 4.144 (2), 4.137 (3), 4.043 ms (6): no loop-carried register rotation, constant offsets */
 #endif
@@ -611,8 +613,14 @@ MT_DEVICE StepSample cloud_step_light(const CloudParams& P, const MarchConst& M,
             }
             X = Xn; Y = Yn; Z = Zn; cell = celln; cur = nxt;
         }
-    } else
+        S.energy = light_energy(h, dl, baseDensity, (MT_PARK_BG && CO.xyz) ? CO.xyz[3 * CO.stride].w : R.phase,
+                                (MT_PARK_BG && CO.xyz) ? CO.xyz[4 * CO.stride].w : R.cosAngle);
+        return S;
+    }
 #endif
+    const float edge = erosion_edge<MT_STD_MAGIC(STD)>(std_curl<STD>(P.curl), std_high<STD>(P.high), skew, h);
+    S.inc = erode(baseDensity * 1.4f, edge) * 0.5f;
+    const float edgeRcp = nice_rcp(1.0f - edge);  // the step's erosion divisor, shared by the six cone samples (radiance only)
     {
 #pragma unroll 1
         for (int i = 0; i < 6; ++i) {  // one copy of the filter in the instruction stream (I-cache)
