@@ -38,31 +38,57 @@ MT_HD ReprojFrame reproject_frame(const ReprojParams& P)
 #else
 #define MT_TAP_BIAS 0x4B000000
 #endif
-MT_DEVICE void reproject_taps(const ReprojParams& P, const ReprojFrame& F, float u, float v, int taps[10])
+// old_uv of a pixel: castRay, the inner-shell intersection, the hit point through the previous frame's view matrix and back to
+// screen space (reprojection.comp:203-232; postProcess_TXAA.frag does the same with its own uv / jitter).  Seven IEEE divisions
+// and three square roots per pixel, each with its range test, branch to a slow path and reconvergence pair.  NICE = the same
+// operations through the fast paths only (mt_math.cuh: div_nice / sqrt_nice / nice_rcp -- correctly rounded whenever no operand
+// or intermediate leaves the normal range), for frames whose constants the host has checked (mt_post_nice_ok, post_passes.cu:
+// orthonormal bases, both eyes inside the inner shell with 100 m to spare, tan(fov/2) in [1e-3, 1e3]): then |p - eye| >= 0.7,
+// 2A ~ 2, the discriminant is 0 or >= 1e-18, |q| >= 100 m; the one divisor no frame constant bounds, -q.z, is tested per pixel.
+template <bool NICE>
+MT_DEVICE void reproject_old_uv(const CamU& cam, const float* m, const RayBasis& basis, f3 eye, f3 ec, f3 o, float C, float u, float v,
+                                float jx, float jy, float& old_u, float& old_v)
 {
-    const float fw = (float)P.W, fh = (float)P.H;  // no y flip here (reprojection.comp:200-201)
-    const f3 dir = cast_ray_dir(P.cam, F.basis, F.eye, u, v, F.jx, F.jy);
+    f3 dir;
+    {   // castRay (mt_math.cuh, cast_ray_dir) with the normalisation on the fast path
+        const float nx = (u * 2.0f - 1.0f) + jx, ny = (v * 2.0f - 1.0f) + jy;
+        const f3 pe = (((eye + basis.look) + basis.right * (nx * cam.tanFovBy2[0])) + basis.up * (ny * cam.tanFovBy2[1])) - eye;
+        dir = NICE ? norm3_nice(pe) : norm3(pe);
+    }
     // raySphereIntersection (reprojection.comp:147-191) with the pixel-independent terms hoisted; only .point is used
     f3 p = mk3(0.0f, 0.0f, 0.0f);
     {
         const float A = dot3(dir, dir);
-        const float B = 2.0f * dot3(dir, F.o);
-        const float disc = B * B - (4.0f * A) * F.C;
+        const float B = 2.0f * dot3(dir, o);
+        const float disc = B * B - (4.0f * A) * C;
         if (!(disc < 0.0f)) {
-            const float sq = sqrtf(disc);
-            float t = (-B - sq) / (2.0f * A);
-            if (t < 0.0f) t = (-B + sq) / (2.0f * A);
-            if (t >= 0.0f) p = ((F.o + dir * t) * MT_R_INNER) + F.ec;
+            const float sq = NICE ? sqrt_nice(disc) : sqrtf(disc);
+            float t = NICE ? div_nice(-B - sq, 2.0f * A) : (-B - sq) / (2.0f * A);
+            if (t < 0.0f) t = NICE ? div_nice(-B + sq, 2.0f * A) : (-B + sq) / (2.0f * A);
+            if (t >= 0.0f) p = ((o + dir * t) * MT_R_INNER) + ec;
         }
     }
-    const float* m = P.camOld.view;
     f3 q = mk3(((m[0] * p.x + m[4] * p.y) + m[8] * p.z) + m[12] * 1.0f,
                ((m[1] * p.x + m[5] * p.y) + m[9] * p.z) + m[13] * 1.0f,
                ((m[2] * p.x + m[6] * p.y) + m[10] * p.z) + m[14] * 1.0f);
-    q = norm3(q);
+    q = NICE ? norm3_nice(q) : norm3(q);
+    if (NICE && fabsf(q.z) >= 1e-30f) {  // (else: zero, denormal or NaN divisor -- the IEEE sequence below)
+        const float nz = -q.z, rz = nice_rcp(nz);
+        old_u = div_nice(div_nice_r(q.x, nz, rz), cam.tanFovBy2[0]) * 0.5f + 0.5f;
+        old_v = div_nice(div_nice_r(q.y, nz, rz), cam.tanFovBy2[1]) * 0.5f + 0.5f;
+        return;
+    }
     q = q / (-q.z);
-    const float old_u = (q.x / P.cam.tanFovBy2[0]) * 0.5f + 0.5f;
-    const float old_v = (q.y / P.cam.tanFovBy2[1]) * 0.5f + 0.5f;
+    old_u = (q.x / cam.tanFovBy2[0]) * 0.5f + 0.5f;
+    old_v = (q.y / cam.tanFovBy2[1]) * 0.5f + 0.5f;
+}
+
+template <bool NICE = false>
+MT_DEVICE void reproject_taps(const ReprojParams& P, const ReprojFrame& F, float u, float v, int taps[10])
+{
+    const float fw = (float)P.W, fh = (float)P.H;  // no y flip here (reprojection.comp:200-201)
+    float old_u, old_v;
+    reproject_old_uv<NICE>(P.cam, P.camOld.view, F.basis, F.eye, F.ec, F.o, F.C, u, v, F.jx, F.jy, old_u, old_v);
     const P2 mv = pk2(old_u - u, old_v - v), dim = pk2(fw, fh);
 #if !defined(MT_HOSTSIM) && MT_REPROJ_FAST
     // (dim - 1) / dim rounded: old * dim <= dim - 1 + 5e-4 and the taps' own roundings move them by < 1e-3 of a pixel,
@@ -353,30 +379,12 @@ MT_DEVICE C4 ldr_border_texel(const uint32_t* img, int W, int H, int x, int y)  
 }
 
 // One fragment of the TXAA pass; returns the packed RGBA8 result.
+template <bool NICE = false>
 MT_DEVICE uint32_t txaa_pixel(const TxaaParams& P, const TxaaFrame& F, int x, int y, float u, float v)
 {
-    // (u, v) = in_uv = ((x + .5) / W, (y + .5) / H), computed once per CTA column / row by the caller
-    const f3 dir = cast_ray_dir(P.cam, F.basis, F.eye, u, v, F.jx, F.jy);
-    f3 p = mk3(0.0f, 0.0f, 0.0f);
-    {
-        const float A = dot3(dir, dir);
-        const float B = 2.0f * dot3(dir, F.o);
-        const float disc = B * B - (4.0f * A) * F.C;
-        if (!(disc < 0.0f)) {
-            const float sq = sqrtf(disc);
-            float t = (-B - sq) / (2.0f * A);
-            if (t < 0.0f) t = (-B + sq) / (2.0f * A);
-            if (t >= 0.0f) p = ((F.o + dir * t) * MT_R_INNER) + F.ec;
-        }
-    }
-    const float* m = P.camOld.view;
-    f3 q = mk3(((m[0] * p.x + m[4] * p.y) + m[8] * p.z) + m[12] * 1.0f,
-               ((m[1] * p.x + m[5] * p.y) + m[9] * p.z) + m[13] * 1.0f,
-               ((m[2] * p.x + m[6] * p.y) + m[10] * p.z) + m[14] * 1.0f);
-    q = norm3(q);
-    q = q / (-q.z);
-    const float old_u = (q.x / P.cam.tanFovBy2[0]) * 0.5f + 0.5f;
-    const float old_v = (q.y / P.cam.tanFovBy2[1]) * 0.5f + 0.5f;
+    // (u, v) = in_uv = ((x + .5) / W, (y + .5) / H), from the context's uv table
+    float old_u, old_v;
+    reproject_old_uv<NICE>(P.cam, P.camOld.view, F.basis, F.eye, F.ec, F.o, F.C, u, v, F.jx, F.jy, old_u, old_v);
 
     // 3x3 neighbourhood of the tone-mapped frame (order: tl tc tr ml mc mr bl bc br)
     C4 n[9];

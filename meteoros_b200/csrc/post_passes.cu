@@ -17,7 +17,7 @@
 // ST = the storage format as a compile-time constant (mt_pixel.cuh): the per-load format test folds away
 // No minimum-blocks bound here (unlike the god-ray kernel): with one, ptxas spends 56 / 53 registers on these two kernels and
 // they get slower (reprojection 38.5 -> 42.5 us, TXAA 55.3 -> 57.4 us at 1080p); both are issue bound, not latency bound.
-template <int ST>
+template <int ST, bool NICE>
 __global__ void __launch_bounds__(256) reproject_kernel(const __grid_constant__ ReprojParams P)
 {
     const int x = blockIdx.x * 32 + (threadIdx.x & 31);
@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(256) reproject_kernel(const __grid_constant__ 
     if (x >= P.W || y >= P.H) return;
     int taps[10];
     // frame constants from the parameter block, (x / W, y / H) from the context's uv table: no shared memory, no barrier
-    reproject_taps(P, P.frame, __ldg(P.uv + x), __ldg(P.uv + P.W + y), taps);
+    reproject_taps<NICE>(P, P.frame, __ldg(P.uv + x), __ldg(P.uv + P.W + y), taps);
     P2 axy = pk2(0.0f, 0.0f), azw = pk2(0.0f, 0.0f);
     // the tap indices carry MT_TAP_BIAS (post_core.cuh): taken out of the base address, never dereferenced without an index
     const char* prevB = reinterpret_cast<const char*>(P.prev) - (size_t)MT_TAP_BIAS * (ST == MT_PX_F16 ? 8u : 16u);
@@ -150,26 +150,67 @@ __global__ void __launch_bounds__(256) tonemap_kernel(const __grid_constant__ To
 }
 
 // ---- TXAA: one pixel per thread; 9 neighbour + 4 history texels are L1 hits, compulsory traffic 4 + 4 + 4 B/pixel ----
+template <bool NICE>
 __global__ void __launch_bounds__(256) txaa_kernel(const __grid_constant__ TxaaParams P)
 {
     const int x = blockIdx.x * 32 + (threadIdx.x & 31);
     const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
     if (x >= P.W || y >= P.H) return;
-    P.out[(size_t)y * P.W + x] = txaa_pixel(P, P.frame, x, y, __ldg(P.uv + P.W + P.H + x), __ldg(P.uv + 2 * P.W + P.H + y));
+    P.out[(size_t)y * P.W + x] = txaa_pixel<NICE>(P, P.frame, x, y, __ldg(P.uv + P.W + P.H + x), __ldg(P.uv + 2 * P.W + P.H + y));
 }
+// May the frame run the fast-path-only arithmetic of reproject_old_uv (post_core.cuh)?  Checked in double on the frame's constants.
+#ifndef MT_POST_NICE
+#define MT_POST_NICE 1
+#endif
+static bool mt_post_nice_ok(const CamU& cam, const CamU& camOld)
+{
+    if (!MT_POST_NICE) return false;
+    const CamU* cams[2] = { &cam, &camOld };
+    for (int c = 0; c < 2; ++c) {
+        const float* v = cams[c]->view;
+        double b[3][3];
+        for (int r = 0; r < 3; ++r) {  // row r of the rotation part, normalised like ray_basis
+            const double x = v[r], y = v[4 + r], z = v[8 + r], l = sqrt(x * x + y * y + z * z);
+            if (!(l > 0.5 && l < 2.0)) return false;
+            b[r][0] = x / l; b[r][1] = y / l; b[r][2] = z / l;
+        }
+        for (int i = 0; i < 3; ++i)
+            for (int j = i + 1; j < 3; ++j)
+                if (!(fabs(b[i][0] * b[j][0] + b[i][1] * b[j][1] + b[i][2] * b[j][2]) <= 1e-3)) return false;
+    }
+    for (int k = 0; k < 2; ++k)
+        if (!(cam.tanFovBy2[k] >= 1e-3f && cam.tanFovBy2[k] <= 1e3f)) return false;
+    // the ray origin (-cam.eye) inside the inner shell with 100 m to spare, and not absurdly far from the origin
+    const double ex = -(double)cam.eye[0], ey = -(double)cam.eye[1], ez = -(double)cam.eye[2];
+    if (!(fabs(ex) <= 1e6 && fabs(ez) <= 1e6 && ey >= -1e5 && ey <= 7400.0)) return false;
+    // the previous frame's eye as its view matrix places it (c = -R^T t), against the CURRENT earth centre (ex, -R, ez)
+    const float* m = camOld.view;
+    const double tx = m[12], ty = m[13], tz = m[14];
+    const double cx = -(m[0] * tx + m[1] * ty + m[2] * tz), cy = -(m[4] * tx + m[5] * ty + m[6] * tz), cz = -(m[8] * tx + m[9] * ty + m[10] * tz);
+    const double dx = cx - ex, dy = cy + (double)MT_EARTH_RADIUS, dz = cz - ez, d = sqrt(dx * dx + dy * dy + dz * dz);
+    return d <= (double)MT_R_INNER - 100.0 && d >= 0.5 * (double)MT_R_INNER;
+}
+
 cudaError_t mt_launch_txaa(const TxaaParams& P, cudaStream_t stream)
 {
     dim3 grid((unsigned)((P.W + 31) / 32), (unsigned)((P.H + 7) / 8), 1);
-    txaa_kernel<<<grid, 256, 0, stream>>>(P);
+    if (mt_post_nice_ok(P.cam, P.camOld)) txaa_kernel<true><<<grid, 256, 0, stream>>>(P);
+    else txaa_kernel<false><<<grid, 256, 0, stream>>>(P);
     return cudaGetLastError();
 }
 
 cudaError_t mt_launch_reproject(const ReprojParams& P, cudaStream_t stream)
 {
     dim3 grid((unsigned)((P.W + 31) / 32), (unsigned)((P.H + 7) / 8), 1);
-    if (P.storage == MT_PX_F16) reproject_kernel<MT_PX_F16><<<grid, 256, 0, stream>>>(P);
-    else if (P.storage == MT_PX_F16_EMULATE) reproject_kernel<MT_PX_F16_EMULATE><<<grid, 256, 0, stream>>>(P);
-    else reproject_kernel<MT_PX_F32><<<grid, 256, 0, stream>>>(P);
+    if (mt_post_nice_ok(P.cam, P.camOld)) {
+        if (P.storage == MT_PX_F16) reproject_kernel<MT_PX_F16, true><<<grid, 256, 0, stream>>>(P);
+        else if (P.storage == MT_PX_F16_EMULATE) reproject_kernel<MT_PX_F16_EMULATE, true><<<grid, 256, 0, stream>>>(P);
+        else reproject_kernel<MT_PX_F32, true><<<grid, 256, 0, stream>>>(P);
+    } else {
+        if (P.storage == MT_PX_F16) reproject_kernel<MT_PX_F16, false><<<grid, 256, 0, stream>>>(P);
+        else if (P.storage == MT_PX_F16_EMULATE) reproject_kernel<MT_PX_F16_EMULATE, false><<<grid, 256, 0, stream>>>(P);
+        else reproject_kernel<MT_PX_F32, false><<<grid, 256, 0, stream>>>(P);
+    }
     return cudaGetLastError();
 }
 template <int K>
