@@ -50,3 +50,60 @@ def test_denormal_scaled_texel_unpack_is_linear():
         got = fma32(w1 * wzs, t1, prod0) * (np.float32(1.0 / 255.0) * np.float32(8192.0))
     # float64 addition of a 48-bit product and a 24-bit addend can itself round; compare where it did not matter
     assert (got == ref).mean() > 0.9999
+
+
+def test_magic_constant_floor_equals_floorf():
+    """lin_axes_xy<MAGIC> / the god-ray tap: t = RD(u + 1.5 * 2^23) holds floor(u) in its low mantissa bits (two's complement
+    below the constant's own bits, so `& (n - 1)` is the REPEAT wrap) and t - 1.5 * 2^23 == floorf(u), for |u| < 2^22."""
+    rng = np.random.default_rng(5)
+    u = np.concatenate([
+        (rng.random(2_000_000) * 2.0 - 1.0) * 2.0 ** rng.integers(-10, 22, 2_000_000),   # all magnitudes, both signs
+        np.arange(-4096, 4096, dtype=np.float64), np.arange(-4096, 4096, dtype=np.float64) + 0.5,
+        np.nextafter(np.arange(-512, 512, dtype=np.float32), np.float32(-np.inf)).astype(np.float64),
+        np.array([-0.0, 0.0, 2.0**22 - 0.5, -(2.0**22) + 0.5]),
+    ]).astype(np.float32)
+    u = u[(u == 0) | (np.abs(u) >= 2.0**-20)]                    # (binary64 holds u + magic exactly only down to 2^-29; the hardware's sum is exact)
+    magic = np.float32(12582912.0)
+    exact = u.astype(np.float64) + float(magic)                 # exact in binary64
+    t = exact.astype(np.float32)                                # round to nearest ...
+    t = np.where(t.astype(np.float64) > exact, np.nextafter(t, np.float32(-np.inf)), t).astype(np.float32)  # ... made round-down
+    fl = np.floor(u)
+    assert np.array_equal(t - magic, fl)                        # the subtraction is exact
+    low = t.view(np.uint32).astype(np.int64) - 0x4B400000       # the mantissa field relative to the constant's bits
+    assert np.array_equal(low, fl.astype(np.int64))
+    for n in (32, 128):
+        assert np.array_equal(t.view(np.uint32) & np.uint32(n - 1), fl.astype(np.int64) & (n - 1))
+
+
+def test_rf_lerp_filter_is_within_guard_of_the_exact_filter():
+    """rf_filter (mt_tex.cuh, MT_CONE_LERP): seven nested lerps on the denormal-scaled (r, F) words.  Its distance from the
+    real-number trilinear filter must stay far inside MT_RF_GUARD / 4 = 2e-6 (the guard band of the light-cone decisions)."""
+    rng = np.random.default_rng(1)
+    n = 200_000
+    r = rng.integers(0, 256, (n, 8)).astype(np.uint32)
+    F = rng.integers(0, 2041, (n, 8)).astype(np.uint32)
+    f = rng.random((n, 3)).astype(np.float32)
+    rw = (r << np.uint32(16)).view(np.float32)      # MT_B3: r * 2^-133
+    Fw = (F << np.uint32(13)).view(np.float32)      # MT_F13: F * 2^-136
+
+    def lerp(a, b, t):  # fma(t, b - a, a): the difference is exact, one rounding in the fma
+        with np.errstate(under="ignore"):
+            d = (b - a).astype(np.float32)
+            return (t.astype(np.float64) * d.astype(np.float64) + a.astype(np.float64)).astype(np.float32)
+
+    def tri(w):
+        l00, l01 = lerp(w[:, 0], w[:, 1], f[:, 0]), lerp(w[:, 2], w[:, 3], f[:, 0])
+        l10, l11 = lerp(w[:, 4], w[:, 5], f[:, 0]), lerp(w[:, 6], w[:, 7], f[:, 0])
+        return lerp(lerp(l00, l01, f[:, 1]), lerp(l10, l11, f[:, 1]), f[:, 2])
+
+    def exact(v):
+        v = v.astype(np.float64)
+        fx, fy, fz = (f[:, i].astype(np.float64) for i in range(3))
+        l00, l01 = v[:, 0] + fx * (v[:, 1] - v[:, 0]), v[:, 2] + fx * (v[:, 3] - v[:, 2])
+        l10, l11 = v[:, 4] + fx * (v[:, 5] - v[:, 4]), v[:, 6] + fx * (v[:, 7] - v[:, 6])
+        m0, m1 = l00 + fy * (l01 - l00), l10 + fy * (l11 - l10)
+        return m0 + fz * (m1 - m0)
+
+    k = np.float32(2.0**133 / 255.0)
+    assert np.abs(tri(rw) * k - exact(r) / 255.0).max() < 4e-7
+    assert np.abs(tri(Fw) * k - exact(F) / 2040.0).max() < 4e-7

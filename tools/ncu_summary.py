@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """Condense an .ncu-rep (read with `ncu -i ... --page raw --csv`) into the handful of counters the design is argued
-from.  Usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep [> profiles/rN_name.md]"""
+from.  Usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep [--blocks [kernel-regex]] [> profiles/rN_name.md]
+--blocks adds, from the source page (`--page source --csv`, reports captured with --import-source on), the opcode mix weighted by
+executions and the basic blocks by execution count (share of warp instructions, share of stall samples, active lanes)."""
 import csv
 import io
 import subprocess
@@ -44,8 +46,51 @@ KEYS = [
 ]
 
 
+def blocks(rep, kernel):
+    import collections
+    import re
+    cmd = ["ncu", "-i", rep, "--page", "source", "--csv"] + (["--kernel-name", "regex:" + kernel] if kernel else [])
+    out = subprocess.run(cmd, capture_output=True, text=True, check=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    groups, cur = [], None
+    for r in rows:
+        if r and r[0] == "Kernel Name":
+            cur = {"name": r[1], "rows": []}
+            groups.append(cur)
+        elif cur is not None:
+            cur["rows"].append(r)
+    for g in groups[:1]:
+        hdr = g["rows"][0]
+        data = [r for r in g["rows"][1:] if len(r) == len(hdr)]
+        ix = {h: i for i, h in enumerate(hdr)}
+        ex = lambda r: int(r[ix["Instructions Executed"]])
+        sm = lambda r: int(r[ix["# Samples"]])
+        tot, ts = sum(map(ex, data)), max(1, sum(map(sm, data)))
+        print(f"## Where the instructions go: `{g['name']}` ({tot} warp instructions, {len(data)} SASS instructions)\n")
+        hist = collections.Counter()
+        for r in data:
+            src = re.sub(r"^@!?U?P\d+\s+", "", r[ix["Source"]].strip())
+            hist[src.split()[0].rstrip(";").split(".")[0]] += ex(r)
+        print("Opcode mix (share of executed warp instructions): " + ", ".join(f"{op} {100 * c / tot:.1f}" for op, c in hist.most_common(24)) + "\n")
+        print("| SASS instructions | executions per instruction | share of warp instructions | share of stall samples | active lanes |")
+        print("|---|---|---|---|---|")
+        prev, start = None, 0
+        for i, r in enumerate(data + [None]):
+            e = ex(r) if r else -1
+            if e != prev:
+                if prev is not None and (i - start) >= 4 and prev * (i - start) / tot > 0.004:
+                    smp = sum(sm(x) for x in data[start:i])
+                    print(f"| {i - start} | {prev} | {100 * prev * (i - start) / tot:.1f} % | {100 * smp / ts:.1f} % | {float(data[start][ix['Avg. Threads Executed']]):.1f} |")
+                start, prev = i, e
+        print()
+
+
 def main():
     rep = sys.argv[1]
+    if "--blocks" in sys.argv:
+        k = sys.argv.index("--blocks")
+        blocks(rep, sys.argv[k + 1] if k + 1 < len(sys.argv) else "")
+        return
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units = rows[0], rows[1]
