@@ -873,3 +873,78 @@ def test_multi_gpu_sharded_frame_is_bit_identical():
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     # peer_store, bulk_store and copy with and without the mask, forward without: seven gathered frames, all identical
     assert r.stdout.count("bit-identical to single-GPU: True") == 7 and "single-GPU: False" not in r.stdout, r.stdout[-2000:]
+
+
+@pytest.mark.parametrize("case", ["default", "origin_above_inner_shell", "wide_fov", "quarter_turn", "old_eye_elsewhere"])
+def test_post_passes_fast_and_generic_paths(api, oracle_mod, case):
+    """The reprojection / TXAA kernels exist twice: fast-path-only division / square root for frames whose constants the host has
+    checked (mt_post_nice_ok) and the IEEE sequences for everything else; inside both, a tap takes the clamp-free path only while
+    old_uv is inside the image.  Cameras on either side of every one of those conditions: tap indices, reprojected image and
+    TXAA bytes stay bit-identical to the oracle."""
+    from meteoros_b200 import scene
+
+    w, h = 208, 117
+    kw, yaw, pitch = {}, 0.25, 0.25
+    old_kw = None
+    if case == "origin_above_inner_shell":
+        kw = dict(eye=(0.0, -9000.0, 2.0), ref=(0.0, -9000.0, 1.0))
+    elif case == "wide_fov":
+        kw = dict(fovy=179.92)                      # tan(fov / 2) > 1e3
+    elif case == "quarter_turn":
+        yaw, pitch = 88.0, 20.0                     # -q.z crosses zero inside the frame: taps far outside the image, per-pixel IEEE path
+    elif case == "old_eye_elsewhere":
+        old_kw = dict(eye=(300.0, -7450.0, 2.0), ref=(300.0, -7450.0, 1.0))   # previous eye within 100 m of the inner shell
+    cam = scene.Camera(w, h, **kw)
+    old = scene.Camera(w, h, **(old_kw or kw)).ubo()
+    cam.rotate_about_up(yaw)
+    cam.rotate_about_right(pitch)
+    new = cam.ubo()
+    sc = scene.Scene()
+    sc.update_time(1 / 60)
+    rng = np.random.default_rng(17)
+    prev = rng.random((h, w, 4), dtype=np.float32)
+    cur_ldr = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+    prev_ldr = np.roll(cur_ldr, 3, axis=1)
+    with api.CloudRenderer(w, h) as r:
+        for fid in (3, 12):
+            sc.time["frameCountMod16"] = fid
+            tm = sc.ubo()
+            r.set_camera(new); r.set_camera_old(old); r.set_time(tm)
+            r.write_image(api.IMAGE_CLOUD_PREV, prev)
+            taps = r.dispatch_reprojection_debug()
+            ref, ref_taps = oracle_mod.reproject(new, old, tm, prev, taps=True)
+            assert np.array_equal(taps, ref_taps), (case, fid)
+            assert np.array_equal(r.read_image(api.IMAGE_CLOUD_CUR), ref)
+            r.write_image(api.IMAGE_LDR, cur_ldr)
+            r.write_image(api.IMAGE_LDR_PREV, prev_ldr)
+            r.dispatch_txaa()
+            assert np.array_equal(r.read_image(api.IMAGE_LDR), oracle_mod.txaa(new, old, tm, cur_ldr, prev_ldr)), (case, fid)
+
+
+def test_cloud_generic_kernels_when_texture_coordinates_are_large(api, oracle_mod, noise):
+    """The STD march kernels floor their filter coordinates with the magic constant (exact for |u| < 2^22); a frame whose constants
+    do not bound the coordinates (here: a wind drift of ~2e4 texture periods) must run the generic kernels -- and still match."""
+    from meteoros_b200 import scene
+
+    w, h = 160, 90
+    cam, tm, _, tun = default_scene(w, h, frame_id=5, total_time=100.0, yaw=15.0)
+    tun["cloud_speed"] = 200.0
+    ref = oracle_mod.cloud(cam, tm, tun, noise, w, h, full=True, counters=True)
+    with make_renderer(api, noise, w, h, flags=api.FLAG_COUNTERS) as r:
+        r.set_camera(cam); r.set_time(tm); r.set_tuning(tun)
+        r.dispatch_cloud_full()
+        assert r.counters() == ref["counters"]
+        assert np.array_equal(r.read_image(api.IMAGE_GODRAY_MASK), ref["mask"])
+        check_hdr(r.read_image(api.IMAGE_CLOUD_CUR), ref["hdr"])
+    sentinel = np.full((h, w, 4), -3.0, np.float32)
+    ref16 = oracle_mod.cloud(cam, tm, tun, noise, w, h, full=False, hdr=sentinel.copy(), mask=sentinel.copy())
+    with make_renderer(api, noise, w, h) as r:
+        r.set_camera(cam); r.set_time(tm); r.set_tuning(tun)
+        r.write_image(api.IMAGE_CLOUD_CUR, sentinel)
+        r.write_image(api.IMAGE_GODRAY_MASK, sentinel)
+        r.dispatch_cloud()
+        got = r.read_image(api.IMAGE_CLOUD_CUR)
+        wr = got[..., 3] != -3.0
+        assert np.array_equal(wr, ref16["hdr"][..., 3] != -3.0)
+        assert np.array_equal(r.read_image(api.IMAGE_GODRAY_MASK), ref16["mask"])
+        check_hdr(got, ref16["hdr"], wr)
