@@ -255,7 +255,10 @@ MT_API MtStatus mtWaitReads(MtContext* ctx);
 MT_API MtStatus mtJoinCopies(MtContext* ctx);
 MT_API MtStatus mtWriteImage(MtContext* ctx, MtImage which, const void* host, size_t bytes); /* H2D, ordered */
 MT_API MtStatus mtClearImages(MtContext* ctx);    /* zero all four images (reference: images are never cleared; zeros assumed) */
-MT_API MtStatus mtImageDevicePtr(MtContext* ctx, MtImage which, void** dev_ptr);             /* zero-copy interop */
+/* Zero-copy interop.  Asking for MT_IMAGE_GODRAY_MASK (here or through mtExportImageHandle) tells the library that the mask may be
+ * written behind its back: from then on every god-ray dispatch rebuilds its decoded copy of the mask from the whole image, instead
+ * of relying on the 1-of-16 Cloud kernel having kept it current. */
+MT_API MtStatus mtImageDevicePtr(MtContext* ctx, MtImage which, void** dev_ptr);
 /* Redirect the cloud pass's HDR / mask stores to caller-provided device memory (same layout and size as the
  * context's own images), e.g. a peer-mapped image on GPU 0 so that row tiles land there through NVLink stores
  * straight from the kernel epilogue.  NULL restores the context's own image.                                  */

@@ -12,6 +12,7 @@
 #include "cloud_core.cuh"
 #include "mt_launch.h"
 #include "mt_pixel.cuh"
+#include "post_core.cuh"
 
 // The per-frame constants (MarchConst, mt_params.h) arrive in the parameter block: M is a reference into the constant bank.  The
 // two jitter tables are indexed per lane, so every CTA stages them (48 words) in shared memory.  MT_MC_PARAM=0 is the A/B
@@ -289,6 +290,25 @@ __device__ __forceinline__ void store_pixel(const CloudParams& P, size_t idx, F4
     px_store(P.hdr, idx, make_float4(hdr.x, hdr.y, hdr.z, hdr.w), P.storage);
     px_store(P.mask, idx, make_float4(mask.x, mask.y, mask.z, mask.w), P.storage);
 }
+// The god-ray pass filters a DECODED copy of the mask (post_core.cuh: pairs (d(x, y), d(x+1, y)) with a one-texel ring), which
+// mask_decode_kernel rebuilds from the whole mask -- 33 MB read for the sixteenth of it a frame's Cloud dispatch rewrote.  The
+// fused 1-of-16 kernel therefore keeps that copy current itself: the texel it has just stored, decoded from the value AS STORED
+// (rounded through binary16 where the images are), goes into its own pair and its left neighbour's.  The host tracks whether the
+// copy is current (mt_context.cu) and skips the decode launch when it is.
+__device__ __forceinline__ void store_pixel_decoded(const CloudParams& P, int px, int py, F4 hdr, F4 mask)
+{
+    store_pixel(P, (size_t)py * P.W + px, hdr, mask);
+    if (P.decoded) {
+        float4 m = make_float4(mask.x, mask.y, mask.z, mask.w);
+        if (P.storage != MT_PX_F32) m = px_round_f16(m);
+        F4 t;
+        t.x = m.x; t.y = m.y; t.z = m.z; t.w = m.w;
+        const float d = mask_texel_decode(t);
+        float2* e = P.decoded + ((size_t)(py + 1) * (size_t)P.decodedPitch + (size_t)(px + 1));
+        e->x = d;
+        e[-1].y = d;
+    }
+}
 
 __global__ void __launch_bounds__(128) cloud_rays_kernel(const __grid_constant__ CloudParams P)
 {
@@ -525,7 +545,7 @@ __global__ void __launch_bounds__(32 * MT_S16_WARPS, MT_S16_MINBLOCKS) cloud_six
             F4 hdr, mask;
             mask.x = mask.y = mask.z = mask.w = 0.0f;
             RaySetup R = cloud_ray_setup<false>(P, M, J, px, py, pixelID, hdr);  // geometry only: the sky is warp 1's
-            if (R.branch == 0) store_pixel(P, (size_t)py * P.W + px, hdr, mask);  // ocean: final
+            if (R.branch == 0) store_pixel_decoded(P, px, py, hdr, mask);  // ocean: final
             else if (R.branch == 2)
                 for (float t = R.t_in; t < R.t_out && n < MT_STEP_SLICES; t += R.stepSize) tk[n++][lane] = t;
             R.nsteps = n;
@@ -544,7 +564,7 @@ __global__ void __launch_bounds__(32 * MT_S16_WARPS, MT_S16_MINBLOCKS) cloud_six
                 F4 hdr, mask;
                 hdr.x = bg.x; hdr.y = bg.y; hdr.z = bg.z; hdr.w = 1.0f;
                 mask.x = mask.y = mask.z = mask.w = 0.0f;
-                store_pixel(P, (size_t)py * P.W + px, hdr, mask);
+                store_pixel_decoded(P, px, py, hdr, mask);
             } else {
                 bgs[lane] = bg;
             }
@@ -581,7 +601,7 @@ __global__ void __launch_bounds__(32 * MT_S16_WARPS, MT_S16_MINBLOCKS) cloud_six
         RaySetup Rc = R;
         Rc.bg = bgs[lane];
         cloud_composite(Rc, accum, color, hdr, mask);
-        store_pixel(P, (size_t)py * P.W + px, hdr, mask);
+        store_pixel_decoded(P, px, py, hdr, mask);
     }
 }
 

@@ -15,6 +15,10 @@
 #include "cloud_core.cuh"
 #include "mt_host_consts.h"
 #include "post_core.cuh"
+
+#ifndef MT_INCREMENTAL_DECODE
+#define MT_INCREMENTAL_DECODE 1  /* the fused 1-of-16 Cloud kernel keeps the god-ray pass's decoded mask current (cloud_raymarch.cu) */
+#endif
 #include "mt_launch.h"
 
 #define MT_FLAG_PASS_TIMING_INTERNAL MT_FLAG_PASS_TIMING
@@ -41,6 +45,9 @@ struct MtContext {
     F4* mask = nullptr;
     float2* maskDecoded = nullptr; // pitch x (H+2) pairs: scratch of the god-ray pass
     float* uvTab = nullptr;        // per-size uv table of the post passes (mt_params.h)
+    bool decodedCurrent = false;   // maskDecoded matches the mask: set by a god-ray dispatch, kept by the fused 1-of-16 Cloud kernel (which
+                                   // updates the pairs it touches), cleared by every other writer of the mask
+    bool maskShared = false;       // the mask's device pointer / IPC handle has been handed out: writes can no longer be tracked
     F4* maskStage = nullptr;       // device snapshot of the mask behind mtReadImageAsync (lazily allocated)
     float* greyStage = nullptr;    // the decoded one-float-per-pixel god-ray image behind mtReadGodRayGreyAsync (lazily allocated)
     uint32_t* ldr[2] = { nullptr, nullptr };  // ping-pong with the HDR images (same `cur`)
@@ -203,6 +210,8 @@ static void adopt_images(MtContext* c, const ImageSet& s)
 {
     c->hdr[0] = s.hdr[0]; c->hdr[1] = s.hdr[1]; c->mask = s.mask;
     c->ldr[0] = s.ldr[0]; c->ldr[1] = s.ldr[1]; c->ldrScratch = s.ldrScratch; c->maskDecoded = s.maskDecoded; c->uvTab = s.uvTab;
+    c->decodedCurrent = false;
+    c->maskShared = false;
     c->cur = 0;
 }
 static MtStatus alloc_images(MtContext* c)
@@ -637,6 +646,11 @@ static MtStatus cloud_dispatch(MtContext* c, int full, const RowTiles* tiles, bo
         P.tileDone = c->tileDone;
         n = 2;
     }
+    // the decoded copy of the mask stays current only through the fused 1-of-16 kernel writing this context's own mask
+    const bool keepsDecoded = stepParallel && !split && !c->outMask && !c->maskShared && c->decodedCurrent && MT_INCREMENTAL_DECODE;
+    P.decoded = keepsDecoded ? c->maskDecoded : nullptr;
+    P.decodedPitch = (int)mt_godray_pitch(c->W);
+    c->decodedCurrent = keepsDecoded;
     if (split) MT_CUDA(c, mt_launch_cloud_sixteenth_split(P, c->stream, &n));
     else if (stepParallel) MT_CUDA(c, mt_launch_cloud_sixteenth_fused(P, c->stream));
     else MT_CUDA(c, mt_launch_cloud(P, c->stream));
@@ -762,6 +776,7 @@ static MtStatus godrays_dispatch(MtContext* c, bool fuse_tonemap)
     P.seed = tonemap_seed(c);
     P.frame = godray_frame(P.cam);
     P.uv = c->uvTab;
+    P.decodedCurrent = c->decodedCurrent && !c->maskShared;
     wait_pending_read(c, P.hdr);
     if (fuse_tonemap) wait_pending_read(c, P.ldr);
     pass_begin(c, MT_PASS_GODRAYS);
@@ -771,7 +786,8 @@ static MtStatus godrays_dispatch(MtContext* c, bool fuse_tonemap)
         pass_begin(c, MT_PASS_TONEMAP);
         pass_end(c, MT_PASS_TONEMAP);
     }
-    c->launches += 2;  // mask_decode_kernel + godrays_kernel
+    c->launches += P.decodedCurrent ? 1 : 2;  // (mask_decode_kernel +) godrays_kernel
+    c->decodedCurrent = true;
     return MT_OK;
 }
 MtStatus mtDispatchGodRays(MtContext* c)
@@ -978,6 +994,7 @@ try {
     MT_CUDA(c, cudaSetDevice(c->device));
     wait_pending_read(c, image_ptr(c, which));
     MT_CUDA(c, cudaMemcpyAsync(image_ptr(c, which), host, bytes, cudaMemcpyHostToDevice, c->stream));
+    if (which == MT_IMAGE_GODRAY_MASK) c->decodedCurrent = false;
     return MT_OK;
 } MT_NOTHROW
 MtStatus mtClearImages(MtContext* c)
@@ -991,6 +1008,7 @@ try {
     MT_CUDA(c, cudaMemsetAsync(c->hdr[0], 0, px * hb, c->stream));
     MT_CUDA(c, cudaMemsetAsync(c->hdr[1], 0, px * hb, c->stream));
     MT_CUDA(c, cudaMemsetAsync(c->mask, 0, px * hb, c->stream));
+    c->decodedCurrent = false;
     MT_CUDA(c, cudaMemsetAsync(c->ldr[0], 0, px * 4, c->stream));
     MT_CUDA(c, cudaMemsetAsync(c->ldr[1], 0, px * 4, c->stream));
     MT_CUDA(c, cudaMemsetAsync(c->ldrScratch, 0, px * 4, c->stream));
@@ -1000,6 +1018,7 @@ MtStatus mtImageDevicePtr(MtContext* c, MtImage which, void** p)
 try {
     if (!c || !p || (int)which < 0 || (int)which > MT_IMAGE_LDR_PREV) return MT_ERR_INVALID;
     *p = image_ptr(c, which);
+    if (which == MT_IMAGE_GODRAY_MASK) c->maskShared = true;  // the caller may write it: the decoded copy is rebuilt by every god-ray dispatch from now on
     return MT_OK;
 } MT_NOTHROW
 MtStatus mtSetCloudOutput(MtContext* c, void* hdr, void* mask)
@@ -1041,6 +1060,7 @@ try {
     MT_CUDA(c, cudaSetDevice(c->device));
     cudaIpcMemHandle_t h;
     MT_CUDA(c, cudaIpcGetMemHandle(&h, image_ptr(c, which)));
+    if (which == MT_IMAGE_GODRAY_MASK) c->maskShared = true;
     memcpy(handle, &h, 64);
     return MT_OK;
 } MT_NOTHROW

@@ -125,6 +125,8 @@ struct CloudParams {
     unsigned* itemCount;           // how many of them (zeroed by cloud_rays_kernel, filled by cloud_base_kernel)
     int rayStride;                 // rays per sample slice = 128 * CTAs of the ray grid
     unsigned* tileDone;            // full-quality row-tile launches with forwarding (mtSetCloudForward): CTAs finished per tile
+    float2* decoded;               // fused 1-of-16 kernel: non-null = also keep the god-ray pass's decoded pair image current (below)
+    int decodedPitch;              //   its row pitch in elements (mt_godray_pitch)
 };
 
 // Per-frame values of the post passes.  Like MarchConst they are evaluated by the HOST per dispatch (reproject_frame, godray_frame,
@@ -181,6 +183,7 @@ struct GodRayParams {
     F4* hdr;
     int W, H;
     int storage;  // MtStorage of the HDR / mask images (mt_pixel.cuh)
+    int decodedCurrent; // the decoded image already matches the mask (the 1-of-16 Cloud kernel kept it so): no decode launch
     uint32_t* ldr;      // non-null: the tone map is fused into this pass's store (mtFrameEx with both passes): packed RGBA8 out
     unsigned seed;      //   uint(time.y) of the tone map's dither
 };

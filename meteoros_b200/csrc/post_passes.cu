@@ -233,11 +233,13 @@ cudaError_t mt_launch_godrays(const GodRayParams& P0, cudaStream_t stream)
                                               (intptr_t)(uint32_t)((uint32_t)MT_FLOOR_MAGIC_BITS << 3));
     P.tapBaseWide = reinterpret_cast<const char*>(reinterpret_cast<uintptr_t>(P.decoded) + ((intptr_t)P.pitch + 1) * (intptr_t)sizeof(float2) -
                                                   (intptr_t)MT_FLOOR_MAGIC_BITS * 8);
-    dim3 dgrid((unsigned)((P.W + 2 + 31) / 32), (unsigned)((P.H + 2 + 7) / 8), 1);
-    if (P.storage == MT_PX_F16) mask_decode_kernel<MT_PX_F16><<<dgrid, 256, 0, stream>>>(P);
-    else mask_decode_kernel<MT_PX_F32><<<dgrid, 256, 0, stream>>>(P);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
+    if (!P.decodedCurrent) {
+        dim3 dgrid((unsigned)((P.W + 2 + 31) / 32), (unsigned)((P.H + 2 + 7) / 8), 1);
+        if (P.storage == MT_PX_F16) mask_decode_kernel<MT_PX_F16><<<dgrid, 256, 0, stream>>>(P);
+        else mask_decode_kernel<MT_PX_F32><<<dgrid, 256, 0, stream>>>(P);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
     dim3 grid((unsigned)((P.W + MT_GODRAY_CTA_W - 1) / MT_GODRAY_CTA_W), (unsigned)((P.H + MT_GODRAY_CTA_H - 1) / MT_GODRAY_CTA_H), 1);
     const unsigned threads = MT_GODRAY_LOG2W == 5 ? 32 * MT_GODRAY_WARPS : 128;
     switch (P.log2pitch) {

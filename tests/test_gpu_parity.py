@@ -948,3 +948,44 @@ def test_cloud_generic_kernels_when_texture_coordinates_are_large(api, oracle_mo
         assert np.array_equal(wr, ref16["hdr"][..., 3] != -3.0)
         assert np.array_equal(r.read_image(api.IMAGE_GODRAY_MASK), ref16["mask"])
         check_hdr(got, ref16["hdr"], wr)
+
+
+@pytest.mark.parametrize("storage", ["f32", "f16"])
+def test_incremental_mask_decode_equals_full_decode(api, noise, storage):
+    """The fused 1-of-16 Cloud kernel keeps the god-ray pass's decoded copy of the mask current (it rewrites the pairs of the texels
+    it stores), so a frame's god-ray dispatch skips mask_decode_kernel.  A context whose mask pointer has been handed out decodes
+    the whole mask every time.  Twelve frames of the reference loop -- with a host write into the mask and a full-quality dispatch
+    in between, both of which must invalidate the copy -- have to come out bit-identical from both."""
+    from meteoros_b200 import scene
+
+    w, h = 256, 144
+    st = api.STORAGE_F16 if storage == "f16" else api.STORAGE_F32
+    outs, launches = [], []
+    for shared in (False, True):
+        cam, sc, sky = scene.Camera(w, h), scene.Scene(), scene.Sky()
+        frames = []
+        with api.CloudRenderer(w, h, storage=st) as r:
+            r.upload_noise(noise)
+            r.set_sun_and_sky(sky.ubo())
+            if shared:
+                assert r.image_device_ptr(api.IMAGE_GODRAY_MASK) != 0   # from here on the library cannot track writes to the mask
+            old = cam.ubo()
+            n0 = r.launch_count()
+            for f in range(12):
+                cam.rotate_about_up(0.5)
+                sc.update_time(1 / 60)
+                r.set_camera(cam.ubo()); r.set_camera_old(old); r.set_time(sc.ubo())
+                if f == 5:     # a host write into the mask: the decoded copy is stale
+                    m = r.read_image(api.IMAGE_GODRAY_MASK)
+                    m[h // 3: h // 2] *= 0.5
+                    r.write_image(api.IMAGE_GODRAY_MASK, m)
+                if f == 8:     # a full-quality dispatch rewrites every mask texel without touching the copy
+                    r.dispatch_cloud_full()
+                r.frame(True, False)
+                frames.append((r.read_image(api.IMAGE_CLOUD_PREV), r.read_image(api.IMAGE_LDR_PREV), r.read_image(api.IMAGE_GODRAY_MASK)))
+                old = cam.ubo()
+            launches.append(r.launch_count() - n0)
+        outs.append(frames)
+    for (h0, l0, m0), (h1, l1, m1) in zip(*outs):
+        assert np.array_equal(m0, m1) and np.array_equal(h0, h1, equal_nan=True) and np.array_equal(l0, l1)
+    assert launches[0] < launches[1]   # the tracked context skipped decode launches (9 of 12 frames)
