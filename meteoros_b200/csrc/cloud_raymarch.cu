@@ -37,37 +37,33 @@
     const MarchTabs& J = Ms.tabs
 #endif
 
-// One thread per 32 cells (one output word): bit x of the word = any of the cell's eight corner texels may carry cloud.
-// Where the (r, F) quads exist, bit 0 of each cell's first word repeats the cell's bit (the pipelined cone loop reads it
-// from the quad it has loaded anyway).
+// One thread per filter cell, a warp = the 32 cells of one bitmap word: each lane tests its cell's eight corner texels (coalesced
+// along x, L1 / L2 hits), a ballot assembles the word.  Where the (r, F) bricks exist, bit 0 of each brick's first word repeats the
+// cell's bit (the pipelined cone loop reads it from the brick it has loaded anyway); the other bits of that word are rf_pack of the
+// cell's own texel, which the lane holds, so the word is stored whole -- no read-modify-write of a 64 MB volume.  (Rounds 1-2: one
+// thread per 32 cells, 65 536 threads looping over 256 texel tests and 32 scattered read-modify-writes each: 71 us per coverage
+// change, 9 % of the 256-view sweep.)
 __global__ void __launch_bounds__(256) occupancy_build_kernel(Tex3D T, uint32_t* occ, float coverage, uint4* rfq)
 {
-    const unsigned wpr = (unsigned)T.w >> 5;
-    const unsigned nwords = wpr * (unsigned)T.h * (unsigned)T.d;
-    const unsigned wi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (wi >= nwords) return;
-    const unsigned xw = wi % wpr, y = (wi / wpr) % (unsigned)T.h, z = wi / (wpr * (unsigned)T.h);
-    const unsigned y1 = (y + 1u) & (unsigned)(T.h - 1), z1 = (z + 1u) & (unsigned)(T.d - 1);
+    const unsigned cell = blockIdx.x * blockDim.x + threadIdx.x;            // (z*h + y)*w + x; w is a multiple of 32
+    const unsigned ncells = (unsigned)T.w * (unsigned)T.h * (unsigned)T.d;
+    if (cell >= ncells) return;                                              // whole warps: ncells is a multiple of 32
+    const unsigned x = cell % (unsigned)T.w, y = (cell / (unsigned)T.w) % (unsigned)T.h, z = cell / ((unsigned)T.w * (unsigned)T.h);
+    const unsigned x1 = (x + 1u) & (unsigned)(T.w - 1), y1 = (y + 1u) & (unsigned)(T.h - 1), z1 = (z + 1u) & (unsigned)(T.d - 1);
     const unsigned rows[4] = { (z * T.h + y) * T.w, (z * T.h + y1) * T.w, (z1 * T.h + y) * T.w, (z1 * T.h + y1) * T.w };
-    uint32_t bits = 0;
-    for (unsigned k = 0; k < 32; ++k) {
-        const unsigned x = xw * 32u + k, x1 = (x + 1u) & (unsigned)(T.w - 1);
-        bool any = false;
+    const uint32_t own = __ldg(T.texels + rows[0] + x);
+    bool any = occ_texel_may_be_cloud(own, coverage) || occ_texel_may_be_cloud(__ldg(T.texels + rows[0] + x1), coverage);
 #pragma unroll
-        for (int r = 0; r < 4; ++r)
-            any = any || occ_texel_may_be_cloud(__ldg(T.texels + rows[r] + x), coverage) ||
-                  occ_texel_may_be_cloud(__ldg(T.texels + rows[r] + x1), coverage);
-        bits |= (any ? 1u : 0u) << k;
+    for (int r = 1; r < 4; ++r)
+        any = any || occ_texel_may_be_cloud(__ldg(T.texels + rows[r] + x), coverage) ||
+              occ_texel_may_be_cloud(__ldg(T.texels + rows[r] + x1), coverage);
+    const uint32_t bits = __ballot_sync(0xffffffffu, any);
+    if ((threadIdx.x & 31) == 0) occ[cell >> 5] = bits;
 #if MT_CONE_PIPE
-        if (rfq) {  // the pipelined cone loop reads the cell's flag from the brick it has loaded: bit 0 of the first word
-            uint32_t* w0 = &rfq[(MT_RF_BRICKS ? 2u : 1u) * ((z * (unsigned)T.h + y) * (unsigned)T.w + x)].x;
-            *w0 = (*w0 & ~1u) | (any ? 1u : 0u);
-        }
+    if (rfq) rfq[(MT_RF_BRICKS ? 2u : 1u) * cell].x = rf_pack(own) | (any ? 1u : 0u);  // = what build_rf_quads_kernel wrote, with this coverage's flag
 #else
-        (void)rfq;
+    (void)rfq;
 #endif
-    }
-    occ[wi] = bits;
 }
 
 // quads[(z*h + y)*w + x] = the 2x2 texels of filter cell (x, y) in slice z, REPEAT applied (d = 1 for 2D textures)
@@ -128,8 +124,8 @@ cudaError_t mt_launch_build_quads(const uint32_t* texels, int w, int h, int d, v
 
 cudaError_t mt_launch_occupancy(const Tex3D& low, uint32_t* occ, float coverage, cudaStream_t stream)
 {
-    const unsigned nwords = (unsigned)(low.w >> 5) * (unsigned)low.h * (unsigned)low.d;
-    occupancy_build_kernel<<<(nwords + 255) / 256, 256, 0, stream>>>(low, occ, coverage, (uint4*)low.rfquads);
+    const unsigned ncells = (unsigned)low.w * (unsigned)low.h * (unsigned)low.d;  // w is a multiple of 32 (mtUploadTexture3D builds the bitmap only then)
+    occupancy_build_kernel<<<(ncells + 255) / 256, 256, 0, stream>>>(low, occ, coverage, (uint4*)low.rfquads);
     return cudaGetLastError();
 }
 
