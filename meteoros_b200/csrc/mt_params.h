@@ -165,6 +165,8 @@ struct ReprojParams {
     int W, H;
     int storage;  // MtStorage of the HDR / mask images (mt_pixel.cuh)
     int* taps;  // debug: 10 per pixel, or null
+    int skipId;   // >= 0: leave out the pixels the frame's 1-of-16 Cloud dispatch with this id writes (pixel % 4 == (id / 4, id % 4) inside
+    int tx, ty;   //   its tx x ty thread grid): mtFrameEx runs that dispatch BESIDE this pass on a second stream; -1: every pixel
 };
 
 struct GodRayParams {

@@ -23,6 +23,8 @@ __global__ void __launch_bounds__(256) reproject_kernel(const __grid_constant__ 
     const int x = blockIdx.x * 32 + (threadIdx.x & 31);
     const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
     if (x >= P.W || y >= P.H) return;
+    // the 1-of-16 Cloud dispatch running beside this pass owns this pixel (the same predicate as its `valid`, cloud_raymarch.cu)
+    if (P.skipId >= 0 && (((x & 3) << 2) | (y & 3)) == P.skipId && (x >> 2) < P.tx && (y >> 2) < P.ty) return;
     int taps[10];
     // frame constants from the parameter block, (x / W, y / H) from the context's uv table: no shared memory, no barrier
     reproject_taps<NICE>(P, P.frame, __ldg(P.uv + x), __ldg(P.uv + P.W + y), taps);
