@@ -525,10 +525,10 @@ __global__ void __launch_bounds__(32 * MT_S16_WARPS, MT_S16_MINBLOCKS) cloud_six
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // the CTA's ray tile: 8x4 rays of the (tx, ty) grid; rows of tiles in mt_tile_order: the marching rows from the horizon
     // upwards first, interleaved with the ocean rows -- the kernel is about two waves of CTAs, so what runs last decides its tail
-    const int tilesX = P.tx >> 3;
+    const int tilesX = P.tx >> MT_S16_LOG2W;
     const int jrow = (int)blockIdx.x / tilesX, txi = (int)blockIdx.x - jrow * tilesX;
     const int tyi = mt_tile_order(P.rows, jrow);
-    const int gx = txi * 8 + (lane & 7), gy = tyi * 4 + (lane >> 3);
+    const int gx = txi * MT_S16_TW + (lane & (MT_S16_TW - 1)), gy = tyi * MT_S16_TH + (lane >> MT_S16_LOG2W);
     const int pixelID = P.tm.frameCountMod16;
     const int px = gx * 4 + (pixelID >> 2), py = gy * 4 + (pixelID & 3);
     const bool valid = gx < P.tx && gy < P.ty && px < P.W && py < P.H;
@@ -603,7 +603,7 @@ __global__ void __launch_bounds__(32 * MT_S16_WARPS, MT_S16_MINBLOCKS) cloud_six
 
 cudaError_t mt_launch_cloud_sixteenth_fused(const CloudParams& P, cudaStream_t stream)
 {
-    const unsigned tiles = (unsigned)((P.tx / 8) * (P.ty / 4));  // tx, ty are multiples of 32
+    const unsigned tiles = (unsigned)((P.tx / MT_S16_TW) * (P.ty / MT_S16_TH));  // tx, ty are multiples of 32
     if (P.tun.use_weather) cloud_sixteenth_kernel<true, false><<<tiles, 32 * MT_S16_WARPS, 0, stream>>>(P);
     else if (mt_std_dims(P)) cloud_sixteenth_kernel<false, true><<<tiles, 32 * MT_S16_WARPS, 0, stream>>>(P);
     else cloud_sixteenth_kernel<false, false><<<tiles, 32 * MT_S16_WARPS, 0, stream>>>(P);

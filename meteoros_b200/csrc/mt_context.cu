@@ -596,8 +596,8 @@ static MtStatus cloud_dispatch(MtContext* c, int full, const RowTiles* tiles, bo
     }
     P.rows.heavy_first = 0;
     if (!full) {  // fused 1-of-16 kernel: its CTAs are 8x4-ray tiles; a row of tiles covers 16 pixel rows (cloud_sixteenth_kernel)
-        P.rows.tile_rows = 16;
-        P.rows.tile_begin = 0; P.rows.tile_stride = 1; P.rows.tile_count = P.ty / 4;
+        P.rows.tile_rows = 4 * MT_S16_TH;
+        P.rows.tile_begin = 0; P.rows.tile_stride = 1; P.rows.tile_count = P.ty / MT_S16_TH;
     }
     if (!(c->flags & MT_FLAG_TOP_DOWN)) {
         // first pixel row whose centre-column ray no longer marches (dir.y < 0.06, cloudRayMarch.comp:730): castRay of

@@ -23,6 +23,13 @@ struct float2 { float x, y; };
 #define MT_CTA_H 8
 #endif
 
+// Ray tile of one CTA of the fused 1-of-16 kernel (cloud_sixteenth_kernel): 2^MT_S16_LOG2W x (32 >> MT_S16_LOG2W) rays, four pixels apart
+#ifndef MT_S16_LOG2W
+#define MT_S16_LOG2W 3  /* 8x4 rays = 32x16 pixels */
+#endif
+#define MT_S16_TW (1 << MT_S16_LOG2W)
+#define MT_S16_TH (32 >> MT_S16_LOG2W)
+
 /* One cap on the march loop for every path -- the sequential kernels, the step-parallel 1-of-16 kernels and the oracle.  The
  * shader's own bound is maxSteps <= 60 (cloudRayMarch.comp:585), i.e. at most 61 iterations of `t += stepSize`; 59 is the most
  * any camera of the test suite produces.  The cap only guards degenerate shells and is never reached. */

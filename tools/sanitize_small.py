@@ -86,3 +86,37 @@ for flags in (api.FLAG_SPLIT_MARCH, api.FLAG_NO_CONE_RF, api.FLAG_TOP_DOWN | api
         r.frame(True, True)
         r.dispatch_cloud_full()
         print("flags", flags, "mean", float(np.nanmean(r.read_image(api.IMAGE_CLOUD_CUR))))
+# round 2, second session: the two-stream frame with the Cloud kernel keeping the decoded mask current (no timing / counting flag),
+# a host write into the mask in between; the generic march kernels (texture coordinates beyond the magic floor's range); the IEEE
+# reprojection / TXAA kernels (ray origin above the inner shell) and taps far outside the image (a quarter turn between frames)
+for size in ((130, 70), (33, 17), (64, 36)):
+    ww, hh = size
+    cam2, sc2 = scene.Camera(ww, hh), scene.Scene()
+    with api.CloudRenderer(ww, hh) as r:
+        r.upload_noise(textures.load_noise())
+        r.set_sun_and_sky(sky.ubo())
+        old2 = cam2.ubo()
+        for f in range(5):
+            cam2.rotate_about_up(0.25 if f != 3 else 88.0)
+            sc2.update_time(1 / 60)
+            r.set_camera(cam2.ubo()); r.set_camera_old(old2); r.set_time(sc2.ubo())
+            if f == 2:
+                r.write_image(api.IMAGE_GODRAY_MASK, r.read_image(api.IMAGE_GODRAY_MASK) * 0.5)
+            r.frame(True, True)
+            old2 = cam2.ubo()
+        tun = scene.default_tuning()
+        tun["cloud_speed"] = 200.0
+        sc2.time["time"] = (0.016, 100.0)
+        r.set_time(sc2.ubo()); r.set_tuning(tun)
+        r.frame(True, True)
+        r.dispatch_cloud_full()
+        print("two-stream frames", size, "mean", float(np.nanmean(r.read_image(api.IMAGE_CLOUD_CUR))))
+    high = scene.Camera(ww, hh, eye=(0.0, -9000.0, 2.0), ref=(0.0, -9000.0, 1.0))
+    with api.CloudRenderer(ww, hh) as r:
+        r.upload_noise(textures.load_noise())
+        r.set_sun_and_sky(sky.ubo())
+        o = high.ubo()
+        high.rotate_about_up(0.25)
+        r.set_camera(high.ubo()); r.set_camera_old(o); r.set_time(sc2.ubo())
+        r.frame(True, True)
+        print("eye above the inner shell", size, "mean", float(np.nanmean(r.read_image(api.IMAGE_CLOUD_PREV))))
