@@ -818,3 +818,137 @@ MT_DEVICE void cloud_ray(const CloudParams& P, const MarchConst& M, const MarchT
 #endif
     cloud_composite(R, accum, color, hdr, mask);
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// MT_WARP_QUEUE: the march of one warp's 32 rays with the in-cloud part of the steps handed round the warp.
+//
+// A march step's contribution (StepSample) does not depend on the steps before it; only the running sums do.  In the plain loop
+// (cloud_ray) the in-cloud part of a step -- erosion, six light-cone samples, light energy: two thirds of the kernel's
+// instructions -- runs with the 26 of 32 lanes whose ray happens to be inside a cloud at that step
+// (profiles/r2b_cloud_final.md).  Here every lane first takes its ray's NEXT step as far as the base density; rays inside a cloud
+// append (sample point, height, base density) to the warp's ring of pending items in shared memory and march on.  Whenever 32
+// items are pending (or a ray has four outstanding, or nothing is left to march) lane j evaluates item j -- whoever's ray it
+// belongs to, with that ray's cached cone offsets -- and writes (inc, energy) back into the item's slot; the owners then fold
+// their results in step order.  The arithmetic of every (ray, step) is the plain loop's, so the image is bit-identical; steps
+// taken past a ray's early exit (accumulated density >= 1) are computed and dropped.
+// ---------------------------------------------------------------------------------------------------------------------
+#if !defined(MT_HOSTSIM)
+#ifndef MT_WARP_QUEUE
+#define MT_WARP_QUEUE 0
+#endif
+#define MT_WQ_SLOTS 64
+struct WarpQueue {
+    float4 a[MT_WQ_SLOTS];    // pos.xyz, h          -- after evaluation: (inc, energy, -, -)
+    float4 b[MT_WQ_SLOTS];    // skew.xyz, baseDensity
+    unsigned owner[MT_WQ_SLOTS];
+};
+
+template <int STD>
+__device__ __forceinline__ void cloud_ray_queued(const CloudParams& P, const MarchConst& M, const MarchTabs& J, int px, int py, int pixelID,
+                                                 bool valid, F4& hdr, F4& mask, F4* coneWarp, int coneStride, WarpQueue& Q)
+{
+    const unsigned FULLM = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u;
+    RayCounters cnt = { 0u, 0u, 0u, 0u, 0u, 0u };
+    mask.x = mask.y = mask.z = mask.w = 0.0f;
+    RaySetup R;
+    R.branch = 0;
+    R.t_in = R.t_out = R.stepSize = 0.0f;
+    R.dir = mk3(0.0f, 0.0f, 0.0f);
+    if (valid) R = cloud_ray_setup(P, M, J, px, py, pixelID, hdr);
+    const bool marching = valid && R.branch == 2;
+    if (!__any_sync(FULLM, marching)) return;  // warp-uniform
+
+    ConeOffsets CO;
+    CO.xyz = coneWarp + lane;
+    CO.stride = coneStride;
+    if (marching) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            P2 oxy;
+            F4 o;
+            cone_offset(M, R.stepSize, i, oxy, o.z);
+            o.x = lo2(oxy); o.y = hi2(oxy);
+            o.w = i == 0 ? R.bg.x : i == 1 ? R.bg.y : i == 2 ? R.bg.z : i == 3 ? R.phase : i == 4 ? R.cosAngle : R.lenToInner;
+            coneWarp[lane + i * coneStride] = o;
+        }
+    }
+    __syncwarp();
+    RaySetup Rt;  // what cloud_step_light reads of a ray beside its parked values: the reciprocal of 1 - coverage (one value per frame)
+    Rt.covRcp = nice_rcp(M.covDen);
+    Rt.stepSize = 0.0f; Rt.phase = 0.0f; Rt.cosAngle = 0.0f;
+
+    float accum = 0.0f, transmittance = 1.0f, color = 0.0f;
+    unsigned st = (unsigned)pixelID << 3;
+    float t = R.t_in;
+    bool active = marching && t < R.t_out;
+    bool done = false;
+    unsigned pend = 0u;            // up to four outstanding items of this ray, oldest in the low byte: slot + 1
+    unsigned head = 0u, count = 0u;  // warp-uniform: the ring holds slots head .. head + count - 1
+    for (;;) {
+        bool hit = false;
+        StepBase B;
+        if (active) {
+            const unsigned off = (st + ((unsigned)mt_f2i(t) << 3)) & 0x70u;
+            const float* sj = reinterpret_cast<const float*>(reinterpret_cast<const char*>(&J.stepJitter[0][0]) + off);
+            B = cloud_step_base<false, false, STD>(P, M, sj, R, t, cnt, CO);
+            hit = B.baseDensity > 0.0f;
+            t += R.stepSize;
+            st += 256u;
+            active = t < R.t_out && st < ((unsigned)MT_MAX_MARCH_ITERS << 8);
+        }
+        const unsigned hm = __ballot_sync(FULLM, hit);
+        if (hit) {
+            const unsigned slot = (head + count + __popc(hm & ((1u << lane) - 1u))) & (MT_WQ_SLOTS - 1u);
+            Q.a[slot] = make_float4(B.pos.x, B.pos.y, B.pos.z, B.h);
+            Q.b[slot] = make_float4(B.skew.x, B.skew.y, B.skew.z, B.baseDensity);
+            Q.owner[slot] = lane;
+            // append to the ray's outstanding list: first free byte
+            const unsigned sh = pend == 0u ? 0u : pend < 0x100u ? 8u : pend < 0x10000u ? 16u : 24u;
+            pend |= (slot + 1u) << sh;
+        }
+        count += __popc(hm);
+        bool anyActive = __any_sync(FULLM, active);
+        __syncwarp();
+        while (count >= 32u || (count > 0u && (!anyActive || __any_sync(FULLM, (pend >> 24) != 0u)))) {
+            const unsigned n = count < 32u ? count : 32u;
+            if (lane < n) {
+                const unsigned slot = (head + lane) & (MT_WQ_SLOTS - 1u);
+                const float4 a = Q.a[slot], b = Q.b[slot];
+                StepBase I;
+                I.pos = mk3(a.x, a.y, a.z); I.h = a.w;
+                I.skew = mk3(b.x, b.y, b.z); I.baseDensity = b.w;
+                ConeOffsets CI;
+                CI.xyz = coneWarp + Q.owner[slot];
+                CI.stride = coneStride;
+                const StepSample S = cloud_step_light<false, false, STD>(P, M, Rt, I, cnt, CI);
+                *reinterpret_cast<float2*>(&Q.a[slot]) = make_float2(S.inc, S.energy);
+            }
+            __syncwarp();
+            while ((pend & 0xffu) != 0u && ((((pend & 0xffu) - 1u) - head) & (MT_WQ_SLOTS - 1u)) < n) {
+                const float2 r = *reinterpret_cast<const float2*>(&Q.a[(pend & 0xffu) - 1u]);
+                pend >>= 8;
+                if (!done) {
+                    StepSample S;
+                    S.inc = r.x; S.energy = r.y;
+                    if (cloud_step_combine(S, accum, transmittance, color)) {
+                        done = true;
+                        active = false;
+                    }
+                }
+            }
+            __syncwarp();
+            head = (head + n) & (MT_WQ_SLOTS - 1u);
+            count -= n;
+            anyActive = __any_sync(FULLM, active);
+        }
+        if (!anyActive && count == 0u) break;
+    }
+    if (marching) {
+        RaySetup Rc;
+        Rc.dir = R.dir;
+        Rc.bg = mk3(CO.xyz[0].w, CO.xyz[coneStride].w, CO.xyz[2 * coneStride].w);
+        cloud_composite(Rc, accum, color, hdr, mask);
+    }
+}
+#endif

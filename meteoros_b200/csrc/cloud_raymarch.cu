@@ -202,10 +202,19 @@ __global__ void __launch_bounds__(128, MT_CLOUD_MINBLOCKS) cloud_raymarch_kernel
     __shared__ __align__(128) float4 outStage[4][32];
     RayCounters cnt = { 0u, 0u, 0u, 0u, 0u, 0u };
     const bool bulk = FULL && MT_WARP_SHAPE == 1 && P.bulkStore && __all_sync(0xffffffffu, valid);  // warp-uniform
+    // MT_WARP_QUEUE (cloud_core.cuh): the production full-quality kernel marches a warp's rays together, in-cloud steps handed round
+    constexpr bool QUEUED = MT_WARP_QUEUE && MT_CONE_CACHE && MT_CONE_PIPE && MT_PARK_BG && FULL && !COUNT && !DEBUG && !WEATHER && STD;
+    F4 hdr, mask;
+#if MT_WARP_QUEUE && MT_CONE_CACHE
+    if constexpr (QUEUED) {
+        __shared__ __align__(16) WarpQueue wq[4];
+        cloud_ray_queued<2>(P, M, J, px, py, pixelID, valid, hdr, mask, &coneXYZ[0][warp << 5], 128, wq[warp]);
+    }
+#endif
     if (valid) {
-        F4 hdr, mask;
         const size_t idx = (size_t)py * (size_t)P.W + (size_t)px;
-        cloud_ray<COUNT, DEBUG, WEATHER, (STD ? (MT_CONE_PIPE ? 2 : 1) : 0)>(P, M, J, px, py, pixelID, hdr, mask, cnt, DEBUG ? (P.debug + idx) : nullptr, cxyz, 128);
+        if constexpr (!QUEUED)
+            cloud_ray<COUNT, DEBUG, WEATHER, (STD ? (MT_CONE_PIPE ? 2 : 1) : 0)>(P, M, J, px, py, pixelID, hdr, mask, cnt, DEBUG ? (P.debug + idx) : nullptr, cxyz, 128);
         const float4 h4 = make_float4(hdr.x, hdr.y, hdr.z, hdr.w);
         if (bulk) {
             // The marching warp must not wait on a remote write: its 32 pixels go to shared memory, and lanes 0 and 16 each
