@@ -17,6 +17,9 @@ reprojection) over one synthetic 3840x2160 frame of the default cloudscape = 8 2
          ranks, HDR tiles stored straight into GPU 0's image over NVLink by the march kernel (BASELINE config 4), timed
          against the same frame on rank 0 alone in the same run, gathered frame compared bit for bit with the single-GPU
          frame.  `--workload frame8k` runs only that, with --gather / --tile-rows variants.
+  seq1080p / views256 (sub-records of the default line)  BASELINE configs 2 and 5 beside the headline: ms per frame of the
+         1920x1080 16-frame pan through mtFrame (reprojection + 1-of-16 Cloud dispatch + god rays + tone map) -- the second
+         half of BASELINE.json's metric -- and the 256-view sun / coverage sweep.  --workload seq1080p / views256 run them alone.
   --impl reference   the reference's Cloud shader compiled for the CPU from its own text (oracle/_ref; else the oracle
          restatement), OpenMP over all host cores (team size set explicitly and reported as measured), on a bounded,
          evenly spread sample of the same frame: the reference's own path needs Vulkan + a window.
@@ -284,6 +287,51 @@ def views256_record(args, api, sharding, torch, dist, world, rank, local_rank, n
             "views_per_rank": 256 // world, "batches": batches, "scaling": "strong"}
 
 
+def seq1080p_record(args, api, torch, dist, world, rank, local_rank, noise, frames=16, repeats=8):
+    """BASELINE config 2 beside the headline ("ms/frame at 1080p" is the second half of BASELINE.json's metric): the reference's
+    frame loop (main.cpp:172-194) at 1920x1080 -- a 16-frame camera pan, RotateAboutUp(0.25 deg) and time += 1/60 per frame, frame
+    ids 1..15, 0 -- through mtFrame: reprojection + 1-of-16 Cloud dispatch + god rays + tone map.  Whole frames, device-timed with
+    events around each 16-frame pass of the pan (no per-pass events, so the passes mtFrameEx runs side by side do); the first pass
+    warms up, the mean of the next `repeats` passes is reported.  Every rank runs the same sequence (replicas); max over ranks."""
+    from meteoros_b200 import scene as _scene
+    w, h = 1920, 1080
+    cam, sc, sky = _scene.Camera(w, h), _scene.Scene(), _scene.Sky()
+    r = api.CloudRenderer(w, h, device=local_rank, storage=args.storage)
+    r.upload_noise(noise)
+    r.set_sun_and_sky(sky.ubo())
+    old = cam.ubo()
+    ms = []
+    for rep in range(repeats + 1):
+        ubos = []
+        for _ in range(frames):
+            cam.rotate_about_up(0.25)
+            sc.update_time(1 / 60)
+            ubos.append((cam.ubo(), old, sc.ubo()))
+            old = cam.ubo()
+        r.event_record(4)
+        for c, o, t in ubos:
+            r.set_camera(c); r.set_camera_old(o); r.set_time(t)
+            r.frame(True, False)
+        r.event_record(5)
+        r.synchronize()
+        if rep:
+            ms.append(r.event_elapsed_ms(4, 5) / frames)
+    launches = r.launch_count()
+    r.close()
+    t_ms = float(statistics.mean(ms))
+    if dist is not None:
+        t = torch.tensor([t_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_ms = float(t[0])
+    if rank != 0:
+        return None
+    return {"workload": "1920x1080 16-frame camera pan through mtFrame: reprojection + 1-of-16 Cloud dispatch + god rays + tone map (BASELINE config 2)",
+            "ms_per_frame": round(t_ms, 4), "frames_per_s": round(1e3 / t_ms, 1), "frames_timed": frames * repeats,
+            "mrays_per_s": round((w // 4) * (h // 4) / (t_ms * 1e-3) / 1e6, 1),
+            "launches_per_frame": round(launches / (frames * (repeats + 1)), 2),
+            "timing": "CUDA events around each 16-frame pass of the pan, warm (L2 not flushed: consecutive frames of one sequence); per-pass times and their rooflines: --workload seq1080p"}
+
+
 def sharded_8k_record(args, api, sharding, torch, dist, world, rank, local_rank, noise, steps, storage=None):
     """BASELINE config 4 beside the N>1 views line: ONE 7680x4320 full-quality frame cut into cyclic row tiles over the
     ranks and gathered on GPU 0 over NVLink, timed like the headline (events on each rank's stream, L2 flushed, max over
@@ -416,6 +464,7 @@ def main():
     ap.add_argument("--gather-mask", action="store_true", help="frame8k: also send the god-ray mask tiles to GPU 0 (needed only if god rays run)")
     ap.add_argument("--sweep", action="store_true", help="N>1: rank r renders view r of the sun/coverage sweep")
     ap.add_argument("--no-views256", action="store_true", help="default workload: skip the views256 sub-record (config 5)")
+    ap.add_argument("--no-seq1080p", action="store_true", help="default workload: skip the seq1080p sub-record (config 2)")
     ap.add_argument("--no-sharded-8k", action="store_true", help="N>1 default workload: skip the sharded_8k sub-record (config 4)")
     ap.add_argument("--storage", type=int, default=0, help="image storage: 0 = RGBA32F (default), 1 = binary16-rounded values in RGBA32F")
     args = ap.parse_args()
@@ -697,6 +746,11 @@ def main():
         rec = views256_record(args, api, sharding, torch, dist if world > 1 else None, world, rank, local_rank, noise)
         if rank == 0:
             line["views256"] = rec
+
+    if args.workload == "cloud4k" and not args.no_seq1080p:
+        rec = seq1080p_record(args, api, torch, dist if world > 1 else None, world, rank, local_rank, noise)
+        if rank == 0:
+            line["seq1080p"] = rec
 
     if world > 1 and args.workload == "cloud4k" and not args.no_sharded_8k:
         rec = sharded_8k_record(args, api, sharding, torch, dist, world, rank, local_rank, noise, steps=max(args.steps, 10))

@@ -892,9 +892,11 @@ try {
         c->stream = c->sideStream;
         st = cloud_dispatch(c, 0, nullptr, false);
         c->stream = mainStream;
+        // joined whether or not the dispatch went through: whatever it did enqueue on the side stream precedes the caller's next call
+        const cudaError_t je = cudaEventRecord(c->sideJoinEv, c->sideStream);
+        const cudaError_t jw = je == cudaSuccess ? cudaStreamWaitEvent(c->stream, c->sideJoinEv, 0) : je;  // the later passes need both
         if (st != MT_OK) return st;
-        MT_CUDA(c, cudaEventRecord(c->sideJoinEv, c->sideStream));
-        MT_CUDA(c, cudaStreamWaitEvent(c->stream, c->sideJoinEv, 0));      // the later passes need both
+        MT_CUDA(c, jw);
     } else {
         if ((st = reproject_dispatch(c, false)) != MT_OK) return st;
         if ((st = cloud_dispatch(c, 0, nullptr, false)) != MT_OK) return st;
