@@ -17,6 +17,7 @@ from .scene import CAMERA_DTYPE, SUNSKY_DTYPE, TIME_DTYPE, TUNING_DTYPE
 MT_OK = 0
 STORAGE_F32, STORAGE_F16_EMULATE, STORAGE_F16 = 0, 1, 2
 FLAG_COUNTERS, FLAG_PASS_TIMING, FLAG_SEQUENTIAL_MARCH, FLAG_TOP_DOWN, FLAG_NO_CONE_RF, FLAG_SPLIT_MARCH, FLAG_NO_FUSED_TONEMAP = 1, 2, 4, 8, 16, 32, 64
+FLAG_HW_CONE_FILTER = 128  # opt-in, outside the parity bar: light-cone samples of full-quality dispatches through the texture unit (meteoros_b200.h)
 TEX_LOW_FREQ, TEX_HIGH_FREQ, TEX_CURL, TEX_WEATHER = 0, 1, 2, 3
 IMAGE_CLOUD_CUR, IMAGE_CLOUD_PREV, IMAGE_GODRAY_MASK, IMAGE_LDR, IMAGE_LDR_PREV = 0, 1, 2, 3, 4
 PASS_REPROJECT, PASS_CLOUD, PASS_GODRAYS, PASS_TONEMAP, PASS_TXAA = 0, 1, 2, 3, 4

@@ -573,6 +573,56 @@ MT_DEVICE StepSample cloud_step_light(const CloudParams& P, const MarchConst& M,
     const float coverage = P.tun.coverage, h = B.h, baseDensity = B.baseDensity;
     if (COUNT) cnt.incloud++;
     float dl = 0.0f;
+#if !defined(MT_HOSTSIM)
+    if (STD == 4) {
+        // MT_FLAG_HW_CONE_FILTER (opt-in; mt_tex.cuh): the texture unit fetches AND filters the six light-cone samples -- one TEX
+        // instruction in place of cell index, bitmap flag, 256-bit brick load, sixteen field extractions and seven packed lerps.  The
+        // samples feed radiance only, and this mode makes no exactness claim for it: the position is scaled by the rounded reciprocal
+        // of the layer thickness (one multiplication instead of the three-instruction exact division), the term is the guard-less
+        // form of cone_term_rf.  Erosion (S.inc, which feeds the accumulated density) stays on the exact path above it.
+        const float edge = erosion_edge<MT_STD_MAGIC(STD)>(std_curl<STD>(P.curl), std_high<STD>(P.high), skew, h);
+        S.inc = erode(baseDensity * 1.4f, edge) * 0.5f;
+        const float edgeRcp = nice_rcp(1.0f - edge);
+        const cudaTextureObject_t tex = (cudaTextureObject_t)P.low.hwtex;
+        const float invT = 1.0f / MT_THICKNESS;
+#ifndef MT_HW_BATCH
+#define MT_HW_BATCH 3  /* fetches requested before the first one is consumed (registers: 4 per fetch in flight) */
+#endif
+#pragma unroll
+        for (int i0 = 0; i0 < 6; i0 += MT_HW_BATCH) {
+            float4 n[MT_HW_BATCH];
+#pragma unroll
+            for (int j = 0; j < MT_HW_BATCH; ++j) {
+                const int i = i0 + j;
+                P2 off;
+                float offz;
+                if (CO.xyz) {
+                    const float4 o = *reinterpret_cast<const float4*>(CO.xyz + i * CO.stride);
+                    off = pk2(o.x, o.y);
+                    offz = o.z;
+                } else cone_offset(M, R.stepSize, i, off, offz);
+                const P2 lxy = sub2(pk2(pos.x + lo2(off), pos.y + hi2(off)), pk2(relOrigin.x, relOrigin.y));
+                const float lz = (pos.z + offz) - relOrigin.z;
+                n[j] = tex3D<float4>(tex, lo2(lxy) * invT, hi2(lxy) * invT, lz * invT);
+            }
+#pragma unroll
+            for (int j = 0; j < MT_HW_BATCH; ++j) {
+                const float fbm = sat1(fmaf(n[j].y, 0.625f, fmaf(n[j].z, 0.25f, n[j].w * 0.125f)));
+                const float omin = fbm - 0.9f;
+                const float d = 1.0f - omin, q = n[j].x - omin;
+                if (q - coverage * d > 0.0f) {
+                    float rd;
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rd) : "f"(d));
+                    const float dens = (fminf(q * rd, 1.0f) - coverage) * M.covScale;
+                    if (dens > 0.0f) dl += fmaf(1.5f, dens, -edge) * edgeRcp;
+                }
+            }
+        }
+        const bool parkedH = MT_PARK_BG && CO.xyz;
+        S.energy = light_energy(h, dl, baseDensity, parkedH ? CO.xyz[3 * CO.stride].w : R.phase, parkedH ? CO.xyz[4 * CO.stride].w : R.cosAngle);
+        return S;
+    }
+#endif
 #if !defined(MT_HOSTSIM) && MT_CONE_PIPE
     if (STD == 2 && MT_CONE_RF && !WEATHER) {  // STD kernels are only launched with the (r, F) bricks present (mt_std_dims)
         const Tex3D low = std_low<STD>(P.low);
@@ -629,7 +679,7 @@ MT_DEVICE StepSample cloud_step_light(const CloudParams& P, const MarchConst& M,
             LinAxis X, Y, Z;
             unsigned cell;
             float cur;
-            if (STD && MT_CONE_RF && !WEATHER && !MT_HW_FILTER) {  // the plain (r, F) loop: the same per-sample term as the pipelined one
+            if (STD && MT_CONE_RF && !WEATHER) {  // the plain (r, F) loop: the same per-sample term as the pipelined one
                 cone_axes<STD>(P, M, CO, pos, relOrigin, R.stepSize, i, sxy, sz, X, Y, Z, cell);
                 const Tex3D low = std_low<STD>(P.low);
 #if !defined(MT_HOSTSIM) && MT_CONE_PIPE && MT_RF_BRICKS
@@ -655,20 +705,6 @@ MT_DEVICE StepSample cloud_step_light(const CloudParams& P, const MarchConst& M,
                 }
                 continue;
             }
-#if MT_HW_FILTER && !defined(MT_HOSTSIM)
-            if (STD && !WEATHER) {  // A/B: the texture unit filters the cone sample (profiles/r2_ab.md); same empty-cell test
-                cone_axes<STD>(P, M, CO, pos, relOrigin, R.stepSize, i, sxy, sz, X, Y, Z, cell);
-                const Tex3D low = std_low<STD>(P.low);
-                cur = 0.0f;
-                if (!low.occ || occ_cell_may_be_cloud(low, cell)) {
-                    const float4 n = tex3D<float4>((cudaTextureObject_t)P.low.hwtex, lo2(sxy), hi2(sxy), sz);
-                    const float fbm = sat1((n.y * 0.625f + n.z * 0.25f) + n.w * 0.125f);
-                    const float omin = fbm - 0.9f;
-                    const float base = sat1(div_nice(n.x - omin, 1.0f - omin));
-                    if (base > coverage) cur = sat1(div_nice_r(base - coverage, M.covDen, R.covRcp)) * coverage;
-                }
-            } else
-#endif
             if (STD && MT_CONE_RF && !WEATHER) {
                 cone_axes<STD>(P, M, CO, pos, relOrigin, R.stepSize, i, sxy, sz, X, Y, Z, cell);
                 const Tex3D low = std_low<STD>(P.low);

@@ -130,7 +130,7 @@ cudaError_t mt_launch_occupancy(const Tex3D& low, uint32_t* occ, float coverage,
 }
 
 
-template <bool FULL, bool COUNT, bool DEBUG, bool WEATHER, bool STD>
+template <bool FULL, bool COUNT, bool DEBUG, bool WEATHER, bool STD, bool HWF = false>  // HWF: MT_FLAG_HW_CONE_FILTER (cloud_core.cuh, STD == 4)
 #ifndef MT_CLOUD_MINBLOCKS
 #define MT_CLOUD_MINBLOCKS 8  /* 64 registers/thread: 8 CTAs = 32 warps per SM (profiles/r1_cloud_ab.md) */
 #endif
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(128, MT_CLOUD_MINBLOCKS) cloud_raymarch_kernel
     if (valid) {
         const size_t idx = (size_t)py * (size_t)P.W + (size_t)px;
         if constexpr (!QUEUED)
-            cloud_ray<COUNT, DEBUG, WEATHER, (STD ? (MT_CONE_PIPE ? 2 : 1) : 0)>(P, M, J, px, py, pixelID, hdr, mask, cnt, DEBUG ? (P.debug + idx) : nullptr, cxyz, 128);
+            cloud_ray<COUNT, DEBUG, WEATHER, (HWF ? 4 : STD ? (MT_CONE_PIPE ? 2 : 1) : 0)>(P, M, J, px, py, pixelID, hdr, mask, cnt, DEBUG ? (P.debug + idx) : nullptr, cxyz, 128);
         const float4 h4 = make_float4(hdr.x, hdr.y, hdr.z, hdr.w);
         if (bulk) {
             // The marching warp must not wait on a remote write: its 32 pixels go to shared memory, and lanes 0 and 16 each
@@ -729,6 +729,7 @@ cudaError_t mt_launch_cloud(const CloudParams& P, cudaStream_t stream)
         if (P.full) {
             if (debug) cloud_raymarch_kernel<true, true, true, false, true><<<grid, block, 0, stream>>>(P);
             else if (count) cloud_raymarch_kernel<true, true, false, false, true><<<grid, block, 0, stream>>>(P);
+            else if (P.hwCone && P.low.hwtex) cloud_raymarch_kernel<true, false, false, false, true, true><<<grid, block, 0, stream>>>(P);  // opt-in
             else cloud_raymarch_kernel<true, false, false, false, true><<<grid, block, 0, stream>>>(P);
         } else {
             if (debug) cloud_raymarch_kernel<false, true, true, false, true><<<grid, block, 0, stream>>>(P);

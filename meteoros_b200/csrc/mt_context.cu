@@ -61,10 +61,8 @@ struct MtContext {
     uint32_t* tex[4] = { nullptr, nullptr, nullptr, nullptr };
     void* quads[4] = { nullptr, nullptr, nullptr, nullptr };  // per-cell 2x2 texel quads (mt_tex.cuh), built at upload
     void* rfQuads = nullptr;      // low-frequency volume only: the quads in (r, F) form for the light-cone samples
-#if MT_HW_FILTER
-    cudaArray_t hwArray = nullptr;          // A/B build only (mt_tex.cuh): the low-frequency volume as a CUDA array + texture object
+    cudaArray_t hwArray = nullptr;          // MT_FLAG_HW_CONE_FILTER (mt_tex.cuh): the low-frequency volume as a CUDA array + texture object
     cudaTextureObject_t hwTex = 0;
-#endif
     int texw[4] = { 0, 0, 0, 0 }, texh[4] = { 0, 0, 0, 0 }, texd[4] = { 0, 0, 0, 0 };
     uint32_t* occ = nullptr;      // empty-cell bitmap of the low-frequency volume (mt_tex.cuh)
     float occCoverage = -1.0f;    // coverage the bitmap was built for; < 0 = stale
@@ -342,10 +340,8 @@ void mtDestroy(MtContext* c)
     free_images(c);
     for (int i = 0; i < 4; ++i) { cudaFree(c->tex[i]); cudaFree(c->quads[i]); }
     cudaFree(c->rfQuads);
-#if MT_HW_FILTER
     if (c->hwTex) cudaDestroyTextureObject(c->hwTex);
     if (c->hwArray) cudaFreeArray(c->hwArray);
-#endif
     cudaFree(c->occ);
     cudaFree(c->counters);
     cudaFree(c->flushBuf);
@@ -465,29 +461,29 @@ static MtStatus upload(MtContext* c, int slot, uint32_t w, uint32_t h, uint32_t 
             c->launches += 1;
         }
     }
-#if MT_HW_FILTER
     if (slot == MT_TEX_LOW_FREQ) {
         if (c->hwTex) { cudaDestroyTextureObject(c->hwTex); c->hwTex = 0; }
         if (c->hwArray) { cudaFreeArray(c->hwArray); c->hwArray = nullptr; }
-        cudaChannelFormatDesc fd = cudaCreateChannelDesc<uchar4>();
-        MT_CUDA(c, cudaMalloc3DArray(&c->hwArray, &fd, make_cudaExtent(w, h, d)));
-        cudaMemcpy3DParms cp = {};
-        cp.srcPtr = make_cudaPitchedPtr((void*)rgba8, (size_t)w * 4, w, h);
-        cp.dstArray = c->hwArray;
-        cp.extent = make_cudaExtent(w, h, d);
-        cp.kind = cudaMemcpyHostToDevice;
-        MT_CUDA(c, cudaMemcpy3D(&cp));
-        cudaResourceDesc rd = {};
-        rd.resType = cudaResourceTypeArray;
-        rd.res.array.array = c->hwArray;
-        cudaTextureDesc td = {};
-        td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeWrap;  // REPEAT (Texture3D.cpp:92-134)
-        td.filterMode = cudaFilterModeLinear;
-        td.readMode = cudaReadModeNormalizedFloat;
-        td.normalizedCoords = 1;
-        MT_CUDA(c, cudaCreateTextureObject(&c->hwTex, &rd, &td, nullptr));
+        if (c->flags & MT_FLAG_HW_CONE_FILTER) {
+            cudaChannelFormatDesc fd = cudaCreateChannelDesc<uchar4>();
+            MT_CUDA(c, cudaMalloc3DArray(&c->hwArray, &fd, make_cudaExtent(w, h, d)));
+            cudaMemcpy3DParms cp = {};
+            cp.srcPtr = make_cudaPitchedPtr((void*)rgba8, (size_t)w * 4, w, h);
+            cp.dstArray = c->hwArray;
+            cp.extent = make_cudaExtent(w, h, d);
+            cp.kind = cudaMemcpyHostToDevice;
+            MT_CUDA(c, cudaMemcpy3D(&cp));
+            cudaResourceDesc rd = {};
+            rd.resType = cudaResourceTypeArray;
+            rd.res.array.array = c->hwArray;
+            cudaTextureDesc td = {};
+            td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeWrap;  // REPEAT (Texture3D.cpp:92-134)
+            td.filterMode = cudaFilterModeLinear;
+            td.readMode = cudaReadModeNormalizedFloat;
+            td.normalizedCoords = 1;
+            MT_CUDA(c, cudaCreateTextureObject(&c->hwTex, &rd, &td, nullptr));
+        }
     }
-#endif
     MT_CUDA(c, cudaStreamSynchronize(c->stream));  // the caller may free its buffer on return
     c->texw[slot] = (int)w; c->texh[slot] = (int)h; c->texd[slot] = (int)d;
     if (slot == MT_TEX_LOW_FREQ) {
@@ -548,9 +544,8 @@ static MtStatus cloud_dispatch(MtContext* c, int full, const RowTiles* tiles, bo
     mt_host_sky_const(c->cam, c->tun, P.sky);
     P.low.quads = (const Quad*)c->quads[MT_TEX_LOW_FREQ];
     P.low.rfquads = (const Quad*)c->rfQuads;
-#if MT_HW_FILTER
-    P.low.hwtex = (unsigned long long)c->hwTex;
-#endif
+    P.low.hwtex = (unsigned long long)c->hwTex;  // 0 unless MT_FLAG_HW_CONE_FILTER
+    P.hwCone = (c->flags & MT_FLAG_HW_CONE_FILTER) && c->hwTex ? 1 : 0;
     P.high.quads = (const Quad*)c->quads[MT_TEX_HIGH_FREQ];
     P.curl.quads = (const Quad*)c->quads[MT_TEX_CURL];
     P.low.texels = c->tex[MT_TEX_LOW_FREQ];

@@ -121,6 +121,7 @@ struct CloudParams {
     int full;    // 0: one id (tm.frameCountMod16) -- 1: all sixteen
     int storage;     // MtStorage of the HDR / mask images (mt_pixel.cuh)
     int bulkStore;   // full-quality kernel: HDR pixels leave through shared memory + cp.async.bulk (mtSetCloudStoreMode)
+    int hwCone;      // MT_FLAG_HW_CONE_FILTER: full-quality production launches take their light-cone samples through low.hwtex
     RowTiles rows;
     unsigned long long* counters;  // 6 x u64 or null
     MtRayDebug* debug;             // W*H records or null

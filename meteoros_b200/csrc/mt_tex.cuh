@@ -33,11 +33,10 @@
 #ifndef MT_RF_BRICKS
 #define MT_RF_BRICKS 1
 #endif
-// MT_HW_FILTER=1: A/B build (tools/ab_bench.sh, profiles/r2_ab.md) in which the light-cone samples go through the texture unit's
-// own trilinear filter (tex3D, 9-bit weights) instead of the exact fp32 filter.  Never the default: it cannot meet the parity bar.
-#ifndef MT_HW_FILTER
-#define MT_HW_FILTER 0
-#endif
+// MT_FLAG_HW_CONE_FILTER (opt-in, per context): the light-cone samples of the full-quality kernel go through the texture unit's own
+// trilinear filter (tex3D over a CUDA array of the low-frequency volume; 8-bit filter weights) instead of the exact fp32 filter.
+// Never the default: radiance moves by up to ~1.6e-3 relative on a few pixels of a 4K frame (profiles/r2_ab.md, r2c_ab.md), beyond
+// the 1e-3 bar; every decision-carrying value (march sample, erosion, accumulated density, mask, alpha) stays on the exact path.
 #if defined(MT_HOSTSIM)
 struct Quad { uint32_t x, y, z, w; };
 #define MT_LDG_QUAD(p) (*(p))
@@ -52,9 +51,7 @@ struct Tex3D {
                              // applied), so that the eight corners of a trilinear fetch are TWO aligned 16-byte loads
                              // instead of eight scattered 4-byte loads (4x the memory: 32 MB for 128^3, L2 resident)
     const Quad* rfquads;     // optional (low-frequency volume): the same quads of (r, F) words, see rf_pack below
-#if MT_HW_FILTER
-    unsigned long long hwtex; // A/B build only: cudaTextureObject_t over the same volume (LINEAR, WRAP, normalized float reads)
-#endif
+    unsigned long long hwtex; // MT_FLAG_HW_CONE_FILTER: cudaTextureObject_t over the same volume (LINEAR, WRAP, normalized float reads), else 0
     int w, h, d;             // powers of two
     const uint32_t* occ;     // optional: 1 bit per filter cell (x fastest, 32 cells per word), 0 = the cell's eight
                              // corner texels all have zero cloud density at the current coverage (see occ_* below)

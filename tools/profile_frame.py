@@ -19,11 +19,12 @@ def main():
     ap.add_argument("--height", type=int, default=2160)
     ap.add_argument("--passes", default="cloud", help="comma list of cloud,cloud16,reproject,godrays,tonemap,frame")
     ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--flags", type=int, default=0, help="MtConfig.flags of the context (e.g. 128 = MT_FLAG_HW_CONE_FILTER)")
     a = ap.parse_args()
     w, h = a.width, a.height
     cam, sc, sky = scene.Camera(w, h), scene.Scene(), scene.Sky()
     sc.update_time(1 / 60)
-    with api.CloudRenderer(w, h) as r:
+    with api.CloudRenderer(w, h, flags=a.flags) as r:
         r.upload_noise(textures.load_noise())
         r.set_camera(cam.ubo()); r.set_camera_old(cam.ubo()); r.set_time(sc.ubo()); r.set_sun_and_sky(sky.ubo())
         for _ in range(a.reps):
