@@ -118,11 +118,12 @@ typedef struct MtConfig {
                                      * the low-frequency volume (saves its 4 bytes/cell copy; bit-identical decisions either way,
                                      * radiance equal to rounding).  Must be set before the low-frequency texture is uploaded. */
 
-#define MT_FLAG_HW_CONE_FILTER 128u /* OPT-IN, outside the parity bar: the six light-cone samples of a full-quality dispatch
-                                     * (mtDispatchCloudFull / mtDispatchCloudTiles) are filtered by the texture unit (a CUDA 3D
+#define MT_FLAG_HW_CONE_FILTER 128u /* OPT-IN, outside the parity bar: the six light-cone samples of an in-cloud step (production
+                                     * kernels of mtDispatchCloud / mtDispatchCloudFull / mtDispatchCloudTiles / mtFrame; not the counting,
+                                     * debug, sequential, split or weather forms) are filtered by the texture unit (a CUDA 3D
                                      * texture object over the low-frequency volume: LINEAR, REPEAT, as Texture3D.cpp:92-134 sets the
                                      * reference's sampler up) instead of the exact fp32 filter -- what a GPU running the reference does,
-                                     * with the hardware's 8-bit filter weights.  ~25 % faster; the god-ray mask and alpha are
+                                     * with the hardware's 8-bit filter weights.  ~29 % faster at 4K; the god-ray mask and alpha are
                                      * bit-identical to the default path (the cone samples never feed the accumulated density), the
                                      * HDR radiance differs by up to ~2e-3 relative on a few pixels per 4K frame (the default path:
                                      * ~1e-6).  Must be set before the low-frequency texture is uploaded.                            */

@@ -162,7 +162,7 @@ MT_DEVICE float low_freq_density(const CloudParams& P, const MarchConst& M, floa
     // whole fetch + filter (SIMT: the branch is free when nobody takes it).
 #if MT_TEX_QUADS && !MT_TEX_BRICKS && !defined(MT_HOSTSIM)
     Rgba n;
-    if ((STD == 3 || (STD == 2 && MT_SPEC_QUADS_FULL)) && !WEATHER && low.occ) {
+    if ((STD == 3 || STD == 5 || (STD == 2 && MT_SPEC_QUADS_FULL)) && !WEATHER && low.occ) {
         // latency-bound callers (the step-parallel 1-of-16 kernel): the cell's quads are requested TOGETHER with its bitmap word
         // instead of after it -- one memory round trip per march sample instead of two, at the price of 32 unused bytes for an
         // empty cell
@@ -574,7 +574,7 @@ MT_DEVICE StepSample cloud_step_light(const CloudParams& P, const MarchConst& M,
     if (COUNT) cnt.incloud++;
     float dl = 0.0f;
 #if !defined(MT_HOSTSIM)
-    if (STD == 4) {
+    if (STD == 4 || STD == 5) {  // 4: the one-thread-per-ray kernel, 5: the step-parallel 1-of-16 kernel (whose march sample is STD == 3's)
         // MT_FLAG_HW_CONE_FILTER (opt-in; mt_tex.cuh): the texture unit fetches AND filters the six light-cone samples -- one TEX
         // instruction in place of cell index, bitmap flag, 256-bit brick load, sixteen field extractions and seven packed lerps.  The
         // samples feed radiance only, and this mode makes no exactness claim for it: the position is scaled by the rounded reciprocal

@@ -522,7 +522,7 @@ static bool mt_std_dims(const CloudParams& P)
 #ifndef MT_S16_MINBLOCKS
 #define MT_S16_MINBLOCKS 6
 #endif
-template <bool WEATHER, bool STD>
+template <bool WEATHER, bool STD, bool HWF = false>  // HWF: MT_FLAG_HW_CONE_FILTER (cloud_core.cuh, STD == 5)
 __global__ void __launch_bounds__(32 * MT_S16_WARPS, MT_S16_MINBLOCKS) cloud_sixteenth_kernel(const __grid_constant__ CloudParams P)
 {
     __shared__ RaySetup rays[32];
@@ -587,7 +587,7 @@ __global__ void __launch_bounds__(32 * MT_S16_WARPS, MT_S16_MINBLOCKS) cloud_six
             if (k < mine) {
                 const float t = tk[k][lane];
                 const int jidx = (pixelID + mt_f2i(t)) & 15;
-                const StepSample S = cloud_step_sample<false, WEATHER, (STD ? MT_S16_CONE : 0)>(P, M, J, R, jidx, t, none, noCache);
+                const StepSample S = cloud_step_sample<false, WEATHER, (HWF ? 5 : STD ? MT_S16_CONE : 0)>(P, M, J, R, jidx, t, none, noCache);
                 smp[k][lane] = make_float2(S.inc, S.energy);
             }
         }
@@ -614,6 +614,7 @@ cudaError_t mt_launch_cloud_sixteenth_fused(const CloudParams& P, cudaStream_t s
 {
     const unsigned tiles = (unsigned)((P.tx / MT_S16_TW) * (P.ty / MT_S16_TH));  // tx, ty are multiples of 32
     if (P.tun.use_weather) cloud_sixteenth_kernel<true, false><<<tiles, 32 * MT_S16_WARPS, 0, stream>>>(P);
+    else if (mt_std_dims(P) && P.hwCone && P.low.hwtex) cloud_sixteenth_kernel<false, true, true><<<tiles, 32 * MT_S16_WARPS, 0, stream>>>(P);  // opt-in
     else if (mt_std_dims(P)) cloud_sixteenth_kernel<false, true><<<tiles, 32 * MT_S16_WARPS, 0, stream>>>(P);
     else cloud_sixteenth_kernel<false, false><<<tiles, 32 * MT_S16_WARPS, 0, stream>>>(P);
     return cudaGetLastError();
