@@ -78,7 +78,7 @@ for storage in (api.STORAGE_F16, api.STORAGE_F16_EMULATE):
             r.join_copies(); r.synchronize()
             r.set_cloud_forward(None)
         print("grey mean", float(r.read_godray_grey().mean()), "storage", storage)
-for flags in (api.FLAG_SPLIT_MARCH, api.FLAG_NO_CONE_RF, api.FLAG_TOP_DOWN | api.FLAG_NO_FUSED_TONEMAP):
+for flags in (api.FLAG_SPLIT_MARCH, api.FLAG_NO_CONE_RF, api.FLAG_TOP_DOWN | api.FLAG_NO_FUSED_TONEMAP, api.FLAG_HW_CONE_FILTER):
     with api.CloudRenderer(w, h, flags=flags) as r:
         r.upload_noise(textures.load_noise())
         r.set_sun_and_sky(sky.ubo())
