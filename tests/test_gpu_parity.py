@@ -888,7 +888,8 @@ def test_full_size_properties_4k(api, noise):
 
 
 def test_committed_golden_frame(api, noise):  # the golden was written by the reference's own cloud shader (make_goldens.py)
-    """The CUDA path against the committed golden (tests/golden/cloud_64x36.npz, oracle-generated)."""
+    """The CUDA path against the committed golden (tests/golden/cloud_64x36.npz: written by the reference's own cloud shader compiled
+    from its text, tests/golden/make_goldens.py, which refuses to write where the oracle disagrees with it)."""
     import pathlib
 
     g = np.load(pathlib.Path(__file__).parent / "golden" / "cloud_64x36.npz")
