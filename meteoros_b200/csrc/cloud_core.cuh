@@ -655,7 +655,14 @@ MT_DEVICE StepSample cloud_step_light(const CloudParams& P, const MarchConst& M,
             if (cur.t[0] & 1u) {  // the cell may hold cloud (flag written with the empty-cell bitmap); else the density is exactly +0
                 const uint32_t t000 = cur.t[0], t001 = cur.t[1], t010 = cur.t[2], t011 = cur.t[3], t100 = cur.t[4], t101 = cur.t[5],
                                t110 = cur.t[6], t111 = cur.t[7];
+#ifdef MT_EMU_WBITS  /* probe build (tools/probes/emu_weight_bits.py, profiles/r2c_ab.md): filter fractions rounded to MT_EMU_WBITS bits, as a texture unit would */
+                LinAxis Xq = X, Yq = Y, Zq = Z;
+                const float qs = (float)(1 << MT_EMU_WBITS);
+                Xq.w1 = rintf(X.w1 * qs) / qs; Yq.w1 = rintf(Y.w1 * qs) / qs; Zq.w1 = rintf(Z.w1 * qs) / qs;
+                const P2 rf = rf_filter(t000, t001, t010, t011, t100, t101, t110, t111, Xq, Yq, Zq);
+#else
                 const P2 rf = rf_filter(t000, t001, t010, t011, t100, t101, t110, t111, X, Y, Z);
+#endif
                 bool hit;
                 const float term = cone_term_rf<STD>(P, M, R.covRcp, coverage, rf, X, Y, Z, cell, edge, edgeRcp, hit);
                 if (COUNT && hit) cnt.cone++;

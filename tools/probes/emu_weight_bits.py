@@ -1,3 +1,9 @@
+#!/usr/bin/env python
+"""How many bits of filter position would the light-cone samples need?  Renders three views of the config-5 sweep at 1920x1080 with the
+exact path, with the texture-unit mode (MT_FLAG_HW_CONE_FILTER) and with probe builds of the exact kernel whose filter fractions are
+rounded to 8 / 9 / 10 bits, and compares each with the exact frame (and the 8-bit emulation with the texture unit's frame).
+  for b in 8 9 10; do make -C meteoros_b200/csrc OUT=../../ab_variants/lib_q$b.so EXTRA=-DMT_EMU_WBITS=$b; done
+  python tools/probes/emu_weight_bits.py          (on the GPU box; record: profiles/r2c_emu_weight_bits.txt)"""
 import os, sys, subprocess, json
 import numpy as np
 sys.path.insert(0, ".")
