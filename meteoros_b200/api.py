@@ -105,6 +105,12 @@ class CloudRenderer:
         a = _as_bytes(ubo, SUNSKY_DTYPE)
         self._check(self._lib.mtSetSunAndSky(self._h, a.ctypes.data), "mtSetSunAndSky")
 
+    def resize(self, width: int, height: int):
+        """mtResize: new images of the new size (transactional: on failure the context keeps the old ones); every image starts cleared,
+        device pointers and exported handles of the old images are invalid afterwards."""
+        self._check(self._lib.mtResize(self._h, int(width), int(height)), "mtResize")
+        self.width, self.height = int(width), int(height)
+
     def set_key_press_query(self, key_debug: int):
         self._check(self._lib.mtSetKeyPressQuery(self._h, int(key_debug)), "mtSetKeyPressQuery")
 

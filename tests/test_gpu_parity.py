@@ -837,8 +837,7 @@ def test_error_paths(api, noise):
 def test_resize(api, oracle_mod, noise):
     cam, tm, _, tun = default_scene(96, 54)
     with make_renderer(api, noise, 64, 36) as r:
-        r._check(r._lib.mtResize(r._h, 96, 54), "mtResize")
-        r.width, r.height = 96, 54
+        r.resize(96, 54)
         r.set_camera(cam); r.set_time(tm)
         r.dispatch_cloud_full()
         hdr = r.read_image(api.IMAGE_CLOUD_CUR)
