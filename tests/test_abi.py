@@ -89,3 +89,19 @@ def test_header_is_plain_c_and_the_example_links(tmp_path):
         run = subprocess.run([str(exe), str(ref), "2", "64", "36"], capture_output=True, text=True)
         assert "assets decoded" in run.stdout            # the C++ decoders ran on the reference's files
         assert run.returncode == 3 and "no CPU path" in run.stderr
+
+
+def test_python_binding_constants_match_the_header():
+    """The MT_FLAG_* values the ctypes binding passes are the header's (a flag added on one side only would silently select nothing)."""
+    import re
+
+    from meteoros_b200 import api
+
+    text = (ROOT / "include" / "meteoros_b200.h").read_text()
+    flags = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+MT_FLAG_(\w+)\s+(\d+)u", text)}
+    assert flags, "no MT_FLAG_* definitions found in the header"
+    for name, value in flags.items():
+        if name == "PASS_TIMING_INTERNAL":
+            continue
+        assert getattr(api, "FLAG_" + name) == value, f"MT_FLAG_{name}"
+    assert len(set(flags.values())) == len(flags), "two flags share a bit"
