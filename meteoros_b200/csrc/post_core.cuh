@@ -152,8 +152,9 @@ MT_DEVICE float mask_texel_decode(F4 t)
 // then takes the dot product with 1/bitEnc; both steps are linear, so the kernel decodes each texel once
 // (mask_decode_kernel) and filters the decoded scalar: 100 taps per pixel.  The god-ray term is radiance only -- no decision
 // depends on it -- and at most 2.5 % of the pixel, so it is held to "equal to rounding" (tests: <= 2e-5 of the term), not to
-// bit-exactness; what is kept exact is the tap POSITION sequence (uv -= delta, 100 roundings, then * dim - 0.5 in two
-// roundings), because a tap position off by one ulp moves a tap by 1e-4 texel, which a high-contrast mask turns into 1e-4.
+// bit-exactness; what is kept exact is the tap POSITION sequence in uv (uv -= delta, 100 roundings), whose drift would
+// otherwise add up along the march.  The texel coordinate of a tap, uv * dim - 0.5, is formed in one rounding on the device
+// (MT_GODRAY_FMA_POS: within half an ulp, 3e-5 texel at 1080p, of the shader's two-rounding form; the filter is continuous).
 // `dec` is the (W+2) x (H+2) decoded image whose one-texel ring holds the border value, so the taps need no bounds tests;
 // each element is the PAIR (d(x, y), d(x+1, y)), so a tap is two 8-byte loads.  Per tap (device): the floor of both
 // coordinates comes from ONE packed add in round-down mode against 1.5 * 2^23 (the integer lands in the low mantissa bits,
@@ -161,6 +162,9 @@ MT_DEVICE float mask_texel_decode(F4 t)
 // a + ay (c - a) on both columns at once, then in x: ~19 instructions per tap instead of 31 (profiles/r2_passes_1080p.md).
 #ifndef MT_GODRAY_WIDE
 #define MT_GODRAY_WIDE 0
+#endif
+#ifndef MT_GODRAY_FMA_POS
+#define MT_GODRAY_FMA_POS 1  /* 1080p: 166.4 us with 0, 154.1 us with 1 (profiles/r2c_ab.md) */
 #endif
 #ifndef MT_GODRAY_SCALAR
 #define MT_GODRAY_SCALAR 0
@@ -187,8 +191,16 @@ MT_DEVICE float mask_decode(const GodRayParams& P, P2 st)
 {
     const float2* dec = P.decoded;
     const int W = P.W, H = P.H;
+#if MT_GODRAY_FMA_POS && !defined(MT_HOSTSIM)
+    // u * dim - 0.5 in ONE rounding (FFMA2) instead of two (FMUL2 + two scalar adds): the position moves by at most half an ulp of
+    // u * dim (3e-5 texel at 1080p) against the shader's two-rounding form, which the bilinear filter -- continuous across cell
+    // boundaries -- turns into < 4e-5 of a tap on a full-contrast edge; the pass is radiance only and held to 2e-5 of its term.
+    const P2 um = fma2(st, pk2((float)W, (float)H), bc2(-0.5f));
+    const float ux = lo2(um), uy = hi2(um);
+#else
     const P2 m = mul2(st, pk2((float)W, (float)H));
     const float ux = lo2(m) - 0.5f, uy = hi2(m) - 0.5f;  // scalar: mul2 -> sub2 would be contracted (mt_math.cuh)
+#endif
     // No clamp: the march runs from the pixel centre towards the sun position, which main() clamps to [0,1]
     // (postProcess_GodRays.frag:90), so u*W - 0.5 lies in [-0.5, W - 0.5] and floor() in [-1, W-1] -- the ring.  The 100
     // roundings of `uv -= delta` move u*W by < 0.05 texel even at W = 7680, against a margin of 0.5.
