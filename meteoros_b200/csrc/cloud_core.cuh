@@ -273,13 +273,20 @@ MT_DEVICE float erosion_edge(const Tex2D& curl, const Tex3D& high, f3 p, float h
 // Radiance only (no decision reads it): the three remaps divide by constants (1 - 0.7, 0.85 - 0.3, 0.34 - 0.07), written as
 // multiplications by the reciprocal -- one instruction instead of the ~9 of an IEEE division, one ulp apart at most.
 MT_DEVICE float remap_rcp(float v, float omin, float rcpRange, float nmin, float nmax) { return nmin + (((v - omin) * rcpRange) * (nmax - nmin)); }
-MT_DEVICE float light_energy(float h, float dl, float ds, float phase, float cosa)
+// The ray's share of it: att * p * phase * 5 with att = max(remap(cosa, .7, 1, p, p * .25), p) = p * max(1 - .75 (cosa - .7) / .3, 1)
+// (p > 0), so everything that depends on the ray alone -- the attenuation's angle factor, the phase function, the constant 5 -- is ONE
+// per-ray factor (evaluated once per ray, parked beside the cone offsets) and a step's energy is scale * p^2 * depth * vert: eight
+// instructions and one shared-memory load fewer per in-cloud step, the same real number (radiance only: equal to rounding).
+MT_DEVICE float light_scale(float phase, float cosa)
+{
+    return (fmaxf(1.0f - 0.75f * ((cosa - 0.7f) * (1.0f / (1.0f - 0.7f))), 1.0f) * phase) * 5.0f;
+}
+MT_DEVICE float light_energy(float h, float dl, float ds, float scale)
 {
     float p = MT_EXPF(-dl);
-    float att = fmaxf(remap_rcp(cosa, 0.7f, 1.0f / (1.0f - 0.7f), p, p * 0.25f), p);
     float depth = 0.05f + MT_POWF(ds, clamp1(remap_rcp(h * 0.125f, 0.3f, 1.0f / (0.85f - 0.3f), 0.5f, 2.0f), 0.5f, 2.0f));
     float vert = MT_POWF(clamp1(remap_rcp(h * 1.5f, 0.07f, 1.0f / (0.34f - 0.07f), 0.1f, 1.0f), 0.1f, 1.0f), 0.8f);
-    return (((att * p) * (depth * vert)) * phase) * 5.0f;
+    return ((p * p) * (depth * vert)) * scale;
 }
 
 MT_DEVICE void encode_mask(float v, F4& o)
@@ -296,7 +303,7 @@ MT_DEVICE void encode_mask(float v, F4& o)
 struct RaySetup {
     f3 dir;
     float t_in, t_out, stepSize;
-    float lenToInner, cosAngle, phase;
+    float lenToInner, cosAngle, phase;  // phase: light_scale(HGModified, cosAngle), the per-ray factor of GetLightEnergy
     f3 bg;           // Preetham sky * max(.62, dir.y)
     int branch;      // 0 ocean, 1 sky band, 2 march
     int nsteps;      // step-parallel path only: iterations of the march loop (cloud_rays_kernel fills it in)
@@ -377,7 +384,8 @@ MT_DEVICE RaySetup cloud_ray_setup(const CloudParams& P, const MarchConst& M, co
     R.t_out = hout.t;
     R.stepSize = (hout.t - hin.t) / maxSteps;
     R.cosAngle = dot3(norm3(dir), M.lightDir);
-    R.phase = fmaxf(hg_phase(R.cosAngle, 0.6f), 0.7f * hg_phase(R.cosAngle, 0.99f - 0.1f));
+    // the ray's light-energy scale (light_scale): the phase function times the attenuation's angle factor times 5
+    R.phase = light_scale(fmaxf(hg_phase(R.cosAngle, 0.6f), 0.7f * hg_phase(R.cosAngle, 0.99f - 0.1f)), R.cosAngle);
     R.lenToInner = len3(hin.point - origin);
     return R;
 }
@@ -619,7 +627,7 @@ MT_DEVICE StepSample cloud_step_light(const CloudParams& P, const MarchConst& M,
             }
         }
         const bool parkedH = MT_PARK_BG && CO.xyz;
-        S.energy = light_energy(h, dl, baseDensity, parkedH ? CO.xyz[3 * CO.stride].w : R.phase, parkedH ? CO.xyz[4 * CO.stride].w : R.cosAngle);
+        S.energy = light_energy(h, dl, baseDensity, parkedH ? CO.xyz[3 * CO.stride].w : R.phase);
         return S;
     }
 #endif
@@ -670,8 +678,7 @@ MT_DEVICE StepSample cloud_step_light(const CloudParams& P, const MarchConst& M,
             }
             X = Xn; Y = Yn; Z = Zn; cell = celln; cur = nxt;
         }
-        S.energy = light_energy(h, dl, baseDensity, (MT_PARK_BG && CO.xyz) ? CO.xyz[3 * CO.stride].w : R.phase,
-                                (MT_PARK_BG && CO.xyz) ? CO.xyz[4 * CO.stride].w : R.cosAngle);
+        S.energy = light_energy(h, dl, baseDensity, (MT_PARK_BG && CO.xyz) ? CO.xyz[3 * CO.stride].w : R.phase);
         return S;
     }
 #endif
@@ -728,7 +735,7 @@ MT_DEVICE StepSample cloud_step_light(const CloudParams& P, const MarchConst& M,
         }
     }
     const bool parked = MT_PARK_BG && CO.xyz;
-    S.energy = light_energy(h, dl, baseDensity, parked ? CO.xyz[3 * CO.stride].w : R.phase, parked ? CO.xyz[4 * CO.stride].w : R.cosAngle);
+    S.energy = light_energy(h, dl, baseDensity, parked ? CO.xyz[3 * CO.stride].w : R.phase);
     return S;
 }
 
