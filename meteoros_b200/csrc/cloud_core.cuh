@@ -283,10 +283,13 @@ MT_DEVICE float light_scale(float phase, float cosa)
 }
 MT_DEVICE float light_energy(float h, float dl, float ds, float scale)
 {
-    float p = MT_EXPF(-dl);
-    float depth = 0.05f + MT_POWF(ds, clamp1(remap_rcp(h * 0.125f, 0.3f, 1.0f / (0.85f - 0.3f), 0.5f, 2.0f), 0.5f, 2.0f));
-    float vert = MT_POWF(clamp1(remap_rcp(h * 1.5f, 0.07f, 1.0f / (0.34f - 0.07f), 0.1f, 1.0f), 0.1f, 1.0f), 0.8f);
-    return ((p * p) * (depth * vert)) * scale;
+    // p^2 = exp(-2 dl) in one ex2; the two remaps are affine in h: one multiply-add each (the same real numbers, radiance only)
+    const float kd = (0.125f * (1.0f / (0.85f - 0.3f))) * (2.0f - 0.5f), cd = 0.5f - (0.3f * (1.0f / (0.85f - 0.3f))) * (2.0f - 0.5f);
+    const float kv = (1.5f * (1.0f / (0.34f - 0.07f))) * (1.0f - 0.1f), cv = 0.1f - (0.07f * (1.0f / (0.34f - 0.07f))) * (1.0f - 0.1f);
+    float pp = MT_EXP_NEG2(dl);
+    float depth = 0.05f + MT_POWF(ds, clamp1(fmaf(h, kd, cd), 0.5f, 2.0f));
+    float vert = MT_POWF(clamp1(fmaf(h, kv, cv), 0.1f, 1.0f), 0.8f);
+    return (pp * (depth * vert)) * scale;
 }
 
 MT_DEVICE void encode_mask(float v, F4& o)
