@@ -234,7 +234,7 @@ MT_DEVICE float cone_term_rf(const CloudParams& P, const MarchConst& M, float co
     const float fbm = sat1(hi2(rf));
     const float omin = fbm - 0.9f;
     const float d = 1.0f - omin, q = lo2(rf) - omin;
-    const float diff = q - coverage * d;
+    const float diff = fmaf(-coverage, d, q);
     if (fabsf(diff) <= MT_RF_GUARD * d) {  // too close to call: the canonical evaluation, values included
         const float dens = cone_density_rf<STD>(P, M, covRcp, coverage, rf, X, Y, Z, cell);
         hit = dens > 0.0f;
@@ -251,7 +251,7 @@ MT_DEVICE float cone_term_rf(const CloudParams& P, const MarchConst& M, float co
 #endif
     const float dens = (base - coverage) * M.covScale;
     hit = dens > 0.0f;  // coverage == 0 scales every density to 0: no hit, as in the shader
-    return hit ? (1.5f * dens - edge) * edgeRcp : 0.0f;
+    return hit ? fmaf(1.5f, dens, -edge) * edgeRcp : 0.0f;
 }
 
 // The part of erodeCloudWithHighFrequency (cloudRayMarch.comp:542-563) that depends only on the march sample:
@@ -768,7 +768,8 @@ MT_DEVICE bool cloud_step_combine(const StepSample& S, float& accum, float& tran
 {
     if (S.energy >= 0.0f) {
         accum += S.inc;
-        transmittance = mix1(transmittance, S.energy, 1.0f - accum);
+        // mix(transmittance, energy, 1 - accum) in its lerp form, a + t (b - a): radiance only (accum, which decides, is untouched)
+        transmittance = fmaf(1.0f - accum, S.energy - transmittance, transmittance);
         color += transmittance;
     }
     if (accum >= 1.0f) {
